@@ -1,0 +1,213 @@
+"""Host-side engine handles: one ``libadvb200`` handle per (model instance, device, clip length).
+
+Everything numerical happens behind the C ABI; torch is used for device memory, the current CUDA stream and the
+random-start noise only (parity needs torch's RNG).
+"""
+import ctypes as C
+import weakref
+
+import torch
+from torch import nn
+
+from . import _lib
+
+_MODEL_KINDS = {"LCNN": _lib.MODEL_LCNN, "SpecRNet": _lib.MODEL_SPECRNET, "RawNet3": _lib.MODEL_RAWNET3}
+_ENGINES = weakref.WeakKeyDictionary()  # module -> {(device index, T): Engine}
+
+
+def unwrap(model: nn.Module) -> nn.Module:
+    """The reference hands the attack an ``nn.DataParallel`` (evaluate_models_on_adversarial_attacks.py:163-169)."""
+    return model.module if isinstance(model, nn.DataParallel) else model
+
+
+def _frontend_kind(state) -> int:
+    if "frontend.filter_mat" in state:
+        return _lib.FRONTEND_LFCC
+    if "frontend.MelSpectrogram.mel_scale.fb" in state:
+        return _lib.FRONTEND_MFCC
+    return _lib.FRONTEND_NONE
+
+
+def _require_cuda(t: torch.Tensor, what: str):
+    if not t.is_cuda:
+        raise RuntimeError(f"advb200 has no CPU path: {what} is on {t.device}; move the model and batch to a CUDA device")
+
+
+class Engine:
+    def __init__(self, module: nn.Module, max_batch: int, n_samples: int):
+        self.lib = _lib.load()
+        kind = _MODEL_KINDS.get(type(module).__name__)
+        if kind is None:
+            raise NotImplementedError(f"advb200 engine does not support model class {type(module).__name__}")
+        self.module_ref = weakref.ref(module)
+        self.max_batch, self.n_samples = int(max_batch), int(n_samples)
+        refs, self._ptrs = self._tensor_table(module)
+        first = next(module.parameters())
+        _require_cuda(first, "the model")
+        self.device = first.device
+        desc = _lib.ModelDesc(kind, _frontend_kind(self._state), self.device.index or 0, self.max_batch, self.n_samples,
+                              len(refs), refs)
+        handle = C.c_void_p()
+        with torch.cuda.device(self.device):
+            _lib.check(self.lib.advb_create(C.byref(handle), C.byref(desc)))
+        self.handle = handle
+        self._finalizer = weakref.finalize(self, self.lib.advb_destroy, handle)
+
+    def _tensor_table(self, module):
+        state = {k: v for k, v in module.state_dict(keep_vars=True).items() if v.dtype == torch.float32}
+        for k, v in state.items():
+            _require_cuda(v, f"tensor '{k}'")
+            if not v.is_contiguous():
+                raise RuntimeError(f"tensor '{k}' is not contiguous")
+        self._state = state  # keeps the storages alive while the handle borrows them
+        self._names = [k.encode() for k in state]
+        refs = (_lib.TensorRef * len(state))()
+        for i, (k, v) in enumerate(state.items()):
+            refs[i] = _lib.TensorRef(self._names[i], v.data_ptr(), v.numel())
+        return refs, tuple(v.data_ptr() for v in state.values())
+
+    def _sync_weights(self):
+        """Weights are read live; only if a storage was *replaced* (load_state_dict keeps storages) re-point."""
+        module = self.module_ref()
+        if module is None:
+            raise RuntimeError("model was garbage-collected")
+        ptrs = tuple(v.data_ptr() for v in module.state_dict(keep_vars=True).values() if v.dtype == torch.float32)
+        if ptrs != self._ptrs:
+            refs, self._ptrs = self._tensor_table(module)
+            _lib.check(self.lib.advb_rebind(self.handle, len(refs), refs))
+
+    def _stream(self):
+        return C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+
+    def _check_x(self, x):
+        _require_cuda(x, "the batch")
+        if x.dtype != torch.float32 or x.dim() != 2:
+            raise ValueError("expected a float32 waveform batch of shape (B, T)")
+        if x.shape[1] != self.n_samples or x.shape[0] > self.max_batch:
+            raise ValueError("batch does not fit this engine handle")
+        return x.contiguous()
+
+    def attack(self, desc: "_lib.AttackDesc", x, y, start=None):
+        x = self._check_x(x)
+        y = y.to(device=x.device, dtype=torch.int64).contiguous()
+        self._sync_weights()
+        out = torch.empty_like(x)
+        sp = C.c_void_p(start.contiguous().data_ptr()) if start is not None else None
+        with torch.cuda.device(self.device):
+            _lib.check(self.lib.advb_attack(self.handle, C.byref(desc), x.data_ptr(), y.data_ptr(), sp, out.data_ptr(),
+                                            x.shape[0], x.shape[1], self._stream()))
+        return out
+
+    def forward(self, x):
+        x = self._check_x(x)
+        self._sync_weights()
+        out = torch.empty(x.shape[0], 1, device=x.device, dtype=torch.float32)
+        with torch.cuda.device(self.device):
+            _lib.check(self.lib.advb_forward(self.handle, x.data_ptr(), out.data_ptr(), x.shape[0], x.shape[1],
+                                             self._stream()))
+        return out
+
+    def grad(self, x, y=None, what=_lib.GRAD_CE, n_global=0):
+        x = self._check_x(x)
+        self._sync_weights()
+        g = torch.empty_like(x)
+        logits = torch.empty(x.shape[0], 1, device=x.device, dtype=torch.float32)
+        yp = None
+        if y is not None:
+            y = y.to(device=x.device, dtype=torch.int64).contiguous()
+            yp = C.c_void_p(y.data_ptr())
+        with torch.cuda.device(self.device):
+            _lib.check(self.lib.advb_grad(self.handle, what, x.data_ptr(), yp, g.data_ptr(), logits.data_ptr(),
+                                          x.shape[0], x.shape[1], n_global, self._stream()))
+        return g, logits
+
+    def frontend_fwd(self, x):
+        x = self._check_x(x)
+        F = 1 + x.shape[1] // 160
+        out = torch.empty(x.shape[0], 80, F, device=x.device, dtype=torch.float32)
+        with torch.cuda.device(self.device):
+            _lib.check(self.lib.advb_frontend_fwd(self.handle, x.data_ptr(), out.data_ptr(), x.shape[0], x.shape[1],
+                                                  self._stream()))
+        return out
+
+    def frontend_bwd(self, x, g_coeff):
+        x = self._check_x(x)
+        g_coeff = g_coeff.contiguous()
+        gx = torch.empty_like(x)
+        with torch.cuda.device(self.device):
+            _lib.check(self.lib.advb_frontend_bwd(self.handle, x.data_ptr(), g_coeff.data_ptr(), gx.data_ptr(),
+                                                  x.shape[0], x.shape[1], self._stream()))
+        return gx
+
+    def debug_stage(self, name: str):
+        """(tensor (B, H+2p, W+2p, C) raw engine layout, pad p) of an internal stage of the last forward."""
+        dims = (C.c_int64 * 5)()
+        n = self.lib.advb_debug_stage(self.handle, name.encode(), None, 0, dims, self._stream())
+        if n < 0:
+            _lib.check(1)
+        buf = torch.empty(n, device=self.device, dtype=torch.float32)
+        n = self.lib.advb_debug_stage(self.handle, name.encode(), buf.data_ptr(), n, dims, self._stream())
+        if n < 0:
+            _lib.check(1)
+        B, H, W, Cc, p = [int(v) for v in dims]
+        return buf.view(B, H + 2 * p, W + 2 * p, Cc), p
+
+    @property
+    def launches(self) -> int:
+        return int(self.lib.advb_launch_count(self.handle))
+
+    @property
+    def workspace_bytes(self) -> int:
+        return int(self.lib.advb_workspace_bytes(self.handle))
+
+
+def engine_for(model: nn.Module, batch: int, n_samples: int) -> Engine:
+    module = unwrap(model)
+    first = next(module.parameters())
+    _require_cuda(first, "the model")
+    per_module = _ENGINES.setdefault(module, {})
+    key = (first.device.index or 0, int(n_samples))
+    eng = per_module.get(key)
+    if eng is None or eng.max_batch < batch:
+        if eng is not None:
+            eng._finalizer()
+        eng = Engine(module, max(batch, eng.max_batch if eng else 0), n_samples)
+        per_module[key] = eng
+    return eng
+
+
+def model_forward(module: nn.Module, x: torch.Tensor) -> torch.Tensor:
+    """``model(x)`` of an advb200 model holder: logits (B,1), computed by the CUDA engine."""
+    _require_cuda(x, "the batch")
+    return engine_for(module, x.shape[0], x.shape[1]).forward(x)
+
+
+def frontend_forward(frontend: nn.Module, x: torch.Tensor) -> torch.Tensor:
+    raise NotImplementedError("call the frontend through a model handle: engine_for(model, B, T).frontend_fwd(x)")
+
+
+def to_minmax(x: torch.Tensor):
+    """src/aa/utils.py:4-9 on the GPU: returns (x01, mn (B,1), mx (B,1))."""
+    _require_cuda(x, "the batch")
+    lib = _lib.load()
+    x = x.contiguous()
+    out = torch.empty_like(x)
+    mn = torch.empty(x.shape[0], 1, device=x.device, dtype=torch.float32)
+    mx = torch.empty_like(mn)
+    with torch.cuda.device(x.device):
+        _lib.check(lib.advb_minmax(x.data_ptr(), out.data_ptr(), mn.data_ptr(), mx.data_ptr(), x.shape[0], x.shape[1],
+                                   C.c_void_p(torch.cuda.current_stream(x.device).cuda_stream)))
+    return out, mn, mx
+
+
+def revert_minmax(x01: torch.Tensor, mn: torch.Tensor, mx: torch.Tensor):
+    """src/aa/utils.py:12-14 on the GPU."""
+    _require_cuda(x01, "the batch")
+    lib = _lib.load()
+    x01 = x01.contiguous()
+    out = torch.empty_like(x01)
+    with torch.cuda.device(x01.device):
+        _lib.check(lib.advb_revert_minmax(x01.data_ptr(), mn.contiguous().data_ptr(), mx.contiguous().data_ptr(),
+                                          out.data_ptr(), x01.shape[0], x01.shape[1],
+                                          C.c_void_p(torch.cuda.current_stream(x01.device).cuda_stream)))
+    return out

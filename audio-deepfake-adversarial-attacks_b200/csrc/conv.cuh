@@ -1,0 +1,43 @@
+// LCNN conv-block host entry points — see conv.cu.
+#pragma once
+#include "common.cuh"
+
+namespace advb {
+
+struct ConvFwdArgs {
+  const float* in;   // (B, H+2*in_pad, W+2*in_pad, Cin) zero-bordered NHWC
+  int in_pad;
+  const float* wf;   // packed [tap][ci][co]
+  const float* bias; // (Cout)
+  const float* bn_mean;    // (Cout/2) or null
+  const float* bn_invstd;  // (Cout/2) or null
+  float* out;        // (B, Ho+2*out_pad, Wo+2*out_pad, Cout/2)
+  int out_pad;
+  unsigned char* codes;  // (B, Ho, Wo, Cout/2): pool arg-max position (bits 0-1) | MFM half (bit 2)
+  int B, H, W, Cin, Cout, KS;
+  int Ho, Wo;
+  bool pool;
+  int band_floats;  // filled by the launcher
+};
+
+struct ConvBwdArgs {
+  const float* gout;           // (B, Ho, Wo, Cout/2) compact gradient of the block output
+  const unsigned char* codes;  // as written by the forward
+  const float* bn_invstd;      // (Cout/2) or null
+  const float* wd;             // packed [flipped tap][co][ci]
+  float* gin;                  // (B, H, W, Cin) compact gradient of the block input
+  int B, H, W, Cin, Cout, KS;
+  int Ho, Wo;
+  bool pool;
+  int band_floats;
+};
+
+int conv_pack_weights(const float* w, float* wf, float* wd, int Cout, int Cin, int KS, cudaStream_t stream);
+int bn_prepare(const float* var, float* invstd, int C, cudaStream_t stream);
+int conv_mfm_forward(ConvFwdArgs a, cudaStream_t stream);
+int conv_mfm_backward(ConvBwdArgs a, cudaStream_t stream);
+// first block (Cin = 1, 5x5, pool, no BN): w0 is the original (64,1,5,5) weight
+int conv0_backward(const float* gout, const unsigned char* codes, const float* w0, float* gin, int B, int H, int W,
+                   int Ho, int Wo, cudaStream_t stream);
+
+}  // namespace advb

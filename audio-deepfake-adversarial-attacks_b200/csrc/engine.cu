@@ -1,0 +1,609 @@
+// libadvb200: handle, workspace, LCNN execution plan and the C ABI of include/advb200.h.
+//
+// One handle = one (model instance, device).  The workspace is allocated once for (max_batch, n_samples); every
+// API call re-reads the borrowed weight tensors (repack kernels at the head of the call), enqueues the whole
+// attack on the caller's stream and returns without synchronising.
+#include <cuda_runtime.h>
+
+#include <map>
+#include <string>
+#include <vector>
+
+#include "../../include/advb200.h"
+#include "common.cuh"
+#include "conv.cuh"
+#include "frontend.cuh"
+#include "rnn.cuh"
+#include "update.cuh"
+
+namespace advb {
+
+static thread_local std::string g_error;
+thread_local LaunchCounter* g_counter = nullptr;
+void set_error(const std::string& msg) { g_error = msg; }
+
+struct TensorRef {
+  const float* p;
+  int64_t n;
+};
+
+struct LcnnBlock {
+  int idx, Cin, Cout, KS, bn_idx;
+  bool pool;
+  int H, W, Ho, Wo;    // conv (pre-pool) size, block output size
+  float* wf = nullptr;  // packed forward weights
+  float* wd = nullptr;  // packed backward weights
+  float* invstd = nullptr;
+  Act out{};             // block output (zero-bordered for the next conv)
+  unsigned char* codes = nullptr;
+  float* gout = nullptr;  // compact gradient of the block output
+};
+
+}  // namespace advb
+
+using namespace advb;
+
+struct advb_handle {
+  int device = 0, model_kind = 0, frontend_kind = 0, Bmax = 0, T = 0, F = 0;
+  std::map<std::string, TensorRef> tensors;
+  LaunchCounter counter;
+  std::vector<void*> allocs;
+  size_t ws_bytes = 0;
+
+  // frontend
+  float *twr = nullptr, *twi = nullptr, *dB = nullptr, *mass_partial = nullptr, *g_coef = nullptr;
+  int *klo = nullptr, *kcnt = nullptr, *mlo = nullptr, *mcnt = nullptr;
+  FrontendState fst{};
+  FrontendTables ftb{};
+
+  // LCNN
+  Act act0{};
+  LcnnBlock blk[9];
+  int L = 0, Wf = 0;
+  float *feats = nullptr, *l1 = nullptr, *l2 = nullptr, *gates1 = nullptr, *gates2 = nullptr, *cs1 = nullptr,
+        *cs2 = nullptr, *dl2 = nullptr, *dl1 = nullptr, *dfeats = nullptr, *logits = nullptr;
+  LstmPacked lp[2]{};
+
+  // attack scratch
+  float *grad = nullptr, *partial_g = nullptr, *partial_d = nullptr, *coef_tmp = nullptr;
+
+  template <typename Tp>
+  int alloc(Tp** out, size_t count) {
+    void* p = nullptr;
+    size_t bytes = count * sizeof(Tp);
+    if (bytes == 0) bytes = 16;
+    ADVB_CUDA_OK(cudaMalloc(&p, bytes));
+    ADVB_CUDA_OK(cudaMemset(p, 0, bytes));
+    allocs.push_back(p);
+    ws_bytes += bytes;
+    *out = reinterpret_cast<Tp*>(p);
+    return 0;
+  }
+  const float* t(const std::string& name) const {
+    auto it = tensors.find(name);
+    return it == tensors.end() ? nullptr : it->second.p;
+  }
+};
+
+namespace {
+
+struct DeviceGuard {
+  int prev = -1;
+  explicit DeviceGuard(int dev) {
+    cudaGetDevice(&prev);
+    if (prev != dev) cudaSetDevice(dev);
+    else prev = -1;
+  }
+  ~DeviceGuard() {
+    if (prev >= 0) cudaSetDevice(prev);
+  }
+};
+
+const int kLcnnSpec[9][6] = {
+    // idx, Cin, Cout, KS, pool, bn_idx   (src/models/lcnn.py:121-153)
+    {0, 1, 64, 5, 1, -1},  {3, 32, 64, 1, 0, 5},    {6, 32, 96, 3, 1, 9},   {10, 48, 96, 1, 0, 12}, {13, 48, 128, 3, 1, -1},
+    {16, 64, 128, 1, 0, 18}, {19, 64, 64, 3, 0, 21}, {22, 32, 64, 1, 0, 24}, {25, 32, 64, 3, 1, -1},
+};
+
+int bind_tensors(advb_handle* h, int n, const advb_tensor_ref* refs) {
+  for (int i = 0; i < n; ++i) {
+    ADVB_CHECK(refs[i].name != nullptr && refs[i].ptr != nullptr, "null tensor reference");
+    h->tensors[refs[i].name] = TensorRef{refs[i].ptr, refs[i].numel};
+  }
+  return 0;
+}
+
+int require(const advb_handle* h, const std::string& name, int64_t numel) {
+  auto it = h->tensors.find(name);
+  if (it == h->tensors.end()) {
+    set_error("missing tensor '" + name + "'");
+    return 1;
+  }
+  if (it->second.n != numel) {
+    set_error("tensor '" + name + "' has " + std::to_string(it->second.n) + " elements, expected " +
+              std::to_string(numel));
+    return 1;
+  }
+  return 0;
+}
+
+int check_frontend_tensors(advb_handle* h) {
+  if (h->frontend_kind == ADVB_FRONTEND_LFCC) {
+    ADVB_TRY(require(h, "frontend.filter_mat", 257 * 128));
+    ADVB_TRY(require(h, "frontend.dct_mat", 128 * 80));
+    ADVB_TRY(require(h, "frontend.Spectrogram.window", 400));
+  } else if (h->frontend_kind == ADVB_FRONTEND_MFCC) {
+    ADVB_TRY(require(h, "frontend.MelSpectrogram.mel_scale.fb", 257 * 128));
+    ADVB_TRY(require(h, "frontend.dct_mat", 128 * 80));
+    ADVB_TRY(require(h, "frontend.MelSpectrogram.spectrogram.window", 400));
+  } else {
+    set_error("model needs an LFCC or MFCC frontend");
+    return 1;
+  }
+  return 0;
+}
+
+void refresh_frontend_tables(advb_handle* h) {
+  FrontendTables& tb = h->ftb;
+  if (h->frontend_kind == ADVB_FRONTEND_LFCC) {
+    tb.fb = h->t("frontend.filter_mat");
+    tb.window = h->t("frontend.Spectrogram.window");
+  } else {
+    tb.fb = h->t("frontend.MelSpectrogram.mel_scale.fb");
+    tb.window = h->t("frontend.MelSpectrogram.spectrogram.window");
+  }
+  tb.dct = h->t("frontend.dct_mat");
+  tb.twr = h->twr;
+  tb.twi = h->twi;
+  tb.klo = h->klo;
+  tb.kcnt = h->kcnt;
+  tb.mlo = h->mlo;
+  tb.mcnt = h->mcnt;
+}
+
+int check_lcnn_tensors(advb_handle* h) {
+  for (int i = 0; i < 9; ++i) {
+    const int* s = kLcnnSpec[i];
+    const std::string p = "m_transform." + std::to_string(s[0]);
+    ADVB_TRY(require(h, p + ".weight", (int64_t)s[2] * s[1] * s[3] * s[3]));
+    ADVB_TRY(require(h, p + ".bias", s[2]));
+    if (s[5] >= 0) {
+      const std::string q = "m_transform." + std::to_string(s[5]);
+      ADVB_TRY(require(h, q + ".running_mean", s[2] / 2));
+      ADVB_TRY(require(h, q + ".running_var", s[2] / 2));
+    }
+  }
+  for (int l = 0; l < 2; ++l)
+    for (int d = 0; d < 2; ++d) {
+      const std::string p = "m_before_pooling." + std::to_string(l) + ".l_blstm.";
+      const std::string sfx = d == 0 ? "_l0" : "_l0_reverse";
+      ADVB_TRY(require(h, p + "weight_ih" + sfx, 320 * 160));
+      ADVB_TRY(require(h, p + "weight_hh" + sfx, 320 * 80));
+      ADVB_TRY(require(h, p + "bias_ih" + sfx, 320));
+      ADVB_TRY(require(h, p + "bias_hh" + sfx, 320));
+    }
+  ADVB_TRY(require(h, "m_output_act.weight", 160));
+  ADVB_TRY(require(h, "m_output_act.bias", 1));
+  return 0;
+}
+
+int build_lcnn(advb_handle* h) {
+  const int B = h->Bmax, F = h->F;
+  ADVB_TRY(check_lcnn_tensors(h));
+  // cepstral image (B, F, 80, 1) with the 2-pixel border of the 5x5 conv
+  h->act0 = Act{nullptr, F, 80, 1, 2};
+  ADVB_TRY(h->alloc(&h->act0.p, (size_t)B * h->act0.per_clip()));
+  int H = F, W = 80;
+  for (int i = 0; i < 9; ++i) {
+    LcnnBlock& k = h->blk[i];
+    const int* s = kLcnnSpec[i];
+    k.idx = s[0];
+    k.Cin = s[1];
+    k.Cout = s[2];
+    k.KS = s[3];
+    k.pool = s[4] != 0;
+    k.bn_idx = s[5];
+    k.H = H;
+    k.W = W;
+    k.Ho = k.pool ? H / 2 : H;
+    k.Wo = k.pool ? W / 2 : W;
+    ADVB_CHECK(k.Ho > 0 && k.Wo > 0, "clip too short for the LCNN pooling stack");
+    const int next_pad = i < 8 ? kLcnnSpec[i + 1][3] / 2 : 0;
+    k.out = Act{nullptr, k.Ho, k.Wo, k.Cout / 2, next_pad};
+    ADVB_TRY(h->alloc(&k.out.p, (size_t)B * k.out.per_clip()));
+    ADVB_TRY(h->alloc(&k.codes, (size_t)B * k.Ho * k.Wo * (k.Cout / 2)));
+    ADVB_TRY(h->alloc(&k.gout, (size_t)B * k.Ho * k.Wo * (k.Cout / 2)));
+    const size_t wn = (size_t)k.Cout * k.Cin * k.KS * k.KS;
+    ADVB_TRY(h->alloc(&k.wf, wn));
+    if (i > 0) ADVB_TRY(h->alloc(&k.wd, wn));
+    if (k.bn_idx >= 0) ADVB_TRY(h->alloc(&k.invstd, k.Cout / 2));
+    H = k.Ho;
+    W = k.Wo;
+  }
+  h->L = H;
+  h->Wf = W;
+  ADVB_CHECK(h->Wf * 32 == 160, "LCNN feature width must be 160");
+  const size_t bl = (size_t)B * h->L;
+  ADVB_TRY(h->alloc(&h->feats, bl * 160));
+  ADVB_TRY(h->alloc(&h->l1, bl * 160));
+  ADVB_TRY(h->alloc(&h->l2, bl * 160));
+  ADVB_TRY(h->alloc(&h->gates1, bl * 640));
+  ADVB_TRY(h->alloc(&h->gates2, bl * 640));
+  ADVB_TRY(h->alloc(&h->cs1, bl * 160));
+  ADVB_TRY(h->alloc(&h->cs2, bl * 160));
+  ADVB_TRY(h->alloc(&h->dl2, bl * 160));
+  ADVB_TRY(h->alloc(&h->dl1, bl * 160));
+  ADVB_TRY(h->alloc(&h->dfeats, bl * 160));
+  for (int l = 0; l < 2; ++l) {
+    ADVB_TRY(h->alloc(&h->lp[l].wihT, 160 * 640));
+    ADVB_TRY(h->alloc(&h->lp[l].bias, 640));
+    ADVB_TRY(h->alloc(&h->lp[l].whhT, 2 * 80 * 320));
+    ADVB_TRY(h->alloc(&h->lp[l].wih_cat, 640 * 160));
+    ADVB_TRY(h->alloc(&h->lp[l].whh, 2 * 320 * 80));
+  }
+  ADVB_TRY(rnn_init());
+  return 0;
+}
+
+// Re-read the live weights: repack convolution / LSTM weights, BatchNorm inverse std, filterbank extents.
+int prepare_lcnn(advb_handle* h, cudaStream_t st) {
+  refresh_frontend_tables(h);
+  ADVB_TRY(frontend_prepare(h->ftb, st));
+  for (int i = 0; i < 9; ++i) {
+    LcnnBlock& k = h->blk[i];
+    const std::string p = "m_transform." + std::to_string(k.idx);
+    ADVB_TRY(conv_pack_weights(h->t(p + ".weight"), k.wf, k.wd, k.Cout, k.Cin, k.KS, st));
+    if (k.bn_idx >= 0)
+      ADVB_TRY(bn_prepare(h->t("m_transform." + std::to_string(k.bn_idx) + ".running_var"), k.invstd, k.Cout / 2, st));
+  }
+  for (int l = 0; l < 2; ++l) {
+    const std::string p = "m_before_pooling." + std::to_string(l) + ".l_blstm.";
+    LstmWeights w;
+    for (int d = 0; d < 2; ++d) {
+      const std::string sfx = d == 0 ? "_l0" : "_l0_reverse";
+      w.w_ih[d] = h->t(p + "weight_ih" + sfx);
+      w.w_hh[d] = h->t(p + "weight_hh" + sfx);
+      w.b_ih[d] = h->t(p + "bias_ih" + sfx);
+      w.b_hh[d] = h->t(p + "bias_hh" + sfx);
+    }
+    ADVB_TRY(lstm_pack(w, h->lp[l], st));
+  }
+  return 0;
+}
+
+int lcnn_forward(advb_handle* h, const float* x, int B, cudaStream_t st) {
+  const Act& a0 = h->act0;
+  ADVB_TRY(frontend_forward(h->ftb, h->fst, x, B, h->T, h->dB, a0.p, (long long)a0.per_clip(), (long long)a0.Wp(), 1,
+                            (long long)a0.pad * a0.Wp() + a0.pad, st));
+  const float* in = a0.p;
+  int in_pad = a0.pad;
+  for (int i = 0; i < 9; ++i) {
+    LcnnBlock& k = h->blk[i];
+    ConvFwdArgs a{};
+    a.in = in;
+    a.in_pad = in_pad;
+    a.wf = k.wf;
+    a.bias = h->t("m_transform." + std::to_string(k.idx) + ".bias");
+    a.bn_mean = k.bn_idx >= 0 ? h->t("m_transform." + std::to_string(k.bn_idx) + ".running_mean") : nullptr;
+    a.bn_invstd = k.bn_idx >= 0 ? k.invstd : nullptr;
+    a.out = k.out.p;
+    a.out_pad = k.out.pad;
+    a.codes = k.codes;
+    a.B = B;
+    a.H = k.H;
+    a.W = k.W;
+    a.Cin = k.Cin;
+    a.Cout = k.Cout;
+    a.KS = k.KS;
+    a.Ho = k.Ho;
+    a.Wo = k.Wo;
+    a.pool = k.pool;
+    ADVB_TRY(conv_mfm_forward(a, st));
+    in = k.out.p;
+    in_pad = k.out.pad;
+  }
+  ADVB_TRY(feats_gather(h->blk[8].out.p, h->feats, B, h->L, h->Wf, 32, st));
+  ADVB_TRY(blstm_forward(h->lp[0], h->feats, h->gates1, h->l1, h->cs1, B, h->L, st));
+  ADVB_TRY(blstm_forward(h->lp[1], h->l1, h->gates2, h->l2, h->cs2, B, h->L, st));
+  ADVB_TRY(head_forward(h->l2, h->feats, h->t("m_output_act.weight"), h->t("m_output_act.bias"), h->logits, B, h->L,
+                        st));
+  return 0;
+}
+
+// Gradient of (mode 0) the mean 2-class CE or (mode 1) the logit, w.r.t. the waveform of the last forward.
+int lcnn_backward(advb_handle* h, const float* x, const int64_t* y, int B, int mode, int n_global, float* gx,
+                  cudaStream_t st) {
+  ADVB_TRY(head_backward(h->logits, reinterpret_cast<const long long*>(y), h->t("m_output_act.weight"), h->dl2, B,
+                         h->L, mode, n_global, st));
+  ADVB_TRY(blstm_backward(h->lp[1], h->gates2, h->dl2, h->cs2, nullptr, h->dl1, B, h->L, st));
+  ADVB_TRY(blstm_backward(h->lp[0], h->gates1, h->dl1, h->cs1, h->dl2, h->dfeats, B, h->L, st));
+  ADVB_TRY(feats_scatter(h->dfeats, h->blk[8].gout, B, h->L, h->Wf, 32, st));
+  for (int i = 8; i >= 1; --i) {
+    LcnnBlock& k = h->blk[i];
+    ConvBwdArgs a{};
+    a.gout = k.gout;
+    a.codes = k.codes;
+    a.bn_invstd = k.bn_idx >= 0 ? k.invstd : nullptr;
+    a.wd = k.wd;
+    a.gin = h->blk[i - 1].gout;
+    a.B = B;
+    a.H = k.H;
+    a.W = k.W;
+    a.Cin = k.Cin;
+    a.Cout = k.Cout;
+    a.KS = k.KS;
+    a.Ho = k.Ho;
+    a.Wo = k.Wo;
+    a.pool = k.pool;
+    ADVB_TRY(conv_mfm_backward(a, st));
+  }
+  const LcnnBlock& k0 = h->blk[0];
+  ADVB_TRY(conv0_backward(k0.gout, k0.codes, h->t("m_transform.0.weight"), h->g_coef, B, k0.H, k0.W, k0.Ho, k0.Wo, st));
+  ADVB_TRY(frontend_backward(h->ftb, h->fst, x, B, h->T, h->dB, h->g_coef, (long long)h->F * 80, 80, 1,
+                             h->mass_partial, gx, st));
+  return 0;
+}
+
+int model_prepare(advb_handle* h, cudaStream_t st) {
+  if (h->model_kind == ADVB_MODEL_LCNN) return prepare_lcnn(h, st);
+  set_error("model kind not implemented");
+  return 1;
+}
+int model_forward(advb_handle* h, const float* x, int B, cudaStream_t st) {
+  if (h->model_kind == ADVB_MODEL_LCNN) return lcnn_forward(h, x, B, st);
+  set_error("model kind not implemented");
+  return 1;
+}
+int model_backward(advb_handle* h, const float* x, const int64_t* y, int B, int mode, int n_global, float* gx,
+                   cudaStream_t st) {
+  if (h->model_kind == ADVB_MODEL_LCNN) return lcnn_backward(h, x, y, B, mode, n_global, gx, st);
+  set_error("model kind not implemented");
+  return 1;
+}
+
+int check_call(advb_handle* h, int B, int T) {
+  ADVB_CHECK(h != nullptr, "null handle");
+  ADVB_CHECK(B > 0 && B <= h->Bmax, "batch exceeds the handle's max_batch");
+  ADVB_CHECK(T == h->T, "clip length differs from the handle's n_samples");
+  return 0;
+}
+
+struct CallScope {
+  DeviceGuard guard;
+  explicit CallScope(advb_handle* h) : guard(h->device) { g_counter = &h->counter; }
+  ~CallScope() { g_counter = nullptr; }
+};
+
+}  // namespace
+
+extern "C" {
+
+int advb_version(void) { return ADVB_VERSION; }
+const char* advb_last_error(void) { return g_error.c_str(); }
+
+int advb_create(advb_handle** out, const advb_model_desc* d) {
+  ADVB_CHECK(out != nullptr && d != nullptr, "null argument");
+  *out = nullptr;
+  ADVB_CHECK(d->max_batch > 0 && d->n_samples >= 512, "bad max_batch / n_samples");
+  int ndev = 0;
+  ADVB_CUDA_OK(cudaGetDeviceCount(&ndev));
+  ADVB_CHECK(d->device >= 0 && d->device < ndev, "no such CUDA device (libadvb200 has no CPU path)");
+  advb_handle* h = new advb_handle();
+  h->device = d->device;
+  h->model_kind = d->model_kind;
+  h->frontend_kind = d->frontend_kind;
+  h->Bmax = d->max_batch;
+  h->T = d->n_samples;
+  h->F = frontend_frames(d->n_samples);
+  CallScope scope(h);
+  auto fail = [&]() {
+    advb_destroy(h);
+    return 1;
+  };
+  if (bind_tensors(h, d->n_tensors, d->tensors)) return fail();
+  if (h->model_kind != ADVB_MODEL_LCNN) {
+    set_error("model kind not implemented yet (LCNN only)");
+    return fail();
+  }
+  if (check_frontend_tensors(h)) return fail();
+  const size_t B = h->Bmax;
+  if (h->alloc(&h->twr, 256) || h->alloc(&h->twi, 256) || h->alloc(&h->klo, 128) || h->alloc(&h->kcnt, 128) ||
+      h->alloc(&h->mlo, 257) || h->alloc(&h->mcnt, 257) || h->alloc(&h->fst.gmax_packed, 1) ||
+      h->alloc(&h->fst.n_clamped, 1) || h->alloc(&h->fst.mass_total, 1) ||
+      h->alloc(&h->dB, B * h->F * 128) || h->alloc(&h->g_coef, B * h->F * 80) ||
+      h->alloc(&h->coef_tmp, B * h->F * 80) ||
+      h->alloc(&h->mass_partial, (size_t)frontend_mass_blocks(h->Bmax, h->T)) || h->alloc(&h->logits, B) ||
+      h->alloc(&h->grad, B * h->T) || h->alloc(&h->partial_g, B * ROW_CHUNKS) ||
+      h->alloc(&h->partial_d, B * ROW_CHUNKS))
+    return fail();
+  if (frontend_init_constants(h->twr, h->twi, 0)) return fail();
+  if (build_lcnn(h)) return fail();
+  if (cudaDeviceSynchronize() != cudaSuccess) {
+    set_error("device error during advb_create");
+    return fail();
+  }
+  *out = h;
+  return 0;
+}
+
+void advb_destroy(advb_handle* h) {
+  if (h == nullptr) return;
+  DeviceGuard guard(h->device);
+  for (void* p : h->allocs) cudaFree(p);
+  delete h;
+}
+
+size_t advb_workspace_bytes(const advb_handle* h) { return h ? h->ws_bytes : 0; }
+int64_t advb_launch_count(const advb_handle* h) { return h ? h->counter.n : 0; }
+
+int advb_rebind(advb_handle* h, int n_tensors, const advb_tensor_ref* tensors) {
+  ADVB_CHECK(h != nullptr, "null handle");
+  ADVB_TRY(bind_tensors(h, n_tensors, tensors));
+  ADVB_TRY(check_frontend_tensors(h));
+  if (h->model_kind == ADVB_MODEL_LCNN) ADVB_TRY(check_lcnn_tensors(h));
+  return 0;
+}
+
+int advb_forward(advb_handle* h, const float* x, float* logits, int B, int T, void* cuda_stream) {
+  ADVB_TRY(check_call(h, B, T));
+  CallScope scope(h);
+  cudaStream_t st = static_cast<cudaStream_t>(cuda_stream);
+  ADVB_TRY(model_prepare(h, st));
+  ADVB_TRY(model_forward(h, x, B, st));
+  ADVB_CUDA_OK(cudaMemcpyAsync(logits, h->logits, (size_t)B * sizeof(float), cudaMemcpyDeviceToDevice, st));
+  return 0;
+}
+
+int advb_grad(advb_handle* h, int what, const float* x, const int64_t* y, float* grad, float* logits, int B, int T,
+              int n_global_batch, void* cuda_stream) {
+  ADVB_TRY(check_call(h, B, T));
+  ADVB_CHECK(what == ADVB_GRAD_CE || what == ADVB_GRAD_LOGIT, "bad gradient kind");
+  ADVB_CHECK(what == ADVB_GRAD_LOGIT || y != nullptr, "labels required");
+  CallScope scope(h);
+  cudaStream_t st = static_cast<cudaStream_t>(cuda_stream);
+  ADVB_TRY(model_prepare(h, st));
+  ADVB_TRY(model_forward(h, x, B, st));
+  ADVB_TRY(model_backward(h, x, y, B, what, n_global_batch > 0 ? n_global_batch : B, grad, st));
+  if (logits != nullptr)
+    ADVB_CUDA_OK(cudaMemcpyAsync(logits, h->logits, (size_t)B * sizeof(float), cudaMemcpyDeviceToDevice, st));
+  return 0;
+}
+
+int advb_attack(advb_handle* h, const advb_attack_desc* atk, const float* x, const int64_t* y, const float* start,
+                float* x_adv, int B, int T, void* cuda_stream) {
+  ADVB_TRY(check_call(h, B, T));
+  ADVB_CHECK(atk != nullptr && x != nullptr && y != nullptr && x_adv != nullptr, "null argument");
+  ADVB_CHECK(x != x_adv, "x_adv must not alias x");
+  CallScope scope(h);
+  cudaStream_t st = static_cast<cudaStream_t>(cuda_stream);
+  const int n_global = atk->n_global_batch > 0 ? atk->n_global_batch : B;
+  const int64_t n = (int64_t)B * T;
+  ADVB_TRY(model_prepare(h, st));
+  switch (atk->kind) {
+    case ADVB_ATTACK_FGSM: {
+      ADVB_TRY(model_forward(h, x, B, st));
+      ADVB_TRY(model_backward(h, x, y, B, ADVB_GRAD_CE, n_global, h->grad, st));
+      ADVB_TRY(fgsm_step(x, h->grad, x_adv, atk->eps, n, st));
+      return 0;
+    }
+    case ADVB_ATTACK_PGD: {
+      ADVB_CHECK(atk->steps >= 0, "bad step count");
+      ADVB_TRY(pgd_start(x, start, x_adv, n, st));
+      for (int it = 0; it < atk->steps; ++it) {
+        ADVB_TRY(model_forward(h, x_adv, B, st));
+        ADVB_TRY(model_backward(h, x_adv, y, B, ADVB_GRAD_CE, n_global, h->grad, st));
+        ADVB_TRY(pgd_step(x, h->grad, x_adv, atk->eps, atk->alpha, n, st));
+      }
+      return 0;
+    }
+    case ADVB_ATTACK_PGDL2: {
+      ADVB_CHECK(atk->steps >= 0, "bad step count");
+      ADVB_TRY(pgd_start(x, start, x_adv, n, st));
+      for (int it = 0; it < atk->steps; ++it) {
+        ADVB_TRY(model_forward(h, x_adv, B, st));
+        ADVB_TRY(model_backward(h, x_adv, y, B, ADVB_GRAD_CE, n_global, h->grad, st));
+        ADVB_TRY(pgdl2_step(x, h->grad, x_adv, atk->eps, atk->alpha, atk->eps_div, B, T, h->partial_g, h->partial_d,
+                            st));
+      }
+      return 0;
+    }
+    default:
+      set_error("attack kind not implemented in the native loop");
+      return 1;
+  }
+}
+
+int advb_frontend_fwd(advb_handle* h, const float* x, float* coeff, int B, int T, void* cuda_stream) {
+  ADVB_TRY(check_call(h, B, T));
+  CallScope scope(h);
+  cudaStream_t st = static_cast<cudaStream_t>(cuda_stream);
+  refresh_frontend_tables(h);
+  ADVB_TRY(frontend_prepare(h->ftb, st));
+  ADVB_TRY(frontend_forward(h->ftb, h->fst, x, B, T, h->dB, coeff, (long long)80 * h->F, 1, h->F, 0, st));
+  return 0;
+}
+
+int advb_frontend_bwd(advb_handle* h, const float* x, const float* g_coeff, float* g_x, int B, int T,
+                      void* cuda_stream) {
+  ADVB_TRY(check_call(h, B, T));
+  CallScope scope(h);
+  cudaStream_t st = static_cast<cudaStream_t>(cuda_stream);
+  refresh_frontend_tables(h);
+  ADVB_TRY(frontend_prepare(h->ftb, st));
+  // forward first: backward needs the batch arg-max / floor state of this input
+  ADVB_TRY(frontend_forward(h->ftb, h->fst, x, B, T, h->dB, h->coef_tmp, (long long)80 * h->F, 1, h->F, 0, st));
+  ADVB_TRY(frontend_backward(h->ftb, h->fst, x, B, T, h->dB, g_coeff, (long long)80 * h->F, 1, h->F, h->mass_partial,
+                             g_x, st));
+  return 0;
+}
+
+int advb_minmax(const float* x, float* x01, float* mn, float* mx, int B, int T, void* cuda_stream) {
+  ADVB_CHECK(x && x01 && mn && mx && B > 0 && T > 0, "bad argument");
+  return minmax_scale(x, x01, mn, mx, B, T, static_cast<cudaStream_t>(cuda_stream));
+}
+int advb_revert_minmax(const float* x01, const float* mn, const float* mx, float* x, int B, int T, void* cuda_stream) {
+  ADVB_CHECK(x && x01 && mn && mx && B > 0 && T > 0, "bad argument");
+  return minmax_revert(x01, mn, mx, x, B, T, static_cast<cudaStream_t>(cuda_stream));
+}
+
+int64_t advb_debug_stage(advb_handle* h, const char* stage, float* dst, int64_t capacity, int64_t dims[5],
+                         void* cuda_stream) {
+  if (h == nullptr || stage == nullptr) {
+    set_error("null argument");
+    return -1;
+  }
+  CallScope scope(h);
+  cudaStream_t st = static_cast<cudaStream_t>(cuda_stream);
+  const std::string s(stage);
+  const float* src = nullptr;
+  int64_t d[5] = {h->Bmax, 1, 1, 1, 0};
+  auto from_act = [&](const Act& a) {
+    src = a.p;
+    d[1] = a.H;
+    d[2] = a.W;
+    d[3] = a.C;
+    d[4] = a.pad;
+  };
+  if (s == "frontend") from_act(h->act0);
+  else if (s.rfind("block", 0) == 0 && s.size() == 6 && s[5] >= '0' && s[5] <= '8') from_act(h->blk[s[5] - '0'].out);
+  else if (s.rfind("gblock", 0) == 0 && s.size() == 7 && s[6] >= '0' && s[6] <= '8') {
+    const LcnnBlock& k = h->blk[s[6] - '0'];
+    src = k.gout;
+    d[1] = k.Ho;
+    d[2] = k.Wo;
+    d[3] = k.Cout / 2;
+  } else if (s == "feats" || s == "lstm1" || s == "lstm2" || s == "dfeats") {
+    src = s == "feats" ? h->feats : s == "lstm1" ? h->l1 : s == "lstm2" ? h->l2 : h->dfeats;
+    d[1] = h->L;
+    d[2] = 1;
+    d[3] = 160;
+  } else if (s == "gcoef") {
+    src = h->g_coef;
+    d[1] = h->F;
+    d[2] = 80;
+    d[3] = 1;
+  } else if (s == "dB") {
+    src = h->dB;
+    d[1] = h->F;
+    d[2] = 1;
+    d[3] = 128;
+  } else {
+    set_error("unknown stage '" + s + "'");
+    return -1;
+  }
+  const int64_t n = d[0] * (d[1] + 2 * d[4]) * (d[2] + 2 * d[4]) * d[3];
+  if (dims != nullptr)
+    for (int i = 0; i < 5; ++i) dims[i] = d[i];
+  if (dst == nullptr) return n;
+  if (capacity < n) {
+    set_error("debug buffer too small");
+    return -1;
+  }
+  if (cudaMemcpyAsync(dst, src, (size_t)n * sizeof(float), cudaMemcpyDeviceToDevice, st) != cudaSuccess) {
+    set_error("debug copy failed");
+    return -1;
+  }
+  return n;
+}
+
+}  // extern "C"

@@ -1,0 +1,584 @@
+// LFCC / MFCC frontend, forward and input-gradient backward (sm_100a).
+//
+// Replaces torchaudio.transforms.LFCC / MFCC as instantiated by the reference's src/frontends.py:13-32
+// (n_fft 512, Hann-400 centred, hop 160, reflect padding, power 2, 128 triangular filters, dB with the
+// batch-wide top_db=80 floor, DCT-II ortho 128->80).  Math: SURVEY.md App. A.1.
+//
+// Data layout: waveform (B,T) fp32 row-major; dB energies (B,F,128); coefficients are written through
+// caller-supplied strides so the same kernel emits torchaudio's (B,80,F), LCNN's zero-bordered (B,F+4,84,1)
+// image or SpecRNet's (B,82,F+2,1) image.  The spectrum (824 KB/clip) is never stored: backward recomputes the
+// STFT from the waveform.
+//
+// Kernels
+//   fe_power_db   : one warp = two frames packed in one 512-point complex FFT held in shared memory;
+//                   power -> sparse triangular filterbank -> 10 log10 -> dB store + batch arg-max (64-bit atomicMax)
+//   fe_floor_dct  : floor at (batch max - 80), DCT by shared-memory matrix, strided store, clamped-element count
+//   fe_floor_mass : (only when the floor is active) sum of the gradient mass of clamped elements, which autograd
+//                   routes to the batch arg-max element; two-stage fixed-order reduction (deterministic)
+//   fe_bwd        : per tile of 16 hops: dct^T, recompute FFT/power/energies, dB+floor backward, filterbank^T,
+//                   one-sided inverse DFT as a packed complex FFT, window, overlap-add and reflect-pad fold in
+//                   shared memory in a fixed order (deterministic, no atomics), gradient store
+#include "frontend.cuh"
+
+#include <math.h>
+
+namespace advb {
+
+namespace {
+
+constexpr int NFFT = 512;
+constexpr int WIN = 400;
+constexpr int WOFF = 56;  // (512-400)/2
+constexpr int HOP = 160;
+constexpr int NBIN = 257;
+constexpr int NFILT = 128;
+constexpr int NCOEF = 80;
+constexpr int FE_WARPS = 8;
+constexpr int FE_THREADS = FE_WARPS * 32;
+constexpr int PSTRIDE = 260;     // padded 257
+constexpr int DCT_LD = 81;       // padded row of the dct matrix in shared memory (bank spread for row-parallel reads)
+constexpr int TILE_HOPS = 16;    // backward tile = 16 hops = 2560 samples
+constexpr int TILE_S = TILE_HOPS * HOP;
+constexpr int NF_MAX = 24;       // frames a backward tile may need (19 interior, a few more at the right edge)
+
+__device__ __forceinline__ int reflect_index(int j, int T) {
+  if (j < 0) j = -j;
+  if (j >= T) j = 2 * T - 2 - j;
+  return j;
+}
+
+// In-place radix-2 DIT FFT of 512 complex points held by one warp; input in bit-reversed order.
+__device__ __forceinline__ void warp_fft512(float* re, float* im, const float* twr, const float* twi, int lane) {
+#pragma unroll 1
+  for (int s = 0; s < 9; ++s) {
+    const int half = 1 << s;
+    const int tstep = 256 >> s;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const int j = lane + 32 * i;
+      const int pos = j & (half - 1);
+      const int i0 = ((j >> s) << (s + 1)) + pos;
+      const int i1 = i0 + half;
+      const float wr = twr[pos * tstep], wi = twi[pos * tstep];
+      const float xr = re[i1], xi = im[i1];
+      const float tr = wr * xr - wi * xi;
+      const float ti = wr * xi + wi * xr;
+      const float ur = re[i0], ui = im[i0];
+      re[i0] = ur + tr;
+      im[i0] = ui + ti;
+      re[i1] = ur - tr;
+      im[i1] = ui - ti;
+    }
+    __syncwarp();
+  }
+}
+
+// Load two windowed frames (ta, ta+1) of clip `xb` packed as re=frame a, im=frame b, bit-reversed.
+__device__ __forceinline__ void load_frame_pair(const float* __restrict__ xb, int T, int F, int ta, const float* s_win,
+                                                float* re, float* im, int lane) {
+  const bool has_b = (ta + 1) < F;
+  for (int n = lane; n < NFFT; n += 32) {
+    float a = 0.f, b = 0.f;
+    if (n >= WOFF && n < WOFF + WIN) {
+      const float w = s_win[n - WOFF];
+      const int ja = HOP * ta + n - NFFT / 2;
+      a = w * __ldg(xb + reflect_index(ja, T));
+      if (has_b) b = w * __ldg(xb + reflect_index(ja + HOP, T));
+    }
+    const int r = __brev((unsigned)n) >> 23;
+    re[r] = a;
+    im[r] = b;
+  }
+  __syncwarp();
+}
+
+// From the packed spectrum Z: one-sided spectra of both frames at bin k.
+__device__ __forceinline__ void unpack_bin(const float* re, const float* im, int k, float& xar, float& xai, float& xbr,
+                                           float& xbi) {
+  const int kk = (NFFT - k) & (NFFT - 1);
+  const float a = re[k], b = im[k], c = re[kk], d = im[kk];
+  xar = 0.5f * (a + c);
+  xai = 0.5f * (b - d);
+  xbr = 0.5f * (b + d);
+  xbi = 0.5f * (c - a);
+}
+
+__device__ __forceinline__ void filter_energy(const float* __restrict__ fb, const int* __restrict__ klo,
+                                              const int* __restrict__ kcnt, const float* pa, const float* pb, int m,
+                                              float& ea, float& eb) {
+  const int k0 = klo[m], n = kcnt[m];
+  float sa = 0.f, sb = 0.f;
+  for (int i = 0; i < n; ++i) {
+    const float w = __ldg(fb + (size_t)(k0 + i) * NFILT + m);
+    sa += pa[k0 + i] * w;
+    sb += pb[k0 + i] * w;
+  }
+  ea = sa;
+  eb = sb;
+}
+
+__device__ __forceinline__ float to_db(float e) { return 10.0f * log10f(fmaxf(e, 1e-10f)); }
+
+// ---------------------------------------------------------------------------------------------------
+__global__ void fe_tables_kernel(const float* __restrict__ fb, int* klo, int* kcnt, int* mlo, int* mcnt) {
+  const int i = threadIdx.x;
+  if (i < NFILT) {  // per filter: first / last non-zero bin
+    int lo = NBIN, hi = -1;
+    for (int k = 0; k < NBIN; ++k)
+      if (fb[(size_t)k * NFILT + i] != 0.f) {
+        if (k < lo) lo = k;
+        hi = k;
+      }
+    klo[i] = hi < 0 ? 0 : lo;
+    kcnt[i] = hi < 0 ? 0 : hi - lo + 1;
+  }
+  if (i < NBIN) {  // per bin: first / last filter with a non-zero weight
+    int lo = NFILT, hi = -1;
+    for (int m = 0; m < NFILT; ++m)
+      if (fb[(size_t)i * NFILT + m] != 0.f) {
+        if (m < lo) lo = m;
+        hi = m;
+      }
+    mlo[i] = hi < 0 ? 0 : lo;
+    mcnt[i] = hi < 0 ? 0 : hi - lo + 1;
+  }
+}
+
+__global__ void fe_twiddle_kernel(float* twr, float* twi) {
+  const int k = threadIdx.x + blockIdx.x * blockDim.x;
+  if (k < 256) {
+    double s, c;
+    sincospi(2.0 * (double)k / 512.0, &s, &c);
+    twr[k] = (float)c;
+    twi[k] = (float)(-s);
+  }
+}
+
+__global__ void fe_reset_kernel(FrontendState st) {
+  *st.gmax_packed = 0ull;
+  *st.n_clamped = 0;
+  *st.mass_total = 0.f;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// Forward 1: waveform -> dB filterbank energies (B,F,128) + batch arg-max.
+__global__ void __launch_bounds__(FE_THREADS) fe_power_db_kernel(const float* __restrict__ x, int T, int F,
+                                                                   FrontendTables tb, FrontendState st,
+                                                                   float* __restrict__ dB) {
+  extern __shared__ float smem[];
+  float* s_twr = smem;                 // 256
+  float* s_twi = s_twr + 256;          // 256
+  float* s_win = s_twi + 256;          // 400
+  float* s_fft = s_win + 400;          // FE_WARPS * 1024
+  float* s_pw = s_fft + FE_WARPS * 1024;  // FE_WARPS * 2 * PSTRIDE
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  for (int i = tid; i < 256; i += FE_THREADS) {
+    s_twr[i] = tb.twr[i];
+    s_twi[i] = tb.twi[i];
+  }
+  for (int i = tid; i < WIN; i += FE_THREADS) s_win[i] = tb.window[i];
+  __syncthreads();
+
+  const int b = blockIdx.y;
+  const int ta = blockIdx.x * (2 * FE_WARPS) + 2 * warp;
+  if (ta >= F) return;
+  const bool has_b = (ta + 1) < F;
+  float* re = s_fft + warp * 1024;
+  float* im = re + 512;
+  float* pa = s_pw + warp * 2 * PSTRIDE;
+  float* pb = pa + PSTRIDE;
+  const float* xb = x + (size_t)b * T;
+
+  load_frame_pair(xb, T, F, ta, s_win, re, im, lane);
+  warp_fft512(re, im, s_twr, s_twi, lane);
+  for (int k = lane; k < NBIN; k += 32) {
+    float xar, xai, xbr, xbi;
+    unpack_bin(re, im, k, xar, xai, xbr, xbi);
+    pa[k] = xar * xar + xai * xai;
+    pb[k] = xbr * xbr + xbi * xbi;
+  }
+  __syncwarp();
+
+  float best = -INFINITY;
+  unsigned best_idx = 0xffffffffu;
+  const size_t rowa = ((size_t)b * F + ta) * NFILT;
+#pragma unroll
+  for (int i = 0; i < NFILT / 32; ++i) {
+    const int m = lane + 32 * i;
+    float ea, eb;
+    filter_energy(tb.fb, tb.klo, tb.kcnt, pa, pb, m, ea, eb);
+    const float da = to_db(ea);
+    dB[rowa + m] = da;
+    if (da > best) {
+      best = da;
+      best_idx = (unsigned)(rowa + m);
+    }
+    if (has_b) {
+      const float db = to_db(eb);
+      dB[rowa + NFILT + m] = db;
+      if (db > best) {
+        best = db;
+        best_idx = (unsigned)(rowa + NFILT + m);
+      }
+    }
+  }
+  // warp arg-max (largest value, smallest index on ties), then one 64-bit atomicMax per warp
+  unsigned long long packed =
+      ((unsigned long long)((unsigned)float_to_key(best) ^ 0x80000000u) << 32) | (unsigned long long)(~best_idx);
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const unsigned long long other = __shfl_xor_sync(0xffffffffu, packed, o);
+    packed = other > packed ? other : packed;
+  }
+  if (lane == 0) atomicMax(st.gmax_packed, packed);
+}
+
+__device__ __forceinline__ void decode_gmax(unsigned long long packed, float& vmax, unsigned& idx) {
+  vmax = key_to_float((int)((unsigned)(packed >> 32) ^ 0x80000000u));
+  idx = ~(unsigned)(packed & 0xffffffffull);
+}
+
+// Forward 2: floor + DCT.  16 frames per CTA, thread = (frame, 5 coefficients).
+__global__ void __launch_bounds__(256) fe_floor_dct_kernel(const float* __restrict__ dB, int F, FrontendTables tb,
+                                                            FrontendState st, float top_db, float* __restrict__ out,
+                                                            long long clip_stride, long long stride_f,
+                                                            long long stride_c, long long offset) {
+  extern __shared__ float smem[];
+  float* s_dct = smem;                     // 128*80
+  float* s_d = s_dct + NFILT * NCOEF;      // 16*128
+  const int tid = threadIdx.x;
+  const int b = blockIdx.y, f0 = blockIdx.x * 16;
+  float vmax;
+  unsigned amax_idx;
+  decode_gmax(*st.gmax_packed, vmax, amax_idx);
+  const float floor_v = vmax - top_db;
+  for (int i = tid; i < NFILT * NCOEF; i += 256) s_dct[i] = tb.dct[i];
+  int clamped = 0;
+  for (int i = tid; i < 16 * NFILT; i += 256) {
+    const int f = f0 + i / NFILT;
+    float d = 0.f;
+    if (f < F) {
+      d = dB[((size_t)b * F + f) * NFILT + (i % NFILT)];
+      if (d < floor_v) {
+        d = floor_v;
+        ++clamped;
+      }
+    }
+    s_d[i] = d;
+  }
+  const int total = __syncthreads_count(clamped);  // counts threads with clamped != 0 (enough for an "active" flag)
+  if (tid == 0 && total > 0) atomicAdd(st.n_clamped, total);
+
+  const int fl = tid >> 4, cg = tid & 15, f = f0 + fl;
+  if (f >= F) return;
+  float acc[5] = {0.f, 0.f, 0.f, 0.f, 0.f};
+  const float* drow = s_d + fl * NFILT;
+#pragma unroll 4
+  for (int m = 0; m < NFILT; ++m) {
+    const float d = drow[m];
+    const float* w = s_dct + m * NCOEF + cg;
+#pragma unroll
+    for (int i = 0; i < 5; ++i) acc[i] += d * w[16 * i];
+  }
+  float* o = out + (size_t)b * clip_stride + offset + (long long)f * stride_f;
+#pragma unroll
+  for (int i = 0; i < 5; ++i) o[(long long)(cg + 16 * i) * stride_c] = acc[i];
+}
+
+// ---------------------------------------------------------------------------------------------------
+// Backward pre-pass: gradient mass of clamped dB elements (routed to the arg-max element by autograd).
+__global__ void __launch_bounds__(FE_THREADS) fe_floor_mass_kernel(const float* __restrict__ dB, int F,
+                                                                     FrontendTables tb, FrontendState st,
+                                                                     float top_db, const float* __restrict__ gcoef,
+                                                                     long long g_clip_stride, long long g_stride_f,
+                                                                     long long g_stride_c, float* partial) {
+  __shared__ float s_gc[FE_WARPS][2][NCOEF];
+  __shared__ float s_part[FE_WARPS];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int bid = blockIdx.y * gridDim.x + blockIdx.x;
+  if (*st.n_clamped == 0) {
+    if (tid == 0) partial[bid] = 0.f;
+    return;
+  }
+  float vmax;
+  unsigned amax_idx;
+  decode_gmax(*st.gmax_packed, vmax, amax_idx);
+  const float floor_v = vmax - top_db;
+  const int b = blockIdx.y;
+  const int ta = blockIdx.x * (2 * FE_WARPS) + 2 * warp;
+  float mass = 0.f;
+  for (int fr = 0; fr < 2; ++fr) {
+    const int t = ta + fr;
+    if (t < F)
+      for (int c = lane; c < NCOEF; c += 32)
+        s_gc[warp][fr][c] = gcoef[(size_t)b * g_clip_stride + (long long)t * g_stride_f + (long long)c * g_stride_c];
+  }
+  __syncwarp();
+  for (int fr = 0; fr < 2; ++fr) {
+    const int t = ta + fr;
+    if (t >= F) continue;
+    for (int m = lane; m < NFILT; m += 32) {
+      const float d = dB[((size_t)b * F + t) * NFILT + m];
+      if (d < floor_v) {
+        float g = 0.f;
+        for (int c = 0; c < NCOEF; ++c) g += __ldg(tb.dct + m * NCOEF + c) * s_gc[warp][fr][c];
+        mass += g;
+      }
+    }
+  }
+  mass = warp_sum(mass);
+  if (lane == 0) s_part[warp] = mass;
+  __syncthreads();
+  if (tid == 0) {
+    float s = 0.f;
+    for (int w = 0; w < FE_WARPS; ++w) s += s_part[w];
+    partial[bid] = s;
+  }
+}
+
+__global__ void __launch_bounds__(1024) fe_mass_reduce_kernel(const float* __restrict__ partial, int n,
+                                                               FrontendState st) {
+  __shared__ float s[1024];
+  float acc = 0.f;
+  for (int i = threadIdx.x; i < n; i += 1024) acc += partial[i];
+  s[threadIdx.x] = acc;
+  __syncthreads();
+  for (int o = 512; o > 0; o >>= 1) {
+    if (threadIdx.x < o) s[threadIdx.x] += s[threadIdx.x + o];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) *st.mass_total = s[0];
+}
+
+// ---------------------------------------------------------------------------------------------------
+// Backward: d coefficients -> d waveform for one tile of TILE_S samples of one clip.
+__global__ void __launch_bounds__(FE_THREADS) fe_bwd_kernel(const float* __restrict__ x, int T, int F,
+                                                             FrontendTables tb, FrontendState st, float top_db,
+                                                             const float* __restrict__ gcoef, long long g_clip_stride,
+                                                             long long g_stride_f, long long g_stride_c,
+                                                             float* __restrict__ gx, int n_tiles) {
+  extern __shared__ float smem[];
+  float* s_twr = smem;                          // 256
+  float* s_twi = s_twr + 256;                   // 256
+  float* s_win = s_twi + 256;                   // 400
+  float* s_dct = s_win + 400;                   // 128*81
+  float* s_fft = s_dct + NFILT * DCT_LD;        // FE_WARPS * 2048 (Z and H buffers)
+  float* s_pw = s_fft + FE_WARPS * 2048;        // FE_WARPS * 2 * PSTRIDE  (power, then d power)
+  float* s_ge = s_pw + FE_WARPS * 2 * PSTRIDE;  // FE_WARPS * 2 * 128       (d energy)
+  float* s_gc = s_ge + FE_WARPS * 2 * NFILT;    // FE_WARPS * 2 * 80        (d coefficients)
+  float* s_yw = s_gc + FE_WARPS * 2 * NCOEF;    // NF_MAX * 400             (windowed frame gradients)
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  for (int i = tid; i < 256; i += FE_THREADS) {
+    s_twr[i] = tb.twr[i];
+    s_twi[i] = tb.twi[i];
+  }
+  for (int i = tid; i < WIN; i += FE_THREADS) s_win[i] = tb.window[i];
+  for (int i = tid; i < NFILT * NCOEF; i += FE_THREADS) s_dct[(i / NCOEF) * DCT_LD + (i % NCOEF)] = tb.dct[i];
+  __syncthreads();
+
+  const int b = blockIdx.y, tile = blockIdx.x;
+  const int s0 = tile * TILE_S;
+  const int s1 = min(T, s0 + TILE_S);
+  // frames whose (reflected) support can touch [s0, s1)
+  int t_lo = (s0 - 199 + 159 + 160 * 4) / 160 - 4;
+  if (t_lo < 0) t_lo = 0;
+  int t_hi = (s1 - 1 + 200) / 160;
+  if (s1 >= T - 202) t_hi = F - 1;
+  if (t_hi > F - 1) t_hi = F - 1;
+  const int nf = t_hi - t_lo + 1;  // host guarantees nf <= NF_MAX
+
+  float vmax;
+  unsigned amax_idx;
+  decode_gmax(*st.gmax_packed, vmax, amax_idx);
+  const float floor_v = vmax - top_db;
+  const float mass_total = *st.mass_total;
+  const float* xb = x + (size_t)b * T;
+
+  float* re = s_fft + warp * 2048;
+  float* im = re + 512;
+  float* re2 = re + 1024;
+  float* im2 = re + 1536;
+  float* pa = s_pw + warp * 2 * PSTRIDE;
+  float* pb = pa + PSTRIDE;
+  float* gea = s_ge + warp * 2 * NFILT;
+  float* geb = gea + NFILT;
+  float* gca = s_gc + warp * 2 * NCOEF;
+  float* gcb = gca + NCOEF;
+
+  for (int pair = warp; 2 * pair < nf; pair += FE_WARPS) {
+    const int ta = t_lo + 2 * pair;
+    const bool has_b = (2 * pair + 1 < nf);  // frame ta+1 is inside [t_lo, t_hi] (hence < F)
+    // 1. d coefficients
+    for (int c = lane; c < NCOEF; c += 32) {
+      const size_t base = (size_t)b * g_clip_stride + (long long)c * g_stride_c;
+      gca[c] = gcoef[base + (long long)ta * g_stride_f];
+      gcb[c] = has_b ? gcoef[base + (long long)(ta + 1) * g_stride_f] : 0.f;
+    }
+    // 2. recompute the packed FFT of both frames
+    load_frame_pair(xb, T, has_b ? F : ta + 1, ta, s_win, re, im, lane);
+    warp_fft512(re, im, s_twr, s_twi, lane);
+    // 3. power
+    for (int k = lane; k < NBIN; k += 32) {
+      float xar, xai, xbr, xbi;
+      unpack_bin(re, im, k, xar, xai, xbr, xbi);
+      pa[k] = xar * xar + xai * xai;
+      pb[k] = xbr * xbr + xbi * xbi;
+    }
+    __syncwarp();
+    // 4. energies, dB, floor backward, d energy
+    const size_t rowa = ((size_t)b * F + ta) * NFILT;
+#pragma unroll 1
+    for (int i = 0; i < NFILT / 32; ++i) {
+      const int m = lane + 32 * i;
+      float ea, eb;
+      filter_energy(tb.fb, tb.klo, tb.kcnt, pa, pb, m, ea, eb);
+      float gda = 0.f, gdb = 0.f;
+      const float* drow = s_dct + m * DCT_LD;
+#pragma unroll 8
+      for (int c = 0; c < NCOEF; ++c) {
+        const float w = drow[c];
+        gda += w * gca[c];
+        gdb += w * gcb[c];
+      }
+      if ((unsigned)(rowa + m) == amax_idx) gda += mass_total;
+      if ((unsigned)(rowa + NFILT + m) == amax_idx) gdb += mass_total;
+      const float k10 = 4.342944819032518f;  // 10 / ln 10
+      const float da = to_db(ea), db = to_db(eb);
+      gea[m] = (da > floor_v && ea >= 1e-10f) ? gda * k10 / ea : 0.f;
+      geb[m] = (has_b && db > floor_v && eb >= 1e-10f) ? gdb * k10 / eb : 0.f;
+    }
+    __syncwarp();
+    // 5. d power (overwrites the power buffers)
+    for (int k = lane; k < NBIN; k += 32) {
+      const int m0 = tb.mlo[k], n = tb.mcnt[k];
+      float sa = 0.f, sb = 0.f;
+      for (int i = 0; i < n; ++i) {
+        const float w = __ldg(tb.fb + (size_t)k * NFILT + m0 + i);
+        sa += w * gea[m0 + i];
+        sb += w * geb[m0 + i];
+      }
+      pa[k] = sa;
+      pb[k] = sb;
+    }
+    __syncwarp();
+    // 6. conj(H), H = Ha + i Hb Hermitian-extended one-sided gradients (no doubling of interior bins), bit-reversed
+    for (int k = lane; k < NBIN; k += 32) {
+      float xar, xai, xbr, xbi;
+      unpack_bin(re, im, k, xar, xai, xbr, xbi);
+      const float ga = pa[k], gb = pb[k];
+      const int rk = __brev((unsigned)k) >> 23;
+      if (k == 0 || k == 256) {
+        re2[rk] = 2.f * ga * xar;
+        im2[rk] = -(2.f * gb * xbr);
+      } else {
+        const float har = ga * xar, hai = ga * xai, hbr = gb * xbr, hbi = gb * xbi;
+        const int rk2 = __brev((unsigned)(NFFT - k)) >> 23;
+        re2[rk] = har - hbi;
+        im2[rk] = -(hai + hbr);
+        re2[rk2] = har + hbi;
+        im2[rk2] = -(hbr - hai);
+      }
+    }
+    __syncwarp();
+    // 7. W = conj(FFT(conj H)): ya = Re, yb = -Im
+    warp_fft512(re2, im2, s_twr, s_twi, lane);
+    // 8. window and park per-frame
+    float* ywa = s_yw + (2 * pair) * WIN;
+    for (int n = lane; n < WIN; n += 32) {
+      const float w = s_win[n];
+      ywa[n] = w * re2[n + WOFF];
+      if (has_b) ywa[WIN + n] = -(w * im2[n + WOFF]);
+    }
+    __syncwarp();
+  }
+  __syncthreads();
+
+  // overlap-add + reflect-pad fold, fixed order
+  for (int sl = tid; sl < s1 - s0; sl += FE_THREADS) {
+    const int s = s0 + sl;
+    float acc = 0.f;
+#pragma unroll 1
+    for (int v = 0; v < 3; ++v) {
+      int j;
+      if (v == 0) j = s;
+      else if (v == 1) {
+        if (s < 1 || s > 256) continue;
+        j = -s;
+      } else {
+        if (s > T - 2 || s < T - 2 - 255) continue;
+        j = 2 * T - 2 - s;
+      }
+      int tf = (j - 199 + 159 + 160 * 4) / 160 - 4;
+      int tl = (j + 200 + 160 * 4) / 160 - 4;
+      if (tf < t_lo) tf = t_lo;
+      if (tl > t_hi) tl = t_hi;
+      for (int t = tf; t <= tl; ++t) acc += s_yw[(t - t_lo) * WIN + (j - HOP * t + 200)];
+    }
+    gx[(size_t)b * T + s] = acc;
+  }
+}
+
+size_t fe_fwd_smem() { return (size_t)(256 + 256 + 400 + FE_WARPS * 1024 + FE_WARPS * 2 * PSTRIDE) * sizeof(float); }
+size_t fe_dct_smem() { return (size_t)(NFILT * NCOEF + 16 * NFILT) * sizeof(float); }
+size_t fe_bwd_smem() {
+  return (size_t)(256 + 256 + 400 + NFILT * DCT_LD + FE_WARPS * 2048 + FE_WARPS * 2 * PSTRIDE + FE_WARPS * 2 * NFILT +
+                  FE_WARPS * 2 * NCOEF + NF_MAX * WIN) *
+         sizeof(float);
+}
+
+}  // namespace
+
+int frontend_frames(int T) { return 1 + T / HOP; }
+int frontend_mass_blocks(int B, int T) { return B * cdiv(frontend_frames(T), 2 * FE_WARPS); }
+
+int frontend_init_constants(float* twr, float* twi, cudaStream_t stream) {
+  fe_twiddle_kernel<<<1, 256, 0, stream>>>(twr, twi);
+  ADVB_LAUNCH_OK();
+  ADVB_CUDA_OK(cudaFuncSetAttribute(fe_power_db_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fe_fwd_smem()));
+  ADVB_CUDA_OK(cudaFuncSetAttribute(fe_floor_dct_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fe_dct_smem()));
+  ADVB_CUDA_OK(cudaFuncSetAttribute(fe_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fe_bwd_smem()));
+  return 0;
+}
+
+int frontend_prepare(const FrontendTables& tb, cudaStream_t stream) {
+  fe_tables_kernel<<<1, 288, 0, stream>>>(tb.fb, tb.klo, tb.kcnt, tb.mlo, tb.mcnt);
+  ADVB_LAUNCH_OK();
+  return 0;
+}
+
+int frontend_forward(const FrontendTables& tb, const FrontendState& st, const float* x, int B, int T, float* dB,
+                     float* out, long long clip_stride, long long stride_f, long long stride_c, long long offset,
+                     cudaStream_t stream) {
+  const int F = frontend_frames(T);
+  ADVB_CHECK(T >= 512, "clip shorter than one FFT frame");
+  fe_reset_kernel<<<1, 1, 0, stream>>>(st);
+  ADVB_LAUNCH_OK();
+  dim3 g1(cdiv(F, 2 * FE_WARPS), B);
+  fe_power_db_kernel<<<g1, FE_THREADS, fe_fwd_smem(), stream>>>(x, T, F, tb, st, dB);
+  ADVB_LAUNCH_OK();
+  dim3 g2(cdiv(F, 16), B);
+  fe_floor_dct_kernel<<<g2, 256, fe_dct_smem(), stream>>>(dB, F, tb, st, 80.0f, out, clip_stride, stride_f, stride_c,
+                                                         offset);
+  ADVB_LAUNCH_OK();
+  return 0;
+}
+
+int frontend_backward(const FrontendTables& tb, const FrontendState& st, const float* x, int B, int T,
+                      const float* dB, const float* gcoef, long long g_clip_stride, long long g_stride_f,
+                      long long g_stride_c, float* mass_partial, float* gx, cudaStream_t stream) {
+  const int F = frontend_frames(T);
+  dim3 g1(cdiv(F, 2 * FE_WARPS), B);
+  fe_floor_mass_kernel<<<g1, FE_THREADS, 0, stream>>>(dB, F, tb, st, 80.0f, gcoef, g_clip_stride, g_stride_f,
+                                                     g_stride_c, mass_partial);
+  ADVB_LAUNCH_OK();
+  fe_mass_reduce_kernel<<<1, 1024, 0, stream>>>(mass_partial, (int)(g1.x * g1.y), st);
+  ADVB_LAUNCH_OK();
+  const int n_tiles = cdiv(T, TILE_S);
+  dim3 g2(n_tiles, B);
+  fe_bwd_kernel<<<g2, FE_THREADS, fe_bwd_smem(), stream>>>(x, T, F, tb, st, 80.0f, gcoef, g_clip_stride, g_stride_f,
+                                                          g_stride_c, gx, n_tiles);
+  ADVB_LAUNCH_OK();
+  return 0;
+}
+
+}  // namespace advb

@@ -1,0 +1,39 @@
+// Frontend (LFCC/MFCC) host entry points — see frontend.cu.
+#pragma once
+#include "common.cuh"
+
+namespace advb {
+
+struct FrontendTables {
+  const float* fb;      // (257,128) live buffer of the model (frontend.filter_mat / ...mel_scale.fb)
+  const float* dct;     // (128,80)  live buffer (frontend.dct_mat)
+  const float* window;  // (400)     live buffer (Hann)
+  const float* twr;     // 256  cos(2 pi k / 512)      (engine-owned constants)
+  const float* twi;     // 256 -sin(2 pi k / 512)
+  int* klo;             // 128: first non-zero bin of each filter   (rebuilt from fb on every call)
+  int* kcnt;            // 128: number of bins spanned
+  int* mlo;             // 257: first filter touching each bin
+  int* mcnt;            // 257
+};
+
+struct FrontendState {
+  unsigned long long* gmax_packed;  // batch arg-max of the dB tensor: (ordered float key << 32) | ~index
+  int* n_clamped;                   // > 0 iff the top_db floor clamped anything in the last forward
+  float* mass_total;                // backward: summed gradient of clamped elements
+};
+
+int frontend_frames(int T);
+int frontend_mass_blocks(int B, int T);
+int frontend_init_constants(float* twr, float* twi, cudaStream_t stream);
+int frontend_prepare(const FrontendTables& tb, cudaStream_t stream);
+
+// out[b*clip_stride + offset + f*stride_f + c*stride_c] = coefficient c of frame f
+int frontend_forward(const FrontendTables& tb, const FrontendState& st, const float* x, int B, int T, float* dB,
+                     float* out, long long clip_stride, long long stride_f, long long stride_c, long long offset,
+                     cudaStream_t stream);
+// gcoef read through the same kind of strides (no offset: pass the shifted pointer); gx (B,T)
+int frontend_backward(const FrontendTables& tb, const FrontendState& st, const float* x, int B, int T,
+                      const float* dB, const float* gcoef, long long g_clip_stride, long long g_stride_f,
+                      long long g_stride_c, float* mass_partial, float* gx, cudaStream_t stream);
+
+}  // namespace advb

@@ -1,0 +1,342 @@
+// Recurrent tail of LCNN: 2 x bidirectional LSTM(160 -> 2x80), residual mean pooling, Linear(160 -> 1), the 2-class
+// cross-entropy head and the backward of all of it (sm_100a, fp32).
+//
+// Replaces BLSTMLayer (src/models/lcnn.py:24-46), the embedding tail (lcnn.py:196-206) and the patched attack head
+// cat([-o, o]) + CrossEntropyLoss + autograd (fgsm.py:43-57, pgd.py:61-72).
+//
+// Structure: the input projection of all time steps is one small GEMM (gemm_kernel); the recurrence keeps W_hh^T
+// (80x320 fp32 = 100 KB) resident in shared memory for the whole sequence, one CTA per (pair of clips, direction);
+// gate activations overwrite the projection buffer in place and are reused by BPTT, which again keeps W_hh in
+// shared memory and overwrites the same buffer with the pre-activation gate gradients; the input gradient is a
+// second small GEMM.  PyTorch gate order i,f,g,o; zero initial state.
+#include "rnn.cuh"
+
+namespace advb {
+
+namespace {
+
+constexpr int HID = 80;
+constexpr int G4 = 4 * HID;  // 320
+constexpr int CL = 2;        // clips per recurrence CTA
+
+// C[M,N] = A[M,K] * Bm[K,N] (+ bias[N]) (+ Cadd[M,N]); row-major; 64x64 tile, 4x4 per thread.
+__global__ void __launch_bounds__(256) gemm_kernel(const float* __restrict__ A, const float* __restrict__ Bm,
+                                                    const float* __restrict__ bias, const float* __restrict__ Cadd,
+                                                    float* __restrict__ C, int M, int N, int K) {
+  __shared__ float As[16][65];
+  __shared__ float Bs[16][64];
+  const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
+  const int m0 = blockIdx.y * 64, n0 = blockIdx.x * 64;
+  float acc[4][4] = {};
+  for (int k0 = 0; k0 < K; k0 += 16) {
+    for (int i = tid; i < 64 * 16; i += 256) {
+      const int r = i >> 4, c = i & 15;
+      const int m = m0 + r, k = k0 + c;
+      As[c][r] = (m < M && k < K) ? A[(size_t)m * K + k] : 0.f;
+    }
+    for (int i = tid; i < 16 * 64; i += 256) {
+      const int r = i >> 6, c = i & 63;
+      const int k = k0 + r, n = n0 + c;
+      Bs[r][c] = (k < K && n < N) ? Bm[(size_t)k * N + n] : 0.f;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int kk = 0; kk < 16; ++kk) {
+      float a[4], bv[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) a[i] = As[kk][ty * 4 + i];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) bv[j] = Bs[kk][tx * 4 + j];
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(a[i], bv[j], acc[i][j]);
+    }
+    __syncthreads();
+  }
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int m = m0 + ty * 4 + i;
+    if (m >= M) continue;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int n = n0 + tx * 4 + j;
+      if (n >= N) continue;
+      float v = acc[i][j];
+      if (bias != nullptr) v += bias[n];
+      if (Cadd != nullptr) v += Cadd[(size_t)m * N + n];
+      C[(size_t)m * N + n] = v;
+    }
+  }
+}
+
+// Pack one BLSTM layer: wihT [160][640] (col = dir*320 + gate row), bias [640] = b_ih + b_hh,
+// whhT [2][80][320], wih_cat [640][160], whh [2][320][80] (straight copies of the live tensors).
+__global__ void lstm_pack_kernel(LstmWeights w, LstmPacked p, int I) {
+  const int tid = blockIdx.x * blockDim.x + threadIdx.x, nt = gridDim.x * blockDim.x;
+  for (int i = tid; i < 2 * G4 * I; i += nt) {
+    const int k = i % I, j = (i / I) % G4, d = i / (I * G4);
+    const float v = (d == 0 ? w.w_ih[0] : w.w_ih[1])[(size_t)j * I + k];
+    p.wihT[(size_t)k * (2 * G4) + d * G4 + j] = v;
+    p.wih_cat[(size_t)(d * G4 + j) * I + k] = v;
+  }
+  for (int i = tid; i < 2 * G4 * HID; i += nt) {
+    const int k = i % HID, j = (i / HID) % G4, d = i / (HID * G4);
+    const float v = (d == 0 ? w.w_hh[0] : w.w_hh[1])[(size_t)j * HID + k];
+    p.whhT[((size_t)d * HID + k) * G4 + j] = v;
+    p.whh[((size_t)d * G4 + j) * HID + k] = v;
+  }
+  for (int i = tid; i < 2 * G4; i += nt) {
+    const int j = i % G4, d = i / G4;
+    p.bias[i] = (d == 0 ? w.b_ih[0] : w.b_ih[1])[j] + (d == 0 ? w.b_hh[0] : w.b_hh[1])[j];
+  }
+}
+
+__device__ __forceinline__ float sigmoidf_(float x) { return 1.0f / (1.0f + expf(-x)); }
+
+// gates (B,L,640): in = input projection (+bias), out = activated gates i,f,g,o.  hout (B,L,160), cs (B,L,2,80).
+__global__ void __launch_bounds__(G4) lstm_rec_fwd_kernel(float* __restrict__ gates, const float* __restrict__ whhT,
+                                                           float* __restrict__ hout, float* __restrict__ cs, int B,
+                                                           int L) {
+  extern __shared__ __align__(16) float smem[];
+  float* s_w = smem;                 // [80][320]
+  float* s_h = s_w + HID * G4;       // [CL][80]
+  float* s_a = s_h + CL * HID;       // [CL][320]
+  const int j = threadIdx.x, dir = blockIdx.y, b0 = blockIdx.x * CL;
+  const float* wsrc = whhT + (size_t)dir * HID * G4;
+  for (int i = j; i < HID * G4; i += G4) s_w[i] = wsrc[i];
+  if (j < CL * HID) s_h[j] = 0.f;
+  float c_reg[CL];
+#pragma unroll
+  for (int cl = 0; cl < CL; ++cl) c_reg[cl] = 0.f;
+  __syncthreads();
+  const int gate = j / HID;
+  for (int step = 0; step < L; ++step) {
+    const int t = dir == 0 ? step : L - 1 - step;
+    float acc[CL];
+#pragma unroll
+    for (int cl = 0; cl < CL; ++cl)
+      acc[cl] = (b0 + cl < B) ? gates[((size_t)(b0 + cl) * L + t) * (2 * G4) + dir * G4 + j] : 0.f;
+#pragma unroll 8
+    for (int k = 0; k < HID; ++k) {
+      const float w = s_w[k * G4 + j];
+#pragma unroll
+      for (int cl = 0; cl < CL; ++cl) acc[cl] = fmaf(w, s_h[cl * HID + k], acc[cl]);
+    }
+#pragma unroll
+    for (int cl = 0; cl < CL; ++cl) {
+      const float a = gate == 2 ? tanhf(acc[cl]) : sigmoidf_(acc[cl]);
+      s_a[cl * G4 + j] = a;
+      if (b0 + cl < B) gates[((size_t)(b0 + cl) * L + t) * (2 * G4) + dir * G4 + j] = a;
+    }
+    __syncthreads();
+    if (j < HID) {
+#pragma unroll
+      for (int cl = 0; cl < CL; ++cl) {
+        const float* a = s_a + cl * G4;
+        const float c = a[HID + j] * c_reg[cl] + a[j] * a[2 * HID + j];
+        const float h = a[3 * HID + j] * tanhf(c);
+        c_reg[cl] = c;
+        s_h[cl * HID + j] = h;
+        if (b0 + cl < B) {
+          hout[((size_t)(b0 + cl) * L + t) * (2 * HID) + dir * HID + j] = h;
+          cs[(((size_t)(b0 + cl) * L + t) * 2 + dir) * HID + j] = c;
+        }
+      }
+    }
+    __syncthreads();
+  }
+}
+
+// BPTT.  gates (B,L,640): in = activated gates, out = gradient w.r.t. gate pre-activations.  dout (B,L,160).
+__global__ void __launch_bounds__(G4) lstm_rec_bwd_kernel(float* __restrict__ gates, const float* __restrict__ whh,
+                                                           const float* __restrict__ dout,
+                                                           const float* __restrict__ cs, int B, int L) {
+  extern __shared__ __align__(16) float smem[];
+  float* s_w = smem;                   // [320][80]
+  float* s_dg = s_w + G4 * HID;        // [CL][320]
+  float* s_dh = s_dg + CL * G4;        // [CL][80]
+  float* s_part = s_dh + CL * HID;     // [CL][4][80]
+  const int j = threadIdx.x, dir = blockIdx.y, b0 = blockIdx.x * CL;
+  const float* wsrc = whh + (size_t)dir * G4 * HID;
+  for (int i = j; i < G4 * HID; i += G4) s_w[i] = wsrc[i];
+  if (j < CL * HID) s_dh[j] = 0.f;
+  float dc[CL];
+#pragma unroll
+  for (int cl = 0; cl < CL; ++cl) dc[cl] = 0.f;
+  __syncthreads();
+  const int part = j / HID, u = j % HID;
+  for (int step = L - 1; step >= 0; --step) {
+    const int t = dir == 0 ? step : L - 1 - step;
+    const int tp = dir == 0 ? t - 1 : t + 1;
+    if (j < HID) {
+#pragma unroll
+      for (int cl = 0; cl < CL; ++cl) {
+        float dgi = 0.f, dgf = 0.f, dgg = 0.f, dgo = 0.f;
+        if (b0 + cl < B) {
+          const size_t bt = (size_t)(b0 + cl) * L + t;
+          const float* g = gates + bt * (2 * G4) + dir * G4;
+          const float gi = g[j], gf = g[HID + j], gg = g[2 * HID + j], go = g[3 * HID + j];
+          const float c = cs[(bt * 2 + dir) * HID + j];
+          const float cp = step > 0 ? cs[((((size_t)(b0 + cl) * L + tp) * 2) + dir) * HID + j] : 0.f;
+          const float dh = dout[bt * (2 * HID) + dir * HID + j] + s_dh[cl * HID + j];
+          const float tc = tanhf(c);
+          const float d_o = dh * tc;
+          const float dcc = dc[cl] + dh * go * (1.f - tc * tc);
+          dc[cl] = dcc * gf;
+          dgi = dcc * gg * gi * (1.f - gi);
+          dgf = dcc * cp * gf * (1.f - gf);
+          dgg = dcc * gi * (1.f - gg * gg);
+          dgo = d_o * go * (1.f - go);
+        }
+        float* d = s_dg + cl * G4;
+        d[j] = dgi;
+        d[HID + j] = dgf;
+        d[2 * HID + j] = dgg;
+        d[3 * HID + j] = dgo;
+      }
+    }
+    __syncthreads();
+#pragma unroll
+    for (int cl = 0; cl < CL; ++cl) {
+      if (b0 + cl < B) gates[((size_t)(b0 + cl) * L + t) * (2 * G4) + dir * G4 + j] = s_dg[cl * G4 + j];
+      float s = 0.f;
+      const float* d = s_dg + cl * G4 + part * HID;
+      const float* w = s_w + (size_t)part * HID * HID + u;
+#pragma unroll 8
+      for (int jj = 0; jj < HID; ++jj) s = fmaf(d[jj], w[jj * HID], s);
+      s_part[(cl * 4 + part) * HID + u] = s;
+    }
+    __syncthreads();
+    if (j < HID) {
+#pragma unroll
+      for (int cl = 0; cl < CL; ++cl) {
+        const float* p = s_part + cl * 4 * HID + j;
+        s_dh[cl * HID + j] = (p[0] + p[HID]) + (p[2 * HID] + p[3 * HID]);
+      }
+    }
+    __syncthreads();
+  }
+}
+
+// NHWC (B,L,Wf,C) block output -> (B,L,C*Wf) features with index c*Wf + w  (lcnn.py:196-199), and back.
+__global__ void feats_gather_kernel(const float* __restrict__ act, float* __restrict__ feats, int n, int Wf, int C) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const int c = i % C, w = (i / C) % Wf;
+  const size_t bl = i / (C * Wf);
+  feats[bl * (C * Wf) + c * Wf + w] = act[i];
+}
+__global__ void feats_scatter_kernel(const float* __restrict__ gfeats, float* __restrict__ gact, int n, int Wf, int C) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const int c = i % C, w = (i / C) % Wf;
+  const size_t bl = i / (C * Wf);
+  gact[i] = gfeats[bl * (C * Wf) + c * Wf + w];
+}
+
+// logits[b] = w . mean_t(l2 + feats) + bias   (lcnn.py:205)
+__global__ void __launch_bounds__(160) head_fwd_kernel(const float* __restrict__ l2, const float* __restrict__ feats,
+                                                        const float* __restrict__ w, const float* __restrict__ bias,
+                                                        float* __restrict__ logits, int L) {
+  __shared__ float s_red[5];
+  const int b = blockIdx.x, k = threadIdx.x;
+  float s = 0.f;
+  for (int t = 0; t < L; ++t) {
+    const size_t o = ((size_t)b * L + t) * 160 + k;
+    s += l2[o] + feats[o];
+  }
+  float v = (s / (float)L) * w[k];
+  v = warp_sum(v);
+  if ((k & 31) == 0) s_red[k >> 5] = v;
+  __syncthreads();
+  if (k == 0) logits[b] = (((s_red[0] + s_red[1]) + (s_red[2] + s_red[3])) + s_red[4]) + bias[0];
+}
+
+// d loss / d logit, then d/d(l2) = d/d(feats residual) = g_o * w / L for every time step.
+__global__ void __launch_bounds__(160) head_bwd_kernel(const float* __restrict__ logits, const long long* __restrict__ y,
+                                                        const float* __restrict__ w, float* __restrict__ dl2, int L,
+                                                        int mode, float inv_n) {
+  const int b = blockIdx.x, k = threadIdx.x;
+  float go = 1.0f;
+  if (mode == 0) {
+    const float o = logits[b];
+    const float p1 = 1.0f / (1.0f + expf(-2.0f * o));
+    go = 2.0f * (p1 - (float)y[b]) * inv_n;
+  }
+  const float v = go * w[k] / (float)L;
+  for (int t = 0; t < L; ++t) dl2[((size_t)b * L + t) * 160 + k] = v;
+}
+
+}  // namespace
+
+size_t lstm_rec_fwd_smem() { return (size_t)(HID * G4 + CL * HID + CL * G4) * sizeof(float); }
+size_t lstm_rec_bwd_smem() { return (size_t)(G4 * HID + CL * G4 + CL * HID + CL * 4 * HID) * sizeof(float); }
+
+int rnn_init() {
+  ADVB_CUDA_OK(cudaFuncSetAttribute(lstm_rec_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                    (int)lstm_rec_fwd_smem()));
+  ADVB_CUDA_OK(cudaFuncSetAttribute(lstm_rec_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                    (int)lstm_rec_bwd_smem()));
+  return 0;
+}
+
+int gemm(const float* A, const float* Bm, const float* bias, const float* Cadd, float* C, int M, int N, int K,
+         cudaStream_t stream) {
+  dim3 grid(cdiv(N, 64), cdiv(M, 64));
+  gemm_kernel<<<grid, 256, 0, stream>>>(A, Bm, bias, Cadd, C, M, N, K);
+  ADVB_LAUNCH_OK();
+  return 0;
+}
+
+int lstm_pack(const LstmWeights& w, const LstmPacked& p, cudaStream_t stream) {
+  lstm_pack_kernel<<<64, 256, 0, stream>>>(w, p, 160);
+  ADVB_LAUNCH_OK();
+  return 0;
+}
+
+int blstm_forward(const LstmPacked& p, const float* x, float* gates, float* hout, float* cs, int B, int L,
+                  cudaStream_t stream) {
+  ADVB_TRY(gemm(x, p.wihT, p.bias, nullptr, gates, B * L, 2 * G4, 160, stream));
+  dim3 grid(cdiv(B, CL), 2);
+  lstm_rec_fwd_kernel<<<grid, G4, lstm_rec_fwd_smem(), stream>>>(gates, p.whhT, hout, cs, B, L);
+  ADVB_LAUNCH_OK();
+  return 0;
+}
+
+int blstm_backward(const LstmPacked& p, float* gates, const float* dout, const float* cs, const float* dx_add,
+                   float* dx, int B, int L, cudaStream_t stream) {
+  dim3 grid(cdiv(B, CL), 2);
+  lstm_rec_bwd_kernel<<<grid, G4, lstm_rec_bwd_smem(), stream>>>(gates, p.whh, dout, cs, B, L);
+  ADVB_LAUNCH_OK();
+  ADVB_TRY(gemm(gates, p.wih_cat, nullptr, dx_add, dx, B * L, 160, 2 * G4, stream));
+  return 0;
+}
+
+int feats_gather(const float* act, float* feats, int B, int L, int Wf, int C, cudaStream_t stream) {
+  const int n = B * L * Wf * C;
+  feats_gather_kernel<<<cdiv(n, 256), 256, 0, stream>>>(act, feats, n, Wf, C);
+  ADVB_LAUNCH_OK();
+  return 0;
+}
+int feats_scatter(const float* gfeats, float* gact, int B, int L, int Wf, int C, cudaStream_t stream) {
+  const int n = B * L * Wf * C;
+  feats_scatter_kernel<<<cdiv(n, 256), 256, 0, stream>>>(gfeats, gact, n, Wf, C);
+  ADVB_LAUNCH_OK();
+  return 0;
+}
+
+int head_forward(const float* l2, const float* feats, const float* w, const float* bias, float* logits, int B, int L,
+                 cudaStream_t stream) {
+  head_fwd_kernel<<<B, 160, 0, stream>>>(l2, feats, w, bias, logits, L);
+  ADVB_LAUNCH_OK();
+  return 0;
+}
+int head_backward(const float* logits, const long long* y, const float* w, float* dl2, int B, int L, int mode,
+                  int n_global, cudaStream_t stream) {
+  head_bwd_kernel<<<B, 160, 0, stream>>>(logits, y, w, dl2, L, mode, 1.0f / (float)n_global);
+  ADVB_LAUNCH_OK();
+  return 0;
+}
+
+}  // namespace advb

@@ -1,0 +1,39 @@
+// BLSTM / head host entry points — see rnn.cu.
+#pragma once
+#include "common.cuh"
+
+namespace advb {
+
+struct LstmWeights {  // live tensors of one nn.LSTM(160, 80, bidirectional=True): [0] forward, [1] reverse
+  const float* w_ih[2];  // (320,160)
+  const float* w_hh[2];  // (320,80)
+  const float* b_ih[2];  // (320)
+  const float* b_hh[2];  // (320)
+};
+struct LstmPacked {
+  float* wihT;     // [160][640]
+  float* bias;     // [640]
+  float* whhT;     // [2][80][320]
+  float* wih_cat;  // [640][160]
+  float* whh;      // [2][320][80]
+};
+
+int rnn_init();
+int gemm(const float* A, const float* Bm, const float* bias, const float* Cadd, float* C, int M, int N, int K,
+         cudaStream_t stream);
+int lstm_pack(const LstmWeights& w, const LstmPacked& p, cudaStream_t stream);
+// x (B,L,160) -> hout (B,L,160); gates (B,L,640) and cs (B,L,2,80) are saved for backward
+int blstm_forward(const LstmPacked& p, const float* x, float* gates, float* hout, float* cs, int B, int L,
+                  cudaStream_t stream);
+// dout (B,L,160) -> dx (B,L,160) (+ dx_add if non-null); gates is overwritten with pre-activation gradients
+int blstm_backward(const LstmPacked& p, float* gates, const float* dout, const float* cs, const float* dx_add,
+                   float* dx, int B, int L, cudaStream_t stream);
+int feats_gather(const float* act, float* feats, int B, int L, int Wf, int C, cudaStream_t stream);
+int feats_scatter(const float* gfeats, float* gact, int B, int L, int Wf, int C, cudaStream_t stream);
+int head_forward(const float* l2, const float* feats, const float* w, const float* bias, float* logits, int B, int L,
+                 cudaStream_t stream);
+// mode 0: d mean-CE / d logit = 2 (sigmoid(2 o) - y) / n_global ; mode 1: 1
+int head_backward(const float* logits, const long long* y, const float* w, float* dl2, int B, int L, int mode,
+                  int n_global, cudaStream_t stream);
+
+}  // namespace advb

@@ -1,0 +1,130 @@
+/*
+ * advb200 — C ABI of the B200-native adversarial-perturbation engine (libadvb200.so).
+ *
+ * The reference (piotrkawa/audio-deepfake-adversarial-attacks) is pure Python; its "FFI" for this path is the
+ * Python call  atk(images, labels)  on a torchattacks object wrapping an nn.Module.  Each entry point below names
+ * the reference interface it replaces (file:line under /root/reference).  Plain pointers and sizes only: all
+ * tensor memory is owned by the caller (device pointers from the PyTorch allocator), the engine owns only its
+ * workspace.  Every function returns 0 on success, non-zero on error (message via advb_last_error()); no C++
+ * exception crosses this boundary.  A handle is bound to one CUDA device and is not thread-safe.
+ */
+#ifndef ADVB200_H
+#define ADVB200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define ADVB_VERSION 100
+#if defined(__GNUC__)
+#define ADVB_API __attribute__((visibility("default")))
+#else
+#define ADVB_API
+#endif
+
+/* model kinds: src/models/models.py:6-18 (get_model names) */
+enum { ADVB_MODEL_LCNN = 1, ADVB_MODEL_SPECRNET = 2, ADVB_MODEL_RAWNET3 = 3 };
+/* frontend kinds: src/frontends.py:13-50 (0 = raw waveform, RawNet3) */
+enum { ADVB_FRONTEND_NONE = 0, ADVB_FRONTEND_LFCC = 1, ADVB_FRONTEND_MFCC = 2 };
+/* attack kinds: adversarial_attacks/torchattacks/attacks/{fgsm,pgd,pgdl2,fab,cw}.py */
+enum { ADVB_ATTACK_FGSM = 1, ADVB_ATTACK_PGD = 2, ADVB_ATTACK_PGDL2 = 3, ADVB_ATTACK_FAB = 4, ADVB_ATTACK_CW = 5 };
+/* what advb_grad differentiates */
+enum { ADVB_GRAD_CE = 0 /* mean 2-class cross-entropy, fgsm.py:43-57 */, ADVB_GRAD_LOGIT = 1 /* d o_i / d x_i, fab.py:90-105 */ };
+
+typedef struct advb_handle advb_handle;
+
+/* One named weight/buffer tensor borrowed from the caller (a state_dict entry; names as in the reference's
+ * state_dict, e.g. "m_transform.6.weight", "frontend.filter_mat").  The engine reads the storage on every call
+ * and never caches values across calls (adversarial training mutates weights, src/trainer.py:309-331). */
+typedef struct {
+  const char* name;
+  const float* ptr; /* device pointer, contiguous fp32 */
+  int64_t numel;
+} advb_tensor_ref;
+
+/* Replaces: models.get_model(model_name, config, device) + load_model (src/models/models.py:6-18,
+ * src/utils.py:47-71) as seen from the attack: Attack.__init__(name, model) (attack.py:14-35). */
+typedef struct {
+  int model_kind;     /* ADVB_MODEL_* */
+  int frontend_kind;  /* ADVB_FRONTEND_* */
+  int device;         /* CUDA ordinal */
+  int max_batch;      /* workspace is sized for this many clips */
+  int n_samples;      /* T: samples per clip (64000 in BASELINE.json, 64600 native) */
+  int n_tensors;
+  const advb_tensor_ref* tensors;
+} advb_model_desc;
+
+/* Replaces the constructor arguments of torchattacks.FGSM/PGD/PGDL2/FAB/CW
+ * (fgsm.py:28, pgd.py:31-32, pgdl2.py:31, fab.py:51-53, cw.py:38). */
+typedef struct {
+  int kind;           /* ADVB_ATTACK_* */
+  float eps;          /* FGSM/PGD/PGDL2/FAB */
+  float alpha;        /* PGD / PGDL2 step */
+  int steps;
+  float eps_div;      /* PGDL2 eps_for_division */
+  float alpha_max;    /* FAB */
+  float eta;          /* FAB */
+  float beta;         /* FAB */
+  float c;            /* CW */
+  float kappa;        /* CW */
+  float lr;           /* CW */
+  int n_global_batch; /* N of the CE mean when the batch is sharded over ranks (0 = use B) */
+} advb_attack_desc;
+
+ADVB_API int advb_version(void);
+ADVB_API const char* advb_last_error(void);
+
+ADVB_API int advb_create(advb_handle** out, const advb_model_desc* desc);
+ADVB_API void advb_destroy(advb_handle* h);
+ADVB_API size_t advb_workspace_bytes(const advb_handle* h);
+/* Re-point the borrowed tensors (same names/sizes) without reallocating the workspace. */
+ADVB_API int advb_rebind(advb_handle* h, int n_tensors, const advb_tensor_ref* tensors);
+
+/* Replaces  atk(images, labels)  = Attack.__call__ -> {FGSM,PGD,PGDL2,FAB,CW}.forward
+ * (attack.py:308-331; fgsm.py:33-62; pgd.py:40-78; pgdl2.py:40-90; fab.py:70-78; cw.py:46-112), called from
+ * evaluate_models_on_adversarial_attacks.py:220 and src/trainer.py:426,470,492,511,539.
+ *   x        [B,T] fp32 in [0,1], device;  y [B] int64 labels (1 = bonafide), device
+ *   start    nullable [B,T]: the random start drawn by the host with torch:
+ *            PGD: the U(-eps,eps) noise added at pgd.py:56;  PGDL2: the already scaled delta of pgdl2.py:57-61
+ *   x_adv    [B,T] fp32 out (must not alias x)
+ * Work is enqueued on `cuda_stream` (a cudaStream_t); the call does not synchronise. */
+ADVB_API int advb_attack(advb_handle* h, const advb_attack_desc* atk, const float* x, const int64_t* y, const float* start,
+                float* x_adv, int B, int T, void* cuda_stream);
+
+/* Replaces  model(x)  (lcnn.py:239-243, specrnet.py:211-214, rawnet3.py:73-137): logits [B] (the (B,1) column).
+ * Used for clean inference on the attacked batch (evaluate_models_on_adversarial_attacks.py:236-238) and
+ * FAB's _get_predicted_label (fab.py:80-85). */
+ADVB_API int advb_forward(advb_handle* h, const float* x, float* logits, int B, int T, void* cuda_stream);
+
+/* Replaces  torch.autograd.grad(cost, adv_images)  (fgsm.py:56-57, pgd.py:71-72, pgdl2.py:76-77) and FAB's
+ * get_diff_logits_grads_batch (fab.py:90-112).  grad [B,T], logits [B] (nullable). */
+ADVB_API int advb_grad(advb_handle* h, int what, const float* x, const int64_t* y, float* grad, float* logits, int B, int T,
+              int n_global_batch, void* cuda_stream);
+
+/* Replaces LFCC_FN(x) / MFCC_FN(x) (src/frontends.py:13-32): coefficients [B,80,F] (torchaudio layout),
+ * F = 1 + T/160, and their vector-Jacobian product.  Test / f4 entry points. */
+ADVB_API int advb_frontend_fwd(advb_handle* h, const float* x, float* coeff, int B, int T, void* cuda_stream);
+ADVB_API int advb_frontend_bwd(advb_handle* h, const float* x, const float* g_coeff, float* g_x, int B, int T,
+                      void* cuda_stream);
+
+/* Replaces to_minmax / revert_minmax (src/aa/utils.py:4-14).  mn, mx: [B]. */
+ADVB_API int advb_minmax(const float* x, float* x01, float* mn, float* mx, int B, int T, void* cuda_stream);
+ADVB_API int advb_revert_minmax(const float* x01, const float* mn, const float* mx, float* x, int B, int T,
+                       void* cuda_stream);
+
+/* Test introspection: copy one internal stage buffer of the last forward (raw engine layout) to `dst` (device).
+ * dims[0..3] receive the logical (B, H, W, C) of the stage, dims[4] the spatial zero-border width of the
+ * stored layout (rows/cols of padding on each side).  Returns the number of floats copied (<0 on error). */
+ADVB_API int64_t advb_debug_stage(advb_handle* h, const char* stage, float* dst, int64_t capacity, int64_t dims[5],
+                         void* cuda_stream);
+
+/* Number of kernel launches issued by this handle since creation (bench.py's "gpu_launches"). */
+ADVB_API int64_t advb_launch_count(const advb_handle* h);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* ADVB200_H */
