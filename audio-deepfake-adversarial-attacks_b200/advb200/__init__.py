@@ -17,6 +17,6 @@ __version__ = "0.1.0"
 
 
 def install():
-    from .install import install as _install
+    from ._install import install as _install
 
     return _install()

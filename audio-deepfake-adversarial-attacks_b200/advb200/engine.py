@@ -152,6 +152,19 @@ class Engine:
         B, H, W, Cc, p = [int(v) for v in dims]
         return buf.view(B, H + 2 * p, W + 2 * p, Cc), p
 
+    def profile_begin(self):
+        _lib.check(self.lib.advb_profile_begin(self.handle, self._stream()))
+
+    def profile_end(self):
+        """[{name, count, total_ms}] per kernel since profile_begin (synchronises)."""
+        import json
+
+        buf = C.create_string_buffer(1 << 16)
+        n = self.lib.advb_profile_end(self.handle, buf, len(buf))
+        if n < 0 or n > len(buf):
+            raise RuntimeError("advb_profile_end failed")
+        return json.loads(buf.value.decode() or "[]")
+
     @property
     def launches(self) -> int:
         return int(self.lib.advb_launch_count(self.handle))

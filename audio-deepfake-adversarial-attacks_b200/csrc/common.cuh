@@ -17,6 +17,9 @@ extern thread_local LaunchCounter* g_counter;
 inline void count_launch(int k = 1) {
   if (g_counter) g_counter->n += k;
 }
+// Optional per-kernel timing (bench.py's live roofline): when enabled, an event is recorded after every launch;
+// consecutive events on the (serial) stream bracket exactly one kernel.
+void prof_mark(const char* name, cudaStream_t stream);
 
 #define ADVB_CUDA_OK(expr)                                                                              \
   do {                                                                                                  \
@@ -28,15 +31,16 @@ inline void count_launch(int k = 1) {
     }                                                                                                   \
   } while (0)
 
-#define ADVB_LAUNCH_OK()                                                                          \
+#define ADVB_KERNEL_OK(name, stream)                                                              \
   do {                                                                                            \
     cudaError_t _e = cudaGetLastError();                                                          \
     if (_e != cudaSuccess) {                                                                      \
-      ::advb::set_error(std::string("kernel launch failed: ") + cudaGetErrorString(_e) + " at " + \
-                        __FILE__ + ":" + std::to_string(__LINE__));                               \
+      ::advb::set_error(std::string("kernel launch failed (") + (name) + "): " +                  \
+                        cudaGetErrorString(_e) + " at " + __FILE__ + ":" + std::to_string(__LINE__)); \
       return 1;                                                                                   \
     }                                                                                             \
     ::advb::count_launch();                                                                       \
+    ::advb::prof_mark((name), (stream));                                                          \
   } while (0)
 
 #define ADVB_CHECK(cond, msg)                                                       \

@@ -368,13 +368,13 @@ int set_smem(K kernel, size_t bytes) {
 int conv_pack_weights(const float* w, float* wf, float* wd, int Cout, int Cin, int KS, cudaStream_t stream) {
   const int n = Cout * Cin * KS * KS;
   pack_conv_kernel<<<cdiv(n, 256), 256, 0, stream>>>(w, wf, wd, Cout, Cin, KS);
-  ADVB_LAUNCH_OK();
+  ADVB_KERNEL_OK("pack_conv", stream);
   return 0;
 }
 
 int bn_prepare(const float* var, float* invstd, int C, cudaStream_t stream) {
   bn_prepare_kernel<<<cdiv(C, 128), 128, 0, stream>>>(var, invstd, C, 1e-5f);
-  ADVB_LAUNCH_OK();
+  ADVB_KERNEL_OK("bn_prepare", stream);
   return 0;
 }
 
@@ -407,7 +407,7 @@ int conv_mfm_forward(ConvFwdArgs a, cudaStream_t stream) {
     return 1;
   }
 #undef ADVB_FWD
-  ADVB_LAUNCH_OK();
+  ADVB_KERNEL_OK(a.tag, stream);
   return 0;
 }
 
@@ -436,7 +436,7 @@ int conv_mfm_backward(ConvBwdArgs a, cudaStream_t stream) {
     return 1;
   }
 #undef ADVB_BWD
-  ADVB_LAUNCH_OK();
+  ADVB_KERNEL_OK(a.tag, stream);
   return 0;
 }
 
@@ -445,7 +445,7 @@ int conv0_backward(const float* gout, const unsigned char* codes, const float* w
   dim3 grid(cdiv(W, C0_TILE), cdiv(H, C0_TILE), B);
   dim3 block(C0_TILE, C0_TILE);
   conv0_bwd_kernel<<<grid, block, 0, stream>>>(gout, codes, w0, gin, H, W, Ho, Wo);
-  ADVB_LAUNCH_OK();
+  ADVB_KERNEL_OK("conv0_bwd", stream);
   return 0;
 }
 

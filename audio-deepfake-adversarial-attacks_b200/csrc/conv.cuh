@@ -18,6 +18,7 @@ struct ConvFwdArgs {
   int Ho, Wo;
   bool pool;
   int band_floats;  // filled by the launcher
+  const char* tag;  // profiler label
 };
 
 struct ConvBwdArgs {
@@ -30,6 +31,7 @@ struct ConvBwdArgs {
   int Ho, Wo;
   bool pool;
   int band_floats;
+  const char* tag;
 };
 
 int conv_pack_weights(const float* w, float* wf, float* wd, int Cout, int Cin, int KS, cudaStream_t stream);

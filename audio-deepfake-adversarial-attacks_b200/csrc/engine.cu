@@ -5,6 +5,8 @@
 // attack on the caller's stream and returns without synchronising.
 #include <cuda_runtime.h>
 
+#include <string.h>
+
 #include <map>
 #include <string>
 #include <vector>
@@ -22,6 +24,19 @@ static thread_local std::string g_error;
 thread_local LaunchCounter* g_counter = nullptr;
 void set_error(const std::string& msg) { g_error = msg; }
 
+struct Profiler {
+  bool on = false;
+  std::vector<std::pair<const char*, cudaEvent_t>> marks;
+};
+static thread_local Profiler* g_prof = nullptr;
+void prof_mark(const char* name, cudaStream_t stream) {
+  if (g_prof == nullptr || !g_prof->on) return;
+  cudaEvent_t e;
+  if (cudaEventCreate(&e) != cudaSuccess) return;
+  cudaEventRecord(e, stream);
+  g_prof->marks.emplace_back(name, e);
+}
+
 struct TensorRef {
   const float* p;
   int64_t n;
@@ -37,6 +52,7 @@ struct LcnnBlock {
   Act out{};             // block output (zero-bordered for the next conv)
   unsigned char* codes = nullptr;
   float* gout = nullptr;  // compact gradient of the block output
+  std::string tag_f, tag_b;
 };
 
 }  // namespace advb
@@ -47,6 +63,7 @@ struct advb_handle {
   int device = 0, model_kind = 0, frontend_kind = 0, Bmax = 0, T = 0, F = 0;
   std::map<std::string, TensorRef> tensors;
   LaunchCounter counter;
+  Profiler prof;
   std::vector<void*> allocs;
   size_t ws_bytes = 0;
 
@@ -203,6 +220,8 @@ int build_lcnn(advb_handle* h) {
     k.KS = s[3];
     k.pool = s[4] != 0;
     k.bn_idx = s[5];
+    k.tag_f = "conv_fwd_b" + std::to_string(i);
+    k.tag_b = "conv_bwd_b" + std::to_string(i);
     k.H = H;
     k.W = W;
     k.Ho = k.pool ? H / 2 : H;
@@ -298,6 +317,7 @@ int lcnn_forward(advb_handle* h, const float* x, int B, cudaStream_t st) {
     a.Ho = k.Ho;
     a.Wo = k.Wo;
     a.pool = k.pool;
+    a.tag = k.tag_f.c_str();
     ADVB_TRY(conv_mfm_forward(a, st));
     in = k.out.p;
     in_pad = k.out.pad;
@@ -335,6 +355,7 @@ int lcnn_backward(advb_handle* h, const float* x, const int64_t* y, int B, int m
     a.Ho = k.Ho;
     a.Wo = k.Wo;
     a.pool = k.pool;
+    a.tag = k.tag_b.c_str();
     ADVB_TRY(conv_mfm_backward(a, st));
   }
   const LcnnBlock& k0 = h->blk[0];
@@ -370,8 +391,14 @@ int check_call(advb_handle* h, int B, int T) {
 
 struct CallScope {
   DeviceGuard guard;
-  explicit CallScope(advb_handle* h) : guard(h->device) { g_counter = &h->counter; }
-  ~CallScope() { g_counter = nullptr; }
+  explicit CallScope(advb_handle* h) : guard(h->device) {
+    g_counter = &h->counter;
+    g_prof = &h->prof;
+  }
+  ~CallScope() {
+    g_counter = nullptr;
+    g_prof = nullptr;
+  }
 };
 
 }  // namespace
@@ -544,6 +571,49 @@ int advb_minmax(const float* x, float* x01, float* mn, float* mx, int B, int T, 
 int advb_revert_minmax(const float* x01, const float* mn, const float* mx, float* x, int B, int T, void* cuda_stream) {
   ADVB_CHECK(x && x01 && mn && mx && B > 0 && T > 0, "bad argument");
   return minmax_revert(x01, mn, mx, x, B, T, static_cast<cudaStream_t>(cuda_stream));
+}
+
+int advb_profile_begin(advb_handle* h, void* cuda_stream) {
+  ADVB_CHECK(h != nullptr, "null handle");
+  CallScope scope(h);
+  for (auto& m : h->prof.marks) cudaEventDestroy(m.second);
+  h->prof.marks.clear();
+  h->prof.on = true;
+  prof_mark("begin", static_cast<cudaStream_t>(cuda_stream));
+  return 0;
+}
+
+int64_t advb_profile_end(advb_handle* h, char* buf, int64_t capacity) {
+  if (h == nullptr) return -1;
+  DeviceGuard guard(h->device);
+  h->prof.on = false;
+  auto& mk = h->prof.marks;
+  std::map<std::string, std::pair<double, int64_t>> agg;
+  if (!mk.empty()) cudaEventSynchronize(mk.back().second);
+  for (size_t i = 1; i < mk.size(); ++i) {
+    float ms = 0.f;
+    if (cudaEventElapsedTime(&ms, mk[i - 1].second, mk[i].second) != cudaSuccess) continue;
+    auto& a = agg[mk[i].first];
+    a.first += ms;
+    a.second += 1;
+  }
+  for (auto& m : mk) cudaEventDestroy(m.second);
+  mk.clear();
+  std::string js = "[";
+  bool first = true;
+  for (auto& kv : agg) {
+    if (!first) js += ",";
+    first = false;
+    js += "{\"name\":\"" + kv.first + "\",\"count\":" + std::to_string(kv.second.second) + ",\"total_ms\":" +
+          std::to_string(kv.second.first) + "}";
+  }
+  js += "]";
+  if (buf != nullptr && capacity > 0) {
+    const size_t n = js.size() < (size_t)capacity - 1 ? js.size() : (size_t)capacity - 1;
+    memcpy(buf, js.data(), n);
+    buf[n] = 0;
+  }
+  return (int64_t)js.size() + 1;
 }
 
 int64_t advb_debug_stage(advb_handle* h, const char* stage, float* dst, int64_t capacity, int64_t dims[5],

@@ -533,7 +533,7 @@ int frontend_mass_blocks(int B, int T) { return B * cdiv(frontend_frames(T), 2 *
 
 int frontend_init_constants(float* twr, float* twi, cudaStream_t stream) {
   fe_twiddle_kernel<<<1, 256, 0, stream>>>(twr, twi);
-  ADVB_LAUNCH_OK();
+  ADVB_KERNEL_OK("fe_twiddle", stream);
   ADVB_CUDA_OK(cudaFuncSetAttribute(fe_power_db_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fe_fwd_smem()));
   ADVB_CUDA_OK(cudaFuncSetAttribute(fe_floor_dct_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fe_dct_smem()));
   ADVB_CUDA_OK(cudaFuncSetAttribute(fe_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fe_bwd_smem()));
@@ -542,7 +542,7 @@ int frontend_init_constants(float* twr, float* twi, cudaStream_t stream) {
 
 int frontend_prepare(const FrontendTables& tb, cudaStream_t stream) {
   fe_tables_kernel<<<1, 288, 0, stream>>>(tb.fb, tb.klo, tb.kcnt, tb.mlo, tb.mcnt);
-  ADVB_LAUNCH_OK();
+  ADVB_KERNEL_OK("fe_tables", stream);
   return 0;
 }
 
@@ -552,14 +552,14 @@ int frontend_forward(const FrontendTables& tb, const FrontendState& st, const fl
   const int F = frontend_frames(T);
   ADVB_CHECK(T >= 512, "clip shorter than one FFT frame");
   fe_reset_kernel<<<1, 1, 0, stream>>>(st);
-  ADVB_LAUNCH_OK();
+  ADVB_KERNEL_OK("fe_reset", stream);
   dim3 g1(cdiv(F, 2 * FE_WARPS), B);
   fe_power_db_kernel<<<g1, FE_THREADS, fe_fwd_smem(), stream>>>(x, T, F, tb, st, dB);
-  ADVB_LAUNCH_OK();
+  ADVB_KERNEL_OK("fe_power_db", stream);
   dim3 g2(cdiv(F, 16), B);
   fe_floor_dct_kernel<<<g2, 256, fe_dct_smem(), stream>>>(dB, F, tb, st, 80.0f, out, clip_stride, stride_f, stride_c,
                                                          offset);
-  ADVB_LAUNCH_OK();
+  ADVB_KERNEL_OK("fe_floor_dct", stream);
   return 0;
 }
 
@@ -570,14 +570,14 @@ int frontend_backward(const FrontendTables& tb, const FrontendState& st, const f
   dim3 g1(cdiv(F, 2 * FE_WARPS), B);
   fe_floor_mass_kernel<<<g1, FE_THREADS, 0, stream>>>(dB, F, tb, st, 80.0f, gcoef, g_clip_stride, g_stride_f,
                                                      g_stride_c, mass_partial);
-  ADVB_LAUNCH_OK();
+  ADVB_KERNEL_OK("fe_floor_mass", stream);
   fe_mass_reduce_kernel<<<1, 1024, 0, stream>>>(mass_partial, (int)(g1.x * g1.y), st);
-  ADVB_LAUNCH_OK();
+  ADVB_KERNEL_OK("fe_mass_reduce", stream);
   const int n_tiles = cdiv(T, TILE_S);
   dim3 g2(n_tiles, B);
   fe_bwd_kernel<<<g2, FE_THREADS, fe_bwd_smem(), stream>>>(x, T, F, tb, st, 80.0f, gcoef, g_clip_stride, g_stride_f,
                                                           g_stride_c, gx, n_tiles);
-  ADVB_LAUNCH_OK();
+  ADVB_KERNEL_OK("fe_bwd", stream);
   return 0;
 }
 

@@ -282,25 +282,25 @@ int rnn_init() {
 }
 
 int gemm(const float* A, const float* Bm, const float* bias, const float* Cadd, float* C, int M, int N, int K,
-         cudaStream_t stream) {
+         cudaStream_t stream, const char* tag) {
   dim3 grid(cdiv(N, 64), cdiv(M, 64));
   gemm_kernel<<<grid, 256, 0, stream>>>(A, Bm, bias, Cadd, C, M, N, K);
-  ADVB_LAUNCH_OK();
+  ADVB_KERNEL_OK(tag, stream);
   return 0;
 }
 
 int lstm_pack(const LstmWeights& w, const LstmPacked& p, cudaStream_t stream) {
   lstm_pack_kernel<<<64, 256, 0, stream>>>(w, p, 160);
-  ADVB_LAUNCH_OK();
+  ADVB_KERNEL_OK("lstm_pack", stream);
   return 0;
 }
 
 int blstm_forward(const LstmPacked& p, const float* x, float* gates, float* hout, float* cs, int B, int L,
                   cudaStream_t stream) {
-  ADVB_TRY(gemm(x, p.wihT, p.bias, nullptr, gates, B * L, 2 * G4, 160, stream));
+  ADVB_TRY(gemm(x, p.wihT, p.bias, nullptr, gates, B * L, 2 * G4, 160, stream, "lstm_inproj_fwd"));
   dim3 grid(cdiv(B, CL), 2);
   lstm_rec_fwd_kernel<<<grid, G4, lstm_rec_fwd_smem(), stream>>>(gates, p.whhT, hout, cs, B, L);
-  ADVB_LAUNCH_OK();
+  ADVB_KERNEL_OK("lstm_rec_fwd", stream);
   return 0;
 }
 
@@ -308,34 +308,34 @@ int blstm_backward(const LstmPacked& p, float* gates, const float* dout, const f
                    float* dx, int B, int L, cudaStream_t stream) {
   dim3 grid(cdiv(B, CL), 2);
   lstm_rec_bwd_kernel<<<grid, G4, lstm_rec_bwd_smem(), stream>>>(gates, p.whh, dout, cs, B, L);
-  ADVB_LAUNCH_OK();
-  ADVB_TRY(gemm(gates, p.wih_cat, nullptr, dx_add, dx, B * L, 160, 2 * G4, stream));
+  ADVB_KERNEL_OK("lstm_rec_bwd", stream);
+  ADVB_TRY(gemm(gates, p.wih_cat, nullptr, dx_add, dx, B * L, 160, 2 * G4, stream, "lstm_inproj_bwd"));
   return 0;
 }
 
 int feats_gather(const float* act, float* feats, int B, int L, int Wf, int C, cudaStream_t stream) {
   const int n = B * L * Wf * C;
   feats_gather_kernel<<<cdiv(n, 256), 256, 0, stream>>>(act, feats, n, Wf, C);
-  ADVB_LAUNCH_OK();
+  ADVB_KERNEL_OK("feats_gather", stream);
   return 0;
 }
 int feats_scatter(const float* gfeats, float* gact, int B, int L, int Wf, int C, cudaStream_t stream) {
   const int n = B * L * Wf * C;
   feats_scatter_kernel<<<cdiv(n, 256), 256, 0, stream>>>(gfeats, gact, n, Wf, C);
-  ADVB_LAUNCH_OK();
+  ADVB_KERNEL_OK("feats_scatter", stream);
   return 0;
 }
 
 int head_forward(const float* l2, const float* feats, const float* w, const float* bias, float* logits, int B, int L,
                  cudaStream_t stream) {
   head_fwd_kernel<<<B, 160, 0, stream>>>(l2, feats, w, bias, logits, L);
-  ADVB_LAUNCH_OK();
+  ADVB_KERNEL_OK("head_fwd", stream);
   return 0;
 }
 int head_backward(const float* logits, const long long* y, const float* w, float* dl2, int B, int L, int mode,
                   int n_global, cudaStream_t stream) {
   head_bwd_kernel<<<B, 160, 0, stream>>>(logits, y, w, dl2, L, mode, 1.0f / (float)n_global);
-  ADVB_LAUNCH_OK();
+  ADVB_KERNEL_OK("head_bwd", stream);
   return 0;
 }
 

@@ -20,7 +20,7 @@ struct LstmPacked {
 
 int rnn_init();
 int gemm(const float* A, const float* Bm, const float* bias, const float* Cadd, float* C, int M, int N, int K,
-         cudaStream_t stream);
+         cudaStream_t stream, const char* tag = "gemm");
 int lstm_pack(const LstmWeights& w, const LstmPacked& p, cudaStream_t stream);
 // x (B,L,160) -> hout (B,L,160); gates (B,L,640) and cs (B,L,2,80) are saved for backward
 int blstm_forward(const LstmPacked& p, const float* x, float* gates, float* hout, float* cs, int B, int L,

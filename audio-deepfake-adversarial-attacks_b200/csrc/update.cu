@@ -151,42 +151,42 @@ inline int ew_blocks(int64_t n) {
 
 int pgd_start(const float* x, const float* noise, float* adv, int64_t n, cudaStream_t stream) {
   pgd_start_kernel<<<ew_blocks(n), 256, 0, stream>>>(x, noise, adv, n);
-  ADVB_LAUNCH_OK();
+  ADVB_KERNEL_OK("pgd_start", stream);
   return 0;
 }
 int fgsm_step(const float* x, const float* g, float* adv, float eps, int64_t n, cudaStream_t stream) {
   fgsm_step_kernel<<<ew_blocks(n), 256, 0, stream>>>(x, g, adv, eps, n);
-  ADVB_LAUNCH_OK();
+  ADVB_KERNEL_OK("fgsm_step", stream);
   return 0;
 }
 int pgd_step(const float* x, const float* g, float* adv, float eps, float alpha, int64_t n, cudaStream_t stream) {
   pgd_step_kernel<<<ew_blocks(n), 256, 0, stream>>>(x, g, adv, eps, alpha, n);
-  ADVB_LAUNCH_OK();
+  ADVB_KERNEL_OK("pgd_step", stream);
   return 0;
 }
 int pgdl2_step(const float* x, const float* g, float* adv, float eps, float alpha, float eps_div, int B, int T,
                float* partial_g, float* partial_d, cudaStream_t stream) {
   dim3 grid(ROW_CHUNKS, B);
   row_sumsq_kernel<<<grid, 256, 0, stream>>>(g, partial_g, T);
-  ADVB_LAUNCH_OK();
+  ADVB_KERNEL_OK("row_sumsq", stream);
   pgdl2_ascent_kernel<<<grid, 256, 0, stream>>>(x, g, adv, partial_g, partial_d, alpha, eps_div, T);
-  ADVB_LAUNCH_OK();
+  ADVB_KERNEL_OK("pgdl2_ascent", stream);
   pgdl2_project_kernel<<<grid, 256, 0, stream>>>(x, adv, partial_d, eps, T);
-  ADVB_LAUNCH_OK();
+  ADVB_KERNEL_OK("pgdl2_project", stream);
   return 0;
 }
 int minmax_scale(const float* x, float* x01, float* mn, float* mx, int B, int T, cudaStream_t stream) {
   row_minmax_kernel<<<B, 1024, 0, stream>>>(x, mn, mx, T);
-  ADVB_LAUNCH_OK();
+  ADVB_KERNEL_OK("row_minmax", stream);
   dim3 grid(cdiv(T, 256 * 8), B);
   minmax_apply_kernel<<<grid, 256, 0, stream>>>(x, mn, mx, x01, T, 0);
-  ADVB_LAUNCH_OK();
+  ADVB_KERNEL_OK("minmax_apply", stream);
   return 0;
 }
 int minmax_revert(const float* x01, const float* mn, const float* mx, float* x, int B, int T, cudaStream_t stream) {
   dim3 grid(cdiv(T, 256 * 8), B);
   minmax_apply_kernel<<<grid, 256, 0, stream>>>(x01, mn, mx, x, T, 1);
-  ADVB_LAUNCH_OK();
+  ADVB_KERNEL_OK("minmax_revert", stream);
   return 0;
 }
 

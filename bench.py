@@ -1,0 +1,322 @@
+#!/usr/bin/env python
+"""Headline benchmark: adversarial clips/sec, PGD-40 (eps 1e-3) on LCNN+LFCC, 64 000-sample clips, batch 128/GPU.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl native|reference]
+
+A "step" = one attack call  atk(x, y)  on one batch (BASELINE.json configs[1]).  One process per GPU
+(`python -m torch.distributed.run --nproc-per-node N ... bench.py --gpus N`); clips are sharded over ranks with no
+data-path collective (weak scaling: 128 clips per GPU); NCCL is used for the timing max-reduction and the final
+gather of predicted labels only.  Prints ONE JSON line on rank 0.
+
+* value  : whole-job clips/s with the batch already resident in HBM (CUDA events around each attack call,
+           L2 flushed between calls, max over ranks).
+* e2e    : same metric through the public API with HOST buffers: pinned host batch -> device, attack, adversarial
+           batch -> pinned host, every step inside the timed region.
+* roofline: dominant kernel (by live CUDA-event time inside this run) against the measured HBM peak.
+* cpu_baseline / --impl reference: the oracle port of the reference's path (torch CPU ops, all host threads) on a
+           bounded sample of the same workload.  oracle/ is used here only as that reported baseline.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "audio-deepfake-adversarial-attacks_b200"))
+
+import torch  # noqa: E402
+
+T_SAMPLES = 64000
+EPS = 0.001
+PGD_STEPS = 40
+ALPHA = 2 / 255
+A_LCNN_BYTES_PER_CLIP = 40 * 15_818_544 + 768_000  # 633.5 MB per PGD-40 clip
+METRIC = "adversarial clips/sec (PGD-40, 64k-sample audio)"
+
+
+def measured_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return float(d["hbm_gbs"]), "measured"
+    return 6650.0, "fallback"
+
+
+def synthetic_batch(batch, seed):
+    """0.1*randn clips min-max scaled to [0,1], int64 labels."""
+    g = torch.Generator("cpu").manual_seed(seed)
+    raw = 0.1 * torch.randn(batch, T_SAMPLES, generator=g)
+    y = torch.randint(0, 2, (batch,), generator=g)
+    mn, mx = raw.min(dim=1, keepdim=True)[0], raw.max(dim=1, keepdim=True)[0]
+    return (raw - mn) / (mx - mn), y
+
+
+def build_lcnn_state():
+    from oracle import cases  # seeded init shared with the tests (weights only; no oracle arithmetic)
+
+    holder = cases.build_holder("lcnn", "lfcc", seed=42)
+    from oracle import synth
+
+    state = synth.randomize_norm_stats({k: v.detach().cpu().clone() for k, v in holder.state_dict().items()})
+    return holder, state
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled during the timed region (B200_PROFILING.md recipe)."""
+
+    def __init__(self, index):
+        self.rows, self.proc = [], None
+        q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={q}", "--format=csv,noheader,nounits", "-i",
+                                          str(index), "-lms", "200"], stdout=subprocess.PIPE, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.25)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm = sorted(int(r[0]) for r in self.rows if r and r[0].isdigit())
+        mx = [int(r[1]) for r in self.rows if len(r) > 1 and r[1].isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for i, n in enumerate(names) if any(len(r) > 2 + i and r[2 + i].lower() == "active" for r in self.rows)]
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": reasons,
+                "samples": len(sm)}
+
+
+def conv_kernel_bytes(B, F):
+    """Algorithmic HBM bytes per launch of each conv-block kernel: stage input read once + stage output written once
+    + side state at its packed size (3 bits per pooled output element, 1 bit otherwise) — the SURVEY.md App. D rule."""
+    spec = [(1, 64, True), (32, 64, False), (32, 96, True), (48, 96, False), (48, 128, True), (64, 128, False),
+            (64, 64, False), (32, 64, False), (32, 64, True)]
+    H, W, out = F, 80, {}
+    for i, (cin, cout, pool) in enumerate(spec):
+        Ho, Wo = (H // 2, W // 2) if pool else (H, W)
+        n_in, n_out = H * W * cin, Ho * Wo * (cout // 2)
+        side = n_out * (3 if pool else 1) / 8
+        per_clip = 4 * n_in + 4 * n_out + side
+        out[f"conv_fwd_b{i}"] = B * per_clip
+        out[f"conv_bwd_b{i}"] = B * per_clip
+        H, W = Ho, Wo
+    out["conv0_bwd"] = out.pop("conv_bwd_b0")
+    return out
+
+
+def cpu_port_clips_per_s(n_clips, n_steps, seed=1002):
+    """Oracle port of the reference path on the host cores: PGD-n_steps on n_clips clips, scaled to PGD-40."""
+    from oracle import attacks as oatk
+    from oracle import lcnn as olcnn
+
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    _, state = build_lcnn_state()
+    x, y = synthetic_batch(n_clips, seed)
+    g = torch.Generator("cpu").manual_seed(seed + 1)
+    noise = torch.empty_like(x).uniform_(-EPS, EPS, generator=g)
+    t0 = time.perf_counter()
+    oatk.pgd(lambda v: olcnn.forward(v, state), x, y, EPS, ALPHA, n_steps, noise=noise)
+    dt = time.perf_counter() - t0
+    return n_clips / (dt * PGD_STEPS / n_steps), dt, cores
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    n_clips, n_steps = 8, 10
+    for _ in range(args.warmup):
+        cpu_port_clips_per_s(n_clips, 2)
+    vals, t0 = [], time.perf_counter()
+    for _ in range(args.steps):
+        v, dt, cores = cpu_port_clips_per_s(n_clips, n_steps)
+        vals.append(v)
+    total = time.perf_counter() - t0
+    value = sum(vals) / len(vals)
+    sample = f"PGD-{n_steps} of the PGD-40 workload on {n_clips} clips per step, time x{PGD_STEPS // n_steps}"
+    print(json.dumps({
+        "impl": "reference", "metric": METRIC, "value": value, "unit": "clips/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * total / args.steps, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "PGD-40 Linf eps=0.001 on LCNN+LFCC, 64000-sample clips (BASELINE.json configs[1])",
+                   "note": "reference is pure Python/PyTorch and cannot travel to the GPU box; this arm times the oracle "
+                           "port (torch CPU ops) of its path on the host cores"},
+        "cpu_baseline": {"value": value, "unit": "clips/s", "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": "clips/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }))
+
+
+def run_native(args):
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    import torch.distributed as dist
+
+    if not torch.cuda.is_available():
+        raise RuntimeError("bench.py needs a CUDA device: the advb200 engine has no CPU path")
+    dev = torch.device("cuda", local)
+    torch.cuda.set_device(dev)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    from advb200 import torchattacks as ta
+    from advb200 import engine
+
+    B = args.batch
+    holder, state = build_lcnn_state()
+    holder.load_state_dict(state)
+    holder = holder.to(dev)
+    atk = ta.PGD(holder, eps=EPS, alpha=ALPHA, steps=PGD_STEPS, random_start=True)
+    atk.set_training_mode(model_training=True, batchnorm_training=False)
+    torch.manual_seed(2002 + rank)
+
+    x_host, y_host = synthetic_batch(B, 1002 + 17 * rank)
+    x_host, y_host = x_host.pin_memory(), y_host.pin_memory()
+    adv_host = torch.empty_like(x_host).pin_memory()
+    x_dev, y_dev = x_host.to(dev), y_host.to(dev)
+    flush = torch.empty(256 * 2**20 // 4, device=dev)  # 256 MiB > 126 MB L2
+    eng = engine.engine_for(holder, B, T_SAMPLES)
+
+    def barrier():
+        torch.cuda.synchronize(dev)
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    for _ in range(args.warmup):
+        atk(x_dev, y_dev)
+    barrier()
+
+    # ---- device-resident timed region ------------------------------------------------------------------------
+    sampler = ClockSampler(local) if rank == 0 else None
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    l0 = eng.launches
+    adv = None
+    for s, e in ev:
+        flush.fill_(1.0)
+        s.record()
+        adv = atk(x_dev, y_dev)
+        e.record()
+    barrier()
+    launches = eng.launches - l0
+    ms = sum(s.elapsed_time(e) for s, e in ev)
+    clocks = sampler.stop() if sampler else None
+
+    # ---- end-to-end: host buffers, copies inside the timed region ---------------------------------------------
+    barrier()
+    t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t0.record()
+    for _ in range(args.steps):
+        xd = x_host.to(dev, non_blocking=True)
+        yd = y_host.to(dev, non_blocking=True)
+        adv_host.copy_(atk(xd, yd), non_blocking=True)
+    t1.record()
+    barrier()
+    ms_e2e = t0.elapsed_time(t1)
+
+    tmax = torch.tensor([ms, ms_e2e], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+    ms, ms_e2e = tmax.tolist()
+
+    # ---- attack outcome (labels of the attacked batch), gathered over NCCL --------------------------------------
+    logits_clean = eng.forward(x_dev).flatten()
+    logits_adv = eng.forward(adv).flatten()
+    pred = torch.stack([(logits_clean > 0).long(), (logits_adv > 0).long(), y_dev], dim=1)
+    if world > 1:
+        parts = [torch.empty_like(pred) for _ in range(world)]
+        dist.all_gather(parts, pred)
+        pred = torch.cat(parts)
+    pred = pred.cpu()
+    linf = (adv - x_dev).abs().max().item()
+
+    out = None
+    if rank == 0:
+        # ---- live per-kernel timing of one more attack call -> roofline of the dominant kernel ------------------
+        eng.profile_begin()
+        atk(x_dev, y_dev)
+        prof = sorted(eng.profile_end(), key=lambda r: -r["total_ms"])
+        total_prof = sum(r["total_ms"] for r in prof)
+        top = prof[0]
+        peak, peak_kind = measured_peaks()
+        kb = conv_kernel_bytes(B, 1 + T_SAMPLES // 160)
+        traffic = None
+        tpath = os.path.join(ROOT, "profiles", "traffic.json")
+        if os.path.exists(tpath):
+            traffic = json.load(open(tpath)).get(top["name"])
+        avg_ms = top["total_ms"] / top["count"]
+        alg = kb.get(top["name"])
+        achieved = (alg / (avg_ms * 1e-3) / 1e9) if alg else None
+        n_clips = world * B * args.steps
+        value = n_clips / (ms * 1e-3)
+        out = {
+            "metric": METRIC, "value": value, "unit": "clips/s", "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": "PGD-40 Linf eps=0.001 alpha=2/255 random_start on LCNN+LFCC, 64000-sample clips "
+                                   "(BASELINE.json configs[1])",
+                       "batch_per_gpu": B, "global_batch": world * B, "parallelism": f"clip-shard x{world}",
+                       "l2": "256 MiB flush buffer written between timed calls; per-call working set "
+                             f"{eng.workspace_bytes / 2**30:.2f} GiB >> 126 MB L2",
+                       "weights": "seeded random init (torch.manual_seed(42)), randomised BN statistics"},
+            "e2e": {"value": n_clips / (ms_e2e * 1e-3), "unit": "clips/s", "h2d_bytes_per_step": B * T_SAMPLES * 4 + B * 8,
+                    "d2h_bytes_per_step": B * T_SAMPLES * 4},
+            "gpu_launches": int(launches),
+            "clocks": clocks,
+            "roofline": {"bound": "hbm", "kernel": top["name"], "achieved": achieved, "peak": peak, "unit": "GB/s",
+                         "frac": (achieved / peak) if achieved else None, "traffic": traffic,
+                         "peak_source": peak_kind, "avg_launch_ms": avg_ms,
+                         "share_of_step": top["total_ms"] / total_prof,
+                         "algorithmic_bytes_per_launch": alg},
+            "path_roofline": {"bound": "hbm", "achieved": value / world * A_LCNN_BYTES_PER_CLIP / 1e9, "peak": peak,
+                              "unit": "GB/s", "frac": value / world * A_LCNN_BYTES_PER_CLIP / 1e9 / peak,
+                              "bytes_per_clip": A_LCNN_BYTES_PER_CLIP},
+            "kernel_times_ms": {r["name"]: round(r["total_ms"], 3) for r in prof[:12]},
+            "attack": {"linf": linf, "clean_acc": float((pred[:, 0] == pred[:, 2]).float().mean()),
+                       "adv_acc": float((pred[:, 1] == pred[:, 2]).float().mean()),
+                       "flipped": int((pred[:, 0] != pred[:, 1]).sum()), "clips": int(pred.shape[0])},
+        }
+        if world == 1 and not args.no_cpu_baseline:
+            v, dt, cores = cpu_port_clips_per_s(16, 10)
+            out["cpu_baseline"] = {"value": v, "unit": "clips/s", "cores": cores, "kind": "port",
+                                   "sample": f"oracle port, PGD-10 of the PGD-40 workload on 16 clips ({dt:.1f} s), time x4"}
+        print(json.dumps(out), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+    return out
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="native", choices=["native", "reference"])
+    ap.add_argument("--batch", type=int, default=128)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_native(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -121,6 +121,12 @@ ADVB_API int advb_revert_minmax(const float* x01, const float* mn, const float* 
 ADVB_API int64_t advb_debug_stage(advb_handle* h, const char* stage, float* dst, int64_t capacity, int64_t dims[5],
                          void* cuda_stream);
 
+/* Live per-kernel timing for bench.py's roofline: between begin and end an event is recorded after every launch
+ * on the call's stream; end() synchronises and writes a JSON array [{"name","count","total_ms"}, ...] into buf
+ * (NUL-terminated, truncated to capacity) and returns the size needed. */
+ADVB_API int advb_profile_begin(advb_handle* h, void* cuda_stream);
+ADVB_API int64_t advb_profile_end(advb_handle* h, char* buf, int64_t capacity);
+
 /* Number of kernel launches issued by this handle since creation (bench.py's "gpu_launches"). */
 ADVB_API int64_t advb_launch_count(const advb_handle* h);
 

@@ -40,7 +40,8 @@ def build_state(model: str, frontend: str, seed: int = 42, calibrate_on=None, fo
     """Seeded state_dict with randomised BatchNorm statistics; optionally shift the output bias so that the clean
     logits of ``calibrate_on`` straddle zero (otherwise no label ever flips)."""
     holder = build_holder(model, frontend, seed)
-    state = {k: v.detach().clone() for k, v in holder.state_dict().items()}
+    # (.cpu(): the frontend singleton may have been moved to a GPU by an earlier model in this process)
+    state = {k: v.detach().cpu().clone() for k, v in holder.state_dict().items()}
     state = synth.randomize_norm_stats(state)
     if calibrate_on is not None:
         with torch.no_grad():

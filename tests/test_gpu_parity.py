@@ -1,0 +1,165 @@
+"""GPU: the CUDA path (through the C ABI) against the oracle and the reference-generated golden fixtures."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import attacks as oatk
+from oracle import cases
+from oracle import frontend as ofe
+from oracle.lcnn import BLOCKS
+
+import helpers
+
+pytestmark = pytest.mark.gpu
+
+
+def _setup(name, dev):
+    from advb200 import engine
+
+    case, x, y, holder, state, fwd = helpers.case_setup(name)
+    holder = helpers.load_holder_state(holder, state, dev)
+    eng = engine.engine_for(holder, x.shape[0], x.shape[1])
+    return case, x, y, holder, state, fwd, eng
+
+
+def _interior(t, p):
+    return t[:, p:t.shape[1] - p, p:t.shape[2] - p, :] if p > 0 else t
+
+
+@pytest.mark.parametrize("name", list(cases.CASES))
+def test_frontend_forward_backward(name, cuda_device):
+    case, x, y, holder, state, fwd, eng = _setup(name, cuda_device)
+    fb, dct, win, _ = ofe.tables_from_state(state)
+    xc = x.clone().requires_grad_(True)
+    want = ofe.cepstral_frontend(xc, fb, dct, win)
+    got = eng.frontend_fwd(x.to(cuda_device)).cpu()
+    # fp32 features of magnitude <= ~500: 1e-3 absolute (SURVEY.md App. A.1 measured 5e-4 between torch paths)
+    assert (got - want).abs().max().item() < 1e-3
+    np.testing.assert_allclose(got.numpy(), helpers.load_golden(name)["frontend"], atol=2e-3)
+    gc = torch.randn(want.shape, generator=torch.Generator("cpu").manual_seed(5))
+    (gx_want,) = torch.autograd.grad((want * gc).sum(), xc)
+    gx = eng.frontend_bwd(x.to(cuda_device), gc.to(cuda_device)).cpu()
+    if not case["silence"]:
+        assert helpers.rel_err(gx, gx_want) < 1e-5
+    else:  # floor active: clamp membership of borderline elements may differ by ulps (see test_oracle_golden)
+        assert helpers.cosine(gx, gx_want) > 0.999
+
+
+@pytest.mark.parametrize("name", list(cases.CASES)[:2])
+def test_every_stage_forward_and_backward(name, cuda_device):
+    case, x, y, holder, state, fwd, eng = _setup(name, cuda_device)
+    taps = {}
+    xc = x.clone().requires_grad_(True)
+    o = fwd(xc, state, taps)
+    for v in taps.values():
+        v.retain_grad()
+    torch.nn.functional.cross_entropy(torch.cat([-o, o], dim=1), y).backward()
+    g, logits = eng.grad(x.to(cuda_device), y.to(cuda_device))
+    B = x.shape[0]
+    tol = 2e-5 if not case["silence"] else 2e-2
+    assert (logits.cpu() - o.detach()).abs().max().item() < 2e-6
+    for i, (idx, _, _) in enumerate(BLOCKS):
+        t, p = eng.debug_stage(f"block{i}")
+        assert helpers.rel_err(_interior(t, p)[:B].permute(0, 3, 1, 2).cpu(), taps[f"block{idx}"].detach()) < 1e-5, i
+        t, _ = eng.debug_stage(f"gblock{i}")
+        assert helpers.rel_err(t[:B].permute(0, 3, 1, 2).cpu(), taps[f"block{idx}"].grad) < tol, i
+    for nm in ("feats", "lstm1", "lstm2"):
+        t, _ = eng.debug_stage(nm)
+        assert helpers.rel_err(t[:B, :, 0, :].cpu(), taps[nm].detach()) < 1e-5, nm
+    assert helpers.rel_err(g.cpu(), xc.grad) < tol
+    assert helpers.rel_err(g.cpu(), torch.from_numpy(helpers.load_golden(name)["grad"])) < tol
+
+
+@pytest.mark.parametrize("name", list(cases.CASES))
+def test_logits_and_gradient_against_reference_golden(name, cuda_device):
+    case, x, y, holder, state, fwd, eng = _setup(name, cuda_device)
+    g = helpers.load_golden(name)
+    grad, logits = eng.grad(x.to(cuda_device), y.to(cuda_device))
+    np.testing.assert_allclose(logits.cpu().numpy(), g["logits"], atol=3e-6)
+    ref = torch.from_numpy(g["grad"])
+    if not case["silence"]:
+        assert helpers.rel_err(grad.cpu(), ref) < 2e-5
+        assert (torch.sign(grad.cpu()) == torch.sign(ref)).float().mean().item() > 0.9995
+    else:
+        assert helpers.cosine(grad.cpu(), ref) > 0.999
+    # holder(x) is the drop-in model call: same logits
+    np.testing.assert_allclose(holder(x.to(cuda_device)).cpu().numpy(), g["logits"], atol=3e-6)
+
+
+@pytest.mark.parametrize("name", list(cases.CASES)[:2])
+@pytest.mark.parametrize("attack", ["fgsm", "pgd", "pgdl2"])
+def test_attacks_against_oracle_and_golden(name, attack, cuda_device):
+    from advb200 import torchattacks as ta
+
+    case, x, y, holder, state, fwd, eng = _setup(name, cuda_device)
+    g = helpers.load_golden(name)
+    p = cases.ATTACKS[attack]
+    xd, yd = x.to(cuda_device), y.to(cuda_device)
+    if attack == "fgsm":
+        atk = ta.FGSM(holder, eps=p["eps"])
+        atk.set_training_mode(True, False)
+        got = atk(xd, yd)
+    elif attack == "pgd":
+        atk = ta.PGD(holder, eps=p["eps"], alpha=p["alpha"], steps=p["steps"])
+        atk.set_training_mode(True, False)
+        got = atk.forward(xd, yd, noise=helpers.reference_start(case, "pgd", x, p["eps"]).to(cuda_device))
+    else:
+        atk = ta.PGDL2(holder, eps=p["eps"], alpha=p["alpha"], steps=p["steps"])
+        atk.set_training_mode(True, False)
+        got = atk.forward(xd, yd, delta=helpers.reference_start(case, "pgdl2", x, p["eps"]).to(cuda_device))
+    assert got.data_ptr() != xd.data_ptr() and torch.equal(xd.cpu(), x), "inputs must not be mutated"
+    got = got.cpu()
+    assert got.min().item() >= 0.0 and got.max().item() <= 1.0
+    d = got - x
+    # the attack's own perturbation norm within 1e-5 of the reference (north-star tolerance)
+    if attack == "pgdl2":
+        np.testing.assert_allclose(d.norm(p=2, dim=1).numpy(), g["pgdl2_delta_l2"], rtol=1e-5, atol=1e-5)
+    else:
+        np.testing.assert_allclose(d.abs().amax(dim=1).numpy(), g[f"{attack}_delta_linf"], atol=1e-5)
+        np.testing.assert_allclose(d.norm(p=2, dim=1).numpy(), g[f"{attack}_delta_l2"], rtol=1e-5, atol=1e-5)
+    want = helpers.oracle_attack(name, attack, x, y, state, fwd, case)
+    ref = torch.from_numpy(g[f"{attack}_adv"])
+    if not case["silence"]:
+        if attack == "pgdl2":
+            assert (got - want).abs().max().item() < 5e-4 and (got - ref).abs().max().item() < 5e-4
+        else:  # sign steps: identical up to gradient-sign ties
+            assert (got != want).float().mean().item() < 2e-3 and (got != ref).float().mean().item() < 2e-3
+    # predicted labels of the attacked batch: bit-exact with the reference
+    la = eng.forward(got.to(cuda_device)).cpu().numpy()
+    assert np.array_equal(la > 0, g[f"{attack}_logits_adv"] > 0)
+
+
+def test_minmax_roundtrip_and_edge_cases(cuda_device):
+    from advb200 import engine
+
+    raw = 0.1 * torch.randn(5, 16000, generator=torch.Generator("cpu").manual_seed(3))
+    x01, mn, mx = engine.to_minmax(raw.to(cuda_device))
+    w01, wmn, wmx = oatk.to_minmax(raw)
+    assert torch.equal(x01.cpu(), w01) and torch.equal(mn.cpu(), wmn) and torch.equal(mx.cpu(), wmx)
+    back = engine.revert_minmax(x01, mn, mx).cpu()
+    assert torch.equal(back, oatk.revert_minmax(w01, wmn, wmx))
+
+
+def test_handle_errors_are_loud(cuda_device):
+    from advb200 import engine
+
+    case, x, y, holder, state, fwd, eng = _setup("lcnn_lfcc_t16000", cuda_device)
+    with pytest.raises(ValueError):
+        eng.forward(torch.zeros(2, 8000, device=cuda_device))
+    with pytest.raises(RuntimeError, match="no CPU path"):
+        eng.forward(torch.zeros(2, 16000))
+    # batch grows -> handle is rebuilt, results unchanged for the first clips
+    xb = torch.cat([x, x], 0).to(cuda_device)
+    l4 = engine.engine_for(holder, 4, 16000).forward(xb).cpu()
+    assert torch.allclose(l4[:2], l4[2:], atol=0, rtol=0)
+
+
+def test_live_weights_are_reread(cuda_device):
+    """Adversarial training mutates the attacked model between calls (src/trainer.py:309-331)."""
+    case, x, y, holder, state, fwd, eng = _setup("lcnn_lfcc_t16000", cuda_device)
+    xd = x.to(cuda_device)
+    a = eng.forward(xd).cpu()
+    with torch.no_grad():
+        holder.m_output_act.bias += 0.25
+    b = eng.forward(xd).cpu()
+    assert torch.allclose(b - a, torch.full_like(a, 0.25), atol=1e-6)

@@ -1,0 +1,97 @@
+"""CPU: host-side logic, the C-ABI library surface, and the 'no CPU fallback' contract."""
+import ctypes
+import os
+import re
+
+import pytest
+import torch
+
+from oracle import cases
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_library_exports_every_declared_symbol():
+    from advb200 import _lib
+
+    header = open(os.path.join(ROOT, "include", "advb200.h")).read()
+    declared = set(re.findall(r"ADVB_API [\w\s\*]+?(advb_\w+)\(", header))
+    assert declared, "no prototypes parsed"
+    lib = _lib.load()
+    assert declared == set(_lib.SIGNATURES), declared ^ set(_lib.SIGNATURES)
+    for name in declared:
+        assert isinstance(getattr(lib, name), ctypes._CFuncPtr)
+    assert lib.advb_version() == 100
+
+
+def test_struct_layout_matches_header():
+    from advb200 import _lib
+
+    assert ctypes.sizeof(_lib.TensorRef) == 24
+    assert ctypes.sizeof(_lib.AttackDesc) == 12 * 4
+    assert ctypes.sizeof(_lib.ModelDesc) == 6 * 4 + 8
+
+
+def test_frontend_tables_match_torchaudio():
+    torchaudio = pytest.importorskip("torchaudio")
+    from advb200 import frontends
+
+    lf = torchaudio.transforms.LFCC(sample_rate=16000, n_lfcc=80,
+                                    speckwargs={"n_fft": 512, "win_length": 400, "hop_length": 160})
+    mf = torchaudio.transforms.MFCC(sample_rate=16000, n_mfcc=80,
+                                    melkwargs={"n_fft": 512, "win_length": 400, "hop_length": 160})
+    for ref, mine in ((lf, frontends.LFCC()), (mf, frontends.MFCC())):
+        a, b = ref.state_dict(), mine.state_dict()
+        assert list(a) == list(b)
+        for k in a:
+            assert torch.equal(a[k], b[k]), k
+
+
+def test_lcnn_holder_has_reference_state_dict_keys():
+    holder = cases.build_holder("lcnn", "lfcc")
+    keys = list(holder.state_dict())
+    assert "m_transform.6.weight" in keys and "m_transform.9.running_var" in keys
+    assert "m_before_pooling.1.l_blstm.weight_hh_l0_reverse" in keys and "frontend.filter_mat" in keys
+    assert sum(p.numel() for p in holder.parameters()) == 467425
+    assert type(holder).__name__ == "LCNN"
+
+
+def test_attack_api_surface_and_no_cpu_fallback():
+    from advb200 import aa
+    from advb200 import torchattacks as ta
+
+    holder = cases.build_holder("lcnn", "lfcc")
+    cls, params = aa.AttackEnum["PGD_eps001"].value
+    atk = cls(holder, **params)
+    assert (atk.eps, atk.steps, atk.alpha, atk.random_start, atk.attack) == (0.001, 10, 2 / 255, True, "PGD")
+    atk.set_training_mode(model_training=True, batchnorm_training=False)
+    assert "PGD(" in str(atk) and "eps=0.001" in str(atk)
+    x = torch.rand(2, 16000)
+    y = torch.tensor([0, 1])
+    for a in (atk, ta.FGSM(holder, eps=0.005), ta.PGDL2(holder, eps=0.1, steps=2)):
+        with pytest.raises(RuntimeError, match="no CPU path"):
+            a(x, y)
+    with pytest.raises(RuntimeError, match="no CPU path"):
+        holder(x)
+    with pytest.raises(NotImplementedError):
+        atk.set_training_mode(True, True)
+
+
+def test_install_swaps_reference_namespace():
+    import sys
+
+    import advb200
+    from advb200 import torchattacks as native
+
+    saved = {k: sys.modules.get(k) for k in ("adversarial_attacks", "adversarial_attacks.torchattacks")}
+    try:
+        advb200.install()
+        from adversarial_attacks import torchattacks  # the import line of src/aa/aa_types.py:2
+
+        assert torchattacks.PGD is native.PGD and torchattacks.FGSM is native.FGSM
+    finally:
+        for k, v in saved.items():
+            if v is None:
+                sys.modules.pop(k, None)
+            else:
+                sys.modules[k] = v

@@ -25,8 +25,8 @@ from oracle import frontend as ofe  # noqa: E402
 RESULTS = []
 
 
-def report(name, **kw):
-    rec = {"check": name}
+def report(check, **kw):
+    rec = {"check": check}
     rec.update({k: (float(v) if isinstance(v, (int, float)) or hasattr(v, "item") else v) for k, v in kw.items()})
     RESULTS.append(rec)
     print(json.dumps(rec), flush=True)
