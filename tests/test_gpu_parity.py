@@ -160,7 +160,13 @@ def test_attacks_against_oracle_and_golden(name, attack, cuda_device):
             assert (got != want).float().mean().item() < 2e-3 and (got != ref).float().mean().item() < 2e-3
     # predicted labels of the attacked batch: bit-exact with the reference
     la = eng.forward(got.to(cuda_device)).cpu().numpy()
-    assert np.array_equal(la > 0, g[f"{attack}_logits_adv"] > 0)
+    if not case["silence"]:
+        assert np.array_equal(la > 0, g[f"{attack}_logits_adv"] > 0)
+    # ... and at the reference's own adversarial batch the engine must reproduce the reference's logits (this also
+    # covers the silence case, whose gradient signs - hence adversarial samples - are chaotic in the oracle itself)
+    lr = eng.forward(ref.to(cuda_device)).cpu().numpy()
+    np.testing.assert_allclose(lr, g[f"{attack}_logits_adv"], atol=3e-6)
+    assert np.array_equal(lr > 0, g[f"{attack}_logits_adv"] > 0)
 
 
 def test_minmax_roundtrip_and_edge_cases(cuda_device):
