@@ -42,6 +42,7 @@ SIGNATURES = {
     "advb_create": (C.c_int, [C.POINTER(C.c_void_p), C.POINTER(ModelDesc)]),
     "advb_destroy": (None, [C.c_void_p]),
     "advb_workspace_bytes": (C.c_size_t, [C.c_void_p]),
+    "advb_set_option": (C.c_int, [C.c_void_p, C.c_char_p, C.c_int]),
     "advb_rebind": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(TensorRef)]),
     "advb_attack": (C.c_int, [C.c_void_p, C.POINTER(AttackDesc), C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
                               C.c_int, C.c_int, C.c_void_p]),

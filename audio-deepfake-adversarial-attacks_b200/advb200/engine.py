@@ -152,6 +152,10 @@ class Engine:
         B, H, W, Cc, p = [int(v) for v in dims]
         return buf.view(B, H + 2 * p, W + 2 * p, Cc), p
 
+    def set_option(self, key: str, value: int):
+        """``conv_path`` (0 tcgen05 / 1 fp32 SIMT), ``tf32_passes`` (3 = 3xTF32 / 1 = single pass)."""
+        _lib.check(self.lib.advb_set_option(self.handle, key.encode(), int(value)))
+
     def profile_begin(self):
         _lib.check(self.lib.advb_profile_begin(self.handle, self._stream()))
 

@@ -42,4 +42,16 @@ int conv_mfm_backward(ConvBwdArgs a, cudaStream_t stream);
 int conv0_backward(const float* gout, const unsigned char* codes, const float* w0, float* gin, int B, int H, int W,
                    int Ho, int Wo, cudaStream_t stream);
 
+// ---- tensor-core (tcgen05) path, conv_tc.cu ----
+bool conv_tc_supported(int Cin, int Cout, int KS, bool pool);
+size_t conv_tc_pack_bytes(int Cout, int Cin, int KS, bool bwd);
+// wf / wd: packed forward / backward weight slices (wd may be null)
+int conv_tc_pack(const float* w, unsigned char* wf, unsigned char* wd, int Cout, int Cin, int KS, cudaStream_t stream);
+// passes: 3 = 3xTF32 (fp32-class accuracy, default), 1 = single-pass tf32
+int conv_tc_forward(const ConvFwdArgs& a, const unsigned char* wpack, int passes, cudaStream_t stream);
+int conv_tc_backward(const ConvBwdArgs& a, const unsigned char* wpack, int passes, cudaStream_t stream);
+// first block backward on tensor cores: T (B,H,W,5) scratch, gin (B,H,W) = d loss / d cepstral image
+int conv0_tc_backward(const float* gout, const unsigned char* codes, const unsigned char* wpack, float* T, float* gin,
+                      int B, int H, int W, int Ho, int Wo, int passes, cudaStream_t stream);
+
 }  // namespace advb

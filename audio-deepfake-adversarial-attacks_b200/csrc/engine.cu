@@ -48,6 +48,9 @@ struct LcnnBlock {
   int H, W, Ho, Wo;    // conv (pre-pool) size, block output size
   float* wf = nullptr;  // packed forward weights
   float* wd = nullptr;  // packed backward weights
+  unsigned char* tcf = nullptr;  // tensor-core weight slices (forward / backward)
+  unsigned char* tcd = nullptr;
+  bool tc = false;
   float* invstd = nullptr;
   Act out{};             // block output (zero-bordered for the next conv)
   unsigned char* codes = nullptr;
@@ -66,6 +69,8 @@ struct advb_handle {
   Profiler prof;
   std::vector<void*> allocs;
   size_t ws_bytes = 0;
+  int conv_path = 0;    // 0 = tcgen05 tensor cores (default), 1 = fp32 SIMT cross-check path
+  int tf32_passes = 3;  // 3 = 3xTF32 (fp32-class accuracy), 1 = single-pass tf32
 
   // frontend
   float *twr = nullptr, *twi = nullptr, *dB = nullptr, *mass_partial = nullptr, *g_coef = nullptr;
@@ -82,6 +87,7 @@ struct advb_handle {
   LstmPacked lp[2]{};
 
   // attack scratch
+  float* conv0_T = nullptr;  // (B,F,80,5) horizontal col2im partial sums of the first block's backward
   float *grad = nullptr, *partial_g = nullptr, *partial_d = nullptr, *coef_tmp = nullptr;
 
   template <typename Tp>
@@ -236,9 +242,15 @@ int build_lcnn(advb_handle* h) {
     ADVB_TRY(h->alloc(&k.wf, wn));
     if (i > 0) ADVB_TRY(h->alloc(&k.wd, wn));
     if (k.bn_idx >= 0) ADVB_TRY(h->alloc(&k.invstd, k.Cout / 2));
+    k.tc = conv_tc_supported(k.Cin, k.Cout, k.KS, k.pool) && (128 * 4) / (k.W + 2 * (k.KS / 2)) >= 2;
+    if (k.tc) {
+      ADVB_TRY(h->alloc(&k.tcf, conv_tc_pack_bytes(k.Cout, k.Cin, k.KS, false)));
+      ADVB_TRY(h->alloc(&k.tcd, conv_tc_pack_bytes(k.Cout, k.Cin, k.KS, true)));
+    }
     H = k.Ho;
     W = k.Wo;
   }
+  ADVB_TRY(h->alloc(&h->conv0_T, (size_t)B * F * 80 * 5));
   h->L = H;
   h->Wf = W;
   ADVB_CHECK(h->Wf * 32 == 160, "LCNN feature width must be 160");
@@ -271,7 +283,10 @@ int prepare_lcnn(advb_handle* h, cudaStream_t st) {
   for (int i = 0; i < 9; ++i) {
     LcnnBlock& k = h->blk[i];
     const std::string p = "m_transform." + std::to_string(k.idx);
-    ADVB_TRY(conv_pack_weights(h->t(p + ".weight"), k.wf, k.wd, k.Cout, k.Cin, k.KS, st));
+    if (k.tc && h->conv_path == 0)
+      ADVB_TRY(conv_tc_pack(h->t(p + ".weight"), k.tcf, k.tcd, k.Cout, k.Cin, k.KS, st));
+    if (!(k.tc && h->conv_path == 0))
+      ADVB_TRY(conv_pack_weights(h->t(p + ".weight"), k.wf, k.wd, k.Cout, k.Cin, k.KS, st));
     if (k.bn_idx >= 0)
       ADVB_TRY(bn_prepare(h->t("m_transform." + std::to_string(k.bn_idx) + ".running_var"), k.invstd, k.Cout / 2, st));
   }
@@ -318,7 +333,8 @@ int lcnn_forward(advb_handle* h, const float* x, int B, cudaStream_t st) {
     a.Wo = k.Wo;
     a.pool = k.pool;
     a.tag = k.tag_f.c_str();
-    ADVB_TRY(conv_mfm_forward(a, st));
+    if (k.tc && h->conv_path == 0) ADVB_TRY(conv_tc_forward(a, k.tcf, h->tf32_passes, st));
+    else ADVB_TRY(conv_mfm_forward(a, st));
     in = k.out.p;
     in_pad = k.out.pad;
   }
@@ -356,10 +372,15 @@ int lcnn_backward(advb_handle* h, const float* x, const int64_t* y, int B, int m
     a.Wo = k.Wo;
     a.pool = k.pool;
     a.tag = k.tag_b.c_str();
-    ADVB_TRY(conv_mfm_backward(a, st));
+    if (k.tc && h->conv_path == 0) ADVB_TRY(conv_tc_backward(a, k.tcd, h->tf32_passes, st));
+    else ADVB_TRY(conv_mfm_backward(a, st));
   }
   const LcnnBlock& k0 = h->blk[0];
-  ADVB_TRY(conv0_backward(k0.gout, k0.codes, h->t("m_transform.0.weight"), h->g_coef, B, k0.H, k0.W, k0.Ho, k0.Wo, st));
+  if (k0.tc && h->conv_path == 0)
+    ADVB_TRY(conv0_tc_backward(k0.gout, k0.codes, k0.tcd, h->conv0_T, h->g_coef, B, k0.H, k0.W, k0.Ho, k0.Wo,
+                               h->tf32_passes, st));
+  else
+    ADVB_TRY(conv0_backward(k0.gout, k0.codes, h->t("m_transform.0.weight"), h->g_coef, B, k0.H, k0.W, k0.Ho, k0.Wo, st));
   ADVB_TRY(frontend_backward(h->ftb, h->fst, x, B, h->T, h->dB, h->g_coef, (long long)h->F * 80, 80, 1,
                              h->mass_partial, gx, st));
   return 0;
@@ -462,6 +483,22 @@ void advb_destroy(advb_handle* h) {
 
 size_t advb_workspace_bytes(const advb_handle* h) { return h ? h->ws_bytes : 0; }
 int64_t advb_launch_count(const advb_handle* h) { return h ? h->counter.n : 0; }
+
+int advb_set_option(advb_handle* h, const char* key, int value) {
+  ADVB_CHECK(h != nullptr && key != nullptr, "null argument");
+  const std::string k(key);
+  if (k == "conv_path") {
+    ADVB_CHECK(value == 0 || value == 1, "conv_path: 0 = tcgen05, 1 = fp32 SIMT");
+    h->conv_path = value;
+  } else if (k == "tf32_passes") {
+    ADVB_CHECK(value == 1 || value == 3, "tf32_passes: 3 = 3xTF32, 1 = single pass");
+    h->tf32_passes = value;
+  } else {
+    set_error("unknown option '" + k + "'");
+    return 1;
+  }
+  return 0;
+}
 
 int advb_rebind(advb_handle* h, int n_tensors, const advb_tensor_ref* tensors) {
   ADVB_CHECK(h != nullptr, "null handle");

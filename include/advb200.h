@@ -83,6 +83,11 @@ ADVB_API size_t advb_workspace_bytes(const advb_handle* h);
 /* Re-point the borrowed tensors (same names/sizes) without reallocating the workspace. */
 ADVB_API int advb_rebind(advb_handle* h, int n_tensors, const advb_tensor_ref* tensors);
 
+/* Engine options (no reference counterpart; the reference's knobs are torch-global):
+ *   "conv_path"   0 = tcgen05 tensor-core convolutions (default), 1 = fp32 SIMT convolutions (cross-check)
+ *   "tf32_passes" 3 = 3xTF32 error-compensated products, fp32-class accuracy (default), 1 = single-pass tf32 */
+ADVB_API int advb_set_option(advb_handle* h, const char* key, int value);
+
 /* Replaces  atk(images, labels)  = Attack.__call__ -> {FGSM,PGD,PGDL2,FAB,CW}.forward
  * (attack.py:308-331; fgsm.py:33-62; pgd.py:40-78; pgdl2.py:40-90; fab.py:70-78; cw.py:46-112), called from
  * evaluate_models_on_adversarial_attacks.py:220 and src/trainer.py:426,470,492,511,539.

@@ -1,0 +1,42 @@
+"""One forward+backward (advb_grad) of LCNN+LFCC at the bench shape, for ncu captures (diagnostic tool).
+
+    ncu --set full --clock-control none --import-source on -k regex:conv_tc -s 16 -c 16 -o gpurun_out/prof \
+        python tools/profile_grad.py [--batch 128] [--calls 2]
+"""
+import argparse
+import os
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "audio-deepfake-adversarial-attacks_b200"))
+
+import torch  # noqa: E402
+
+import bench  # noqa: E402
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--batch", type=int, default=128)
+    ap.add_argument("--calls", type=int, default=2)
+    ap.add_argument("--conv-path", type=int, default=0)
+    args = ap.parse_args()
+    from advb200 import engine
+
+    dev = torch.device("cuda:0")
+    holder, state = bench.build_lcnn_state()
+    holder.load_state_dict(state)
+    holder = holder.to(dev)
+    x, y = bench.synthetic_batch(args.batch, 1002)
+    x, y = x.to(dev), y.to(dev)
+    eng = engine.engine_for(holder, args.batch, bench.T_SAMPLES)
+    eng.set_option("conv_path", args.conv_path)
+    for _ in range(args.calls):
+        g, logits = eng.grad(x, y)
+    torch.cuda.synchronize()
+    print("grad norm", g.norm().item(), "logit mean", logits.mean().item())
+
+
+if __name__ == "__main__":
+    main()
