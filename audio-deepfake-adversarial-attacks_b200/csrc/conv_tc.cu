@@ -32,7 +32,9 @@ namespace {
 using namespace tc;
 
 constexpr int TC_THREADS = 256;
-constexpr int NM_MAX = 4;  // M-tiles (128 pixels each) per CTA
+// NM = M-tiles (128 pixels each) per CTA is a template parameter: 4 for the weight-heavy 3x3 layers (each weight
+// slice streamed from L2 is reused by 512 pixels; one CTA per SM), 2 for the light layers (first block, 1x1
+// convolutions), whose <= 113 KB footprint lets two CTAs share an SM and hide each other's fill / epilogue.
 
 __host__ __device__ constexpr int pow2_ceil(int v) {
   int p = 32;
@@ -40,10 +42,10 @@ __host__ __device__ constexpr int pow2_ceil(int v) {
   return p;
 }
 
-template <int NOUT>
+template <int NOUT, int NM>
 struct TcCfg {
   static constexpr int NSTRIDE = pow2_ceil(NOUT);         // TMEM columns reserved per M-tile accumulator
-  static constexpr int TMEM_COLS = NM_MAX * NSTRIDE;      // 128 .. 512 (power of two)
+  static constexpr int TMEM_COLS = pow2_ceil(NM * NSTRIDE);  // 32 .. 512 (power of two)
   static constexpr int SLICE_BYTES = 2 * NOUT * 128;      // hi + lo image of one (chunk, tap) weight slice
   static constexpr int NST = SLICE_BYTES <= 8192 ? 4 : 2;  // ring depth
 };
@@ -118,9 +120,10 @@ __device__ __forceinline__ float4 load_item(const TcArgs& a, int b, int q, int c
 }
 
 // KS: filter size; KTOT: contraction channels per tap (fwd: Cin, bwd: Cout); NOUT: GEMM N (fwd: Cout, bwd: Cin).
-template <int KS, int KTOT, int NOUT, bool POOL, bool BWD, bool IM2COL = false>
-__global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(TcArgs a) {
-  using Cfg = TcCfg<NOUT>;
+template <int KS, int KTOT, int NOUT, bool POOL, bool BWD, bool IM2COL = false, int NM = 4>
+__global__ void __launch_bounds__(TC_THREADS, NM <= 2 ? 2 : 1) conv_tc_kernel(TcArgs a) {
+  using Cfg = TcCfg<NOUT, NM>;
+  constexpr int NM_MAX = NM;
   constexpr int PC = KS / 2, NTAP = KS * KS, NKC = (KTOT + 31) / 32;
   constexpr int NSLICE = NKC * NTAP;
   constexpr int NST = Cfg::NST;
@@ -431,9 +434,9 @@ struct TcPlan {
   size_t smem;
 };
 
-template <int NOUT>
+template <int NOUT, int NM_MAX>
 TcPlan make_plan(int H, int W, int Ho, int KS, bool pool, bool bwd) {
-  using Cfg = TcCfg<NOUT>;
+  using Cfg = TcCfg<NOUT, NM_MAX>;
   const int pc = KS / 2, Wp = W + 2 * pc;
   const int Heff = (!bwd && pool) ? 2 * Ho : H;
   const bool even = !bwd && pool;
@@ -456,13 +459,13 @@ TcPlan make_plan(int H, int W, int Ho, int KS, bool pool, bool bwd) {
   return p;
 }
 
-template <int KS, int KTOT, int NOUT, bool POOL, bool BWD, bool IM2COL = false>
+template <int KS, int KTOT, int NOUT, bool POOL, bool BWD, bool IM2COL = false, int NM = 4>
 int launch_tc(TcArgs a, const char* tag, cudaStream_t stream) {
-  const TcPlan p = make_plan<NOUT>(a.H, a.W, a.Ho, KS, POOL, BWD);
+  const TcPlan p = make_plan<NOUT, NM>(a.H, a.W, a.Ho, KS, POOL, BWD);
   ADVB_CHECK(p.tiles > 0 && p.smem <= 227 * 1024, "tensor-core conv tile does not fit (image too wide)");
   a.R = p.R;
   a.band_rows = p.band_rows;
-  auto kern = conv_tc_kernel<KS, KTOT, NOUT, POOL, BWD, IM2COL>;
+  auto kern = conv_tc_kernel<KS, KTOT, NOUT, POOL, BWD, IM2COL, NM>;
   ADVB_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.smem));
   dim3 grid(p.tiles, a.B);
   kern<<<grid, TC_THREADS, p.smem, stream>>>(a);
@@ -517,7 +520,7 @@ int conv_tc_forward(const ConvFwdArgs& f, const unsigned char* wpack, int passes
     a.in = f.in, a.out = f.out, a.out_pad = f.out_pad, a.codes = f.codes, a.bias = f.bias;
     a.bn_mean = f.bn_mean, a.bn_invstd = f.bn_invstd;
     a.passes = passes;
-    return launch_tc<1, 32, 64, true, false, true>(a, f.tag, stream);
+    return launch_tc<1, 32, 64, true, false, true, 2>(a, f.tag, stream);
   }
   a.B = f.B, a.H = f.H, a.W = f.W, a.Ho = f.Ho, a.Wo = f.Wo;
   a.wpack = wpack;
@@ -526,7 +529,7 @@ int conv_tc_forward(const ConvFwdArgs& f, const unsigned char* wpack, int passes
   a.passes = passes;
 #define ADVB_TCF(KS_, CI_, CO_, POOL_)                                             \
   if (f.KS == KS_ && f.Cin == CI_ && f.Cout == CO_ && f.pool == POOL_)             \
-  return launch_tc<KS_, CI_, CO_, POOL_, false>(a, f.tag, stream)
+  return launch_tc<KS_, CI_, CO_, POOL_, false, false, (KS_ == 1 ? 2 : 4)>(a, f.tag, stream)
   ADVB_TCF(1, 32, 64, false);
   ADVB_TCF(1, 48, 96, false);
   ADVB_TCF(1, 64, 128, false);
@@ -560,7 +563,7 @@ int conv0_tc_backward(const float* gout, const unsigned char* codes, const unsig
   a.wpack = wpack;
   a.gout = gout, a.codes_in = codes, a.gin = T, a.bn_invstd = nullptr;
   a.passes = passes;
-  ADVB_TRY((launch_tc<1, 64, 32, true, true, true>(a, "conv0_bwd_gemm", stream)));
+  ADVB_TRY((launch_tc<1, 64, 32, true, true, true, 2>(a, "conv0_bwd_gemm", stream)));
   const int n = B * H * W;
   conv0_col2im_rows_kernel<<<cdiv(n, 256), 256, 0, stream>>>(T, gin, H, W, n);
   ADVB_KERNEL_OK("conv0_bwd_rows", stream);
@@ -575,7 +578,7 @@ int conv_tc_backward(const ConvBwdArgs& g, const unsigned char* wpack, int passe
   a.passes = passes;
 #define ADVB_TCB(KS_, CI_, CO_, POOL_)                                             \
   if (g.KS == KS_ && g.Cin == CI_ && g.Cout == CO_ && g.pool == POOL_)             \
-  return launch_tc<KS_, CO_, CI_, POOL_, true>(a, g.tag, stream)
+  return launch_tc<KS_, CO_, CI_, POOL_, true, false, (KS_ == 1 ? 2 : 4)>(a, g.tag, stream)
   ADVB_TCB(1, 32, 64, false);
   ADVB_TCB(1, 48, 96, false);
   ADVB_TCB(1, 64, 128, false);

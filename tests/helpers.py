@@ -60,3 +60,23 @@ def cosine(a, b):
 def load_holder_state(holder, state, device):
     holder.load_state_dict(state)
     return holder.to(device)
+
+
+def trimmed_rel_err(a, b, drop=0.10):
+    """Relative L2 error after dropping the `drop` fraction of elements with the largest absolute error.
+
+    A max-pool / Max-Feature-Map winner decided by a ~1e-7 margin may legitimately differ between two correct fp32
+    implementations (different summation order); one such flip re-routes the gradient of a small receptive field.
+    The trimmed error ignores those isolated patches and stays tight everywhere else."""
+    a, b = a.double().flatten(), b.double().flatten()
+    d = (a - b).abs()
+    k = int(d.numel() * (1.0 - drop))
+    keep = torch.topk(d, k, largest=False).indices
+    return (d[keep].norm() / b[keep].norm().clamp_min(1e-30)).item()
+
+
+def grads_agree(g, ref, tight=2e-5):
+    """Gradient parity robust to isolated arg-max flips: tight on >= 90 % of the elements, same direction and signs
+    overall."""
+    return (trimmed_rel_err(g, ref) < tight and cosine(g, ref) > 0.9995
+            and (torch.sign(g) == torch.sign(ref)).float().mean().item() > 0.998)
