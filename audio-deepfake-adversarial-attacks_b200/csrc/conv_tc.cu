@@ -241,18 +241,20 @@ __global__ void __launch_bounds__(TC_THREADS, NM <= 2 ? 2 : 1) conv_tc_kernel(Tc
 #pragma unroll 1
         for (int ks = 0; ks < kvalid / 8; ++ks) {
           const uint64_t bh = desc_sw128(w_hi + ks * 32), bl = desc_sw128(w_lo + ks * 32);
-#pragma unroll 1
-          for (int p = 0; p < a.passes; ++p) {
-            const uint32_t abase = (p == 2 ? a_lo_addr : a_hi_addr) + row_off + ks * 32;
-            const uint64_t bd = (p == 1) ? bl : bh;
-            const uint32_t acc = (sl > 0 || ks > 0 || p > 0) ? 1u : 0u;
-            uint64_t ad = desc_sw128(abase);
-            uint32_t dcol = tmem;
-#pragma unroll 1
-            for (int m = 0; m < nM; ++m) {
-              if (leader) mma_tf32(dcol, ad, bd, IDESC, acc);
-              ad += (128 * 128) >> 4;  // next M-tile: 128 rows further down the band
-              dcol += Cfg::NSTRIDE;
+          const uint64_t ah = desc_sw128(a_hi_addr + row_off + ks * 32), al = desc_sw128(a_lo_addr + row_off + ks * 32);
+          const uint32_t acc0 = (sl > 0 || ks > 0) ? 1u : 0u;
+          // fully unrolled over (pass, M-tile): the operand moves to uniform registers batch up ahead of a run of
+          // back-to-back UTCHMMAs instead of serialising with each one
+#pragma unroll
+          for (int m = 0; m < NM; ++m) {
+            if (m < nM && leader) {
+              const uint32_t dcol = tmem + m * Cfg::NSTRIDE;
+              const uint64_t moff = (uint64_t)(m * ((128 * 128) >> 4));
+              mma_tf32(dcol, ah + moff, bh, IDESC, acc0);
+              if (a.passes == 3) {
+                mma_tf32(dcol, ah + moff, bl, IDESC, 1u);
+                mma_tf32(dcol, al + moff, bh, IDESC, 1u);
+              }
             }
           }
         }
