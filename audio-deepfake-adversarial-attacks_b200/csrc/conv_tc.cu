@@ -47,7 +47,8 @@ struct TcCfg {
   static constexpr int NSTRIDE = pow2_ceil(NOUT);         // TMEM columns reserved per M-tile accumulator
   static constexpr int TMEM_COLS = pow2_ceil(NM * NSTRIDE);  // 32 .. 512 (power of two)
   static constexpr int SLICE_BYTES = 2 * NOUT * 128;      // hi + lo image of one (chunk, tap) weight slice
-  static constexpr int NST = SLICE_BYTES <= 8192 ? 4 : 2;  // ring depth
+  // ring depth: deeper for small slices, but never so deep that an NM = 2 kernel loses its second CTA per SM
+  static constexpr int NST = (SLICE_BYTES <= 8192 && NM > 2) ? 4 : 2;
 };
 
 struct TcArgs {
@@ -580,7 +581,7 @@ int conv_tc_backward(const ConvBwdArgs& g, const unsigned char* wpack, int passe
   a.passes = passes;
 #define ADVB_TCB(KS_, CI_, CO_, POOL_)                                             \
   if (g.KS == KS_ && g.Cin == CI_ && g.Cout == CO_ && g.pool == POOL_)             \
-  return launch_tc<KS_, CO_, CI_, POOL_, true, false, (KS_ == 1 ? 2 : 4)>(a, g.tag, stream)
+  return launch_tc<KS_, CO_, CI_, POOL_, true, false, 2>(a, g.tag, stream)
   ADVB_TCB(1, 32, 64, false);
   ADVB_TCB(1, 48, 96, false);
   ADVB_TCB(1, 64, 128, false);

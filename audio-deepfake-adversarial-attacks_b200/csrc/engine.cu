@@ -243,7 +243,7 @@ int build_lcnn(advb_handle* h) {
     if (i > 0) ADVB_TRY(h->alloc(&k.wd, wn));
     if (k.bn_idx >= 0) ADVB_TRY(h->alloc(&k.invstd, k.Cout / 2));
     k.tc = conv_tc_supported(k.Cin, k.Cout, k.KS, k.pool) &&
-           (k.KS == 3 ? (128 * 4) / (k.W + 2) : (128 * 2) / k.W) >= 2;  // a CTA tile must hold >= 2 image rows
+           (128 * 2) / (k.W + 2 * (k.KS / 2 == 2 ? 0 : k.KS / 2)) >= 2;  // the smallest CTA tile (2 M-tiles) must hold >= 2 image rows
     if (k.tc) {
       ADVB_TRY(h->alloc(&k.tcf, conv_tc_pack_bytes(k.Cout, k.Cin, k.KS, false)));
       ADVB_TRY(h->alloc(&k.tcd, conv_tc_pack_bytes(k.Cout, k.Cin, k.KS, true)));

@@ -35,6 +35,8 @@ constexpr int NFILT = 128;
 constexpr int NCOEF = 80;
 constexpr int FE_WARPS = 8;
 constexpr int FE_THREADS = FE_WARPS * 32;
+constexpr int FB_WARPS = 10;     // backward: an interior tile of 16 hops needs 19-20 frames = 10 frame pairs = one round
+constexpr int FB_THREADS = FB_WARPS * 32;
 constexpr int PSTRIDE = 260;     // padded 257
 constexpr int DCT_LD = 81;       // padded row of the dct matrix in shared memory (bank spread for row-parallel reads)
 constexpr int TILE_HOPS = 16;    // backward tile = 16 hops = 2560 samples
@@ -352,7 +354,7 @@ __global__ void __launch_bounds__(1024) fe_mass_reduce_kernel(const float* __res
 
 // ---------------------------------------------------------------------------------------------------
 // Backward: d coefficients -> d waveform for one tile of TILE_S samples of one clip.
-__global__ void __launch_bounds__(FE_THREADS) fe_bwd_kernel(const float* __restrict__ x, int T, int F,
+__global__ void __launch_bounds__(FB_THREADS) fe_bwd_kernel(const float* __restrict__ x, int T, int F,
                                                              FrontendTables tb, FrontendState st, float top_db,
                                                              const float* __restrict__ gcoef, long long g_clip_stride,
                                                              long long g_stride_f, long long g_stride_c,
@@ -362,18 +364,18 @@ __global__ void __launch_bounds__(FE_THREADS) fe_bwd_kernel(const float* __restr
   float* s_twi = s_twr + 256;                   // 256
   float* s_win = s_twi + 256;                   // 400
   float* s_dct = s_win + 400;                   // 128*81
-  float* s_fft = s_dct + NFILT * DCT_LD;        // FE_WARPS * 2048 (Z and H buffers)
-  float* s_pw = s_fft + FE_WARPS * 2048;        // FE_WARPS * 2 * PSTRIDE  (power, then d power)
-  float* s_ge = s_pw + FE_WARPS * 2 * PSTRIDE;  // FE_WARPS * 2 * 128       (d energy)
-  float* s_gc = s_ge + FE_WARPS * 2 * NFILT;    // FE_WARPS * 2 * 80        (d coefficients)
-  float* s_yw = s_gc + FE_WARPS * 2 * NCOEF;    // NF_MAX * 400             (windowed frame gradients)
+  float* s_fft = s_dct + NFILT * DCT_LD;        // FB_WARPS * 2048 (Z and H buffers)
+  float* s_pw = s_fft + FB_WARPS * 2048;        // FB_WARPS * 2 * PSTRIDE  (power, then d power)
+  float* s_ge = s_pw + FB_WARPS * 2 * PSTRIDE;  // FB_WARPS * 2 * 128       (d energy)
+  float* s_gc = s_ge + FB_WARPS * 2 * NFILT;    // FB_WARPS * 2 * 80        (d coefficients)
+  float* s_yw = s_gc + FB_WARPS * 2 * NCOEF;    // NF_MAX * 400             (windowed frame gradients)
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  for (int i = tid; i < 256; i += FE_THREADS) {
+  for (int i = tid; i < 256; i += FB_THREADS) {
     s_twr[i] = tb.twr[i];
     s_twi[i] = tb.twi[i];
   }
-  for (int i = tid; i < WIN; i += FE_THREADS) s_win[i] = tb.window[i];
-  for (int i = tid; i < NFILT * NCOEF; i += FE_THREADS) s_dct[(i / NCOEF) * DCT_LD + (i % NCOEF)] = tb.dct[i];
+  for (int i = tid; i < WIN; i += FB_THREADS) s_win[i] = tb.window[i];
+  for (int i = tid; i < NFILT * NCOEF; i += FB_THREADS) s_dct[(i / NCOEF) * DCT_LD + (i % NCOEF)] = tb.dct[i];
   __syncthreads();
 
   const int b = blockIdx.y, tile = blockIdx.x;
@@ -405,7 +407,7 @@ __global__ void __launch_bounds__(FE_THREADS) fe_bwd_kernel(const float* __restr
   float* gca = s_gc + warp * 2 * NCOEF;
   float* gcb = gca + NCOEF;
 
-  for (int pair = warp; 2 * pair < nf; pair += FE_WARPS) {
+  for (int pair = warp; 2 * pair < nf; pair += FB_WARPS) {
     const int ta = t_lo + 2 * pair;
     const bool has_b = (2 * pair + 1 < nf);  // frame ta+1 is inside [t_lo, t_hi] (hence < F)
     // 1. d coefficients
@@ -494,7 +496,7 @@ __global__ void __launch_bounds__(FE_THREADS) fe_bwd_kernel(const float* __restr
   __syncthreads();
 
   // overlap-add + reflect-pad fold, fixed order
-  for (int sl = tid; sl < s1 - s0; sl += FE_THREADS) {
+  for (int sl = tid; sl < s1 - s0; sl += FB_THREADS) {
     const int s = s0 + sl;
     float acc = 0.f;
 #pragma unroll 1
@@ -521,8 +523,8 @@ __global__ void __launch_bounds__(FE_THREADS) fe_bwd_kernel(const float* __restr
 size_t fe_fwd_smem() { return (size_t)(256 + 256 + 400 + FE_WARPS * 1024 + FE_WARPS * 2 * PSTRIDE) * sizeof(float); }
 size_t fe_dct_smem() { return (size_t)(NFILT * NCOEF + 16 * NFILT) * sizeof(float); }
 size_t fe_bwd_smem() {
-  return (size_t)(256 + 256 + 400 + NFILT * DCT_LD + FE_WARPS * 2048 + FE_WARPS * 2 * PSTRIDE + FE_WARPS * 2 * NFILT +
-                  FE_WARPS * 2 * NCOEF + NF_MAX * WIN) *
+  return (size_t)(256 + 256 + 400 + NFILT * DCT_LD + FB_WARPS * 2048 + FB_WARPS * 2 * PSTRIDE + FB_WARPS * 2 * NFILT +
+                  FB_WARPS * 2 * NCOEF + NF_MAX * WIN) *
          sizeof(float);
 }
 
@@ -575,7 +577,7 @@ int frontend_backward(const FrontendTables& tb, const FrontendState& st, const f
   ADVB_KERNEL_OK("fe_mass_reduce", stream);
   const int n_tiles = cdiv(T, TILE_S);
   dim3 g2(n_tiles, B);
-  fe_bwd_kernel<<<g2, FE_THREADS, fe_bwd_smem(), stream>>>(x, T, F, tb, st, 80.0f, gcoef, g_clip_stride, g_stride_f,
+  fe_bwd_kernel<<<g2, FB_THREADS, fe_bwd_smem(), stream>>>(x, T, F, tb, st, 80.0f, gcoef, g_clip_stride, g_stride_f,
                                                           g_stride_c, gx, n_tiles);
   ADVB_KERNEL_OK("fe_bwd", stream);
   return 0;
