@@ -18,4 +18,8 @@ class AttackEnum(Enum):
     FGSM_eps00075 = (torchattacks.FGSM, {"eps": 0.00075})
     FGSM_eps001 = (torchattacks.FGSM, {"eps": 0.001})
 
+    FAB = (torchattacks.FAB, {"n_classes": 2, "eta": 10})
+    FAB_eta20 = (torchattacks.FAB, {"n_classes": 2, "eta": 20})
+    FAB_eta30 = (torchattacks.FAB, {"n_classes": 2, "eta": 30})
+
     NO_ATTACK = (None, {})

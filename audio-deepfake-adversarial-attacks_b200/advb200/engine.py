@@ -139,6 +139,16 @@ class Engine:
                                                   x.shape[0], x.shape[1], self._stream()))
         return gx
 
+    def row_diff_norms(self, a, b):
+        """Per-clip (L-inf, L2) norms of ``a - b`` (fab.py:515-521)."""
+        a, b = a.contiguous(), b.contiguous()
+        linf = torch.empty(a.shape[0], device=a.device, dtype=torch.float32)
+        l2 = torch.empty_like(linf)
+        with torch.cuda.device(self.device):
+            _lib.check(self.lib.advb_row_diff_norms(a.data_ptr(), b.data_ptr(), linf.data_ptr(), l2.data_ptr(),
+                                                    a.shape[0], a.shape[1], self._stream()))
+        return linf, l2
+
     def debug_stage(self, name: str):
         """(tensor (B, H+2p, W+2p, C) raw engine layout, pad p) of an internal stage of the last forward."""
         dims = (C.c_int64 * 5)()
@@ -201,6 +211,18 @@ def model_forward(module: nn.Module, x: torch.Tensor) -> torch.Tensor:
 
 def frontend_forward(frontend: nn.Module, x: torch.Tensor) -> torch.Tensor:
     raise NotImplementedError("call the frontend through a model handle: engine_for(model, B, T).frontend_fwd(x)")
+
+
+def projection_linf(t: torch.Tensor, w: torch.Tensor, b: torch.Tensor) -> torch.Tensor:
+    """fab.py:562-614 on the GPU (rows independent)."""
+    _require_cuda(t, "the points")
+    lib = _lib.load()
+    t, w, b = t.contiguous(), w.contiguous(), b.contiguous()
+    d = torch.empty_like(t)
+    with torch.cuda.device(t.device):
+        _lib.check(lib.advb_projection_linf(t.data_ptr(), w.data_ptr(), b.data_ptr(), d.data_ptr(), t.shape[0], t.shape[1],
+                                            C.c_void_p(torch.cuda.current_stream(t.device).cuda_stream)))
+    return d
 
 
 def to_minmax(x: torch.Tensor):

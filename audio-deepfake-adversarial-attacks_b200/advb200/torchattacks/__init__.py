@@ -5,7 +5,7 @@ Same constructor signatures, public attributes, ``set_training_mode`` and ``__ca
 model forward, CE, input gradient, update rule) runs in libadvb200's CUDA kernels.
 """
 from .attack import Attack
-from .attacks import FGSM, PGD, PGDL2
+from .attacks import CW, FAB, FGSM, PGD, PGDL2
 
 __version__ = "3.2.7+advb200"
-__all__ = ["Attack", "FGSM", "PGD", "PGDL2"]
+__all__ = ["Attack", "FGSM", "PGD", "PGDL2", "FAB", "CW"]

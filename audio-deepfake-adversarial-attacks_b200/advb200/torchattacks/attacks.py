@@ -66,3 +66,90 @@ class PGDL2(Attack):
             delta = delta.to(images.device)
         d = _desc(_lib.ATTACK_PGDL2, eps=self.eps, alpha=self.alpha, steps=self.steps, eps_div=self.eps_for_division)
         return self._engine(images).attack(d, images, labels, delta)
+
+
+class FAB(Attack):
+    """fab.py:11-78, :495-526 (perturb), :131-307 (attack_single_run).  The native loop covers what the repo's
+    ``AttackEnum`` reaches: ``norm='Linf'``, untargeted, ``n_restarts=1`` (no random start).  The index selection of
+    the reference (attack only the clips that are still correctly classified) stays here as tensor plumbing; every
+    forward, gradient, projection and norm runs in libadvb200."""
+
+    def __init__(self, model, norm="Linf", eps=None, steps=100, n_restarts=1, alpha_max=0.1, eta=1.05, beta=0.9,
+                 verbose=False, seed=0, targeted=False, n_classes=10):
+        super().__init__("FAB", model)
+        if norm != "Linf":
+            raise NotImplementedError("advb200 FAB implements norm='Linf' (the AttackEnum presets); L2/L1 are SURVEY §8 f4")
+        if n_restarts != 1 or targeted:
+            raise NotImplementedError("advb200 FAB implements n_restarts=1, untargeted (the AttackEnum presets)")
+        self.norm = norm
+        self.n_restarts = n_restarts
+        self.eps = eps if eps is not None else {"Linf": 0.3, "L2": 1.0, "L1": 5.0}[norm]
+        self.alpha_max = alpha_max
+        self.eta = eta
+        self.beta = beta
+        self.steps = steps
+        self.targeted = False
+        self.verbose = verbose
+        self.seed = seed
+        self.target_class = None
+        self.n_target_classes = n_classes - 1
+        self._supported_mode = ["default"]
+
+    def forward(self, images, labels):
+        images, labels = self._prepare(images, labels)
+        return self.perturb(images, labels)
+
+    def _get_predicted_label(self, x):
+        # argmax of cat([-o, o]) (fab.py:80-85): class 1 iff o > 0 (a tie goes to class 0)
+        return (self._engine(x).forward(x)[:, 0] > 0).long()
+
+    def attack_single_run(self, x, y=None, use_rand_start=False):
+        if use_rand_start:
+            raise NotImplementedError("random restarts are not built natively (n_restarts=1 in every preset)")
+        y_pred = self._get_predicted_label(x)
+        y = y_pred.clone() if y is None else y.clone().long().to(x.device)
+        pred = y_pred == y
+        if pred.sum() == 0:
+            return x
+        idx = pred.nonzero().flatten()
+        im2, la2 = x[idx].contiguous(), y[idx].contiguous()
+        d = _desc(_lib.ATTACK_FAB, eps=self.eps, steps=self.steps, alpha_max=self.alpha_max, eta=self.eta, beta=self.beta)
+        adv = self._engine(x).attack(d, im2, la2)  # rows never found adversarial come back equal to im2
+        adv_c = x.clone()
+        adv_c[idx] = adv
+        return adv_c
+
+    def perturb(self, x, y):
+        adv = x.clone()
+        acc = self._get_predicted_label(x) == y
+        # fab.py:504-505: the reference reseeds the global RNGs on every call (kept: it affects later shuffles)
+        torch.random.manual_seed(self.seed)
+        torch.cuda.random.manual_seed(self.seed)
+        ind_to_fool = acc.nonzero().flatten()
+        if ind_to_fool.numel() != 0:
+            x_to_fool, y_to_fool = x[ind_to_fool].contiguous(), y[ind_to_fool].contiguous()
+            adv_curr = self.attack_single_run(x_to_fool, y_to_fool, use_rand_start=False)
+            eng = self._engine(x)
+            acc_curr = self._get_predicted_label(adv_curr) == y_to_fool
+            res, _ = eng.row_diff_norms(x_to_fool, adv_curr)
+            acc_curr = torch.max(acc_curr, res > self.eps)
+            ind_curr = (acc_curr == 0).nonzero().flatten()
+            adv[ind_to_fool[ind_curr]] = adv_curr[ind_curr].clone()
+        return adv
+
+
+class CW(Attack):
+    """cw.py:10-134: tanh-space Adam on  sum ||x' - x||^2 + c sum f(x')  with the batch-wide early stop."""
+
+    def __init__(self, model, c=1e-4, kappa=0, steps=1000, lr=0.01):
+        super().__init__("CW", model)
+        self.c = c
+        self.kappa = kappa
+        self.steps = steps
+        self.lr = lr
+        self._supported_mode = ["default"]
+
+    def forward(self, images, labels):
+        images, labels = self._prepare(images, labels)
+        d = _desc(_lib.ATTACK_CW, c=self.c, kappa=self.kappa, steps=self.steps, lr=self.lr)
+        return self._engine(images).attack(d, images, labels)

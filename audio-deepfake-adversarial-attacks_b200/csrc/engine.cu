@@ -14,6 +14,7 @@
 #include "../../include/advb200.h"
 #include "common.cuh"
 #include "conv.cuh"
+#include "fabcw.cuh"
 #include "frontend.cuh"
 #include "rnn.cuh"
 #include "update.cuh"
@@ -89,6 +90,9 @@ struct advb_handle {
   // attack scratch
   float* conv0_T = nullptr;  // (B,F,80,5) horizontal col2im partial sums of the first block's backward
   float *grad = nullptr, *partial_g = nullptr, *partial_d = nullptr, *coef_tmp = nullptr;
+  FabScratch fab{};  // allocated on the first FAB / CW call
+  CwScratch cw{};
+  float* host_cost = nullptr;  // pinned: CW's batch-wide early-stop scalar (cw.py:107-110)
 
   template <typename Tp>
   int alloc(Tp** out, size_t count) {
@@ -349,9 +353,9 @@ int lcnn_forward(advb_handle* h, const float* x, int B, cudaStream_t st) {
 
 // Gradient of (mode 0) the mean 2-class CE or (mode 1) the logit, w.r.t. the waveform of the last forward.
 int lcnn_backward(advb_handle* h, const float* x, const int64_t* y, int B, int mode, int n_global, float* gx,
-                  cudaStream_t st) {
+                  cudaStream_t st, const float* coef = nullptr) {
   ADVB_TRY(head_backward(h->logits, reinterpret_cast<const long long*>(y), h->t("m_output_act.weight"), h->dl2, B,
-                         h->L, mode, n_global, st));
+                         h->L, mode, n_global, st, coef));
   ADVB_TRY(blstm_backward(h->lp[1], h->gates2, h->dl2, h->cs2, nullptr, h->dl1, B, h->L, st));
   ADVB_TRY(blstm_backward(h->lp[0], h->gates1, h->dl1, h->cs1, h->dl2, h->dfeats, B, h->L, st));
   ADVB_TRY(feats_scatter(h->dfeats, h->blk[8].gout, B, h->L, h->Wf, 32, st));
@@ -398,8 +402,8 @@ int model_forward(advb_handle* h, const float* x, int B, cudaStream_t st) {
   return 1;
 }
 int model_backward(advb_handle* h, const float* x, const int64_t* y, int B, int mode, int n_global, float* gx,
-                   cudaStream_t st) {
-  if (h->model_kind == ADVB_MODEL_LCNN) return lcnn_backward(h, x, y, B, mode, n_global, gx, st);
+                   cudaStream_t st, const float* coef = nullptr) {
+  if (h->model_kind == ADVB_MODEL_LCNN) return lcnn_backward(h, x, y, B, mode, n_global, gx, st, coef);
   set_error("model kind not implemented");
   return 1;
 }
@@ -408,6 +412,37 @@ int check_call(advb_handle* h, int B, int T) {
   ADVB_CHECK(h != nullptr, "null handle");
   ADVB_CHECK(B > 0 && B <= h->Bmax, "batch exceeds the handle's max_batch");
   ADVB_CHECK(T == h->T, "clip length differs from the handle's n_samples");
+  return 0;
+}
+
+constexpr int ADVB_GRAD_SEEDED = 2;  // internal: d (sum_b coef[b] o_b) / d x
+
+int ensure_fab_scratch(advb_handle* h) {
+  if (h->fab.x1 != nullptr) return 0;
+  const size_t n = (size_t)h->Bmax * h->T;
+  ADVB_TRY(h->alloc(&h->fab.x1, n));
+  ADVB_TRY(h->alloc(&h->fab.d3, 2 * n));
+  ADVB_TRY(h->alloc(&h->fab.w, n));
+  ADVB_TRY(h->alloc(&h->fab.bh, h->Bmax));
+  ADVB_TRY(h->alloc(&h->fab.a0, 2 * (size_t)h->Bmax));
+  ADVB_TRY(h->alloc(&h->fab.res2, h->Bmax));
+  return 0;
+}
+
+int ensure_cw_scratch(advb_handle* h) {
+  if (h->cw.w != nullptr) return 0;
+  const size_t n = (size_t)h->Bmax * h->T;
+  ADVB_TRY(h->alloc(&h->cw.w, n));
+  ADVB_TRY(h->alloc(&h->cw.m, n));
+  ADVB_TRY(h->alloc(&h->cw.v, n));
+  ADVB_TRY(h->alloc(&h->cw.adv, n));
+  ADVB_TRY(h->alloc(&h->cw.l2_partial, (size_t)h->Bmax * 8));
+  ADVB_TRY(h->alloc(&h->cw.cur_l2, h->Bmax));
+  ADVB_TRY(h->alloc(&h->cw.best_l2, h->Bmax));
+  ADVB_TRY(h->alloc(&h->cw.coef, h->Bmax));
+  ADVB_TRY(h->alloc(&h->cw.mask, h->Bmax));
+  ADVB_TRY(h->alloc(&h->cw.cost, 1));
+  ADVB_CUDA_OK(cudaMallocHost(reinterpret_cast<void**>(&h->host_cost), sizeof(float)));
   return 0;
 }
 
@@ -479,6 +514,7 @@ void advb_destroy(advb_handle* h) {
   if (h == nullptr) return;
   DeviceGuard guard(h->device);
   for (void* p : h->allocs) cudaFree(p);
+  if (h->host_cost != nullptr) cudaFreeHost(h->host_cost);
   delete h;
 }
 
@@ -572,10 +608,72 @@ int advb_attack(advb_handle* h, const advb_attack_desc* atk, const float* x, con
       }
       return 0;
     }
+    case ADVB_ATTACK_FAB: {
+      // attack_single_run (fab.py:131-307) on a batch of correctly classified clips: L-inf, untargeted, no random
+      // start.  One backward per step (the class-0 gradient of z = [-o, o] is the exact negation of class 1's).
+      ADVB_CHECK(atk->steps >= 0, "bad step count");
+      ADVB_TRY(ensure_fab_scratch(h));
+      const long long* yl = reinterpret_cast<const long long*>(y);
+      ADVB_TRY(fab_init(x, x_adv, h->fab, B, T, st));
+      for (int it = 0; it < atk->steps; ++it) {
+        ADVB_TRY(model_forward(h, h->fab.x1, B, st));
+        ADVB_TRY(model_backward(h, h->fab.x1, y, B, ADVB_GRAD_LOGIT, n_global, h->grad, st));
+        ADVB_TRY(fab_hyperplane(h->grad, h->logits, yl, h->fab, B, T, st));
+        ADVB_TRY(fab_project(x, h->fab, B, T, st));
+        ADVB_TRY(fab_combine(x, h->fab, atk->eta, atk->alpha_max, B, T, st));
+        ADVB_TRY(model_forward(h, h->fab.x1, B, st));
+        ADVB_TRY(fab_bookkeep(x, h->logits, yl, x_adv, h->fab, atk->beta, B, T, st));
+      }
+      return 0;
+    }
+    case ADVB_ATTACK_CW: {
+      ADVB_CHECK(atk->steps >= 0, "bad step count");
+      ADVB_TRY(ensure_cw_scratch(h));
+      const long long* yl = reinterpret_cast<const long long*>(y);
+      ADVB_TRY(cw_init(x, x_adv, h->cw, B, T, st));
+      float prev_cost = 1e10f;
+      const int every = atk->steps / 10 > 1 ? atk->steps / 10 : 1;
+      for (int step = 0; step < atk->steps; ++step) {
+        ADVB_TRY(cw_forward_image(x, h->cw, B, T, st));
+        ADVB_TRY(model_forward(h, h->cw.adv, B, st));
+        ADVB_TRY(cw_head(h->logits, yl, h->cw, atk->c, atk->kappa, B, st));
+        ADVB_TRY(model_backward(h, h->cw.adv, y, B, ADVB_GRAD_SEEDED, n_global, h->grad, st, h->cw.coef));
+        ADVB_TRY(cw_adam(x, h->grad, x_adv, h->cw, atk->lr, step + 1, B, T, st));
+        if (step % every == 0) {  // batch-wide early stop: the one host sync the reference has too (cw.py:107-110)
+          ADVB_CUDA_OK(cudaMemcpyAsync(h->host_cost, h->cw.cost, sizeof(float), cudaMemcpyDeviceToHost, st));
+          ADVB_CUDA_OK(cudaStreamSynchronize(st));
+          if (*h->host_cost > prev_cost) return 0;
+          prev_cost = *h->host_cost;
+        }
+      }
+      return 0;
+    }
     default:
       set_error("attack kind not implemented in the native loop");
       return 1;
   }
+}
+
+int advb_projection_linf(const float* t, const float* w, const float* b, float* d, int R, int T, void* cuda_stream) {
+  ADVB_CHECK(t && w && b && d && R > 0 && T > 0, "bad argument");
+  cudaStream_t st = static_cast<cudaStream_t>(cuda_stream);
+  // rows are independent: run them as the "x1" half of a FAB step whose second half is empty
+  float* a0 = nullptr;
+  ADVB_CUDA_OK(cudaMallocAsync(reinterpret_cast<void**>(&a0), sizeof(float) * R, st));
+  FabScratch s{};
+  s.x1 = const_cast<float*>(t);
+  s.w = const_cast<float*>(w);
+  s.bh = const_cast<float*>(b);
+  s.d3 = d;
+  s.a0 = a0;
+  const int rc = fab_project_rows(s, R, T, st);
+  cudaFreeAsync(a0, st);
+  return rc;
+}
+
+int advb_row_diff_norms(const float* a, const float* b, float* linf, float* l2, int B, int T, void* cuda_stream) {
+  ADVB_CHECK(a && b && (linf || l2) && B > 0 && T > 0, "bad argument");
+  return row_diff_norms(a, b, linf, l2, B, T, static_cast<cudaStream_t>(cuda_stream));
 }
 
 int advb_frontend_fwd(advb_handle* h, const float* x, float* coeff, int B, int T, void* cuda_stream) {

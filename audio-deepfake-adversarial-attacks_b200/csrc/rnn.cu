@@ -256,9 +256,10 @@ __global__ void __launch_bounds__(160) head_fwd_kernel(const float* __restrict__
 // d loss / d logit, then d/d(l2) = d/d(feats residual) = g_o * w / L for every time step.
 __global__ void __launch_bounds__(160) head_bwd_kernel(const float* __restrict__ logits, const long long* __restrict__ y,
                                                         const float* __restrict__ w, float* __restrict__ dl2, int L,
-                                                        int mode, float inv_n) {
+                                                        int mode, float inv_n, const float* __restrict__ coef) {
   const int b = blockIdx.x, k = threadIdx.x;
   float go = 1.0f;
+  if (mode == 2) go = coef[b];
   if (mode == 0) {
     const float o = logits[b];
     const float p1 = 1.0f / (1.0f + expf(-2.0f * o));
@@ -333,8 +334,8 @@ int head_forward(const float* l2, const float* feats, const float* w, const floa
   return 0;
 }
 int head_backward(const float* logits, const long long* y, const float* w, float* dl2, int B, int L, int mode,
-                  int n_global, cudaStream_t stream) {
-  head_bwd_kernel<<<B, 160, 0, stream>>>(logits, y, w, dl2, L, mode, 1.0f / (float)n_global);
+                  int n_global, cudaStream_t stream, const float* coef) {
+  head_bwd_kernel<<<B, 160, 0, stream>>>(logits, y, w, dl2, L, mode, 1.0f / (float)n_global, coef);
   ADVB_KERNEL_OK("head_bwd", stream);
   return 0;
 }

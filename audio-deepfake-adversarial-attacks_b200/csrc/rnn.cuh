@@ -32,8 +32,8 @@ int feats_gather(const float* act, float* feats, int B, int L, int Wf, int C, cu
 int feats_scatter(const float* gfeats, float* gact, int B, int L, int Wf, int C, cudaStream_t stream);
 int head_forward(const float* l2, const float* feats, const float* w, const float* bias, float* logits, int B, int L,
                  cudaStream_t stream);
-// mode 0: d mean-CE / d logit = 2 (sigmoid(2 o) - y) / n_global ; mode 1: 1
+// mode 0: d mean-CE / d logit = 2 (sigmoid(2 o) - y) / n_global ; mode 1: 1 ; mode 2: coef[b] (caller-supplied seed)
 int head_backward(const float* logits, const long long* y, const float* w, float* dl2, int B, int L, int mode,
-                  int n_global, cudaStream_t stream);
+                  int n_global, cudaStream_t stream, const float* coef = nullptr);
 
 }  // namespace advb

@@ -94,6 +94,9 @@ ADVB_API int advb_set_option(advb_handle* h, const char* key, int value);
  *   x        [B,T] fp32 in [0,1], device;  y [B] int64 labels (1 = bonafide), device
  *   start    nullable [B,T]: the random start drawn by the host with torch:
  *            PGD: the U(-eps,eps) noise added at pgd.py:56;  PGDL2: the already scaled delta of pgdl2.py:57-61
+ *   FAB      runs attack_single_run (fab.py:131-307; L-inf, untargeted, n_restarts = 1) on the given clips, which
+ *            the caller has already restricted to the correctly classified ones as FAB.perturb does (fab.py:506-513)
+ *   CW       cw.py:46-112, including the batch-wide early stop (one host sync every steps/10 iterations)
  *   x_adv    [B,T] fp32 out (must not alias x)
  * Work is enqueued on `cuda_stream` (a cudaStream_t); the call does not synchronise. */
 ADVB_API int advb_attack(advb_handle* h, const advb_attack_desc* atk, const float* x, const int64_t* y, const float* start,
@@ -119,6 +122,14 @@ ADVB_API int advb_frontend_bwd(advb_handle* h, const float* x, const float* g_co
 ADVB_API int advb_minmax(const float* x, float* x01, float* mn, float* mx, int B, int T, void* cuda_stream);
 ADVB_API int advb_revert_minmax(const float* x01, const float* mn, const float* mx, float* x, int B, int T,
                        void* cuda_stream);
+
+/* Replaces projection_linf(points_to_project, w_hyperplane, b_hyperplane) (fab.py:562-614): for each of R rows the
+ * minimal-L-inf move d with <w, t + d> = b, t + d in [0,1]^T.  t, w, d: [R,T]; b: [R].  Test / f4 entry point. */
+ADVB_API int advb_projection_linf(const float* t, const float* w, const float* b, float* d, int R, int T, void* cuda_stream);
+
+/* Per-clip perturbation norms  ||a_i - b_i||_inf  and  ||a_i - b_i||_2  (either output nullable): the row reductions of
+ * FAB.perturb (fab.py:515-521) and of the L-inf / L2 parity gates. */
+ADVB_API int advb_row_diff_norms(const float* a, const float* b, float* linf, float* l2, int B, int T, void* cuda_stream);
 
 /* Test introspection: copy one internal stage buffer of the last forward (raw engine layout) to `dst` (device).
  * dims[0..3] receive the logical (B, H, W, C) of the stage, dims[4] the spatial zero-border width of the

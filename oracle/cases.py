@@ -18,12 +18,20 @@ CASES = {
     "lcnn_lfcc_t16000": dict(model="lcnn", frontend="lfcc", T=16000, B=2, cfg_id=11, silence=False),
     "lcnn_lfcc_t16000_silence": dict(model="lcnn", frontend="lfcc", T=16000, B=2, cfg_id=12, silence=True),
     "lcnn_lfcc_t64000": dict(model="lcnn", frontend="lfcc", T=64000, B=1, cfg_id=13, silence=False),
+    # FAB / CW: clean logits sit at +margin (all predicted bonafide) and labels are fixed, so the clips labelled 1 are
+    # correctly classified and must be pushed across a real margin; the clip labelled 0 is already misclassified and
+    # exercises FAB's "attack only the correctly classified clips" path (fab.py:506-513)
+    "lcnn_lfcc_t16000_margin": dict(model="lcnn", frontend="lfcc", T=16000, B=4, cfg_id=14, silence=False,
+                                    margin=0.01, labels=(1, 1, 0, 1), attacks=("fab", "cw")),
 }
+DEFAULT_ATTACKS = ("fgsm", "pgd", "pgdl2")
 
 ATTACKS = {
     "fgsm": dict(eps=0.005),
     "pgd": dict(eps=0.001, alpha=2 / 255, steps=3),
     "pgdl2": dict(eps=0.1, alpha=0.2, steps=3),
+    "fab": dict(eps=0.3, steps=8, eta=10.0, alpha_max=0.1, beta=0.9),   # AttackEnum.FAB preset, fewer steps
+    "cw": dict(c=1e-4, kappa=0.0, steps=20, lr=0.01),
 }
 
 
@@ -36,7 +44,7 @@ def build_holder(model: str, frontend: str, seed: int = 42):
     return get_model(model, cfg, "cpu")
 
 
-def build_state(model: str, frontend: str, seed: int = 42, calibrate_on=None, forward_fn=None):
+def build_state(model: str, frontend: str, seed: int = 42, calibrate_on=None, forward_fn=None, margin: float = 0.0):
     """Seeded state_dict with randomised BatchNorm statistics; optionally shift the output bias so that the clean
     logits of ``calibrate_on`` straddle zero (otherwise no label ever flips)."""
     holder = build_holder(model, frontend, seed)
@@ -47,10 +55,12 @@ def build_state(model: str, frontend: str, seed: int = 42, calibrate_on=None, fo
         with torch.no_grad():
             o = forward_fn(calibrate_on, state)
         key = {"lcnn": "m_output_act.bias", "specrnet": "fc2_gru.bias", "rawnet3": "fc6.bias"}[model]
-        state[key] = state[key] - o.median()
+        state[key] = state[key] - o.median() + margin
     return holder, state
 
 
 def case_inputs(case: dict):
     x, y = synth.clips(case["cfg_id"], case["B"], case["T"], silence=case["silence"])
+    if case.get("labels") is not None:
+        y = torch.tensor(case["labels"], dtype=torch.int64)
     return x, y

@@ -34,10 +34,14 @@ def main():
 
     torch.set_num_threads(8)
     os.makedirs(cases.GOLDEN_DIR, exist_ok=True)
+    only = set(sys.argv[1:])  # optional: regenerate just the named cases
     for name, case in cases.CASES.items():
+        if only and name not in only:
+            continue
         x, y = cases.case_inputs(case)
         fwd = {"lcnn": olcnn.forward}[case["model"]]
-        _, state = cases.build_state(case["model"], case["frontend"], calibrate_on=x, forward_fn=fwd)
+        _, state = cases.build_state(case["model"], case["frontend"], calibrate_on=x, forward_fn=fwd,
+                                     margin=case.get("margin", 0.0))
         ref = reference_model(case, state)
         ref.eval()
         out = {"digest": np.array(synth.state_digest(state)), "x_sum": np.array(x.double().sum().item())}
@@ -56,8 +60,14 @@ def main():
         out["grad"] = torch.autograd.grad(cost, xr)[0].numpy()
         ref.eval()
 
-        for an, ap in cases.ATTACKS.items():
-            if an == "fgsm":
+        for an in case.get("attacks", cases.DEFAULT_ATTACKS):
+            ap = cases.ATTACKS[an]
+            if an == "fab":
+                atk = torchattacks.FAB(ref, norm="Linf", eps=ap["eps"], steps=ap["steps"], eta=ap["eta"],
+                                       alpha_max=ap["alpha_max"], beta=ap["beta"], n_classes=2)
+            elif an == "cw":
+                atk = torchattacks.CW(ref, c=ap["c"], kappa=ap["kappa"], steps=ap["steps"], lr=ap["lr"])
+            elif an == "fgsm":
                 atk = torchattacks.FGSM(ref, eps=ap["eps"])
             elif an == "pgd":
                 atk = torchattacks.PGD(ref, eps=ap["eps"], alpha=ap["alpha"], steps=ap["steps"], random_start=True)
@@ -78,7 +88,8 @@ def main():
             out[f"{an}_logits_adv"] = la.numpy()
         path = os.path.join(cases.GOLDEN_DIR, name + ".npz")
         np.savez_compressed(path, **out)
-        print(name, "logits", out["logits"].ravel(), "pgd logits", out["pgd_logits_adv"].ravel(),
+        first = case.get("attacks", cases.DEFAULT_ATTACKS)[-1]
+        print(name, "logits", out["logits"].ravel(), first, "logits", out[f"{first}_logits_adv"].ravel(),
               os.path.getsize(path) // 1024, "KiB")
 
 

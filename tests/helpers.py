@@ -19,7 +19,8 @@ def case_setup(name):
     case = cases.CASES[name]
     x, y = cases.case_inputs(case)
     fwd = ORACLE_FWD[case["model"]]
-    holder, state = cases.build_state(case["model"], case["frontend"], calibrate_on=x, forward_fn=fwd)
+    holder, state = cases.build_state(case["model"], case["frontend"], calibrate_on=x, forward_fn=fwd,
+                                       margin=case.get("margin", 0.0))
     return case, x, y, holder, state, fwd
 
 
@@ -40,6 +41,10 @@ def oracle_attack(name, attack, x, y, state, fwd, case):
     model_fn = lambda v: fwd(v, state)  # noqa: E731
     if attack == "fgsm":
         return oatk.fgsm(model_fn, x, y, p["eps"])
+    if attack == "fab":
+        return oatk.fab(model_fn, x, y, p["eps"], p["steps"], p["alpha_max"], p["eta"], p["beta"])
+    if attack == "cw":
+        return oatk.cw(model_fn, x, y, p["c"], p["kappa"], p["steps"], p["lr"])
     if attack == "pgd":
         return oatk.pgd(model_fn, x, y, p["eps"], p["alpha"], p["steps"], noise=reference_start(case, "pgd", x, p["eps"]))
     delta = reference_start(case, "pgdl2", x, p["eps"])

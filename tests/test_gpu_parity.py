@@ -249,3 +249,69 @@ def test_tensor_core_path_matches_simt_path(name, cuda_device):
     finally:
         eng.set_option("tf32_passes", 3)
         eng.set_option("conv_path", 0)
+
+
+def test_projection_linf_against_oracle(cuda_device):
+    """fab.py:562-614: the sort-free CUDA projection against the sort-based restatement, all three branches
+    (unreachable hyperplane -> box corner, uniform level, saturating level), ragged row length."""
+    from advb200 import engine
+
+    g = torch.Generator("cpu").manual_seed(11)
+    R, T = 12, 16001
+    t = torch.rand(R, T, generator=g)
+    w = torch.randn(R, T, generator=g) * 1e-3
+    w[3, ::7] = 0.0  # exact zeros: (w != 0) mask
+    z = torch.rand(R, T, generator=g)
+    b = (w * z).sum(1)                       # hyperplane through a box point: saturating level
+    b[0] = (w[0] * t[0]).sum() + 1e-4        # almost on the plane: uniform level (c_l)
+    b[1] = (w[1] * t[1]).sum() - 2e-4
+    b[2] = (w[2].abs()).sum() * 5            # does not meet the box: corner
+    t[4, :100] = 0.0                         # ties at the box faces
+    t[4, 100:200] = 1.0
+    want = oatk.projection_linf(t, w, b)
+    got = engine.projection_linf(t.to(cuda_device), w.to(cuda_device), b.to(cuda_device)).cpu()
+    # the attack only uses d through x + eta d and ||d||_inf: compare those scales
+    scale = want.abs().amax(dim=1).clamp_min(1e-12)
+    assert ((got - want).abs().amax(dim=1) / scale).max().item() < 2e-4
+    np.testing.assert_allclose(got.abs().amax(dim=1).numpy(), want.abs().amax(dim=1).numpy(), rtol=2e-4)
+    hit = [i for i in range(R) if i != 2]
+    np.testing.assert_allclose((w * (t + got)).sum(1)[hit].numpy(), b[hit].numpy(), rtol=1e-3, atol=2e-5)
+
+
+@pytest.mark.parametrize("attack", ["fab", "cw"])
+def test_fab_cw_against_oracle_and_golden(attack, cuda_device):
+    from advb200 import torchattacks as ta
+
+    name = "lcnn_lfcc_t16000_margin"
+    case, x, y, holder, state, fwd, eng = _setup(name, cuda_device)
+    g = helpers.load_golden(name)
+    p = cases.ATTACKS[attack]
+    xd, yd = x.to(cuda_device), y.to(cuda_device)
+    if attack == "fab":
+        atk = ta.FAB(holder, norm="Linf", eps=p["eps"], steps=p["steps"], eta=p["eta"], alpha_max=p["alpha_max"],
+                     beta=p["beta"], n_classes=2)
+    else:
+        atk = ta.CW(holder, c=p["c"], kappa=p["kappa"], steps=p["steps"], lr=p["lr"])
+    atk.set_training_mode(True, False)
+    got = atk(xd, yd)
+    assert torch.equal(xd.cpu(), x), "inputs must not be mutated"
+    got = got.cpu()
+    assert got.min().item() >= 0.0 and got.max().item() <= 1.0
+    d = got - x
+    ref = torch.from_numpy(g[f"{attack}_adv"])
+    if attack == "fab":
+        # FAB's own norm is L-inf; the reference's run-to-run noise on it is 5e-7 (SURVEY.md §4): 1e-5 relative + 1e-6
+        np.testing.assert_allclose(d.abs().amax(dim=1).numpy(), g["fab_delta_linf"], rtol=1e-5, atol=1e-6)
+        np.testing.assert_allclose(d.norm(p=2, dim=1).numpy(), g["fab_delta_l2"], rtol=1e-4, atol=1e-5)
+        assert torch.equal(got[2], x[2]), "a clip that is misclassified from the start must come back untouched"
+        # like FGSM/PGD, the L-inf projection moves every sample by +-lambda along -sign(w): elements agree except where
+        # the gradient sign itself is a tie between two fp32 implementations
+        assert ((got - ref).abs() > 1e-5).float().mean().item() < 2e-3
+    else:
+        # CW's own norm is L2.  Its first Adam steps are sign-like (m / sqrt(v) = +-1) on a gradient dominated by the
+        # fp32 rounding of tanh(atanh(.)), so elements differ between any two libm's; the norm is what is stable.
+        np.testing.assert_allclose(d.norm(p=2, dim=1).numpy(), g["cw_delta_l2"], rtol=2e-2, atol=1e-5)
+    la = eng.forward(got.to(cuda_device)).cpu().numpy()
+    assert np.array_equal(la > 0, g[f"{attack}_logits_adv"] > 0), "label flips differ"
+    lr = eng.forward(ref.to(cuda_device)).cpu().numpy()
+    np.testing.assert_allclose(lr, g[f"{attack}_logits_adv"], atol=3e-6)

@@ -49,3 +49,35 @@ def test_oracle_attacks_match_reference(name, attack):
     with torch.no_grad():
         la = fwd(xa, state)
     assert np.array_equal((la.numpy() > 0), (g[f"{attack}_logits_adv"] > 0)), "label flips differ"
+
+
+@pytest.mark.parametrize("attack", ["fab", "cw"])
+def test_oracle_fab_cw_match_reference(attack):
+    name = "lcnn_lfcc_t16000_margin"
+    case, x, y, holder, state, fwd = helpers.case_setup(name)
+    g = helpers.load_golden(name)
+    xa = helpers.oracle_attack(name, attack, x, y, state, fwd, case)
+    ref = torch.from_numpy(g[f"{attack}_adv"])
+    # FAB's own norm is L-inf, CW's is L2; the clip labelled 0 is misclassified from the start and must
+    # come back untouched by FAB (fab.py:506-513)
+    np.testing.assert_allclose((xa - x).abs().amax(dim=1).numpy(), g[f"{attack}_delta_linf"], rtol=1e-5, atol=1e-6)
+    np.testing.assert_allclose((xa - x).norm(p=2, dim=1).numpy(), g[f"{attack}_delta_l2"], rtol=1e-4, atol=1e-5)
+    assert (xa - ref).abs().max().item() < 1e-5
+    if attack == "fab":
+        assert torch.equal(xa[2], x[2])
+    with torch.no_grad():
+        la = fwd(xa, state)
+    assert np.array_equal((la.numpy() > 0), (g[f"{attack}_logits_adv"] > 0)), "label flips differ"
+
+
+def test_oracle_projection_linf_solves_the_box_hyperplane_problem():
+    """fab.py:562-614: the returned d satisfies <w, t + d> = b with t + d in [0,1]^n whenever the hyperplane meets the
+    box (property check of the restatement, independent of the golden vectors)."""
+    g = torch.Generator().manual_seed(5)
+    t = torch.rand(6, 500, generator=g)
+    w = torch.randn(6, 500, generator=g)
+    z = torch.rand(6, 500, generator=g)  # a point of the box: choose b so the hyperplane passes through it
+    b = (w * z).sum(1)
+    d = oatk.projection_linf(t, w, b)
+    assert ((t + d) >= -1e-6).all() and ((t + d) <= 1 + 1e-6).all()
+    np.testing.assert_allclose((w * (t + d)).sum(1).numpy(), b.numpy(), rtol=1e-4, atol=1e-4)
