@@ -18,6 +18,8 @@ CASES = {
     "lcnn_lfcc_t16000": dict(model="lcnn", frontend="lfcc", T=16000, B=2, cfg_id=11, silence=False),
     "lcnn_lfcc_t16000_silence": dict(model="lcnn", frontend="lfcc", T=16000, B=2, cfg_id=12, silence=True),
     "lcnn_lfcc_t64000": dict(model="lcnn", frontend="lfcc", T=64000, B=1, cfg_id=13, silence=False),
+    "specrnet_mfcc_t16000": dict(model="specrnet", frontend="mfcc", T=16000, B=3, cfg_id=15, silence=False),
+    "specrnet_lfcc_t64000": dict(model="specrnet", frontend="lfcc", T=64000, B=1, cfg_id=16, silence=False),
     # FAB / CW: clean logits sit at +margin (all predicted bonafide) and labels are fixed, so the clips labelled 1 are
     # correctly classified and must be pushed across a real margin; the clip labelled 0 is already misclassified and
     # exercises FAB's "attack only the correctly classified clips" path (fab.py:506-513)

@@ -15,6 +15,7 @@ sys.path.insert(0, "/root/reference")
 
 from . import cases, synth  # noqa: E402
 from . import lcnn as olcnn  # noqa: E402
+from . import specrnet as ospec  # noqa: E402
 
 
 def reference_model(case, state):
@@ -22,6 +23,10 @@ def reference_model(case, state):
         from src.models.lcnn import LCNN
 
         m = LCNN(device="cpu", input_channels=1, frontend_algorithm=[case["frontend"]])
+    elif case["model"] == "specrnet":
+        from src.models.specrnet import SpecRNet, get_config
+
+        m = SpecRNet(get_config(1), device="cpu", input_channels=1, frontend_algorithm=[case["frontend"]])
     else:
         raise NotImplementedError(case["model"])
     missing = m.load_state_dict(state, strict=True)
@@ -39,7 +44,7 @@ def main():
         if only and name not in only:
             continue
         x, y = cases.case_inputs(case)
-        fwd = {"lcnn": olcnn.forward}[case["model"]]
+        fwd = {"lcnn": olcnn.forward, "specrnet": ospec.forward}[case["model"]]
         _, state = cases.build_state(case["model"], case["frontend"], calibrate_on=x, forward_fn=fwd,
                                      margin=case.get("margin", 0.0))
         ref = reference_model(case, state)

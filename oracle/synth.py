@@ -41,6 +41,10 @@ def randomize_norm_stats(state: dict, seed: int = 7) -> dict:
             out[k] = 0.2 * torch.randn(v.shape, generator=g)
         elif k.endswith("running_var"):
             out[k] = 0.5 + torch.rand(v.shape, generator=g)
+        elif (k.endswith(".weight") or k.endswith(".bias")) and k.rsplit(".", 1)[0] + ".running_mean" in state:
+            # affine BatchNorm (SpecRNet): non-trivial scale / shift
+            out[k] = (0.75 + 0.5 * torch.rand(v.shape, generator=g)) if k.endswith(".weight") else \
+                0.1 * torch.randn(v.shape, generator=g)
         else:
             out[k] = v.clone()
     return out

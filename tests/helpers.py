@@ -7,8 +7,9 @@ import torch
 from oracle import attacks as oatk
 from oracle import cases, synth
 from oracle import lcnn as olcnn
+from oracle import specrnet as ospec
 
-ORACLE_FWD = {"lcnn": olcnn.forward}
+ORACLE_FWD = {"lcnn": olcnn.forward, "specrnet": ospec.forward}
 
 
 def load_golden(name):
