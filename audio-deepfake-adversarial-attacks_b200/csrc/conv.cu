@@ -15,92 +15,13 @@
 // Backward is the same contraction over an on-the-fly expanded gradient band (BN scale, un-pool, un-MFM applied
 // while staging), with tap-flipped / transposed weights; the expanded gradient never touches HBM.
 #include "conv.cuh"
+#include "conv_core.cuh"
 
 namespace advb {
 
 namespace {
 
-__device__ __forceinline__ void fma4(float (&acc)[8], int off, float a, const float4& w) {
-  acc[off + 0] = fmaf(a, w.x, acc[off + 0]);
-  acc[off + 1] = fmaf(a, w.y, acc[off + 1]);
-  acc[off + 2] = fmaf(a, w.z, acc[off + 2]);
-  acc[off + 3] = fmaf(a, w.w, acc[off + 3]);
-}
-
-// acc[p][0..3] -> channels g4..g4+3, acc[p][4..7] -> channels nh+g4..nh+g4+3, p = 2x2 pixel of the quad.
-template <int KS>
-__device__ __forceinline__ void conv_core(const float* band, int BW, int CK, int CKp, const float* __restrict__ wg,
-                                          float* w_s, int N, int rb, int cb, int g4, bool valid, float (&acc)[4][8]) {
-  const int nh = N >> 1;
-  const int slab4 = (CK * N) >> 2;
-#pragma unroll 1
-  for (int tap = 0; tap < KS * KS; ++tap) {
-    const int dy = tap / KS, dx = tap % KS;
-    __syncthreads();
-    {
-      const float4* src = reinterpret_cast<const float4*>(wg + (size_t)tap * CK * N);
-      float4* dst = reinterpret_cast<float4*>(w_s);
-      for (int i = threadIdx.x; i < slab4; i += blockDim.x) dst[i] = __ldg(src + i);
-    }
-    __syncthreads();
-    if (!valid) continue;
-    const float* p00 = band + ((size_t)(rb + dy) * BW + cb + dx) * CKp;
-    const float* p01 = p00 + CKp;
-    const float* p10 = p00 + (size_t)BW * CKp;
-    const float* p11 = p10 + CKp;
-    if ((CK & 3) == 0) {
-#pragma unroll 1
-      for (int ci = 0; ci < CK; ci += 4) {
-        const float4 a0 = *reinterpret_cast<const float4*>(p00 + ci);
-        const float4 a1 = *reinterpret_cast<const float4*>(p01 + ci);
-        const float4 a2 = *reinterpret_cast<const float4*>(p10 + ci);
-        const float4 a3 = *reinterpret_cast<const float4*>(p11 + ci);
-        const float av[4][4] = {{a0.x, a0.y, a0.z, a0.w}, {a1.x, a1.y, a1.z, a1.w}, {a2.x, a2.y, a2.z, a2.w},
-                                {a3.x, a3.y, a3.z, a3.w}};
-#pragma unroll
-        for (int u = 0; u < 4; ++u) {
-          const float4 wl = *reinterpret_cast<const float4*>(w_s + (ci + u) * N + g4);
-          const float4 wh = *reinterpret_cast<const float4*>(w_s + (ci + u) * N + nh + g4);
-#pragma unroll
-          for (int p = 0; p < 4; ++p) {
-            fma4(acc[p], 0, av[p][u], wl);
-            fma4(acc[p], 4, av[p][u], wh);
-          }
-        }
-      }
-    } else {
-#pragma unroll 1
-      for (int ci = 0; ci < CK; ++ci) {
-        const float av[4] = {p00[ci], p01[ci], p10[ci], p11[ci]};
-        const float4 wl = *reinterpret_cast<const float4*>(w_s + ci * N + g4);
-        const float4 wh = *reinterpret_cast<const float4*>(w_s + ci * N + nh + g4);
-#pragma unroll
-        for (int p = 0; p < 4; ++p) {
-          fma4(acc[p], 0, av[p], wl);
-          fma4(acc[p], 4, av[p], wh);
-        }
-      }
-    }
-  }
-}
-
-struct TileGeom {
-  int QW, QH, nQ, q0, q1, qy0, nrows, BW;
-};
-
-__device__ __forceinline__ TileGeom tile_geom(int H, int W, bool floor_quads, int pc) {
-  TileGeom g;
-  g.QW = floor_quads ? W / 2 : (W + 1) / 2;
-  g.QH = floor_quads ? H / 2 : (H + 1) / 2;
-  g.nQ = g.QH * g.QW;
-  g.q0 = blockIdx.x * 32;
-  g.q1 = min(g.q0 + 32, g.nQ) - 1;
-  g.qy0 = g.q0 / g.QW;
-  const int qy1 = g.q1 / g.QW;
-  g.nrows = 2 * (qy1 - g.qy0 + 1) + 2 * pc;
-  g.BW = 2 * g.QW + 2 * pc;
-  return g;
-}
+using namespace convcore;
 
 template <int KS, bool POOL>
 __global__ void __launch_bounds__(512) conv_fwd_kernel(ConvFwdArgs a) {
@@ -348,12 +269,6 @@ __global__ void pack_conv_kernel(const float* __restrict__ w, float* wf, float* 
 __global__ void bn_prepare_kernel(const float* __restrict__ var, float* invstd, int C, float eps) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i < C) invstd[i] = 1.0f / sqrtf(var[i] + eps);
-}
-
-int band_rows_max(int QH, int QW, int pc) {
-  int span = (32 + QW - 2) / QW + 1;
-  if (span > QH) span = QH;
-  return 2 * span + 2 * pc;
 }
 
 template <typename K>

@@ -17,6 +17,7 @@
 #include "fabcw.cuh"
 #include "frontend.cuh"
 #include "rnn.cuh"
+#include "specrnet.cuh"
 #include "update.cuh"
 
 namespace advb {
@@ -86,6 +87,12 @@ struct advb_handle {
   float *feats = nullptr, *l1 = nullptr, *l2 = nullptr, *gates1 = nullptr, *gates2 = nullptr, *cs1 = nullptr,
         *cs2 = nullptr, *dl2 = nullptr, *dl1 = nullptr, *dfeats = nullptr, *logits = nullptr;
   LstmPacked lp[2]{};
+
+  // SpecRNet
+  SrBlock sr[3]{};
+  SrGru gru{};
+  float *sr_img = nullptr, *sr_bn4 = nullptr;
+  int sr_L = 0;
 
   // attack scratch
   float* conv0_T = nullptr;  // (B,F,80,5) horizontal col2im partial sums of the first block's backward
@@ -391,19 +398,185 @@ int lcnn_backward(advb_handle* h, const float* x, const int64_t* y, int B, int m
   return 0;
 }
 
+// ---- SpecRNet (src/models/specrnet.py) ----
+const char* kSrNames[3] = {"0", "2", "4"};
+
+int check_specrnet_tensors(advb_handle* h) {
+  const int cin[3] = {1, 20, 64}, cout[3] = {20, 64, 64};
+  ADVB_TRY(require(h, "first_bn.weight", 1));
+  ADVB_TRY(require(h, "first_bn.bias", 1));
+  ADVB_TRY(require(h, "first_bn.running_mean", 1));
+  ADVB_TRY(require(h, "first_bn.running_var", 1));
+  for (int i = 0; i < 3; ++i) {
+    const std::string p = std::string("block") + kSrNames[i] + ".0.";
+    ADVB_TRY(require(h, p + "conv1.weight", (int64_t)cout[i] * cin[i] * 9));
+    ADVB_TRY(require(h, p + "conv1.bias", cout[i]));
+    ADVB_TRY(require(h, p + "conv2.weight", (int64_t)cout[i] * cout[i] * 9));
+    ADVB_TRY(require(h, p + "conv2.bias", cout[i]));
+    for (const char* q : {"bn2.weight", "bn2.bias", "bn2.running_mean", "bn2.running_var"}) ADVB_TRY(require(h, p + q, cout[i]));
+    if (cin[i] != cout[i]) {
+      ADVB_TRY(require(h, p + "conv_downsample.weight", (int64_t)cout[i] * cin[i]));
+      ADVB_TRY(require(h, p + "conv_downsample.bias", cout[i]));
+    }
+    const std::string a = std::string("fc_attention") + kSrNames[i] + ".0.";
+    ADVB_TRY(require(h, a + "weight", (int64_t)cout[i] * cout[i]));
+    ADVB_TRY(require(h, a + "bias", cout[i]));
+  }
+  for (const char* q : {"weight", "bias", "running_mean", "running_var"}) ADVB_TRY(require(h, std::string("bn_before_gru.") + q, 64));
+  for (int l = 0; l < 2; ++l)
+    for (int d = 0; d < 2; ++d) {
+      const std::string sfx = "_l" + std::to_string(l) + (d ? "_reverse" : "");
+      ADVB_TRY(require(h, "gru.weight_ih" + sfx, 192 * (l == 0 ? 64 : 128)));
+      ADVB_TRY(require(h, "gru.weight_hh" + sfx, 192 * 64));
+      ADVB_TRY(require(h, "gru.bias_ih" + sfx, 192));
+      ADVB_TRY(require(h, "gru.bias_hh" + sfx, 192));
+    }
+  ADVB_TRY(require(h, "fc1_gru.weight", 128 * 128));
+  ADVB_TRY(require(h, "fc1_gru.bias", 128));
+  ADVB_TRY(require(h, "fc2_gru.weight", 128));
+  ADVB_TRY(require(h, "fc2_gru.bias", 1));
+  return 0;
+}
+
+void bind_specrnet(advb_handle* h) {
+  for (int i = 0; i < 3; ++i) {
+    SrBlock& k = h->sr[i];
+    const std::string p = std::string("block") + kSrNames[i] + ".0.";
+    k.w1 = h->t(p + "conv1.weight"), k.b1 = h->t(p + "conv1.bias");
+    k.w2 = h->t(p + "conv2.weight"), k.b2 = h->t(p + "conv2.bias");
+    k.wds = h->t(p + "conv_downsample.weight"), k.bds = h->t(p + "conv_downsample.bias");
+    k.bn_w = h->t(p + "bn2.weight"), k.bn_b = h->t(p + "bn2.bias");
+    k.bn_rm = h->t(p + "bn2.running_mean"), k.bn_rv = h->t(p + "bn2.running_var");
+    const std::string a = std::string("fc_attention") + kSrNames[i] + ".0.";
+    k.att_w = h->t(a + "weight"), k.att_b = h->t(a + "bias");
+  }
+  SrGru& g = h->gru;
+  for (int l = 0; l < 2; ++l)
+    for (int d = 0; d < 2; ++d) {
+      const std::string sfx = "_l" + std::to_string(l) + (d ? "_reverse" : "");
+      g.w_ih[l][d] = h->t("gru.weight_ih" + sfx), g.w_hh[l][d] = h->t("gru.weight_hh" + sfx);
+      g.b_ih[l][d] = h->t("gru.bias_ih" + sfx), g.b_hh[l][d] = h->t("gru.bias_hh" + sfx);
+    }
+  g.fc1_w = h->t("fc1_gru.weight"), g.fc1_b = h->t("fc1_gru.bias");
+  g.fc2_w = h->t("fc2_gru.weight"), g.fc2_b = h->t("fc2_gru.bias");
+  g.bn_w = h->t("bn_before_gru.weight"), g.bn_b = h->t("bn_before_gru.bias");
+  g.bn_rm = h->t("bn_before_gru.running_mean"), g.bn_rv = h->t("bn_before_gru.running_var");
+}
+
+int build_specrnet(advb_handle* h) {
+  const size_t B = h->Bmax;
+  ADVB_TRY(check_specrnet_tensors(h));
+  const int cin[3] = {1, 20, 64}, cout[3] = {20, 64, 64};
+  int H = h->F, W = 80;
+  ADVB_TRY(h->alloc(&h->sr_img, B * (H + 2) * (W + 2)));
+  ADVB_TRY(h->alloc(&h->sr_bn4, 4));
+  for (int i = 0; i < 3; ++i) {
+    SrBlock& k = h->sr[i];
+    k.Cin = cin[i], k.Cout = cout[i];
+    k.Ci = cin[i] == 1 ? 1 : (cin[i] + 7) / 8 * 8;
+    k.C = (cout[i] + 7) / 8 * 8;
+    k.H = H, k.W = W, k.Hb = H / 2, k.Wb = W / 2, k.Hn = k.Hb / 2, k.Wn = k.Wb / 2;
+    ADVB_CHECK(k.Hn > 0 && k.Wn > 0, "clip too short for the SpecRNet pooling stack");
+    k.downsample = cin[i] != cout[i];
+    k.n_tiles = sr_conv2_tiles(H, W);
+    k.xn_pad = i < 2 ? 1 : 0;
+    const size_t C = k.C;
+    ADVB_TRY(h->alloc(&k.w1f, 9 * (size_t)k.Ci * C));
+    ADVB_TRY(h->alloc(&k.w1d, 9 * C * (size_t)(k.Ci < 8 ? 8 : k.Ci)));
+    ADVB_TRY(h->alloc(&k.w2f, 9 * C * C));
+    ADVB_TRY(h->alloc(&k.w2d, 9 * C * C));
+    ADVB_TRY(h->alloc(&k.wdf, (size_t)k.Ci * C));
+    ADVB_TRY(h->alloc(&k.wdd, C * (size_t)(k.Ci < 8 ? 8 : k.Ci)));
+    ADVB_TRY(h->alloc(&k.b1p, C));
+    ADVB_TRY(h->alloc(&k.b2p, C));
+    ADVB_TRY(h->alloc(&k.bdp, C));
+    ADVB_TRY(h->alloc(&k.bn_scale, C));
+    ADVB_TRY(h->alloc(&k.bn_shift, C));
+    ADVB_TRY(h->alloc(&k.h, B * (H + 2) * (W + 2) * C));
+    ADVB_TRY(h->alloc(&k.xb, B * k.Hb * k.Wb * C));
+    ADVB_TRY(h->alloc(&k.code1, B * k.Hb * k.Wb * C));
+    ADVB_TRY(h->alloc(&k.psum, B * k.n_tiles * C));
+    ADVB_TRY(h->alloc(&k.y, B * C));
+    ADVB_TRY(h->alloc(&k.xn, B * (k.Hn + 2 * k.xn_pad) * (k.Wn + 2 * k.xn_pad) * C));
+    ADVB_TRY(h->alloc(&k.code2, B * k.Hn * k.Wn * C));
+    ADVB_TRY(h->alloc(&k.g_xn, B * k.Hn * k.Wn * C));
+    ADVB_TRY(h->alloc(&k.gadd, B * C));
+    ADVB_TRY(h->alloc(&k.g_c1, B * H * W * C));
+    H = k.Hn, W = k.Wn;
+  }
+  ADVB_CHECK(W == 1, "SpecRNet expects the coefficient axis to pool down to 1");
+  h->sr_L = H;
+  SrGru& g = h->gru;
+  for (int l = 0; l < 2; ++l)
+    for (int d = 0; d < 2; ++d) {
+      ADVB_TRY(h->alloc(&g.wihT[l][d], 192 * (size_t)(l == 0 ? 64 : 128)));
+      ADVB_TRY(h->alloc(&g.whhT[l][d], 192 * 64));
+    }
+  ADVB_TRY(h->alloc(&g.v, 128));
+  ADVB_TRY(h->alloc(&g.bn_scale, 64));
+  ADVB_TRY(h->alloc(&g.bn_shift, 64));
+  ADVB_TRY(h->alloc(&g.gates, B * 2 * 2 * h->sr_L * 256));
+  ADVB_TRY(h->alloc(&g.outs, B * 2 * h->sr_L * 128));
+  ADVB_TRY(h->alloc(&g.xin, B * h->sr_L * 64));
+  return 0;
+}
+
+int prepare_specrnet(advb_handle* h, cudaStream_t st) {
+  refresh_frontend_tables(h);
+  ADVB_TRY(frontend_prepare(h->ftb, st));
+  bind_specrnet(h);
+  ADVB_TRY(sr_pack_first_bn(h->t("first_bn.weight"), h->t("first_bn.bias"), h->t("first_bn.running_mean"),
+                            h->t("first_bn.running_var"), h->sr_bn4, st));
+  for (int i = 0; i < 3; ++i) ADVB_TRY(sr_pack_block(h->sr[i], st));
+  ADVB_TRY(sr_pack_gru(h->gru, st));
+  return 0;
+}
+
+int specrnet_forward(advb_handle* h, const float* x, int B, cudaStream_t st) {
+  const int F = h->F;
+  ADVB_TRY(frontend_forward(h->ftb, h->fst, x, B, h->T, h->dB, h->sr_img, (long long)(F + 2) * 82, 82, 1, 82 + 1, st));
+  ADVB_TRY(sr_input_forward(h->sr_img, h->sr_bn4, B, F, 80, st));
+  const float* in = h->sr_img;
+  const char* tags[3] = {"sr_b0", "sr_b2", "sr_b4"};
+  for (int i = 0; i < 3; ++i) {
+    ADVB_TRY(sr_block_forward(h->sr[i], in, B, tags[i], st));
+    in = h->sr[i].xn;
+  }
+  ADVB_TRY(sr_gru_forward(h->gru, h->sr[2].xn, h->logits, B, h->sr_L, st));
+  return 0;
+}
+
+int specrnet_backward(advb_handle* h, const float* x, const int64_t* y, int B, int mode, int n_global, float* gx,
+                      cudaStream_t st, const float* coef) {
+  ADVB_TRY(sr_gru_backward(h->gru, h->sr[2].xn, h->logits, reinterpret_cast<const long long*>(y), mode, n_global, coef,
+                           h->sr[2].g_xn, B, h->sr_L, st));
+  const char* tags[3] = {"sr_b0", "sr_b2", "sr_b4"};
+  for (int i = 2; i >= 0; --i) {
+    const float* in = i == 0 ? h->sr_img : h->sr[i - 1].xn;
+    float* gin = i == 0 ? h->g_coef : h->sr[i - 1].g_xn;
+    ADVB_TRY(sr_block_backward(h->sr[i], in, gin, B, i == 0, h->sr_bn4, tags[i], st));
+  }
+  ADVB_TRY(frontend_backward(h->ftb, h->fst, x, B, h->T, h->dB, h->g_coef, (long long)h->F * 80, 80, 1, h->mass_partial,
+                             gx, st));
+  return 0;
+}
+
 int model_prepare(advb_handle* h, cudaStream_t st) {
   if (h->model_kind == ADVB_MODEL_LCNN) return prepare_lcnn(h, st);
+  if (h->model_kind == ADVB_MODEL_SPECRNET) return prepare_specrnet(h, st);
   set_error("model kind not implemented");
   return 1;
 }
 int model_forward(advb_handle* h, const float* x, int B, cudaStream_t st) {
   if (h->model_kind == ADVB_MODEL_LCNN) return lcnn_forward(h, x, B, st);
+  if (h->model_kind == ADVB_MODEL_SPECRNET) return specrnet_forward(h, x, B, st);
   set_error("model kind not implemented");
   return 1;
 }
 int model_backward(advb_handle* h, const float* x, const int64_t* y, int B, int mode, int n_global, float* gx,
                    cudaStream_t st, const float* coef = nullptr) {
   if (h->model_kind == ADVB_MODEL_LCNN) return lcnn_backward(h, x, y, B, mode, n_global, gx, st, coef);
+  if (h->model_kind == ADVB_MODEL_SPECRNET) return specrnet_backward(h, x, y, B, mode, n_global, gx, st, coef);
   set_error("model kind not implemented");
   return 1;
 }
@@ -485,8 +658,8 @@ int advb_create(advb_handle** out, const advb_model_desc* d) {
     return 1;
   };
   if (bind_tensors(h, d->n_tensors, d->tensors)) return fail();
-  if (h->model_kind != ADVB_MODEL_LCNN) {
-    set_error("model kind not implemented yet (LCNN only)");
+  if (h->model_kind != ADVB_MODEL_LCNN && h->model_kind != ADVB_MODEL_SPECRNET) {
+    set_error("model kind not implemented yet (LCNN and SpecRNet only)");
     return fail();
   }
   if (check_frontend_tensors(h)) return fail();
@@ -501,7 +674,7 @@ int advb_create(advb_handle** out, const advb_model_desc* d) {
       h->alloc(&h->partial_d, B * ROW_CHUNKS))
     return fail();
   if (frontend_init_constants(h->twr, h->twi, 0)) return fail();
-  if (build_lcnn(h)) return fail();
+  if (h->model_kind == ADVB_MODEL_LCNN ? build_lcnn(h) : build_specrnet(h)) return fail();
   if (cudaDeviceSynchronize() != cudaSuccess) {
     set_error("device error during advb_create");
     return fail();
@@ -542,6 +715,7 @@ int advb_rebind(advb_handle* h, int n_tensors, const advb_tensor_ref* tensors) {
   ADVB_TRY(bind_tensors(h, n_tensors, tensors));
   ADVB_TRY(check_frontend_tensors(h));
   if (h->model_kind == ADVB_MODEL_LCNN) ADVB_TRY(check_lcnn_tensors(h));
+  if (h->model_kind == ADVB_MODEL_SPECRNET) ADVB_TRY(check_specrnet_tensors(h));
   return 0;
 }
 
@@ -770,7 +944,18 @@ int64_t advb_debug_stage(advb_handle* h, const char* stage, float* dst, int64_t 
     d[3] = a.C;
     d[4] = a.pad;
   };
-  if (s == "frontend") from_act(h->act0);
+  const bool is_sr = h->model_kind == ADVB_MODEL_SPECRNET;
+  auto sr_idx = [&](char c) { return c == '0' ? 0 : c == '2' ? 1 : c == '4' ? 2 : -1; };
+  if (is_sr && s == "frontend") {
+    src = h->sr_img;
+    d[1] = h->F, d[2] = 80, d[3] = 1, d[4] = 1;
+  } else if (is_sr && s.size() == 6 && (s.rfind("sr_xb", 0) == 0 || s.rfind("sr_xn", 0) == 0 || s.rfind("sr_gn", 0) == 0) &&
+             sr_idx(s[5]) >= 0) {
+    const SrBlock& k = h->sr[sr_idx(s[5])];
+    const bool xb = s[4] == 'b', xn = s[3] == 'x' && s[4] == 'n';
+    src = xb ? k.xb : xn ? k.xn : k.g_xn;
+    d[1] = xb ? k.Hb : k.Hn, d[2] = xb ? k.Wb : k.Wn, d[3] = k.C, d[4] = xn ? k.xn_pad : 0;
+  } else if (s == "frontend") from_act(h->act0);
   else if (s.rfind("block", 0) == 0 && s.size() == 6 && s[5] >= '0' && s[5] <= '8') from_act(h->blk[s[5] - '0'].out);
   else if (s.rfind("gblock", 0) == 0 && s.size() == 7 && s[6] >= '0' && s[6] <= '8') {
     const LcnnBlock& k = h->blk[s[6] - '0'];

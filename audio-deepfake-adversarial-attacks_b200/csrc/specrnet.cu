@@ -1,0 +1,789 @@
+// SpecRNet forward and input-gradient backward (sm_100a, fp32 SIMT first path).
+//
+// Replaces src/models/specrnet.py:73-91 (Residual_block2D; its bn1/lrelu output is discarded by the reference, so the
+// effective block is conv1(x) -> bn2 -> LeakyReLU(0.3) -> conv2 (+ conv_downsample(x) | + x) -> MaxPool2d(2)),
+// :139-181 (first_bn + SELU, three blocks each followed by y = sigmoid(fc(avgpool)), x*y + y, MaxPool2d(2);
+// bn_before_gru + SELU, 2-layer bidirectional GRU, last time step, fc1_gru, fc2_gru) and the autograd input gradient.
+//
+// Layout: [frames][coeffs][channels] fp32 (the transposed cepstral image, as on the LCNN path; conv taps are
+// transposed while packing), zero border of 1 pixel where a 3x3 conv consumes the tensor, channels padded to a multiple
+// of 8 (20 -> 24) with zero weights so padded channels stay exactly 0.
+//
+// Per block, forward:   F1  h  = lrelu(bn2(conv1(x)))                                      (B,H,W,C)
+//                       F2  xb = maxpool(conv2(h) + identity(x)) + 2-bit arg-max + partial channel sums
+//                       ATT y  = sigmoid(fc(mean xb))                                      (B,C)
+//                       SP  xn = maxpool(xb * y + y) + 2-bit arg-max
+// backward (no conv input is needed; the expanded gradient g_o of the conv2 output is rebuilt on the fly
+// from g_xn, the two arg-max codes, y and the attention broadcast term and never stored):
+//                       ATT' gadd = fc^T(gy * y(1-y)) / (Hb Wb),  gy = sum g_u (xb + 1)
+//                       B2  g_c1 = conv2^T(g_o) * lrelu'(h) * bn2 scale
+//                       B1  g_x  = conv1^T(g_c1) + downsample^T(g_o) | + g_o
+// Algorithmic HBM bytes per clip: every tensor above written once and read once (bench.py kernel_bytes).
+#include "specrnet.cuh"
+
+#include "conv_core.cuh"
+
+namespace advb {
+
+namespace {
+
+using namespace convcore;
+
+constexpr float SELU_ALPHA = 1.6732632423543772f;
+constexpr float SELU_SCALE = 1.0507009873554805f;
+__device__ __forceinline__ float selu_f(float u) { return u > 0.f ? SELU_SCALE * u : SELU_SCALE * SELU_ALPHA * expm1f(u); }
+// derivative expressed with the OUTPUT v = selu(u): u > 0 <=> v > 0; for u <= 0, scale*alpha*e^u = v + scale*alpha
+__device__ __forceinline__ float selu_grad_from_out(float v) { return v > 0.f ? SELU_SCALE : v + SELU_SCALE * SELU_ALPHA; }
+
+enum { F1 = 0, F2 = 1, B2 = 2, B1 = 3 };
+
+struct SrArgs {
+  int B, H, W, CK, N;   // conv grid; contraction channels as staged (padded); output channels (padded)
+  int Hb, Wb, Hn, Wn, C;  // pooled grids and block-output channels (padded) for the gradient expansion
+  const float* in;      // F1: x (bordered 1), F2: h (bordered 1), B1: g_c1 (compact)
+  const float* wpk;     // [tap][CK][N]
+  const float* bias;    // (N) padded
+  const float* scale;   // bn2 scale / shift (padded)
+  const float* shift;
+  float* out;
+  int out_pad;
+  const float* x;       // block input, bordered 1 (identity path of F2)
+  int Ci;               // its channels (padded)
+  const float* wd;      // F2: downsample [Ci][N] or null;  B1: downsample^T [C][N] or null
+  const float* bd;
+  unsigned char* code1w;
+  float* psum;
+  const float* g_xn;
+  const unsigned char* code2;
+  const unsigned char* code1;
+  const float* y;
+  const float* gadd;
+  const float* h;
+};
+
+// 4 consecutive channels (c..c+3) of the gradient at conv2's output pixel (yy, xx): un-pool of
+// g_xb = unpool2(g_xn) * y + gadd through the block's own max-pool.
+__device__ __forceinline__ float4 expand_go(const SrArgs& a, int b, int yy, int xx, int c) {
+  float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (yy < 0 || yy >= a.H || xx < 0 || xx >= a.W) return v;
+  const int cy = yy >> 1, cx = xx >> 1;
+  if (cy >= a.Hb || cx >= a.Wb) return v;
+  const size_t o1 = (((size_t)b * a.Hb + cy) * a.Wb + cx) * a.C + c;
+  const uchar4 c1 = __ldg(reinterpret_cast<const uchar4*>(a.code1 + o1));
+  const unsigned pos1 = (unsigned)(((yy & 1) << 1) | (xx & 1));
+  if (c1.x != pos1 && c1.y != pos1 && c1.z != pos1 && c1.w != pos1) return v;
+  float4 g = __ldg(reinterpret_cast<const float4*>(a.gadd + (size_t)b * a.C + c));
+  const int ny = cy >> 1, nx = cx >> 1;
+  if (ny < a.Hn && nx < a.Wn) {
+    const size_t o2 = (((size_t)b * a.Hn + ny) * a.Wn + nx) * a.C + c;
+    const uchar4 c2 = __ldg(reinterpret_cast<const uchar4*>(a.code2 + o2));
+    const float4 gn = __ldg(reinterpret_cast<const float4*>(a.g_xn + o2));
+    const float4 yv = __ldg(reinterpret_cast<const float4*>(a.y + (size_t)b * a.C + c));
+    const unsigned pos2 = (unsigned)(((cy & 1) << 1) | (cx & 1));
+    if (c2.x == pos2) g.x += gn.x * yv.x;
+    if (c2.y == pos2) g.y += gn.y * yv.y;
+    if (c2.z == pos2) g.z += gn.z * yv.z;
+    if (c2.w == pos2) g.w += gn.w * yv.w;
+  }
+  v.x = c1.x == pos1 ? g.x : 0.f;
+  v.y = c1.y == pos1 ? g.y : 0.f;
+  v.z = c1.z == pos1 ? g.z : 0.f;
+  v.w = c1.w == pos1 ? g.w : 0.f;
+  return v;
+}
+
+template <int MODE>
+__global__ void __launch_bounds__(256) sr_conv_kernel(SrArgs a, int band_floats) {
+  extern __shared__ __align__(16) float smem[];
+  __shared__ float s_part[MODE == F2 ? 32 * 64 : 1];
+  const TileGeom g = tile_geom(a.H, a.W, MODE == F2, 1);
+  const int CK = a.CK;
+  const int CKp = (CK & 3) == 0 ? CK + 4 : CK;
+  float* band = smem;
+  float* w_s = smem + band_floats;
+  const int b = blockIdx.y, tid = threadIdx.x, nt = blockDim.x;
+
+  // ---- stage the band: rows 2*qy0-1 ..., columns -1 .. 2*QW ----
+  if (MODE == F1 || MODE == F2) {
+    const int Hp = a.H + 2, Wp = a.W + 2;
+    const float* inb = a.in + (size_t)b * Hp * Wp * CK;
+    if ((CK & 3) == 0) {
+      const int c4n = CK >> 2, total = g.nrows * g.BW * c4n;
+      for (int i = tid; i < total; i += nt) {
+        const int c4 = i % c4n, col = (i / c4n) % g.BW, r = i / (c4n * g.BW);
+        const int yp = 2 * g.qy0 + r, xp = col;  // (-1 + r) + pad 1
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (yp < Hp && xp < Wp) v = __ldg(reinterpret_cast<const float4*>(inb + ((size_t)yp * Wp + xp) * CK + 4 * c4));
+        *reinterpret_cast<float4*>(band + ((size_t)r * g.BW + col) * CKp + 4 * c4) = v;
+      }
+    } else {
+      const int total = g.nrows * g.BW * CK;
+      for (int i = tid; i < total; i += nt) {
+        const int c = i % CK, col = (i / CK) % g.BW, r = i / (CK * g.BW);
+        const int yp = 2 * g.qy0 + r, xp = col;
+        float v = 0.f;
+        if (yp < Hp && xp < Wp) v = __ldg(inb + ((size_t)yp * Wp + xp) * CK + c);
+        band[((size_t)r * g.BW + col) * CKp + c] = v;
+      }
+    }
+  } else {
+    const int c4n = CK >> 2, total = g.nrows * g.BW * c4n;
+    for (int i = tid; i < total; i += nt) {
+      const int c4 = i % c4n, col = (i / c4n) % g.BW, r = i / (c4n * g.BW);
+      const int y = 2 * g.qy0 - 1 + r, x = col - 1;
+      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (MODE == B2) {
+        v = expand_go(a, b, y, x, 4 * c4);
+      } else if (y >= 0 && y < a.H && x >= 0 && x < a.W) {
+        v = __ldg(reinterpret_cast<const float4*>(a.in + (((size_t)b * a.H + y) * a.W + x) * CK + 4 * c4));
+      }
+      *reinterpret_cast<float4*>(band + ((size_t)r * g.BW + col) * CKp + 4 * c4) = v;
+    }
+  }
+
+  const int N = a.N, G = N >> 3;
+  const int cg = tid % G, ql = tid / G;
+  const int q = g.q0 + ql;
+  const bool valid = q <= g.q1;
+  const int qy = q / g.QW, qx = q % g.QW;
+  float acc[4][8];
+#pragma unroll
+  for (int p = 0; p < 4; ++p)
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[p][j] = 0.f;
+  conv_core<3>(band, g.BW, CK, CKp, a.wpk, w_s, N, 2 * (qy - g.qy0), 2 * qx, 4 * cg, valid, acc);
+
+  const int nh = N >> 1, c0 = 4 * cg;
+  if (MODE == F1) {
+    if (!valid) return;
+    const int Hp = a.H + 2, Wp = a.W + 2;
+#pragma unroll
+    for (int p = 0; p < 4; ++p) {
+      const int y = 2 * qy + (p >> 1), x = 2 * qx + (p & 1);
+      if (y >= a.H || x >= a.W) continue;
+      float o[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const int c = (j < 4 ? c0 : nh + c0 - 4) + j;
+        float v = acc[p][j] + __ldg(a.bias + c);
+        v = fmaf(v, __ldg(a.scale + c), __ldg(a.shift + c));
+        o[j] = v > 0.f ? v : 0.3f * v;
+      }
+      float* dst = a.out + (((size_t)b * Hp + y + 1) * Wp + x + 1) * N;
+      *reinterpret_cast<float4*>(dst + c0) = make_float4(o[0], o[1], o[2], o[3]);
+      *reinterpret_cast<float4*>(dst + nh + c0) = make_float4(o[4], o[5], o[6], o[7]);
+    }
+  } else if (MODE == F2) {
+    float best[8];
+    unsigned char code[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      best[j] = 0.f;
+      code[j] = 0;
+    }
+    if (valid) {
+      const int Hp = a.H + 2, Wp = a.W + 2;
+      float idv[4][8];
+#pragma unroll
+      for (int p = 0; p < 4; ++p) {
+        const int y = 2 * qy + (p >> 1), x = 2 * qx + (p & 1);
+        const float* xp = a.x + (((size_t)b * Hp + y + 1) * Wp + x + 1) * a.Ci;
+        if (a.wd != nullptr) {
+#pragma unroll
+          for (int j = 0; j < 8; ++j) idv[p][j] = 0.f;
+          for (int ci = 0; ci < a.Ci; ++ci) {
+            const float xv = __ldg(xp + ci);
+            const float4 wl = __ldg(reinterpret_cast<const float4*>(a.wd + (size_t)ci * N + c0));
+            const float4 wh = __ldg(reinterpret_cast<const float4*>(a.wd + (size_t)ci * N + nh + c0));
+            fma4(idv[p], 0, xv, wl);
+            fma4(idv[p], 4, xv, wh);
+          }
+#pragma unroll
+          for (int j = 0; j < 8; ++j) idv[p][j] += __ldg(a.bd + (j < 4 ? c0 : nh + c0 - 4) + j);
+        } else {
+          const float4 lo = __ldg(reinterpret_cast<const float4*>(xp + c0));
+          const float4 hi = __ldg(reinterpret_cast<const float4*>(xp + nh + c0));
+          idv[p][0] = lo.x, idv[p][1] = lo.y, idv[p][2] = lo.z, idv[p][3] = lo.w;
+          idv[p][4] = hi.x, idv[p][5] = hi.y, idv[p][6] = hi.z, idv[p][7] = hi.w;
+        }
+      }
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const float bj = __ldg(a.bias + (j < 4 ? c0 : nh + c0 - 4) + j);
+        float bv = (acc[0][j] + bj) + idv[0][j];
+        unsigned cd = 0;
+#pragma unroll
+        for (int p = 1; p < 4; ++p) {
+          const float v = (acc[p][j] + bj) + idv[p][j];
+          if (v > bv) {
+            bv = v;
+            cd = (unsigned)p;
+          }
+        }
+        best[j] = bv;
+        code[j] = (unsigned char)cd;
+      }
+      const size_t o = (((size_t)b * a.Hb + qy) * a.Wb + qx) * N;
+      *reinterpret_cast<float4*>(a.out + o + c0) = make_float4(best[0], best[1], best[2], best[3]);
+      *reinterpret_cast<float4*>(a.out + o + nh + c0) = make_float4(best[4], best[5], best[6], best[7]);
+      *reinterpret_cast<uchar4*>(a.code1w + o + c0) = make_uchar4(code[0], code[1], code[2], code[3]);
+      *reinterpret_cast<uchar4*>(a.code1w + o + nh + c0) = make_uchar4(code[4], code[5], code[6], code[7]);
+    }
+    // deterministic partial channel sums of this CTA's quads (avgpool of the attention)
+#pragma unroll
+    for (int j = 0; j < 8; ++j) s_part[ql * 64 + (j < 4 ? c0 : nh + c0 - 4) + j] = valid ? best[j] : 0.f;
+    __syncthreads();
+    if (tid < N) {
+      float s = 0.f;
+      for (int r = 0; r < 32; ++r) s += s_part[r * 64 + tid];
+      a.psum[((size_t)b * gridDim.x + blockIdx.x) * N + tid] = s;
+    }
+  } else if (MODE == B2) {
+    if (!valid) return;
+    const int Hp = a.H + 2, Wp = a.W + 2;
+#pragma unroll
+    for (int p = 0; p < 4; ++p) {
+      const int y = 2 * qy + (p >> 1), x = 2 * qx + (p & 1);
+      if (y >= a.H || x >= a.W) continue;
+      const float* hp = a.h + (((size_t)b * Hp + y + 1) * Wp + x + 1) * N;
+      const float4 hl = __ldg(reinterpret_cast<const float4*>(hp + c0));
+      const float4 hh = __ldg(reinterpret_cast<const float4*>(hp + nh + c0));
+      const float hv[8] = {hl.x, hl.y, hl.z, hl.w, hh.x, hh.y, hh.z, hh.w};
+      float o[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const int c = (j < 4 ? c0 : nh + c0 - 4) + j;
+        o[j] = acc[p][j] * (hv[j] > 0.f ? 1.0f : 0.3f) * __ldg(a.scale + c);
+      }
+      float* dst = a.out + (((size_t)b * a.H + y) * a.W + x) * N;
+      *reinterpret_cast<float4*>(dst + c0) = make_float4(o[0], o[1], o[2], o[3]);
+      *reinterpret_cast<float4*>(dst + nh + c0) = make_float4(o[4], o[5], o[6], o[7]);
+    }
+  } else {  // B1
+    if (!valid) return;
+#pragma unroll
+    for (int p = 0; p < 4; ++p) {
+      const int y = 2 * qy + (p >> 1), x = 2 * qx + (p & 1);
+      if (y >= a.H || x >= a.W) continue;
+      float o[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) o[j] = acc[p][j];
+      if (a.wd != nullptr) {  // + conv_downsample^T(g_o)
+        for (int co = 0; co < a.C; co += 4) {
+          const float4 go = expand_go(a, b, y, x, co);
+          const float gv[4] = {go.x, go.y, go.z, go.w};
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            if (gv[u] == 0.f) continue;
+            const float4 wl = __ldg(reinterpret_cast<const float4*>(a.wd + (size_t)(co + u) * N + c0));
+            const float4 wh = __ldg(reinterpret_cast<const float4*>(a.wd + (size_t)(co + u) * N + nh + c0));
+            fma4(o, 0, gv[u], wl);
+            fma4(o, 4, gv[u], wh);
+          }
+        }
+      } else {  // + g_o (identity shortcut)
+        const float4 gl = expand_go(a, b, y, x, c0), gh = expand_go(a, b, y, x, nh + c0);
+        o[0] += gl.x, o[1] += gl.y, o[2] += gl.z, o[3] += gl.w;
+        o[4] += gh.x, o[5] += gh.y, o[6] += gh.z, o[7] += gh.w;
+      }
+      float* dst = a.out + (((size_t)b * a.H + y) * a.W + x) * N;
+      *reinterpret_cast<float4*>(dst + c0) = make_float4(o[0], o[1], o[2], o[3]);
+      *reinterpret_cast<float4*>(dst + nh + c0) = make_float4(o[4], o[5], o[6], o[7]);
+    }
+  }
+}
+
+// First block, backward of conv1 (C -> 1 channel) + downsample^T + SELU' + first_bn scale: one thread per pixel.
+__global__ void __launch_bounds__(256) sr_first_bwd_kernel(SrArgs a, const float* __restrict__ w1 /*[co][3][3] ref layout*/,
+                                                            const float* __restrict__ wds /*[co]*/, int Cout,
+                                                            const float* __restrict__ bn4, float* __restrict__ g_feat) {
+  __shared__ float s_w[9 * 64];
+  __shared__ float s_d[64];
+  const int C = a.C;
+  for (int i = threadIdx.x; i < 9 * C; i += blockDim.x) {
+    const int co = i % C, tap = i / C;  // tap = r*3 + c over (frames, coeffs); flipped for the transpose
+    const int r = tap / 3, c = tap % 3;
+    // reference weight w[co][0][kh = coeff][kw = frame]; correlation transpose: g_x[p] = sum_t g[p - t] w[t]
+    s_w[i] = co < Cout ? w1[co * 9 + (2 - c) * 3 + (2 - r)] : 0.f;
+  }
+  for (int i = threadIdx.x; i < C; i += blockDim.x) s_d[i] = i < Cout ? wds[i] : 0.f;
+  __syncthreads();
+  const int b = blockIdx.y;
+  const int px = blockIdx.x * blockDim.x + threadIdx.x;
+  if (px >= a.H * a.W) return;
+  const int y = px / a.W, x = px % a.W;
+  float acc = 0.f;
+#pragma unroll 1
+  for (int tap = 0; tap < 9; ++tap) {
+    const int yy = y + tap / 3 - 1, xx = x + tap % 3 - 1;
+    if (yy < 0 || yy >= a.H || xx < 0 || xx >= a.W) continue;
+    const float* gp = a.in + (((size_t)b * a.H + yy) * a.W + xx) * C;
+    const float* wp = s_w + tap * C;
+    for (int c = 0; c < C; c += 4) {
+      const float4 gv = __ldg(reinterpret_cast<const float4*>(gp + c));
+      acc = fmaf(gv.x, wp[c], acc);
+      acc = fmaf(gv.y, wp[c + 1], acc);
+      acc = fmaf(gv.z, wp[c + 2], acc);
+      acc = fmaf(gv.w, wp[c + 3], acc);
+    }
+  }
+  for (int c = 0; c < C; c += 4) {
+    const float4 go = expand_go(a, b, y, x, c);
+    acc = fmaf(go.x, s_d[c], acc);
+    acc = fmaf(go.y, s_d[c + 1], acc);
+    acc = fmaf(go.z, s_d[c + 2], acc);
+    acc = fmaf(go.w, s_d[c + 3], acc);
+  }
+  const float x0 = __ldg(a.x + ((size_t)b * (a.H + 2) + y + 1) * (a.W + 2) + x + 1);
+  const float sc = __ldg(bn4 + 0) / sqrtf(__ldg(bn4 + 3) + 1e-5f);
+  g_feat[((size_t)b * a.H + y) * a.W + x] = acc * selu_grad_from_out(x0) * sc;
+}
+
+__global__ void sr_input_kernel(float* __restrict__ img, const float* __restrict__ bn4, int H, int W, int64_t n) {
+  const float sc = bn4[0] / sqrtf(bn4[3] + 1e-5f), sh = bn4[1] - bn4[2] * sc;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    const int x = (int)(i % W), y = (int)((i / W) % H);
+    const int64_t b = i / ((int64_t)W * H);
+    float* p = img + (b * (H + 2) + y + 1) * (W + 2) + x + 1;
+    *p = selu_f(fmaf(*p, sc, sh));
+  }
+}
+
+__global__ void __launch_bounds__(64) sr_attention_fwd_kernel(const float* __restrict__ psum, int n_tiles,
+                                                               const float* __restrict__ att_w,
+                                                               const float* __restrict__ att_b, float* __restrict__ y,
+                                                               int C, int Cout, float inv_hw) {
+  __shared__ float s_avg[64];
+  const int b = blockIdx.x, c = threadIdx.x;
+  if (c < C) {
+    float s = 0.f;
+    for (int t = 0; t < n_tiles; ++t) s += psum[((size_t)b * n_tiles + t) * C + c];
+    s_avg[c] = s * inv_hw;
+  }
+  __syncthreads();
+  if (c < C) {
+    float v = 0.f;
+    if (c < Cout) {
+      float z = __ldg(att_b + c);
+      for (int k = 0; k < Cout; ++k) z = fmaf(__ldg(att_w + c * Cout + k), s_avg[k], z);
+      v = 1.0f / (1.0f + expf(-z));
+    }
+    y[(size_t)b * C + c] = v;  // padded channels: 0, so x*y + y stays 0
+  }
+}
+
+__global__ void sr_scale_pool_kernel(const float* __restrict__ xb, const float* __restrict__ y, float* __restrict__ xn,
+                                     unsigned char* __restrict__ code2, int Hb, int Wb, int Hn, int Wn, int C, int pad,
+                                     int64_t n4) {
+  const int C4 = C >> 2;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n4; i += (int64_t)gridDim.x * blockDim.x) {
+    const int c = 4 * (int)(i % C4);
+    const int nx = (int)((i / C4) % Wn), ny = (int)((i / ((int64_t)C4 * Wn)) % Hn);
+    const int64_t b = i / ((int64_t)C4 * Wn * Hn);
+    const float4 yv = *reinterpret_cast<const float4*>(y + b * C + c);
+    float best[4];
+    unsigned cd[4] = {0, 0, 0, 0};
+#pragma unroll
+    for (int p = 0; p < 4; ++p) {
+      const float4 v = *reinterpret_cast<const float4*>(xb + ((b * Hb + 2 * ny + (p >> 1)) * Wb + 2 * nx + (p & 1)) * C + c);
+      const float u[4] = {__fadd_rn(__fmul_rn(v.x, yv.x), yv.x), __fadd_rn(__fmul_rn(v.y, yv.y), yv.y),
+                          __fadd_rn(__fmul_rn(v.z, yv.z), yv.z), __fadd_rn(__fmul_rn(v.w, yv.w), yv.w)};
+#pragma unroll
+      for (int k = 0; k < 4; ++k)
+        if (p == 0 || u[k] > best[k]) {
+          best[k] = u[k];
+          cd[k] = (unsigned)p;
+        }
+    }
+    *reinterpret_cast<float4*>(xn + ((b * (Hn + 2 * pad) + ny + pad) * (Wn + 2 * pad) + nx + pad) * C + c) =
+        make_float4(best[0], best[1], best[2], best[3]);
+    *reinterpret_cast<uchar4*>(code2 + ((b * Hn + ny) * Wn + nx) * C + c) =
+        make_uchar4((unsigned char)cd[0], (unsigned char)cd[1], (unsigned char)cd[2], (unsigned char)cd[3]);
+  }
+}
+
+// gadd[b][k] = (1 / (Hb Wb)) sum_c att_w[c][k] * gy[c] * y[c] (1 - y[c]),  gy[c] = sum_cells g_xn * (xb[winner] + 1)
+__global__ void __launch_bounds__(256) sr_attention_bwd_kernel(const float* __restrict__ g_xn,
+                                                                const unsigned char* __restrict__ code2,
+                                                                const float* __restrict__ xb, const float* __restrict__ y,
+                                                                const float* __restrict__ att_w, float* __restrict__ gadd,
+                                                                int Hb, int Wb, int Hn, int Wn, int C, int Cout,
+                                                                float inv_hw) {
+  __shared__ float s_acc[256];
+  __shared__ float s_gz[64];
+  const int b = blockIdx.x, tid = threadIdx.x;
+  const int R = blockDim.x / C;
+  const int c = tid % C, r = tid / C;
+  float acc = 0.f;
+  if (r < R) {
+    for (int cell = r; cell < Hn * Wn; cell += R) {
+      const int ny = cell / Wn, nx = cell % Wn;
+      const size_t o2 = (((size_t)b * Hn + ny) * Wn + nx) * C + c;
+      const unsigned p = code2[o2];
+      const float xv = xb[(((size_t)b * Hb + 2 * ny + (p >> 1)) * Wb + 2 * nx + (p & 1)) * C + c];
+      acc = fmaf(g_xn[o2], xv + 1.0f, acc);
+    }
+  }
+  s_acc[tid] = acc;
+  __syncthreads();
+  if (tid < C) {
+    float s = 0.f;
+    for (int k = 0; k < R; ++k) s += s_acc[k * C + tid];
+    const float yv = y[(size_t)b * C + tid];
+    s_gz[tid] = tid < Cout ? s * yv * (1.0f - yv) : 0.f;
+  }
+  __syncthreads();
+  if (tid < C) {
+    float s = 0.f;
+    if (tid < Cout)
+      for (int cc = 0; cc < Cout; ++cc) s = fmaf(__ldg(att_w + cc * Cout + tid), s_gz[cc], s);
+    gadd[(size_t)b * C + tid] = s * inv_hw;
+  }
+}
+
+// ---- packing (live weights -> engine layouts) ----
+// fwd: dst[((r*3+c)*CK + ci)*N + n] = w[n][ci][kh=c][kw=r];  bwd: dst[((r*3+c)*CKb + co)*Nb + ci] = w[co][ci][2-c][2-r]
+__global__ void sr_pack_conv_kernel(const float* __restrict__ w, float* __restrict__ dst, int Cout, int Cin, int CK, int N,
+                                    int bwd) {
+  const int total = 9 * CK * N;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+    const int n = i % N, k = (i / N) % CK, tap = i / (N * CK);
+    const int r = tap / 3, c = tap % 3;
+    float v = 0.f;
+    if (!bwd) {
+      if (n < Cout && k < Cin) v = w[((size_t)(n * Cin + k) * 3 + c) * 3 + r];
+    } else {
+      if (k < Cout && n < Cin) v = w[((size_t)(k * Cin + n) * 3 + (2 - c)) * 3 + (2 - r)];
+    }
+    dst[i] = v;
+  }
+}
+// 1x1: fwd dst[ci*N + n] = w[n][ci]; bwd dst[co*Nb + ci] = w[co][ci]
+__global__ void sr_pack_1x1_kernel(const float* __restrict__ w, float* __restrict__ dst, int Cout, int Cin, int K, int N,
+                                   int bwd) {
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < K * N; i += gridDim.x * blockDim.x) {
+    const int n = i % N, k = i / N;
+    float v = 0.f;
+    if (!bwd) {
+      if (n < Cout && k < Cin) v = w[n * Cin + k];
+    } else {
+      if (k < Cout && n < Cin) v = w[k * Cin + n];
+    }
+    dst[i] = v;
+  }
+}
+__global__ void sr_pack_vec_kernel(const float* __restrict__ b1, const float* __restrict__ b2, const float* __restrict__ bd,
+                                   const float* __restrict__ bn_w, const float* __restrict__ bn_b,
+                                   const float* __restrict__ bn_rm, const float* __restrict__ bn_rv, float* b1p, float* b2p,
+                                   float* bdp, float* scale, float* shift, int Cout, int C) {
+  const int c = threadIdx.x;
+  if (c >= C) return;
+  const bool ok = c < Cout;
+  b1p[c] = ok ? b1[c] : 0.f;
+  b2p[c] = ok ? b2[c] : 0.f;
+  bdp[c] = (ok && bd != nullptr) ? bd[c] : 0.f;
+  const float sc = ok ? bn_w[c] / sqrtf(bn_rv[c] + 1e-5f) : 0.f;
+  scale[c] = sc;
+  shift[c] = ok ? bn_b[c] - bn_rm[c] * sc : 0.f;
+}
+
+// ---- GRU + head ----
+constexpr int GH = 64, G3 = 192, GL_MAX = 16;
+
+__global__ void sr_gru_pack_kernel(SrGru g) {
+  // transposes [192][K] -> [K][192]; head vector v = fc2 . fc1; bn_before_gru scale / shift
+  const int tid = blockIdx.x * blockDim.x + threadIdx.x, nthr = gridDim.x * blockDim.x;
+  for (int l = 0; l < 2; ++l)
+    for (int d = 0; d < 2; ++d) {
+      const int K = l == 0 ? 64 : 128;
+      for (int i = tid; i < G3 * K; i += nthr) g.wihT[l][d][(i % K) * G3 + i / K] = g.w_ih[l][d][i];
+      for (int i = tid; i < G3 * GH; i += nthr) g.whhT[l][d][(i % GH) * G3 + i / GH] = g.w_hh[l][d][i];
+    }
+  for (int k = tid; k < 128; k += nthr) {
+    float s = 0.f;
+    for (int j = 0; j < 128; ++j) s = fmaf(g.fc2_w[j], g.fc1_w[j * 128 + k], s);
+    g.v[k] = s;
+  }
+  for (int c = tid; c < 64; c += nthr) {
+    const float sc = g.bn_w[c] / sqrtf(g.bn_rv[c] + 1e-5f);
+    g.bn_scale[c] = sc;
+    g.bn_shift[c] = g.bn_b[c] - g.bn_rm[c] * sc;
+  }
+}
+
+__device__ __forceinline__ float sigmoid_f(float v) { return 1.0f / (1.0f + expf(-v)); }
+
+// One CTA per clip, 384 threads = 2 directions x 192 gate rows.
+__global__ void __launch_bounds__(384) sr_gru_fwd_kernel(SrGru g, const float* __restrict__ xn, float* __restrict__ logits,
+                                                          int L) {
+  __shared__ float s_in[GL_MAX][128];   // current layer input sequence
+  __shared__ float s_out[GL_MAX][128];  // current layer output sequence
+  __shared__ float s_h[2][GH];
+  __shared__ float s_gi[2][G3], s_gh[2][G3];
+  __shared__ float s_red[4];
+  const int b = blockIdx.x, tid = threadIdx.x, d = tid / G3, j = tid % G3;
+  for (int i = tid; i < L * GH; i += 384) {
+    const int t = i / GH, c = i % GH;
+    const float v = selu_f(fmaf(xn[((size_t)b * L + t) * GH + c], g.bn_scale[c], g.bn_shift[c]));
+    s_in[t][c] = v;
+    g.xin[((size_t)b * L + t) * GH + c] = v;
+  }
+  __syncthreads();
+  for (int l = 0; l < 2; ++l) {
+    const int K = l == 0 ? 64 : 128;
+    if (tid < 2 * GH) s_h[tid / GH][tid % GH] = 0.f;
+    __syncthreads();
+    const float* wih = g.wihT[l][d];
+    const float* whh = g.whhT[l][d];
+    const float bi = g.b_ih[l][d][j], bh = g.b_hh[l][d][j];
+    for (int s = 0; s < L; ++s) {
+      const int t = d == 0 ? s : L - 1 - s;
+      float gi = bi, gh = bh;
+      for (int k = 0; k < K; ++k) gi = fmaf(__ldg(wih + k * G3 + j), s_in[t][k], gi);
+      for (int k = 0; k < GH; ++k) gh = fmaf(__ldg(whh + k * G3 + j), s_h[d][k], gh);
+      s_gi[d][j] = gi;
+      s_gh[d][j] = gh;
+      __syncthreads();
+      if (j < GH) {
+        const float r = sigmoid_f(s_gi[d][j] + s_gh[d][j]);
+        const float z = sigmoid_f(s_gi[d][GH + j] + s_gh[d][GH + j]);
+        const float hn = s_gh[d][2 * GH + j];
+        const float n = tanhf(s_gi[d][2 * GH + j] + r * hn);
+        const float hnew = (1.0f - z) * n + z * s_h[d][j];
+        s_h[d][j] = hnew;
+        s_out[t][d * GH + j] = hnew;
+        float* gs = g.gates + ((((size_t)b * 2 + l) * 2 + d) * L + t) * 4 * GH;
+        gs[j] = r;
+        gs[GH + j] = z;
+        gs[2 * GH + j] = n;
+        gs[3 * GH + j] = hn;
+      }
+      __syncthreads();
+    }
+    for (int i = tid; i < L * 128; i += 384) {
+      const float v = s_out[i / 128][i % 128];
+      g.outs[(((size_t)b * 2 + l) * L + i / 128) * 128 + i % 128] = v;
+      s_in[i / 128][i % 128] = v;
+    }
+    __syncthreads();
+  }
+  // head: fc2(fc1(out[L-1]))
+  float part = 0.f;
+  if (tid < 128) {
+    float v = g.fc1_b[tid];
+    for (int k = 0; k < 128; ++k) v = fmaf(__ldg(g.fc1_w + tid * 128 + k), s_in[L - 1][k], v);
+    part = v * g.fc2_w[tid];
+  }
+  part = warp_sum(part);
+  if (tid < 128 && (tid & 31) == 0) s_red[tid >> 5] = part;
+  __syncthreads();
+  if (tid == 0) logits[b] = s_red[0] + s_red[1] + s_red[2] + s_red[3] + g.fc2_b[0];
+}
+
+// One CTA per clip, 256 threads = 2 directions x 128.
+__global__ void __launch_bounds__(256) sr_gru_bwd_kernel(SrGru g, const float* __restrict__ xn,
+                                                          const float* __restrict__ logits, const long long* __restrict__ y,
+                                                          int mode, float inv_n, const float* __restrict__ coef,
+                                                          float* __restrict__ g_xn, int L) {
+  __shared__ float s_gout[GL_MAX][128];    // gradient w.r.t. the current layer's output sequence
+  __shared__ float s_gin[2][GL_MAX][128];  // per-direction gradient w.r.t. the current layer's input sequence
+  __shared__ float s_dh[2][GH];
+  __shared__ float s_ggi[2][G3], s_ggh[2][G3];
+  const int b = blockIdx.x, tid = threadIdx.x, d = tid >> 7, i = tid & 127;
+  float go = 1.0f;
+  if (mode == 2) go = coef[b];
+  if (mode == 0) go = 2.0f * (sigmoid_f(2.0f * logits[b]) - (float)y[b]) * inv_n;
+  for (int k = tid; k < L * 128; k += 256) s_gout[k / 128][k % 128] = 0.f;
+  __syncthreads();
+  if (tid < 128) s_gout[L - 1][tid] = go * g.v[tid];
+  __syncthreads();
+  for (int l = 1; l >= 0; --l) {
+    const int K = l == 0 ? 64 : 128;
+    if (i < GH) s_dh[d][i] = 0.f;
+    for (int k = i; k < L * 128; k += 128) s_gin[d][k / 128][k % 128] = 0.f;
+    __syncthreads();
+    const float* wih = g.w_ih[l][d];  // [192][K]
+    const float* whh = g.w_hh[l][d];  // [192][64]
+    for (int s = L - 1; s >= 0; --s) {
+      const int t = d == 0 ? s : L - 1 - s;          // time index processed at step s
+      const int tp = d == 0 ? t - 1 : t + 1;         // time index of the previous hidden state
+      if (i < GH) {
+        const float* gs = g.gates + ((((size_t)b * 2 + l) * 2 + d) * L + t) * 4 * GH;
+        const float r = gs[i], z = gs[GH + i], n = gs[2 * GH + i], hn = gs[3 * GH + i];
+        const float hprev = s > 0 ? g.outs[(((size_t)b * 2 + l) * L + tp) * 128 + d * GH + i] : 0.f;
+        const float dh = s_dh[d][i] + s_gout[t][d * GH + i];
+        const float dn = dh * (1.0f - z);
+        const float dz = dh * (hprev - n);
+        const float dnp = dn * (1.0f - n * n);
+        const float drp = dnp * hn * r * (1.0f - r);
+        const float dzp = dz * z * (1.0f - z);
+        s_ggi[d][i] = drp;
+        s_ggi[d][GH + i] = dzp;
+        s_ggi[d][2 * GH + i] = dnp;
+        s_ggh[d][i] = drp;
+        s_ggh[d][GH + i] = dzp;
+        s_ggh[d][2 * GH + i] = dnp * r;
+        s_dh[d][i] = dh * z;  // direct path; the W_hh^T term is added below
+      }
+      __syncthreads();
+      if (i < K) {
+        float acc = 0.f;
+        for (int j = 0; j < G3; ++j) acc = fmaf(__ldg(wih + j * K + i), s_ggi[d][j], acc);
+        s_gin[d][t][i] = acc;
+      }
+      float accH = 0.f;
+      if (i < GH)
+        for (int j = 0; j < G3; ++j) accH = fmaf(__ldg(whh + j * GH + i), s_ggh[d][j], accH);
+      __syncthreads();
+      if (i < GH) s_dh[d][i] += accH;
+      __syncthreads();
+    }
+    for (int k = tid; k < L * 128; k += 256) s_gout[k / 128][k % 128] = s_gin[0][k / 128][k % 128] + s_gin[1][k / 128][k % 128];
+    __syncthreads();
+  }
+  // bn_before_gru + SELU backward (from the saved output)
+  for (int k = tid; k < L * GH; k += 256) {
+    const int t = k / GH, c = k % GH;
+    const float v = g.xin[((size_t)b * L + t) * GH + c];
+    g_xn[((size_t)b * L + t) * GH + c] = s_gout[t][c] * selu_grad_from_out(v) * g.bn_scale[c];
+  }
+}
+
+__global__ void sr_pack4_kernel(const float* w, const float* b, const float* rm, const float* rv, float* bn4) {
+  bn4[0] = w[0], bn4[1] = b[0], bn4[2] = rm[0], bn4[3] = rv[0];
+}
+
+inline int ew_blocks(int64_t n) {
+  int64_t b = (n + 255) / 256;
+  return (int)(b > 148 * 16 ? 148 * 16 : b);
+}
+
+template <int MODE>
+int launch_conv(SrArgs a, bool floor_quads, const char* tag, cudaStream_t stream) {
+  const int QW = floor_quads ? a.W / 2 : (a.W + 1) / 2, QH = floor_quads ? a.H / 2 : (a.H + 1) / 2;
+  ADVB_CHECK(QW > 0 && QH > 0, "empty SpecRNet conv output");
+  const int CKp = (a.CK % 4 == 0) ? a.CK + 4 : a.CK;
+  int band = band_rows_max(QH, QW, 1) * (2 * QW + 2) * CKp;
+  band = (band + 3) & ~3;
+  const size_t smem = (size_t)(band + a.CK * a.N) * sizeof(float);
+  ADVB_CHECK(smem <= 227 * 1024, "SpecRNet conv tile does not fit shared memory");
+  ADVB_CHECK(a.N % 8 == 0 && a.N <= 64, "SpecRNet conv: N must be a multiple of 8, <= 64");
+  ADVB_CUDA_OK(cudaFuncSetAttribute(sr_conv_kernel<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  dim3 grid(cdiv(QH * QW, 32), a.B);
+  sr_conv_kernel<MODE><<<grid, 32 * (a.N / 8), smem, stream>>>(a, band);
+  ADVB_KERNEL_OK(tag, stream);
+  return 0;
+}
+
+SrArgs base_args(const SrBlock& k, int B) {
+  SrArgs a{};
+  a.B = B, a.H = k.H, a.W = k.W, a.Hb = k.Hb, a.Wb = k.Wb, a.Hn = k.Hn, a.Wn = k.Wn, a.C = k.C;
+  a.g_xn = k.g_xn, a.code2 = k.code2, a.code1 = k.code1, a.y = k.y, a.gadd = k.gadd, a.h = k.h;
+  a.scale = k.bn_scale, a.shift = k.bn_shift;
+  return a;
+}
+
+}  // namespace
+
+int sr_conv2_tiles(int H, int W) { return cdiv((H / 2) * (W / 2), 32); }
+
+int sr_pack_first_bn(const float* w, const float* b, const float* rm, const float* rv, float* bn4, cudaStream_t stream) {
+  sr_pack4_kernel<<<1, 1, 0, stream>>>(w, b, rm, rv, bn4);
+  ADVB_KERNEL_OK("sr_pack", stream);
+  return 0;
+}
+
+int sr_pack_block(SrBlock& k, cudaStream_t stream) {
+  sr_pack_conv_kernel<<<cdiv(9 * k.Ci * k.C, 256), 256, 0, stream>>>(k.w1, k.w1f, k.Cout, k.Cin, k.Ci, k.C, 0);
+  ADVB_KERNEL_OK("sr_pack", stream);
+  sr_pack_conv_kernel<<<cdiv(9 * k.C * k.C, 256), 256, 0, stream>>>(k.w2, k.w2f, k.Cout, k.Cout, k.C, k.C, 0);
+  ADVB_KERNEL_OK("sr_pack", stream);
+  sr_pack_conv_kernel<<<cdiv(9 * k.C * k.C, 256), 256, 0, stream>>>(k.w2, k.w2d, k.Cout, k.Cout, k.C, k.C, 1);
+  ADVB_KERNEL_OK("sr_pack", stream);
+  if (k.Cin > 1) {
+    sr_pack_conv_kernel<<<cdiv(9 * k.C * k.Ci, 256), 256, 0, stream>>>(k.w1, k.w1d, k.Cout, k.Cin, k.C, k.Ci, 1);
+    ADVB_KERNEL_OK("sr_pack", stream);
+  }
+  if (k.downsample) {
+    sr_pack_1x1_kernel<<<cdiv(k.Ci * k.C, 256), 256, 0, stream>>>(k.wds, k.wdf, k.Cout, k.Cin, k.Ci, k.C, 0);
+    ADVB_KERNEL_OK("sr_pack", stream);
+    if (k.Cin > 1) {
+      sr_pack_1x1_kernel<<<cdiv(k.C * k.Ci, 256), 256, 0, stream>>>(k.wds, k.wdd, k.Cout, k.Cin, k.C, k.Ci, 1);
+      ADVB_KERNEL_OK("sr_pack", stream);
+    }
+  }
+  sr_pack_vec_kernel<<<1, 64, 0, stream>>>(k.b1, k.b2, k.downsample ? k.bds : nullptr, k.bn_w, k.bn_b, k.bn_rm, k.bn_rv,
+                                          k.b1p, k.b2p, k.bdp, k.bn_scale, k.bn_shift, k.Cout, k.C);
+  ADVB_KERNEL_OK("sr_pack", stream);
+  return 0;
+}
+
+int sr_pack_gru(SrGru& g, cudaStream_t stream) {
+  sr_gru_pack_kernel<<<32, 256, 0, stream>>>(g);
+  ADVB_KERNEL_OK("sr_gru_pack", stream);
+  return 0;
+}
+
+int sr_input_forward(float* img, const float* bn4, int B, int H, int W, cudaStream_t stream) {
+  const int64_t n = (int64_t)B * H * W;
+  sr_input_kernel<<<ew_blocks(n), 256, 0, stream>>>(img, bn4, H, W, n);
+  ADVB_KERNEL_OK("sr_input", stream);
+  return 0;
+}
+
+int sr_block_forward(const SrBlock& k, const float* x, int B, const char* tag, cudaStream_t stream) {
+  const std::string t(tag);
+  SrArgs a = base_args(k, B);
+  a.CK = k.Ci, a.N = k.C;
+  a.in = x, a.wpk = k.w1f, a.bias = k.b1p, a.out = k.h;
+  ADVB_TRY(launch_conv<F1>(a, false, (t + "_conv1").c_str(), stream));
+  a.CK = k.C, a.in = k.h, a.wpk = k.w2f, a.bias = k.b2p, a.out = k.xb;
+  a.x = x, a.Ci = k.Ci, a.wd = k.downsample ? k.wdf : nullptr, a.bd = k.bdp, a.code1w = k.code1, a.psum = k.psum;
+  ADVB_TRY(launch_conv<F2>(a, true, (t + "_conv2").c_str(), stream));
+  sr_attention_fwd_kernel<<<B, 64, 0, stream>>>(k.psum, k.n_tiles, k.att_w, k.att_b, k.y, k.C, k.Cout,
+                                               1.0f / (float)(k.Hb * k.Wb));
+  ADVB_KERNEL_OK("sr_attention", stream);
+  const int64_t n4 = (int64_t)B * k.Hn * k.Wn * (k.C / 4);
+  sr_scale_pool_kernel<<<ew_blocks(n4), 256, 0, stream>>>(k.xb, k.y, k.xn, k.code2, k.Hb, k.Wb, k.Hn, k.Wn, k.C, k.xn_pad,
+                                                         n4);
+  ADVB_KERNEL_OK("sr_scale_pool", stream);
+  return 0;
+}
+
+int sr_block_backward(const SrBlock& k, const float* x, float* g_x, int B, bool first, const float* bn4, const char* tag,
+                      cudaStream_t stream) {
+  const std::string t(tag);
+  const int threads = (256 / k.C) * k.C;
+  sr_attention_bwd_kernel<<<B, threads, 0, stream>>>(k.g_xn, k.code2, k.xb, k.y, k.att_w, k.gadd, k.Hb, k.Wb, k.Hn, k.Wn,
+                                                    k.C, k.Cout, 1.0f / (float)(k.Hb * k.Wb));
+  ADVB_KERNEL_OK("sr_attention_bwd", stream);
+  SrArgs a = base_args(k, B);
+  a.CK = k.C, a.N = k.C, a.wpk = k.w2d, a.out = k.g_c1;
+  ADVB_TRY(launch_conv<B2>(a, false, (t + "_conv2_bwd").c_str(), stream));
+  a.in = k.g_c1, a.x = x;
+  if (first) {
+    dim3 grid(cdiv(k.H * k.W, 256), B);
+    sr_first_bwd_kernel<<<grid, 256, 0, stream>>>(a, k.w1, k.wds, k.Cout, bn4, g_x);
+    ADVB_KERNEL_OK((t + "_conv1_bwd").c_str(), stream);
+    return 0;
+  }
+  a.CK = k.C, a.N = k.Ci, a.wpk = k.w1d, a.out = g_x, a.wd = k.downsample ? k.wdd : nullptr;
+  ADVB_TRY(launch_conv<B1>(a, false, (t + "_conv1_bwd").c_str(), stream));
+  return 0;
+}
+
+int sr_gru_forward(const SrGru& g, const float* xn, float* logits, int B, int L, cudaStream_t stream) {
+  ADVB_CHECK(L >= 1 && L <= GL_MAX, "SpecRNet GRU sequence length out of range (clip too short or too long)");
+  sr_gru_fwd_kernel<<<B, 384, 0, stream>>>(g, xn, logits, L);
+  ADVB_KERNEL_OK("sr_gru_fwd", stream);
+  return 0;
+}
+
+int sr_gru_backward(const SrGru& g, const float* xn, const float* logits, const long long* y, int mode, int n_global,
+                    const float* coef, float* g_xn, int B, int L, cudaStream_t stream) {
+  sr_gru_bwd_kernel<<<B, 256, 0, stream>>>(g, xn, logits, y, mode, 1.0f / (float)n_global, coef, g_xn, L);
+  ADVB_KERNEL_OK("sr_gru_bwd", stream);
+  return 0;
+}
+
+}  // namespace advb

@@ -56,6 +56,18 @@ def test_lcnn_holder_has_reference_state_dict_keys():
     assert type(holder).__name__ == "LCNN"
 
 
+def test_specrnet_holder_has_reference_state_dict_keys():
+    holder = cases.build_holder("specrnet", "mfcc")
+    keys = list(holder.state_dict())
+    for k in ("first_bn.running_var", "block0.0.conv_downsample.weight", "block2.0.bn1.weight", "block4.0.conv2.bias",
+              "fc_attention4.0.weight", "bn_before_gru.bias", "gru.weight_ih_l1_reverse", "fc2_gru.bias",
+              "frontend.MelSpectrogram.mel_scale.fb"):
+        assert k in keys, k
+    assert "block4.0.conv_downsample.weight" not in keys
+    assert sum(p.numel() for p in holder.parameters()) == 277963
+    assert type(holder).__name__ == "SpecRNet"
+
+
 def test_attack_api_surface_and_no_cpu_fallback():
     from advb200 import aa
     from advb200 import torchattacks as ta
