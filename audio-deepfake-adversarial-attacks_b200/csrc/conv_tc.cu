@@ -25,6 +25,8 @@
 #include "conv.cuh"
 #include "tc_common.cuh"
 
+#include <stdlib.h>
+
 namespace advb {
 
 namespace {
@@ -72,57 +74,9 @@ struct TcArgs {
   int passes;  // 3 = 3xTF32 (default), 1 = single-pass tf32 (fast, reduced precision)
 };
 
-// One 16-byte group (4 consecutive contraction channels starting at `ch`) of band row q (flat padded pixel of clip b).
-//   forward : the stage input itself (its zero border supplies the conv padding)
-//   IM2COL  : first block (1 input channel, 5x5): contraction index = tap, gathered from the zero-bordered image
-//   backward: the expanded gradient of the conv output: BN scale, un-pool, un-MFM of the compact stage gradient
-template <int KS, int KTOT, bool POOL, bool BWD, bool IM2COL>
-__device__ __forceinline__ float4 load_item(const TcArgs& a, int b, int q, int ch, int c4, int Hp, int Wp) {
-  constexpr int PC = KS / 2;
-  float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-  if (q < 0 || q >= Hp * Wp || ch >= KTOT) return v;
-  if (IM2COL && !BWD) {
-    const int y = q / Wp, x = q - y * Wp;
-    const float* img = a.in + (size_t)b * (a.H + 4) * (a.W + 4) + (size_t)y * (a.W + 4) + x;
-    float t[4];
-#pragma unroll
-    for (int u = 0; u < 4; ++u) {
-      const int tap = 4 * c4 + u;  // warp-uniform per c4, no divergence inside a channel group
-      const int dy = tap / 5, dx = tap - dy * 5;
-      t[u] = tap < 25 ? __ldg(img + dy * (a.W + 4) + dx) : 0.f;
-    }
-    return make_float4(t[0], t[1], t[2], t[3]);
-  }
-  if (!BWD) return __ldg(reinterpret_cast<const float4*>(a.in + ((size_t)b * Hp * Wp + q) * KTOT + ch));
-  const int yp = q / Wp, xp = q - yp * Wp;
-  const int y = yp - PC, x = xp - PC;
-  if (y < 0 || y >= a.H || x < 0 || x >= a.W) return v;
-  const int py = POOL ? (y >> 1) : y, px = POOL ? (x >> 1) : x;
-  if (py >= a.Ho || px >= a.Wo) return v;
-  constexpr int Ch = KTOT / 2;
-  const int half = ch >= Ch ? 1 : 0;
-  const int c = ch - half * Ch;
-  const size_t o = (((size_t)b * a.Ho + py) * a.Wo + px) * Ch + c;
-  float4 g = __ldg(reinterpret_cast<const float4*>(a.gout + o));
-  const uchar4 cd = __ldg(reinterpret_cast<const uchar4*>(a.codes_in + o));
-  const unsigned want = (POOL ? (unsigned)(((y & 1) << 1) | (x & 1)) : 0u) | (unsigned)(half << 2);
-  if (a.bn_invstd != nullptr) {
-    const float4 sc = __ldg(reinterpret_cast<const float4*>(a.bn_invstd + c));
-    g.x *= sc.x;
-    g.y *= sc.y;
-    g.z *= sc.z;
-    g.w *= sc.w;
-  }
-  v.x = cd.x == want ? g.x : 0.f;
-  v.y = cd.y == want ? g.y : 0.f;
-  v.z = cd.z == want ? g.z : 0.f;
-  v.w = cd.w == want ? g.w : 0.f;
-  return v;
-}
-
 // KS: filter size; KTOT: contraction channels per tap (fwd: Cin, bwd: Cout); NOUT: GEMM N (fwd: Cout, bwd: Cin).
 template <int KS, int KTOT, int NOUT, bool POOL, bool BWD, bool IM2COL = false, int NM = 4>
-__global__ void __launch_bounds__(TC_THREADS, NM <= 2 ? 2 : 1) conv_tc_kernel(TcArgs a) {
+__global__ void __launch_bounds__(TC_THREADS, NM == 1 ? 3 : (NM == 2 ? 2 : 1)) conv_tc_kernel(TcArgs a) {
   using Cfg = TcCfg<NOUT, NM>;
   constexpr int NM_MAX = NM;
   constexpr int PC = KS / 2, NTAP = KS * KS, NKC = (KTOT + 31) / 32;
@@ -190,34 +144,135 @@ __global__ void __launch_bounds__(TC_THREADS, NM <= 2 ? 2 : 1) conv_tc_kernel(Tc
       tc_fence_after();
     }
     // ---- stage chunk kc of the band: 32 channels per row, tf32 hi / lo, SWIZZLE_128B ----
-    // FILL_U independent items (16-byte channel groups) are loaded before any is consumed, so one thread keeps
-    // FILL_U global loads in flight (the band is read exactly once; latency, not bandwidth, is the enemy here).
+    // Two phases per batch of FILL_U items (16-byte channel groups): first every global load of the batch is issued
+    // from branch-free, clamped addresses, then the batch is post-processed.  The band is read exactly once, so
+    // latency - not bandwidth - is the enemy: an earlier version whose per-item bounds checks were branches had its
+    // loads serialised by the compiler and spent half of its samples waiting on them (profiles/r01_conv_tc_fill.md).
     {
       constexpr int FILL_U = 8;
       const int total = band_used * 8;
       const int c4 = tid & 7;  // TC_THREADS is a multiple of 8: a thread always owns the same channel group
       const int ch = 32 * kc + 4 * c4;
+      const bool ch_ok = ch < KTOT;
+      const int npix = Hp * Wp;
+      if (BWD) {
+        constexpr int Ch = KTOT / 2;
+        const int half = ch >= Ch ? 1 : 0;
+        const int c = ch - half * Ch;
+        float4 sc = make_float4(1.f, 1.f, 1.f, 1.f);
+        if (a.bn_invstd != nullptr && ch_ok) sc = __ldg(reinterpret_cast<const float4*>(a.bn_invstd + c));
 #pragma unroll 1
-      for (int i0 = tid; i0 < total; i0 += FILL_U * TC_THREADS) {
-        float4 v[FILL_U];
+        for (int i0 = tid; i0 < total; i0 += FILL_U * TC_THREADS) {
+          float4 g[FILL_U];
+          uchar4 cd[FILL_U];
+          unsigned want[FILL_U];
 #pragma unroll
-        for (int u = 0; u < FILL_U; ++u) {
-          const int i = i0 + u * TC_THREADS;
-          v[u] = make_float4(0.f, 0.f, 0.f, 0.f);
-          if (i < total) v[u] = load_item<KS, KTOT, POOL, BWD, IM2COL>(a, b, q_lo + (i >> 3), ch, c4, Hp, Wp);
+          for (int u = 0; u < FILL_U; ++u) {
+            const int i = i0 + u * TC_THREADS;
+            const int q = q_lo + (i >> 3);
+            bool ok = ch_ok && i < total && q >= 0 && q < npix;
+            const int qq = ok ? q : 0;
+            const int yp = qq / Wp, xp = qq - yp * Wp;
+            const int y = yp - PC, x = xp - PC;
+            ok = ok && y >= 0 && y < a.H && x >= 0 && x < a.W;
+            const int py = POOL ? (y >> 1) : y, px = POOL ? (x >> 1) : x;
+            ok = ok && py < a.Ho && px < a.Wo;
+            const size_t o = ok ? (((size_t)b * a.Ho + py) * a.Wo + px) * Ch + c : 0;
+            g[u] = __ldg(reinterpret_cast<const float4*>(a.gout + o));
+            cd[u] = __ldg(reinterpret_cast<const uchar4*>(a.codes_in + o));
+            want[u] = ok ? ((POOL ? (unsigned)(((y & 1) << 1) | (x & 1)) : 0u) | (unsigned)(half << 2)) : 0xffu;
+          }
+#pragma unroll
+          for (int u = 0; u < FILL_U; ++u) {
+            const int i = i0 + u * TC_THREADS;
+            if (i < total) {
+              float4 v;
+              v.x = cd[u].x == want[u] ? g[u].x * sc.x : 0.f;
+              v.y = cd[u].y == want[u] ? g[u].y * sc.y : 0.f;
+              v.z = cd[u].z == want[u] ? g[u].z * sc.z : 0.f;
+              v.w = cd[u].w == want[u] ? g[u].w * sc.w : 0.f;
+              float4 hi, lo;
+              split_tf32(v.x, hi.x, lo.x);
+              split_tf32(v.y, hi.y, lo.y);
+              split_tf32(v.z, hi.z, lo.z);
+              split_tf32(v.w, hi.w, lo.w);
+              const uint32_t off = sw128_chunk(i >> 3, c4);
+              *reinterpret_cast<float4*>(a_hi + off) = hi;
+              *reinterpret_cast<float4*>(a_lo + off) = lo;
+            }
+          }
         }
+      } else if (IM2COL) {
+        // first block: contraction index = tap (4 per channel group), gathered from the zero-bordered image
+        const int Wi = a.W + 4;
+        int toff[4];
+        bool tok[4];
 #pragma unroll
-        for (int u = 0; u < FILL_U; ++u) {
-          const int i = i0 + u * TC_THREADS;
-          if (i < total) {
-            float4 hi, lo;
-            split_tf32(v[u].x, hi.x, lo.x);
-            split_tf32(v[u].y, hi.y, lo.y);
-            split_tf32(v[u].z, hi.z, lo.z);
-            split_tf32(v[u].w, hi.w, lo.w);
-            const uint32_t off = sw128_chunk(i >> 3, c4);
-            *reinterpret_cast<float4*>(a_hi + off) = hi;
-            *reinterpret_cast<float4*>(a_lo + off) = lo;
+        for (int u4 = 0; u4 < 4; ++u4) {
+          const int tap = 4 * c4 + u4;
+          tok[u4] = tap < 25;
+          const int dy = tap / 5, dx = tap - dy * 5;
+          toff[u4] = tok[u4] ? dy * Wi + dx : 0;
+        }
+        const float* imgb = a.in + (size_t)b * (a.H + 4) * Wi;
+#pragma unroll 1
+        for (int i0 = tid; i0 < total; i0 += FILL_U * TC_THREADS) {
+          float t[FILL_U][4];
+#pragma unroll
+          for (int u = 0; u < FILL_U; ++u) {
+            const int i = i0 + u * TC_THREADS;
+            const int q = q_lo + (i >> 3);
+            const bool ok = i < total && q >= 0 && q < npix;
+            const int qq = ok ? q : 0;
+            const int y = qq / Wp, x = qq - y * Wp;
+            const float* img = imgb + (size_t)y * Wi + x;
+#pragma unroll
+            for (int u4 = 0; u4 < 4; ++u4) {
+              const float val = __ldg(img + toff[u4]);
+              t[u][u4] = (ok && tok[u4]) ? val : 0.f;
+            }
+          }
+#pragma unroll
+          for (int u = 0; u < FILL_U; ++u) {
+            const int i = i0 + u * TC_THREADS;
+            if (i < total) {
+              float4 hi, lo;
+              split_tf32(t[u][0], hi.x, lo.x);
+              split_tf32(t[u][1], hi.y, lo.y);
+              split_tf32(t[u][2], hi.z, lo.z);
+              split_tf32(t[u][3], hi.w, lo.w);
+              const uint32_t off = sw128_chunk(i >> 3, c4);
+              *reinterpret_cast<float4*>(a_hi + off) = hi;
+              *reinterpret_cast<float4*>(a_lo + off) = lo;
+            }
+          }
+        }
+      } else {
+        const float* inb = a.in + (size_t)b * npix * KTOT + ch;
+#pragma unroll 1
+        for (int i0 = tid; i0 < total; i0 += FILL_U * TC_THREADS) {
+          float4 v[FILL_U];
+#pragma unroll
+          for (int u = 0; u < FILL_U; ++u) {
+            const int i = i0 + u * TC_THREADS;
+            const int q = q_lo + (i >> 3);
+            const bool ok = ch_ok && i < total && q >= 0 && q < npix;
+            const float4 val = __ldg(reinterpret_cast<const float4*>(ok ? inb + (size_t)q * KTOT : a.in));
+            v[u] = ok ? val : make_float4(0.f, 0.f, 0.f, 0.f);
+          }
+#pragma unroll
+          for (int u = 0; u < FILL_U; ++u) {
+            const int i = i0 + u * TC_THREADS;
+            if (i < total) {
+              float4 hi, lo;
+              split_tf32(v[u].x, hi.x, lo.x);
+              split_tf32(v[u].y, hi.y, lo.y);
+              split_tf32(v[u].z, hi.z, lo.z);
+              split_tf32(v[u].w, hi.w, lo.w);
+              const uint32_t off = sw128_chunk(i >> 3, c4);
+              *reinterpret_cast<float4*>(a_hi + off) = hi;
+              *reinterpret_cast<float4*>(a_lo + off) = lo;
+            }
           }
         }
       }
@@ -432,6 +487,15 @@ __global__ void pack_tc_kernel(const float* __restrict__ w, unsigned char* __res
   }
 }
 
+// Tuning knob (environment, read once): M-tiles per CTA of the 1x1 layers.  Measured on B200 (profiles/): see DESIGN.md.
+int tune_light_nm() {
+  static const int v = [] {
+    const char* e = getenv("ADVB_LIGHT_NM");
+    return e != nullptr ? atoi(e) : 2;
+  }();
+  return v;
+}
+
 struct TcPlan {
   int R, tiles, band_rows;
   size_t smem;
@@ -530,9 +594,11 @@ int conv_tc_forward(const ConvFwdArgs& f, const unsigned char* wpack, int passes
   a.in = f.in, a.out = f.out, a.out_pad = f.out_pad, a.codes = f.codes, a.bias = f.bias;
   a.bn_mean = f.bn_mean, a.bn_invstd = f.bn_invstd;
   a.passes = passes;
-#define ADVB_TCF(KS_, CI_, CO_, POOL_)                                             \
-  if (f.KS == KS_ && f.Cin == CI_ && f.Cout == CO_ && f.pool == POOL_)             \
-  return launch_tc<KS_, CI_, CO_, POOL_, false, false, (KS_ == 1 ? 2 : 4)>(a, f.tag, stream)
+#define ADVB_TCF(KS_, CI_, CO_, POOL_)                                                              \
+  if (f.KS == KS_ && f.Cin == CI_ && f.Cout == CO_ && f.pool == POOL_) {                            \
+    if (KS_ == 1 && tune_light_nm() == 1) return launch_tc<KS_, CI_, CO_, POOL_, false, false, 1>(a, f.tag, stream); \
+    return launch_tc<KS_, CI_, CO_, POOL_, false, false, (KS_ == 1 ? 2 : 4)>(a, f.tag, stream);     \
+  }
   ADVB_TCF(1, 32, 64, false);
   ADVB_TCF(1, 48, 96, false);
   ADVB_TCF(1, 64, 128, false);
@@ -579,9 +645,11 @@ int conv_tc_backward(const ConvBwdArgs& g, const unsigned char* wpack, int passe
   a.wpack = wpack;
   a.gout = g.gout, a.codes_in = g.codes, a.gin = g.gin, a.bn_invstd = g.bn_invstd;
   a.passes = passes;
-#define ADVB_TCB(KS_, CI_, CO_, POOL_)                                             \
-  if (g.KS == KS_ && g.Cin == CI_ && g.Cout == CO_ && g.pool == POOL_)             \
-  return launch_tc<KS_, CO_, CI_, POOL_, true, false, 2>(a, g.tag, stream)
+#define ADVB_TCB(KS_, CI_, CO_, POOL_)                                                              \
+  if (g.KS == KS_ && g.Cin == CI_ && g.Cout == CO_ && g.pool == POOL_) {                            \
+    if (KS_ == 1 && tune_light_nm() == 1) return launch_tc<KS_, CO_, CI_, POOL_, true, false, 1>(a, g.tag, stream); \
+    return launch_tc<KS_, CO_, CI_, POOL_, true, false, 2>(a, g.tag, stream);                       \
+  }
   ADVB_TCB(1, 32, 64, false);
   ADVB_TCB(1, 48, 96, false);
   ADVB_TCB(1, 64, 128, false);

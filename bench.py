@@ -262,6 +262,8 @@ def run_native(args):
         atk(x_dev, y_dev)
         prof = sorted(eng.profile_end(), key=lambda r: -r["total_ms"])
         total_prof = sum(r["total_ms"] for r in prof)
+        if args.kernel_times:
+            json.dump(prof, open(args.kernel_times, "w"), indent=1)
         top = prof[0]
         peak, peak_kind = measured_peaks()
         kb = kernel_bytes(B, 1 + T_SAMPLES // 160, T_SAMPLES)
@@ -321,6 +323,7 @@ def main():
     ap.add_argument("--impl", default="native", choices=["native", "reference"])
     ap.add_argument("--batch", type=int, default=128)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--kernel-times", default=None, help="write the full per-kernel timing table of one call (JSON)")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)
