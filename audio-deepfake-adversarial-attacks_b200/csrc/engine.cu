@@ -75,7 +75,8 @@ struct advb_handle {
   int tf32_passes = 3;  // 3 = 3xTF32 (fp32-class accuracy), 1 = single-pass tf32
 
   // frontend
-  float *twr = nullptr, *twi = nullptr, *dB = nullptr, *mass_partial = nullptr, *g_coef = nullptr;
+  float2* tw = nullptr;
+  float *dB = nullptr, *mass_partial = nullptr, *g_coef = nullptr;
   int *klo = nullptr, *kcnt = nullptr, *mlo = nullptr, *mcnt = nullptr;
   FrontendState fst{};
   FrontendTables ftb{};
@@ -187,8 +188,7 @@ void refresh_frontend_tables(advb_handle* h) {
     tb.window = h->t("frontend.MelSpectrogram.spectrogram.window");
   }
   tb.dct = h->t("frontend.dct_mat");
-  tb.twr = h->twr;
-  tb.twi = h->twi;
+  tb.tw = h->tw;
   tb.klo = h->klo;
   tb.kcnt = h->kcnt;
   tb.mlo = h->mlo;
@@ -664,7 +664,7 @@ int advb_create(advb_handle** out, const advb_model_desc* d) {
   }
   if (check_frontend_tensors(h)) return fail();
   const size_t B = h->Bmax;
-  if (h->alloc(&h->twr, 256) || h->alloc(&h->twi, 256) || h->alloc(&h->klo, 128) || h->alloc(&h->kcnt, 128) ||
+  if (h->alloc(&h->tw, 512) || h->alloc(&h->klo, 128) || h->alloc(&h->kcnt, 128) ||
       h->alloc(&h->mlo, 257) || h->alloc(&h->mcnt, 257) || h->alloc(&h->fst.gmax_packed, 1) ||
       h->alloc(&h->fst.n_clamped, 1) || h->alloc(&h->fst.mass_total, 1) ||
       h->alloc(&h->dB, B * h->F * 128) || h->alloc(&h->g_coef, B * h->F * 80) ||
@@ -673,7 +673,7 @@ int advb_create(advb_handle** out, const advb_model_desc* d) {
       h->alloc(&h->grad, B * h->T) || h->alloc(&h->partial_g, B * ROW_CHUNKS) ||
       h->alloc(&h->partial_d, B * ROW_CHUNKS))
     return fail();
-  if (frontend_init_constants(h->twr, h->twi, 0)) return fail();
+  if (frontend_init_constants(h->tw, 0)) return fail();
   if (h->model_kind == ADVB_MODEL_LCNN ? build_lcnn(h) : build_specrnet(h)) return fail();
   if (cudaDeviceSynchronize() != cudaSuccess) {
     set_error("device error during advb_create");

@@ -38,7 +38,7 @@ constexpr int FE_THREADS = FE_WARPS * 32;
 constexpr int FB_WARPS = 10;     // backward: an interior tile of 16 hops needs 19-20 frames = 10 frame pairs = one round
 constexpr int FB_THREADS = FB_WARPS * 32;
 constexpr int PSTRIDE = 260;     // padded 257
-constexpr int DCT_LD = 81;       // padded row of the dct matrix in shared memory (bank spread for row-parallel reads)
+constexpr int DCT_LD = 84;       // padded row of the dct matrix in shared memory: 16-byte aligned rows, conflict-free float4 reads
 constexpr int TILE_HOPS = 16;    // backward tile = 16 hops = 2560 samples
 constexpr int TILE_S = TILE_HOPS * HOP;
 constexpr int NF_MAX = 24;       // frames a backward tile may need (19 interior, a few more at the right edge)
@@ -49,35 +49,85 @@ __device__ __forceinline__ int reflect_index(int j, int T) {
   return j;
 }
 
-// In-place radix-2 DIT FFT of 512 complex points held by one warp; input in bit-reversed order.
-__device__ __forceinline__ void warp_fft512(float* re, float* im, const float* twr, const float* twi, int lane) {
-#pragma unroll 1
-  for (int s = 0; s < 9; ++s) {
-    const int half = 1 << s;
-    const int tstep = 256 >> s;
-#pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      const int j = lane + 32 * i;
-      const int pos = j & (half - 1);
-      const int i0 = ((j >> s) << (s + 1)) + pos;
-      const int i1 = i0 + half;
-      const float wr = twr[pos * tstep], wi = twi[pos * tstep];
-      const float xr = re[i1], xi = im[i1];
-      const float tr = wr * xr - wi * xi;
-      const float ti = wr * xi + wi * xr;
-      const float ur = re[i0], ui = im[i0];
-      re[i0] = ur + tr;
-      im[i0] = ui + ti;
-      re[i1] = ur - tr;
-      im[i1] = ui - ti;
-    }
-    __syncwarp();
-  }
+// ---- 512-point complex FFT of one warp: radix-8 Stockham autosort, 3 out-of-place passes A -> B -> A -> B ----
+// Each lane owns 2 x 8 points per pass (16 independent shared-memory loads in flight, one __syncwarp per pass); input
+// and output are in natural order (no bit reversal).  A: 512 float2; B: 576 float2 - the intermediate after pass 1 is
+// stored at i + (i >> 3) so that its stride-8 scatter is bank-conflict free.
+constexpr int FFT_A = 512;   // float2 elements of buffer A
+constexpr int FFT_B = 576;   // float2 elements of buffer B
+
+__device__ __forceinline__ float2 cmul(float2 a, float2 b) {
+  return make_float2(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x);
+}
+__device__ __forceinline__ float2 cadd(float2 a, float2 b) { return make_float2(a.x + b.x, a.y + b.y); }
+__device__ __forceinline__ float2 csub(float2 a, float2 b) { return make_float2(a.x - b.x, a.y - b.y); }
+__device__ __forceinline__ float2 mul_mi(float2 a) { return make_float2(a.y, -a.x); }  // a * (-i)
+
+// forward DFT-8 (kernel e^{-2 pi i nk/8}) in registers, decimation in frequency
+__device__ __forceinline__ void dft8(float2 (&v)[8]) {
+  const float h = 0.70710678118654752f;
+  const float2 a0 = cadd(v[0], v[4]), a4 = csub(v[0], v[4]);
+  const float2 a1 = cadd(v[1], v[5]);
+  float2 a5 = csub(v[1], v[5]);
+  const float2 a2 = cadd(v[2], v[6]);
+  float2 a6 = csub(v[2], v[6]);
+  const float2 a3 = cadd(v[3], v[7]);
+  float2 a7 = csub(v[3], v[7]);
+  a5 = make_float2(h * (a5.x + a5.y), h * (a5.y - a5.x));    // * (1 - i)/sqrt2
+  a6 = mul_mi(a6);                                           // * (-i)
+  a7 = make_float2(h * (a7.y - a7.x), -h * (a7.x + a7.y));   // * (-1 - i)/sqrt2
+  const float2 b0 = cadd(a0, a2), b2 = csub(a0, a2), b1 = cadd(a1, a3), b3 = mul_mi(csub(a1, a3));
+  const float2 b4 = cadd(a4, a6), b6 = csub(a4, a6), b5 = cadd(a5, a7), b7 = mul_mi(csub(a5, a7));
+  v[0] = cadd(b0, b1);
+  v[4] = csub(b0, b1);
+  v[2] = cadd(b2, b3);
+  v[6] = csub(b2, b3);
+  v[1] = cadd(b4, b5);
+  v[5] = csub(b4, b5);
+  v[3] = cadd(b6, b7);
+  v[7] = csub(b6, b7);
 }
 
-// Load two windowed frames (ta, ta+1) of clip `xb` packed as re=frame a, im=frame b, bit-reversed.
+// PASS 0: Ns = 1 (A -> B padded), PASS 1: Ns = 8 (B padded -> A), PASS 2: Ns = 64 (A -> B natural)
+template <int PASS>
+__device__ __forceinline__ void fft_pass(const float2* __restrict__ in, float2* __restrict__ out,
+                                         const float2* __restrict__ s_tw, int lane) {
+  constexpr int Ns = PASS == 0 ? 1 : (PASS == 1 ? 8 : 64);
+#pragma unroll
+  for (int h = 0; h < 2; ++h) {
+    const int j = lane + 32 * h;
+    const int k = j & (Ns - 1);
+    float2 v[8];
+#pragma unroll
+    for (int r = 0; r < 8; ++r) {
+      const int i = j + 64 * r;
+      v[r] = in[PASS == 1 ? i + (i >> 3) : i];
+    }
+    if (PASS > 0) {
+#pragma unroll
+      for (int r = 1; r < 8; ++r) v[r] = cmul(v[r], s_tw[(r * k * (PASS == 1 ? 8 : 1)) & 511]);
+    }
+    dft8(v);
+    const int j0 = ((j - k) << 3) + k;
+#pragma unroll
+    for (int r = 0; r < 8; ++r) {
+      const int i = j0 + r * Ns;
+      out[PASS == 0 ? i + (i >> 3) : i] = v[r];
+    }
+  }
+  __syncwarp();
+}
+
+// Z = FFT(bufA) -> bufB (natural order); bufA is clobbered.
+__device__ __forceinline__ void warp_fft512(float2* bufA, float2* bufB, const float2* s_tw, int lane) {
+  fft_pass<0>(bufA, bufB, s_tw, lane);
+  fft_pass<1>(bufB, bufA, s_tw, lane);
+  fft_pass<2>(bufA, bufB, s_tw, lane);
+}
+
+// Load two windowed frames (ta, ta+1) of clip `xb` packed as re = frame a, im = frame b, natural order.
 __device__ __forceinline__ void load_frame_pair(const float* __restrict__ xb, int T, int F, int ta, const float* s_win,
-                                                float* re, float* im, int lane) {
+                                                float2* buf, int lane) {
   const bool has_b = (ta + 1) < F;
   for (int n = lane; n < NFFT; n += 32) {
     float a = 0.f, b = 0.f;
@@ -87,22 +137,18 @@ __device__ __forceinline__ void load_frame_pair(const float* __restrict__ xb, in
       a = w * __ldg(xb + reflect_index(ja, T));
       if (has_b) b = w * __ldg(xb + reflect_index(ja + HOP, T));
     }
-    const int r = __brev((unsigned)n) >> 23;
-    re[r] = a;
-    im[r] = b;
+    buf[n] = make_float2(a, b);
   }
   __syncwarp();
 }
 
 // From the packed spectrum Z: one-sided spectra of both frames at bin k.
-__device__ __forceinline__ void unpack_bin(const float* re, const float* im, int k, float& xar, float& xai, float& xbr,
-                                           float& xbi) {
-  const int kk = (NFFT - k) & (NFFT - 1);
-  const float a = re[k], b = im[k], c = re[kk], d = im[kk];
-  xar = 0.5f * (a + c);
-  xai = 0.5f * (b - d);
-  xbr = 0.5f * (b + d);
-  xbi = 0.5f * (c - a);
+__device__ __forceinline__ void unpack_bin(const float2* z, int k, float& xar, float& xai, float& xbr, float& xbi) {
+  const float2 p = z[k], q = z[(NFFT - k) & (NFFT - 1)];
+  xar = 0.5f * (p.x + q.x);
+  xai = 0.5f * (p.y - q.y);
+  xbr = 0.5f * (p.y + q.y);
+  xbi = 0.5f * (q.x - p.x);
 }
 
 __device__ __forceinline__ void filter_energy(const float* __restrict__ fb, const int* __restrict__ klo,
@@ -146,13 +192,12 @@ __global__ void fe_tables_kernel(const float* __restrict__ fb, int* klo, int* kc
   }
 }
 
-__global__ void fe_twiddle_kernel(float* twr, float* twi) {
+__global__ void fe_twiddle_kernel(float2* tw) {
   const int k = threadIdx.x + blockIdx.x * blockDim.x;
-  if (k < 256) {
+  if (k < 512) {
     double s, c;
     sincospi(2.0 * (double)k / 512.0, &s, &c);
-    twr[k] = (float)c;
-    twi[k] = (float)(-s);
+    tw[k] = make_float2((float)c, (float)(-s));
   }
 }
 
@@ -167,17 +212,13 @@ __global__ void fe_reset_kernel(FrontendState st) {
 __global__ void __launch_bounds__(FE_THREADS) fe_power_db_kernel(const float* __restrict__ x, int T, int F,
                                                                    FrontendTables tb, FrontendState st,
                                                                    float* __restrict__ dB) {
-  extern __shared__ float smem[];
-  float* s_twr = smem;                 // 256
-  float* s_twi = s_twr + 256;          // 256
-  float* s_win = s_twi + 256;          // 400
-  float* s_fft = s_win + 400;          // FE_WARPS * 1024
-  float* s_pw = s_fft + FE_WARPS * 1024;  // FE_WARPS * 2 * PSTRIDE
+  extern __shared__ __align__(16) float smem[];
+  float2* s_tw = reinterpret_cast<float2*>(smem);                    // 512 float2
+  float* s_win = smem + 1024;                                        // 400
+  float2* s_fft = reinterpret_cast<float2*>(s_win + 400);            // FE_WARPS * (FFT_A + FFT_B) float2
+  float* s_pw = reinterpret_cast<float*>(s_fft + FE_WARPS * (FFT_A + FFT_B));  // FE_WARPS * 2 * PSTRIDE
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  for (int i = tid; i < 256; i += FE_THREADS) {
-    s_twr[i] = tb.twr[i];
-    s_twi[i] = tb.twi[i];
-  }
+  for (int i = tid; i < 512; i += FE_THREADS) s_tw[i] = tb.tw[i];
   for (int i = tid; i < WIN; i += FE_THREADS) s_win[i] = tb.window[i];
   __syncthreads();
 
@@ -185,17 +226,17 @@ __global__ void __launch_bounds__(FE_THREADS) fe_power_db_kernel(const float* __
   const int ta = blockIdx.x * (2 * FE_WARPS) + 2 * warp;
   if (ta >= F) return;
   const bool has_b = (ta + 1) < F;
-  float* re = s_fft + warp * 1024;
-  float* im = re + 512;
+  float2* bufA = s_fft + warp * (FFT_A + FFT_B);
+  float2* bufB = bufA + FFT_A;
   float* pa = s_pw + warp * 2 * PSTRIDE;
   float* pb = pa + PSTRIDE;
   const float* xb = x + (size_t)b * T;
 
-  load_frame_pair(xb, T, F, ta, s_win, re, im, lane);
-  warp_fft512(re, im, s_twr, s_twi, lane);
+  load_frame_pair(xb, T, F, ta, s_win, bufA, lane);
+  warp_fft512(bufA, bufB, s_tw, lane);
   for (int k = lane; k < NBIN; k += 32) {
     float xar, xai, xbr, xbi;
-    unpack_bin(re, im, k, xar, xai, xbr, xbi);
+    unpack_bin(bufB, k, xar, xai, xbr, xbi);
     pa[k] = xar * xar + xai * xai;
     pb[k] = xbr * xbr + xbi * xbi;
   }
@@ -359,21 +400,17 @@ __global__ void __launch_bounds__(FB_THREADS) fe_bwd_kernel(const float* __restr
                                                              const float* __restrict__ gcoef, long long g_clip_stride,
                                                              long long g_stride_f, long long g_stride_c,
                                                              float* __restrict__ gx, int n_tiles) {
-  extern __shared__ float smem[];
-  float* s_twr = smem;                          // 256
-  float* s_twi = s_twr + 256;                   // 256
-  float* s_win = s_twi + 256;                   // 400
-  float* s_dct = s_win + 400;                   // 128*81
-  float* s_fft = s_dct + NFILT * DCT_LD;        // FB_WARPS * 2048 (Z and H buffers)
-  float* s_pw = s_fft + FB_WARPS * 2048;        // FB_WARPS * 2 * PSTRIDE  (power, then d power)
+  extern __shared__ __align__(16) float smem[];
+  float2* s_tw = reinterpret_cast<float2*>(smem);                  // 512 float2
+  float* s_win = smem + 1024;                                      // 400
+  float* s_dct = s_win + 400;                                      // 128 * DCT_LD
+  float2* s_fft = reinterpret_cast<float2*>(s_dct + NFILT * DCT_LD);  // FB_WARPS * (FFT_A + FFT_B) float2
+  float* s_pw = reinterpret_cast<float*>(s_fft + FB_WARPS * (FFT_A + FFT_B));  // FB_WARPS * 2 * PSTRIDE (power, d power)
   float* s_ge = s_pw + FB_WARPS * 2 * PSTRIDE;  // FB_WARPS * 2 * 128       (d energy)
   float* s_gc = s_ge + FB_WARPS * 2 * NFILT;    // FB_WARPS * 2 * 80        (d coefficients)
   float* s_yw = s_gc + FB_WARPS * 2 * NCOEF;    // NF_MAX * 400             (windowed frame gradients)
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  for (int i = tid; i < 256; i += FB_THREADS) {
-    s_twr[i] = tb.twr[i];
-    s_twi[i] = tb.twi[i];
-  }
+  for (int i = tid; i < 512; i += FB_THREADS) s_tw[i] = tb.tw[i];
   for (int i = tid; i < WIN; i += FB_THREADS) s_win[i] = tb.window[i];
   for (int i = tid; i < NFILT * NCOEF; i += FB_THREADS) s_dct[(i / NCOEF) * DCT_LD + (i % NCOEF)] = tb.dct[i];
   __syncthreads();
@@ -396,10 +433,8 @@ __global__ void __launch_bounds__(FB_THREADS) fe_bwd_kernel(const float* __restr
   const float mass_total = *st.mass_total;
   const float* xb = x + (size_t)b * T;
 
-  float* re = s_fft + warp * 2048;
-  float* im = re + 512;
-  float* re2 = re + 1024;
-  float* im2 = re + 1536;
+  float2* bufA = s_fft + warp * (FFT_A + FFT_B);
+  float2* bufB = bufA + FFT_A;
   float* pa = s_pw + warp * 2 * PSTRIDE;
   float* pb = pa + PSTRIDE;
   float* gea = s_ge + warp * 2 * NFILT;
@@ -416,38 +451,49 @@ __global__ void __launch_bounds__(FB_THREADS) fe_bwd_kernel(const float* __restr
       gca[c] = gcoef[base + (long long)ta * g_stride_f];
       gcb[c] = has_b ? gcoef[base + (long long)(ta + 1) * g_stride_f] : 0.f;
     }
-    // 2. recompute the packed FFT of both frames
-    load_frame_pair(xb, T, has_b ? F : ta + 1, ta, s_win, re, im, lane);
-    warp_fft512(re, im, s_twr, s_twi, lane);
+    // 2. recompute the packed FFT of both frames: Z in bufB
+    load_frame_pair(xb, T, has_b ? F : ta + 1, ta, s_win, bufA, lane);
+    warp_fft512(bufA, bufB, s_tw, lane);
     // 3. power
     for (int k = lane; k < NBIN; k += 32) {
       float xar, xai, xbr, xbi;
-      unpack_bin(re, im, k, xar, xai, xbr, xbi);
+      unpack_bin(bufB, k, xar, xai, xbr, xbi);
       pa[k] = xar * xar + xai * xai;
       pb[k] = xbr * xbr + xbi * xbi;
     }
     __syncwarp();
-    // 4. energies, dB, floor backward, d energy
-    const size_t rowa = ((size_t)b * F + ta) * NFILT;
-#pragma unroll 1
-    for (int i = 0; i < NFILT / 32; ++i) {
-      const int m = lane + 32 * i;
-      float ea, eb;
-      filter_energy(tb.fb, tb.klo, tb.kcnt, pa, pb, m, ea, eb);
-      float gda = 0.f, gdb = 0.f;
-      const float* drow = s_dct + m * DCT_LD;
-#pragma unroll 8
-      for (int c = 0; c < NCOEF; ++c) {
-        const float w = drow[c];
-        gda += w * gca[c];
-        gdb += w * gcb[c];
+    // 4. energies, dct^T (register-tiled: 4 filters x 2 frames per lane, float4 shared-memory reads), dB / floor
+    //    backward, d energy
+    {
+      float ea[4], eb[4], gda[4], gdb[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        filter_energy(tb.fb, tb.klo, tb.kcnt, pa, pb, lane + 32 * i, ea[i], eb[i]);
+        gda[i] = 0.f;
+        gdb[i] = 0.f;
       }
-      if ((unsigned)(rowa + m) == amax_idx) gda += mass_total;
-      if ((unsigned)(rowa + NFILT + m) == amax_idx) gdb += mass_total;
+#pragma unroll 4
+      for (int c = 0; c < NCOEF; c += 4) {
+        const float4 ga = *reinterpret_cast<const float4*>(gca + c);
+        const float4 gb = *reinterpret_cast<const float4*>(gcb + c);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const float4 w = *reinterpret_cast<const float4*>(s_dct + (lane + 32 * i) * DCT_LD + c);
+          gda[i] = fmaf(w.x, ga.x, fmaf(w.y, ga.y, fmaf(w.z, ga.z, fmaf(w.w, ga.w, gda[i]))));
+          gdb[i] = fmaf(w.x, gb.x, fmaf(w.y, gb.y, fmaf(w.z, gb.z, fmaf(w.w, gb.w, gdb[i]))));
+        }
+      }
+      const size_t rowa = ((size_t)b * F + ta) * NFILT;
       const float k10 = 4.342944819032518f;  // 10 / ln 10
-      const float da = to_db(ea), db = to_db(eb);
-      gea[m] = (da > floor_v && ea >= 1e-10f) ? gda * k10 / ea : 0.f;
-      geb[m] = (has_b && db > floor_v && eb >= 1e-10f) ? gdb * k10 / eb : 0.f;
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const int m = lane + 32 * i;
+        if ((unsigned)(rowa + m) == amax_idx) gda[i] += mass_total;
+        if ((unsigned)(rowa + NFILT + m) == amax_idx) gdb[i] += mass_total;
+        const float da = to_db(ea[i]), db = to_db(eb[i]);
+        gea[m] = (da > floor_v && ea[i] >= 1e-10f) ? gda[i] * k10 / ea[i] : 0.f;
+        geb[m] = (has_b && db > floor_v && eb[i] >= 1e-10f) ? gdb[i] * k10 / eb[i] : 0.f;
+      }
     }
     __syncwarp();
     // 5. d power (overwrites the power buffers)
@@ -463,33 +509,29 @@ __global__ void __launch_bounds__(FB_THREADS) fe_bwd_kernel(const float* __restr
       pb[k] = sb;
     }
     __syncwarp();
-    // 6. conj(H), H = Ha + i Hb Hermitian-extended one-sided gradients (no doubling of interior bins), bit-reversed
+    // 6. conj(H) into bufA, H = Ha + i Hb Hermitian-extended one-sided gradients (no doubling of interior bins)
     for (int k = lane; k < NBIN; k += 32) {
       float xar, xai, xbr, xbi;
-      unpack_bin(re, im, k, xar, xai, xbr, xbi);
+      unpack_bin(bufB, k, xar, xai, xbr, xbi);
       const float ga = pa[k], gb = pb[k];
-      const int rk = __brev((unsigned)k) >> 23;
       if (k == 0 || k == 256) {
-        re2[rk] = 2.f * ga * xar;
-        im2[rk] = -(2.f * gb * xbr);
+        bufA[k] = make_float2(2.f * ga * xar, -(2.f * gb * xbr));
       } else {
         const float har = ga * xar, hai = ga * xai, hbr = gb * xbr, hbi = gb * xbi;
-        const int rk2 = __brev((unsigned)(NFFT - k)) >> 23;
-        re2[rk] = har - hbi;
-        im2[rk] = -(hai + hbr);
-        re2[rk2] = har + hbi;
-        im2[rk2] = -(hbr - hai);
+        bufA[k] = make_float2(har - hbi, -(hai + hbr));
+        bufA[NFFT - k] = make_float2(har + hbi, -(hbr - hai));
       }
     }
     __syncwarp();
-    // 7. W = conj(FFT(conj H)): ya = Re, yb = -Im
-    warp_fft512(re2, im2, s_twr, s_twi, lane);
+    // 7. W = conj(FFT(conj H)): ya = Re, yb = -Im   (result in bufB; Z is no longer needed)
+    warp_fft512(bufA, bufB, s_tw, lane);
     // 8. window and park per-frame
     float* ywa = s_yw + (2 * pair) * WIN;
     for (int n = lane; n < WIN; n += 32) {
       const float w = s_win[n];
-      ywa[n] = w * re2[n + WOFF];
-      if (has_b) ywa[WIN + n] = -(w * im2[n + WOFF]);
+      const float2 v = bufB[n + WOFF];
+      ywa[n] = w * v.x;
+      if (has_b) ywa[WIN + n] = -(w * v.y);
     }
     __syncwarp();
   }
@@ -520,10 +562,10 @@ __global__ void __launch_bounds__(FB_THREADS) fe_bwd_kernel(const float* __restr
   }
 }
 
-size_t fe_fwd_smem() { return (size_t)(256 + 256 + 400 + FE_WARPS * 1024 + FE_WARPS * 2 * PSTRIDE) * sizeof(float); }
+size_t fe_fwd_smem() { return (size_t)(1024 + 400 + FE_WARPS * 2 * (FFT_A + FFT_B) + FE_WARPS * 2 * PSTRIDE) * sizeof(float); }
 size_t fe_dct_smem() { return (size_t)(NFILT * NCOEF + 16 * NFILT) * sizeof(float); }
 size_t fe_bwd_smem() {
-  return (size_t)(256 + 256 + 400 + NFILT * DCT_LD + FB_WARPS * 2048 + FB_WARPS * 2 * PSTRIDE + FB_WARPS * 2 * NFILT +
+  return (size_t)(1024 + 400 + NFILT * DCT_LD + FB_WARPS * 2 * (FFT_A + FFT_B) + FB_WARPS * 2 * PSTRIDE + FB_WARPS * 2 * NFILT +
                   FB_WARPS * 2 * NCOEF + NF_MAX * WIN) *
          sizeof(float);
 }
@@ -533,8 +575,8 @@ size_t fe_bwd_smem() {
 int frontend_frames(int T) { return 1 + T / HOP; }
 int frontend_mass_blocks(int B, int T) { return B * cdiv(frontend_frames(T), 2 * FE_WARPS); }
 
-int frontend_init_constants(float* twr, float* twi, cudaStream_t stream) {
-  fe_twiddle_kernel<<<1, 256, 0, stream>>>(twr, twi);
+int frontend_init_constants(float2* tw, cudaStream_t stream) {
+  fe_twiddle_kernel<<<2, 256, 0, stream>>>(tw);
   ADVB_KERNEL_OK("fe_twiddle", stream);
   ADVB_CUDA_OK(cudaFuncSetAttribute(fe_power_db_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fe_fwd_smem()));
   ADVB_CUDA_OK(cudaFuncSetAttribute(fe_floor_dct_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fe_dct_smem()));

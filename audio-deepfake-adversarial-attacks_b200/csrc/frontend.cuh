@@ -8,8 +8,7 @@ struct FrontendTables {
   const float* fb;      // (257,128) live buffer of the model (frontend.filter_mat / ...mel_scale.fb)
   const float* dct;     // (128,80)  live buffer (frontend.dct_mat)
   const float* window;  // (400)     live buffer (Hann)
-  const float* twr;     // 256  cos(2 pi k / 512)      (engine-owned constants)
-  const float* twi;     // 256 -sin(2 pi k / 512)
+  const float2* tw;     // 512  (cos, -sin)(2 pi n / 512)   (engine-owned constants)
   int* klo;             // 128: first non-zero bin of each filter   (rebuilt from fb on every call)
   int* kcnt;            // 128: number of bins spanned
   int* mlo;             // 257: first filter touching each bin
@@ -24,7 +23,7 @@ struct FrontendState {
 
 int frontend_frames(int T);
 int frontend_mass_blocks(int B, int T);
-int frontend_init_constants(float* twr, float* twi, cudaStream_t stream);
+int frontend_init_constants(float2* tw, cudaStream_t stream);
 int frontend_prepare(const FrontendTables& tb, cudaStream_t stream);
 
 // out[b*clip_stride + offset + f*stride_f + c*stride_c] = coefficient c of frame f

@@ -19,48 +19,51 @@ constexpr int HID = 80;
 constexpr int G4 = 4 * HID;  // 320
 constexpr int CL = 2;        // clips per recurrence CTA
 
-// C[M,N] = A[M,K] * Bm[K,N] (+ bias[N]) (+ Cadd[M,N]); row-major; 64x64 tile, 4x4 per thread.
+// C[M,N] = A[M,K] * Bm[K,N] (+ bias[N]) (+ Cadd[M,N]); row-major; TILE x TILE tile, (TILE/16)^2 per thread.
+// TILE = 32 is used when 64x64 tiles would leave most SMs idle (the narrow N = 160 backward projections).
+template <int TILE>
 __global__ void __launch_bounds__(256) gemm_kernel(const float* __restrict__ A, const float* __restrict__ Bm,
                                                     const float* __restrict__ bias, const float* __restrict__ Cadd,
                                                     float* __restrict__ C, int M, int N, int K) {
-  __shared__ float As[16][65];
-  __shared__ float Bs[16][64];
+  constexpr int R = TILE / 16;
+  __shared__ float As[16][TILE + 1];
+  __shared__ float Bs[16][TILE];
   const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
-  const int m0 = blockIdx.y * 64, n0 = blockIdx.x * 64;
-  float acc[4][4] = {};
+  const int m0 = blockIdx.y * TILE, n0 = blockIdx.x * TILE;
+  float acc[R][R] = {};
   for (int k0 = 0; k0 < K; k0 += 16) {
-    for (int i = tid; i < 64 * 16; i += 256) {
+    for (int i = tid; i < TILE * 16; i += 256) {
       const int r = i >> 4, c = i & 15;
       const int m = m0 + r, k = k0 + c;
       As[c][r] = (m < M && k < K) ? A[(size_t)m * K + k] : 0.f;
     }
-    for (int i = tid; i < 16 * 64; i += 256) {
-      const int r = i >> 6, c = i & 63;
+    for (int i = tid; i < 16 * TILE; i += 256) {
+      const int r = i / TILE, c = i % TILE;
       const int k = k0 + r, n = n0 + c;
       Bs[r][c] = (k < K && n < N) ? Bm[(size_t)k * N + n] : 0.f;
     }
     __syncthreads();
 #pragma unroll
     for (int kk = 0; kk < 16; ++kk) {
-      float a[4], bv[4];
+      float a[R], bv[R];
 #pragma unroll
-      for (int i = 0; i < 4; ++i) a[i] = As[kk][ty * 4 + i];
+      for (int i = 0; i < R; ++i) a[i] = As[kk][ty * R + i];
 #pragma unroll
-      for (int j = 0; j < 4; ++j) bv[j] = Bs[kk][tx * 4 + j];
+      for (int j = 0; j < R; ++j) bv[j] = Bs[kk][tx * R + j];
 #pragma unroll
-      for (int i = 0; i < 4; ++i)
+      for (int i = 0; i < R; ++i)
 #pragma unroll
-        for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(a[i], bv[j], acc[i][j]);
+        for (int j = 0; j < R; ++j) acc[i][j] = fmaf(a[i], bv[j], acc[i][j]);
     }
     __syncthreads();
   }
 #pragma unroll
-  for (int i = 0; i < 4; ++i) {
-    const int m = m0 + ty * 4 + i;
+  for (int i = 0; i < R; ++i) {
+    const int m = m0 + ty * R + i;
     if (m >= M) continue;
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      const int n = n0 + tx * 4 + j;
+    for (int j = 0; j < R; ++j) {
+      const int n = n0 + tx * R + j;
       if (n >= N) continue;
       float v = acc[i][j];
       if (bias != nullptr) v += bias[n];
@@ -284,8 +287,13 @@ int rnn_init() {
 
 int gemm(const float* A, const float* Bm, const float* bias, const float* Cadd, float* C, int M, int N, int K,
          cudaStream_t stream, const char* tag) {
-  dim3 grid(cdiv(N, 64), cdiv(M, 64));
-  gemm_kernel<<<grid, 256, 0, stream>>>(A, Bm, bias, Cadd, C, M, N, K);
+  if (cdiv(N, 64) * cdiv(M, 64) < 2 * 148) {
+    dim3 grid(cdiv(N, 32), cdiv(M, 32));
+    gemm_kernel<32><<<grid, 256, 0, stream>>>(A, Bm, bias, Cadd, C, M, N, K);
+  } else {
+    dim3 grid(cdiv(N, 64), cdiv(M, 64));
+    gemm_kernel<64><<<grid, 256, 0, stream>>>(A, Bm, bias, Cadd, C, M, N, K);
+  }
   ADVB_KERNEL_OK(tag, stream);
   return 0;
 }
