@@ -54,4 +54,11 @@ int conv_tc_backward(const ConvBwdArgs& a, const unsigned char* wpack, int passe
 int conv0_tc_backward(const float* gout, const unsigned char* codes, const unsigned char* wpack, float* T, float* gin,
                       int B, int H, int W, int Ho, int Wo, int passes, cudaStream_t stream);
 
+// ---- persistent pipelined kernels for the first block and the 1x1 blocks, conv_light.cu (same packed weights) ----
+bool conv_light_supported(int Cin, int Cout, int KS, bool pool, bool bwd);
+int conv_light_forward(const ConvFwdArgs& a, const unsigned char* wpack, int passes, cudaStream_t stream);
+int conv_light_backward(const ConvBwdArgs& a, const unsigned char* wpack, int passes, cudaStream_t stream);
+int conv0_light_backward_gemm(const float* gout, const unsigned char* codes, const unsigned char* wpack, float* T, int B,
+                              int H, int W, int Ho, int Wo, int passes, cudaStream_t stream);
+
 }  // namespace advb

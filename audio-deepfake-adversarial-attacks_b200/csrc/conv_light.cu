@@ -1,0 +1,557 @@
+// LCNN "light" convolution blocks on tcgen05: the first block (1 -> 64, 5x5, as an im2col GEMM with K = 25 taps), its
+// backward GEMM, and the 1x1 blocks, as PERSISTENT software-pipelined kernels (sm_100a).
+//
+// These layers have almost no arithmetic per byte (K <= 64): conv_tc.cu's one-tile-per-CTA version spent its time on
+// per-CTA fixed costs and on the serial latency chain  global load -> convert -> MMA -> TMEM load -> store  (7 us per
+// 128-pixel tile, profiles/r01_launches_tc.md).  Here a CTA loops over 128-pixel tiles and keeps, per SM:
+//   * all weight slices resident in shared memory (one TMA bulk copy per CTA),
+//   * the NEXT tile's global loads in flight in registers while the current tile is converted / multiplied / drained,
+//   * two TMEM accumulators and a dedicated MMA-issue warp, so the MMAs of tile i overlap the epilogue of tile i-1
+//     (TMEM -> registers -> bias / Max-Feature-Map -> shared staging -> pool / BatchNorm -> coalesced stores) run by
+//     the 8 worker warps.  (Issuing tcgen05.mma blocks the issuing thread for about as long as the MMAs execute - the
+//     queue is shallow - so an issuer that also takes part in the epilogue's barriers serialises the two; measured
+//     with the kernel's own clock64 phase counters, ADVB_LIGHT_PROF=1.)
+// Numerics are identical to conv_tc.cu (3xTF32 split, fp32 accumulation in TMEM, same epilogue arithmetic).
+//
+// Tile -> pixel maps (no halo: K spans channels or im2col taps only):
+//   FLAT  1x1 blocks: 128 consecutive pixels of the clip's H*W grid;
+//   BLK   first block forward: 8 rows x 16 columns, so the 2x2 max-pool stays inside the tile;
+//   OVL4  first block backward: 128 consecutive pixels, consecutive tiles overlap by 4 so the horizontal half of
+//         col2im (T[y][x][dy] = sum_dx Z[y][x - dx + 2][5 dy + dx]) finds its +-2 neighbours inside the tile.
+#include <stdlib.h>
+
+#include "conv.cuh"
+#include "tc_common.cuh"
+
+namespace advb {
+
+namespace {
+
+using namespace tc;
+
+constexpr int LW = 256;       // worker threads (load / convert / epilogue)
+constexpr int LT = LW + 32;   // + one dedicated MMA-issue warp
+
+__host__ __device__ constexpr int pow2_ceil32(int v) {
+  int p = 32;
+  while (p < v) p <<= 1;
+  return p;
+}
+
+struct LArgs {
+  int B, H, W, Ho, Wo;
+  int tiles_per_clip, n_tiles, tiles_x;
+  const unsigned char* wpack;
+  const float* in;
+  float* out;
+  int out_pad;
+  unsigned char* codes;
+  const float* bias;
+  const float* bn_mean;
+  const float* bn_invstd;
+  const float* gout;
+  const unsigned char* codes_in;
+  float* gin;
+  int passes;
+  long long* prof;  // optional (ADVB_LIGHT_PROF=1): per-phase cycle counts of CTA 0, thread 0
+};
+
+template <int KTOT, int NOUT, bool POOL, bool BWD, bool IM2COL>
+struct LCfg {
+  static constexpr int NKC = (KTOT + 31) / 32;
+  static constexpr int NSTRIDE = pow2_ceil32(NOUT);
+  static constexpr int TMEM_COLS = 2 * NSTRIDE;          // two accumulators (power of two)
+  static constexpr int W_BYTES = NKC * 2 * NOUT * 128;   // resident weights: per chunk hi image then lo image
+  static constexpr int BAND_BYTES = NKC * 2 * 128 * 128; // per chunk: hi rows then lo rows (128 rows x 128 B)
+  static constexpr int CS = BWD ? NOUT : NOUT / 2;       // channels per staged pixel
+  static constexpr int SS = CS + 4;
+  static constexpr int STAGE_BYTES = 128 * SS * 4 + 128 * 8;
+  static constexpr size_t SMEM = (size_t)W_BYTES + BAND_BYTES + STAGE_BYTES + 1024;
+  static constexpr int MAP = IM2COL ? (BWD ? 1 : 2) : 0;  // 0 FLAT, 1 OVL4, 2 BLK
+  static constexpr int STEP = MAP == 1 ? 124 : 128;       // new pixels per tile (FLAT / OVL4)
+};
+
+// pixel of tile-local row m: (y, x) on the conv grid; false when the row is padding
+template <int MAP>
+__device__ __forceinline__ bool tile_pixel(const LArgs& a, int tl, int m, int Heff, int& y, int& x) {
+  if (MAP == 2) {
+    const int ty = tl / a.tiles_x, tx = tl - ty * a.tiles_x;
+    y = 8 * ty + (m >> 4);
+    x = 16 * tx + (m & 15);
+    return y < Heff && x < a.W;
+  }
+  const int px = (MAP == 1 ? 124 * tl - 2 : 128 * tl) + m;
+  const bool ok = px >= 0 && px < Heff * a.W;
+  const int p = ok ? px : 0;
+  y = p / a.W;
+  x = p - y * a.W;
+  return ok;
+}
+
+template <int KTOT, int NOUT, bool POOL, bool BWD, bool IM2COL>
+__global__ void __launch_bounds__(LT, (LCfg<KTOT, NOUT, POOL, BWD, IM2COL>::SMEM <= 113 * 1024) ? 2 : 1)
+conv_light_kernel(LArgs a) {
+  using Cfg = LCfg<KTOT, NOUT, POOL, BWD, IM2COL>;
+  constexpr int NKC = Cfg::NKC, CS = Cfg::CS, SS = Cfg::SS, MAP = Cfg::MAP;
+  constexpr uint32_t IDESC = idesc_tf32(128, NOUT);
+  static_assert(!BWD || KTOT == 64, "light backward kernels assume Cout = 64 (one 32-channel chunk per MFM half)");
+  static_assert(!(IM2COL && !BWD) || KTOT == 32, "first-block forward: 25 taps padded to one 32-wide chunk");
+
+  extern __shared__ unsigned char smem_raw[];
+  unsigned char* base = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  unsigned char* w_s = base;                       // [NKC][hi NOUT x 128 B | lo NOUT x 128 B]
+  unsigned char* band = w_s + Cfg::W_BYTES;        // [NKC][hi 128 x 128 B | lo 128 x 128 B]   (W_BYTES is a multiple of 1024)
+  float* stage = reinterpret_cast<float*>(band + Cfg::BAND_BYTES);
+  unsigned long long* flags = reinterpret_cast<unsigned long long*>(stage + 128 * SS);
+  __shared__ uint64_t bar_w, bar_mma[2], bar_full;
+  __shared__ uint32_t tmem_base_s;
+  __shared__ float s_bias[BWD ? 1 : NOUT];
+
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int Heff = (!BWD && POOL) ? 2 * a.Ho : a.H;
+
+  if (tid == 0) {
+    mbar_init(&bar_w, 1);
+    mbar_init(&bar_mma[0], 1);
+    mbar_init(&bar_mma[1], 1);
+    mbar_init(&bar_full, LW / 32);
+    fence_barrier_init();
+  }
+  if (warp == 0) tmem_alloc<Cfg::TMEM_COLS>(&tmem_base_s);
+  if (!BWD)
+    for (int i = tid; i < NOUT; i += LT) s_bias[i] = __ldg(a.bias + i);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = tmem_base_s;
+  if (tid == 0) {
+    mbar_expect_tx(&bar_w, Cfg::W_BYTES);
+    bulk_g2s(w_s, a.wpack, Cfg::W_BYTES, &bar_w);
+  }
+
+  if (warp == LW / 32) {
+    // ================= MMA-issue warp =================
+    mbar_wait(&bar_w, 0u);
+    const bool leader = elect_one();
+    int it = 0;
+    for (int tile = blockIdx.x; tile < a.n_tiles; tile += gridDim.x, ++it) {
+      const int buf = it & 1;
+      mbar_wait(&bar_full, (uint32_t)(it & 1));  // band of tile `it` is staged (and accumulator `buf` has been drained)
+      tc_fence_after();
+      const uint32_t dcol = tmem + buf * Cfg::NSTRIDE;
+#pragma unroll
+      for (int kc = 0; kc < NKC; ++kc) {
+        const int kvalid = (KTOT - 32 * kc) >= 32 ? 32 : (KTOT - 32 * kc);
+        const uint32_t a_hi = smem_u32(band + (size_t)kc * 2 * 128 * 128), a_lo = a_hi + 128 * 128;
+        const uint32_t w_hi = smem_u32(w_s + (size_t)kc * 2 * NOUT * 128), w_lo = w_hi + NOUT * 128;
+#pragma unroll 1
+        for (int ks = 0; ks < kvalid / 8; ++ks) {
+          const uint64_t ah = desc_sw128(a_hi + ks * 32), al = desc_sw128(a_lo + ks * 32);
+          const uint64_t bh = desc_sw128(w_hi + ks * 32), bl = desc_sw128(w_lo + ks * 32);
+          if (leader) {
+            mma_tf32(dcol, ah, bh, IDESC, (kc > 0 || ks > 0) ? 1u : 0u);
+            if (a.passes == 3) {
+              mma_tf32(dcol, ah, bl, IDESC, 1u);
+              mma_tf32(dcol, al, bh, IDESC, 1u);
+            }
+          }
+        }
+      }
+      if (leader) mma_commit(&bar_mma[buf]);
+      __syncwarp();
+    }
+    tc_fence_before();
+    __syncthreads();  // matches the workers' final barrier
+    return;
+  }
+  // ================= worker warps =================
+
+  // ---- per-thread item geometry: 4 band rows (m = tid/8 + 32 u), one 16-byte channel group c4 of every chunk ----
+  const int c4 = tid & 7, m0 = tid >> 3;
+  int toff[4];
+  bool tok[4];
+  if (IM2COL && !BWD) {
+    const int Wi = a.W + 4;
+#pragma unroll
+    for (int u4 = 0; u4 < 4; ++u4) {
+      const int tap = 4 * c4 + u4;
+      tok[u4] = tap < 25;
+      const int dy = tap / 5, dx = tap - dy * 5;
+      toff[u4] = tok[u4] ? dy * Wi + dx : 0;
+    }
+  }
+  float4 sc = make_float4(1.f, 1.f, 1.f, 1.f);
+  if (BWD && a.bn_invstd != nullptr) sc = __ldg(reinterpret_cast<const float4*>(a.bn_invstd + 4 * c4));
+
+  // registers holding the next tile's raw loads
+  float4 rv[4][BWD ? 1 : NKC];
+  uchar4 rc[4];
+  unsigned rwant = 0;  // BWD: per item the pool position code it corresponds to (8 bits each), 0xff = padding row
+  unsigned rok = 0;    // forward: bit u = item u is a real pixel (loads are kept RAW until convert_store, so that they
+                       // stay in flight across the epilogue: any use of a loaded value would stall the in-order warp)
+
+  auto issue_loads = [&](int tile) {
+    const int b = tile / a.tiles_per_clip, tl = tile - b * a.tiles_per_clip;
+    rwant = 0;
+    rok = 0;
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      int y, x;
+      bool ok = tile_pixel<MAP>(a, tl, m0 + 32 * u, Heff, y, x);
+      if (BWD) {
+        const int py = POOL ? (y >> 1) : y, px = POOL ? (x >> 1) : x;
+        ok = ok && py < a.Ho && px < a.Wo;
+        const size_t o = ok ? (((size_t)b * a.Ho + py) * a.Wo + px) * 32 + 4 * c4 : 0;
+        rv[u][0] = __ldg(reinterpret_cast<const float4*>(a.gout + o));
+        rc[u] = __ldg(reinterpret_cast<const uchar4*>(a.codes_in + o));
+        const unsigned w = ok ? (POOL ? (unsigned)(((y & 1) << 1) | (x & 1)) : 0u) : 0xffu;
+        rwant |= w << (8 * u);
+      } else if (IM2COL) {
+        const float* img = a.in + ((size_t)b * (a.H + 4) + (ok ? y : 0)) * (a.W + 4) + (ok ? x : 0);
+        rv[u][0].x = __ldg(img + toff[0]);
+        rv[u][0].y = __ldg(img + toff[1]);
+        rv[u][0].z = __ldg(img + toff[2]);
+        rv[u][0].w = __ldg(img + toff[3]);
+        rok |= (ok ? 1u : 0u) << u;
+      } else {
+        const size_t pix = ((size_t)b * a.H + (ok ? y : 0)) * a.W + (ok ? x : 0);
+#pragma unroll
+        for (int kc = 0; kc < NKC; ++kc) {
+          const int ch = 32 * kc + 4 * c4;
+          const bool okc = ok && ch < KTOT;
+          rv[u][kc] = __ldg(reinterpret_cast<const float4*>(a.in + (okc ? pix * KTOT + ch : 0)));
+        }
+        rok |= (ok ? 1u : 0u) << u;
+      }
+    }
+  };
+
+  auto store_item = [&](int kc, int m, float4 v) {
+    float4 hi, lo;
+    split_tf32(v.x, hi.x, lo.x);
+    split_tf32(v.y, hi.y, lo.y);
+    split_tf32(v.z, hi.z, lo.z);
+    split_tf32(v.w, hi.w, lo.w);
+    unsigned char* hb = band + (size_t)kc * 2 * 128 * 128;
+    const uint32_t off = sw128_chunk(m, c4);
+    *reinterpret_cast<float4*>(hb + off) = hi;
+    *reinterpret_cast<float4*>(hb + 128 * 128 + off) = lo;
+  };
+
+  auto convert_store = [&]() {
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int m = m0 + 32 * u;
+      if (BWD) {
+        const unsigned w = (rwant >> (8 * u)) & 0xffu;
+        const float4 g = make_float4(rv[u][0].x * sc.x, rv[u][0].y * sc.y, rv[u][0].z * sc.z, rv[u][0].w * sc.w);
+#pragma unroll
+        for (int kc = 0; kc < NKC; ++kc) {  // chunk kc = MFM half kc of the same 32 channels
+          const unsigned want = w == 0xffu ? 0xffu : (w | (unsigned)(kc << 2));
+          float4 v;
+          v.x = rc[u].x == want ? g.x : 0.f;
+          v.y = rc[u].y == want ? g.y : 0.f;
+          v.z = rc[u].z == want ? g.z : 0.f;
+          v.w = rc[u].w == want ? g.w : 0.f;
+          store_item(kc, m, v);
+        }
+      } else if (IM2COL) {
+        const bool ok = (rok >> u) & 1u;
+        store_item(0, m, make_float4((ok && tok[0]) ? rv[u][0].x : 0.f, (ok && tok[1]) ? rv[u][0].y : 0.f,
+                                     (ok && tok[2]) ? rv[u][0].z : 0.f, (ok && tok[3]) ? rv[u][0].w : 0.f));
+      } else {
+        const bool ok = (rok >> u) & 1u;
+#pragma unroll
+        for (int kc = 0; kc < NKC; ++kc) {
+          const bool okc = ok && (32 * kc + 4 * c4) < KTOT;
+          store_item(kc, m, okc ? rv[u][kc] : make_float4(0.f, 0.f, 0.f, 0.f));
+        }
+      }
+    }
+  };
+
+  // ---- epilogue of one tile: TMEM accumulator `buf` -> staging -> global ----
+  auto epilogue = [&](int tile, int buf) {
+    const int b = tile / a.tiles_per_clip, tl = tile - b * a.tiles_per_clip;
+    asm volatile("bar.sync 1, %0;" ::"n"(LW) : "memory");  // every worker has finished reading the previous staging tile
+    {
+      // TMEM -> registers -> staging.  Warps w and w+4 share TMEM lane quadrant w%4 and split the columns.
+      const int wq = warp & 3, hsel = warp >> 2;
+      const int r = wq * 32 + lane;
+      const uint32_t taddr = tmem + ((uint32_t)(wq * 32) << 16) + buf * Cfg::NSTRIDE;
+      float* srow = stage + (size_t)r * SS;
+      if (BWD) {
+#pragma unroll 1
+        for (int c0 = hsel * 16; c0 < NOUT; c0 += 32) {
+          uint32_t v[16];
+          tmem_ld16_issue(taddr + c0, v);
+          tmem_ld_wait();
+#pragma unroll
+          for (int j = 0; j < 16; j += 4)
+            *reinterpret_cast<float4*>(srow + c0 + j) = make_float4(__uint_as_float(v[j]), __uint_as_float(v[j + 1]),
+                                                                   __uint_as_float(v[j + 2]), __uint_as_float(v[j + 3]));
+        }
+      } else {
+        unsigned fl = 0u;  // this warp's 16-channel groups: bit (c0 + j) of the pixel's MFM flags
+#pragma unroll 1
+        for (int c0 = hsel * 16; c0 < CS; c0 += 32) {
+          uint32_t lo[16], hi[16];
+          tmem_ld16_issue(taddr + c0, lo);
+          tmem_ld16_issue(taddr + CS + c0, hi);
+          tmem_ld_wait();
+          float m4[16];
+#pragma unroll
+          for (int j = 0; j < 16; ++j) {
+            const float l = __uint_as_float(lo[j]) + s_bias[c0 + j];
+            const float h = __uint_as_float(hi[j]) + s_bias[CS + c0 + j];
+            const bool sel = h > l;
+            m4[j] = sel ? h : l;
+            fl |= (sel ? 1u : 0u) << j;
+          }
+#pragma unroll
+          for (int j = 0; j < 16; j += 4)
+            *reinterpret_cast<float4*>(srow + c0 + j) = make_float4(m4[j], m4[j + 1], m4[j + 2], m4[j + 3]);
+          // flags as 16-bit fields: field index = c0 / 16
+          reinterpret_cast<unsigned short*>(flags + r)[c0 >> 4] = (unsigned short)fl;
+          fl = 0u;
+        }
+      }
+    }
+    tc_fence_before();
+    asm volatile("bar.sync 1, %0;" ::"n"(LW) : "memory");
+    constexpr int C4 = CS / 4;
+    if (BWD && IM2COL) {
+      // T[y][x][dy] for the 124 interior pixels of the tile
+      for (int i = tid; i < 124 * 5; i += LW) {
+        const int dy = i % 5, ml = 2 + i / 5;
+        const int px = 124 * tl - 2 + ml;
+        if (px >= a.H * a.W) continue;
+        const int y = px / a.W, x = px - y * a.W;
+        float acc = 0.f;
+#pragma unroll
+        for (int dx = 0; dx < 5; ++dx) {
+          const int xs = x - dx + 2;
+          if (xs >= 0 && xs < a.W) acc += stage[(size_t)(ml - dx + 2) * SS + 5 * dy + dx];
+        }
+        a.gin[((size_t)b * a.H * a.W + px) * 5 + dy] = acc;
+      }
+    } else if (BWD) {
+      const int npx = min(128, a.H * a.W - 128 * tl);
+      for (int i = tid; i < npx * C4; i += LW) {
+        const int c4i = i % C4, ml = i / C4;
+        const float4 v = *reinterpret_cast<const float4*>(stage + (size_t)ml * SS + 4 * c4i);
+        *reinterpret_cast<float4*>(a.gin + ((size_t)b * a.H * a.W + 128 * tl + ml) * NOUT + 4 * c4i) = v;
+      }
+    } else if (POOL) {
+      // 8 x 16 pixel tile -> 4 x 8 pooled cells
+      const int ty = tl / a.tiles_x, tx = tl - ty * a.tiles_x;
+      const int Hop = a.Ho + 2 * a.out_pad, Wop = a.Wo + 2 * a.out_pad;
+      for (int i = tid; i < 32 * C4; i += LW) {
+        const int c4i = i % C4, cell = i / C4;
+        const int cy = cell >> 3, cx = cell & 7;
+        const int oy = 4 * ty + cy, ox = 8 * tx + cx;
+        if (oy >= a.Ho || ox >= a.Wo) continue;
+        const int c = 4 * c4i;
+        const int r00 = (2 * cy) * 16 + 2 * cx;
+        const int rr[4] = {r00, r00 + 1, r00 + 16, r00 + 17};
+        float best[4];
+        unsigned code[4];
+#pragma unroll
+        for (int p = 0; p < 4; ++p) {
+          const float4 t = *reinterpret_cast<const float4*>(stage + (size_t)rr[p] * SS + c);
+          const unsigned f = (unsigned)(flags[rr[p]] >> c) & 15u;
+          const float tv[4] = {t.x, t.y, t.z, t.w};
+#pragma unroll
+          for (int k = 0; k < 4; ++k)
+            if (p == 0 || tv[k] > best[k]) {
+              best[k] = tv[k];
+              code[k] = (((f >> k) & 1u) << 2) | (unsigned)p;
+            }
+        }
+        float4 v = make_float4(best[0], best[1], best[2], best[3]);
+        if (a.bn_mean != nullptr) {
+          const float4 is = __ldg(reinterpret_cast<const float4*>(a.bn_invstd + c));
+          v.x = (v.x - __ldg(a.bn_mean + c)) * is.x;
+          v.y = (v.y - __ldg(a.bn_mean + c + 1)) * is.y;
+          v.z = (v.z - __ldg(a.bn_mean + c + 2)) * is.z;
+          v.w = (v.w - __ldg(a.bn_mean + c + 3)) * is.w;
+        }
+        *reinterpret_cast<float4*>(a.out + (((size_t)b * Hop + oy + a.out_pad) * Wop + ox + a.out_pad) * CS + c) = v;
+        *reinterpret_cast<uchar4*>(a.codes + (((size_t)b * a.Ho + oy) * a.Wo + ox) * CS + c) =
+            make_uchar4((unsigned char)code[0], (unsigned char)code[1], (unsigned char)code[2], (unsigned char)code[3]);
+      }
+    } else {
+      const int Hop = a.Ho + 2 * a.out_pad, Wop = a.Wo + 2 * a.out_pad;
+      const int npx = min(128, a.H * a.W - 128 * tl);
+      for (int i = tid; i < npx * C4; i += LW) {
+        const int c4i = i % C4, ml = i / C4;
+        const int c = 4 * c4i;
+        const int px = 128 * tl + ml;
+        const int y = px / a.W, x = px - y * a.W;
+        float4 v = *reinterpret_cast<const float4*>(stage + (size_t)ml * SS + c);
+        const unsigned f = (unsigned)(flags[ml] >> c) & 15u;
+        if (a.bn_mean != nullptr) {
+          const float4 is = __ldg(reinterpret_cast<const float4*>(a.bn_invstd + c));
+          v.x = (v.x - __ldg(a.bn_mean + c)) * is.x;
+          v.y = (v.y - __ldg(a.bn_mean + c + 1)) * is.y;
+          v.z = (v.z - __ldg(a.bn_mean + c + 2)) * is.z;
+          v.w = (v.w - __ldg(a.bn_mean + c + 3)) * is.w;
+        }
+        *reinterpret_cast<float4*>(a.out + (((size_t)b * Hop + y + a.out_pad) * Wop + x + a.out_pad) * CS + c) = v;
+        *reinterpret_cast<uchar4*>(a.codes + ((size_t)b * a.H * a.W + px) * CS + c) =
+            make_uchar4((unsigned char)((f & 1u) << 2), (unsigned char)(((f >> 1) & 1u) << 2),
+                        (unsigned char)(((f >> 2) & 1u) << 2), (unsigned char)(((f >> 3) & 1u) << 2));
+      }
+    }
+  };
+
+  // ---- persistent loop (workers) ----
+  int tile = blockIdx.x;
+  if (tile < a.n_tiles) issue_loads(tile);
+  int it = 0, prev_tile = -1;
+  long long pc[4] = {0, 0, 0, 0};
+  const bool prof = a.prof != nullptr && blockIdx.x == 0 && tid == 0;
+#define LPROF(k)                      \
+  if (prof) {                         \
+    const long long now_ = clock64(); \
+    pc[k] += now_ - t_last;           \
+    t_last = now_;                    \
+  }
+  long long t_last = clock64();
+  for (; tile < a.n_tiles; tile += gridDim.x, ++it) {
+    const int buf = it & 1;
+    if (it > 0) {  // MMAs of the previous tile have finished reading the band (and its accumulator is complete)
+      mbar_wait(&bar_mma[buf ^ 1], (uint32_t)(((it - 1) >> 1) & 1));
+      tc_fence_after();
+    }
+    LPROF(0)
+    convert_store();
+    fence_proxy_async();
+    tc_fence_before();
+    __syncwarp();
+    if (lane == 0) mbar_arrive(&bar_full);  // 8 worker warps -> the MMA warp may issue tile `it`
+    LPROF(1)
+    const int next = tile + gridDim.x;
+    if (next < a.n_tiles) issue_loads(next);
+    LPROF(2)
+    if (it > 0) epilogue(prev_tile, buf ^ 1);  // overlaps the MMAs of tile `it`
+    LPROF(3)
+    prev_tile = tile;
+  }
+  if (prof) {
+    for (int k = 0; k < 4; ++k) a.prof[k] = pc[k];
+    a.prof[6] = it;
+  }
+  if (it > 0) {
+    const int buf = (it - 1) & 1;
+    mbar_wait(&bar_mma[buf], (uint32_t)(((it - 1) >> 1) & 1));
+    tc_fence_after();
+    epilogue(prev_tile, buf);
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc<Cfg::TMEM_COLS>(tmem);
+}
+
+int tune_light_persistent() {
+  static const int v = [] {
+    const char* e = getenv("ADVB_LIGHT_PERSISTENT");
+    return e != nullptr ? atoi(e) : 1;
+  }();
+  return v;
+}
+
+template <int KTOT, int NOUT, bool POOL, bool BWD, bool IM2COL>
+int launch_light(LArgs a, const char* tag, cudaStream_t stream) {
+  using Cfg = LCfg<KTOT, NOUT, POOL, BWD, IM2COL>;
+  static_assert(Cfg::SMEM <= 227 * 1024, "light conv kernel does not fit shared memory");
+  static_assert(Cfg::W_BYTES % 1024 == 0, "weight image must keep the band 1024-byte aligned");
+  const int Heff = (!BWD && POOL) ? 2 * a.Ho : a.H;
+  if (Cfg::MAP == 2) {
+    a.tiles_x = cdiv(a.W, 16);
+    a.tiles_per_clip = cdiv(Heff, 8) * a.tiles_x;
+  } else {
+    a.tiles_x = 1;
+    a.tiles_per_clip = cdiv(Heff * a.W, Cfg::STEP);
+  }
+  a.n_tiles = a.B * a.tiles_per_clip;
+  auto kern = conv_light_kernel<KTOT, NOUT, POOL, BWD, IM2COL>;
+  ADVB_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::SMEM));
+  ADVB_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+  // CTAs per SM by shared memory (227 KB, + 1 KB the driver reserves per CTA), TMEM columns (512) and registers
+  // (__launch_bounds__ asks for 2).  A larger grid than the SMs can hold at once is harmless: tiles are strided by
+  // gridDim.x and the surplus CTAs simply start later.
+  int per_sm = (int)((227 * 1024) / (Cfg::SMEM + 1024));
+  if (per_sm > 512 / Cfg::TMEM_COLS) per_sm = 512 / Cfg::TMEM_COLS;
+  if (per_sm > 2) per_sm = 2;
+  if (per_sm < 1) per_sm = 1;
+  int n_sm = 148;
+  int dev = 0;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev);
+  int grid = n_sm * per_sm;
+  if (grid > a.n_tiles) grid = a.n_tiles;
+  static long long* prof_buf = nullptr;
+  static const bool want_prof = getenv("ADVB_LIGHT_PROF") != nullptr;
+  if (want_prof && prof_buf == nullptr) cudaMalloc(reinterpret_cast<void**>(&prof_buf), 8 * sizeof(long long));
+  a.prof = want_prof ? prof_buf : nullptr;
+  kern<<<grid, LT, Cfg::SMEM, stream>>>(a);
+  ADVB_KERNEL_OK(tag, stream);
+  if (want_prof) {
+    long long hp[8];
+    cudaStreamSynchronize(stream);
+    cudaMemcpy(hp, prof_buf, sizeof(hp), cudaMemcpyDeviceToHost);
+    fprintf(stderr, "[light %s] grid %d per_sm %d tiles/cta %lld | cycles/tile: wait_mma %lld convert %lld issue_loads %lld epilogue %lld\n",
+            tag, grid, per_sm, hp[6], hp[0] / hp[6], hp[1] / hp[6], hp[2] / hp[6], hp[3] / hp[6]);
+  }
+  return 0;
+}
+
+}  // namespace
+
+bool conv_light_supported(int Cin, int Cout, int KS, bool pool, bool bwd) {
+  if (tune_light_persistent() == 0) return false;
+  if (KS == 5) return Cin == 1 && Cout == 64 && pool;
+  if (KS != 1 || pool) return false;
+  if (!bwd) return (Cin == 32 && Cout == 64) || (Cin == 48 && Cout == 96) || (Cin == 64 && Cout == 128);
+  return Cout == 64 && Cin == 32;
+}
+
+int conv_light_forward(const ConvFwdArgs& f, const unsigned char* wpack, int passes, cudaStream_t stream) {
+  LArgs a{};
+  a.B = f.B, a.H = f.H, a.W = f.W, a.Ho = f.Ho, a.Wo = f.Wo;
+  a.wpack = wpack;
+  a.in = f.in, a.out = f.out, a.out_pad = f.out_pad, a.codes = f.codes, a.bias = f.bias;
+  a.bn_mean = f.bn_mean, a.bn_invstd = f.bn_invstd;
+  a.passes = passes;
+  if (f.KS == 5) return launch_light<32, 64, true, false, true>(a, f.tag, stream);
+  ADVB_CHECK(f.in_pad == 0, "1x1 light conv expects a border-free input");
+  if (f.Cin == 32 && f.Cout == 64) return launch_light<32, 64, false, false, false>(a, f.tag, stream);
+  if (f.Cin == 48 && f.Cout == 96) return launch_light<48, 96, false, false, false>(a, f.tag, stream);
+  if (f.Cin == 64 && f.Cout == 128) return launch_light<64, 128, false, false, false>(a, f.tag, stream);
+  set_error("conv shape has no light instantiation");
+  return 1;
+}
+
+int conv_light_backward(const ConvBwdArgs& g, const unsigned char* wpack, int passes, cudaStream_t stream) {
+  LArgs a{};
+  a.B = g.B, a.H = g.H, a.W = g.W, a.Ho = g.Ho, a.Wo = g.Wo;
+  a.wpack = wpack;
+  a.gout = g.gout, a.codes_in = g.codes, a.gin = g.gin, a.bn_invstd = g.bn_invstd;
+  a.passes = passes;
+  if (g.KS == 1 && g.Cout == 64 && g.Cin == 32 && !g.pool) return launch_light<64, 32, false, true, false>(a, g.tag, stream);
+  set_error("conv shape has no light instantiation (backward)");
+  return 1;
+}
+
+int conv0_light_backward_gemm(const float* gout, const unsigned char* codes, const unsigned char* wpack, float* T, int B,
+                              int H, int W, int Ho, int Wo, int passes, cudaStream_t stream) {
+  LArgs a{};
+  a.B = B, a.H = H, a.W = W, a.Ho = Ho, a.Wo = Wo;
+  a.wpack = wpack;
+  a.gout = gout, a.codes_in = codes, a.gin = T, a.bn_invstd = nullptr;
+  a.passes = passes;
+  return launch_light<64, 32, true, true, true>(a, "conv0_bwd_gemm", stream);
+}
+
+}  // namespace advb

@@ -579,6 +579,7 @@ bool conv_tc_supported(int Cin, int Cout, int KS, bool pool) {
 
 int conv_tc_forward(const ConvFwdArgs& f, const unsigned char* wpack, int passes, cudaStream_t stream) {
   ADVB_CHECK(f.in_pad == f.KS / 2, "tensor-core conv needs the input border to equal the conv padding");
+  if (conv_light_supported(f.Cin, f.Cout, f.KS, f.pool, false)) return conv_light_forward(f, wpack, passes, stream);
   TcArgs a{};
   if (f.KS == 5) {  // first block: contraction over the 25 taps (padded to 32), pixel grid without border
     ADVB_CHECK(f.Cin == 1 && f.Cout == 64 && f.pool, "5x5 tensor-core conv is the LCNN first block only");
@@ -632,7 +633,10 @@ int conv0_tc_backward(const float* gout, const unsigned char* codes, const unsig
   a.wpack = wpack;
   a.gout = gout, a.codes_in = codes, a.gin = T, a.bn_invstd = nullptr;
   a.passes = passes;
-  ADVB_TRY((launch_tc<1, 64, 32, true, true, true, 2>(a, "conv0_bwd_gemm", stream)));
+  if (conv_light_supported(1, 64, 5, true, true))
+    ADVB_TRY(conv0_light_backward_gemm(gout, codes, wpack, T, B, H, W, Ho, Wo, passes, stream));
+  else
+    ADVB_TRY((launch_tc<1, 64, 32, true, true, true, 2>(a, "conv0_bwd_gemm", stream)));
   const int n = B * H * W;
   conv0_col2im_rows_kernel<<<cdiv(n, 256), 256, 0, stream>>>(T, gin, H, W, n);
   ADVB_KERNEL_OK("conv0_bwd_rows", stream);
@@ -640,6 +644,7 @@ int conv0_tc_backward(const float* gout, const unsigned char* codes, const unsig
 }
 
 int conv_tc_backward(const ConvBwdArgs& g, const unsigned char* wpack, int passes, cudaStream_t stream) {
+  if (conv_light_supported(g.Cin, g.Cout, g.KS, g.pool, true)) return conv_light_backward(g, wpack, passes, stream);
   TcArgs a{};
   a.B = g.B, a.H = g.H, a.W = g.W, a.Ho = g.Ho, a.Wo = g.Wo;
   a.wpack = wpack;
