@@ -53,6 +53,7 @@ struct LArgs {
   const unsigned char* codes_in;
   float* gin;
   int passes;
+  FastDiv dTiles, dTx, dW;  // tiles per clip, column tiles (BLK map), conv grid width
   long long* prof;  // optional (ADVB_LIGHT_PROF=1): per-phase cycle counts of CTA 0, thread 0
 };
 
@@ -75,7 +76,7 @@ struct LCfg {
 template <int MAP>
 __device__ __forceinline__ bool tile_pixel(const LArgs& a, int tl, int m, int Heff, int& y, int& x) {
   if (MAP == 2) {
-    const int ty = tl / a.tiles_x, tx = tl - ty * a.tiles_x;
+    const int ty = fdiv(tl, a.dTx), tx = tl - ty * a.tiles_x;
     y = 8 * ty + (m >> 4);
     x = 16 * tx + (m & 15);
     return y < Heff && x < a.W;
@@ -83,7 +84,7 @@ __device__ __forceinline__ bool tile_pixel(const LArgs& a, int tl, int m, int He
   const int px = (MAP == 1 ? 124 * tl - 2 : 128 * tl) + m;
   const bool ok = px >= 0 && px < Heff * a.W;
   const int p = ok ? px : 0;
-  y = p / a.W;
+  y = fdiv(p, a.dW);
   x = p - y * a.W;
   return ok;
 }
@@ -191,7 +192,7 @@ conv_light_kernel(LArgs a) {
                        // stay in flight across the epilogue: any use of a loaded value would stall the in-order warp)
 
   auto issue_loads = [&](int tile) {
-    const int b = tile / a.tiles_per_clip, tl = tile - b * a.tiles_per_clip;
+    const int b = fdiv(tile, a.dTiles), tl = tile - b * a.tiles_per_clip;
     rwant = 0;
     rok = 0;
 #pragma unroll
@@ -272,7 +273,7 @@ conv_light_kernel(LArgs a) {
 
   // ---- epilogue of one tile: TMEM accumulator `buf` -> staging -> global ----
   auto epilogue = [&](int tile, int buf) {
-    const int b = tile / a.tiles_per_clip, tl = tile - b * a.tiles_per_clip;
+    const int b = fdiv(tile, a.dTiles), tl = tile - b * a.tiles_per_clip;
     asm volatile("bar.sync 1, %0;" ::"n"(LW) : "memory");  // every worker has finished reading the previous staging tile
     {
       // TMEM -> registers -> staging.  Warps w and w+4 share TMEM lane quadrant w%4 and split the columns.
@@ -326,7 +327,7 @@ conv_light_kernel(LArgs a) {
         const int dy = i % 5, ml = 2 + i / 5;
         const int px = 124 * tl - 2 + ml;
         if (px >= a.H * a.W) continue;
-        const int y = px / a.W, x = px - y * a.W;
+        const int y = fdiv(px, a.dW), x = px - y * a.W;
         float acc = 0.f;
 #pragma unroll
         for (int dx = 0; dx < 5; ++dx) {
@@ -344,7 +345,7 @@ conv_light_kernel(LArgs a) {
       }
     } else if (POOL) {
       // 8 x 16 pixel tile -> 4 x 8 pooled cells
-      const int ty = tl / a.tiles_x, tx = tl - ty * a.tiles_x;
+      const int ty = fdiv(tl, a.dTx), tx = tl - ty * a.tiles_x;
       const int Hop = a.Ho + 2 * a.out_pad, Wop = a.Wo + 2 * a.out_pad;
       for (int i = tid; i < 32 * C4; i += LW) {
         const int c4i = i % C4, cell = i / C4;
@@ -387,7 +388,7 @@ conv_light_kernel(LArgs a) {
         const int c4i = i % C4, ml = i / C4;
         const int c = 4 * c4i;
         const int px = 128 * tl + ml;
-        const int y = px / a.W, x = px - y * a.W;
+        const int y = fdiv(px, a.dW), x = px - y * a.W;
         float4 v = *reinterpret_cast<const float4*>(stage + (size_t)ml * SS + c);
         const unsigned f = (unsigned)(flags[ml] >> c) & 15u;
         if (a.bn_mean != nullptr) {
@@ -475,6 +476,9 @@ int launch_light(LArgs a, const char* tag, cudaStream_t stream) {
     a.tiles_per_clip = cdiv(Heff * a.W, Cfg::STEP);
   }
   a.n_tiles = a.B * a.tiles_per_clip;
+  a.dTiles = make_fastdiv(a.tiles_per_clip);
+  a.dTx = make_fastdiv(a.tiles_x);
+  a.dW = make_fastdiv(a.W);
   auto kern = conv_light_kernel<KTOT, NOUT, POOL, BWD, IM2COL>;
   ADVB_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::SMEM));
   ADVB_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));

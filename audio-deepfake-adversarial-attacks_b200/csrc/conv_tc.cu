@@ -72,6 +72,7 @@ struct TcArgs {
   const unsigned char* codes_in;
   float* gin;
   int passes;  // 3 = 3xTF32 (default), 1 = single-pass tf32 (fast, reduced precision)
+  FastDiv dWp, dW, dWo;  // padded row length, conv grid width, output grid width
 };
 
 // KS: filter size; KTOT: contraction channels per tap (fwd: Cin, bwd: Cout); NOUT: GEMM N (fwd: Cout, bwd: Cin).
@@ -172,7 +173,7 @@ __global__ void __launch_bounds__(TC_THREADS, NM == 1 ? 3 : (NM == 2 ? 2 : 1)) c
             const int q = q_lo + (i >> 3);
             bool ok = ch_ok && i < total && q >= 0 && q < npix;
             const int qq = ok ? q : 0;
-            const int yp = qq / Wp, xp = qq - yp * Wp;
+            const int yp = fdiv(qq, a.dWp), xp = qq - yp * Wp;
             const int y = yp - PC, x = xp - PC;
             ok = ok && y >= 0 && y < a.H && x >= 0 && x < a.W;
             const int py = POOL ? (y >> 1) : y, px = POOL ? (x >> 1) : x;
@@ -224,7 +225,7 @@ __global__ void __launch_bounds__(TC_THREADS, NM == 1 ? 3 : (NM == 2 ? 2 : 1)) c
             const int q = q_lo + (i >> 3);
             const bool ok = i < total && q >= 0 && q < npix;
             const int qq = ok ? q : 0;
-            const int y = qq / Wp, x = qq - y * Wp;
+            const int y = fdiv(qq, a.dWp), x = qq - y * Wp;
             const float* img = imgb + (size_t)y * Wi + x;
 #pragma unroll
             for (int u4 = 0; u4 < 4; ++u4) {
@@ -385,7 +386,7 @@ __global__ void __launch_bounds__(TC_THREADS, NM == 1 ? 3 : (NM == 2 ? 2 : 1)) c
     //   T[y][x][dy] = sum_dx Z[y][x - dx + 2][5 dy + dx];   conv0_col2im_rows() then sums the 5 rows.
     const int items = rows * a.W * 5;
     for (int i = tid; i < items; i += TC_THREADS) {
-      const int dy = i % 5, x = (i / 5) % a.W, yl = i / (5 * a.W);
+      const int i5 = i / 5, dy = i - 5 * i5, yl = fdiv(i5, a.dW), x = i5 - yl * a.W;
       float acc = 0.f;
 #pragma unroll
       for (int dx = 0; dx < 5; ++dx) {
@@ -397,7 +398,7 @@ __global__ void __launch_bounds__(TC_THREADS, NM == 1 ? 3 : (NM == 2 ? 2 : 1)) c
   } else if (BWD) {
     const int items = rows * a.W * C4;
     for (int i = tid; i < items; i += TC_THREADS) {
-      const int c4 = i % C4, x = (i / C4) % a.W, yl = i / (C4 * a.W);
+      const int ic = i / C4, c4 = i - C4 * ic, yl = fdiv(ic, a.dW), x = ic - yl * a.W;
       const float4 v = *reinterpret_cast<const float4*>(stage + (size_t)(yl * Wp + x + PC) * SS + 4 * c4);
       *reinterpret_cast<float4*>(a.gin + (((size_t)b * a.H + y0 + yl) * a.W + x) * NOUT + 4 * c4) = v;
     }
@@ -406,7 +407,7 @@ __global__ void __launch_bounds__(TC_THREADS, NM == 1 ? 3 : (NM == 2 ? 2 : 1)) c
     const int orows = POOL ? rows / 2 : rows, oy0 = POOL ? y0 / 2 : y0;
     const int items = orows * a.Wo * C4;
     for (int i = tid; i < items; i += TC_THREADS) {
-      const int c4 = i % C4, x = (i / C4) % a.Wo, yl = i / (C4 * a.Wo);
+      const int ic = i / C4, c4 = i - C4 * ic, yl = fdiv(ic, a.dWo), x = ic - yl * a.Wo;
       const int c = 4 * c4;
       float4 v;
       uchar4 cd;
@@ -532,6 +533,9 @@ int launch_tc(TcArgs a, const char* tag, cudaStream_t stream) {
   ADVB_CHECK(p.tiles > 0 && p.smem <= 227 * 1024, "tensor-core conv tile does not fit (image too wide)");
   a.R = p.R;
   a.band_rows = p.band_rows;
+  a.dWp = make_fastdiv(a.W + 2 * (KS / 2));
+  a.dW = make_fastdiv(a.W);
+  a.dWo = make_fastdiv(a.Wo);
   auto kern = conv_tc_kernel<KS, KTOT, NOUT, POOL, BWD, IM2COL, NM>;
   ADVB_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.smem));
   dim3 grid(p.tiles, a.B);

@@ -121,6 +121,21 @@ __device__ __forceinline__ bool elect_one() {
   return pred != 0;
 }
 
+// ---- division by a launch-time constant ------------------------------------------------------------------------
+// n / d as one multiply-high: m = ceil(2^32 / d) is exact whenever n * d < 2^32 (pixel and tile indices here are
+// < 2^17 and divisors < 2^16).  A runtime integer division costs ~25 SASS instructions; the fill and epilogue loops
+// of the convolution kernels were issue-bound on them (profiles/r01_ncu_full_persistent.md).
+struct FastDiv {
+  uint32_t d, m;
+};
+inline FastDiv make_fastdiv(int d) {
+  FastDiv f;
+  f.d = (uint32_t)d;
+  f.m = d > 1 ? (uint32_t)((0x100000000ull + (uint64_t)d - 1) / (uint64_t)d) : 0u;
+  return f;
+}
+__device__ __forceinline__ int fdiv(int n, const FastDiv& f) { return f.d > 1 ? (int)__umulhi((uint32_t)n, f.m) : n; }
+
 // ---- 3xTF32 split -------------------------------------------------------------------------------------------
 // x = hi + lo exactly, hi = round-to-nearest tf32(x).  The tensor core then computes
 // hi_a*hi_b + hi_a*lo_b + lo_a*hi_b with fp32 accumulation: products carry ~2^-22 relative error, i.e. fp32-class

@@ -35,7 +35,18 @@ EPS = 0.001
 PGD_STEPS = 40
 ALPHA = 2 / 255
 A_LCNN_BYTES_PER_CLIP = 40 * 15_818_544 + 768_000  # 633.5 MB per PGD-40 clip
+A_SPECRNET_BYTES_PER_CLIP = 40 * 18_624_736 + 768_000  # SURVEY.md App. D (SpecRNet+MFCC): 745.8 MB per PGD-40 clip
 METRIC = "adversarial clips/sec (PGD-40, 64k-sample audio)"
+WORKLOADS = {
+    # BASELINE.json configs[1] (the config the metric is quoted on) and configs[2]
+    "lcnn": dict(model="lcnn", frontend="lfcc", batch=128, bytes_per_clip=A_LCNN_BYTES_PER_CLIP, bias="m_output_act.bias",
+                 text="PGD-40 Linf eps=0.001 alpha=2/255 random_start on LCNN+LFCC, 64000-sample clips "
+                      "(BASELINE.json configs[1])"),
+    "specrnet": dict(model="specrnet", frontend="mfcc", batch=256, bytes_per_clip=A_SPECRNET_BYTES_PER_CLIP,
+                     bias="fc2_gru.bias",
+                     text="PGD-40 Linf eps=0.001 alpha=2/255 random_start on SpecRNet+MFCC, 64000-sample clips "
+                          "(BASELINE.json configs[2])"),
+}
 
 
 def measured_peaks():
@@ -55,10 +66,10 @@ def synthetic_batch(batch, seed):
     return (raw - mn) / (mx - mn), y
 
 
-def build_lcnn_state():
+def build_lcnn_state(model="lcnn", frontend="lfcc"):
     from oracle import cases  # seeded init shared with the tests (weights only; no oracle arithmetic)
 
-    holder = cases.build_holder("lcnn", "lfcc", seed=42)
+    holder = cases.build_holder(model, frontend, seed=42)
     from oracle import synth
 
     state = synth.randomize_norm_stats({k: v.detach().cpu().clone() for k, v in holder.state_dict().items()})
@@ -119,6 +130,17 @@ def kernel_bytes(B, F, T):
         out[f"conv_bwd_b{i}"] = B * per_clip
         H, W = Ho, Wo
     out["conv0_bwd_gemm"] = out.pop("conv_bwd_b0")  # the (F,80,5) col2im scratch is an implementation artefact
+    # SpecRNet blocks (csrc/specrnet.cu): conv1 reads x writes h; conv2 reads h, x writes xb + 2-bit code; backward
+    # kernels read the stage gradient / codes / h and write the gradient of their input
+    H, W, ci = F, 80, 1
+    for name, c in (("sr_b0", 24), ("sr_b2", 64), ("sr_b4", 64)):
+        hw, hb = H * W, (H // 2) * (W // 2)
+        hn = (H // 4) * (W // 4)
+        out[name + "_conv1"] = B * 4 * (hw * ci + hw * c)
+        out[name + "_conv2"] = B * (4 * (hw * c + hw * ci) + hb * c * 4.25)
+        out[name + "_conv2_bwd"] = B * (hn * c * 4.25 + hb * c * 0.25 + 4 * hw * c + 4 * hw * c)
+        out[name + "_conv1_bwd"] = B * 4 * (hw * c + hw * ci)
+        H, W, ci = H // 4, W // 4, c
     out["fe_power_db"] = B * 4 * (T + F * 128)
     out["fe_floor_dct"] = B * 4 * (F * 128 + F * 80)
     out["fe_bwd"] = B * 4 * (T + F * 80 + T)        # waveform (STFT recompute) + d coefficients in, d waveform out
@@ -185,8 +207,9 @@ def run_native(args):
     from advb200 import torchattacks as ta
     from advb200 import engine
 
-    B = args.batch
-    holder, state = build_lcnn_state()
+    wl = WORKLOADS[args.workload]
+    B = args.batch or wl["batch"]
+    holder, state = build_lcnn_state(wl["model"], wl["frontend"])
     holder.load_state_dict(state)
     holder = holder.to(dev)
     atk = ta.PGD(holder, eps=EPS, alpha=ALPHA, steps=PGD_STEPS, random_start=True)
@@ -200,7 +223,7 @@ def run_native(args):
     flush = torch.empty(256 * 2**20 // 4, device=dev)  # 256 MiB > 126 MB L2
     eng = engine.engine_for(holder, B, T_SAMPLES)
     with torch.no_grad():  # calibrated synthetic checkpoint: clean logits straddle 0 so labels can flip
-        holder.m_output_act.bias -= eng.forward(x_dev).median()
+        dict(holder.named_parameters())[wl["bias"]] -= eng.forward(x_dev).median()
 
     def barrier():
         torch.cuda.synchronize(dev)
@@ -239,20 +262,15 @@ def run_native(args):
     barrier()
     ms_e2e = t0.elapsed_time(t1)
 
-    tmax = torch.tensor([ms, ms_e2e], device=dev, dtype=torch.float64)
-    if world > 1:
-        dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
-    ms, ms_e2e = tmax.tolist()
+    from advb200 import shard
+
+    ms, ms_e2e = shard.max_over_ranks(ms, dev), shard.max_over_ranks(ms_e2e, dev)  # slowest rank
 
     # ---- attack outcome (labels of the attacked batch), gathered over NCCL --------------------------------------
     logits_clean = eng.forward(x_dev).flatten()
     logits_adv = eng.forward(adv).flatten()
     pred = torch.stack([(logits_clean > 0).long(), (logits_adv > 0).long(), y_dev], dim=1)
-    if world > 1:
-        parts = [torch.empty_like(pred) for _ in range(world)]
-        dist.all_gather(parts, pred)
-        pred = torch.cat(parts)
-    pred = pred.cpu()
+    pred = shard.gather_rows(pred, world * B).cpu()  # NCCL all_gather: the only collective of the job
     linf = (adv - x_dev).abs().max().item()
 
     out = None
@@ -280,8 +298,7 @@ def run_native(args):
             "metric": METRIC, "value": value, "unit": "clips/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": "PGD-40 Linf eps=0.001 alpha=2/255 random_start on LCNN+LFCC, 64000-sample clips "
-                                   "(BASELINE.json configs[1])",
+            "config": {"workload": wl["text"],
                        "batch_per_gpu": B, "global_batch": world * B, "parallelism": f"clip-shard x{world}",
                        "l2": "256 MiB flush buffer written between timed calls; per-call working set "
                              f"{eng.workspace_bytes / 2**30:.2f} GiB >> 126 MB L2",
@@ -296,15 +313,15 @@ def run_native(args):
                          "peak_source": peak_kind, "avg_launch_ms": avg_ms,
                          "share_of_step": top["total_ms"] / total_prof,
                          "algorithmic_bytes_per_launch": alg},
-            "path_roofline": {"bound": "hbm", "achieved": value / world * A_LCNN_BYTES_PER_CLIP / 1e9, "peak": peak,
-                              "unit": "GB/s", "frac": value / world * A_LCNN_BYTES_PER_CLIP / 1e9 / peak,
-                              "bytes_per_clip": A_LCNN_BYTES_PER_CLIP},
+            "path_roofline": {"bound": "hbm", "achieved": value / world * wl["bytes_per_clip"] / 1e9, "peak": peak,
+                              "unit": "GB/s", "frac": value / world * wl["bytes_per_clip"] / 1e9 / peak,
+                              "bytes_per_clip": wl["bytes_per_clip"]},
             "kernel_times_ms": {r["name"]: round(r["total_ms"], 3) for r in prof[:12]},
             "attack": {"linf": linf, "clean_acc": float((pred[:, 0] == pred[:, 2]).float().mean()),
                        "adv_acc": float((pred[:, 1] == pred[:, 2]).float().mean()),
                        "flipped": int((pred[:, 0] != pred[:, 1]).sum()), "clips": int(pred.shape[0])},
         }
-        if world == 1 and not args.no_cpu_baseline:
+        if world == 1 and not args.no_cpu_baseline and args.workload == "lcnn":
             v, dt, cores = cpu_port_clips_per_s(16, 10)
             out["cpu_baseline"] = {"value": v, "unit": "clips/s", "cores": cores, "kind": "port",
                                    "sample": f"oracle port, PGD-10 of the PGD-40 workload on 16 clips ({dt:.1f} s), time x4"}
@@ -321,7 +338,9 @@ def main():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="native", choices=["native", "reference"])
-    ap.add_argument("--batch", type=int, default=128)
+    ap.add_argument("--batch", type=int, default=0, help="clips per GPU (default: the workload's BASELINE.json batch)")
+    ap.add_argument("--workload", default="lcnn", choices=sorted(WORKLOADS),
+                    help="lcnn = BASELINE.json configs[1] (the headline), specrnet = configs[2]")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--kernel-times", default=None, help="write the full per-kernel timing table of one call (JSON)")
     args = ap.parse_args()
