@@ -584,6 +584,7 @@ bool conv_tc_supported(int Cin, int Cout, int KS, bool pool) {
 int conv_tc_forward(const ConvFwdArgs& f, const unsigned char* wpack, int passes, cudaStream_t stream) {
   ADVB_CHECK(f.in_pad == f.KS / 2, "tensor-core conv needs the input border to equal the conv padding");
   if (conv_light_supported(f.Cin, f.Cout, f.KS, f.pool, false)) return conv_light_forward(f, wpack, passes, stream);
+  if (conv_p3_supported(f.Cin, f.Cout, f.KS, f.pool, f.W)) return conv_p3_forward(f, wpack, passes, stream);
   TcArgs a{};
   if (f.KS == 5) {  // first block: contraction over the 25 taps (padded to 32), pixel grid without border
     ADVB_CHECK(f.Cin == 1 && f.Cout == 64 && f.pool, "5x5 tensor-core conv is the LCNN first block only");
@@ -649,6 +650,7 @@ int conv0_tc_backward(const float* gout, const unsigned char* codes, const unsig
 
 int conv_tc_backward(const ConvBwdArgs& g, const unsigned char* wpack, int passes, cudaStream_t stream) {
   if (conv_light_supported(g.Cin, g.Cout, g.KS, g.pool, true)) return conv_light_backward(g, wpack, passes, stream);
+  if (conv_p3_supported(g.Cin, g.Cout, g.KS, g.pool, g.W)) return conv_p3_backward(g, wpack, passes, stream);
   TcArgs a{};
   a.B = g.B, a.H = g.H, a.W = g.W, a.Ho = g.Ho, a.Wo = g.Wo;
   a.wpack = wpack;
