@@ -65,5 +65,8 @@ int conv0_light_backward_gemm(const float* gout, const unsigned char* codes, con
 bool conv_p3_supported(int Cin, int Cout, int KS, bool pool, int W);
 int conv_p3_forward(const ConvFwdArgs& a, const unsigned char* wpack, int passes, cudaStream_t stream);
 int conv_p3_backward(const ConvBwdArgs& a, const unsigned char* wpack, int passes, cudaStream_t stream);
+// "horizontal scatter" backward (N = 3 C_in): needs its own weight image in the layer's backward pack buffer
+bool conv_p3_bwd_hs(int Cin, int Cout, int KS, bool pool, int W);
+int conv_p3_pack_hs(const float* w, unsigned char* wd, int Cout, int Cin, cudaStream_t stream);
 
 }  // namespace advb

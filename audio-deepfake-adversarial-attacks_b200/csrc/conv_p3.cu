@@ -24,10 +24,12 @@ namespace {
 
 using namespace tc;
 
-constexpr int PW = 256;            // worker threads
-constexpr int PT = PW + 64;        // + MMA warp + weight warp
-constexpr int NM3 = 2;             // M-tiles (128 pixels) per tile
-constexpr int NI_MAX = 11;         // prefetch items per worker thread: ceil((2*128 + 2*(42+1)) * 8 / 256)
+// worker threads per CTA: 8 warps forward, 16 warps backward (the backward band fill - un-pool / un-MFM / BN scale per
+// element - is instruction-heavy; with 8 workers it, not the MMAs, set the pace); + 1 MMA warp + 1 weight warp
+// M-tiles (128 pixels) per tile and band buffering are chosen per direction:
+//   forward  : 2 M-tiles (pooled layers need an even number of image rows per tile), one band buffer;
+//   backward : 1 M-tile and TWO band buffers, so the convert of unit u+1 overlaps the MMAs of unit u (3-4 chunks per
+//              tile and N = 32/48 operand-read-bound MMAs made the single-buffer version convert-then-multiply serial).
 
 __host__ __device__ constexpr int p3_pow2(int v) {
   int p = 32;
@@ -53,17 +55,33 @@ struct P3Args {
   FastDiv dTiles, dWp, dW, dWo;
 };
 
-template <int KTOT, int NOUT, bool POOL, bool BWD>
+// HS ("horizontal scatter", backward only): the MMA computes Z[q][dx][ci] = sum_dy sum_co g[q + (dy-1) Wp][co] Wt[dy][dx][co][ci]
+// with N = 3 C_in (one MMA per vertical tap instead of nine per 3x3 tap) and the epilogue gathers
+// gin[q][ci] = sum_dx Z[q + dx - 1][dx][ci].  The plain backward has N = C_in = 32 / 48, and tcgen05.mma costs ~64 cycles
+// per M=128, K=8 instruction however small N is (measured: block 2 backward ran at exactly that issue floor whatever the
+// schedule), so 3x fewer, 3x wider MMAs cut its tensor time 3x.
+template <int KTOT, int NOUT, bool POOL, bool BWD, bool HS>
 struct P3Cfg {
+  static_assert(!HS || BWD, "horizontal scatter is a backward formulation");
+  static constexpr int PW = 256;
+  static constexpr int PT = PW + 64;
+  static constexpr int NM3 = BWD ? 1 : 2;
+  static constexpr int NTAP = HS ? 3 : 9;
+  static constexpr int NMMA = HS ? 3 * NOUT : NOUT;  // MMA N = accumulator columns per M-tile
+  static constexpr int BR = (NM3 * 128 + 2 * (42 + 1) + 7) & ~7;  // band rows per buffer (widest layer: W = 40)
+  static constexpr int NI_MAX = (BR * 8 + PW - 1) / PW;            // prefetch items per worker thread
   static constexpr int NKC = (KTOT + 31) / 32;
-  static constexpr int NSLICE = NKC * 9;
-  static constexpr int NSTRIDE = p3_pow2(NOUT);
+  static constexpr int NSLICE = NKC * NTAP;
+  static constexpr int NSTRIDE = p3_pow2(NMMA);
   static constexpr int TMEM_COLS = p3_pow2(2 * NM3 * NSTRIDE);
-  static constexpr int SLICE_BYTES = 2 * NOUT * 128;
-  static constexpr int CS = BWD ? NOUT : NOUT / 2;
+  static constexpr int SLICE_BYTES = 2 * NMMA * 128;
+  static constexpr int CS = BWD ? NMMA : NOUT / 2;  // staged floats per pixel
   static constexpr int SS = CS + 4;
   static constexpr int STAGE_BYTES = NM3 * 128 * SS * 4 + NM3 * 128 * 8;
-  static constexpr int BAND_BYTES = 2 * 344 * 128;
+  static constexpr int BUF_BYTES = 2 * BR * 128;                    // hi rows then lo rows
+  // second band buffer (convert of unit u+1 overlaps the MMAs of unit u) wherever it fits beside staging + a 2-slice ring
+  static constexpr bool DB = BWD && (227 * 1024 - 1024 - 2 * BUF_BYTES - STAGE_BYTES >= 2 * SLICE_BYTES);
+  static constexpr int BAND_BYTES = (DB ? 2 : 1) * BUF_BYTES;
   static constexpr int ROOM = 227 * 1024 - 1024 - BAND_BYTES - STAGE_BYTES;
   static constexpr int NST = ROOM / SLICE_BYTES >= 4 ? 4 : (ROOM / SLICE_BYTES >= 3 ? 3 : 2);
   static constexpr size_t SMEM = (size_t)NST * SLICE_BYTES + BAND_BYTES + STAGE_BYTES + 1024;
@@ -71,20 +89,22 @@ struct P3Cfg {
   static_assert(ROOM / SLICE_BYTES >= 2, "weight ring does not fit");
 };
 
-template <int KTOT, int NOUT, bool POOL, bool BWD>
-__global__ void __launch_bounds__(PT, 1) conv_p3_kernel(P3Args a) {
-  using Cfg = P3Cfg<KTOT, NOUT, POOL, BWD>;
+template <int KTOT, int NOUT, bool POOL, bool BWD, bool HS>
+__global__ void __launch_bounds__(P3Cfg<KTOT, NOUT, POOL, BWD, HS>::PT, 1) conv_p3_kernel(P3Args a) {
+  using Cfg = P3Cfg<KTOT, NOUT, POOL, BWD, HS>;
+  constexpr int PW = Cfg::PW, PT = Cfg::PT;
   constexpr int NKC = Cfg::NKC, NSLICE = Cfg::NSLICE, NST = Cfg::NST, CS = Cfg::CS, SS = Cfg::SS;
-  constexpr uint32_t IDESC = idesc_tf32(128, NOUT);
+  constexpr int NM3 = Cfg::NM3, NI_MAX = Cfg::NI_MAX, BR = Cfg::BR, NTAP = Cfg::NTAP, NMMA = Cfg::NMMA;
+  constexpr bool DB = Cfg::DB;
+  constexpr uint32_t IDESC = idesc_tf32(128, Cfg::NMMA);
 
   extern __shared__ unsigned char smem_raw[];
   unsigned char* base = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  unsigned char* a_hi = base;
-  unsigned char* a_lo = a_hi + 344 * 128;
-  unsigned char* wring = a_lo + 344 * 128;  // 88 064 = 86 * 1024: stays 1024-byte aligned
+  unsigned char* band = base;                        // [buffer][hi BR x 128 B | lo BR x 128 B]
+  unsigned char* wring = band + Cfg::BAND_BYTES;     // BUF_BYTES is a multiple of 1024: stays 1024-byte aligned
   float* stage = reinterpret_cast<float*>(wring + (size_t)NST * Cfg::SLICE_BYTES);
   unsigned long long* flags = reinterpret_cast<unsigned long long*>(stage + (size_t)NM3 * 128 * SS);
-  __shared__ uint64_t bar_wfull[NST], bar_wempty[NST], bar_band_full, bar_unit_done;
+  __shared__ uint64_t bar_wfull[NST], bar_wempty[NST], bar_band_full, bar_unit_done[2];
   __shared__ uint32_t tmem_base_s;
   __shared__ float s_bias[BWD ? 1 : NOUT];
 
@@ -99,7 +119,8 @@ __global__ void __launch_bounds__(PT, 1) conv_p3_kernel(P3Args a) {
       mbar_init(&bar_wempty[s], 1);
     }
     mbar_init(&bar_band_full, PW / 32);
-    mbar_init(&bar_unit_done, 1);
+    mbar_init(&bar_unit_done[0], 1);
+    mbar_init(&bar_unit_done[1], 1);
     fence_barrier_init();
   }
   if (warp == 0) tmem_alloc<Cfg::TMEM_COLS>(&tmem_base_s);
@@ -137,7 +158,6 @@ __global__ void __launch_bounds__(PT, 1) conv_p3_kernel(P3Args a) {
   } else if (warp == PW / 32) {
     // ================= MMA warp =================
     const bool leader = elect_one();
-    const uint32_t a_hi_addr = smem_u32(a_hi), a_lo_addr = smem_u32(a_lo);
     int u_glob = 0, s_glob = 0, it = 0;
     for (int tile = blockIdx.x; tile < a.n_tiles; tile += gridDim.x, ++it) {
       int b, y0, rows, nM;
@@ -147,14 +167,16 @@ __global__ void __launch_bounds__(PT, 1) conv_p3_kernel(P3Args a) {
       for (int kc = 0; kc < NKC; ++kc, ++u_glob) {
         mbar_wait(&bar_band_full, (uint32_t)(u_glob & 1));
         tc_fence_after();
+        const uint32_t a_hi_addr = smem_u32(band + (DB ? (size_t)(u_glob & 1) * Cfg::BUF_BYTES : 0));
+        const uint32_t a_lo_addr = a_hi_addr + BR * 128;
         const int kvalid = (KTOT - 32 * kc) >= 32 ? 32 : (KTOT - 32 * kc);
 #pragma unroll 1
-        for (int tap = 0; tap < 9; ++tap, ++s_glob) {
+        for (int tap = 0; tap < NTAP; ++tap, ++s_glob) {
           const int slot = s_glob % NST;
           mbar_wait(&bar_wfull[slot], (uint32_t)((s_glob / NST) & 1));
           tc_fence_after();
-          const uint32_t w_hi = smem_u32(wring + (size_t)slot * Cfg::SLICE_BYTES), w_lo = w_hi + NOUT * 128;
-          const int dy = tap / 3, dx = tap - dy * 3;
+          const uint32_t w_hi = smem_u32(wring + (size_t)slot * Cfg::SLICE_BYTES), w_lo = w_hi + NMMA * 128;
+          const int dy = HS ? tap : tap / 3, dx = HS ? 1 : tap - dy * 3;  // HS: vertical taps only, centre column
           const uint32_t row_off = (uint32_t)(dy * Wp + dx) * 128u;
 #pragma unroll 1
           for (int ks = 0; ks < kvalid / 8; ++ks) {
@@ -177,13 +199,14 @@ __global__ void __launch_bounds__(PT, 1) conv_p3_kernel(P3Args a) {
           if (leader) mma_commit(&bar_wempty[slot]);  // slot free once these MMAs have read it
           __syncwarp();
         }
-        if (leader) mma_commit(&bar_unit_done);  // band free; after the last chunk the accumulator is complete
+        if (leader) mma_commit(&bar_unit_done[DB ? (u_glob & 1) : 0]);  // band buffer free; last chunk: accumulator complete
         __syncwarp();
       }
     }
   } else {
     // ================= worker warps =================
-    const int c4 = tid & 7, r0 = tid >> 3;  // channel group; first band row (rows r0 + 32 u)
+    const int c4 = tid & 7, r0 = tid >> 3;  // channel group; first band row (rows r0 + (PW / 8) u)
+    constexpr int RSTEP = PW / 8;
     float4 rv[NI_MAX];
     uchar4 rc[NI_MAX];
     unsigned rok = 0;  // bit u: item u is a real element (loads stay RAW in registers until convert)
@@ -203,7 +226,7 @@ __global__ void __launch_bounds__(PT, 1) conv_p3_kernel(P3Args a) {
         const int c = ch - half * Ch;
 #pragma unroll
         for (int u = 0; u < NI_MAX; ++u) {
-          const int r = r0 + 32 * u;
+          const int r = r0 + RSTEP * u;
           const int q = q_lo + r;
           bool ok = ch_ok && r < band_used && q >= 0 && q < npix;
           const int qq = ok ? q : 0;
@@ -221,7 +244,7 @@ __global__ void __launch_bounds__(PT, 1) conv_p3_kernel(P3Args a) {
         const float* inb = a.in + (size_t)b * npix * KTOT + ch;
 #pragma unroll
         for (int u = 0; u < NI_MAX; ++u) {
-          const int r = r0 + 32 * u;
+          const int r = r0 + RSTEP * u;
           const int q = q_lo + r;
           const bool ok = ch_ok && r < band_used && q >= 0 && q < npix;
           rv[u] = __ldg(reinterpret_cast<const float4*>(ok ? inb + (size_t)q * KTOT : a.in));
@@ -230,9 +253,11 @@ __global__ void __launch_bounds__(PT, 1) conv_p3_kernel(P3Args a) {
       }
     };
 
-    auto convert_store = [&](int tile, int kc) {
+    auto convert_store = [&](int tile, int kc, int bufsel) {
       int b, y0, rows, nM;
       tile_geom(tile, b, y0, rows, nM);
+      unsigned char* a_hi = band + (size_t)bufsel * Cfg::BUF_BYTES;
+      unsigned char* a_lo = a_hi + BR * 128;
       const int band_used = nM * 128 + 2 * (Wp + 1);
       float4 sc = make_float4(1.f, 1.f, 1.f, 1.f);
       if (BWD && a.bn_invstd != nullptr) {
@@ -242,7 +267,7 @@ __global__ void __launch_bounds__(PT, 1) conv_p3_kernel(P3Args a) {
       }
 #pragma unroll
       for (int u = 0; u < NI_MAX; ++u) {
-        const int r = r0 + 32 * u;
+        const int r = r0 + RSTEP * u;
         if (r < band_used) {
           float4 v;
           if (BWD) {
@@ -278,7 +303,7 @@ __global__ void __launch_bounds__(PT, 1) conv_p3_kernel(P3Args a) {
           float* srow = stage + (size_t)r * SS;
           if (BWD) {
 #pragma unroll 1
-            for (int c0 = 0; c0 < NOUT; c0 += 16) {
+            for (int c0 = 0; c0 < NMMA; c0 += 16) {
               uint32_t v[16];
               tmem_ld16_issue(taddr + c0, v);
               tmem_ld_wait();
@@ -316,10 +341,20 @@ __global__ void __launch_bounds__(PT, 1) conv_p3_kernel(P3Args a) {
       asm volatile("bar.sync 1, %0;" ::"n"(PW) : "memory");
       constexpr int C4 = CS / 4;
       if (BWD) {
-        const int items = rows * a.W * C4;
+        constexpr int O4 = NOUT / 4;  // float4 groups of the C_in output channels
+        const int items = rows * a.W * O4;
         for (int i = tid; i < items; i += PW) {
-          const int ic = i / C4, c4i = i - C4 * ic, yl = fdiv(ic, a.dW), x = ic - yl * a.W;
-          const float4 v = *reinterpret_cast<const float4*>(stage + (size_t)(yl * Wp + x + 1) * SS + 4 * c4i);
+          const int ic = i / O4, c4i = i - O4 * ic, yl = fdiv(ic, a.dW), x = ic - yl * a.W;
+          const float* sp = stage + (size_t)(yl * Wp + x + 1) * SS + 4 * c4i;
+          float4 v;
+          if (HS) {  // gin[q] = Z[q-1][dx=0] + Z[q][dx=1] + Z[q+1][dx=2]
+            const float4 z0 = *reinterpret_cast<const float4*>(sp - SS);
+            const float4 z1 = *reinterpret_cast<const float4*>(sp + NOUT);
+            const float4 z2 = *reinterpret_cast<const float4*>(sp + SS + 2 * NOUT);
+            v = make_float4(z0.x + z1.x + z2.x, z0.y + z1.y + z2.y, z0.z + z1.z + z2.z, z0.w + z1.w + z2.w);
+          } else {
+            v = *reinterpret_cast<const float4*>(sp);
+          }
           *reinterpret_cast<float4*>(a.gin + (((size_t)b * a.H + y0 + yl) * a.W + x) * NOUT + 4 * c4i) = v;
         }
       } else {
@@ -374,12 +409,16 @@ __global__ void __launch_bounds__(PT, 1) conv_p3_kernel(P3Args a) {
     // ---- persistent loop over units (tile, chunk) ----
     int tile = blockIdx.x, kc = 0, u_glob = 0, it = 0, prev_tile = -1;
     if (tile < a.n_tiles) issue_loads(tile, 0);
+    // unit u commits bar_unit_done[DB ? u & 1 : 0]; its k-th completion there has parity k & 1
+    auto wait_unit = [&](int u) {
+      if (DB) mbar_wait(&bar_unit_done[u & 1], (uint32_t)((u >> 1) & 1));
+      else mbar_wait(&bar_unit_done[0], (uint32_t)(u & 1));
+      tc_fence_after();
+    };
     while (tile < a.n_tiles) {
-      if (u_glob > 0) {  // MMAs of the previous unit have finished reading the band (and, at kc = 0, tile it-1 is complete)
-        mbar_wait(&bar_unit_done, (uint32_t)((u_glob - 1) & 1));
-        tc_fence_after();
-      }
-      convert_store(tile, kc);
+      // the band buffer this unit overwrites must have been read completely: unit u-1 (single buffer) / u-2 (double)
+      if (u_glob >= (DB ? 2 : 1)) wait_unit(u_glob - (DB ? 2 : 1));
+      convert_store(tile, kc, DB ? (u_glob & 1) : 0);
       fence_proxy_async();
       tc_fence_before();
       __syncwarp();
@@ -391,7 +430,10 @@ __global__ void __launch_bounds__(PT, 1) conv_p3_kernel(P3Args a) {
         ntile = tile + gridDim.x;
       }
       if (ntile < a.n_tiles) issue_loads(ntile, nkc);
-      if (kc == 0 && it > 0) epilogue(prev_tile, (it - 1) & 1);  // overlaps the MMAs of this tile
+      if (kc == 0 && it > 0) {  // overlaps the MMAs of this tile
+        if (DB) wait_unit(u_glob - 1);  // last chunk of the previous tile (already awaited when single-buffered)
+        epilogue(prev_tile, (it - 1) & 1);
+      }
       if (nkc == 0) {
         prev_tile = tile;
         ++it;
@@ -401,8 +443,7 @@ __global__ void __launch_bounds__(PT, 1) conv_p3_kernel(P3Args a) {
       ++u_glob;
     }
     if (it > 0) {
-      mbar_wait(&bar_unit_done, (uint32_t)((u_glob - 1) & 1));
-      tc_fence_after();
+      wait_unit(u_glob - 1);
       epilogue(prev_tile, (it - 1) & 1);
     }
   }
@@ -419,12 +460,13 @@ int tune_p3() {
   return v;
 }
 
-template <int KTOT, int NOUT, bool POOL, bool BWD>
+template <int KTOT, int NOUT, bool POOL, bool BWD, bool HS = false>
 int launch_p3(P3Args a, const char* tag, cudaStream_t stream) {
-  using Cfg = P3Cfg<KTOT, NOUT, POOL, BWD>;
+  using Cfg = P3Cfg<KTOT, NOUT, POOL, BWD, HS>;
   const int Wp = a.W + 2;
   const int Heff = (!BWD && POOL) ? 2 * a.Ho : a.H;
   const bool even = !BWD && POOL;
+  constexpr int NM3 = Cfg::NM3;
   int Rmax = (NM3 * 128) / Wp;
   if (even) Rmax &= ~1;
   ADVB_CHECK(Rmax >= (even ? 2 : 1) && Wp <= 42, "persistent 3x3 conv: image too wide for the tile");
@@ -440,19 +482,58 @@ int launch_p3(P3Args a, const char* tag, cudaStream_t stream) {
   a.dWp = make_fastdiv(Wp);
   a.dW = make_fastdiv(a.W);
   a.dWo = make_fastdiv(a.Wo);
-  ADVB_CHECK((cdiv(R * Wp, 128) * 128 + 2 * (Wp + 1)) * 8 <= NI_MAX * PW, "persistent 3x3 conv: band exceeds the prefetch registers");
-  auto kern = conv_p3_kernel<KTOT, NOUT, POOL, BWD>;
+  ADVB_CHECK(cdiv(R * Wp, 128) * 128 + 2 * (Wp + 1) <= Cfg::BR, "persistent 3x3 conv: band exceeds its buffer");
+  auto kern = conv_p3_kernel<KTOT, NOUT, POOL, BWD, HS>;
   ADVB_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::SMEM));
   int n_sm = 148, dev = 0;
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev);
   const int grid = a.n_tiles < n_sm ? a.n_tiles : n_sm;
-  kern<<<grid, PT, Cfg::SMEM, stream>>>(a);
+  kern<<<grid, Cfg::PT, Cfg::SMEM, stream>>>(a);
   ADVB_KERNEL_OK(tag, stream);
   return 0;
 }
 
+// HS weight slices in consumption order [chunk kc][dy]: K-major SWIZZLE_128B matrix [3 C_in rows][32 k], hi image then
+// lo image; row n = dx * C_in + ci, column k <-> co = 32 kc + k; value = W[co][ci][2 - dy][2 - dx] (transposed conv).
+__global__ void pack_hs_kernel(const float* __restrict__ w, unsigned char* __restrict__ dst, int Cout, int Cin) {
+  const int N = 3 * Cin, NKC = (Cout + 31) / 32;
+  const int total = NKC * 3 * N * 32;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+    const int k = i & 31, n = (i >> 5) % N, sl = i / (32 * N);
+    const int dy = sl % 3, kc = sl / 3;
+    const int dx = n / Cin, ci = n - dx * Cin, co = 32 * kc + k;
+    float v = 0.f;
+    if (co < Cout) v = w[((size_t)co * Cin + ci) * 9 + (2 - dy) * 3 + (2 - dx)];
+    float hi, lo;
+    tc::split_tf32(v, hi, lo);
+    const size_t slice = (size_t)sl * 2 * N * 128;
+    const uint32_t off = (uint32_t)(n * 128 + ((((k >> 2) ^ (n & 7)) << 4) | ((k & 3) << 2)));
+    *reinterpret_cast<float*>(dst + slice + off) = hi;
+    *reinterpret_cast<float*>(dst + slice + (size_t)N * 128 + off) = lo;
+  }
+}
+
+int tune_hs() {
+  static const int v = [] {
+    const char* e = getenv("ADVB_P3_HS");
+    return e != nullptr ? atoi(e) : 1;
+  }();
+  return v;
+}
+
 }  // namespace
+
+bool conv_p3_bwd_hs(int Cin, int Cout, int KS, bool pool, int W) {
+  return tune_hs() != 0 && conv_p3_supported(Cin, Cout, KS, pool, W) && pool && Cin <= 48;
+}
+
+int conv_p3_pack_hs(const float* w, unsigned char* wd, int Cout, int Cin, cudaStream_t stream) {
+  const int n = ((Cout + 31) / 32) * 3 * 3 * Cin * 32;
+  pack_hs_kernel<<<cdiv(n, 256), 256, 0, stream>>>(w, wd, Cout, Cin);
+  ADVB_KERNEL_OK("pack_tc_bwd_hs", stream);
+  return 0;
+}
 
 bool conv_p3_supported(int Cin, int Cout, int KS, bool pool, int W) {
   if (tune_p3() == 0 || KS != 3 || W > 40) return false;
@@ -482,6 +563,11 @@ int conv_p3_backward(const ConvBwdArgs& g, const unsigned char* wpack, int passe
   a.wpack = wpack;
   a.gout = g.gout, a.codes_in = g.codes, a.gin = g.gin, a.bn_invstd = g.bn_invstd;
   a.passes = passes;
+  if (conv_p3_bwd_hs(g.Cin, g.Cout, g.KS, g.pool, g.W)) {  // wpack is then in the HS layout (conv_p3_pack_hs)
+    if (g.Cin == 32 && g.Cout == 96) return launch_p3<96, 32, true, true, true>(a, g.tag, stream);
+    if (g.Cin == 48 && g.Cout == 128) return launch_p3<128, 48, true, true, true>(a, g.tag, stream);
+    if (g.Cin == 32 && g.Cout == 64) return launch_p3<64, 32, true, true, true>(a, g.tag, stream);
+  }
   if (g.Cin == 32 && g.Cout == 96 && g.pool) return launch_p3<96, 32, true, true>(a, g.tag, stream);
   if (g.Cin == 48 && g.Cout == 128 && g.pool) return launch_p3<128, 48, true, true>(a, g.tag, stream);
   if (g.Cin == 32 && g.Cout == 64 && g.pool) return launch_p3<64, 32, true, true>(a, g.tag, stream);

@@ -295,8 +295,11 @@ int prepare_lcnn(advb_handle* h, cudaStream_t st) {
   for (int i = 0; i < 9; ++i) {
     LcnnBlock& k = h->blk[i];
     const std::string p = "m_transform." + std::to_string(k.idx);
-    if (k.tc && h->conv_path == 0)
+    if (k.tc && h->conv_path == 0) {
       ADVB_TRY(conv_tc_pack(h->t(p + ".weight"), k.tcf, k.tcd, k.Cout, k.Cin, k.KS, st));
+      if (conv_p3_bwd_hs(k.Cin, k.Cout, k.KS, k.pool, k.W))  // same bytes, horizontal-scatter layout
+        ADVB_TRY(conv_p3_pack_hs(h->t(p + ".weight"), k.tcd, k.Cout, k.Cin, st));
+    }
     if (!(k.tc && h->conv_path == 0))
       ADVB_TRY(conv_pack_weights(h->t(p + ".weight"), k.wf, k.wd, k.Cout, k.Cin, k.KS, st));
     if (k.bn_idx >= 0)
