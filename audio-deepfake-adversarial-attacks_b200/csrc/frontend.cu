@@ -285,47 +285,53 @@ __device__ __forceinline__ void decode_gmax(unsigned long long packed, float& vm
 __global__ void __launch_bounds__(256) fe_floor_dct_kernel(const float* __restrict__ dB, int F, FrontendTables tb,
                                                             FrontendState st, float top_db, float* __restrict__ out,
                                                             long long clip_stride, long long stride_f,
-                                                            long long stride_c, long long offset) {
+                                                            long long stride_c, long long offset, int n_blocks,
+                                                            int n_clips) {
   extern __shared__ float smem[];
   float* s_dct = smem;                     // 128*80
   float* s_d = s_dct + NFILT * NCOEF;      // 16*128
   const int tid = threadIdx.x;
-  const int b = blockIdx.y, f0 = blockIdx.x * 16;
   float vmax;
   unsigned amax_idx;
   decode_gmax(*st.gmax_packed, vmax, amax_idx);
   const float floor_v = vmax - top_db;
-  for (int i = tid; i < NFILT * NCOEF; i += 256) s_dct[i] = tb.dct[i];
-  int clamped = 0;
-  for (int i = tid; i < 16 * NFILT; i += 256) {
-    const int f = f0 + i / NFILT;
-    float d = 0.f;
-    if (f < F) {
-      d = dB[((size_t)b * F + f) * NFILT + (i % NFILT)];
-      if (d < floor_v) {
-        d = floor_v;
-        ++clamped;
+  for (int i = tid; i < NFILT * NCOEF; i += 256) s_dct[i] = tb.dct[i];  // staged once per (persistent) CTA
+  int clamped_any = 0;
+  for (int work = blockIdx.x; work < n_blocks * n_clips; work += gridDim.x) {
+    const int b = work / n_blocks, f0 = (work - b * n_blocks) * 16;
+    __syncthreads();  // previous iteration's reads of s_d are done (and s_dct is complete on the first pass)
+    int clamped = 0;
+    for (int i = tid; i < 16 * NFILT; i += 256) {
+      const int f = f0 + i / NFILT;
+      float d = 0.f;
+      if (f < F) {
+        d = dB[((size_t)b * F + f) * NFILT + (i % NFILT)];
+        if (d < floor_v) {
+          d = floor_v;
+          ++clamped;
+        }
       }
+      s_d[i] = d;
     }
-    s_d[i] = d;
-  }
-  const int total = __syncthreads_count(clamped);  // counts threads with clamped != 0 (enough for an "active" flag)
-  if (tid == 0 && total > 0) atomicAdd(st.n_clamped, total);
+    clamped_any += __syncthreads_count(clamped);  // threads that clamped something (enough for an "active" flag)
 
-  const int fl = tid >> 4, cg = tid & 15, f = f0 + fl;
-  if (f >= F) return;
-  float acc[5] = {0.f, 0.f, 0.f, 0.f, 0.f};
-  const float* drow = s_d + fl * NFILT;
+    const int fl = tid >> 4, cg = tid & 15, f = f0 + fl;
+    if (f < F) {
+      float acc[5] = {0.f, 0.f, 0.f, 0.f, 0.f};
+      const float* drow = s_d + fl * NFILT;
 #pragma unroll 4
-  for (int m = 0; m < NFILT; ++m) {
-    const float d = drow[m];
-    const float* w = s_dct + m * NCOEF + cg;
+      for (int m = 0; m < NFILT; ++m) {
+        const float d = drow[m];
+        const float* w = s_dct + m * NCOEF + cg;
 #pragma unroll
-    for (int i = 0; i < 5; ++i) acc[i] += d * w[16 * i];
+        for (int i = 0; i < 5; ++i) acc[i] += d * w[16 * i];
+      }
+      float* o = out + (size_t)b * clip_stride + offset + (long long)f * stride_f;
+#pragma unroll
+      for (int i = 0; i < 5; ++i) o[(long long)(cg + 16 * i) * stride_c] = acc[i];
+    }
   }
-  float* o = out + (size_t)b * clip_stride + offset + (long long)f * stride_f;
-#pragma unroll
-  for (int i = 0; i < 5; ++i) o[(long long)(cg + 16 * i) * stride_c] = acc[i];
+  if (tid == 0 && clamped_any > 0) atomicAdd(st.n_clamped, clamped_any);
 }
 
 // ---------------------------------------------------------------------------------------------------
@@ -399,7 +405,7 @@ __global__ void __launch_bounds__(FB_THREADS) fe_bwd_kernel(const float* __restr
                                                              FrontendTables tb, FrontendState st, float top_db,
                                                              const float* __restrict__ gcoef, long long g_clip_stride,
                                                              long long g_stride_f, long long g_stride_c,
-                                                             float* __restrict__ gx, int n_tiles) {
+                                                             float* __restrict__ gx, int n_tiles, int n_clips) {
   extern __shared__ __align__(16) float smem[];
   float2* s_tw = reinterpret_cast<float2*>(smem);                  // 512 float2
   float* s_win = smem + 1024;                                      // 400
@@ -415,7 +421,16 @@ __global__ void __launch_bounds__(FB_THREADS) fe_bwd_kernel(const float* __restr
   for (int i = tid; i < NFILT * NCOEF; i += FB_THREADS) s_dct[(i / NCOEF) * DCT_LD + (i % NCOEF)] = tb.dct[i];
   __syncthreads();
 
-  const int b = blockIdx.y, tile = blockIdx.x;
+  float vmax;
+  unsigned amax_idx;
+  decode_gmax(*st.gmax_packed, vmax, amax_idx);
+  const float floor_v = vmax - top_db;
+  const float mass_total = *st.mass_total;
+
+  // persistent over (clip, tile): the 47 KB of tables above are staged once per CTA instead of once per tile (the
+  // prologue was 18 % of the kernel's samples when every tile was its own CTA)
+  for (int work = blockIdx.x; work < n_tiles * n_clips; work += gridDim.x) {
+  const int b = work / n_tiles, tile = work - b * n_tiles;
   const int s0 = tile * TILE_S;
   const int s1 = min(T, s0 + TILE_S);
   // frames whose (reflected) support can touch [s0, s1)
@@ -425,12 +440,6 @@ __global__ void __launch_bounds__(FB_THREADS) fe_bwd_kernel(const float* __restr
   if (s1 >= T - 202) t_hi = F - 1;
   if (t_hi > F - 1) t_hi = F - 1;
   const int nf = t_hi - t_lo + 1;  // host guarantees nf <= NF_MAX
-
-  float vmax;
-  unsigned amax_idx;
-  decode_gmax(*st.gmax_packed, vmax, amax_idx);
-  const float floor_v = vmax - top_db;
-  const float mass_total = *st.mass_total;
   const float* xb = x + (size_t)b * T;
 
   float2* bufA = s_fft + warp * (FFT_A + FFT_B);
@@ -560,6 +569,8 @@ __global__ void __launch_bounds__(FB_THREADS) fe_bwd_kernel(const float* __restr
     }
     gx[(size_t)b * T + s] = acc;
   }
+  __syncthreads();  // s_yw is reused by the next tile
+  }
 }
 
 size_t fe_fwd_smem() { return (size_t)(1024 + 400 + FE_WARPS * 2 * (FFT_A + FFT_B) + FE_WARPS * 2 * PSTRIDE) * sizeof(float); }
@@ -600,9 +611,10 @@ int frontend_forward(const FrontendTables& tb, const FrontendState& st, const fl
   dim3 g1(cdiv(F, 2 * FE_WARPS), B);
   fe_power_db_kernel<<<g1, FE_THREADS, fe_fwd_smem(), stream>>>(x, T, F, tb, st, dB);
   ADVB_KERNEL_OK("fe_power_db", stream);
-  dim3 g2(cdiv(F, 16), B);
+  const int n_blocks = cdiv(F, 16);
+  const int g2 = n_blocks * B < 148 * 4 ? n_blocks * B : 148 * 4;  // persistent: 48 KB of shared memory -> 4 CTAs / SM
   fe_floor_dct_kernel<<<g2, 256, fe_dct_smem(), stream>>>(dB, F, tb, st, 80.0f, out, clip_stride, stride_f, stride_c,
-                                                         offset);
+                                                         offset, n_blocks, B);
   ADVB_KERNEL_OK("fe_floor_dct", stream);
   return 0;
 }
@@ -618,9 +630,9 @@ int frontend_backward(const FrontendTables& tb, const FrontendState& st, const f
   fe_mass_reduce_kernel<<<1, 1024, 0, stream>>>(mass_partial, (int)(g1.x * g1.y), st);
   ADVB_KERNEL_OK("fe_mass_reduce", stream);
   const int n_tiles = cdiv(T, TILE_S);
-  dim3 g2(n_tiles, B);
-  fe_bwd_kernel<<<g2, FB_THREADS, fe_bwd_smem(), stream>>>(x, T, F, tb, st, 80.0f, gcoef, g_clip_stride, g_stride_f,
-                                                          g_stride_c, gx, n_tiles);
+  const int grid = n_tiles * B < 148 ? n_tiles * B : 148;  // one persistent CTA per SM (211 KB of shared memory each)
+  fe_bwd_kernel<<<grid, FB_THREADS, fe_bwd_smem(), stream>>>(x, T, F, tb, st, 80.0f, gcoef, g_clip_stride, g_stride_f,
+                                                           g_stride_c, gx, n_tiles, B);
   ADVB_KERNEL_OK("fe_bwd", stream);
   return 0;
 }

@@ -731,15 +731,26 @@ int sr_input_forward(float* img, const float* bn4, int B, int H, int W, cudaStre
   return 0;
 }
 
+// profiler labels must outlive the call (prof_mark keeps the pointer): string literals per block
+struct SrTags {
+  const char *conv1, *conv2, *conv2_bwd, *conv1_bwd;
+};
+const SrTags& sr_tags(const char* tag) {
+  static const SrTags t0{"sr_b0_conv1", "sr_b0_conv2", "sr_b0_conv2_bwd", "sr_b0_conv1_bwd"};
+  static const SrTags t2{"sr_b2_conv1", "sr_b2_conv2", "sr_b2_conv2_bwd", "sr_b2_conv1_bwd"};
+  static const SrTags t4{"sr_b4_conv1", "sr_b4_conv2", "sr_b4_conv2_bwd", "sr_b4_conv1_bwd"};
+  return tag[4] == '0' ? t0 : (tag[4] == '2' ? t2 : t4);
+}
+
 int sr_block_forward(const SrBlock& k, const float* x, int B, const char* tag, cudaStream_t stream) {
-  const std::string t(tag);
+  const SrTags& t = sr_tags(tag);
   SrArgs a = base_args(k, B);
   a.CK = k.Ci, a.N = k.C;
   a.in = x, a.wpk = k.w1f, a.bias = k.b1p, a.out = k.h;
-  ADVB_TRY(launch_conv<F1>(a, false, (t + "_conv1").c_str(), stream));
+  ADVB_TRY(launch_conv<F1>(a, false, t.conv1, stream));
   a.CK = k.C, a.in = k.h, a.wpk = k.w2f, a.bias = k.b2p, a.out = k.xb;
   a.x = x, a.Ci = k.Ci, a.wd = k.downsample ? k.wdf : nullptr, a.bd = k.bdp, a.code1w = k.code1, a.psum = k.psum;
-  ADVB_TRY(launch_conv<F2>(a, true, (t + "_conv2").c_str(), stream));
+  ADVB_TRY(launch_conv<F2>(a, true, t.conv2, stream));
   sr_attention_fwd_kernel<<<B, 64, 0, stream>>>(k.psum, k.n_tiles, k.att_w, k.att_b, k.y, k.C, k.Cout,
                                                1.0f / (float)(k.Hb * k.Wb));
   ADVB_KERNEL_OK("sr_attention", stream);
@@ -752,23 +763,23 @@ int sr_block_forward(const SrBlock& k, const float* x, int B, const char* tag, c
 
 int sr_block_backward(const SrBlock& k, const float* x, float* g_x, int B, bool first, const float* bn4, const char* tag,
                       cudaStream_t stream) {
-  const std::string t(tag);
+  const SrTags& t = sr_tags(tag);
   const int threads = (256 / k.C) * k.C;
   sr_attention_bwd_kernel<<<B, threads, 0, stream>>>(k.g_xn, k.code2, k.xb, k.y, k.att_w, k.gadd, k.Hb, k.Wb, k.Hn, k.Wn,
                                                     k.C, k.Cout, 1.0f / (float)(k.Hb * k.Wb));
   ADVB_KERNEL_OK("sr_attention_bwd", stream);
   SrArgs a = base_args(k, B);
   a.CK = k.C, a.N = k.C, a.wpk = k.w2d, a.out = k.g_c1;
-  ADVB_TRY(launch_conv<B2>(a, false, (t + "_conv2_bwd").c_str(), stream));
+  ADVB_TRY(launch_conv<B2>(a, false, t.conv2_bwd, stream));
   a.in = k.g_c1, a.x = x;
   if (first) {
     dim3 grid(cdiv(k.H * k.W, 256), B);
     sr_first_bwd_kernel<<<grid, 256, 0, stream>>>(a, k.w1, k.wds, k.Cout, bn4, g_x);
-    ADVB_KERNEL_OK((t + "_conv1_bwd").c_str(), stream);
+    ADVB_KERNEL_OK(t.conv1_bwd, stream);
     return 0;
   }
   a.CK = k.C, a.N = k.Ci, a.wpk = k.w1d, a.out = g_x, a.wd = k.downsample ? k.wdd : nullptr;
-  ADVB_TRY(launch_conv<B1>(a, false, (t + "_conv1_bwd").c_str(), stream));
+  ADVB_TRY(launch_conv<B1>(a, false, t.conv1_bwd, stream));
   return 0;
 }
 
