@@ -163,7 +163,8 @@ class Engine:
         return buf.view(B, H + 2 * p, W + 2 * p, Cc), p
 
     def set_option(self, key: str, value: int):
-        """``conv_path`` (0 tcgen05 / 1 fp32 SIMT), ``tf32_passes`` (3 = 3xTF32 / 1 = single pass)."""
+        """``conv_path`` (0 tcgen05 / 1 fp32 SIMT), ``tf32_passes`` (3 = 3xTF32 / 1 = single pass), ``conv_sched``
+        (0 persistent kernels / 1 one-tile-per-CTA kernels)."""
         _lib.check(self.lib.advb_set_option(self.handle, key.encode(), int(value)))
 
     def profile_begin(self):

@@ -17,6 +17,10 @@ extern thread_local LaunchCounter* g_counter;
 inline void count_launch(int k = 1) {
   if (g_counter) g_counter->n += k;
 }
+// Convolution schedule of the current call (engine option "conv_sched"): 0 = persistent warp-specialised kernels
+// (default), 1 = one-tile-per-CTA kernels of conv_tc.cu only (the first tcgen05 version, kept as an in-process cross-check).
+extern thread_local int g_conv_sched;
+
 // Optional per-kernel timing (bench.py's live roofline): when enabled, an event is recorded after every launch;
 // consecutive events on the (serial) stream bracket exactly one kernel.
 void prof_mark(const char* name, cudaStream_t stream);

@@ -514,7 +514,7 @@ int launch_light(LArgs a, const char* tag, cudaStream_t stream) {
 }  // namespace
 
 bool conv_light_supported(int Cin, int Cout, int KS, bool pool, bool bwd) {
-  if (tune_light_persistent() == 0) return false;
+  if (tune_light_persistent() == 0 || g_conv_sched != 0) return false;
   if (KS == 5) return Cin == 1 && Cout == 64 && pool;
   if (KS != 1 || pool) return false;
   if (!bwd) return (Cin == 32 && Cout == 64) || (Cin == 48 && Cout == 96) || (Cin == 64 && Cout == 128);

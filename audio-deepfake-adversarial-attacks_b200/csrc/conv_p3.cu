@@ -536,7 +536,7 @@ int conv_p3_pack_hs(const float* w, unsigned char* wd, int Cout, int Cin, cudaSt
 }
 
 bool conv_p3_supported(int Cin, int Cout, int KS, bool pool, int W) {
-  if (tune_p3() == 0 || KS != 3 || W > 40) return false;
+  if (tune_p3() == 0 || g_conv_sched != 0 || KS != 3 || W > 40) return false;
   if (pool) return (Cin == 32 && Cout == 96) || (Cin == 48 && Cout == 128) || (Cin == 32 && Cout == 64);
   return Cin == 64 && Cout == 64;
 }

@@ -24,6 +24,7 @@ namespace advb {
 
 static thread_local std::string g_error;
 thread_local LaunchCounter* g_counter = nullptr;
+thread_local int g_conv_sched = 0;
 void set_error(const std::string& msg) { g_error = msg; }
 
 struct Profiler {
@@ -73,6 +74,7 @@ struct advb_handle {
   size_t ws_bytes = 0;
   int conv_path = 0;    // 0 = tcgen05 tensor cores (default), 1 = fp32 SIMT cross-check path
   int tf32_passes = 3;  // 3 = 3xTF32 (fp32-class accuracy), 1 = single-pass tf32
+  int conv_sched = 0;   // 0 = persistent warp-specialised conv kernels, 1 = one-tile-per-CTA kernels only
 
   // frontend
   float2* tw = nullptr;
@@ -627,6 +629,7 @@ struct CallScope {
   explicit CallScope(advb_handle* h) : guard(h->device) {
     g_counter = &h->counter;
     g_prof = &h->prof;
+    g_conv_sched = h->conv_sched;
   }
   ~CallScope() {
     g_counter = nullptr;
@@ -706,6 +709,9 @@ int advb_set_option(advb_handle* h, const char* key, int value) {
   } else if (k == "tf32_passes") {
     ADVB_CHECK(value == 1 || value == 3, "tf32_passes: 3 = 3xTF32, 1 = single pass");
     h->tf32_passes = value;
+  } else if (k == "conv_sched") {
+    ADVB_CHECK(value == 0 || value == 1, "conv_sched: 0 = persistent kernels, 1 = one-tile-per-CTA kernels");
+    h->conv_sched = value;
   } else {
     set_error("unknown option '" + k + "'");
     return 1;

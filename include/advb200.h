@@ -85,7 +85,9 @@ ADVB_API int advb_rebind(advb_handle* h, int n_tensors, const advb_tensor_ref* t
 
 /* Engine options (no reference counterpart; the reference's knobs are torch-global):
  *   "conv_path"   0 = tcgen05 tensor-core convolutions (default), 1 = fp32 SIMT convolutions (cross-check)
- *   "tf32_passes" 3 = 3xTF32 error-compensated products, fp32-class accuracy (default), 1 = single-pass tf32 */
+ *   "tf32_passes" 3 = 3xTF32 error-compensated products, fp32-class accuracy (default), 1 = single-pass tf32
+ *   "conv_sched"  0 = persistent warp-specialised convolution kernels (default), 1 = one-tile-per-CTA kernels only
+ *                 (the first tcgen05 version; same arithmetic, kept as an in-process cross-check) */
 ADVB_API int advb_set_option(advb_handle* h, const char* key, int value);
 
 /* Replaces  atk(images, labels)  = Attack.__call__ -> {FGSM,PGD,PGDL2,FAB,CW}.forward
