@@ -19,51 +19,63 @@ constexpr int HID = 80;
 constexpr int G4 = 4 * HID;  // 320
 constexpr int CL = 2;        // clips per recurrence CTA
 
-// C[M,N] = A[M,K] * Bm[K,N] (+ bias[N]) (+ Cadd[M,N]); row-major; TILE x TILE tile, (TILE/16)^2 per thread.
-// TILE = 32 is used when 64x64 tiles would leave most SMs idle (the narrow N = 160 backward projections).
-template <int TILE>
+// C[M,N] = A[M,K] * Bm[K,N] (+ bias[N]) (+ Cadd[M,N]); row-major, K and N multiples of 4, 16-byte aligned rows.
+// BM x BN tile, 16-deep k-steps, 256 threads with a (BM/16) x (BN/16) register tile; 128-bit global and shared loads.
+// BN = 32 is used when 64-wide tiles would leave most SMs idle (the narrow N = 160 backward projections).
+template <int BM, int BN>
 __global__ void __launch_bounds__(256) gemm_kernel(const float* __restrict__ A, const float* __restrict__ Bm,
                                                     const float* __restrict__ bias, const float* __restrict__ Cadd,
                                                     float* __restrict__ C, int M, int N, int K) {
-  constexpr int R = TILE / 16;
-  __shared__ float As[16][TILE + 1];
-  __shared__ float Bs[16][TILE];
+  constexpr int RM = BM / 16, RN = BN / 16;
+  static_assert(BM == 64 && (BN == 64 || BN == 32), "tile shapes used by the BLSTM projections");
+  __shared__ __align__(16) float As[16][BM + 4];  // k-major: As[k][m]
+  __shared__ __align__(16) float Bs[16][BN];
   const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
-  const int m0 = blockIdx.y * TILE, n0 = blockIdx.x * TILE;
-  float acc[R][R] = {};
+  const int m0 = blockIdx.y * BM, n0 = blockIdx.x * BN;
+  float acc[RM][RN] = {};
+  const int a_row = tid >> 2, a_kq = (tid & 3) * 4;            // A tile: 64 rows x 4 float4 along k
+  const int b_row = tid / (BN / 4), b_c4 = (tid % (BN / 4)) * 4;  // B tile: 16 rows x BN/4 float4
   for (int k0 = 0; k0 < K; k0 += 16) {
-    for (int i = tid; i < TILE * 16; i += 256) {
-      const int r = i >> 4, c = i & 15;
-      const int m = m0 + r, k = k0 + c;
-      As[c][r] = (m < M && k < K) ? A[(size_t)m * K + k] : 0.f;
+    {
+      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (m0 + a_row < M && k0 + a_kq < K) v = __ldg(reinterpret_cast<const float4*>(A + (size_t)(m0 + a_row) * K + k0 + a_kq));
+      As[a_kq + 0][a_row] = v.x;
+      As[a_kq + 1][a_row] = v.y;
+      As[a_kq + 2][a_row] = v.z;
+      As[a_kq + 3][a_row] = v.w;
     }
-    for (int i = tid; i < 16 * TILE; i += 256) {
-      const int r = i / TILE, c = i % TILE;
-      const int k = k0 + r, n = n0 + c;
-      Bs[r][c] = (k < K && n < N) ? Bm[(size_t)k * N + n] : 0.f;
+    if (b_row < 16) {
+      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (k0 + b_row < K && n0 + b_c4 < N) v = __ldg(reinterpret_cast<const float4*>(Bm + (size_t)(k0 + b_row) * N + n0 + b_c4));
+      *reinterpret_cast<float4*>(&Bs[b_row][b_c4]) = v;
     }
     __syncthreads();
 #pragma unroll
     for (int kk = 0; kk < 16; ++kk) {
-      float a[R], bv[R];
+      float a[RM], bv[RN];
+      const float4 av = *reinterpret_cast<const float4*>(&As[kk][ty * 4]);
+      a[0] = av.x, a[1] = av.y, a[2] = av.z, a[3] = av.w;
+      if (RN == 4) {
+        const float4 b4 = *reinterpret_cast<const float4*>(&Bs[kk][tx * 4]);
+        bv[0] = b4.x, bv[1] = b4.y, bv[RN - 2] = b4.z, bv[RN - 1] = b4.w;
+      } else {
+        const float2 b2 = *reinterpret_cast<const float2*>(&Bs[kk][tx * 2]);
+        bv[0] = b2.x, bv[1] = b2.y;
+      }
 #pragma unroll
-      for (int i = 0; i < R; ++i) a[i] = As[kk][ty * R + i];
+      for (int i = 0; i < RM; ++i)
 #pragma unroll
-      for (int j = 0; j < R; ++j) bv[j] = Bs[kk][tx * R + j];
-#pragma unroll
-      for (int i = 0; i < R; ++i)
-#pragma unroll
-        for (int j = 0; j < R; ++j) acc[i][j] = fmaf(a[i], bv[j], acc[i][j]);
+        for (int j = 0; j < RN; ++j) acc[i][j] = fmaf(a[i], bv[j], acc[i][j]);
     }
     __syncthreads();
   }
 #pragma unroll
-  for (int i = 0; i < R; ++i) {
-    const int m = m0 + ty * R + i;
+  for (int i = 0; i < RM; ++i) {
+    const int m = m0 + ty * RM + i;
     if (m >= M) continue;
 #pragma unroll
-    for (int j = 0; j < R; ++j) {
-      const int n = n0 + tx * R + j;
+    for (int j = 0; j < RN; ++j) {
+      const int n = n0 + tx * RN + j;
       if (n >= N) continue;
       float v = acc[i][j];
       if (bias != nullptr) v += bias[n];
@@ -120,11 +132,14 @@ __global__ void __launch_bounds__(G4) lstm_rec_fwd_kernel(float* __restrict__ ga
 #pragma unroll
     for (int cl = 0; cl < CL; ++cl)
       acc[cl] = (b0 + cl < B) ? gates[((size_t)(b0 + cl) * L + t) * (2 * G4) + dir * G4 + j] : 0.f;
-#pragma unroll 8
-    for (int k = 0; k < HID; ++k) {
-      const float w = s_w[k * G4 + j];
+#pragma unroll 4
+    for (int k = 0; k < HID; k += 4) {  // h as 128-bit broadcast loads: 4 + CL shared-memory loads per 4 CL FMAs
+      const float w0 = s_w[k * G4 + j], w1 = s_w[(k + 1) * G4 + j], w2 = s_w[(k + 2) * G4 + j], w3 = s_w[(k + 3) * G4 + j];
 #pragma unroll
-      for (int cl = 0; cl < CL; ++cl) acc[cl] = fmaf(w, s_h[cl * HID + k], acc[cl]);
+      for (int cl = 0; cl < CL; ++cl) {
+        const float4 hv = *reinterpret_cast<const float4*>(s_h + cl * HID + k);
+        acc[cl] = fmaf(w3, hv.w, fmaf(w2, hv.z, fmaf(w1, hv.y, fmaf(w0, hv.x, acc[cl]))));
+      }
     }
 #pragma unroll
     for (int cl = 0; cl < CL; ++cl) {
@@ -287,12 +302,13 @@ int rnn_init() {
 
 int gemm(const float* A, const float* Bm, const float* bias, const float* Cadd, float* C, int M, int N, int K,
          cudaStream_t stream, const char* tag) {
+  ADVB_CHECK(K % 4 == 0 && N % 4 == 0, "gemm: K and N must be multiples of 4");
   if (cdiv(N, 64) * cdiv(M, 64) < 2 * 148) {
-    dim3 grid(cdiv(N, 32), cdiv(M, 32));
-    gemm_kernel<32><<<grid, 256, 0, stream>>>(A, Bm, bias, Cadd, C, M, N, K);
+    dim3 grid(cdiv(N, 32), cdiv(M, 64));
+    gemm_kernel<64, 32><<<grid, 256, 0, stream>>>(A, Bm, bias, Cadd, C, M, N, K);
   } else {
     dim3 grid(cdiv(N, 64), cdiv(M, 64));
-    gemm_kernel<64><<<grid, 256, 0, stream>>>(A, Bm, bias, Cadd, C, M, N, K);
+    gemm_kernel<64, 64><<<grid, 256, 0, stream>>>(A, Bm, bias, Cadd, C, M, N, K);
   }
   ADVB_KERNEL_OK(tag, stream);
   return 0;
