@@ -114,33 +114,56 @@ __global__ void __launch_bounds__(G4) lstm_rec_fwd_kernel(float* __restrict__ ga
                                                            float* __restrict__ hout, float* __restrict__ cs, int B,
                                                            int L) {
   extern __shared__ __align__(16) float smem[];
-  float* s_w = smem;                 // [80][320]
-  float* s_h = s_w + HID * G4;       // [CL][80]
+  float* s_h = smem;                 // [CL][80]
   float* s_a = s_h + CL * HID;       // [CL][320]
   const int j = threadIdx.x, dir = blockIdx.y, b0 = blockIdx.x * CL;
+  // persistent-RNN style: thread j keeps its 80 recurrent weights (column j of W_hh^T) in registers for the whole
+  // sequence, so a step reads only h from shared memory (the per-step W reads were 2/3 of the shared-memory traffic)
   const float* wsrc = whhT + (size_t)dir * HID * G4;
-  for (int i = j; i < HID * G4; i += G4) s_w[i] = wsrc[i];
+  float wreg[HID];
+#pragma unroll
+  for (int k = 0; k < HID; ++k) wreg[k] = __ldg(wsrc + (size_t)k * G4 + j);
   if (j < CL * HID) s_h[j] = 0.f;
   float c_reg[CL];
 #pragma unroll
   for (int cl = 0; cl < CL; ++cl) c_reg[cl] = 0.f;
   __syncthreads();
   const int gate = j / HID;
+  // the input projection of step s+1 is fetched while step s runs: the L2 round trip (~0.5 us) was a dependent load
+  // at the head of each of the 25 sequential steps
+  float pre[CL];
+  {
+    const int t0 = dir == 0 ? 0 : L - 1;
+#pragma unroll
+    for (int cl = 0; cl < CL; ++cl)
+      pre[cl] = (b0 + cl < B) ? gates[((size_t)(b0 + cl) * L + t0) * (2 * G4) + dir * G4 + j] : 0.f;
+  }
   for (int step = 0; step < L; ++step) {
     const int t = dir == 0 ? step : L - 1 - step;
     float acc[CL];
 #pragma unroll
-    for (int cl = 0; cl < CL; ++cl)
-      acc[cl] = (b0 + cl < B) ? gates[((size_t)(b0 + cl) * L + t) * (2 * G4) + dir * G4 + j] : 0.f;
-#pragma unroll 4
-    for (int k = 0; k < HID; k += 4) {  // h as 128-bit broadcast loads: 4 + CL shared-memory loads per 4 CL FMAs
-      const float w0 = s_w[k * G4 + j], w1 = s_w[(k + 1) * G4 + j], w2 = s_w[(k + 2) * G4 + j], w3 = s_w[(k + 3) * G4 + j];
+    for (int cl = 0; cl < CL; ++cl) acc[cl] = pre[cl];
+    if (step + 1 < L) {
+      const int tn = dir == 0 ? step + 1 : L - 2 - step;
+#pragma unroll
+      for (int cl = 0; cl < CL; ++cl)
+        pre[cl] = (b0 + cl < B) ? gates[((size_t)(b0 + cl) * L + tn) * (2 * G4) + dir * G4 + j] : 0.f;
+    }
+    float acc2[CL];  // second accumulator chain per clip (halves the dependent FMA chain)
+#pragma unroll
+    for (int cl = 0; cl < CL; ++cl) acc2[cl] = 0.f;
+#pragma unroll
+    for (int k = 0; k < HID; k += 8) {
 #pragma unroll
       for (int cl = 0; cl < CL; ++cl) {
-        const float4 hv = *reinterpret_cast<const float4*>(s_h + cl * HID + k);
-        acc[cl] = fmaf(w3, hv.w, fmaf(w2, hv.z, fmaf(w1, hv.y, fmaf(w0, hv.x, acc[cl]))));
+        const float4 h0 = *reinterpret_cast<const float4*>(s_h + cl * HID + k);
+        const float4 h1 = *reinterpret_cast<const float4*>(s_h + cl * HID + k + 4);
+        acc[cl] = fmaf(wreg[k + 3], h0.w, fmaf(wreg[k + 2], h0.z, fmaf(wreg[k + 1], h0.y, fmaf(wreg[k], h0.x, acc[cl]))));
+        acc2[cl] = fmaf(wreg[k + 7], h1.w, fmaf(wreg[k + 6], h1.z, fmaf(wreg[k + 5], h1.y, fmaf(wreg[k + 4], h1.x, acc2[cl]))));
       }
     }
+#pragma unroll
+    for (int cl = 0; cl < CL; ++cl) acc[cl] += acc2[cl];
 #pragma unroll
     for (int cl = 0; cl < CL; ++cl) {
       const float a = gate == 2 ? tanhf(acc[cl]) : sigmoidf_(acc[cl]);
@@ -171,33 +194,60 @@ __global__ void __launch_bounds__(G4) lstm_rec_bwd_kernel(float* __restrict__ ga
                                                            const float* __restrict__ dout,
                                                            const float* __restrict__ cs, int B, int L) {
   extern __shared__ __align__(16) float smem[];
-  float* s_w = smem;                   // [320][80]
-  float* s_dg = s_w + G4 * HID;        // [CL][320]
+  float* s_dg = smem;                  // [CL][320]
   float* s_dh = s_dg + CL * G4;        // [CL][80]
   float* s_part = s_dh + CL * HID;     // [CL][4][80]
   const int j = threadIdx.x, dir = blockIdx.y, b0 = blockIdx.x * CL;
   const float* wsrc = whh + (size_t)dir * G4 * HID;
-  for (int i = j; i < G4 * HID; i += G4) s_w[i] = wsrc[i];
   if (j < CL * HID) s_dh[j] = 0.f;
   float dc[CL];
 #pragma unroll
   for (int cl = 0; cl < CL; ++cl) dc[cl] = 0.f;
   __syncthreads();
   const int part = j / HID, u = j % HID;
-  for (int step = L - 1; step >= 0; --step) {
+  // thread (part, u) keeps W_hh[part*80 + jj][u], jj = 0..79, in registers for the whole sequence
+  float wreg[HID];
+#pragma unroll
+  for (int jj = 0; jj < HID; ++jj) wreg[jj] = __ldg(wsrc + (size_t)(part * HID + jj) * HID + u);
+  // operands of a step (gates, cell, previous cell, dout) are fetched one step ahead (threads j < HID)
+  float n_g[CL][4], n_c[CL], n_cp[CL], n_do[CL];
+  auto fetch = [&](int step) {
     const int t = dir == 0 ? step : L - 1 - step;
     const int tp = dir == 0 ? t - 1 : t + 1;
+#pragma unroll
+    for (int cl = 0; cl < CL; ++cl) {
+      n_g[cl][0] = n_g[cl][1] = n_g[cl][2] = n_g[cl][3] = 0.f;
+      n_c[cl] = n_cp[cl] = n_do[cl] = 0.f;
+      if (j < HID && b0 + cl < B) {
+        const size_t bt = (size_t)(b0 + cl) * L + t;
+        const float* g = gates + bt * (2 * G4) + dir * G4;
+        n_g[cl][0] = g[j], n_g[cl][1] = g[HID + j], n_g[cl][2] = g[2 * HID + j], n_g[cl][3] = g[3 * HID + j];
+        n_c[cl] = cs[(bt * 2 + dir) * HID + j];
+        n_cp[cl] = step > 0 ? cs[((((size_t)(b0 + cl) * L + tp) * 2) + dir) * HID + j] : 0.f;
+        n_do[cl] = dout[bt * (2 * HID) + dir * HID + j];
+      }
+    }
+  };
+  fetch(L - 1);
+  for (int step = L - 1; step >= 0; --step) {
+    const int t = dir == 0 ? step : L - 1 - step;
+    float c_g[CL][4], c_c[CL], c_cp[CL], c_do[CL];
+#pragma unroll
+    for (int cl = 0; cl < CL; ++cl) {
+      c_g[cl][0] = n_g[cl][0], c_g[cl][1] = n_g[cl][1], c_g[cl][2] = n_g[cl][2], c_g[cl][3] = n_g[cl][3];
+      c_c[cl] = n_c[cl], c_cp[cl] = n_cp[cl], c_do[cl] = n_do[cl];
+    }
+    // NOTE: the gates row of step-1 is still the forward's activations: this step only overwrites row `t` below
+    if (step > 0) fetch(step - 1);
     if (j < HID) {
 #pragma unroll
       for (int cl = 0; cl < CL; ++cl) {
         float dgi = 0.f, dgf = 0.f, dgg = 0.f, dgo = 0.f;
         if (b0 + cl < B) {
-          const size_t bt = (size_t)(b0 + cl) * L + t;
-          const float* g = gates + bt * (2 * G4) + dir * G4;
-          const float gi = g[j], gf = g[HID + j], gg = g[2 * HID + j], go = g[3 * HID + j];
-          const float c = cs[(bt * 2 + dir) * HID + j];
-          const float cp = step > 0 ? cs[((((size_t)(b0 + cl) * L + tp) * 2) + dir) * HID + j] : 0.f;
-          const float dh = dout[bt * (2 * HID) + dir * HID + j] + s_dh[cl * HID + j];
+          const float gi = c_g[cl][0], gf = c_g[cl][1], gg = c_g[cl][2], go = c_g[cl][3];
+          const float c = c_c[cl];
+          const float cp = c_cp[cl];
+          const float dh = c_do[cl] + s_dh[cl * HID + j];
           const float tc = tanhf(c);
           const float d_o = dh * tc;
           const float dcc = dc[cl] + dh * go * (1.f - tc * tc);
@@ -218,12 +268,15 @@ __global__ void __launch_bounds__(G4) lstm_rec_bwd_kernel(float* __restrict__ ga
 #pragma unroll
     for (int cl = 0; cl < CL; ++cl) {
       if (b0 + cl < B) gates[((size_t)(b0 + cl) * L + t) * (2 * G4) + dir * G4 + j] = s_dg[cl * G4 + j];
-      float s = 0.f;
+      float s = 0.f, s2 = 0.f;
       const float* d = s_dg + cl * G4 + part * HID;
-      const float* w = s_w + (size_t)part * HID * HID + u;
-#pragma unroll 8
-      for (int jj = 0; jj < HID; ++jj) s = fmaf(d[jj], w[jj * HID], s);
-      s_part[(cl * 4 + part) * HID + u] = s;
+#pragma unroll
+      for (int jj = 0; jj < HID; jj += 8) {
+        const float4 d0 = *reinterpret_cast<const float4*>(d + jj), d1 = *reinterpret_cast<const float4*>(d + jj + 4);
+        s = fmaf(d0.w, wreg[jj + 3], fmaf(d0.z, wreg[jj + 2], fmaf(d0.y, wreg[jj + 1], fmaf(d0.x, wreg[jj], s))));
+        s2 = fmaf(d1.w, wreg[jj + 7], fmaf(d1.z, wreg[jj + 6], fmaf(d1.y, wreg[jj + 5], fmaf(d1.x, wreg[jj + 4], s2))));
+      }
+      s_part[(cl * 4 + part) * HID + u] = s + s2;
     }
     __syncthreads();
     if (j < HID) {
@@ -289,8 +342,8 @@ __global__ void __launch_bounds__(160) head_bwd_kernel(const float* __restrict__
 
 }  // namespace
 
-size_t lstm_rec_fwd_smem() { return (size_t)(HID * G4 + CL * HID + CL * G4) * sizeof(float); }
-size_t lstm_rec_bwd_smem() { return (size_t)(G4 * HID + CL * G4 + CL * HID + CL * 4 * HID) * sizeof(float); }
+size_t lstm_rec_fwd_smem() { return (size_t)(CL * HID + CL * G4) * sizeof(float); }
+size_t lstm_rec_bwd_smem() { return (size_t)(CL * G4 + CL * HID + CL * 4 * HID) * sizeof(float); }
 
 int rnn_init() {
   ADVB_CUDA_OK(cudaFuncSetAttribute(lstm_rec_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
