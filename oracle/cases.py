@@ -20,6 +20,12 @@ CASES = {
     "lcnn_lfcc_t64000": dict(model="lcnn", frontend="lfcc", T=64000, B=1, cfg_id=13, silence=False),
     "specrnet_mfcc_t16000": dict(model="specrnet", frontend="mfcc", T=16000, B=3, cfg_id=15, silence=False),
     "specrnet_lfcc_t64000": dict(model="specrnet", frontend="lfcc", T=64000, B=1, cfg_id=16, silence=False),
+    # RawNet3 is a raw-waveform model (no spectral frontend, rawnet3.py:73-137)
+    "rawnet3_t16000": dict(model="rawnet3", frontend="none", T=16000, B=2, cfg_id=17, silence=False),
+    "rawnet3_t64000": dict(model="rawnet3", frontend="none", T=64000, B=1, cfg_id=18, silence=False,
+                           attacks=("fgsm", "pgdl2")),
+    "rawnet3_t16000_margin": dict(model="rawnet3", frontend="none", T=16000, B=3, cfg_id=19, silence=False,
+                                  margin=0.01, labels=(1, 0, 1), attacks=("fab",)),
     # FAB / CW: clean logits sit at +margin (all predicted bonafide) and labels are fixed, so the clips labelled 1 are
     # correctly classified and must be pushed across a real margin; the clip labelled 0 is already misclassified and
     # exercises FAB's "attack only the correctly classified clips" path (fab.py:506-513)
@@ -42,7 +48,7 @@ def build_holder(model: str, frontend: str, seed: int = 42):
     from advb200.models import get_model
 
     torch.manual_seed(seed)
-    cfg = {"input_channels": 1, "frontend_algorithm": [frontend]}
+    cfg = {"input_channels": 1, "frontend_algorithm": [frontend]} if model != "rawnet3" else {}
     return get_model(model, cfg, "cpu")
 
 

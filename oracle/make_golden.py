@@ -12,9 +12,12 @@ import torch
 
 warnings.filterwarnings("ignore")
 sys.path.insert(0, "/root/reference")
+# third-party dependency of the reference that is not installed here (restated, see its docstring)
+sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "third_party"))
 
 from . import cases, synth  # noqa: E402
 from . import lcnn as olcnn  # noqa: E402
+from . import rawnet3 as orn  # noqa: E402
 from . import specrnet as ospec  # noqa: E402
 
 
@@ -27,6 +30,10 @@ def reference_model(case, state):
         from src.models.specrnet import SpecRNet, get_config
 
         m = SpecRNet(get_config(1), device="cpu", input_channels=1, frontend_algorithm=[case["frontend"]])
+    elif case["model"] == "rawnet3":
+        from src.models.rawnet3 import prepare_model
+
+        m = prepare_model()
     else:
         raise NotImplementedError(case["model"])
     missing = m.load_state_dict(state, strict=True)
@@ -44,7 +51,7 @@ def main():
         if only and name not in only:
             continue
         x, y = cases.case_inputs(case)
-        fwd = {"lcnn": olcnn.forward, "specrnet": ospec.forward}[case["model"]]
+        fwd = {"lcnn": olcnn.forward, "specrnet": ospec.forward, "rawnet3": orn.forward}[case["model"]]
         _, state = cases.build_state(case["model"], case["frontend"], calibrate_on=x, forward_fn=fwd,
                                      margin=case.get("margin", 0.0))
         ref = reference_model(case, state)
@@ -52,8 +59,8 @@ def main():
         out = {"digest": np.array(synth.state_digest(state)), "x_sum": np.array(x.double().sum().item())}
         with torch.no_grad():
             out["logits"] = ref(x).numpy()
-            feat = ref.frontend(x)
-            out["frontend"] = feat.numpy()
+            if hasattr(ref, "frontend"):
+                out["frontend"] = ref.frontend(x).numpy()
         # CE gradient exactly as the attacks build it (fgsm.py:43-57)
         xr = x.clone().requires_grad_(True)
         ref.train()

@@ -7,9 +7,10 @@ import torch
 from oracle import attacks as oatk
 from oracle import cases, synth
 from oracle import lcnn as olcnn
+from oracle import rawnet3 as orn
 from oracle import specrnet as ospec
 
-ORACLE_FWD = {"lcnn": olcnn.forward, "specrnet": ospec.forward}
+ORACLE_FWD = {"lcnn": olcnn.forward, "specrnet": ospec.forward, "rawnet3": orn.forward}
 
 
 def load_golden(name):

@@ -21,12 +21,13 @@ def test_oracle_forward_and_gradient_match_reference(name):
     with torch.no_grad():
         o = fwd(x, state, taps)
     np.testing.assert_allclose(o.numpy(), g["logits"], atol=2e-6)
-    np.testing.assert_allclose(taps["frontend"].squeeze(1).numpy(), g["frontend"], atol=2e-3)
+    if "frontend" in g.files:
+        np.testing.assert_allclose(taps["frontend"].squeeze(1).numpy(), g["frontend"], atol=2e-3)
     _, grad = oatk.loss_and_grad(lambda v: fwd(v, state), x, y)
     assert helpers.rel_err(grad, torch.from_numpy(g["grad"])) < 1e-4
 
 
-@pytest.mark.parametrize("name", CASES[:2])
+@pytest.mark.parametrize("name", CASES[:2] + ["rawnet3_t16000"])
 @pytest.mark.parametrize("attack", ["fgsm", "pgd", "pgdl2"])
 def test_oracle_attacks_match_reference(name, attack):
     case, x, y, holder, state, fwd = helpers.case_setup(name)
@@ -42,7 +43,10 @@ def test_oracle_attacks_match_reference(name, attack):
         # With the dB floor active (silence case) the loss is discontinuous in x (clamp membership + arg-max
         # routing): ulp-level differences flip borderline elements and iterates drift apart, so
         # element-wise comparison is only meaningful on the smooth case; norms and labels are checked on both.
-        if not case["silence"]:
+        # RawNet3: log(|sinc| + 1e-6) makes the gradient ill-conditioned near the zero crossings of the filter outputs;
+        # the reference run with 1 vs 8 threads drifts to cosine 0.83 between its own 3-step PGDL2 perturbations
+        # (measured), so only the first step is comparable element-wise (tested on the GPU per step).
+        if not case["silence"] and case["model"] != "rawnet3":
             assert (xa - ref).abs().max().item() < 5e-6
     else:
         assert (xa != ref).float().mean().item() < 2e-3
@@ -51,9 +55,9 @@ def test_oracle_attacks_match_reference(name, attack):
     assert np.array_equal((la.numpy() > 0), (g[f"{attack}_logits_adv"] > 0)), "label flips differ"
 
 
-@pytest.mark.parametrize("attack", ["fab", "cw"])
-def test_oracle_fab_cw_match_reference(attack):
-    name = "lcnn_lfcc_t16000_margin"
+@pytest.mark.parametrize("name,attack", [("lcnn_lfcc_t16000_margin", "fab"), ("lcnn_lfcc_t16000_margin", "cw"),
+                                         ("rawnet3_t16000_margin", "fab")])
+def test_oracle_fab_cw_match_reference(name, attack):
     case, x, y, holder, state, fwd = helpers.case_setup(name)
     g = helpers.load_golden(name)
     xa = helpers.oracle_attack(name, attack, x, y, state, fwd, case)
@@ -64,7 +68,8 @@ def test_oracle_fab_cw_match_reference(attack):
     np.testing.assert_allclose((xa - x).norm(p=2, dim=1).numpy(), g[f"{attack}_delta_l2"], rtol=1e-4, atol=1e-5)
     assert (xa - ref).abs().max().item() < 1e-5
     if attack == "fab":
-        assert torch.equal(xa[2], x[2])
+        wrong = [i for i, lab in enumerate(case["labels"]) if lab == 0]  # predicted bonafide, labelled spoof
+        assert all(torch.equal(xa[i], x[i]) for i in wrong)
     with torch.no_grad():
         la = fwd(xa, state)
     assert np.array_equal((la.numpy() > 0), (g[f"{attack}_logits_adv"] > 0)), "label flips differ"
