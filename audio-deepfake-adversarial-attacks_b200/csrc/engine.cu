@@ -16,6 +16,7 @@
 #include "conv.cuh"
 #include "fabcw.cuh"
 #include "frontend.cuh"
+#include "rawnet3.cuh"
 #include "rnn.cuh"
 #include "specrnet.cuh"
 #include "update.cuh"
@@ -96,6 +97,9 @@ struct advb_handle {
   SrGru gru{};
   float *sr_img = nullptr, *sr_bn4 = nullptr;
   int sr_L = 0;
+
+  // RawNet3
+  RnModel rn{};
 
   // attack scratch
   float* conv0_T = nullptr;  // (B,F,80,5) horizontal col2im partial sums of the first block's backward
@@ -566,13 +570,33 @@ int specrnet_backward(advb_handle* h, const float* x, const int64_t* y, int B, i
   return 0;
 }
 
+// ---- RawNet3 (src/models/rawnet3.py) ----
+int check_rawnet3_tensors(advb_handle* h) {
+  return rn_check_tensors([h](const std::string& name, long long numel) { return require(h, name, numel); });
+}
+int build_rawnet3(advb_handle* h) {
+  ADVB_TRY(check_rawnet3_tensors(h));
+  return rn_build(h->rn, h->Bmax, h->T, [h](void** p, size_t bytes) {
+    unsigned char* q = nullptr;
+    const int r = h->alloc(&q, bytes);
+    *p = q;
+    return r;
+  });
+}
+int prepare_rawnet3(advb_handle* h, cudaStream_t st) {
+  rn_bind(h->rn, [h](const std::string& name) { return h->t(name); });
+  return rn_prepare(h->rn, h->conv_path, st);
+}
+
 int model_prepare(advb_handle* h, cudaStream_t st) {
+  if (h->model_kind == ADVB_MODEL_RAWNET3) return prepare_rawnet3(h, st);
   if (h->model_kind == ADVB_MODEL_LCNN) return prepare_lcnn(h, st);
   if (h->model_kind == ADVB_MODEL_SPECRNET) return prepare_specrnet(h, st);
   set_error("model kind not implemented");
   return 1;
 }
 int model_forward(advb_handle* h, const float* x, int B, cudaStream_t st) {
+  if (h->model_kind == ADVB_MODEL_RAWNET3) return rn_forward(h->rn, x, h->logits, B, h->conv_path, h->tf32_passes, st);
   if (h->model_kind == ADVB_MODEL_LCNN) return lcnn_forward(h, x, B, st);
   if (h->model_kind == ADVB_MODEL_SPECRNET) return specrnet_forward(h, x, B, st);
   set_error("model kind not implemented");
@@ -580,6 +604,9 @@ int model_forward(advb_handle* h, const float* x, int B, cudaStream_t st) {
 }
 int model_backward(advb_handle* h, const float* x, const int64_t* y, int B, int mode, int n_global, float* gx,
                    cudaStream_t st, const float* coef = nullptr) {
+  if (h->model_kind == ADVB_MODEL_RAWNET3)
+    return rn_backward(h->rn, x, h->logits, reinterpret_cast<const long long*>(y), B, mode, n_global, coef, gx, h->conv_path,
+                       h->tf32_passes, st);
   if (h->model_kind == ADVB_MODEL_LCNN) return lcnn_backward(h, x, y, B, mode, n_global, gx, st, coef);
   if (h->model_kind == ADVB_MODEL_SPECRNET) return specrnet_backward(h, x, y, B, mode, n_global, gx, st, coef);
   set_error("model kind not implemented");
@@ -664,12 +691,27 @@ int advb_create(advb_handle** out, const advb_model_desc* d) {
     return 1;
   };
   if (bind_tensors(h, d->n_tensors, d->tensors)) return fail();
-  if (h->model_kind != ADVB_MODEL_LCNN && h->model_kind != ADVB_MODEL_SPECRNET) {
-    set_error("model kind not implemented yet (LCNN and SpecRNet only)");
+  if (h->model_kind != ADVB_MODEL_LCNN && h->model_kind != ADVB_MODEL_SPECRNET && h->model_kind != ADVB_MODEL_RAWNET3) {
+    set_error("unknown model kind");
     return fail();
   }
-  if (check_frontend_tensors(h)) return fail();
   const size_t B = h->Bmax;
+  if (h->model_kind == ADVB_MODEL_RAWNET3) {  // raw-waveform model: no spectral frontend (rawnet3.py:73-137)
+    if (h->frontend_kind != ADVB_FRONTEND_NONE) {
+      set_error("RawNet3 takes the raw waveform (frontend_kind must be ADVB_FRONTEND_NONE)");
+      return fail();
+    }
+    if (h->alloc(&h->logits, B) || h->alloc(&h->grad, B * h->T) || h->alloc(&h->partial_g, B * ROW_CHUNKS) ||
+        h->alloc(&h->partial_d, B * ROW_CHUNKS) || build_rawnet3(h))
+      return fail();
+    if (cudaDeviceSynchronize() != cudaSuccess) {
+      set_error("device error during advb_create");
+      return fail();
+    }
+    *out = h;
+    return 0;
+  }
+  if (check_frontend_tensors(h)) return fail();
   if (h->alloc(&h->tw, 512) || h->alloc(&h->klo, 128) || h->alloc(&h->kcnt, 128) ||
       h->alloc(&h->mlo, 257) || h->alloc(&h->mcnt, 257) || h->alloc(&h->fst.gmax_packed, 1) ||
       h->alloc(&h->fst.n_clamped, 1) || h->alloc(&h->fst.mass_total, 1) ||
@@ -722,6 +764,7 @@ int advb_set_option(advb_handle* h, const char* key, int value) {
 int advb_rebind(advb_handle* h, int n_tensors, const advb_tensor_ref* tensors) {
   ADVB_CHECK(h != nullptr, "null handle");
   ADVB_TRY(bind_tensors(h, n_tensors, tensors));
+  if (h->model_kind == ADVB_MODEL_RAWNET3) return check_rawnet3_tensors(h);
   ADVB_TRY(check_frontend_tensors(h));
   if (h->model_kind == ADVB_MODEL_LCNN) ADVB_TRY(check_lcnn_tensors(h));
   if (h->model_kind == ADVB_MODEL_SPECRNET) ADVB_TRY(check_specrnet_tensors(h));
@@ -861,6 +904,7 @@ int advb_row_diff_norms(const float* a, const float* b, float* linf, float* l2, 
 
 int advb_frontend_fwd(advb_handle* h, const float* x, float* coeff, int B, int T, void* cuda_stream) {
   ADVB_TRY(check_call(h, B, T));
+  ADVB_CHECK(h->frontend_kind != ADVB_FRONTEND_NONE, "this model takes the raw waveform: it has no spectral frontend");
   CallScope scope(h);
   cudaStream_t st = static_cast<cudaStream_t>(cuda_stream);
   refresh_frontend_tables(h);
@@ -872,6 +916,7 @@ int advb_frontend_fwd(advb_handle* h, const float* x, float* coeff, int B, int T
 int advb_frontend_bwd(advb_handle* h, const float* x, const float* g_coeff, float* g_x, int B, int T,
                       void* cuda_stream) {
   ADVB_TRY(check_call(h, B, T));
+  ADVB_CHECK(h->frontend_kind != ADVB_FRONTEND_NONE, "this model takes the raw waveform: it has no spectral frontend");
   CallScope scope(h);
   cudaStream_t st = static_cast<cudaStream_t>(cuda_stream);
   refresh_frontend_tables(h);
@@ -955,7 +1000,16 @@ int64_t advb_debug_stage(advb_handle* h, const char* stage, float* dst, int64_t 
   };
   const bool is_sr = h->model_kind == ADVB_MODEL_SPECRNET;
   auto sr_idx = [&](char c) { return c == '0' ? 0 : c == '2' ? 1 : c == '4' ? 2 : -1; };
-  if (is_sr && s == "frontend") {
+  if (h->model_kind == ADVB_MODEL_RAWNET3) {
+    int rows = 0, cols = 0;
+    src = rn_stage(h->rn, s, &rows, &cols);
+    if (src == nullptr) {
+      set_error("unknown stage '" + s + "'");
+      return -1;
+    }
+    if (s == "rn_filt") d[0] = 1;                  // one filter bank, shared by every clip
+    d[1] = rows, d[2] = 1, d[3] = cols, d[4] = 0;  // raw rows (zero border rows included); W = 1, no reported border
+  } else if (is_sr && s == "frontend") {
     src = h->sr_img;
     d[1] = h->F, d[2] = 80, d[3] = 1, d[4] = 1;
   } else if (is_sr && s.size() == 6 && (s.rfind("sr_xb", 0) == 0 || s.rfind("sr_xn", 0) == 0 || s.rfind("sr_gn", 0) == 0) &&

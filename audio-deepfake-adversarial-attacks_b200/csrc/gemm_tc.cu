@@ -1,0 +1,401 @@
+// GEMM with fused epilogue for RawNet3's Conv1d contractions (contract: gemm.cuh).
+//
+// gemm_tc_kernel<NT, NSTAGE> (the product path): one CTA = one 128-row x NT-column output tile (NT = 256, or 128 when
+// N = 128), fp32 accumulator in TMEM, 3xTF32 on tcgen05 (tc_common.cuh).  Roles:
+//   * 8 worker warps: prefetch the next 128 x 32 fp32 chunk of A into registers (kept raw until converted, as in
+//     conv_light.cu), split it into tf32 hi / lo and store it K-major SWIZZLE_128B into a ring stage; thread 0 also
+//     launches the 1-D TMA bulk copy of the matching pre-packed weight slice into the same stage;
+//   * warp 8: waits for the stage (8 warp arrivals + the copy's bytes on one mbarrier), issues 4 k-steps x 3 passes of
+//     M=128, N=NT, K=8 MMAs and releases the stage with tcgen05.commit;
+//   * epilogue (the worker warps again): tcgen05.ld 32x32b (thread = row) -> per-warp shared-memory transpose ->
+//     thread = (row, 4 columns) so that every load / store of the fused epilogue (bias, ReLU + mask, BatchNorm, addend,
+//     gate, second output) is a coalesced 16-byte access.
+// blockIdx.x walks the N tiles fastest, so the CTAs that share a 128-row slab of A run together and the slab is read
+// from HBM once and from L2 N/NT - 1 times.
+//
+// gemm_simt_kernel: the same contract in plain fp32 FMA (64 x 64 tiles), engine option conv_path = 1 (cross-check).
+#include "gemm.cuh"
+#include "tc_common.cuh"
+
+namespace advb {
+
+namespace {
+
+using namespace tc;
+
+constexpr int GW = 256;        // worker threads
+constexpr int GT = GW + 32;    // + the MMA warp
+constexpr int SINC_K = 251, SINC_STRIDE = 10;
+
+__host__ __device__ constexpr int tile_n(int N) { return (N % 256 == 0) ? 256 : 128; }
+
+__device__ __forceinline__ float4 ldg4(const float* p) { return __ldg(reinterpret_cast<const float4*>(p)); }
+
+// x = hi + lo with BOTH parts rounded to nearest tf32.  kind::tf32 truncates its inputs (tc_common.cuh); an fp32 `lo`
+// (13 significant bits) would be truncated towards zero - a biased 2^-21 |x| error that adds up linearly over RawNet3's
+// 1024..3072-long contractions (measured: 4e-6 systematic logit offset).  Rounded, the residual is unbiased and 2x smaller.
+__device__ __forceinline__ void split_rn(float x, float& hi, float& lo) {
+  uint32_t h, l;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(h) : "f"(x));
+  hi = __uint_as_float(h);
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(l) : "f"(x - hi));
+  lo = __uint_as_float(l);
+}
+
+// The fused epilogue on 4 consecutive columns n..n+3 of valid row r (clip = r / Tp).
+__device__ __forceinline__ void epi_apply(const GemmArgs& a, int r, int clip, int n, float4 v) {
+  if (a.bias != nullptr) {
+    const float4 b = ldg4(a.bias + (a.bias_per_clip ? (size_t)clip * a.N : (size_t)0) + n);
+    v.x += b.x, v.y += b.y, v.z += b.z, v.w += b.w;
+  }
+  if (a.relu) {
+    if (a.mask_out != nullptr)
+      *reinterpret_cast<uchar4*>(a.mask_out + (size_t)r * a.ld_mask + n) =
+          make_uchar4(v.x > 0.f ? 1 : 0, v.y > 0.f ? 1 : 0, v.z > 0.f ? 1 : 0, v.w > 0.f ? 1 : 0);
+    v.x = fmaxf(v.x, 0.f), v.y = fmaxf(v.y, 0.f), v.z = fmaxf(v.z, 0.f), v.w = fmaxf(v.w, 0.f);
+  }
+  if (a.bn_scale != nullptr) {
+    const float4 s = ldg4(a.bn_scale + n), t = ldg4(a.bn_shift + n);
+    v.x = fmaf(v.x, s.x, t.x), v.y = fmaf(v.y, s.y, t.y), v.z = fmaf(v.z, s.z, t.z), v.w = fmaf(v.w, s.w, t.w);
+  }
+  if (a.add != nullptr) {
+    const float4 d = *reinterpret_cast<const float4*>(a.add + (size_t)r * a.ld_add + n);  // may alias out: plain load
+    v.x += d.x, v.y += d.y, v.z += d.z, v.w += d.w;
+  }
+  if (a.out != nullptr) {
+    float4 o = v;
+    if (a.gate_scale != nullptr) {
+      const float4 s = ldg4(a.gate_scale + n);
+      const uchar4 m = __ldg(reinterpret_cast<const uchar4*>(a.gate_mask + (size_t)r * a.ld_gate + n));
+      o.x = m.x ? v.x * s.x : 0.f, o.y = m.y ? v.y * s.y : 0.f, o.z = m.z ? v.z * s.z : 0.f, o.w = m.w ? v.w * s.w : 0.f;
+    }
+    *reinterpret_cast<float4*>(a.out + (size_t)r * a.ldc + n) = o;
+  }
+  if (a.out2 != nullptr) {
+    float4 o = v;
+    if (a.add2 != nullptr) {
+      const float4 d = ldg4(a.add2 + (size_t)r * a.ld_add2 + n);
+      o.x += d.x, o.y += d.y, o.z += d.z, o.w += d.w;
+    }
+    if (a.gate2_scale != nullptr) {
+      const float4 s = ldg4(a.gate2_scale + n);
+      const uchar4 m = __ldg(reinterpret_cast<const uchar4*>(a.gate2_mask + (size_t)r * a.ld_gate2 + n));
+      o.x = m.x ? o.x * s.x : 0.f, o.y = m.y ? o.y * s.y : 0.f, o.z = m.z ? o.z * s.z : 0.f, o.w = m.w ? o.w * s.w : 0.f;
+    }
+    *reinterpret_cast<float4*>(a.out2 + (size_t)r * a.ld2 + n) = o;
+  }
+}
+
+__device__ __forceinline__ bool row_valid(const GemmArgs& a, int r, int& clip) {
+  clip = r / a.Tp;
+  const int tp = r - clip * a.Tp;
+  return r < a.M && tp >= a.pad && tp < a.pad + a.Tv;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+template <int NT, int NSTAGE>
+__global__ void __launch_bounds__(GT, 1) gemm_tc_kernel(const GemmArgs a, const int passes) {
+  constexpr int A_BYTES = 128 * 128;                 // one tf32 part of a 128 x 32 chunk
+  constexpr int W_BYTES = NT * 128;                  // one tf32 part of an NT x 32 weight slice
+  constexpr int STAGE_BYTES = 2 * A_BYTES + 2 * W_BYTES;
+  constexpr uint32_t IDESC = idesc_tf32(128, NT);
+
+  extern __shared__ unsigned char smem_raw[];
+  unsigned char* base = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  __shared__ uint64_t bar_full[NSTAGE], bar_empty[NSTAGE], bar_done;
+  __shared__ uint32_t tmem_base_s;
+
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int ntile = blockIdx.x, m0 = blockIdx.y * 128;
+  const int kchunks = a.K >> 5, NKC = a.ntap * kchunks;
+
+  if (tid == 0) {
+    for (int s = 0; s < NSTAGE; ++s) {
+      mbar_init(&bar_full[s], GW / 32 + 1);  // 8 worker warps + the expect_tx arrival of the weight copy
+      mbar_init(&bar_empty[s], 1);
+    }
+    mbar_init(&bar_done, 1);
+    fence_barrier_init();
+  }
+  if (warp == GW / 32) tmem_alloc<NT>(&tmem_base_s);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = tmem_base_s;
+
+  if (warp == GW / 32) {
+    // ---- MMA warp ----
+    const bool leader = elect_one();
+#pragma unroll 1
+    for (int kc = 0; kc < NKC; ++kc) {
+      const int s = kc % NSTAGE;
+      mbar_wait(&bar_full[s], (uint32_t)((kc / NSTAGE) & 1));
+      tc_fence_after();
+      const uint32_t a_hi = smem_u32(base + (size_t)s * STAGE_BYTES), a_lo = a_hi + A_BYTES;
+      const uint32_t w_hi = a_lo + A_BYTES, w_lo = w_hi + W_BYTES;
+      if (leader) {
+#pragma unroll
+        for (int ks = 0; ks < 4; ++ks) {
+          const uint64_t ah = desc_sw128(a_hi + ks * 32), al = desc_sw128(a_lo + ks * 32);
+          const uint64_t bh = desc_sw128(w_hi + ks * 32), bl = desc_sw128(w_lo + ks * 32);
+          mma_tf32(tmem, ah, bh, IDESC, (kc > 0 || ks > 0) ? 1u : 0u);
+          if (passes == 3) {
+            mma_tf32(tmem, ah, bl, IDESC, 1u);
+            mma_tf32(tmem, al, bh, IDESC, 1u);
+          }
+        }
+        mma_commit(&bar_empty[s]);                    // the stage may be refilled once these MMAs have read it
+        if (kc == NKC - 1) mma_commit(&bar_done);     // accumulator complete
+      }
+      __syncwarp();
+    }
+  } else {
+    // ---- worker warps: A chunk -> registers -> tf32 hi / lo -> stage ----
+    const int c4 = tid & 7, r0 = tid >> 3;  // this thread's 16-byte column group and first row (rows r0 + 32 u)
+    // Register prefetch PF chunks ahead: one chunk's MMAs take 0.4-0.6 us, a global load ~0.8 us, so a distance of one
+    // chunk left the loop latency-bound (first version: 19 us per 128 x 128, K = 384 tile against a 4.8 us MMA floor).
+    constexpr int PF = 4;
+    float4 rv[PF][4];
+    unsigned rok[PF];
+    auto issue_loads = [&](int kc, float4 (&dst)[4], unsigned& okm) {
+      const int tap = kc / kchunks, kk = kc - tap * kchunks;
+      okm = 0;
+      if (a.im2col_T > 0) {
+        const int k = kk * 32 + c4 * 4;
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const int r = m0 + r0 + 32 * u;
+          const int rr = r < a.M ? r : 0;
+          const int clip = rr / a.Tp, l = rr - clip * a.Tp;
+          const long long idx = (long long)SINC_STRIDE * l + k;
+          const float* src = a.A + (size_t)clip * a.im2col_T;
+          float t[4];
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const bool ok = r < a.M && (k + j) < SINC_K && (idx + j) < a.im2col_T;
+            t[j] = ok ? __ldg(src + idx + j) : 0.f;  // (scalar gather: the sinc layer is 2 % of the model's MACs)
+          }
+          dst[u] = make_float4(t[0], t[1], t[2], t[3]);
+          okm |= 1u << u;
+        }
+      } else {
+        const int sh = a.shift[tap];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const int r = m0 + r0 + 32 * u + sh;
+          const bool ok = r >= 0 && r < a.M;
+          dst[u] = ldg4(a.A + (size_t)(ok ? r : 0) * a.lda + kk * 32 + c4 * 4);
+          okm |= (ok ? 1u : 0u) << u;
+        }
+      }
+    };
+#pragma unroll
+    for (int d = 0; d < PF; ++d)
+      if (d < NKC) issue_loads(d, rv[d], rok[d]);
+#pragma unroll 1
+    for (int kc0 = 0; kc0 < NKC; kc0 += PF) {
+#pragma unroll
+      for (int d = 0; d < PF; ++d) {
+        const int kc = kc0 + d;
+        if (kc < NKC) {
+          const int s = kc % NSTAGE, use = kc / NSTAGE;
+          if (use > 0) {
+            mbar_wait(&bar_empty[s], (uint32_t)((use - 1) & 1));
+            tc_fence_after();
+          }
+          unsigned char* st = base + (size_t)s * STAGE_BYTES;
+          if (tid == 0) {
+            mbar_expect_tx(&bar_full[s], 2 * W_BYTES);
+            bulk_g2s(st + 2 * A_BYTES, a.wpack + ((size_t)ntile * NKC + kc) * (2 * W_BYTES), 2 * W_BYTES, &bar_full[s]);
+          }
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            const bool ok = (rok[d] >> u) & 1u;
+            const float4 v = ok ? rv[d][u] : make_float4(0.f, 0.f, 0.f, 0.f);
+            float4 hi, lo;
+            split_rn(v.x, hi.x, lo.x);
+            split_rn(v.y, hi.y, lo.y);
+            split_rn(v.z, hi.z, lo.z);
+            split_rn(v.w, hi.w, lo.w);
+            const uint32_t off = sw128_chunk(r0 + 32 * u, c4);
+            *reinterpret_cast<float4*>(st + off) = hi;
+            *reinterpret_cast<float4*>(st + A_BYTES + off) = lo;
+          }
+          fence_proxy_async();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&bar_full[s]);
+          if (kc + PF < NKC) issue_loads(kc + PF, rv[d], rok[d]);
+        }
+      }
+    }
+
+    // ---- epilogue ----
+    mbar_wait(&bar_done, 0u);
+    tc_fence_after();
+    float* stg = reinterpret_cast<float*>(base) + (size_t)warp * (32 * 33);  // per-warp transpose tile (ring is idle now)
+    const int q = warp & 3, half = warp >> 2;
+    const int rsub = lane >> 3, cc = (lane & 7) * 4;
+    int clip_p[8];
+    unsigned valid = 0;
+#pragma unroll
+    for (int p = 0; p < 8; ++p) {
+      const int r = m0 + 32 * q + 4 * p + rsub;
+      int clip;
+      valid |= (row_valid(a, r, clip) ? 1u : 0u) << p;
+      clip_p[p] = clip;
+    }
+    const uint32_t taddr = tmem + ((uint32_t)(32 * q) << 16);
+#pragma unroll 1
+    for (int cb = 0; cb < NT / 64; ++cb) {
+      const int col0 = half * (NT / 2) + cb * 32;
+      uint32_t v0[16], v1[16];
+      tmem_ld16_issue(taddr + col0, v0);
+      tmem_ld16_issue(taddr + col0 + 16, v1);
+      tmem_ld_wait();
+#pragma unroll
+      for (int j = 0; j < 16; ++j) {
+        stg[lane * 33 + j] = __uint_as_float(v0[j]);
+        stg[lane * 33 + 16 + j] = __uint_as_float(v1[j]);
+      }
+      __syncwarp();
+#pragma unroll
+      for (int p = 0; p < 8; ++p) {
+        const int rl = 4 * p + rsub;
+        const float4 v = make_float4(stg[rl * 33 + cc], stg[rl * 33 + cc + 1], stg[rl * 33 + cc + 2], stg[rl * 33 + cc + 3]);
+        if ((valid >> p) & 1u) epi_apply(a, m0 + 32 * q + rl, clip_p[p], ntile * NT + col0 + cc, v);
+      }
+      __syncwarp();
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == GW / 32) tmem_dealloc<NT>(tmem);
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// Weight image: for N-tile j and chunk kc = tap * (K/32) + kk: [hi: NT rows x 128 B, SWIZZLE_128B][lo: same].
+__global__ void gemm_pack_kernel(GemmW w, int N, int K, int ntap, unsigned char* __restrict__ dst) {
+  const int NT = tile_n(N), kchunks = K >> 5, NKC = ntap * kchunks;
+  const long long total = (long long)N * NKC * 32;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int k = (int)(i & 31);
+    const int nl = (int)((i >> 5) % NT);
+    const long long sl = i / (32LL * NT);  // slice index = ntile * NKC + kc
+    const int kc = (int)(sl % NKC), ntile = (int)(sl / NKC);
+    const int tap = kc / kchunks, kk = kc - tap * kchunks;
+    const int n = ntile * NT + nl, kg = kk * 32 + k;
+    float v = 0.f;
+    if (n < w.n_valid && kg < w.k_valid) v = w.w[(long long)n * w.s_n + (long long)tap * w.s_tap + (long long)kg * w.s_k];
+    float hi, lo;
+    split_rn(v, hi, lo);
+    unsigned char* slice = dst + (size_t)sl * (2 * (size_t)NT * 128);
+    const uint32_t off = (uint32_t)(nl * 128 + ((((k >> 2) ^ (nl & 7)) << 4) | ((k & 3) << 2)));
+    *reinterpret_cast<float*>(slice + off) = hi;
+    *reinterpret_cast<float*>(slice + (size_t)NT * 128 + off) = lo;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// fp32 SIMT cross-check: 64 x 64 tile, 256 threads, 4 x 4 outputs per thread, K in steps of 16.
+__global__ void __launch_bounds__(256) gemm_simt_kernel(const GemmArgs a) {
+  __shared__ float As[16][64 + 4];
+  __shared__ float Ws[16][64 + 4];
+  const int tid = threadIdx.x;
+  const int n0 = blockIdx.x * 64, m0 = blockIdx.y * 64;
+  const int tx = tid & 15, ty = tid >> 4;  // outputs: rows m0 + 4 ty + i, columns n0 + 4 tx + j
+  float acc[4][4] = {};
+  const int lr = tid >> 2, lk = (tid & 3) * 4;  // loader: row / column lr of the tile, k offset lk..lk+3
+  for (int tap = 0; tap < a.ntap; ++tap) {
+    for (int k0 = 0; k0 < a.K; k0 += 16) {
+      {
+        float t[4] = {0.f, 0.f, 0.f, 0.f};
+        if (a.im2col_T > 0) {
+          const int r = m0 + lr;
+          if (r < a.M) {
+            const int clip = r / a.Tp, l = r - clip * a.Tp;
+            for (int j = 0; j < 4; ++j) {
+              const int k = k0 + lk + j;
+              const long long idx = (long long)SINC_STRIDE * l + k;
+              if (k < SINC_K && idx < a.im2col_T) t[j] = a.A[(size_t)clip * a.im2col_T + idx];
+            }
+          }
+        } else {
+          const int r = m0 + lr + a.shift[tap];
+          if (r >= 0 && r < a.M && (m0 + lr) < a.M) {
+            const float4 v = ldg4(a.A + (size_t)r * a.lda + k0 + lk);
+            t[0] = v.x, t[1] = v.y, t[2] = v.z, t[3] = v.w;
+          }
+        }
+        for (int j = 0; j < 4; ++j) As[lk + j][lr] = t[j];
+        const int n = n0 + lr;
+        for (int j = 0; j < 4; ++j) {
+          const int k = k0 + lk + j;
+          float wv = 0.f;
+          if (n < a.w.n_valid && k < a.w.k_valid)
+            wv = a.w.w[(long long)n * a.w.s_n + (long long)tap * a.w.s_tap + (long long)k * a.w.s_k];
+          Ws[lk + j][lr] = wv;
+        }
+      }
+      __syncthreads();
+#pragma unroll
+      for (int k = 0; k < 16; ++k) {
+        const float4 av = *reinterpret_cast<const float4*>(&As[k][4 * ty]);
+        const float4 wv = *reinterpret_cast<const float4*>(&Ws[k][4 * tx]);
+        const float ar[4] = {av.x, av.y, av.z, av.w}, wr[4] = {wv.x, wv.y, wv.z, wv.w};
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+#pragma unroll
+          for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(ar[i], wr[j], acc[i][j]);
+      }
+      __syncthreads();
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int r = m0 + 4 * ty + i;
+    int clip;
+    if (row_valid(a, r, clip)) epi_apply(a, r, clip, n0 + 4 * tx, make_float4(acc[i][0], acc[i][1], acc[i][2], acc[i][3]));
+  }
+}
+
+template <int NT, int NSTAGE>
+int launch_tc(const GemmArgs& a, int passes, cudaStream_t stream) {
+  constexpr size_t smem = (size_t)NSTAGE * (2 * 128 * 128 + 2 * NT * 128) + 1024;
+  static bool configured = false;
+  if (!configured) {
+    ADVB_CUDA_OK(cudaFuncSetAttribute(gemm_tc_kernel<NT, NSTAGE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    configured = true;
+  }
+  dim3 grid(a.N / NT, cdiv(a.M, 128));
+  gemm_tc_kernel<NT, NSTAGE><<<grid, GT, smem, stream>>>(a, passes);
+  ADVB_KERNEL_OK(a.tag, stream);
+  return 0;
+}
+
+}  // namespace
+
+size_t gemm_pack_bytes(int N, int K, int ntap) { return (size_t)N * ntap * K * 8; }
+
+int gemm_pack(const GemmW& w, int N, int K, int ntap, unsigned char* dst, cudaStream_t stream) {
+  ADVB_CHECK(N % 128 == 0 && K % 32 == 0 && ntap >= 1 && ntap <= 3, "unsupported GEMM weight shape");
+  const long long total = (long long)N * ntap * K;
+  gemm_pack_kernel<<<(int)std::min<long long>(cdiv64(total, 256), 148 * 16), 256, 0, stream>>>(w, N, K, ntap, dst);
+  ADVB_KERNEL_OK("gemm_pack", stream);
+  return 0;
+}
+
+int gemm_run(const GemmArgs& a, int path, int passes, cudaStream_t stream) {
+  ADVB_CHECK(a.N % 128 == 0 && a.K % 32 == 0 && a.ntap >= 1 && a.ntap <= 3 && a.M > 0, "unsupported GEMM shape");
+  ADVB_CHECK(a.im2col_T > 0 || (a.lda % 4 == 0 && (reinterpret_cast<uintptr_t>(a.A) & 15) == 0), "A operand must be 16-byte aligned");
+  if (path == 1) {
+    dim3 grid(a.N / 64, cdiv(a.M, 64));
+    gemm_simt_kernel<<<grid, 256, 0, stream>>>(a);
+    ADVB_KERNEL_OK(a.tag, stream);
+    return 0;
+  }
+  ADVB_CHECK(a.wpack != nullptr, "tcgen05 GEMM needs the packed weight image");
+  if (tile_n(a.N) == 256) return launch_tc<256, 2>(a, passes, stream);
+  return launch_tc<128, 3>(a, passes, stream);
+}
+
+}  // namespace advb

@@ -36,6 +36,7 @@ PGD_STEPS = 40
 ALPHA = 2 / 255
 A_LCNN_BYTES_PER_CLIP = 40 * 15_818_544 + 768_000  # 633.5 MB per PGD-40 clip
 A_SPECRNET_BYTES_PER_CLIP = 40 * 18_624_736 + 768_000  # SURVEY.md App. D (SpecRNet+MFCC): 745.8 MB per PGD-40 clip
+RAWNET3_FLOP_PER_CLIP_ITER = 76.5e9  # forward + input-gradient backward of one 64 000-sample clip
 METRIC = "adversarial clips/sec (PGD-40, 64k-sample audio)"
 WORKLOADS = {
     # BASELINE.json configs[1] (the config the metric is quoted on) and configs[2]
@@ -46,6 +47,12 @@ WORKLOADS = {
                      bias="fc2_gru.bias",
                      text="PGD-40 Linf eps=0.001 alpha=2/255 random_start on SpecRNet+MFCC, 64000-sample clips "
                           "(BASELINE.json configs[2])"),
+    # BASELINE.json configs[3], the PGDL2 half (AttackEnum.PGDL2: eps 0.1, alpha 0.2, steps 10), 16 clips per GPU; the path is
+    # tensor-core bound, so its roofline is FLOP/s against the measured dense bf16 peak
+    "rawnet3": dict(model="rawnet3", frontend="none", batch=16, bias="fc6.bias", attack="pgdl2",
+                    flop_per_clip=10 * RAWNET3_FLOP_PER_CLIP_ITER,
+                    text="PGDL2 eps=0.1 alpha=0.2 steps=10 random_start (AttackEnum.PGDL2) on RawNet3, 64000-sample clips, "
+                         "16 clips per GPU (BASELINE.json configs[3])"),
 }
 
 
@@ -148,6 +155,47 @@ def kernel_bytes(B, F, T):
     return out
 
 
+def rawnet3_gemm_flops(B, T):
+    """FLOPs (2 x MACs, single pass: the 3xTF32 split triples the issued MMAs, not the algorithmic work) of every GEMM
+    launch of one gradient evaluation, summed per profiler tag (csrc/rawnet3.cu)."""
+    L0 = (T - 251) // 10 + 1
+    T2, T3 = L0 // 5, L0 // 5 // 3
+    out = {}
+
+    def add(tag, rows, n, k):
+        out[tag] = out.get(tag, 0.0) + 2.0 * B * rows * n * k
+
+    add("rn_sinc_fwd", L0, 256, 251)
+    add("rn_sinc_bwd", L0, 256, 251)
+    for rows, cin in ((L0, 256), (T2, 1024), (T3, 1024)):
+        for d in ("fwd", "bwd"):
+            add("rn_conv1_" + d, rows, 1024, cin)
+            add("rn_conv3_" + d, rows, 1024, 1024)
+            add("rn_res2_" + d, rows, 128, 7 * 3 * 128)
+            if cin == 256:
+                add("rn_res_" + d, rows, 1024, cin)
+    for d in ("fwd", "bwd"):
+        add("rn_layer4_" + d, T3, 1536, 3072)
+        add("rn_att1_" + d, T3, 128, 1536)
+        add("rn_att2_" + d, T3, 1536, 128)
+    return out
+
+
+def cpu_port_rawnet3_clips_per_s(n_clips, n_steps, seed=1002):
+    """Oracle port of the reference path on the host cores: PGDL2-n_steps on n_clips RawNet3 clips, scaled to 10 steps."""
+    from oracle import attacks as oatk
+    from oracle import rawnet3 as orn
+
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    _, state = build_lcnn_state("rawnet3", "none")
+    x, y = synthetic_batch(n_clips, seed)
+    t0 = time.perf_counter()
+    oatk.pgdl2(lambda v: orn.forward(v, state), x, y, 0.1, 0.2, n_steps, start=x.clone())
+    dt = time.perf_counter() - t0
+    return n_clips / (dt * 10 / n_steps), dt, cores
+
+
 def cpu_port_clips_per_s(n_clips, n_steps, seed=1002):
     """Oracle port of the reference path on the host cores: PGD-n_steps on n_clips clips, scaled to PGD-40."""
     from oracle import attacks as oatk
@@ -169,6 +217,8 @@ def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
+    if args.workload == "rawnet3":
+        return run_reference_rawnet3(args)
     n_clips, n_steps = 8, 10
     for _ in range(args.warmup):
         cpu_port_clips_per_s(n_clips, 2)
@@ -186,6 +236,28 @@ def run_reference(args):
         "config": {"workload": "PGD-40 Linf eps=0.001 on LCNN+LFCC, 64000-sample clips (BASELINE.json configs[1])",
                    "note": "reference is pure Python/PyTorch and cannot travel to the GPU box; this arm times the oracle "
                            "port (torch CPU ops) of its path on the host cores"},
+        "cpu_baseline": {"value": value, "unit": "clips/s", "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": "clips/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }))
+
+
+def run_reference_rawnet3(args):
+    n_clips, n_steps = 4, 2
+    for _ in range(min(args.warmup, 1)):
+        cpu_port_rawnet3_clips_per_s(2, 1)
+    vals, t0 = [], time.perf_counter()
+    for _ in range(args.steps):
+        v, dt, cores = cpu_port_rawnet3_clips_per_s(n_clips, n_steps)
+        vals.append(v)
+    total = time.perf_counter() - t0
+    value = sum(vals) / len(vals)
+    sample = f"PGDL2-{n_steps} of the PGDL2-10 workload on {n_clips} clips per step, time x{10 // n_steps}"
+    print(json.dumps({
+        "impl": "reference", "metric": METRIC, "value": value, "unit": "clips/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * total / args.steps, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": WORKLOADS["rawnet3"]["text"],
+                   "note": "oracle port (torch CPU ops) of the reference path on the host cores"},
         "cpu_baseline": {"value": value, "unit": "clips/s", "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": value, "unit": "clips/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }))
@@ -212,7 +284,10 @@ def run_native(args):
     holder, state = build_lcnn_state(wl["model"], wl["frontend"])
     holder.load_state_dict(state)
     holder = holder.to(dev)
-    atk = ta.PGD(holder, eps=EPS, alpha=ALPHA, steps=PGD_STEPS, random_start=True)
+    if wl.get("attack") == "pgdl2":
+        atk = ta.PGDL2(holder, eps=0.1, alpha=0.2, steps=10, random_start=True)
+    else:
+        atk = ta.PGD(holder, eps=EPS, alpha=ALPHA, steps=PGD_STEPS, random_start=True)
     atk.set_training_mode(model_training=True, batchnorm_training=False)
     torch.manual_seed(2002 + rank)
 
@@ -282,7 +357,11 @@ def run_native(args):
         total_prof = sum(r["total_ms"] for r in prof)
         if args.kernel_times:
             json.dump(prof, open(args.kernel_times, "w"), indent=1)
-        top = prof[0]
+        if wl["model"] == "rawnet3":  # pack / fold kernels run once per call, not per iteration: not roofline candidates
+            gemm_tags = rawnet3_gemm_flops(B, T_SAMPLES)
+            top = next(r for r in prof if r["name"] in gemm_tags)
+        else:
+            top = prof[0]
         peak, peak_kind = measured_peaks()
         kb = kernel_bytes(B, 1 + T_SAMPLES // 160, T_SAMPLES)
         traffic = None
@@ -313,14 +392,34 @@ def run_native(args):
                          "peak_source": peak_kind, "avg_launch_ms": avg_ms,
                          "share_of_step": top["total_ms"] / total_prof,
                          "algorithmic_bytes_per_launch": alg},
-            "path_roofline": {"bound": "hbm", "achieved": value / world * wl["bytes_per_clip"] / 1e9, "peak": peak,
-                              "unit": "GB/s", "frac": value / world * wl["bytes_per_clip"] / 1e9 / peak,
-                              "bytes_per_clip": wl["bytes_per_clip"]},
+            "path_roofline": ({"bound": "hbm", "achieved": value / world * wl["bytes_per_clip"] / 1e9, "peak": peak,
+                               "unit": "GB/s", "frac": value / world * wl["bytes_per_clip"] / 1e9 / peak,
+                               "bytes_per_clip": wl["bytes_per_clip"]} if "bytes_per_clip" in wl else None),
             "kernel_times_ms": {r["name"]: round(r["total_ms"], 3) for r in prof[:12]},
             "attack": {"linf": linf, "clean_acc": float((pred[:, 0] == pred[:, 2]).float().mean()),
                        "adv_acc": float((pred[:, 1] == pred[:, 2]).float().mean()),
                        "flipped": int((pred[:, 0] != pred[:, 1]).sum()), "clips": int(pred.shape[0])},
         }
+        if wl["model"] == "rawnet3":
+            # tensor-bound path: FLOP/s of the dominant GEMM tag (all its launches of the 10 iterations) and of the whole
+            # path against the measured dense bf16 peak (sustained figure: the kernel is timed inside a long step)
+            pk = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json"))) if os.path.exists(
+                os.path.join(ROOT, "MEASURED_PEAKS.json")) else {}
+            tpeak = float(pk.get("bf16_tflops_sustained", 1392.4))
+            flops_tag = gemm_tags[top["name"]] * 10
+            ach = flops_tag / (top["total_ms"] * 1e-3) / 1e12
+            out["roofline"] = {"bound": "tensor", "kernel": top["name"], "achieved": ach, "peak": tpeak, "unit": "TFLOP/s",
+                               "frac": ach / tpeak, "traffic": None, "peak_source": "measured (sustained bf16)" if pk else "fallback",
+                               "avg_launch_ms": top["total_ms"] / top["count"], "share_of_step": top["total_ms"] / total_prof,
+                               "algorithmic_flops_per_launch": flops_tag / top["count"],
+                               "note": "fp32-class accuracy via 3xTF32: 3 tf32 MMAs per algorithmic product"}
+            pach = value / world * wl["flop_per_clip"] / 1e12
+            out["path_roofline"] = {"bound": "tensor", "achieved": pach, "peak": tpeak, "unit": "TFLOP/s", "frac": pach / tpeak,
+                                    "flop_per_clip": wl["flop_per_clip"]}
+            if world == 1 and not args.no_cpu_baseline:
+                v, dt, cores = cpu_port_rawnet3_clips_per_s(4, 2)
+                out["cpu_baseline"] = {"value": v, "unit": "clips/s", "cores": cores, "kind": "port",
+                                       "sample": f"oracle port, PGDL2-2 of the PGDL2-10 workload on 4 clips ({dt:.1f} s), time x5"}
         if world == 1 and not args.no_cpu_baseline and args.workload == "lcnn":
             v, dt, cores = cpu_port_clips_per_s(16, 10)
             out["cpu_baseline"] = {"value": v, "unit": "clips/s", "cores": cores, "kind": "port",
@@ -340,7 +439,7 @@ def main():
     ap.add_argument("--impl", default="native", choices=["native", "reference"])
     ap.add_argument("--batch", type=int, default=0, help="clips per GPU (default: the workload's BASELINE.json batch)")
     ap.add_argument("--workload", default="lcnn", choices=sorted(WORKLOADS),
-                    help="lcnn = BASELINE.json configs[1] (the headline), specrnet = configs[2]")
+                    help="lcnn = BASELINE.json configs[1] (the headline), specrnet = configs[2], rawnet3 = configs[3] (PGDL2)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--kernel-times", default=None, help="write the full per-kernel timing table of one call (JSON)")
     args = ap.parse_args()

@@ -66,16 +66,15 @@ def bottle2neck(x, state, p, dilation, pool, taps=None):
     return (out + state[p + ".afms.alpha"]) * y.unsqueeze(2)
 
 
-def forward(x, state, taps=None):
-    """waveform (B,T) -> logit (B,1).  rawnet3.py:73-137."""
+def preprocess(x, state):
+    """PreEmphasis (rawnet3.py:151-158) + InstanceNorm1d(1, eps=1e-4, affine) (:24-26): (B,T) -> (B,1,T)."""
     v = x.unsqueeze(1)
     v = F.conv1d(F.pad(v, (1, 0), "reflect"), state["preprocess.0.flipped_filter"])
-    v = F.instance_norm(v, weight=state["preprocess.1.weight"], bias=state["preprocess.1.bias"], eps=1e-4)
-    if taps is not None:
-        taps["pre"] = v
-    s = F.conv1d(v, sinc_filters(state), stride=10)
-    if taps is not None:
-        taps["sinc_raw"] = s
+    return F.instance_norm(v, weight=state["preprocess.1.weight"], bias=state["preprocess.1.bias"], eps=1e-4)
+
+
+def tail(s, state, taps=None):
+    """Everything after the sinc convolution: raw filter outputs (B,256,L) -> logit (B,1).  rawnet3.py:80-137."""
     v = torch.log(torch.abs(s) + 1e-6)
     v = v - v.mean(dim=-1, keepdim=True)
     if taps is not None:
@@ -100,3 +99,14 @@ def forward(x, state, taps=None):
     if taps is not None:
         taps["pooled"] = pooled
     return bn(pooled, state, "bn5") @ state["fc6.weight"].t() + state["fc6.bias"]
+
+
+def forward(x, state, taps=None):
+    """waveform (B,T) -> logit (B,1).  rawnet3.py:73-137."""
+    v = preprocess(x, state)
+    if taps is not None:
+        taps["pre"] = v
+    s = F.conv1d(v, sinc_filters(state), stride=10)
+    if taps is not None:
+        taps["sinc_raw"] = s
+    return tail(s, state, taps)
