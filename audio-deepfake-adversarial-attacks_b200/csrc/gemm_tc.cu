@@ -17,6 +17,8 @@
 #include "gemm.cuh"
 #include "tc_common.cuh"
 
+#include <algorithm>
+
 namespace advb {
 
 namespace {
@@ -273,6 +275,228 @@ __global__ void __launch_bounds__(GT, 1) gemm_tc_kernel(const GemmArgs a, const 
 }
 
 // ---------------------------------------------------------------------------------------------------------------
+// Persistent, warp-specialised version (the default schedule): one CTA per SM walks the output tiles (N tile fastest),
+// the stage ring and the register prefetch run straight across tile boundaries, and two TMEM accumulators let the MMAs
+// of tile i+1 overlap the epilogue of tile i.  Roles: warps 0-7 fill A (+ thread 0 the weight TMA), warp 8 issues the
+// MMAs, warps 9-16 run the epilogue (two per TMEM lane quarter, each half of the tile's columns).
+// Hand-offs: bar_full / bar_empty per ring stage as above; acc_full[2] (tcgen05.commit after a tile's last MMA ->
+// epilogue warps), acc_empty[2] (8 epilogue warps, as soon as their last tcgen05.ld of the tile has landed -> MMA warp).
+constexpr int PT = GW + 32 + 256;  // 544 threads
+
+template <int NT, int NSTAGE>
+__global__ void __launch_bounds__(PT, 1) gemm_tc_persistent_kernel(const GemmArgs a, const int passes, const int n_tiles) {
+  constexpr int A_BYTES = 128 * 128;
+  constexpr int W_BYTES = NT * 128;
+  constexpr int STAGE_BYTES = 2 * A_BYTES + 2 * W_BYTES;
+  constexpr int TM_COLS = 2 * NT;  // two accumulators
+  constexpr uint32_t IDESC = idesc_tf32(128, NT);
+
+  extern __shared__ unsigned char smem_raw[];
+  unsigned char* base = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  float* stg_all = reinterpret_cast<float*>(base + (size_t)NSTAGE * STAGE_BYTES);  // 8 x (32 x 33) floats
+  __shared__ uint64_t bar_full[NSTAGE], bar_empty[NSTAGE], acc_full[2], acc_empty[2];
+  __shared__ uint32_t tmem_base_s;
+
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int ntn = a.N / NT;
+  const int kchunks = a.K >> 5, NKC = a.ntap * kchunks;
+
+  if (tid == 0) {
+    for (int s = 0; s < NSTAGE; ++s) {
+      mbar_init(&bar_full[s], GW / 32 + 1);
+      mbar_init(&bar_empty[s], 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&acc_full[i], 1);
+      mbar_init(&acc_empty[i], 8);
+    }
+    fence_barrier_init();
+  }
+  if (warp == GW / 32) tmem_alloc<TM_COLS>(&tmem_base_s);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = tmem_base_s;
+
+  if (warp == GW / 32) {
+    // ---- MMA warp ----
+    const bool leader = elect_one();
+    int g = 0, it = 0;
+#pragma unroll 1
+    for (int t = blockIdx.x; t < n_tiles; t += gridDim.x, ++it) {
+      const int buf = it & 1;
+      if (it >= 2) {  // the epilogue of the tile that used this accumulator two tiles ago has drained it
+        mbar_wait(&acc_empty[buf], (uint32_t)(((it >> 1) - 1) & 1));
+        tc_fence_after();
+      }
+      const uint32_t dcol = tmem + buf * NT;
+#pragma unroll 1
+      for (int kc = 0; kc < NKC; ++kc, ++g) {
+        const int s = g % NSTAGE;
+        mbar_wait(&bar_full[s], (uint32_t)((g / NSTAGE) & 1));
+        tc_fence_after();
+        const uint32_t a_hi = smem_u32(base + (size_t)s * STAGE_BYTES), a_lo = a_hi + A_BYTES;
+        const uint32_t w_hi = a_lo + A_BYTES, w_lo = w_hi + W_BYTES;
+        if (leader) {
+#pragma unroll
+          for (int ks = 0; ks < 4; ++ks) {
+            const uint64_t ah = desc_sw128(a_hi + ks * 32), al = desc_sw128(a_lo + ks * 32);
+            const uint64_t bh = desc_sw128(w_hi + ks * 32), bl = desc_sw128(w_lo + ks * 32);
+            mma_tf32(dcol, ah, bh, IDESC, (kc > 0 || ks > 0) ? 1u : 0u);
+            if (passes == 3) {
+              mma_tf32(dcol, ah, bl, IDESC, 1u);
+              mma_tf32(dcol, al, bh, IDESC, 1u);
+            }
+          }
+          mma_commit(&bar_empty[s]);
+          if (kc == NKC - 1) mma_commit(&acc_full[buf]);
+        }
+        __syncwarp();
+      }
+    }
+  } else if (warp < GW / 32) {
+    // ---- fill warps ----
+    const int c4 = tid & 7, r0 = tid >> 3;
+    constexpr int PF = 4;
+    float4 rv[PF][4];
+    unsigned rok[PF];
+    auto issue_loads = [&](int m0, int kc, float4 (&dst)[4], unsigned& okm) {
+      const int tap = kc / kchunks, kk = kc - tap * kchunks;
+      okm = 0;
+      if (a.im2col_T > 0) {
+        const int k = kk * 32 + c4 * 4;
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const int r = m0 + r0 + 32 * u;
+          const int rr = r < a.M ? r : 0;
+          const int clip = rr / a.Tp, l = rr - clip * a.Tp;
+          const long long idx = (long long)SINC_STRIDE * l + k;
+          const float* src = a.A + (size_t)clip * a.im2col_T;
+          float tt[4];
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const bool ok = r < a.M && (k + j) < SINC_K && (idx + j) < a.im2col_T;
+            tt[j] = ok ? __ldg(src + idx + j) : 0.f;
+          }
+          dst[u] = make_float4(tt[0], tt[1], tt[2], tt[3]);
+          okm |= 1u << u;
+        }
+      } else {
+        const int sh = a.shift[tap];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const int r = m0 + r0 + 32 * u + sh;
+          const bool ok = r >= 0 && r < a.M;
+          dst[u] = ldg4(a.A + (size_t)(ok ? r : 0) * a.lda + kk * 32 + c4 * 4);
+          okm |= (ok ? 1u : 0u) << u;
+        }
+      }
+    };
+    // prefetch cursor (tile, chunk) runs PF chunks ahead of the store cursor, across tile boundaries
+    int pt = blockIdx.x, pk = 0;
+    auto prefetch_next = [&](float4 (&dst)[4], unsigned& okm) {
+      if (pt < n_tiles) {
+        issue_loads((pt / ntn) * 128, pk, dst, okm);
+        if (++pk == NKC) pk = 0, pt += gridDim.x;
+      }
+    };
+#pragma unroll
+    for (int d = 0; d < PF; ++d) prefetch_next(rv[d], rok[d]);
+    int t = blockIdx.x, kc = 0, g = 0;
+#pragma unroll 1
+    while (t < n_tiles) {
+#pragma unroll
+      for (int d = 0; d < PF; ++d) {
+        if (t < n_tiles) {
+          const int s = g % NSTAGE, use = g / NSTAGE;
+          if (use > 0) {
+            mbar_wait(&bar_empty[s], (uint32_t)((use - 1) & 1));
+            tc_fence_after();
+          }
+          unsigned char* st = base + (size_t)s * STAGE_BYTES;
+          if (tid == 0) {
+            mbar_expect_tx(&bar_full[s], 2 * W_BYTES);
+            bulk_g2s(st + 2 * A_BYTES, a.wpack + ((size_t)(t % ntn) * NKC + kc) * (2 * W_BYTES), 2 * W_BYTES, &bar_full[s]);
+          }
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            const bool ok = (rok[d] >> u) & 1u;
+            const float4 v = ok ? rv[d][u] : make_float4(0.f, 0.f, 0.f, 0.f);
+            float4 hi, lo;
+            split_rn(v.x, hi.x, lo.x);
+            split_rn(v.y, hi.y, lo.y);
+            split_rn(v.z, hi.z, lo.z);
+            split_rn(v.w, hi.w, lo.w);
+            const uint32_t off = sw128_chunk(r0 + 32 * u, c4);
+            *reinterpret_cast<float4*>(st + off) = hi;
+            *reinterpret_cast<float4*>(st + A_BYTES + off) = lo;
+          }
+          fence_proxy_async();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&bar_full[s]);
+          prefetch_next(rv[d], rok[d]);
+          ++g;
+          if (++kc == NKC) kc = 0, t += gridDim.x;
+        }
+      }
+    }
+  } else {
+    // ---- epilogue warps ----
+    const int ew = warp - (GW / 32 + 1);   // 0..7
+    const int q = warp & 3, half = ew >> 2;  // TMEM lane quarter is fixed by the hardware warp id
+    float* stg = stg_all + (size_t)ew * (32 * 33);
+    const int rsub = lane >> 3, cc = (lane & 7) * 4;
+    int it = 0;
+#pragma unroll 1
+    for (int t = blockIdx.x; t < n_tiles; t += gridDim.x, ++it) {
+      const int buf = it & 1;
+      const int m0 = (t / ntn) * 128, ntile = t % ntn;
+      int clip_p[8];
+      unsigned valid = 0;
+#pragma unroll
+      for (int p = 0; p < 8; ++p) {
+        const int r = m0 + 32 * q + 4 * p + rsub;
+        int clip;
+        valid |= (row_valid(a, r, clip) ? 1u : 0u) << p;
+        clip_p[p] = clip;
+      }
+      mbar_wait(&acc_full[buf], (uint32_t)((it >> 1) & 1));
+      tc_fence_after();
+      const uint32_t taddr = tmem + ((uint32_t)(32 * q) << 16) + buf * NT;
+#pragma unroll 1
+      for (int cb = 0; cb < NT / 64; ++cb) {
+        const int col0 = half * (NT / 2) + cb * 32;
+        uint32_t v0[16], v1[16];
+        tmem_ld16_issue(taddr + col0, v0);
+        tmem_ld16_issue(taddr + col0 + 16, v1);
+        tmem_ld_wait();
+        if (cb == NT / 64 - 1) {  // accumulator drained: hand it back before the global stores of this block
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&acc_empty[buf]);
+        }
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+          stg[lane * 33 + j] = __uint_as_float(v0[j]);
+          stg[lane * 33 + 16 + j] = __uint_as_float(v1[j]);
+        }
+        __syncwarp();
+#pragma unroll
+        for (int p = 0; p < 8; ++p) {
+          const int rl = 4 * p + rsub;
+          const float4 v = make_float4(stg[rl * 33 + cc], stg[rl * 33 + cc + 1], stg[rl * 33 + cc + 2], stg[rl * 33 + cc + 3]);
+          if ((valid >> p) & 1u) epi_apply(a, m0 + 32 * q + rl, clip_p[p], ntile * NT + col0 + cc, v);
+        }
+        __syncwarp();
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == GW / 32) tmem_dealloc<TM_COLS>(tmem);
+}
+
+// ---------------------------------------------------------------------------------------------------------------
 // Weight image: for N-tile j and chunk kc = tap * (K/32) + kk: [hi: NT rows x 128 B, SWIZZLE_128B][lo: same].
 __global__ void gemm_pack_kernel(GemmW w, int N, int K, int ntap, unsigned char* __restrict__ dst) {
   const int NT = tile_n(N), kchunks = K >> 5, NKC = ntap * kchunks;
@@ -361,13 +585,25 @@ __global__ void __launch_bounds__(256) gemm_simt_kernel(const GemmArgs a) {
 template <int NT, int NSTAGE>
 int launch_tc(const GemmArgs& a, int passes, cudaStream_t stream) {
   constexpr size_t smem = (size_t)NSTAGE * (2 * 128 * 128 + 2 * NT * 128) + 1024;
-  static bool configured = false;
-  if (!configured) {
-    ADVB_CUDA_OK(cudaFuncSetAttribute(gemm_tc_kernel<NT, NSTAGE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    configured = true;
-  }
+  ADVB_CUDA_OK(cudaFuncSetAttribute(gemm_tc_kernel<NT, NSTAGE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   dim3 grid(a.N / NT, cdiv(a.M, 128));
   gemm_tc_kernel<NT, NSTAGE><<<grid, GT, smem, stream>>>(a, passes);
+  ADVB_KERNEL_OK(a.tag, stream);
+  return 0;
+}
+
+template <int NT, int NSTAGE>
+int launch_tc_persistent(const GemmArgs& a, int passes, cudaStream_t stream) {
+  constexpr size_t smem = (size_t)NSTAGE * (2 * 128 * 128 + 2 * NT * 128) + 8 * 32 * 33 * sizeof(float) + 1024;
+  ADVB_CUDA_OK(cudaFuncSetAttribute(gemm_tc_persistent_kernel<NT, NSTAGE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  static int n_sm = 0;
+  if (n_sm == 0) {
+    int dev = 0;
+    ADVB_CUDA_OK(cudaGetDevice(&dev));
+    ADVB_CUDA_OK(cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev));
+  }
+  const int n_tiles = (a.N / NT) * cdiv(a.M, 128);
+  gemm_tc_persistent_kernel<NT, NSTAGE><<<std::min(n_tiles, n_sm), PT, smem, stream>>>(a, passes, n_tiles);
   ADVB_KERNEL_OK(a.tag, stream);
   return 0;
 }
@@ -394,8 +630,12 @@ int gemm_run(const GemmArgs& a, int path, int passes, cudaStream_t stream) {
     return 0;
   }
   ADVB_CHECK(a.wpack != nullptr, "tcgen05 GEMM needs the packed weight image");
-  if (tile_n(a.N) == 256) return launch_tc<256, 2>(a, passes, stream);
-  return launch_tc<128, 3>(a, passes, stream);
+  if (g_conv_sched == 1) {  // one tile per CTA: the first tcgen05 version, kept as an in-process cross-check
+    if (tile_n(a.N) == 256) return launch_tc<256, 2>(a, passes, stream);
+    return launch_tc<128, 3>(a, passes, stream);
+  }
+  if (tile_n(a.N) == 256) return launch_tc_persistent<256, 2>(a, passes, stream);
+  return launch_tc_persistent<128, 3>(a, passes, stream);
 }
 
 }  // namespace advb
