@@ -17,6 +17,8 @@
 #include "gemm.cuh"
 #include "tc_common.cuh"
 
+#include <stdlib.h>
+
 #include <algorithm>
 
 namespace advb {
@@ -33,6 +35,14 @@ __host__ __device__ constexpr int tile_n(int N) { return (N % 256 == 0) ? 256 : 
 
 __device__ __forceinline__ float4 ldg4(const float* p) { return __ldg(reinterpret_cast<const float4*>(p)); }
 
+// Per-chunk hand-offs (ring stage full / empty) are waited for with a bare try_wait loop: try_wait already suspends the
+// thread in hardware for a bounded time, and the __nanosleep back-off of tc::mbar_wait (right for the once-per-tile waits of
+// the convolution kernels) adds a sleep quantum to EVERY link of the fill -> MMA -> fill chain.
+__device__ __forceinline__ void wait_hot(uint64_t* bar, uint32_t parity) {
+  while (!mbar_try(bar, parity)) {
+  }
+}
+
 // x = hi + lo with BOTH parts rounded to nearest tf32.  kind::tf32 truncates its inputs (tc_common.cuh); an fp32 `lo`
 // (13 significant bits) would be truncated towards zero - a biased 2^-21 |x| error that adds up linearly over RawNet3's
 // 1024..3072-long contractions (measured: 4e-6 systematic logit offset).  Rounded, the residual is unbiased and 2x smaller.
@@ -44,10 +54,40 @@ __device__ __forceinline__ void split_rn(float x, float& hi, float& lo) {
   lo = __uint_as_float(l);
 }
 
-// The fused epilogue on 4 consecutive columns n..n+3 of valid row r (clip = r / Tp).
-__device__ __forceinline__ void epi_apply(const GemmArgs& a, int r, int clip, int n, float4 v) {
+// The fused epilogue on 4 consecutive columns n..n+3 of valid row r (clip = r / Tp), split in three steps so that a caller
+// can issue the global loads of several rows back to back BEFORE the first store: written as one function per row, the
+// possible aliasing of `out` with `add` / `add2` pins every load behind the previous row's stores and each row pays 3-5
+// serial global-load latencies (measured: 43 us per 128 x 128 tile of the Res2 chain against a 4.7 us MMA floor).
+struct EpiCol {  // per-column operands: the same for every row a thread handles
+  float4 bias, bn_s, bn_t, gs, gs2;
+};
+struct EpiRow {  // per-row operands (`add` and `add2` are never used by the same GEMM: one register set serves both)
+  float4 addv;
+  uchar4 gm, gm2;
+};
+__device__ __forceinline__ EpiCol epi_load_col(const GemmArgs& a, int n) {
+  EpiCol c;
+  c.bias = c.bn_s = c.bn_t = c.gs = c.gs2 = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (a.bias != nullptr && !a.bias_per_clip) c.bias = ldg4(a.bias + n);
+  if (a.bn_scale != nullptr) c.bn_s = ldg4(a.bn_scale + n), c.bn_t = ldg4(a.bn_shift + n);
+  if (a.gate_scale != nullptr) c.gs = ldg4(a.gate_scale + n);
+  if (a.gate2_scale != nullptr) c.gs2 = ldg4(a.gate2_scale + n);
+  return c;
+}
+__device__ __forceinline__ EpiRow epi_load_row(const GemmArgs& a, int r, int n) {
+  EpiRow w;
+  w.addv = make_float4(0.f, 0.f, 0.f, 0.f);
+  w.gm = w.gm2 = make_uchar4(0, 0, 0, 0);
+  if (a.add != nullptr) w.addv = *reinterpret_cast<const float4*>(a.add + (size_t)r * a.ld_add + n);  // may alias out: plain load
+  else if (a.add2 != nullptr) w.addv = ldg4(a.add2 + (size_t)r * a.ld_add2 + n);
+  if (a.gate_scale != nullptr) w.gm = __ldg(reinterpret_cast<const uchar4*>(a.gate_mask + (size_t)r * a.ld_gate + n));
+  if (a.gate2_scale != nullptr) w.gm2 = __ldg(reinterpret_cast<const uchar4*>(a.gate2_mask + (size_t)r * a.ld_gate2 + n));
+  return w;
+}
+__device__ __forceinline__ void epi_finish(const GemmArgs& a, int r, int clip, int n, float4 v, const EpiCol& c, const EpiRow& w) {
   if (a.bias != nullptr) {
-    const float4 b = ldg4(a.bias + (a.bias_per_clip ? (size_t)clip * a.N : (size_t)0) + n);
+    // (per-clip bias: the attention layer only, 128 floats per clip - read here, it stays in L1)
+    const float4 b = a.bias_per_clip ? ldg4(a.bias + (size_t)clip * a.N + n) : c.bias;
     v.x += b.x, v.y += b.y, v.z += b.z, v.w += b.w;
   }
   if (a.relu) {
@@ -57,35 +97,63 @@ __device__ __forceinline__ void epi_apply(const GemmArgs& a, int r, int clip, in
     v.x = fmaxf(v.x, 0.f), v.y = fmaxf(v.y, 0.f), v.z = fmaxf(v.z, 0.f), v.w = fmaxf(v.w, 0.f);
   }
   if (a.bn_scale != nullptr) {
-    const float4 s = ldg4(a.bn_scale + n), t = ldg4(a.bn_shift + n);
-    v.x = fmaf(v.x, s.x, t.x), v.y = fmaf(v.y, s.y, t.y), v.z = fmaf(v.z, s.z, t.z), v.w = fmaf(v.w, s.w, t.w);
+    v.x = fmaf(v.x, c.bn_s.x, c.bn_t.x), v.y = fmaf(v.y, c.bn_s.y, c.bn_t.y);
+    v.z = fmaf(v.z, c.bn_s.z, c.bn_t.z), v.w = fmaf(v.w, c.bn_s.w, c.bn_t.w);
   }
-  if (a.add != nullptr) {
-    const float4 d = *reinterpret_cast<const float4*>(a.add + (size_t)r * a.ld_add + n);  // may alias out: plain load
-    v.x += d.x, v.y += d.y, v.z += d.z, v.w += d.w;
-  }
+  if (a.add != nullptr) v.x += w.addv.x, v.y += w.addv.y, v.z += w.addv.z, v.w += w.addv.w;
   if (a.out != nullptr) {
     float4 o = v;
-    if (a.gate_scale != nullptr) {
-      const float4 s = ldg4(a.gate_scale + n);
-      const uchar4 m = __ldg(reinterpret_cast<const uchar4*>(a.gate_mask + (size_t)r * a.ld_gate + n));
-      o.x = m.x ? v.x * s.x : 0.f, o.y = m.y ? v.y * s.y : 0.f, o.z = m.z ? v.z * s.z : 0.f, o.w = m.w ? v.w * s.w : 0.f;
-    }
+    if (a.gate_scale != nullptr)
+      o.x = w.gm.x ? v.x * c.gs.x : 0.f, o.y = w.gm.y ? v.y * c.gs.y : 0.f, o.z = w.gm.z ? v.z * c.gs.z : 0.f,
+      o.w = w.gm.w ? v.w * c.gs.w : 0.f;
     *reinterpret_cast<float4*>(a.out + (size_t)r * a.ldc + n) = o;
   }
   if (a.out2 != nullptr) {
     float4 o = v;
-    if (a.add2 != nullptr) {
-      const float4 d = ldg4(a.add2 + (size_t)r * a.ld_add2 + n);
-      o.x += d.x, o.y += d.y, o.z += d.z, o.w += d.w;
-    }
-    if (a.gate2_scale != nullptr) {
-      const float4 s = ldg4(a.gate2_scale + n);
-      const uchar4 m = __ldg(reinterpret_cast<const uchar4*>(a.gate2_mask + (size_t)r * a.ld_gate2 + n));
-      o.x = m.x ? o.x * s.x : 0.f, o.y = m.y ? o.y * s.y : 0.f, o.z = m.z ? o.z * s.z : 0.f, o.w = m.w ? o.w * s.w : 0.f;
-    }
+    if (a.add2 != nullptr) o.x += w.addv.x, o.y += w.addv.y, o.z += w.addv.z, o.w += w.addv.w;
+    if (a.gate2_scale != nullptr)
+      o.x = w.gm2.x ? o.x * c.gs2.x : 0.f, o.y = w.gm2.y ? o.y * c.gs2.y : 0.f, o.z = w.gm2.z ? o.z * c.gs2.z : 0.f,
+      o.w = w.gm2.w ? o.w * c.gs2.w : 0.f;
     *reinterpret_cast<float4*>(a.out2 + (size_t)r * a.ld2 + n) = o;
   }
+}
+__device__ __forceinline__ void epi_apply(const GemmArgs& a, int r, int clip, int n, float4 v) {
+  const EpiCol c = epi_load_col(a, n);
+  const EpiRow w = epi_load_row(a, r, n);
+  epi_finish(a, r, clip, n, v, c, w);
+}
+
+// One 32-row x 32-column block of a tile: the caller fetches every global operand of the block's 8 rows per thread
+// (epi_prefetch) BEFORE waiting for tcgen05.ld; epi_block then transposes the TMEM values (thread = row) through the warp's
+// private staging tile and finishes with thread = (row 4 p + rsub, columns cc..cc+3).
+struct EpiPre {
+  EpiCol col;
+  EpiRow row[8];
+};
+__device__ __forceinline__ void epi_prefetch(const GemmArgs& a, int rbase, int rsub, unsigned valid, int n, EpiPre& pre) {
+  pre.col = epi_load_col(a, n);
+#pragma unroll
+  for (int p = 0; p < 8; ++p) {
+    const int r = ((valid >> p) & 1u) ? rbase + 4 * p + rsub : rbase;  // invalid rows: any in-range address, result unused
+    pre.row[p] = epi_load_row(a, r < a.M ? r : 0, n);
+  }
+}
+__device__ __forceinline__ void epi_block(const GemmArgs& a, float* stg, int lane, int rbase, int rsub, int cc, unsigned valid,
+                                          const int (&clip_p)[8], int n, const uint32_t (&v0)[16], const uint32_t (&v1)[16],
+                                          const EpiPre& pre) {
+#pragma unroll
+  for (int j = 0; j < 16; ++j) {
+    stg[lane * 33 + j] = __uint_as_float(v0[j]);
+    stg[lane * 33 + 16 + j] = __uint_as_float(v1[j]);
+  }
+  __syncwarp();
+#pragma unroll
+  for (int p = 0; p < 8; ++p) {
+    const int rl = 4 * p + rsub;
+    const float4 v = make_float4(stg[rl * 33 + cc], stg[rl * 33 + cc + 1], stg[rl * 33 + cc + 2], stg[rl * 33 + cc + 3]);
+    if ((valid >> p) & 1u) epi_finish(a, rbase + rl, clip_p[p], n, v, pre.col, pre.row[p]);
+  }
+  __syncwarp();
 }
 
 __device__ __forceinline__ bool row_valid(const GemmArgs& a, int r, int& clip) {
@@ -131,7 +199,7 @@ __global__ void __launch_bounds__(GT, 1) gemm_tc_kernel(const GemmArgs a, const 
 #pragma unroll 1
     for (int kc = 0; kc < NKC; ++kc) {
       const int s = kc % NSTAGE;
-      mbar_wait(&bar_full[s], (uint32_t)((kc / NSTAGE) & 1));
+      wait_hot(&bar_full[s], (uint32_t)((kc / NSTAGE) & 1));
       tc_fence_after();
       const uint32_t a_hi = smem_u32(base + (size_t)s * STAGE_BYTES), a_lo = a_hi + A_BYTES;
       const uint32_t w_hi = a_lo + A_BYTES, w_lo = w_hi + W_BYTES;
@@ -202,7 +270,7 @@ __global__ void __launch_bounds__(GT, 1) gemm_tc_kernel(const GemmArgs a, const 
         if (kc < NKC) {
           const int s = kc % NSTAGE, use = kc / NSTAGE;
           if (use > 0) {
-            mbar_wait(&bar_empty[s], (uint32_t)((use - 1) & 1));
+            wait_hot(&bar_empty[s], (uint32_t)((use - 1) & 1));
             tc_fence_after();
           }
           unsigned char* st = base + (size_t)s * STAGE_BYTES;
@@ -251,22 +319,12 @@ __global__ void __launch_bounds__(GT, 1) gemm_tc_kernel(const GemmArgs a, const 
     for (int cb = 0; cb < NT / 64; ++cb) {
       const int col0 = half * (NT / 2) + cb * 32;
       uint32_t v0[16], v1[16];
+      EpiPre pre;
+      epi_prefetch(a, m0 + 32 * q, rsub, valid, ntile * NT + col0 + cc, pre);
       tmem_ld16_issue(taddr + col0, v0);
       tmem_ld16_issue(taddr + col0 + 16, v1);
       tmem_ld_wait();
-#pragma unroll
-      for (int j = 0; j < 16; ++j) {
-        stg[lane * 33 + j] = __uint_as_float(v0[j]);
-        stg[lane * 33 + 16 + j] = __uint_as_float(v1[j]);
-      }
-      __syncwarp();
-#pragma unroll
-      for (int p = 0; p < 8; ++p) {
-        const int rl = 4 * p + rsub;
-        const float4 v = make_float4(stg[rl * 33 + cc], stg[rl * 33 + cc + 1], stg[rl * 33 + cc + 2], stg[rl * 33 + cc + 3]);
-        if ((valid >> p) & 1u) epi_apply(a, m0 + 32 * q + rl, clip_p[p], ntile * NT + col0 + cc, v);
-      }
-      __syncwarp();
+      epi_block(a, stg, lane, m0 + 32 * q, rsub, cc, valid, clip_p, ntile * NT + col0 + cc, v0, v1, pre);
     }
   }
   tc_fence_before();
@@ -278,13 +336,46 @@ __global__ void __launch_bounds__(GT, 1) gemm_tc_kernel(const GemmArgs a, const 
 // Persistent, warp-specialised version (the default schedule): one CTA per SM walks the output tiles (N tile fastest),
 // the stage ring and the register prefetch run straight across tile boundaries, and two TMEM accumulators let the MMAs
 // of tile i+1 overlap the epilogue of tile i.  Roles: warps 0-7 fill A (+ thread 0 the weight TMA), warp 8 issues the
-// MMAs, warps 9-16 run the epilogue (two per TMEM lane quarter, each half of the tile's columns).
+// MMAs, warps 9-12 run the epilogue (one per TMEM lane quarter, all of the tile's columns).
 // Hand-offs: bar_full / bar_empty per ring stage as above; acc_full[2] (tcgen05.commit after a tile's last MMA ->
-// epilogue warps), acc_empty[2] (8 epilogue warps, as soon as their last tcgen05.ld of the tile has landed -> MMA warp).
-constexpr int PT = GW + 32 + 256;  // 544 threads
+// epilogue warps), acc_empty[2] (4 epilogue warps, as soon as their last tcgen05.ld of the tile has landed -> MMA warp).
+// ---- thread-block cluster helpers (weight multicast) ----
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// 1-D TMA bulk copy global -> the SAME shared-memory offset of every CTA in `mask`; each destination CTA's mbarrier (same
+// offset) receives complete_tx for the bytes it got.
+__device__ __forceinline__ void bulk_g2s_multicast(void* dst_smem, const void* src_gmem, uint32_t bytes, uint64_t* bar, uint16_t mask) {
+  asm volatile(
+      "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1], %2, [%3], %4;" ::"r"(
+          smem_u32(dst_smem)),
+      "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar)), "h"(mask)
+      : "memory");
+}
+// tcgen05.commit that arrives on the mbarrier at this offset in every CTA of `mask`
+__device__ __forceinline__ void mma_commit_multicast(uint64_t* bar, uint16_t mask) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(
+                   smem_u32(bar)),
+               "h"(mask)
+               : "memory");
+}
 
-template <int NT, int NSTAGE>
-__global__ void __launch_bounds__(PT, 1) gemm_tc_persistent_kernel(const GemmArgs a, const int passes, const int n_tiles) {
+// CL = cluster size along M (1, 2 or 4).  The CTAs of a cluster work on CL consecutive M tiles of the SAME N tile in
+// lock-step, so every weight slice is fetched from L2 once per cluster: CTA r loads the r-th 1/CL of the slice and
+// multicasts it into all CL shared memories.  Without it the kernel is bound by L2 -> SM traffic, not by the tensor pipe:
+// a 128 x 256 tile streams 64 KB of weights + 16 KB of activations per 32-wide K chunk, 8.5 TB/s over 148 SMs at the
+// measured 1.4 us per chunk (MMA time per chunk: 0.6 us).  A ring stage is released only when all CL CTAs have consumed
+// it (multicast tcgen05.commit onto every CTA's bar_empty, count CL).
+// EPW = epilogue warps: 4 (one per TMEM lane quarter; 13 warps => 128 registers per thread) or 8 (two per quarter, each half of
+// the columns; 17 warps put 5 on one SM sub-partition and cap every thread at 96 registers).
+template <int NT, int NSTAGE, int EPW, int CL>
+__global__ void __launch_bounds__(GW + 32 + 32 * EPW, 1) gemm_tc_persistent_kernel(const GemmArgs a, const int passes, const int n_items) {
+  // work item w = (M group of CL tiles, N tile), N tile fastest; cluster c takes items c, c + n_clusters, ...
   constexpr int A_BYTES = 128 * 128;
   constexpr int W_BYTES = NT * 128;
   constexpr int STAGE_BYTES = 2 * A_BYTES + 2 * W_BYTES;
@@ -293,28 +384,32 @@ __global__ void __launch_bounds__(PT, 1) gemm_tc_persistent_kernel(const GemmArg
 
   extern __shared__ unsigned char smem_raw[];
   unsigned char* base = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  float* stg_all = reinterpret_cast<float*>(base + (size_t)NSTAGE * STAGE_BYTES);  // 8 x (32 x 33) floats
+  float* stg_all = reinterpret_cast<float*>(base + (size_t)NSTAGE * STAGE_BYTES);  // EPW x (32 x 33) floats
   __shared__ uint64_t bar_full[NSTAGE], bar_empty[NSTAGE], acc_full[2], acc_empty[2];
   __shared__ uint32_t tmem_base_s;
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int ntn = a.N / NT;
   const int kchunks = a.K >> 5, NKC = a.ntap * kchunks;
+  const int crank = CL > 1 ? (int)cluster_ctarank() : 0;
+  const int item0 = blockIdx.x / CL, item_step = gridDim.x / CL;
+  constexpr uint16_t CMASK = (uint16_t)((1u << CL) - 1u);
 
   if (tid == 0) {
     for (int s = 0; s < NSTAGE; ++s) {
       mbar_init(&bar_full[s], GW / 32 + 1);
-      mbar_init(&bar_empty[s], 1);
+      mbar_init(&bar_empty[s], CL);
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&acc_full[i], 1);
-      mbar_init(&acc_empty[i], 8);
+      mbar_init(&acc_empty[i], EPW);
     }
     fence_barrier_init();
   }
   if (warp == GW / 32) tmem_alloc<TM_COLS>(&tmem_base_s);
   tc_fence_before();
   __syncthreads();
+  if (CL > 1) cluster_sync_all();  // every CTA's barriers are initialised before any peer signals them
   tc_fence_after();
   const uint32_t tmem = tmem_base_s;
 
@@ -323,7 +418,7 @@ __global__ void __launch_bounds__(PT, 1) gemm_tc_persistent_kernel(const GemmArg
     const bool leader = elect_one();
     int g = 0, it = 0;
 #pragma unroll 1
-    for (int t = blockIdx.x; t < n_tiles; t += gridDim.x, ++it) {
+    for (int t = item0; t < n_items; t += item_step, ++it) {
       const int buf = it & 1;
       if (it >= 2) {  // the epilogue of the tile that used this accumulator two tiles ago has drained it
         mbar_wait(&acc_empty[buf], (uint32_t)(((it >> 1) - 1) & 1));
@@ -333,7 +428,7 @@ __global__ void __launch_bounds__(PT, 1) gemm_tc_persistent_kernel(const GemmArg
 #pragma unroll 1
       for (int kc = 0; kc < NKC; ++kc, ++g) {
         const int s = g % NSTAGE;
-        mbar_wait(&bar_full[s], (uint32_t)((g / NSTAGE) & 1));
+        wait_hot(&bar_full[s], (uint32_t)((g / NSTAGE) & 1));
         tc_fence_after();
         const uint32_t a_hi = smem_u32(base + (size_t)s * STAGE_BYTES), a_lo = a_hi + A_BYTES;
         const uint32_t w_hi = a_lo + A_BYTES, w_lo = w_hi + W_BYTES;
@@ -348,7 +443,8 @@ __global__ void __launch_bounds__(PT, 1) gemm_tc_persistent_kernel(const GemmArg
               mma_tf32(dcol, al, bh, IDESC, 1u);
             }
           }
-          mma_commit(&bar_empty[s]);
+          if (CL > 1) mma_commit_multicast(&bar_empty[s], CMASK);
+          else mma_commit(&bar_empty[s]);
           if (kc == NKC - 1) mma_commit(&acc_full[buf]);
         }
         __syncwarp();
@@ -393,30 +489,36 @@ __global__ void __launch_bounds__(PT, 1) gemm_tc_persistent_kernel(const GemmArg
       }
     };
     // prefetch cursor (tile, chunk) runs PF chunks ahead of the store cursor, across tile boundaries
-    int pt = blockIdx.x, pk = 0;
+    int pt = item0, pk = 0;
     auto prefetch_next = [&](float4 (&dst)[4], unsigned& okm) {
-      if (pt < n_tiles) {
-        issue_loads((pt / ntn) * 128, pk, dst, okm);
-        if (++pk == NKC) pk = 0, pt += gridDim.x;
+      if (pt < n_items) {
+        issue_loads(((pt / ntn) * CL + crank) * 128, pk, dst, okm);
+        if (++pk == NKC) pk = 0, pt += item_step;
       }
     };
 #pragma unroll
     for (int d = 0; d < PF; ++d) prefetch_next(rv[d], rok[d]);
-    int t = blockIdx.x, kc = 0, g = 0;
+    int t = item0, kc = 0, g = 0;
 #pragma unroll 1
-    while (t < n_tiles) {
+    while (t < n_items) {
 #pragma unroll
       for (int d = 0; d < PF; ++d) {
-        if (t < n_tiles) {
+        if (t < n_items) {
           const int s = g % NSTAGE, use = g / NSTAGE;
           if (use > 0) {
-            mbar_wait(&bar_empty[s], (uint32_t)((use - 1) & 1));
+            wait_hot(&bar_empty[s], (uint32_t)((use - 1) & 1));
             tc_fence_after();
           }
           unsigned char* st = base + (size_t)s * STAGE_BYTES;
           if (tid == 0) {
             mbar_expect_tx(&bar_full[s], 2 * W_BYTES);
-            bulk_g2s(st + 2 * A_BYTES, a.wpack + ((size_t)(t % ntn) * NKC + kc) * (2 * W_BYTES), 2 * W_BYTES, &bar_full[s]);
+            const unsigned char* src = a.wpack + ((size_t)(t % ntn) * NKC + kc) * (2 * W_BYTES);
+            if (CL > 1) {
+              constexpr uint32_t PART = 2 * W_BYTES / CL;
+              bulk_g2s_multicast(st + 2 * A_BYTES + crank * PART, src + crank * PART, PART, &bar_full[s], CMASK);
+            } else {
+              bulk_g2s(st + 2 * A_BYTES, src, 2 * W_BYTES, &bar_full[s]);
+            }
           }
 #pragma unroll
           for (int u = 0; u < 4; ++u) {
@@ -436,21 +538,22 @@ __global__ void __launch_bounds__(PT, 1) gemm_tc_persistent_kernel(const GemmArg
           if (lane == 0) mbar_arrive(&bar_full[s]);
           prefetch_next(rv[d], rok[d]);
           ++g;
-          if (++kc == NKC) kc = 0, t += gridDim.x;
+          if (++kc == NKC) kc = 0, t += item_step;
         }
       }
     }
   } else {
     // ---- epilogue warps ----
-    const int ew = warp - (GW / 32 + 1);   // 0..7
-    const int q = warp & 3, half = ew >> 2;  // TMEM lane quarter is fixed by the hardware warp id
+    const int ew = warp - (GW / 32 + 1);      // 0..EPW-1
+    const int q = warp & 3, half = ew >> 2;   // TMEM lane quarter is fixed by the hardware warp id
+    constexpr int NBLK = NT / 32 / (EPW / 4);  // 32-column blocks per warp
     float* stg = stg_all + (size_t)ew * (32 * 33);
     const int rsub = lane >> 3, cc = (lane & 7) * 4;
     int it = 0;
 #pragma unroll 1
-    for (int t = blockIdx.x; t < n_tiles; t += gridDim.x, ++it) {
+    for (int t = item0; t < n_items; t += item_step, ++it) {
       const int buf = it & 1;
-      const int m0 = (t / ntn) * 128, ntile = t % ntn;
+      const int m0 = ((t / ntn) * CL + crank) * 128, ntile = t % ntn;
       int clip_p[8];
       unsigned valid = 0;
 #pragma unroll
@@ -464,35 +567,26 @@ __global__ void __launch_bounds__(PT, 1) gemm_tc_persistent_kernel(const GemmArg
       tc_fence_after();
       const uint32_t taddr = tmem + ((uint32_t)(32 * q) << 16) + buf * NT;
 #pragma unroll 1
-      for (int cb = 0; cb < NT / 64; ++cb) {
-        const int col0 = half * (NT / 2) + cb * 32;
+      for (int cb = 0; cb < NBLK; ++cb) {
+        const int col0 = (half * NBLK + cb) * 32;
         uint32_t v0[16], v1[16];
+        EpiPre pre;
+        epi_prefetch(a, m0 + 32 * q, rsub, valid, ntile * NT + col0 + cc, pre);
         tmem_ld16_issue(taddr + col0, v0);
         tmem_ld16_issue(taddr + col0 + 16, v1);
         tmem_ld_wait();
-        if (cb == NT / 64 - 1) {  // accumulator drained: hand it back before the global stores of this block
+        if (cb == NBLK - 1) {  // accumulator drained: hand it back before the global stores of this block
           tc_fence_before();
           __syncwarp();
           if (lane == 0) mbar_arrive(&acc_empty[buf]);
         }
-#pragma unroll
-        for (int j = 0; j < 16; ++j) {
-          stg[lane * 33 + j] = __uint_as_float(v0[j]);
-          stg[lane * 33 + 16 + j] = __uint_as_float(v1[j]);
-        }
-        __syncwarp();
-#pragma unroll
-        for (int p = 0; p < 8; ++p) {
-          const int rl = 4 * p + rsub;
-          const float4 v = make_float4(stg[rl * 33 + cc], stg[rl * 33 + cc + 1], stg[rl * 33 + cc + 2], stg[rl * 33 + cc + 3]);
-          if ((valid >> p) & 1u) epi_apply(a, m0 + 32 * q + rl, clip_p[p], ntile * NT + col0 + cc, v);
-        }
-        __syncwarp();
+        epi_block(a, stg, lane, m0 + 32 * q, rsub, cc, valid, clip_p, ntile * NT + col0 + cc, v0, v1, pre);
       }
     }
   }
   tc_fence_before();
   __syncthreads();
+  if (CL > 1) cluster_sync_all();  // no CTA leaves while a peer may still signal its barriers
   if (warp == GW / 32) tmem_dealloc<TM_COLS>(tmem);
 }
 
@@ -592,20 +686,72 @@ int launch_tc(const GemmArgs& a, int passes, cudaStream_t stream) {
   return 0;
 }
 
-template <int NT, int NSTAGE>
+int tune_env(const char* name, int dflt) {
+  const char* e = getenv(name);
+  return e != nullptr ? atoi(e) : dflt;
+}
+int tune_epw() {
+  static const int v = tune_env("ADVB_GEMM_EPW", 8) == 4 ? 4 : 8;
+  return v;
+}
+int tune_cluster() {  // cluster size along M for the weight multicast (1 = off)
+  static const int v = [] {
+    const int c = tune_env("ADVB_GEMM_CLUSTER", 2);
+    return (c == 1 || c == 2 || c == 4) ? c : 2;
+  }();
+  return v;
+}
+
+template <int NT, int NSTAGE, int EPW, int CL>
 int launch_tc_persistent(const GemmArgs& a, int passes, cudaStream_t stream) {
-  constexpr size_t smem = (size_t)NSTAGE * (2 * 128 * 128 + 2 * NT * 128) + 8 * 32 * 33 * sizeof(float) + 1024;
-  ADVB_CUDA_OK(cudaFuncSetAttribute(gemm_tc_persistent_kernel<NT, NSTAGE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  static int n_sm = 0;
-  if (n_sm == 0) {
-    int dev = 0;
-    ADVB_CUDA_OK(cudaGetDevice(&dev));
-    ADVB_CUDA_OK(cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev));
+  constexpr size_t smem = (size_t)NSTAGE * (2 * 128 * 128 + 2 * NT * 128) + EPW * 32 * 33 * sizeof(float) + 1024;
+  constexpr int PT = GW + 32 + 32 * EPW;
+  auto kern = gemm_tc_persistent_kernel<NT, NSTAGE, EPW, CL>;
+  ADVB_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  cudaLaunchConfig_t cfg{};
+  cfg.blockDim = dim3(PT);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = CL, attr[0].val.clusterDim.y = 1, attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  static int max_clusters = 0;  // co-resident clusters of this shape (persistent kernel: never launch more)
+  if (max_clusters == 0) {
+    cfg.gridDim = dim3(CL);
+    int n = 0;
+    if (CL > 1) {
+      ADVB_CUDA_OK(cudaOccupancyMaxActiveClusters(&n, kern, &cfg));
+    } else {
+      int dev = 0;
+      ADVB_CUDA_OK(cudaGetDevice(&dev));
+      ADVB_CUDA_OK(cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev));
+    }
+    ADVB_CHECK(n > 0, "no co-resident cluster of the persistent GEMM fits on this device");
+    max_clusters = n;
   }
-  const int n_tiles = (a.N / NT) * cdiv(a.M, 128);
-  gemm_tc_persistent_kernel<NT, NSTAGE><<<std::min(n_tiles, n_sm), PT, smem, stream>>>(a, passes, n_tiles);
+  const int n_items = (a.N / NT) * cdiv(cdiv(a.M, 128), CL);
+  cfg.gridDim = dim3(std::min(n_items, max_clusters) * CL);
+  GemmArgs ac = a;
+  int p = passes, ni = n_items;
+  void* params[3] = {&ac, &p, &ni};
+  ADVB_CUDA_OK(cudaLaunchKernelExC(&cfg, reinterpret_cast<const void*>(kern), params));
   ADVB_KERNEL_OK(a.tag, stream);
   return 0;
+}
+
+template <int NT, int NSTAGE>
+int launch_tc_persistent_tuned(const GemmArgs& a, int passes, cudaStream_t stream) {
+  const int cl = tune_cluster();
+  if (tune_epw() == 4) {
+    if (cl == 4) return launch_tc_persistent<NT, NSTAGE, 4, 4>(a, passes, stream);
+    if (cl == 2) return launch_tc_persistent<NT, NSTAGE, 4, 2>(a, passes, stream);
+    return launch_tc_persistent<NT, NSTAGE, 4, 1>(a, passes, stream);
+  }
+  if (cl == 4) return launch_tc_persistent<NT, NSTAGE, 8, 4>(a, passes, stream);
+  if (cl == 2) return launch_tc_persistent<NT, NSTAGE, 8, 2>(a, passes, stream);
+  return launch_tc_persistent<NT, NSTAGE, 8, 1>(a, passes, stream);
 }
 
 }  // namespace
@@ -622,6 +768,7 @@ int gemm_pack(const GemmW& w, int N, int K, int ntap, unsigned char* dst, cudaSt
 
 int gemm_run(const GemmArgs& a, int path, int passes, cudaStream_t stream) {
   ADVB_CHECK(a.N % 128 == 0 && a.K % 32 == 0 && a.ntap >= 1 && a.ntap <= 3 && a.M > 0, "unsupported GEMM shape");
+  ADVB_CHECK(a.add == nullptr || a.add2 == nullptr, "add and add2 are mutually exclusive");
   ADVB_CHECK(a.im2col_T > 0 || (a.lda % 4 == 0 && (reinterpret_cast<uintptr_t>(a.A) & 15) == 0), "A operand must be 16-byte aligned");
   if (path == 1) {
     dim3 grid(a.N / 64, cdiv(a.M, 64));
@@ -634,8 +781,8 @@ int gemm_run(const GemmArgs& a, int path, int passes, cudaStream_t stream) {
     if (tile_n(a.N) == 256) return launch_tc<256, 2>(a, passes, stream);
     return launch_tc<128, 3>(a, passes, stream);
   }
-  if (tile_n(a.N) == 256) return launch_tc_persistent<256, 2>(a, passes, stream);
-  return launch_tc_persistent<128, 3>(a, passes, stream);
+  if (tile_n(a.N) == 256) return launch_tc_persistent_tuned<256, 2>(a, passes, stream);
+  return launch_tc_persistent_tuned<128, 3>(a, passes, stream);
 }
 
 }  // namespace advb

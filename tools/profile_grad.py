@@ -1,4 +1,4 @@
-"""One forward+backward (advb_grad) of LCNN+LFCC at the bench shape, for ncu captures (diagnostic tool).
+"""One forward+backward (advb_grad) of LCNN+LFCC (or --model rawnet3 / specrnet) at the bench shape, for ncu captures (diagnostic tool).
 
     ncu --set full --clock-control none --import-source on -k regex:conv_tc -s 16 -c 16 -o gpurun_out/prof \
         python tools/profile_grad.py [--batch 128] [--calls 2]
@@ -21,11 +21,13 @@ def main():
     ap.add_argument("--batch", type=int, default=128)
     ap.add_argument("--calls", type=int, default=2)
     ap.add_argument("--conv-path", type=int, default=0)
+    ap.add_argument("--model", default="lcnn", choices=["lcnn", "specrnet", "rawnet3"])
     args = ap.parse_args()
     from advb200 import engine
 
     dev = torch.device("cuda:0")
-    holder, state = bench.build_lcnn_state()
+    fe = {"lcnn": "lfcc", "specrnet": "mfcc", "rawnet3": "none"}[args.model]
+    holder, state = bench.build_lcnn_state(args.model, fe)
     holder.load_state_dict(state)
     holder = holder.to(dev)
     x, y = bench.synthetic_batch(args.batch, 1002)
