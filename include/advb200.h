@@ -84,9 +84,9 @@ ADVB_API size_t advb_workspace_bytes(const advb_handle* h);
 ADVB_API int advb_rebind(advb_handle* h, int n_tensors, const advb_tensor_ref* tensors);
 
 /* Engine options (no reference counterpart; the reference's knobs are torch-global):
- *   "conv_path"   0 = tcgen05 tensor-core convolutions (default), 1 = fp32 SIMT convolutions (cross-check)
+ *   "conv_path"   0 = tcgen05 tensor-core convolutions / GEMMs (default), 1 = fp32 SIMT convolutions / GEMMs (cross-check)
  *   "tf32_passes" 3 = 3xTF32 error-compensated products, fp32-class accuracy (default), 1 = single-pass tf32
- *   "conv_sched"  0 = persistent warp-specialised convolution kernels (default), 1 = one-tile-per-CTA kernels only
+ *   "conv_sched"  0 = persistent warp-specialised convolution / GEMM kernels (default), 1 = one-tile-per-CTA kernels only
  *                 (the first tcgen05 version; same arithmetic, kept as an in-process cross-check) */
 ADVB_API int advb_set_option(advb_handle* h, const char* key, int value);
 
@@ -115,7 +115,8 @@ ADVB_API int advb_grad(advb_handle* h, int what, const float* x, const int64_t* 
               int n_global_batch, void* cuda_stream);
 
 /* Replaces LFCC_FN(x) / MFCC_FN(x) (src/frontends.py:13-32): coefficients [B,80,F] (torchaudio layout),
- * F = 1 + T/160, and their vector-Jacobian product.  Test / f4 entry points. */
+ * F = 1 + T/160, and their vector-Jacobian product.  Test / f4 entry points.  Error for a handle created with
+ * ADVB_FRONTEND_NONE (RawNet3 consumes the raw waveform, rawnet3.py:73-137). */
 ADVB_API int advb_frontend_fwd(advb_handle* h, const float* x, float* coeff, int B, int T, void* cuda_stream);
 ADVB_API int advb_frontend_bwd(advb_handle* h, const float* x, const float* g_coeff, float* g_x, int B, int T,
                       void* cuda_stream);
