@@ -54,40 +54,13 @@ __device__ __forceinline__ void split_rn(float x, float& hi, float& lo) {
   lo = __uint_as_float(l);
 }
 
-// The fused epilogue on 4 consecutive columns n..n+3 of valid row r (clip = r / Tp), split in three steps so that a caller
-// can issue the global loads of several rows back to back BEFORE the first store: written as one function per row, the
-// possible aliasing of `out` with `add` / `add2` pins every load behind the previous row's stores and each row pays 3-5
-// serial global-load latencies (measured: 43 us per 128 x 128 tile of the Res2 chain against a 4.7 us MMA floor).
-struct EpiCol {  // per-column operands: the same for every row a thread handles
-  float4 bias, bn_s, bn_t, gs, gs2;
-};
-struct EpiRow {  // per-row operands (`add` and `add2` are never used by the same GEMM: one register set serves both)
-  float4 addv;
-  uchar4 gm, gm2;
-};
-__device__ __forceinline__ EpiCol epi_load_col(const GemmArgs& a, int n) {
-  EpiCol c;
-  c.bias = c.bn_s = c.bn_t = c.gs = c.gs2 = make_float4(0.f, 0.f, 0.f, 0.f);
-  if (a.bias != nullptr && !a.bias_per_clip) c.bias = ldg4(a.bias + n);
-  if (a.bn_scale != nullptr) c.bn_s = ldg4(a.bn_scale + n), c.bn_t = ldg4(a.bn_shift + n);
-  if (a.gate_scale != nullptr) c.gs = ldg4(a.gate_scale + n);
-  if (a.gate2_scale != nullptr) c.gs2 = ldg4(a.gate2_scale + n);
-  return c;
-}
-__device__ __forceinline__ EpiRow epi_load_row(const GemmArgs& a, int r, int n) {
-  EpiRow w;
-  w.addv = make_float4(0.f, 0.f, 0.f, 0.f);
-  w.gm = w.gm2 = make_uchar4(0, 0, 0, 0);
-  if (a.add != nullptr) w.addv = *reinterpret_cast<const float4*>(a.add + (size_t)r * a.ld_add + n);  // may alias out: plain load
-  else if (a.add2 != nullptr) w.addv = ldg4(a.add2 + (size_t)r * a.ld_add2 + n);
-  if (a.gate_scale != nullptr) w.gm = __ldg(reinterpret_cast<const uchar4*>(a.gate_mask + (size_t)r * a.ld_gate + n));
-  if (a.gate2_scale != nullptr) w.gm2 = __ldg(reinterpret_cast<const uchar4*>(a.gate2_mask + (size_t)r * a.ld_gate2 + n));
-  return w;
-}
-__device__ __forceinline__ void epi_finish(const GemmArgs& a, int r, int clip, int n, float4 v, const EpiCol& c, const EpiRow& w) {
+// The fused epilogue on 4 consecutive columns n..n+3 of valid row r (clip = r / Tp).
+// (A variant that fetched the row operands of a whole 32 x 32 block before the first store was measured and dropped: with 17
+// warps the kernel is capped at 96 registers, the extra live values spilled the fill warps' prefetch registers - which makes
+// their loads synchronous - and the plain GEMMs got 1.5-2x slower; without spills it was no faster than this one.)
+__device__ __forceinline__ void epi_apply(const GemmArgs& a, int r, int clip, int n, float4 v) {
   if (a.bias != nullptr) {
-    // (per-clip bias: the attention layer only, 128 floats per clip - read here, it stays in L1)
-    const float4 b = a.bias_per_clip ? ldg4(a.bias + (size_t)clip * a.N + n) : c.bias;
+    const float4 b = ldg4(a.bias + (a.bias_per_clip ? (size_t)clip * a.N : (size_t)0) + n);
     v.x += b.x, v.y += b.y, v.z += b.z, v.w += b.w;
   }
   if (a.relu) {
@@ -97,50 +70,41 @@ __device__ __forceinline__ void epi_finish(const GemmArgs& a, int r, int clip, i
     v.x = fmaxf(v.x, 0.f), v.y = fmaxf(v.y, 0.f), v.z = fmaxf(v.z, 0.f), v.w = fmaxf(v.w, 0.f);
   }
   if (a.bn_scale != nullptr) {
-    v.x = fmaf(v.x, c.bn_s.x, c.bn_t.x), v.y = fmaf(v.y, c.bn_s.y, c.bn_t.y);
-    v.z = fmaf(v.z, c.bn_s.z, c.bn_t.z), v.w = fmaf(v.w, c.bn_s.w, c.bn_t.w);
+    const float4 s = ldg4(a.bn_scale + n), t = ldg4(a.bn_shift + n);
+    v.x = fmaf(v.x, s.x, t.x), v.y = fmaf(v.y, s.y, t.y), v.z = fmaf(v.z, s.z, t.z), v.w = fmaf(v.w, s.w, t.w);
   }
-  if (a.add != nullptr) v.x += w.addv.x, v.y += w.addv.y, v.z += w.addv.z, v.w += w.addv.w;
+  if (a.add != nullptr) {
+    const float4 d = *reinterpret_cast<const float4*>(a.add + (size_t)r * a.ld_add + n);  // may alias out: plain load
+    v.x += d.x, v.y += d.y, v.z += d.z, v.w += d.w;
+  }
   if (a.out != nullptr) {
     float4 o = v;
-    if (a.gate_scale != nullptr)
-      o.x = w.gm.x ? v.x * c.gs.x : 0.f, o.y = w.gm.y ? v.y * c.gs.y : 0.f, o.z = w.gm.z ? v.z * c.gs.z : 0.f,
-      o.w = w.gm.w ? v.w * c.gs.w : 0.f;
+    if (a.gate_scale != nullptr) {
+      const float4 s = ldg4(a.gate_scale + n);
+      const uchar4 m = __ldg(reinterpret_cast<const uchar4*>(a.gate_mask + (size_t)r * a.ld_gate + n));
+      o.x = m.x ? v.x * s.x : 0.f, o.y = m.y ? v.y * s.y : 0.f, o.z = m.z ? v.z * s.z : 0.f, o.w = m.w ? v.w * s.w : 0.f;
+    }
     *reinterpret_cast<float4*>(a.out + (size_t)r * a.ldc + n) = o;
   }
   if (a.out2 != nullptr) {
     float4 o = v;
-    if (a.add2 != nullptr) o.x += w.addv.x, o.y += w.addv.y, o.z += w.addv.z, o.w += w.addv.w;
-    if (a.gate2_scale != nullptr)
-      o.x = w.gm2.x ? o.x * c.gs2.x : 0.f, o.y = w.gm2.y ? o.y * c.gs2.y : 0.f, o.z = w.gm2.z ? o.z * c.gs2.z : 0.f,
-      o.w = w.gm2.w ? o.w * c.gs2.w : 0.f;
+    if (a.add2 != nullptr) {
+      const float4 d = ldg4(a.add2 + (size_t)r * a.ld_add2 + n);
+      o.x += d.x, o.y += d.y, o.z += d.z, o.w += d.w;
+    }
+    if (a.gate2_scale != nullptr) {
+      const float4 s = ldg4(a.gate2_scale + n);
+      const uchar4 m = __ldg(reinterpret_cast<const uchar4*>(a.gate2_mask + (size_t)r * a.ld_gate2 + n));
+      o.x = m.x ? o.x * s.x : 0.f, o.y = m.y ? o.y * s.y : 0.f, o.z = m.z ? o.z * s.z : 0.f, o.w = m.w ? o.w * s.w : 0.f;
+    }
     *reinterpret_cast<float4*>(a.out2 + (size_t)r * a.ld2 + n) = o;
   }
 }
-__device__ __forceinline__ void epi_apply(const GemmArgs& a, int r, int clip, int n, float4 v) {
-  const EpiCol c = epi_load_col(a, n);
-  const EpiRow w = epi_load_row(a, r, n);
-  epi_finish(a, r, clip, n, v, c, w);
-}
 
-// One 32-row x 32-column block of a tile: the caller fetches every global operand of the block's 8 rows per thread
-// (epi_prefetch) BEFORE waiting for tcgen05.ld; epi_block then transposes the TMEM values (thread = row) through the warp's
-// private staging tile and finishes with thread = (row 4 p + rsub, columns cc..cc+3).
-struct EpiPre {
-  EpiCol col;
-  EpiRow row[8];
-};
-__device__ __forceinline__ void epi_prefetch(const GemmArgs& a, int rbase, int rsub, unsigned valid, int n, EpiPre& pre) {
-  pre.col = epi_load_col(a, n);
-#pragma unroll
-  for (int p = 0; p < 8; ++p) {
-    const int r = ((valid >> p) & 1u) ? rbase + 4 * p + rsub : rbase;  // invalid rows: any in-range address, result unused
-    pre.row[p] = epi_load_row(a, r < a.M ? r : 0, n);
-  }
-}
+// One 32-row x 32-column block of a tile: transpose the TMEM values (thread = row) through the warp's private staging tile and
+// finish with thread = (row 4 p + rsub, columns cc..cc+3) so that every global access of the epilogue is a coalesced 16-byte one.
 __device__ __forceinline__ void epi_block(const GemmArgs& a, float* stg, int lane, int rbase, int rsub, int cc, unsigned valid,
-                                          const int (&clip_p)[8], int n, const uint32_t (&v0)[16], const uint32_t (&v1)[16],
-                                          const EpiPre& pre) {
+                                          const int (&clip_p)[8], int n, const uint32_t (&v0)[16], const uint32_t (&v1)[16]) {
 #pragma unroll
   for (int j = 0; j < 16; ++j) {
     stg[lane * 33 + j] = __uint_as_float(v0[j]);
@@ -151,7 +115,7 @@ __device__ __forceinline__ void epi_block(const GemmArgs& a, float* stg, int lan
   for (int p = 0; p < 8; ++p) {
     const int rl = 4 * p + rsub;
     const float4 v = make_float4(stg[rl * 33 + cc], stg[rl * 33 + cc + 1], stg[rl * 33 + cc + 2], stg[rl * 33 + cc + 3]);
-    if ((valid >> p) & 1u) epi_finish(a, rbase + rl, clip_p[p], n, v, pre.col, pre.row[p]);
+    if ((valid >> p) & 1u) epi_apply(a, rbase + rl, clip_p[p], n, v);
   }
   __syncwarp();
 }
@@ -319,12 +283,10 @@ __global__ void __launch_bounds__(GT, 1) gemm_tc_kernel(const GemmArgs a, const 
     for (int cb = 0; cb < NT / 64; ++cb) {
       const int col0 = half * (NT / 2) + cb * 32;
       uint32_t v0[16], v1[16];
-      EpiPre pre;
-      epi_prefetch(a, m0 + 32 * q, rsub, valid, ntile * NT + col0 + cc, pre);
       tmem_ld16_issue(taddr + col0, v0);
       tmem_ld16_issue(taddr + col0 + 16, v1);
       tmem_ld_wait();
-      epi_block(a, stg, lane, m0 + 32 * q, rsub, cc, valid, clip_p, ntile * NT + col0 + cc, v0, v1, pre);
+      epi_block(a, stg, lane, m0 + 32 * q, rsub, cc, valid, clip_p, ntile * NT + col0 + cc, v0, v1);
     }
   }
   tc_fence_before();
@@ -570,8 +532,6 @@ __global__ void __launch_bounds__(GW + 32 + 32 * EPW, 1) gemm_tc_persistent_kern
       for (int cb = 0; cb < NBLK; ++cb) {
         const int col0 = (half * NBLK + cb) * 32;
         uint32_t v0[16], v1[16];
-        EpiPre pre;
-        epi_prefetch(a, m0 + 32 * q, rsub, valid, ntile * NT + col0 + cc, pre);
         tmem_ld16_issue(taddr + col0, v0);
         tmem_ld16_issue(taddr + col0 + 16, v1);
         tmem_ld_wait();
@@ -580,7 +540,7 @@ __global__ void __launch_bounds__(GW + 32 + 32 * EPW, 1) gemm_tc_persistent_kern
           __syncwarp();
           if (lane == 0) mbar_arrive(&acc_empty[buf]);
         }
-        epi_block(a, stg, lane, m0 + 32 * q, rsub, cc, valid, clip_p, ntile * NT + col0 + cc, v0, v1, pre);
+        epi_block(a, stg, lane, m0 + 32 * q, rsub, cc, valid, clip_p, ntile * NT + col0 + cc, v0, v1);
       }
     }
   }

@@ -68,6 +68,41 @@ def test_specrnet_holder_has_reference_state_dict_keys():
     assert type(holder).__name__ == "SpecRNet"
 
 
+def test_rawnet3_holder_has_reference_state_dict_keys():
+    from advb200.models import get_model
+    from advb200.models.rawnet3 import RawNet3
+
+    holder = get_model("rawnet3", {}, "cpu")
+    keys = list(holder.state_dict())
+    for k in ("preprocess.0.flipped_filter", "preprocess.1.weight", "conv1.filterbank.low_hz_", "conv1.filterbank.band_hz_",
+              "conv1.filterbank.window_", "conv1.filterbank.n_", "bn1.running_var", "layer1.residual.0.weight",
+              "layer1.convs.6.weight", "layer2.bns.3.running_mean", "layer3.afms.alpha", "layer3.afms.fc.bias", "layer4.weight",
+              "attention.0.weight", "attention.2.running_var", "attention.3.bias", "bn5.weight", "fc6.bias", "bn6.weight"):
+        assert k in keys, k
+    assert "layer2.residual.0.weight" not in keys  # identity residual when in == out (rawnet3.py:234-240)
+    sd = holder.state_dict()
+    assert tuple(sd["layer1.convs.0.weight"].shape) == (128, 128, 3) and tuple(sd["attention.0.weight"].shape) == (128, 4608, 1)
+    assert tuple(sd["conv1.filterbank.low_hz_"].shape) == (128, 1) and tuple(sd["conv1.filterbank.n_"].shape) == (1, 125)
+    assert sum(p.numel() for p in holder.parameters()) == 15496197  # the reference's prepare_model() (measured in the build container)
+    assert type(holder).__name__ == "RawNet3"
+    with pytest.raises(ValueError):
+        RawNet3(encoder_type="ASP")  # only the reference's prepare_model() configuration is built natively
+    with pytest.raises(RuntimeError, match="no CPU path"):
+        holder(torch.rand(1, 16000))
+
+
+def test_rawnet3_sinc_filter_restatement_properties():
+    """The restated asteroid ParamSincFB (oracle side): 128 cosine (even) + 128 sine (odd) filters of 251 taps, unit centre
+    tap for the cosine half, zero for the sine half."""
+    from oracle import rawnet3 as orn
+
+    holder = cases.build_holder("rawnet3", "none")
+    f = orn.sinc_filters(holder.state_dict())[:, 0]
+    assert tuple(f.shape) == (256, 251)
+    assert torch.allclose(f[:128], f[:128].flip(1)) and torch.allclose(f[128:], -f[128:].flip(1))
+    assert torch.allclose(f[:128, 125], torch.ones(128)) and torch.equal(f[128:, 125], torch.zeros(128))
+
+
 def test_attack_api_surface_and_no_cpu_fallback():
     from advb200 import aa
     from advb200 import torchattacks as ta
