@@ -53,6 +53,18 @@ WORKLOADS = {
                     flop_per_clip=10 * RAWNET3_FLOP_PER_CLIP_ITER,
                     text="PGDL2 eps=0.1 alpha=0.2 steps=10 random_start (AttackEnum.PGDL2) on RawNet3, 64000-sample clips, "
                          "16 clips per GPU (BASELINE.json configs[3])"),
+    # BASELINE.json configs[3], the FAB half (AttackEnum.FAB_eta10: Linf, eps 0.3, 100 steps, eta 10): per step one forward +
+    # logit-gradient backward at x1, one forward for the bookkeeping, two sort-free projections
+    "rawnet3_fab": dict(model="rawnet3", frontend="none", batch=16, bias="fc6.bias", attack="fab",
+                        flop_per_clip=100 * 1.5 * RAWNET3_FLOP_PER_CLIP_ITER,
+                        text="FAB Linf eps=0.3 steps=100 eta=10 (AttackEnum.FAB_eta10) on RawNet3, 64000-sample clips, "
+                             "16 clips per GPU (BASELINE.json configs[3])"),
+    # BASELINE.json configs[4]: the attack call of adversarial training (src/trainer.py:507-514, ONLY_ADV): AttackEnum.PGD_eps0005
+    # (eps 5e-4, 10 steps) on LCNN+LFCC, 64 clips per GPU; the weight-gradient step around it is SURVEY.md §8(f3), not built
+    "lcnn_advtrain": dict(model="lcnn", frontend="lfcc", batch=64, bytes_per_clip=10 * 15_818_544 + 768_000,
+                          bias="m_output_act.bias", attack="pgd10",
+                          text="PGD-10 Linf eps=0.0005 alpha=2/255 (AttackEnum.PGD_eps0005, the inner attack of adversarial training) "
+                               "on LCNN+LFCC, 64000-sample clips, 64 clips per GPU (BASELINE.json configs[4]; attack call only)"),
 }
 
 
@@ -286,6 +298,10 @@ def run_native(args):
     holder = holder.to(dev)
     if wl.get("attack") == "pgdl2":
         atk = ta.PGDL2(holder, eps=0.1, alpha=0.2, steps=10, random_start=True)
+    elif wl.get("attack") == "fab":
+        atk = ta.FAB(holder, norm="Linf", eps=0.3, steps=100, eta=10, n_classes=2)
+    elif wl.get("attack") == "pgd10":
+        atk = ta.PGD(holder, eps=0.0005, alpha=ALPHA, steps=10, random_start=True)
     else:
         atk = ta.PGD(holder, eps=EPS, alpha=ALPHA, steps=PGD_STEPS, random_start=True)
     atk.set_training_mode(model_training=True, batchnorm_training=False)
@@ -406,7 +422,8 @@ def run_native(args):
             pk = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json"))) if os.path.exists(
                 os.path.join(ROOT, "MEASURED_PEAKS.json")) else {}
             tpeak = float(pk.get("bf16_tflops_sustained", 1392.4))
-            flops_tag = gemm_tags[top["name"]] * 10
+            n_eval = {"pgdl2": 10, "fab": 200}[wl["attack"]]  # forward passes per call (FAB: 2 per step, half with a backward)
+            flops_tag = gemm_tags[top["name"]] * n_eval / (1 if top["name"].endswith("_fwd") or wl["attack"] != "fab" else 2)
             ach = flops_tag / (top["total_ms"] * 1e-3) / 1e12
             out["roofline"] = {"bound": "tensor", "kernel": top["name"], "achieved": ach, "peak": tpeak, "unit": "TFLOP/s",
                                "frac": ach / tpeak, "traffic": None, "peak_source": "measured (sustained bf16)" if pk else "fallback",
@@ -416,7 +433,7 @@ def run_native(args):
             pach = value / world * wl["flop_per_clip"] / 1e12
             out["path_roofline"] = {"bound": "tensor", "achieved": pach, "peak": tpeak, "unit": "TFLOP/s", "frac": pach / tpeak,
                                     "flop_per_clip": wl["flop_per_clip"]}
-            if world == 1 and not args.no_cpu_baseline:
+            if world == 1 and not args.no_cpu_baseline and wl["attack"] == "pgdl2":
                 v, dt, cores = cpu_port_rawnet3_clips_per_s(4, 2)
                 out["cpu_baseline"] = {"value": v, "unit": "clips/s", "cores": cores, "kind": "port",
                                        "sample": f"oracle port, PGDL2-2 of the PGDL2-10 workload on 4 clips ({dt:.1f} s), time x5"}
@@ -439,7 +456,8 @@ def main():
     ap.add_argument("--impl", default="native", choices=["native", "reference"])
     ap.add_argument("--batch", type=int, default=0, help="clips per GPU (default: the workload's BASELINE.json batch)")
     ap.add_argument("--workload", default="lcnn", choices=sorted(WORKLOADS),
-                    help="lcnn = BASELINE.json configs[1] (the headline), specrnet = configs[2], rawnet3 = configs[3] (PGDL2)")
+                    help="lcnn = BASELINE.json configs[1] (the headline), specrnet = configs[2], rawnet3 / rawnet3_fab = configs[3] "
+                         "(PGDL2 / FAB), lcnn_advtrain = configs[4] (attack call of adversarial training)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--kernel-times", default=None, help="write the full per-kernel timing table of one call (JSON)")
     args = ap.parse_args()
