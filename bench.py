@@ -423,16 +423,18 @@ def run_native(args):
                 os.path.join(ROOT, "MEASURED_PEAKS.json")) else {}
             tpeak = float(pk.get("bf16_tflops_sustained", 1392.4))
             n_eval = {"pgdl2": 10, "fab": 200}[wl["attack"]]  # forward passes per call (FAB: 2 per step, half with a backward)
-            flops_tag = gemm_tags[top["name"]] * n_eval / (1 if top["name"].endswith("_fwd") or wl["attack"] != "fab" else 2)
+            # FAB only works on the clips that are still correctly classified (fab.py:506-513): count their FLOPs only
+            frac = float((pred[:, 0] == pred[:, 2]).float().mean()) if wl["attack"] == "fab" else 1.0
+            flops_tag = frac * gemm_tags[top["name"]] * n_eval / (1 if top["name"].endswith("_fwd") or wl["attack"] != "fab" else 2)
             ach = flops_tag / (top["total_ms"] * 1e-3) / 1e12
             out["roofline"] = {"bound": "tensor", "kernel": top["name"], "achieved": ach, "peak": tpeak, "unit": "TFLOP/s",
                                "frac": ach / tpeak, "traffic": None, "peak_source": "measured (sustained bf16)" if pk else "fallback",
                                "avg_launch_ms": top["total_ms"] / top["count"], "share_of_step": top["total_ms"] / total_prof,
                                "algorithmic_flops_per_launch": flops_tag / top["count"],
                                "note": "fp32-class accuracy via 3xTF32: 3 tf32 MMAs per algorithmic product"}
-            pach = value / world * wl["flop_per_clip"] / 1e12
+            pach = frac * value / world * wl["flop_per_clip"] / 1e12
             out["path_roofline"] = {"bound": "tensor", "achieved": pach, "peak": tpeak, "unit": "TFLOP/s", "frac": pach / tpeak,
-                                    "flop_per_clip": wl["flop_per_clip"]}
+                                    "flop_per_clip": wl["flop_per_clip"], "fraction_of_clips_attacked": frac}
             if world == 1 and not args.no_cpu_baseline and wl["attack"] == "pgdl2":
                 v, dt, cores = cpu_port_rawnet3_clips_per_s(4, 2)
                 out["cpu_baseline"] = {"value": v, "unit": "clips/s", "cores": cores, "kind": "port",
