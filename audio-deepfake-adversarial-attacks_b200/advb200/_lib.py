@@ -46,6 +46,8 @@ SIGNATURES = {
     "advb_rebind": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(TensorRef)]),
     "advb_attack": (C.c_int, [C.c_void_p, C.POINTER(AttackDesc), C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
                               C.c_int, C.c_int, C.c_void_p]),
+    "advb_attack_minmax": (C.c_int, [C.c_void_p, C.POINTER(AttackDesc), C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                                     C.c_int, C.c_int, C.c_void_p]),
     "advb_forward": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p]),
     "advb_grad": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int,
                             C.c_int, C.c_void_p]),

@@ -23,3 +23,17 @@ class AttackEnum(Enum):
     FAB_eta30 = (torchattacks.FAB, {"n_classes": 2, "eta": 30})
 
     NO_ATTACK = (None, {})
+
+
+def attack_minmax(atk, x, y):
+    """``revert_minmax(atk(to_minmax(x)), ...)`` - the three lines every call site of the reference wraps around an attack
+    (evaluate_models_on_adversarial_attacks.py:219-221, src/trainer.py:425-427) - as ONE native call for FGSM / PGD / PGDL2
+    (SURVEY.md §8 f2); FAB and CW, whose Python shims issue several engine calls, go through the three GPU kernels."""
+    if isinstance(atk, (torchattacks.FGSM, torchattacks.PGD, torchattacks.PGDL2)):
+        atk._fused_minmax = True
+        try:
+            return atk(x, y)
+        finally:
+            atk._fused_minmax = False
+    x01, mn, mx = to_minmax(x.to(atk.device))
+    return revert_minmax(atk(x01, y), mn, mx)

@@ -87,14 +87,16 @@ class Engine:
             raise ValueError("batch does not fit this engine handle")
         return x.contiguous()
 
-    def attack(self, desc: "_lib.AttackDesc", x, y, start=None):
+    def attack(self, desc: "_lib.AttackDesc", x, y, start=None, minmax=False):
+        """``minmax=True``: ``x`` is the raw waveform batch; to_minmax / revert_minmax run inside the same native call."""
         x = self._check_x(x)
         y = y.to(device=x.device, dtype=torch.int64).contiguous()
         self._sync_weights()
         out = torch.empty_like(x)
         sp = C.c_void_p(start.contiguous().data_ptr()) if start is not None else None
+        fn = self.lib.advb_attack_minmax if minmax else self.lib.advb_attack
         with torch.cuda.device(self.device):
-            _lib.check(self.lib.advb_attack(self.handle, C.byref(desc), x.data_ptr(), y.data_ptr(), sp, out.data_ptr(),
+            _lib.check(fn(self.handle, C.byref(desc), x.data_ptr(), y.data_ptr(), sp, out.data_ptr(),
                                             x.shape[0], x.shape[1], self._stream()))
         return out
 

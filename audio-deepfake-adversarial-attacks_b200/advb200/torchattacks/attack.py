@@ -19,6 +19,7 @@ class Attack(object):
         self._model_training = False
         self._batchnorm_training = False
         self._dropout_training = False
+        self._fused_minmax = False  # aa.attack_minmax: raw waveforms in / out, min-max scaling inside the native call
 
     def forward(self, *input):
         raise NotImplementedError

@@ -21,7 +21,7 @@ class FGSM(Attack):
 
     def forward(self, images, labels):
         images, labels = self._prepare(images, labels)
-        return self._engine(images).attack(_desc(_lib.ATTACK_FGSM, eps=self.eps), images, labels)
+        return self._engine(images).attack(_desc(_lib.ATTACK_FGSM, eps=self.eps), images, labels, minmax=self._fused_minmax)
 
 
 class PGD(Attack):
@@ -41,7 +41,7 @@ class PGD(Attack):
         if noise is not None:
             noise = noise.to(images.device)
         d = _desc(_lib.ATTACK_PGD, eps=self.eps, alpha=self.alpha, steps=self.steps)
-        return self._engine(images).attack(d, images, labels, noise)
+        return self._engine(images).attack(d, images, labels, noise, minmax=self._fused_minmax)
 
 
 class PGDL2(Attack):
@@ -65,7 +65,7 @@ class PGDL2(Attack):
         if delta is not None:
             delta = delta.to(images.device)
         d = _desc(_lib.ATTACK_PGDL2, eps=self.eps, alpha=self.alpha, steps=self.steps, eps_div=self.eps_for_division)
-        return self._engine(images).attack(d, images, labels, delta)
+        return self._engine(images).attack(d, images, labels, delta, minmax=self._fused_minmax)
 
 
 class FAB(Attack):

@@ -106,6 +106,7 @@ struct advb_handle {
   float *grad = nullptr, *partial_g = nullptr, *partial_d = nullptr, *coef_tmp = nullptr;
   FabScratch fab{};  // allocated on the first FAB / CW call
   CwScratch cw{};
+  float *mm_x01 = nullptr, *mm_adv = nullptr, *mm_mn = nullptr, *mm_mx = nullptr;  // advb_attack_minmax scratch (first use)
   float* host_cost = nullptr;  // pinned: CW's batch-wide early-stop scalar (cw.py:107-110)
 
   template <typename Tp>
@@ -796,13 +797,12 @@ int advb_grad(advb_handle* h, int what, const float* x, const int64_t* y, float*
   return 0;
 }
 
-int advb_attack(advb_handle* h, const advb_attack_desc* atk, const float* x, const int64_t* y, const float* start,
-                float* x_adv, int B, int T, void* cuda_stream) {
-  ADVB_TRY(check_call(h, B, T));
-  ADVB_CHECK(atk != nullptr && x != nullptr && y != nullptr && x_adv != nullptr, "null argument");
-  ADVB_CHECK(x != x_adv, "x_adv must not alias x");
-  CallScope scope(h);
-  cudaStream_t st = static_cast<cudaStream_t>(cuda_stream);
+}  // extern "C"
+
+namespace {
+// The attack loops (caller holds a CallScope and has validated the arguments).
+int run_attack(advb_handle* h, const advb_attack_desc* atk, const float* x, const int64_t* y, const float* start, float* x_adv,
+               int B, int T, cudaStream_t st) {
   const int n_global = atk->n_global_batch > 0 ? atk->n_global_batch : B;
   const int64_t n = (int64_t)B * T;
   ADVB_TRY(model_prepare(h, st));
@@ -878,6 +878,37 @@ int advb_attack(advb_handle* h, const advb_attack_desc* atk, const float* x, con
       set_error("attack kind not implemented in the native loop");
       return 1;
   }
+}
+}  // namespace
+
+extern "C" {
+
+int advb_attack(advb_handle* h, const advb_attack_desc* atk, const float* x, const int64_t* y, const float* start,
+                float* x_adv, int B, int T, void* cuda_stream) {
+  ADVB_TRY(check_call(h, B, T));
+  ADVB_CHECK(atk != nullptr && x != nullptr && y != nullptr && x_adv != nullptr, "null argument");
+  ADVB_CHECK(x != x_adv, "x_adv must not alias x");
+  CallScope scope(h);
+  return run_attack(h, atk, x, y, start, x_adv, B, T, static_cast<cudaStream_t>(cuda_stream));
+}
+
+int advb_attack_minmax(advb_handle* h, const advb_attack_desc* atk, const float* x_raw, const int64_t* y, const float* start,
+                       float* x_adv_raw, int B, int T, void* cuda_stream) {
+  ADVB_TRY(check_call(h, B, T));
+  ADVB_CHECK(atk != nullptr && x_raw != nullptr && y != nullptr && x_adv_raw != nullptr, "null argument");
+  CallScope scope(h);
+  cudaStream_t st = static_cast<cudaStream_t>(cuda_stream);
+  if (h->mm_x01 == nullptr) {
+    const size_t n = (size_t)h->Bmax * h->T;
+    ADVB_TRY(h->alloc(&h->mm_x01, n));
+    ADVB_TRY(h->alloc(&h->mm_adv, n));
+    ADVB_TRY(h->alloc(&h->mm_mn, h->Bmax));
+    ADVB_TRY(h->alloc(&h->mm_mx, h->Bmax));
+  }
+  ADVB_TRY(minmax_scale(x_raw, h->mm_x01, h->mm_mn, h->mm_mx, B, T, st));
+  ADVB_TRY(run_attack(h, atk, h->mm_x01, y, start, h->mm_adv, B, T, st));
+  ADVB_TRY(minmax_revert(h->mm_adv, h->mm_mn, h->mm_mx, x_adv_raw, B, T, st));
+  return 0;
 }
 
 int advb_projection_linf(const float* t, const float* w, const float* b, float* d, int R, int T, void* cuda_stream) {

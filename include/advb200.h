@@ -104,6 +104,14 @@ ADVB_API int advb_set_option(advb_handle* h, const char* key, int value);
 ADVB_API int advb_attack(advb_handle* h, const advb_attack_desc* atk, const float* x, const int64_t* y, const float* start,
                 float* x_adv, int B, int T, void* cuda_stream);
 
+/* the three steps every call site wraps around the attack, in ONE call -
+ *   x01, mn, mx = to_minmax(x_raw);  adv01 = atk(x01, y);  x_adv_raw = revert_minmax(adv01, mn, mx)
+ * (evaluate_models_on_adversarial_attacks.py:219-221, src/trainer.py:425-427,469-471,491-493,510-512,538-540;
+ * src/aa/utils.py:4-14).  Same arguments as advb_attack, raw (unscaled) waveforms in and out; x_adv_raw may alias x_raw.
+ * A constant clip yields NaN, as in the reference (division by max - min = 0). */
+ADVB_API int advb_attack_minmax(advb_handle* h, const advb_attack_desc* atk, const float* x_raw, const int64_t* y,
+                       const float* start, float* x_adv_raw, int B, int T, void* cuda_stream);
+
 /* Replaces  model(x)  (lcnn.py:239-243, specrnet.py:211-214, rawnet3.py:73-137): logits [B] (the (B,1) column).
  * Used for clean inference on the attacked batch (evaluate_models_on_adversarial_attacks.py:236-238) and
  * FAB's _get_predicted_label (fab.py:80-85). */

@@ -207,6 +207,32 @@ def test_minmax_roundtrip_and_edge_cases(cuda_device):
     assert torch.equal(back, oatk.revert_minmax(w01, wmn, wmx))
 
 
+def test_fused_minmax_attack_matches_the_three_call_sequence(cuda_device):
+    """to_minmax -> atk -> revert_minmax in one native call (advb_attack_minmax) is bit-identical to the
+    three calls the reference makes (evaluate_models_on_adversarial_attacks.py:219-221)."""
+    from advb200 import aa
+    from advb200 import torchattacks as ta
+
+    name = "lcnn_lfcc_t16000"
+    case, x, y, holder, state, fwd, eng = _setup(name, cuda_device)
+    raw = (0.3 * (x - 0.4)).to(cuda_device)  # an unscaled waveform batch
+    yd = y.to(cuda_device)
+    for atk in (ta.FGSM(holder, eps=0.005), ta.PGD(holder, eps=0.001, steps=3), ta.PGDL2(holder, eps=0.1, steps=2)):
+        atk.set_training_mode(True, False)
+        torch.manual_seed(7)
+        torch.cuda.manual_seed(7)
+        x01, mn, mx = aa.to_minmax(raw)
+        want = aa.revert_minmax(atk(x01, yd), mn, mx)
+        torch.manual_seed(7)
+        torch.cuda.manual_seed(7)
+        got = aa.attack_minmax(atk, raw, yd)
+        assert torch.equal(got, want), type(atk).__name__
+        assert not atk._fused_minmax
+    ref = raw.cpu()
+    mn, mx = ref.min(dim=1, keepdim=True)[0], ref.max(dim=1, keepdim=True)[0]
+    assert (got.cpu() - ref).abs().max().item() <= 0.11 * (mx - mn).max().item()  # an L2 ball of 0.1 in the scaled domain
+
+
 def test_handle_errors_are_loud(cuda_device):
     from advb200 import engine
 
