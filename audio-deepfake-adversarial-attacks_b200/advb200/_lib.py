@@ -9,6 +9,7 @@ import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libadvb200.so")
+LIB_PATH = os.environ.get("ADVB_LIB", LIB_PATH)  # tuning experiments: an alternative build of the same library
 
 MODEL_LCNN, MODEL_SPECRNET, MODEL_RAWNET3 = 1, 2, 3
 FRONTEND_NONE, FRONTEND_LFCC, FRONTEND_MFCC = 0, 1, 2

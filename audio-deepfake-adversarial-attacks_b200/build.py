@@ -36,7 +36,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
         o = os.path.join(objdir, src[:-3] + ".o")
         objs.append(o)
         if force or _stale(o, [s] + headers):
-            cmd = [NVCC] + FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-c", s, "-o", o]
+            cmd = [NVCC] + FLAGS + os.environ.get("NVCC_EXTRA", "").split() + (["-Xptxas", "-v"] if verbose else []) + ["-c", s, "-o", o]
             jobs.append(cmd)
 
     def run(cmd):

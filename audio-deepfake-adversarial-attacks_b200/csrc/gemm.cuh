@@ -58,6 +58,7 @@ struct GemmArgs {
   const unsigned char* gate2_mask = nullptr;
   int ld_gate2 = 0;
   const char* tag = "gemm";
+  long long* prof = nullptr;  // diagnostics (ADVB_GEMM_PROF=1): clock64 phase counters of CTA 0, see gemm_tc.cu
 };
 
 // Bytes of the packed tcgen05 weight image of an (N, ntap, K) view.

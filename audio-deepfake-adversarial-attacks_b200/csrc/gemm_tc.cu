@@ -31,6 +31,7 @@ constexpr int GW = 256;        // worker threads
 constexpr int GT = GW + 32;    // + the MMA warp
 constexpr int SINC_K = 251, SINC_STRIDE = 10;
 
+
 __host__ __device__ constexpr int tile_n(int N) { return (N % 256 == 0) ? 256 : 128; }
 
 __device__ __forceinline__ float4 ldg4(const float* p) { return __ldg(reinterpret_cast<const float4*>(p)); }
@@ -55,12 +56,43 @@ __device__ __forceinline__ void split_rn(float x, float& hi, float& lo) {
 }
 
 // The fused epilogue on 4 consecutive columns n..n+3 of valid row r (clip = r / Tp).
-// (A variant that fetched the row operands of a whole 32 x 32 block before the first store was measured and dropped: with 17
-// warps the kernel is capped at 96 registers, the extra live values spilled the fill warps' prefetch registers - which makes
-// their loads synchronous - and the plain GEMMs got 1.5-2x slower; without spills it was no faster than this one.)
-__device__ __forceinline__ void epi_apply(const GemmArgs& a, int r, int clip, int n, float4 v) {
+// Per-column operands (EpiCol) are fetched once per 32-column block, not once per row: with 227 KB of the SM's 256 KB given to
+// shared memory the L1 is ~28 KB and the output stores keep evicting those vectors, so every row paid 3 L2 round trips
+// (measured: +12 us per 128 x 256 tile for the bias / ReLU / BatchNorm epilogue over the plain one).
+// Per-row operands (EpiRow: addend, gate masks) of ROWS_AHEAD rows are fetched back to back before the first of them is
+// finished: written one row at a time, the possible aliasing of `out` with `add` pins every load behind the previous row's
+// stores and each row pays a full HBM latency.  (Fetching all 8 rows of a block up front needs ~100 registers; with 17 warps
+// the kernel is capped at 96 and the spills landed on the fill warps' prefetch registers.)
+struct EpiCol {
+  float4 bias, bn_s, bn_t, gs, gs2;
+};
+struct EpiRow {  // `add` and `add2` are never used by the same GEMM: one register set serves both
+  float4 addv;
+  uchar4 gm, gm2;
+};
+__device__ __forceinline__ EpiCol epi_load_col(const GemmArgs& a, int n) {
+  EpiCol c;
+  c.bias = c.bn_s = c.bn_t = c.gs = c.gs2 = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (a.bias != nullptr && !a.bias_per_clip) c.bias = ldg4(a.bias + n);
+  if (a.bn_scale != nullptr) c.bn_s = ldg4(a.bn_scale + n), c.bn_t = ldg4(a.bn_shift + n);
+  if (a.gate_scale != nullptr) c.gs = ldg4(a.gate_scale + n);
+  if (a.gate2_scale != nullptr) c.gs2 = ldg4(a.gate2_scale + n);
+  return c;
+}
+__device__ __forceinline__ EpiRow epi_load_row(const GemmArgs& a, int r, int n) {
+  EpiRow w;
+  w.addv = make_float4(0.f, 0.f, 0.f, 0.f);
+  w.gm = w.gm2 = make_uchar4(0, 0, 0, 0);
+  if (a.add != nullptr) w.addv = *reinterpret_cast<const float4*>(a.add + (size_t)r * a.ld_add + n);  // may alias out: plain load
+  else if (a.add2 != nullptr) w.addv = ldg4(a.add2 + (size_t)r * a.ld_add2 + n);
+  if (a.gate_scale != nullptr) w.gm = __ldg(reinterpret_cast<const uchar4*>(a.gate_mask + (size_t)r * a.ld_gate + n));
+  if (a.gate2_scale != nullptr) w.gm2 = __ldg(reinterpret_cast<const uchar4*>(a.gate2_mask + (size_t)r * a.ld_gate2 + n));
+  return w;
+}
+__device__ __forceinline__ void epi_finish(const GemmArgs& a, int r, int clip, int n, float4 v, const EpiCol& c, const EpiRow& w) {
   if (a.bias != nullptr) {
-    const float4 b = ldg4(a.bias + (a.bias_per_clip ? (size_t)clip * a.N : (size_t)0) + n);
+    // (per-clip bias: the attention layer only, 128 floats per clip)
+    const float4 b = a.bias_per_clip ? ldg4(a.bias + (size_t)clip * a.N + n) : c.bias;
     v.x += b.x, v.y += b.y, v.z += b.z, v.w += b.w;
   }
   if (a.relu) {
@@ -70,54 +102,91 @@ __device__ __forceinline__ void epi_apply(const GemmArgs& a, int r, int clip, in
     v.x = fmaxf(v.x, 0.f), v.y = fmaxf(v.y, 0.f), v.z = fmaxf(v.z, 0.f), v.w = fmaxf(v.w, 0.f);
   }
   if (a.bn_scale != nullptr) {
-    const float4 s = ldg4(a.bn_scale + n), t = ldg4(a.bn_shift + n);
-    v.x = fmaf(v.x, s.x, t.x), v.y = fmaf(v.y, s.y, t.y), v.z = fmaf(v.z, s.z, t.z), v.w = fmaf(v.w, s.w, t.w);
+    v.x = fmaf(v.x, c.bn_s.x, c.bn_t.x), v.y = fmaf(v.y, c.bn_s.y, c.bn_t.y);
+    v.z = fmaf(v.z, c.bn_s.z, c.bn_t.z), v.w = fmaf(v.w, c.bn_s.w, c.bn_t.w);
   }
-  if (a.add != nullptr) {
-    const float4 d = *reinterpret_cast<const float4*>(a.add + (size_t)r * a.ld_add + n);  // may alias out: plain load
-    v.x += d.x, v.y += d.y, v.z += d.z, v.w += d.w;
-  }
+  if (a.add != nullptr) v.x += w.addv.x, v.y += w.addv.y, v.z += w.addv.z, v.w += w.addv.w;
   if (a.out != nullptr) {
     float4 o = v;
-    if (a.gate_scale != nullptr) {
-      const float4 s = ldg4(a.gate_scale + n);
-      const uchar4 m = __ldg(reinterpret_cast<const uchar4*>(a.gate_mask + (size_t)r * a.ld_gate + n));
-      o.x = m.x ? v.x * s.x : 0.f, o.y = m.y ? v.y * s.y : 0.f, o.z = m.z ? v.z * s.z : 0.f, o.w = m.w ? v.w * s.w : 0.f;
-    }
+    if (a.gate_scale != nullptr)
+      o.x = w.gm.x ? v.x * c.gs.x : 0.f, o.y = w.gm.y ? v.y * c.gs.y : 0.f, o.z = w.gm.z ? v.z * c.gs.z : 0.f,
+      o.w = w.gm.w ? v.w * c.gs.w : 0.f;
     *reinterpret_cast<float4*>(a.out + (size_t)r * a.ldc + n) = o;
   }
   if (a.out2 != nullptr) {
     float4 o = v;
-    if (a.add2 != nullptr) {
-      const float4 d = ldg4(a.add2 + (size_t)r * a.ld_add2 + n);
-      o.x += d.x, o.y += d.y, o.z += d.z, o.w += d.w;
-    }
-    if (a.gate2_scale != nullptr) {
-      const float4 s = ldg4(a.gate2_scale + n);
-      const uchar4 m = __ldg(reinterpret_cast<const uchar4*>(a.gate2_mask + (size_t)r * a.ld_gate2 + n));
-      o.x = m.x ? o.x * s.x : 0.f, o.y = m.y ? o.y * s.y : 0.f, o.z = m.z ? o.z * s.z : 0.f, o.w = m.w ? o.w * s.w : 0.f;
-    }
+    if (a.add2 != nullptr) o.x += w.addv.x, o.y += w.addv.y, o.z += w.addv.z, o.w += w.addv.w;
+    if (a.gate2_scale != nullptr)
+      o.x = w.gm2.x ? o.x * c.gs2.x : 0.f, o.y = w.gm2.y ? o.y * c.gs2.y : 0.f, o.z = w.gm2.z ? o.z * c.gs2.z : 0.f,
+      o.w = w.gm2.w ? o.w * c.gs2.w : 0.f;
     *reinterpret_cast<float4*>(a.out2 + (size_t)r * a.ld2 + n) = o;
   }
 }
+__device__ __forceinline__ void epi_apply(const GemmArgs& a, int r, int clip, int n, float4 v) {  // SIMT kernel
+  epi_finish(a, r, clip, n, v, epi_load_col(a, n), epi_load_row(a, r, n));
+}
 
-// One 32-row x 32-column block of a tile: transpose the TMEM values (thread = row) through the warp's private staging tile and
-// finish with thread = (row 4 p + rsub, columns cc..cc+3) so that every global access of the epilogue is a coalesced 16-byte one.
-__device__ __forceinline__ void epi_block(const GemmArgs& a, float* stg, int lane, int rbase, int rsub, int cc, unsigned valid,
-                                          const int (&clip_p)[8], int n, const uint32_t (&v0)[16], const uint32_t (&v1)[16]) {
+// Tensor-core kernels: 16 consecutive columns n0..n0+15 of row r, straight from the tcgen05.ld registers (thread = row).
+// No shared-memory transpose: the phase counters (ADVB_GEMM_PROF) showed the transposing epilogue at 33-53 thousand cycles
+// per 128 x 256 tile - ~130 cycles per LDS / STS, because the tensor core's operand reads own the shared-memory pipe - which
+// made every GEMM with K <= 384 epilogue-bound (the MMA warp waited for a free accumulator 40 % of its time).  Here each
+// thread reads / writes 64 contiguous bytes of its own row (4 x 16 B; the warp touches 32 rows per instruction, L2 merges
+// the sectors), per-column vectors are warp-uniform broadcast loads, and the ReLU / gate masks move as one 16-byte word.
+__device__ __forceinline__ void epi_direct16(const GemmArgs& a, int r, int clip, int n0, const uint32_t (&v)[16]) {
+  float4 addv[4];
+  uint4 gm = make_uint4(0, 0, 0, 0), gm2 = make_uint4(0, 0, 0, 0);
+  const float* addp = a.add != nullptr ? a.add + (size_t)r * a.ld_add + n0
+                                       : (a.add2 != nullptr ? a.add2 + (size_t)r * a.ld_add2 + n0 : nullptr);
+  if (addp != nullptr) {
 #pragma unroll
-  for (int j = 0; j < 16; ++j) {
-    stg[lane * 33 + j] = __uint_as_float(v0[j]);
-    stg[lane * 33 + 16 + j] = __uint_as_float(v1[j]);
+    for (int j = 0; j < 4; ++j) addv[j] = *reinterpret_cast<const float4*>(addp + 4 * j);  // `add` may alias out: plain loads
   }
-  __syncwarp();
+  if (a.gate_scale != nullptr) gm = *reinterpret_cast<const uint4*>(a.gate_mask + (size_t)r * a.ld_gate + n0);
+  if (a.gate2_scale != nullptr) gm2 = *reinterpret_cast<const uint4*>(a.gate2_mask + (size_t)r * a.ld_gate2 + n0);
+  const uint32_t gmw[4] = {gm.x, gm.y, gm.z, gm.w}, gm2w[4] = {gm2.x, gm2.y, gm2.z, gm2.w};
+  uint32_t mb[4] = {0u, 0u, 0u, 0u};
 #pragma unroll
-  for (int p = 0; p < 8; ++p) {
-    const int rl = 4 * p + rsub;
-    const float4 v = make_float4(stg[rl * 33 + cc], stg[rl * 33 + cc + 1], stg[rl * 33 + cc + 2], stg[rl * 33 + cc + 3]);
-    if ((valid >> p) & 1u) epi_apply(a, rbase + rl, clip_p[p], n, v);
+  for (int j = 0; j < 4; ++j) {
+    const int n = n0 + 4 * j;
+    float4 x = make_float4(__uint_as_float(v[4 * j]), __uint_as_float(v[4 * j + 1]), __uint_as_float(v[4 * j + 2]),
+                           __uint_as_float(v[4 * j + 3]));
+    if (a.bias != nullptr) {
+      const float4 b = ldg4(a.bias + (a.bias_per_clip ? (size_t)clip * a.N : (size_t)0) + n);
+      x.x += b.x, x.y += b.y, x.z += b.z, x.w += b.w;
+    }
+    if (a.relu) {
+      mb[j] = (x.x > 0.f ? 1u : 0u) | (x.y > 0.f ? 0x100u : 0u) | (x.z > 0.f ? 0x10000u : 0u) | (x.w > 0.f ? 0x1000000u : 0u);
+      x.x = fmaxf(x.x, 0.f), x.y = fmaxf(x.y, 0.f), x.z = fmaxf(x.z, 0.f), x.w = fmaxf(x.w, 0.f);
+    }
+    if (a.bn_scale != nullptr) {
+      const float4 sc = ldg4(a.bn_scale + n), sh = ldg4(a.bn_shift + n);
+      x.x = fmaf(x.x, sc.x, sh.x), x.y = fmaf(x.y, sc.y, sh.y), x.z = fmaf(x.z, sc.z, sh.z), x.w = fmaf(x.w, sc.w, sh.w);
+    }
+    if (a.add != nullptr) x.x += addv[j].x, x.y += addv[j].y, x.z += addv[j].z, x.w += addv[j].w;
+    if (a.out != nullptr) {
+      float4 o = x;
+      if (a.gate_scale != nullptr) {
+        const float4 sc = ldg4(a.gate_scale + n);
+        const uint32_t m = gmw[j];
+        o.x = (m & 0xffu) ? x.x * sc.x : 0.f, o.y = (m & 0xff00u) ? x.y * sc.y : 0.f;
+        o.z = (m & 0xff0000u) ? x.z * sc.z : 0.f, o.w = (m & 0xff000000u) ? x.w * sc.w : 0.f;
+      }
+      *reinterpret_cast<float4*>(a.out + (size_t)r * a.ldc + n) = o;
+    }
+    if (a.out2 != nullptr) {
+      float4 o = x;
+      if (a.add2 != nullptr) o.x += addv[j].x, o.y += addv[j].y, o.z += addv[j].z, o.w += addv[j].w;
+      if (a.gate2_scale != nullptr) {
+        const float4 sc = ldg4(a.gate2_scale + n);
+        const uint32_t m = gm2w[j];
+        o.x = (m & 0xffu) ? o.x * sc.x : 0.f, o.y = (m & 0xff00u) ? o.y * sc.y : 0.f;
+        o.z = (m & 0xff0000u) ? o.z * sc.z : 0.f, o.w = (m & 0xff000000u) ? o.w * sc.w : 0.f;
+      }
+      *reinterpret_cast<float4*>(a.out2 + (size_t)r * a.ld2 + n) = o;
+    }
   }
-  __syncwarp();
+  if (a.relu && a.mask_out != nullptr)
+    *reinterpret_cast<uint4*>(a.mask_out + (size_t)r * a.ld_mask + n0) = make_uint4(mb[0], mb[1], mb[2], mb[3]);
 }
 
 __device__ __forceinline__ bool row_valid(const GemmArgs& a, int r, int& clip) {
@@ -266,18 +335,10 @@ __global__ void __launch_bounds__(GT, 1) gemm_tc_kernel(const GemmArgs a, const 
     // ---- epilogue ----
     mbar_wait(&bar_done, 0u);
     tc_fence_after();
-    float* stg = reinterpret_cast<float*>(base) + (size_t)warp * (32 * 33);  // per-warp transpose tile (ring is idle now)
     const int q = warp & 3, half = warp >> 2;
-    const int rsub = lane >> 3, cc = (lane & 7) * 4;
-    int clip_p[8];
-    unsigned valid = 0;
-#pragma unroll
-    for (int p = 0; p < 8; ++p) {
-      const int r = m0 + 32 * q + 4 * p + rsub;
-      int clip;
-      valid |= (row_valid(a, r, clip) ? 1u : 0u) << p;
-      clip_p[p] = clip;
-    }
+    const int r = m0 + 32 * q + lane;  // thread = row
+    int clip;
+    const bool valid = row_valid(a, r, clip);
     const uint32_t taddr = tmem + ((uint32_t)(32 * q) << 16);
 #pragma unroll 1
     for (int cb = 0; cb < NT / 64; ++cb) {
@@ -286,7 +347,10 @@ __global__ void __launch_bounds__(GT, 1) gemm_tc_kernel(const GemmArgs a, const 
       tmem_ld16_issue(taddr + col0, v0);
       tmem_ld16_issue(taddr + col0 + 16, v1);
       tmem_ld_wait();
-      epi_block(a, stg, lane, m0 + 32 * q, rsub, cc, valid, clip_p, ntile * NT + col0 + cc, v0, v1);
+      if (valid) {
+        epi_direct16(a, r, clip, ntile * NT + col0, v0);
+        epi_direct16(a, r, clip, ntile * NT + col0 + 16, v1);
+      }
     }
   }
   tc_fence_before();
@@ -346,7 +410,6 @@ __global__ void __launch_bounds__(GW + 32 + 32 * EPW, 1) gemm_tc_persistent_kern
 
   extern __shared__ unsigned char smem_raw[];
   unsigned char* base = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  float* stg_all = reinterpret_cast<float*>(base + (size_t)NSTAGE * STAGE_BYTES);  // EPW x (32 x 33) floats
   __shared__ uint64_t bar_full[NSTAGE], bar_empty[NSTAGE], acc_full[2], acc_empty[2];
   __shared__ uint32_t tmem_base_s;
 
@@ -379,6 +442,18 @@ __global__ void __launch_bounds__(GW + 32 + 32 * EPW, 1) gemm_tc_persistent_kern
     // ---- MMA warp ----
     const bool leader = elect_one();
     int g = 0, it = 0;
+    const bool prof = a.prof != nullptr && blockIdx.x == 0;
+    long long pc_acc = 0, pc_full = 0, pc_issue = 0, t_last = clock64();
+#ifdef ADVB_GEMM_PROFILE  // diagnostic build only (python build.py with NVCC_EXTRA=-DADVB_GEMM_PROFILE): the counters cost registers
+#define GPROF(acc_)                    \
+  if (prof) {                          \
+    const long long now_ = clock64();  \
+    acc_ += now_ - t_last;             \
+    t_last = now_;                     \
+  }
+#else
+#define GPROF(acc_)
+#endif
 #pragma unroll 1
     for (int t = item0; t < n_items; t += item_step, ++it) {
       const int buf = it & 1;
@@ -386,12 +461,14 @@ __global__ void __launch_bounds__(GW + 32 + 32 * EPW, 1) gemm_tc_persistent_kern
         mbar_wait(&acc_empty[buf], (uint32_t)(((it >> 1) - 1) & 1));
         tc_fence_after();
       }
+      GPROF(pc_acc)
       const uint32_t dcol = tmem + buf * NT;
 #pragma unroll 1
       for (int kc = 0; kc < NKC; ++kc, ++g) {
         const int s = g % NSTAGE;
         wait_hot(&bar_full[s], (uint32_t)((g / NSTAGE) & 1));
         tc_fence_after();
+        GPROF(pc_full)
         const uint32_t a_hi = smem_u32(base + (size_t)s * STAGE_BYTES), a_lo = a_hi + A_BYTES;
         const uint32_t w_hi = a_lo + A_BYTES, w_lo = w_hi + W_BYTES;
         if (leader) {
@@ -410,8 +487,10 @@ __global__ void __launch_bounds__(GW + 32 + 32 * EPW, 1) gemm_tc_persistent_kern
           if (kc == NKC - 1) mma_commit(&acc_full[buf]);
         }
         __syncwarp();
+        GPROF(pc_issue)
       }
     }
+    if (prof && lane == 0) a.prof[0] = pc_acc, a.prof[1] = pc_full, a.prof[2] = pc_issue, a.prof[3] = it;
   } else if (warp < GW / 32) {
     // ---- fill warps ----
     const int c4 = tid & 7, r0 = tid >> 3;
@@ -461,16 +540,20 @@ __global__ void __launch_bounds__(GW + 32 + 32 * EPW, 1) gemm_tc_persistent_kern
 #pragma unroll
     for (int d = 0; d < PF; ++d) prefetch_next(rv[d], rok[d]);
     int t = item0, kc = 0, g = 0;
+    const bool prof = a.prof != nullptr && blockIdx.x == 0 && warp == 0;
+    long long pc_empty = 0, pc_work = 0, pc_fence = 0, pc_pref = 0, t_last = clock64();
 #pragma unroll 1
     while (t < n_items) {
 #pragma unroll
       for (int d = 0; d < PF; ++d) {
         if (t < n_items) {
           const int s = g % NSTAGE, use = g / NSTAGE;
+          GPROF(pc_work)
           if (use > 0) {
             wait_hot(&bar_empty[s], (uint32_t)((use - 1) & 1));
             tc_fence_after();
           }
+          GPROF(pc_empty)
           unsigned char* st = base + (size_t)s * STAGE_BYTES;
           if (tid == 0) {
             mbar_expect_tx(&bar_full[s], 2 * W_BYTES);
@@ -495,55 +578,63 @@ __global__ void __launch_bounds__(GW + 32 + 32 * EPW, 1) gemm_tc_persistent_kern
             *reinterpret_cast<float4*>(st + off) = hi;
             *reinterpret_cast<float4*>(st + A_BYTES + off) = lo;
           }
+          GPROF(pc_work)
           fence_proxy_async();
+          GPROF(pc_fence)
           __syncwarp();
           if (lane == 0) mbar_arrive(&bar_full[s]);
           prefetch_next(rv[d], rok[d]);
+          GPROF(pc_pref)
           ++g;
           if (++kc == NKC) kc = 0, t += item_step;
         }
       }
     }
+    if (prof && lane == 0) a.prof[4] = pc_empty, a.prof[5] = pc_work, a.prof[9] = pc_fence, a.prof[10] = pc_pref;
   } else {
     // ---- epilogue warps ----
     const int ew = warp - (GW / 32 + 1);      // 0..EPW-1
     const int q = warp & 3, half = ew >> 2;   // TMEM lane quarter is fixed by the hardware warp id
     constexpr int NBLK = NT / 32 / (EPW / 4);  // 32-column blocks per warp
-    float* stg = stg_all + (size_t)ew * (32 * 33);
-    const int rsub = lane >> 3, cc = (lane & 7) * 4;
     int it = 0;
+    const bool prof = a.prof != nullptr && blockIdx.x == 0 && ew == 0;
+    long long pc_wait = 0, pc_tmem = 0, pc_store = 0, t_last = clock64();
 #pragma unroll 1
     for (int t = item0; t < n_items; t += item_step, ++it) {
       const int buf = it & 1;
       const int m0 = ((t / ntn) * CL + crank) * 128, ntile = t % ntn;
-      int clip_p[8];
-      unsigned valid = 0;
-#pragma unroll
-      for (int p = 0; p < 8; ++p) {
-        const int r = m0 + 32 * q + 4 * p + rsub;
-        int clip;
-        valid |= (row_valid(a, r, clip) ? 1u : 0u) << p;
-        clip_p[p] = clip;
-      }
+      const int r = m0 + 32 * q + lane;  // thread = row
+      int clip;
+      const bool valid = row_valid(a, r, clip);
+      GPROF(pc_store)
       mbar_wait(&acc_full[buf], (uint32_t)((it >> 1) & 1));
       tc_fence_after();
+      GPROF(pc_wait)
       const uint32_t taddr = tmem + ((uint32_t)(32 * q) << 16) + buf * NT;
 #pragma unroll 1
       for (int cb = 0; cb < NBLK; ++cb) {
         const int col0 = (half * NBLK + cb) * 32;
         uint32_t v0[16], v1[16];
+        GPROF(pc_store)
         tmem_ld16_issue(taddr + col0, v0);
         tmem_ld16_issue(taddr + col0 + 16, v1);
         tmem_ld_wait();
+        GPROF(pc_tmem)
         if (cb == NBLK - 1) {  // accumulator drained: hand it back before the global stores of this block
           tc_fence_before();
           __syncwarp();
           if (lane == 0) mbar_arrive(&acc_empty[buf]);
         }
-        epi_block(a, stg, lane, m0 + 32 * q, rsub, cc, valid, clip_p, ntile * NT + col0 + cc, v0, v1);
+        if (valid) {
+          epi_direct16(a, r, clip, ntile * NT + col0, v0);
+          epi_direct16(a, r, clip, ntile * NT + col0 + 16, v1);
+        }
       }
     }
+    GPROF(pc_store)
+    if (prof && lane == 0) a.prof[6] = pc_wait, a.prof[7] = pc_tmem, a.prof[8] = pc_store;
   }
+#undef GPROF
   tc_fence_before();
   __syncthreads();
   if (CL > 1) cluster_sync_all();  // no CTA leaves while a peer may still signal its barriers
@@ -656,15 +747,17 @@ int tune_epw() {
 }
 int tune_cluster() {  // cluster size along M for the weight multicast (1 = off)
   static const int v = [] {
-    const int c = tune_env("ADVB_GEMM_CLUSTER", 2);
-    return (c == 1 || c == 2 || c == 4) ? c : 2;
+    // default 1: the 2-CTA weight multicast measured +1.4 % (146 vs 144 clips/s) - the kernel is not L2 -> SM bound - and is
+    // kept as an opt-in (ADVB_GEMM_CLUSTER=2 or 4)
+    const int c = tune_env("ADVB_GEMM_CLUSTER", 1);
+    return (c == 1 || c == 2 || c == 4) ? c : 1;
   }();
   return v;
 }
 
 template <int NT, int NSTAGE, int EPW, int CL>
 int launch_tc_persistent(const GemmArgs& a, int passes, cudaStream_t stream) {
-  constexpr size_t smem = (size_t)NSTAGE * (2 * 128 * 128 + 2 * NT * 128) + EPW * 32 * 33 * sizeof(float) + 1024;
+  constexpr size_t smem = (size_t)NSTAGE * (2 * 128 * 128 + 2 * NT * 128) + 1024;
   constexpr int PT = GW + 32 + 32 * EPW;
   auto kern = gemm_tc_persistent_kernel<NT, NSTAGE, EPW, CL>;
   ADVB_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -694,10 +787,27 @@ int launch_tc_persistent(const GemmArgs& a, int passes, cudaStream_t stream) {
   const int n_items = (a.N / NT) * cdiv(cdiv(a.M, 128), CL);
   cfg.gridDim = dim3(std::min(n_items, max_clusters) * CL);
   GemmArgs ac = a;
+  static const bool prof_on = tune_env("ADVB_GEMM_PROF", 0) != 0;
+  static long long* prof_dev = nullptr;
+  if (prof_on) {
+    if (prof_dev == nullptr) ADVB_CUDA_OK(cudaMalloc(&prof_dev, 16 * sizeof(long long)));
+    ADVB_CUDA_OK(cudaMemsetAsync(prof_dev, 0, 16 * sizeof(long long), stream));
+    ac.prof = prof_dev;
+  }
   int p = passes, ni = n_items;
   void* params[3] = {&ac, &p, &ni};
   ADVB_CUDA_OK(cudaLaunchKernelExC(&cfg, reinterpret_cast<const void*>(kern), params));
   ADVB_KERNEL_OK(a.tag, stream);
+  if (prof_on) {  // diagnostics only: synchronous read-back of CTA 0's phase counters (cycles)
+    long long hcnt[16];
+    ADVB_CUDA_OK(cudaMemcpyAsync(hcnt, prof_dev, sizeof(hcnt), cudaMemcpyDeviceToHost, stream));
+    ADVB_CUDA_OK(cudaStreamSynchronize(stream));
+    fprintf(stderr,
+            "GEMMPROF %s M=%d N=%d K=%d taps=%d NT=%d tiles(cta0)=%lld | mma: acc_wait %lld full_wait %lld issue %lld | fill: "
+            "empty_wait %lld convert+sts %lld fence %lld arrive+prefetch %lld | epi: full_wait %lld tmem %lld store %lld\n",
+            a.tag, a.M, a.N, a.K, a.ntap, NT, hcnt[3], hcnt[0], hcnt[1], hcnt[2], hcnt[4], hcnt[5], hcnt[9], hcnt[10], hcnt[6], hcnt[7],
+            hcnt[8]);
+  }
   return 0;
 }
 
