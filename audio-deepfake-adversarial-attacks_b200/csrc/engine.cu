@@ -79,7 +79,7 @@ struct advb_handle {
 
   // frontend
   float2* tw = nullptr;
-  float *dB = nullptr, *mass_partial = nullptr, *g_coef = nullptr;
+  float *dB = nullptr, *g_dB = nullptr, *mass_partial = nullptr, *g_coef = nullptr;
   int *klo = nullptr, *kcnt = nullptr, *mlo = nullptr, *mcnt = nullptr;
   FrontendState fst{};
   FrontendTables ftb{};
@@ -404,7 +404,7 @@ int lcnn_backward(advb_handle* h, const float* x, const int64_t* y, int B, int m
   else
     ADVB_TRY(conv0_backward(k0.gout, k0.codes, h->t("m_transform.0.weight"), h->g_coef, B, k0.H, k0.W, k0.Ho, k0.Wo, st));
   ADVB_TRY(frontend_backward(h->ftb, h->fst, x, B, h->T, h->dB, h->g_coef, (long long)h->F * 80, 80, 1,
-                             h->mass_partial, gx, st));
+                             h->mass_partial, h->g_dB, gx, st));
   return 0;
 }
 
@@ -567,7 +567,7 @@ int specrnet_backward(advb_handle* h, const float* x, const int64_t* y, int B, i
     ADVB_TRY(sr_block_backward(h->sr[i], in, gin, B, i == 0, h->sr_bn4, tags[i], st));
   }
   ADVB_TRY(frontend_backward(h->ftb, h->fst, x, B, h->T, h->dB, h->g_coef, (long long)h->F * 80, 80, 1, h->mass_partial,
-                             gx, st));
+                             h->g_dB, gx, st));
   return 0;
 }
 
@@ -716,7 +716,7 @@ int advb_create(advb_handle** out, const advb_model_desc* d) {
   if (h->alloc(&h->tw, 512) || h->alloc(&h->klo, 128) || h->alloc(&h->kcnt, 128) ||
       h->alloc(&h->mlo, 257) || h->alloc(&h->mcnt, 257) || h->alloc(&h->fst.gmax_packed, 1) ||
       h->alloc(&h->fst.n_clamped, 1) || h->alloc(&h->fst.mass_total, 1) ||
-      h->alloc(&h->dB, B * h->F * 128) || h->alloc(&h->g_coef, B * h->F * 80) ||
+      h->alloc(&h->dB, B * h->F * 128) || h->alloc(&h->g_dB, B * h->F * 128) || h->alloc(&h->g_coef, B * h->F * 80) ||
       h->alloc(&h->coef_tmp, B * h->F * 80) ||
       h->alloc(&h->mass_partial, (size_t)frontend_mass_blocks(h->Bmax, h->T)) || h->alloc(&h->logits, B) ||
       h->alloc(&h->grad, B * h->T) || h->alloc(&h->partial_g, B * ROW_CHUNKS) ||
@@ -955,7 +955,7 @@ int advb_frontend_bwd(advb_handle* h, const float* x, const float* g_coeff, floa
   // forward first: backward needs the batch arg-max / floor state of this input
   ADVB_TRY(frontend_forward(h->ftb, h->fst, x, B, T, h->dB, h->coef_tmp, (long long)80 * h->F, 1, h->F, 0, st));
   ADVB_TRY(frontend_backward(h->ftb, h->fst, x, B, T, h->dB, g_coeff, (long long)80 * h->F, 1, h->F, h->mass_partial,
-                             g_x, st));
+                             h->g_dB, g_x, st));
   return 0;
 }
 

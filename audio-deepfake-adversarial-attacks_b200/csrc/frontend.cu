@@ -15,12 +15,15 @@
 //   fe_floor_dct  : floor at (batch max - 80), DCT by shared-memory matrix, strided store, clamped-element count
 //   fe_floor_mass : (only when the floor is active) sum of the gradient mass of clamped elements, which autograd
 //                   routes to the batch arg-max element; two-stage fixed-order reduction (deterministic)
-//   fe_bwd        : per tile of 16 hops: dct^T, recompute FFT/power/energies, dB+floor backward, filterbank^T,
-//                   one-sided inverse DFT as a packed complex FFT, window, overlap-add and reflect-pad fold in
-//                   shared memory in a fixed order (deterministic, no atomics), gradient store
+//   fe_dct_t      : d dB = d coefficients x dct^T for every frame (register-tiled fp32 SIMT product, (B,F,128) out)
+//   fe_bwd        : per tile of 40 hops, one warp per frame pair: recompute FFT/power/energies, dB+floor backward,
+//                   filterbank^T, one-sided inverse DFT as a packed complex FFT, window, overlap-add and reflect-pad
+//                   fold in shared memory in a fixed order (deterministic, no atomics), gradient store
 #include "frontend.cuh"
 
 #include <math.h>
+
+#include <algorithm>
 
 namespace advb {
 
@@ -35,13 +38,14 @@ constexpr int NFILT = 128;
 constexpr int NCOEF = 80;
 constexpr int FE_WARPS = 8;
 constexpr int FE_THREADS = FE_WARPS * 32;
-constexpr int FB_WARPS = 10;     // backward: an interior tile of 16 hops needs 19-20 frames = 10 frame pairs = one round
+constexpr int FB_WARPS = 24;     // backward: a tile of 40 hops needs 43-45 frames = at most 23 frame pairs = one warp each
 constexpr int FB_THREADS = FB_WARPS * 32;
 constexpr int PSTRIDE = 260;     // padded 257
-constexpr int DCT_LD = 84;       // padded row of the dct matrix in shared memory: 16-byte aligned rows, conflict-free float4 reads
-constexpr int TILE_HOPS = 16;    // backward tile = 16 hops = 2560 samples
+constexpr int TILE_HOPS = 40;    // backward tile = 40 hops = 6400 samples (10 % of the frames are recomputed by a neighbour)
 constexpr int TILE_S = TILE_HOPS * HOP;
-constexpr int NF_MAX = 24;       // frames a backward tile may need (19 interior, a few more at the right edge)
+constexpr int NF_MAX = 2 * FB_WARPS;  // frames a backward tile may need (checked on the host: one frame pair per warp)
+constexpr int DT_FR = 64;        // fe_dct_t: frames per work item
+constexpr int DT_GLD = 84;       // fe_dct_t: padded row of the staged coefficient gradients (16-byte aligned rows)
 
 __device__ __forceinline__ int reflect_index(int j, int T) {
   if (j < 0) j = -j;
@@ -216,7 +220,6 @@ __global__ void __launch_bounds__(FE_THREADS) fe_power_db_kernel(const float* __
   float2* s_tw = reinterpret_cast<float2*>(smem);                    // 512 float2
   float* s_win = smem + 1024;                                        // 400
   float2* s_fft = reinterpret_cast<float2*>(s_win + 400);            // FE_WARPS * (FFT_A + FFT_B) float2
-  float* s_pw = reinterpret_cast<float*>(s_fft + FE_WARPS * (FFT_A + FFT_B));  // FE_WARPS * 2 * PSTRIDE
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   for (int i = tid; i < 512; i += FE_THREADS) s_tw[i] = tb.tw[i];
   for (int i = tid; i < WIN; i += FE_THREADS) s_win[i] = tb.window[i];
@@ -228,7 +231,7 @@ __global__ void __launch_bounds__(FE_THREADS) fe_power_db_kernel(const float* __
   const bool has_b = (ta + 1) < F;
   float2* bufA = s_fft + warp * (FFT_A + FFT_B);
   float2* bufB = bufA + FFT_A;
-  float* pa = s_pw + warp * 2 * PSTRIDE;
+  float* pa = reinterpret_cast<float*>(bufA);  // power vectors live in buffer A, which is scratch once Z sits in buffer B
   float* pb = pa + PSTRIDE;
   const float* xb = x + (size_t)b * T;
 
@@ -400,25 +403,89 @@ __global__ void __launch_bounds__(1024) fe_mass_reduce_kernel(const float* __res
 }
 
 // ---------------------------------------------------------------------------------------------------
-// Backward: d coefficients -> d waveform for one tile of TILE_S samples of one clip.
-__global__ void __launch_bounds__(FB_THREADS) fe_bwd_kernel(const float* __restrict__ x, int T, int F,
-                                                             FrontendTables tb, FrontendState st, float top_db,
-                                                             const float* __restrict__ gcoef, long long g_clip_stride,
-                                                             long long g_stride_f, long long g_stride_c,
-                                                             float* __restrict__ gx, int n_tiles, int n_clips) {
+// Backward pre-pass: d dB (before the floor) = d coefficients x dct^T, one (B F, 80) x (80, 128) fp32 SIMT product.
+// Thread = 8 frames x 4 filters (32 accumulators): per 4 coefficients 4 conflict-free LDS.128 of dct^T and 8 broadcast
+// LDS.128 of the gradients feed 128 FMAs.  Persistent: dct^T (40 KB) is staged once per CTA.
+__global__ void __launch_bounds__(256) fe_dct_t_kernel(const float* __restrict__ gcoef, long long g_clip_stride,
+                                                        long long g_stride_f, long long g_stride_c, int F,
+                                                        FrontendTables tb, float* __restrict__ gd, int n_blocks,
+                                                        int n_clips) {
+  extern __shared__ __align__(16) float smem[];
+  float* s_w = smem;                  // 80 x 128: s_w[c][m] = dct[m][c]
+  float* s_g = s_w + NCOEF * NFILT;   // DT_FR x DT_GLD
+  const int tid = threadIdx.x, mq = tid & 31, fg = tid >> 5;
+  for (int i = tid; i < NFILT * NCOEF; i += 256) {
+    const int c = i / NFILT, m = i - c * NFILT;
+    s_w[i] = tb.dct[m * NCOEF + c];
+  }
+  for (int work = blockIdx.x; work < n_blocks * n_clips; work += gridDim.x) {
+    const int b = work / n_blocks, f0 = (work - b * n_blocks) * DT_FR;
+    const float* gb = gcoef + (size_t)b * g_clip_stride;
+    __syncthreads();  // the previous item's reads of s_g are done
+    if (g_stride_c == 1) {
+      for (int i = tid; i < DT_FR * NCOEF; i += 256) {
+        const int f = i / NCOEF, c = i - f * NCOEF;
+        s_g[f * DT_GLD + c] = (f0 + f < F) ? gb[(long long)(f0 + f) * g_stride_f + c] : 0.f;
+      }
+    } else {
+      for (int i = tid; i < DT_FR * NCOEF; i += 256) {
+        const int c = i / DT_FR, f = i - c * DT_FR;
+        s_g[f * DT_GLD + c] = (f0 + f < F) ? gb[(long long)(f0 + f) * g_stride_f + (long long)c * g_stride_c] : 0.f;
+      }
+    }
+    __syncthreads();
+    float acc[8][4];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[j][0] = acc[j][1] = acc[j][2] = acc[j][3] = 0.f;
+#pragma unroll 2
+    for (int c = 0; c < NCOEF; c += 4) {
+      float4 w[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) w[i] = *reinterpret_cast<const float4*>(s_w + (c + i) * NFILT + 4 * mq);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const float4 g = *reinterpret_cast<const float4*>(s_g + (fg * 8 + j) * DT_GLD + c);
+        acc[j][0] = fmaf(g.w, w[3].x, fmaf(g.z, w[2].x, fmaf(g.y, w[1].x, fmaf(g.x, w[0].x, acc[j][0]))));
+        acc[j][1] = fmaf(g.w, w[3].y, fmaf(g.z, w[2].y, fmaf(g.y, w[1].y, fmaf(g.x, w[0].y, acc[j][1]))));
+        acc[j][2] = fmaf(g.w, w[3].z, fmaf(g.z, w[2].z, fmaf(g.y, w[1].z, fmaf(g.x, w[0].z, acc[j][2]))));
+        acc[j][3] = fmaf(g.w, w[3].w, fmaf(g.z, w[2].w, fmaf(g.y, w[1].w, fmaf(g.x, w[0].w, acc[j][3]))));
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int f = f0 + fg * 8 + j;
+      if (f < F)
+        *reinterpret_cast<float4*>(gd + ((size_t)b * F + f) * NFILT + 4 * mq) =
+            make_float4(acc[j][0], acc[j][1], acc[j][2], acc[j][3]);
+    }
+  }
+}
+
+// Frames whose (reflected) support can touch the samples [s0, s1) of a clip of T samples / F frames.
+__host__ __device__ __forceinline__ void tile_frames(int s0, int s1, int T, int F, int& t_lo, int& t_hi) {
+  t_lo = (s0 - 199 + 159 + 160 * 4) / 160 - 4;
+  if (t_lo < 0) t_lo = 0;
+  t_hi = (s1 - 1 + 200) / 160;
+  if (s1 >= T - 202) t_hi = F - 1;
+  if (t_hi > F - 1) t_hi = F - 1;
+}
+
+// Backward: d dB -> d waveform for one tile of TILE_S samples of one clip.  One warp per frame pair, 24 warps per SM.
+// Shared memory per warp is the two FFT buffers only (8.5 KB): after the forward FFT buffer A is scratch and holds the
+// power / d power / d energy vectors, and the windowless frame gradients stay in buffer B until the overlap-add reads
+// them there.  (With a private dct^T, power and frame-gradient buffers the kernel fitted 10 warps per SM and sat on
+// shared-memory latency: 15 % of the warp slots, 29 % of the issue slots, profiles/r01_ncu_full_final.md.)
+__global__ void __launch_bounds__(FB_THREADS, 1) fe_bwd_kernel(const float* __restrict__ x, int T, int F,
+                                                                FrontendTables tb, FrontendState st, float top_db,
+                                                                const float* __restrict__ gd, float* __restrict__ gx,
+                                                                int n_tiles, int n_clips) {
   extern __shared__ __align__(16) float smem[];
   float2* s_tw = reinterpret_cast<float2*>(smem);                  // 512 float2
   float* s_win = smem + 1024;                                      // 400
-  float* s_dct = s_win + 400;                                      // 128 * DCT_LD
-  float2* s_fft = reinterpret_cast<float2*>(s_dct + NFILT * DCT_LD);  // FB_WARPS * (FFT_A + FFT_B) float2
-  float* s_pw = reinterpret_cast<float*>(s_fft + FB_WARPS * (FFT_A + FFT_B));  // FB_WARPS * 2 * PSTRIDE (power, d power)
-  float* s_ge = s_pw + FB_WARPS * 2 * PSTRIDE;  // FB_WARPS * 2 * 128       (d energy)
-  float* s_gc = s_ge + FB_WARPS * 2 * NFILT;    // FB_WARPS * 2 * 80        (d coefficients)
-  float* s_yw = s_gc + FB_WARPS * 2 * NCOEF;    // NF_MAX * 400             (windowed frame gradients)
+  float2* s_fft = reinterpret_cast<float2*>(s_win + 400);          // FB_WARPS * (FFT_A + FFT_B) float2
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   for (int i = tid; i < 512; i += FB_THREADS) s_tw[i] = tb.tw[i];
   for (int i = tid; i < WIN; i += FB_THREADS) s_win[i] = tb.window[i];
-  for (int i = tid; i < NFILT * NCOEF; i += FB_THREADS) s_dct[(i / NCOEF) * DCT_LD + (i % NCOEF)] = tb.dct[i];
   __syncthreads();
 
   float vmax;
@@ -427,159 +494,136 @@ __global__ void __launch_bounds__(FB_THREADS) fe_bwd_kernel(const float* __restr
   const float floor_v = vmax - top_db;
   const float mass_total = *st.mass_total;
 
-  // persistent over (clip, tile): the 47 KB of tables above are staged once per CTA instead of once per tile (the
-  // prologue was 18 % of the kernel's samples when every tile was its own CTA)
-  for (int work = blockIdx.x; work < n_tiles * n_clips; work += gridDim.x) {
-  const int b = work / n_tiles, tile = work - b * n_tiles;
-  const int s0 = tile * TILE_S;
-  const int s1 = min(T, s0 + TILE_S);
-  // frames whose (reflected) support can touch [s0, s1)
-  int t_lo = (s0 - 199 + 159 + 160 * 4) / 160 - 4;
-  if (t_lo < 0) t_lo = 0;
-  int t_hi = (s1 - 1 + 200) / 160;
-  if (s1 >= T - 202) t_hi = F - 1;
-  if (t_hi > F - 1) t_hi = F - 1;
-  const int nf = t_hi - t_lo + 1;  // host guarantees nf <= NF_MAX
-  const float* xb = x + (size_t)b * T;
-
   float2* bufA = s_fft + warp * (FFT_A + FFT_B);
   float2* bufB = bufA + FFT_A;
-  float* pa = s_pw + warp * 2 * PSTRIDE;
+  float* pa = reinterpret_cast<float*>(bufA);  // power, then d power        (buffer A is free once Z sits in buffer B)
   float* pb = pa + PSTRIDE;
-  float* gea = s_ge + warp * 2 * NFILT;
-  float* geb = gea + NFILT;
-  float* gca = s_gc + warp * 2 * NCOEF;
-  float* gcb = gca + NCOEF;
+  float* gea = pb + PSTRIDE;                   // d energy
+  float* geb = gea + NFILT;                    // 2 * 260 + 2 * 128 = 776 floats <= 1024
 
-  for (int pair = warp; 2 * pair < nf; pair += FB_WARPS) {
-    const int ta = t_lo + 2 * pair;
-    const bool has_b = (2 * pair + 1 < nf);  // frame ta+1 is inside [t_lo, t_hi] (hence < F)
-    // 1. d coefficients
-    for (int c = lane; c < NCOEF; c += 32) {
-      const size_t base = (size_t)b * g_clip_stride + (long long)c * g_stride_c;
-      gca[c] = gcoef[base + (long long)ta * g_stride_f];
-      gcb[c] = has_b ? gcoef[base + (long long)(ta + 1) * g_stride_f] : 0.f;
-    }
-    // 2. recompute the packed FFT of both frames: Z in bufB
-    load_frame_pair(xb, T, has_b ? F : ta + 1, ta, s_win, bufA, lane);
-    warp_fft512(bufA, bufB, s_tw, lane);
-    // 3. power
-    for (int k = lane; k < NBIN; k += 32) {
-      float xar, xai, xbr, xbi;
-      unpack_bin(bufB, k, xar, xai, xbr, xbi);
-      pa[k] = xar * xar + xai * xai;
-      pb[k] = xbr * xbr + xbi * xbi;
-    }
-    __syncwarp();
-    // 4. energies, dct^T (register-tiled: 4 filters x 2 frames per lane, float4 shared-memory reads), dB / floor
-    //    backward, d energy
-    {
-      float ea[4], eb[4], gda[4], gdb[4];
+  for (int work = blockIdx.x; work < n_tiles * n_clips; work += gridDim.x) {
+    const int b = work / n_tiles, tile = work - b * n_tiles;
+    const int s0 = tile * TILE_S;
+    const int s1 = min(T, s0 + TILE_S);
+    int t_lo, t_hi;
+    tile_frames(s0, s1, T, F, t_lo, t_hi);
+    const int nf = t_hi - t_lo + 1;  // host guarantees nf <= NF_MAX: warp w owns frames t_lo + 2 w, t_lo + 2 w + 1
+    const float* xb = x + (size_t)b * T;
+
+    if (2 * warp < nf) {
+      const int ta = t_lo + 2 * warp;
+      const bool has_b = (2 * warp + 1 < nf);  // frame ta+1 is inside [t_lo, t_hi] (hence < F)
+      // 1. d dB of both frames (4 filters per lane), in flight during the FFT
+      const size_t rowa = ((size_t)b * F + ta) * NFILT;
+      float gda[4], gdb[4];
 #pragma unroll
       for (int i = 0; i < 4; ++i) {
-        filter_energy(tb.fb, tb.klo, tb.kcnt, pa, pb, lane + 32 * i, ea[i], eb[i]);
-        gda[i] = 0.f;
-        gdb[i] = 0.f;
+        gda[i] = __ldg(gd + rowa + lane + 32 * i);
+        gdb[i] = has_b ? __ldg(gd + rowa + NFILT + lane + 32 * i) : 0.f;
       }
-#pragma unroll 4
-      for (int c = 0; c < NCOEF; c += 4) {
-        const float4 ga = *reinterpret_cast<const float4*>(gca + c);
-        const float4 gb = *reinterpret_cast<const float4*>(gcb + c);
+      // 2. recompute the packed FFT of both frames: Z in bufB
+      load_frame_pair(xb, T, has_b ? F : ta + 1, ta, s_win, bufA, lane);
+      warp_fft512(bufA, bufB, s_tw, lane);
+      // 3. power
+      for (int k = lane; k < NBIN; k += 32) {
+        float xar, xai, xbr, xbi;
+        unpack_bin(bufB, k, xar, xai, xbr, xbi);
+        pa[k] = xar * xar + xai * xai;
+        pb[k] = xbr * xbr + xbi * xbi;
+      }
+      __syncwarp();
+      // 4. energies, dB / floor backward, d energy
+      {
+        const float k10 = 4.342944819032518f;  // 10 / ln 10
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
-          const float4 w = *reinterpret_cast<const float4*>(s_dct + (lane + 32 * i) * DCT_LD + c);
-          gda[i] = fmaf(w.x, ga.x, fmaf(w.y, ga.y, fmaf(w.z, ga.z, fmaf(w.w, ga.w, gda[i]))));
-          gdb[i] = fmaf(w.x, gb.x, fmaf(w.y, gb.y, fmaf(w.z, gb.z, fmaf(w.w, gb.w, gdb[i]))));
+          const int m = lane + 32 * i;
+          float ea, eb;
+          filter_energy(tb.fb, tb.klo, tb.kcnt, pa, pb, m, ea, eb);
+          if ((unsigned)(rowa + m) == amax_idx) gda[i] += mass_total;
+          if ((unsigned)(rowa + NFILT + m) == amax_idx) gdb[i] += mass_total;
+          const float da = to_db(ea), db = to_db(eb);
+          gea[m] = (da > floor_v && ea >= 1e-10f) ? gda[i] * k10 / ea : 0.f;
+          geb[m] = (has_b && db > floor_v && eb >= 1e-10f) ? gdb[i] * k10 / eb : 0.f;
         }
       }
-      const size_t rowa = ((size_t)b * F + ta) * NFILT;
-      const float k10 = 4.342944819032518f;  // 10 / ln 10
+      __syncwarp();
+      // 5. d power (overwrites the power vectors), kept in registers: step 6 overwrites buffer A
+      float ga[9], gb[9];
 #pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        const int m = lane + 32 * i;
-        if ((unsigned)(rowa + m) == amax_idx) gda[i] += mass_total;
-        if ((unsigned)(rowa + NFILT + m) == amax_idx) gdb[i] += mass_total;
-        const float da = to_db(ea[i]), db = to_db(eb[i]);
-        gea[m] = (da > floor_v && ea[i] >= 1e-10f) ? gda[i] * k10 / ea[i] : 0.f;
-        geb[m] = (has_b && db > floor_v && eb[i] >= 1e-10f) ? gdb[i] * k10 / eb[i] : 0.f;
+      for (int i = 0; i < 9; ++i) {
+        const int k = lane + 32 * i;
+        float sa = 0.f, sb = 0.f;
+        if (k < NBIN) {
+          const int m0 = tb.mlo[k], n = tb.mcnt[k];
+          for (int q = 0; q < n; ++q) {
+            const float w = __ldg(tb.fb + (size_t)k * NFILT + m0 + q);
+            sa += w * gea[m0 + q];
+            sb += w * geb[m0 + q];
+          }
+        }
+        ga[i] = sa;
+        gb[i] = sb;
       }
-    }
-    __syncwarp();
-    // 5. d power (overwrites the power buffers)
-    for (int k = lane; k < NBIN; k += 32) {
-      const int m0 = tb.mlo[k], n = tb.mcnt[k];
-      float sa = 0.f, sb = 0.f;
-      for (int i = 0; i < n; ++i) {
-        const float w = __ldg(tb.fb + (size_t)k * NFILT + m0 + i);
-        sa += w * gea[m0 + i];
-        sb += w * geb[m0 + i];
+      __syncwarp();
+      // 6. conj(H) into bufA, H = Ha + i Hb Hermitian-extended one-sided gradients (no doubling of interior bins)
+#pragma unroll
+      for (int i = 0; i < 9; ++i) {
+        const int k = lane + 32 * i;
+        if (k < NBIN) {
+          float xar, xai, xbr, xbi;
+          unpack_bin(bufB, k, xar, xai, xbr, xbi);
+          if (k == 0 || k == 256) {
+            bufA[k] = make_float2(2.f * ga[i] * xar, -(2.f * gb[i] * xbr));
+          } else {
+            const float har = ga[i] * xar, hai = ga[i] * xai, hbr = gb[i] * xbr, hbi = gb[i] * xbi;
+            bufA[k] = make_float2(har - hbi, -(hai + hbr));
+            bufA[NFFT - k] = make_float2(har + hbi, -(hbr - hai));
+          }
+        }
       }
-      pa[k] = sa;
-      pb[k] = sb;
+      __syncwarp();
+      // 7. W = conj(FFT(conj H)): ya = Re, yb = -Im; stays in bufB (natural order) for the overlap-add below
+      warp_fft512(bufA, bufB, s_tw, lane);
     }
-    __syncwarp();
-    // 6. conj(H) into bufA, H = Ha + i Hb Hermitian-extended one-sided gradients (no doubling of interior bins)
-    for (int k = lane; k < NBIN; k += 32) {
-      float xar, xai, xbr, xbi;
-      unpack_bin(bufB, k, xar, xai, xbr, xbi);
-      const float ga = pa[k], gb = pb[k];
-      if (k == 0 || k == 256) {
-        bufA[k] = make_float2(2.f * ga * xar, -(2.f * gb * xbr));
-      } else {
-        const float har = ga * xar, hai = ga * xai, hbr = gb * xbr, hbi = gb * xbi;
-        bufA[k] = make_float2(har - hbi, -(hai + hbr));
-        bufA[NFFT - k] = make_float2(har + hbi, -(hbr - hai));
-      }
-    }
-    __syncwarp();
-    // 7. W = conj(FFT(conj H)): ya = Re, yb = -Im   (result in bufB; Z is no longer needed)
-    warp_fft512(bufA, bufB, s_tw, lane);
-    // 8. window and park per-frame
-    float* ywa = s_yw + (2 * pair) * WIN;
-    for (int n = lane; n < WIN; n += 32) {
-      const float w = s_win[n];
-      const float2 v = bufB[n + WOFF];
-      ywa[n] = w * v.x;
-      if (has_b) ywa[WIN + n] = -(w * v.y);
-    }
-    __syncwarp();
-  }
-  __syncthreads();
+    __syncthreads();
 
-  // overlap-add + reflect-pad fold, fixed order
-  for (int sl = tid; sl < s1 - s0; sl += FB_THREADS) {
-    const int s = s0 + sl;
-    float acc = 0.f;
+    // window + overlap-add + reflect-pad fold, fixed order
+    for (int sl = tid; sl < s1 - s0; sl += FB_THREADS) {
+      const int s = s0 + sl;
+      float acc = 0.f;
 #pragma unroll 1
-    for (int v = 0; v < 3; ++v) {
-      int j;
-      if (v == 0) j = s;
-      else if (v == 1) {
-        if (s < 1 || s > 256) continue;
-        j = -s;
-      } else {
-        if (s > T - 2 || s < T - 2 - 255) continue;
-        j = 2 * T - 2 - s;
+      for (int v = 0; v < 3; ++v) {
+        int j;
+        if (v == 0) j = s;
+        else if (v == 1) {
+          if (s < 1 || s > 256) continue;
+          j = -s;
+        } else {
+          if (s > T - 2 || s < T - 2 - 255) continue;
+          j = 2 * T - 2 - s;
+        }
+        int tf = (j - 199 + 159 + 160 * 4) / 160 - 4;
+        int tl = (j + 200 + 160 * 4) / 160 - 4;
+        if (tf < t_lo) tf = t_lo;
+        if (tl > t_hi) tl = t_hi;
+        for (int t = tf; t <= tl; ++t) {
+          const int fi = t - t_lo, n = j - HOP * t + 200;
+          const float2 wv = s_fft[(fi >> 1) * (FFT_A + FFT_B) + FFT_A + WOFF + n];
+          const float w = s_win[n];
+          acc += (fi & 1) ? -__fmul_rn(w, wv.y) : __fmul_rn(w, wv.x);
+        }
       }
-      int tf = (j - 199 + 159 + 160 * 4) / 160 - 4;
-      int tl = (j + 200 + 160 * 4) / 160 - 4;
-      if (tf < t_lo) tf = t_lo;
-      if (tl > t_hi) tl = t_hi;
-      for (int t = tf; t <= tl; ++t) acc += s_yw[(t - t_lo) * WIN + (j - HOP * t + 200)];
+      gx[(size_t)b * T + s] = acc;
     }
-    gx[(size_t)b * T + s] = acc;
-  }
-  __syncthreads();  // s_yw is reused by the next tile
+    __syncthreads();  // the FFT buffers are reused by the next tile
   }
 }
 
-size_t fe_fwd_smem() { return (size_t)(1024 + 400 + FE_WARPS * 2 * (FFT_A + FFT_B) + FE_WARPS * 2 * PSTRIDE) * sizeof(float); }
+size_t fe_fwd_smem() { return (size_t)(1024 + 400 + FE_WARPS * 2 * (FFT_A + FFT_B)) * sizeof(float); }  // 74 KB: 3 CTAs / SM
 size_t fe_dct_smem() { return (size_t)(NFILT * NCOEF + 16 * NFILT) * sizeof(float); }
-size_t fe_bwd_smem() {
-  return (size_t)(1024 + 400 + NFILT * DCT_LD + FB_WARPS * 2 * (FFT_A + FFT_B) + FB_WARPS * 2 * PSTRIDE + FB_WARPS * 2 * NFILT +
-                  FB_WARPS * 2 * NCOEF + NF_MAX * WIN) *
-         sizeof(float);
-}
+size_t fe_dct_t_smem() { return (size_t)(NCOEF * NFILT + DT_FR * DT_GLD) * sizeof(float); }
+size_t fe_bwd_smem() { return (size_t)(1024 + 400 + FB_WARPS * 2 * (FFT_A + FFT_B)) * sizeof(float); }
 
 }  // namespace
 
@@ -592,6 +636,7 @@ int frontend_init_constants(float2* tw, cudaStream_t stream) {
   ADVB_CUDA_OK(cudaFuncSetAttribute(fe_power_db_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fe_fwd_smem()));
   ADVB_CUDA_OK(cudaFuncSetAttribute(fe_floor_dct_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fe_dct_smem()));
   ADVB_CUDA_OK(cudaFuncSetAttribute(fe_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fe_bwd_smem()));
+  ADVB_CUDA_OK(cudaFuncSetAttribute(fe_dct_t_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fe_dct_t_smem()));
   return 0;
 }
 
@@ -621,7 +666,7 @@ int frontend_forward(const FrontendTables& tb, const FrontendState& st, const fl
 
 int frontend_backward(const FrontendTables& tb, const FrontendState& st, const float* x, int B, int T,
                       const float* dB, const float* gcoef, long long g_clip_stride, long long g_stride_f,
-                      long long g_stride_c, float* mass_partial, float* gx, cudaStream_t stream) {
+                      long long g_stride_c, float* mass_partial, float* gd, float* gx, cudaStream_t stream) {
   const int F = frontend_frames(T);
   dim3 g1(cdiv(F, 2 * FE_WARPS), B);
   fe_floor_mass_kernel<<<g1, FE_THREADS, 0, stream>>>(dB, F, tb, st, 80.0f, gcoef, g_clip_stride, g_stride_f,
@@ -629,10 +674,18 @@ int frontend_backward(const FrontendTables& tb, const FrontendState& st, const f
   ADVB_KERNEL_OK("fe_floor_mass", stream);
   fe_mass_reduce_kernel<<<1, 1024, 0, stream>>>(mass_partial, (int)(g1.x * g1.y), st);
   ADVB_KERNEL_OK("fe_mass_reduce", stream);
+  const int n_blocks = cdiv(F, DT_FR);
+  const int g2 = n_blocks * B < 148 * 3 ? n_blocks * B : 148 * 3;  // persistent: 61 KB of shared memory -> 3 CTAs / SM
+  fe_dct_t_kernel<<<g2, 256, fe_dct_t_smem(), stream>>>(gcoef, g_clip_stride, g_stride_f, g_stride_c, F, tb, gd, n_blocks, B);
+  ADVB_KERNEL_OK("fe_dct_t", stream);
   const int n_tiles = cdiv(T, TILE_S);
-  const int grid = n_tiles * B < 148 ? n_tiles * B : 148;  // one persistent CTA per SM (211 KB of shared memory each)
-  fe_bwd_kernel<<<grid, FB_THREADS, fe_bwd_smem(), stream>>>(x, T, F, tb, st, 80.0f, gcoef, g_clip_stride, g_stride_f,
-                                                           g_stride_c, gx, n_tiles, B);
+  for (int tile = 0; tile < n_tiles; ++tile) {
+    int t_lo, t_hi;
+    tile_frames(tile * TILE_S, std::min(T, (tile + 1) * TILE_S), T, F, t_lo, t_hi);
+    ADVB_CHECK(t_hi - t_lo + 1 <= NF_MAX, "frontend backward: a tile needs more frames than the kernel has warps for");
+  }
+  const int grid = n_tiles * B < 148 ? n_tiles * B : 148;  // one persistent CTA per SM (210 KB of shared memory each)
+  fe_bwd_kernel<<<grid, FB_THREADS, fe_bwd_smem(), stream>>>(x, T, F, tb, st, 80.0f, gd, gx, n_tiles, B);
   ADVB_KERNEL_OK("fe_bwd", stream);
   return 0;
 }

@@ -30,9 +30,10 @@ int frontend_prepare(const FrontendTables& tb, cudaStream_t stream);
 int frontend_forward(const FrontendTables& tb, const FrontendState& st, const float* x, int B, int T, float* dB,
                      float* out, long long clip_stride, long long stride_f, long long stride_c, long long offset,
                      cudaStream_t stream);
-// gcoef read through the same kind of strides (no offset: pass the shifted pointer); gx (B,T)
+// gcoef read through the same kind of strides (no offset: pass the shifted pointer); gd: (B,F,128) scratch for the
+// gradient of the dB tensor; gx (B,T)
 int frontend_backward(const FrontendTables& tb, const FrontendState& st, const float* x, int B, int T,
                       const float* dB, const float* gcoef, long long g_clip_stride, long long g_stride_f,
-                      long long g_stride_c, float* mass_partial, float* gx, cudaStream_t stream);
+                      long long g_stride_c, float* mass_partial, float* gd, float* gx, cudaStream_t stream);
 
 }  // namespace advb

@@ -163,6 +163,7 @@ def kernel_bytes(B, F, T):
     out["fe_power_db"] = B * 4 * (T + F * 128)
     out["fe_floor_dct"] = B * 4 * (F * 128 + F * 80)
     out["fe_bwd"] = B * 4 * (T + F * 80 + T)        # waveform (STFT recompute) + d coefficients in, d waveform out
+    out["fe_dct_t"] = B * 4 * (F * 80 + F * 128)     # d coefficients in, d dB out (scratch re-read by fe_bwd)
     out["pgd_step"] = B * 4 * 4 * T                   # x, g, adv in; adv out
     return out
 
