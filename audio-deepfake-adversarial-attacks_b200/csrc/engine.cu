@@ -81,6 +81,7 @@ struct advb_handle {
   float2* tw = nullptr;
   float *dB = nullptr, *g_dB = nullptr, *mass_partial = nullptr, *g_coef = nullptr;
   int *klo = nullptr, *kcnt = nullptr, *mlo = nullptr, *mcnt = nullptr;
+  float* dctT = nullptr;
   FrontendState fst{};
   FrontendTables ftb{};
 
@@ -196,6 +197,7 @@ void refresh_frontend_tables(advb_handle* h) {
   }
   tb.dct = h->t("frontend.dct_mat");
   tb.tw = h->tw;
+  tb.dctT = h->dctT;
   tb.klo = h->klo;
   tb.kcnt = h->kcnt;
   tb.mlo = h->mlo;
@@ -713,7 +715,7 @@ int advb_create(advb_handle** out, const advb_model_desc* d) {
     return 0;
   }
   if (check_frontend_tensors(h)) return fail();
-  if (h->alloc(&h->tw, 512) || h->alloc(&h->klo, 128) || h->alloc(&h->kcnt, 128) ||
+  if (h->alloc(&h->tw, 512) || h->alloc(&h->dctT, 128 * 80) || h->alloc(&h->klo, 128) || h->alloc(&h->kcnt, 128) ||
       h->alloc(&h->mlo, 257) || h->alloc(&h->mcnt, 257) || h->alloc(&h->fst.gmax_packed, 1) ||
       h->alloc(&h->fst.n_clamped, 1) || h->alloc(&h->fst.mass_total, 1) ||
       h->alloc(&h->dB, B * h->F * 128) || h->alloc(&h->g_dB, B * h->F * 128) || h->alloc(&h->g_coef, B * h->F * 80) ||

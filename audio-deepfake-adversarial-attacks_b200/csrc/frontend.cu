@@ -196,6 +196,11 @@ __global__ void fe_tables_kernel(const float* __restrict__ fb, int* klo, int* kc
   }
 }
 
+__global__ void fe_dct_transpose_kernel(const float* __restrict__ dct, float* __restrict__ dctT) {
+  const int i = threadIdx.x + blockIdx.x * blockDim.x;  // i = c * 128 + m
+  if (i < NFILT * NCOEF) dctT[i] = dct[(i % NFILT) * NCOEF + i / NFILT];
+}
+
 __global__ void fe_twiddle_kernel(float2* tw) {
   const int k = threadIdx.x + blockIdx.x * blockDim.x;
   if (k < 512) {
@@ -284,54 +289,74 @@ __device__ __forceinline__ void decode_gmax(unsigned long long packed, float& vm
   idx = ~(unsigned)(packed & 0xffffffffull);
 }
 
-// Forward 2: floor + DCT.  16 frames per CTA, thread = (frame, 5 coefficients).
-__global__ void __launch_bounds__(256) fe_floor_dct_kernel(const float* __restrict__ dB, int F, FrontendTables tb,
+// Forward 2: floor + DCT, (B F, 128) x (128, 80) fp32 SIMT.  60 frames per work item; thread = (coefficient quad, group of
+// 5 frames): per 4 filters 4 LDS.128 of dct rows + 5 LDS.128 of dB values feed 80 FMAs (the first version, thread =
+// (frame, 5 coefficients), issued 6 LDS per 5 FMAs).  Persistent: the dct matrix (40 KB) is staged once per CTA.
+constexpr int FD_FR = 60;    // frames per work item = 12 groups of 5
+constexpr int FD_LD = 132;   // padded dB row in shared memory (16-byte aligned; the two frame groups of a warp hit different banks)
+__global__ void __launch_bounds__(256, 3) fe_floor_dct_kernel(const float* __restrict__ dB, int F, FrontendTables tb,
                                                             FrontendState st, float top_db, float* __restrict__ out,
                                                             long long clip_stride, long long stride_f,
-                                                            long long stride_c, long long offset, int n_blocks,
-                                                            int n_clips) {
-  extern __shared__ float smem[];
-  float* s_dct = smem;                     // 128*80
-  float* s_d = s_dct + NFILT * NCOEF;      // 16*128
+                                                            long long stride_c, long long offset, int n_rows) {
+  extern __shared__ __align__(16) float smem[];
+  float* s_dct = smem;                     // 128 x 80
+  float* s_d = s_dct + NFILT * NCOEF;      // FD_FR x FD_LD
   const int tid = threadIdx.x;
   float vmax;
   unsigned amax_idx;
   decode_gmax(*st.gmax_packed, vmax, amax_idx);
   const float floor_v = vmax - top_db;
-  for (int i = tid; i < NFILT * NCOEF; i += 256) s_dct[i] = tb.dct[i];  // staged once per (persistent) CTA
+  for (int i = tid; i < NFILT * NCOEF / 4; i += 256)  // staged once per (persistent) CTA
+    reinterpret_cast<float4*>(s_dct)[i] = __ldg(reinterpret_cast<const float4*>(tb.dct) + i);
+  const int cq = tid % 20, fg = tid / 20;  // fg 0..11 active, 12 idle (threads 240..255)
   int clamped_any = 0;
-  for (int work = blockIdx.x; work < n_blocks * n_clips; work += gridDim.x) {
-    const int b = work / n_blocks, f0 = (work - b * n_blocks) * 16;
+  // rows = (clip, frame) pairs, flat: dB is (B F, 128) contiguous
+  for (int r0 = blockIdx.x * FD_FR; r0 < n_rows; r0 += gridDim.x * FD_FR) {
     __syncthreads();  // previous iteration's reads of s_d are done (and s_dct is complete on the first pass)
     int clamped = 0;
-    for (int i = tid; i < 16 * NFILT; i += 256) {
-      const int f = f0 + i / NFILT;
-      float d = 0.f;
-      if (f < F) {
-        d = dB[((size_t)b * F + f) * NFILT + (i % NFILT)];
-        if (d < floor_v) {
-          d = floor_v;
-          ++clamped;
-        }
+    for (int i = tid; i < FD_FR * (NFILT / 4); i += 256) {
+      const int fl = i >> 5, m4 = i & 31;
+      float4 d = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (r0 + fl < n_rows) {
+        d = __ldg(reinterpret_cast<const float4*>(dB + (size_t)(r0 + fl) * NFILT) + m4);
+        if (d.x < floor_v) d.x = floor_v, ++clamped;
+        if (d.y < floor_v) d.y = floor_v, ++clamped;
+        if (d.z < floor_v) d.z = floor_v, ++clamped;
+        if (d.w < floor_v) d.w = floor_v, ++clamped;
       }
-      s_d[i] = d;
+      *reinterpret_cast<float4*>(s_d + fl * FD_LD + 4 * m4) = d;
     }
     clamped_any += __syncthreads_count(clamped);  // threads that clamped something (enough for an "active" flag)
 
-    const int fl = tid >> 4, cg = tid & 15, f = f0 + fl;
-    if (f < F) {
-      float acc[5] = {0.f, 0.f, 0.f, 0.f, 0.f};
-      const float* drow = s_d + fl * NFILT;
-#pragma unroll 4
-      for (int m = 0; m < NFILT; ++m) {
-        const float d = drow[m];
-        const float* w = s_dct + m * NCOEF + cg;
+    if (fg < FD_FR / 5) {
+      float acc[5][4];
 #pragma unroll
-        for (int i = 0; i < 5; ++i) acc[i] += d * w[16 * i];
+      for (int j = 0; j < 5; ++j) acc[j][0] = acc[j][1] = acc[j][2] = acc[j][3] = 0.f;
+      const float* drow = s_d + (fg * 5) * FD_LD;
+#pragma unroll 2
+      for (int m = 0; m < NFILT; m += 4) {
+        float4 w[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) w[i] = *reinterpret_cast<const float4*>(s_dct + (m + i) * NCOEF + 4 * cq);
+#pragma unroll
+        for (int j = 0; j < 5; ++j) {
+          const float4 d = *reinterpret_cast<const float4*>(drow + j * FD_LD + m);
+          acc[j][0] = fmaf(d.w, w[3].x, fmaf(d.z, w[2].x, fmaf(d.y, w[1].x, fmaf(d.x, w[0].x, acc[j][0]))));
+          acc[j][1] = fmaf(d.w, w[3].y, fmaf(d.z, w[2].y, fmaf(d.y, w[1].y, fmaf(d.x, w[0].y, acc[j][1]))));
+          acc[j][2] = fmaf(d.w, w[3].z, fmaf(d.z, w[2].z, fmaf(d.y, w[1].z, fmaf(d.x, w[0].z, acc[j][2]))));
+          acc[j][3] = fmaf(d.w, w[3].w, fmaf(d.z, w[2].w, fmaf(d.y, w[1].w, fmaf(d.x, w[0].w, acc[j][3]))));
+        }
       }
-      float* o = out + (size_t)b * clip_stride + offset + (long long)f * stride_f;
 #pragma unroll
-      for (int i = 0; i < 5; ++i) o[(long long)(cg + 16 * i) * stride_c] = acc[i];
+      for (int j = 0; j < 5; ++j) {
+        const int r = r0 + fg * 5 + j;
+        if (r < n_rows) {
+          const int b = r / F, f = r - b * F;
+          float* o = out + (size_t)b * clip_stride + offset + (long long)f * stride_f + (long long)(4 * cq) * stride_c;
+#pragma unroll
+          for (int i = 0; i < 4; ++i) o[(long long)i * stride_c] = acc[j][i];
+        }
+      }
     }
   }
   if (tid == 0 && clamped_any > 0) atomicAdd(st.n_clamped, clamped_any);
@@ -406,32 +431,29 @@ __global__ void __launch_bounds__(1024) fe_mass_reduce_kernel(const float* __res
 // Backward pre-pass: d dB (before the floor) = d coefficients x dct^T, one (B F, 80) x (80, 128) fp32 SIMT product.
 // Thread = 8 frames x 4 filters (32 accumulators): per 4 coefficients 4 conflict-free LDS.128 of dct^T and 8 broadcast
 // LDS.128 of the gradients feed 128 FMAs.  Persistent: dct^T (40 KB) is staged once per CTA.
-__global__ void __launch_bounds__(256) fe_dct_t_kernel(const float* __restrict__ gcoef, long long g_clip_stride,
+__global__ void __launch_bounds__(256, 3) fe_dct_t_kernel(const float* __restrict__ gcoef, long long g_clip_stride,
                                                         long long g_stride_f, long long g_stride_c, int F,
-                                                        FrontendTables tb, float* __restrict__ gd, int n_blocks,
-                                                        int n_clips) {
+                                                        FrontendTables tb, float* __restrict__ gd, int n_rows) {
   extern __shared__ __align__(16) float smem[];
   float* s_w = smem;                  // 80 x 128: s_w[c][m] = dct[m][c]
   float* s_g = s_w + NCOEF * NFILT;   // DT_FR x DT_GLD
   const int tid = threadIdx.x, mq = tid & 31, fg = tid >> 5;
-  for (int i = tid; i < NFILT * NCOEF; i += 256) {
-    const int c = i / NFILT, m = i - c * NFILT;
-    s_w[i] = tb.dct[m * NCOEF + c];
-  }
-  for (int work = blockIdx.x; work < n_blocks * n_clips; work += gridDim.x) {
-    const int b = work / n_blocks, f0 = (work - b * n_blocks) * DT_FR;
-    const float* gb = gcoef + (size_t)b * g_clip_stride;
+  for (int i = tid; i < NFILT * NCOEF / 4; i += 256)
+    reinterpret_cast<float4*>(s_w)[i] = __ldg(reinterpret_cast<const float4*>(tb.dctT) + i);
+  // rows = (clip, frame) pairs, flat
+  for (int r0 = blockIdx.x * DT_FR; r0 < n_rows; r0 += gridDim.x * DT_FR) {
     __syncthreads();  // the previous item's reads of s_g are done
-    if (g_stride_c == 1) {
-      for (int i = tid; i < DT_FR * NCOEF; i += 256) {
-        const int f = i / NCOEF, c = i - f * NCOEF;
-        s_g[f * DT_GLD + c] = (f0 + f < F) ? gb[(long long)(f0 + f) * g_stride_f + c] : 0.f;
+    for (int i = tid; i < DT_FR * NCOEF; i += 256) {
+      int fl, c;
+      if (g_stride_c == 1) fl = i / NCOEF, c = i - fl * NCOEF;   // coefficient-contiguous gradients (the engine's layout)
+      else c = i / DT_FR, fl = i - c * DT_FR;                   // frame-contiguous (torchaudio's (B,80,F))
+      const int r = r0 + fl;
+      float v = 0.f;
+      if (r < n_rows) {
+        const int b = r / F, f = r - b * F;
+        v = gcoef[(size_t)b * g_clip_stride + (long long)f * g_stride_f + (long long)c * g_stride_c];
       }
-    } else {
-      for (int i = tid; i < DT_FR * NCOEF; i += 256) {
-        const int c = i / DT_FR, f = i - c * DT_FR;
-        s_g[f * DT_GLD + c] = (f0 + f < F) ? gb[(long long)(f0 + f) * g_stride_f + (long long)c * g_stride_c] : 0.f;
-      }
+      s_g[fl * DT_GLD + c] = v;
     }
     __syncthreads();
     float acc[8][4];
@@ -453,9 +475,9 @@ __global__ void __launch_bounds__(256) fe_dct_t_kernel(const float* __restrict__
     }
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
-      const int f = f0 + fg * 8 + j;
-      if (f < F)
-        *reinterpret_cast<float4*>(gd + ((size_t)b * F + f) * NFILT + 4 * mq) =
+      const int r = r0 + fg * 8 + j;
+      if (r < n_rows)
+        *reinterpret_cast<float4*>(gd + (size_t)r * NFILT + 4 * mq) =
             make_float4(acc[j][0], acc[j][1], acc[j][2], acc[j][3]);
     }
   }
@@ -621,7 +643,7 @@ __global__ void __launch_bounds__(FB_THREADS, 1) fe_bwd_kernel(const float* __re
 }
 
 size_t fe_fwd_smem() { return (size_t)(1024 + 400 + FE_WARPS * 2 * (FFT_A + FFT_B)) * sizeof(float); }  // 74 KB: 3 CTAs / SM
-size_t fe_dct_smem() { return (size_t)(NFILT * NCOEF + 16 * NFILT) * sizeof(float); }
+size_t fe_dct_smem() { return (size_t)(NFILT * NCOEF + FD_FR * FD_LD) * sizeof(float); }
 size_t fe_dct_t_smem() { return (size_t)(NCOEF * NFILT + DT_FR * DT_GLD) * sizeof(float); }
 size_t fe_bwd_smem() { return (size_t)(1024 + 400 + FB_WARPS * 2 * (FFT_A + FFT_B)) * sizeof(float); }
 
@@ -643,6 +665,8 @@ int frontend_init_constants(float2* tw, cudaStream_t stream) {
 int frontend_prepare(const FrontendTables& tb, cudaStream_t stream) {
   fe_tables_kernel<<<1, 288, 0, stream>>>(tb.fb, tb.klo, tb.kcnt, tb.mlo, tb.mcnt);
   ADVB_KERNEL_OK("fe_tables", stream);
+  fe_dct_transpose_kernel<<<cdiv(NFILT * NCOEF, 256), 256, 0, stream>>>(tb.dct, tb.dctT);
+  ADVB_KERNEL_OK("fe_dct_transpose", stream);
   return 0;
 }
 
@@ -656,10 +680,10 @@ int frontend_forward(const FrontendTables& tb, const FrontendState& st, const fl
   dim3 g1(cdiv(F, 2 * FE_WARPS), B);
   fe_power_db_kernel<<<g1, FE_THREADS, fe_fwd_smem(), stream>>>(x, T, F, tb, st, dB);
   ADVB_KERNEL_OK("fe_power_db", stream);
-  const int n_blocks = cdiv(F, 16);
-  const int g2 = n_blocks * B < 148 * 4 ? n_blocks * B : 148 * 4;  // persistent: 48 KB of shared memory -> 4 CTAs / SM
+  const int n_items = cdiv(B * F, FD_FR);
+  const int g2 = n_items < 148 * 3 ? n_items : 148 * 3;  // persistent: 71 KB of shared memory -> 3 CTAs / SM
   fe_floor_dct_kernel<<<g2, 256, fe_dct_smem(), stream>>>(dB, F, tb, st, 80.0f, out, clip_stride, stride_f, stride_c,
-                                                         offset, n_blocks, B);
+                                                         offset, B * F);
   ADVB_KERNEL_OK("fe_floor_dct", stream);
   return 0;
 }
@@ -674,9 +698,9 @@ int frontend_backward(const FrontendTables& tb, const FrontendState& st, const f
   ADVB_KERNEL_OK("fe_floor_mass", stream);
   fe_mass_reduce_kernel<<<1, 1024, 0, stream>>>(mass_partial, (int)(g1.x * g1.y), st);
   ADVB_KERNEL_OK("fe_mass_reduce", stream);
-  const int n_blocks = cdiv(F, DT_FR);
-  const int g2 = n_blocks * B < 148 * 3 ? n_blocks * B : 148 * 3;  // persistent: 61 KB of shared memory -> 3 CTAs / SM
-  fe_dct_t_kernel<<<g2, 256, fe_dct_t_smem(), stream>>>(gcoef, g_clip_stride, g_stride_f, g_stride_c, F, tb, gd, n_blocks, B);
+  const int n_items = cdiv(B * F, DT_FR);
+  const int g2 = n_items < 148 * 3 ? n_items : 148 * 3;  // persistent: 61 KB of shared memory -> 3 CTAs / SM
+  fe_dct_t_kernel<<<g2, 256, fe_dct_t_smem(), stream>>>(gcoef, g_clip_stride, g_stride_f, g_stride_c, F, tb, gd, B * F);
   ADVB_KERNEL_OK("fe_dct_t", stream);
   const int n_tiles = cdiv(T, TILE_S);
   for (int tile = 0; tile < n_tiles; ++tile) {

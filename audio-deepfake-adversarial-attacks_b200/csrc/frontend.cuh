@@ -9,6 +9,7 @@ struct FrontendTables {
   const float* dct;     // (128,80)  live buffer (frontend.dct_mat)
   const float* window;  // (400)     live buffer (Hann)
   const float2* tw;     // 512  (cos, -sin)(2 pi n / 512)   (engine-owned constants)
+  float* dctT;          // (80,128) transpose of dct            (rebuilt from dct on every call)
   int* klo;             // 128: first non-zero bin of each filter   (rebuilt from fb on every call)
   int* kcnt;            // 128: number of bins spanned
   int* mlo;             // 257: first filter touching each bin
