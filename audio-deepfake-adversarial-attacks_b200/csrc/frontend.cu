@@ -155,18 +155,31 @@ __device__ __forceinline__ void unpack_bin(const float2* z, int k, float& xar, f
   xbi = 0.5f * (q.x - p.x);
 }
 
-__device__ __forceinline__ void filter_energy(const float* __restrict__ fb, const int* __restrict__ klo,
-                                              const int* __restrict__ kcnt, const float* pa, const float* pb, int m,
-                                              float& ea, float& eb) {
-  const int k0 = klo[m], n = kcnt[m];
-  float sa = 0.f, sb = 0.f;
-  for (int i = 0; i < n; ++i) {
-    const float w = __ldg(fb + (size_t)(k0 + i) * NFILT + m);
-    sa += pa[k0 + i] * w;
-    sb += pb[k0 + i] * w;
+// Energies of filters lane, lane+32, lane+64, lane+96 for both frames.  The four sparse dot products advance together: each
+// is a chain of dependent L1 loads of run-time length, and run one after the other they were ~4 x the latency.  Per filter
+// the bins are still added in ascending order (bit-identical to the sequential form).
+__device__ __forceinline__ void filter_energy4(const float* __restrict__ fb, const int* __restrict__ klo,
+                                               const int* __restrict__ kcnt, const float* pa, const float* pb, int lane,
+                                               float (&ea)[4], float (&eb)[4]) {
+  int k0[4], n[4], nmax = 0;
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    k0[q] = klo[lane + 32 * q];
+    n[q] = kcnt[lane + 32 * q];
+    nmax = max(nmax, n[q]);
+    ea[q] = 0.f;
+    eb[q] = 0.f;
   }
-  ea = sa;
-  eb = sb;
+  for (int i = 0; i < nmax; ++i) {
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      if (i < n[q]) {
+        const float w = __ldg(fb + (size_t)(k0[q] + i) * NFILT + lane + 32 * q);
+        ea[q] += pa[k0[q] + i] * w;
+        eb[q] += pb[k0[q] + i] * w;
+      }
+    }
+  }
 }
 
 __device__ __forceinline__ float to_db(float e) { return 10.0f * log10f(fmaxf(e, 1e-10f)); }
@@ -253,19 +266,19 @@ __global__ void __launch_bounds__(FE_THREADS) fe_power_db_kernel(const float* __
   float best = -INFINITY;
   unsigned best_idx = 0xffffffffu;
   const size_t rowa = ((size_t)b * F + ta) * NFILT;
+  float ea[4], eb[4];
+  filter_energy4(tb.fb, tb.klo, tb.kcnt, pa, pb, lane, ea, eb);
 #pragma unroll
   for (int i = 0; i < NFILT / 32; ++i) {
     const int m = lane + 32 * i;
-    float ea, eb;
-    filter_energy(tb.fb, tb.klo, tb.kcnt, pa, pb, m, ea, eb);
-    const float da = to_db(ea);
+    const float da = to_db(ea[i]);
     dB[rowa + m] = da;
     if (da > best) {
       best = da;
       best_idx = (unsigned)(rowa + m);
     }
     if (has_b) {
-      const float db = to_db(eb);
+      const float db = to_db(eb[i]);
       dB[rowa + NFILT + m] = db;
       if (db > best) {
         best = db;
@@ -557,35 +570,43 @@ __global__ void __launch_bounds__(FB_THREADS, 1) fe_bwd_kernel(const float* __re
       // 4. energies, dB / floor backward, d energy
       {
         const float k10 = 4.342944819032518f;  // 10 / ln 10
+        float ea[4], eb[4];
+        filter_energy4(tb.fb, tb.klo, tb.kcnt, pa, pb, lane, ea, eb);
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
           const int m = lane + 32 * i;
-          float ea, eb;
-          filter_energy(tb.fb, tb.klo, tb.kcnt, pa, pb, m, ea, eb);
           if ((unsigned)(rowa + m) == amax_idx) gda[i] += mass_total;
           if ((unsigned)(rowa + NFILT + m) == amax_idx) gdb[i] += mass_total;
-          const float da = to_db(ea), db = to_db(eb);
-          gea[m] = (da > floor_v && ea >= 1e-10f) ? gda[i] * k10 / ea : 0.f;
-          geb[m] = (has_b && db > floor_v && eb >= 1e-10f) ? gdb[i] * k10 / eb : 0.f;
+          const float da = to_db(ea[i]), db = to_db(eb[i]);
+          gea[m] = (da > floor_v && ea[i] >= 1e-10f) ? gda[i] * k10 / ea[i] : 0.f;
+          geb[m] = (has_b && db > floor_v && eb[i] >= 1e-10f) ? gdb[i] * k10 / eb[i] : 0.f;
         }
       }
       __syncwarp();
       // 5. d power (overwrites the power vectors), kept in registers: step 6 overwrites buffer A
       float ga[9], gb[9];
+      {
+        // the 9 bins of a lane advance together (same reason as filter_energy4); per bin ascending filter order
+        int mlo9[9], n9[9], nmax = 0;
 #pragma unroll
-      for (int i = 0; i < 9; ++i) {
-        const int k = lane + 32 * i;
-        float sa = 0.f, sb = 0.f;
-        if (k < NBIN) {
-          const int m0 = tb.mlo[k], n = tb.mcnt[k];
-          for (int q = 0; q < n; ++q) {
-            const float w = __ldg(tb.fb + (size_t)k * NFILT + m0 + q);
-            sa += w * gea[m0 + q];
-            sb += w * geb[m0 + q];
+        for (int i = 0; i < 9; ++i) {
+          const int k = lane + 32 * i;
+          mlo9[i] = k < NBIN ? tb.mlo[k] : 0;
+          n9[i] = k < NBIN ? tb.mcnt[k] : 0;
+          nmax = max(nmax, n9[i]);
+          ga[i] = 0.f;
+          gb[i] = 0.f;
+        }
+        for (int q = 0; q < nmax; ++q) {
+#pragma unroll
+          for (int i = 0; i < 9; ++i) {
+            if (q < n9[i]) {
+              const float w = __ldg(tb.fb + (size_t)(lane + 32 * i) * NFILT + mlo9[i] + q);
+              ga[i] += w * gea[mlo9[i] + q];
+              gb[i] += w * geb[mlo9[i] + q];
+            }
           }
         }
-        ga[i] = sa;
-        gb[i] = sb;
       }
       __syncwarp();
       // 6. conj(H) into bufA, H = Ha + i Hb Hermitian-extended one-sided gradients (no doubling of interior bins)

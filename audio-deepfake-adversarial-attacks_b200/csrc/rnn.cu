@@ -35,20 +35,27 @@ __global__ void __launch_bounds__(256) gemm_kernel(const float* __restrict__ A, 
   float acc[RM][RN] = {};
   const int a_row = tid >> 2, a_kq = (tid & 3) * 4;            // A tile: 64 rows x 4 float4 along k
   const int b_row = tid / (BN / 4), b_c4 = (tid % (BN / 4)) * 4;  // B tile: 16 rows x BN/4 float4
+  // register prefetch: the global loads of k-step i+1 are in flight while k-step i is multiplied (one exposed load
+  // latency per launch instead of one per k-step; the K = 640 backward projection has 40 of them)
+  auto load_a = [&](int k0) {
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (m0 + a_row < M && k0 + a_kq < K) v = __ldg(reinterpret_cast<const float4*>(A + (size_t)(m0 + a_row) * K + k0 + a_kq));
+    return v;
+  };
+  auto load_b = [&](int k0) {
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (b_row < 16 && k0 + b_row < K && n0 + b_c4 < N)
+      v = __ldg(reinterpret_cast<const float4*>(Bm + (size_t)(k0 + b_row) * N + n0 + b_c4));
+    return v;
+  };
+  float4 pa = load_a(0), pb = load_b(0);
   for (int k0 = 0; k0 < K; k0 += 16) {
-    {
-      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (m0 + a_row < M && k0 + a_kq < K) v = __ldg(reinterpret_cast<const float4*>(A + (size_t)(m0 + a_row) * K + k0 + a_kq));
-      As[a_kq + 0][a_row] = v.x;
-      As[a_kq + 1][a_row] = v.y;
-      As[a_kq + 2][a_row] = v.z;
-      As[a_kq + 3][a_row] = v.w;
-    }
-    if (b_row < 16) {
-      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (k0 + b_row < K && n0 + b_c4 < N) v = __ldg(reinterpret_cast<const float4*>(Bm + (size_t)(k0 + b_row) * N + n0 + b_c4));
-      *reinterpret_cast<float4*>(&Bs[b_row][b_c4]) = v;
-    }
+    As[a_kq + 0][a_row] = pa.x;
+    As[a_kq + 1][a_row] = pa.y;
+    As[a_kq + 2][a_row] = pa.z;
+    As[a_kq + 3][a_row] = pa.w;
+    if (b_row < 16) *reinterpret_cast<float4*>(&Bs[b_row][b_c4]) = pb;
+    if (k0 + 16 < K) pa = load_a(k0 + 16), pb = load_b(k0 + 16);
     __syncthreads();
 #pragma unroll
     for (int kk = 0; kk < 16; ++kk) {
