@@ -166,7 +166,8 @@ class Engine:
 
     def set_option(self, key: str, value: int):
         """``conv_path`` (0 tcgen05 / 1 fp32 SIMT), ``tf32_passes`` (3 = 3xTF32 / 1 = single pass), ``conv_sched``
-        (0 persistent kernels / 1 one-tile-per-CTA kernels)."""
+        (0 persistent kernels / 1 one-tile-per-CTA kernels), ``conv0_bwd`` (first block backward: 0 fp32 cell kernel /
+        1 tcgen05 GEMM + col2im)."""
         _lib.check(self.lib.advb_set_option(self.handle, key.encode(), int(value)))
 
     def profile_begin(self):

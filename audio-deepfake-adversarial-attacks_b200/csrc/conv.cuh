@@ -42,6 +42,11 @@ int conv_mfm_backward(ConvBwdArgs a, cudaStream_t stream);
 int conv0_backward(const float* gout, const unsigned char* codes, const float* w0, float* gin, int B, int H, int W,
                    int Ho, int Wo, cudaStream_t stream);
 
+// first block backward, production kernel (conv0_bwd.cu): fp32, thread per pooled cell, fused col2im; LCNN geometry only
+bool conv0_cells_supported(int H, int W, int Ho, int Wo);
+int conv0_cells_backward(const float* gout, const unsigned char* codes, const float* w0, float* gin, int B, int H, int W,
+                         int Ho, int Wo, cudaStream_t stream);
+
 // ---- tensor-core (tcgen05) path, conv_tc.cu ----
 bool conv_tc_supported(int Cin, int Cout, int KS, bool pool);
 size_t conv_tc_pack_bytes(int Cout, int Cin, int KS, bool bwd);

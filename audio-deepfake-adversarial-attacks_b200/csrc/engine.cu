@@ -76,6 +76,7 @@ struct advb_handle {
   int conv_path = 0;    // 0 = tcgen05 tensor cores (default), 1 = fp32 SIMT cross-check path
   int tf32_passes = 3;  // 3 = 3xTF32 (fp32-class accuracy), 1 = single-pass tf32
   int conv_sched = 0;   // 0 = persistent warp-specialised conv kernels, 1 = one-tile-per-CTA kernels only
+  int conv0_bwd = 0;    // first block backward: 0 = fp32 cell kernel (conv0_bwd.cu), 1 = tcgen05 GEMM + col2im
 
   // frontend
   float2* tw = nullptr;
@@ -400,7 +401,9 @@ int lcnn_backward(advb_handle* h, const float* x, const int64_t* y, int B, int m
     else ADVB_TRY(conv_mfm_backward(a, st));
   }
   const LcnnBlock& k0 = h->blk[0];
-  if (k0.tc && h->conv_path == 0)
+  if (k0.tc && h->conv_path == 0 && h->conv0_bwd == 0 && conv0_cells_supported(k0.H, k0.W, k0.Ho, k0.Wo))
+    ADVB_TRY(conv0_cells_backward(k0.gout, k0.codes, h->t("m_transform.0.weight"), h->g_coef, B, k0.H, k0.W, k0.Ho, k0.Wo, st));
+  else if (k0.tc && h->conv_path == 0)
     ADVB_TRY(conv0_tc_backward(k0.gout, k0.codes, k0.tcd, h->conv0_T, h->g_coef, B, k0.H, k0.W, k0.Ho, k0.Wo,
                                h->tf32_passes, st));
   else
@@ -757,6 +760,9 @@ int advb_set_option(advb_handle* h, const char* key, int value) {
   } else if (k == "conv_sched") {
     ADVB_CHECK(value == 0 || value == 1, "conv_sched: 0 = persistent kernels, 1 = one-tile-per-CTA kernels");
     h->conv_sched = value;
+  } else if (k == "conv0_bwd") {
+    ADVB_CHECK(value == 0 || value == 1, "conv0_bwd: 0 = fp32 cell kernel, 1 = tcgen05 GEMM + col2im");
+    h->conv0_bwd = value;
   } else {
     set_error("unknown option '" + k + "'");
     return 1;

@@ -278,6 +278,11 @@ def test_tensor_core_path_matches_simt_path(name, cuda_device):
         eng.set_option("conv_sched", 0)
         assert torch.equal(l_classic, l_tc)
         assert helpers.rel_err(g_classic.cpu(), g_tc.cpu()) < 2e-5
+        # first block backward: the fp32 cell kernel (default, conv0_bwd.cu) against the tcgen05 GEMM + col2im version
+        eng.set_option("conv0_bwd", 1)
+        g_c0tc, _ = eng.grad(xd, yd)
+        eng.set_option("conv0_bwd", 0)
+        assert helpers.rel_err(g_c0tc.cpu(), g_tc.cpu()) < 2e-5
         # single-pass tf32: reduced precision, documented as an opt-in; sanity only
         eng.set_option("tf32_passes", 1)
         g_fast, l_fast = eng.grad(xd, yd)
@@ -287,6 +292,7 @@ def test_tensor_core_path_matches_simt_path(name, cuda_device):
         eng.set_option("tf32_passes", 3)
         eng.set_option("conv_path", 0)
         eng.set_option("conv_sched", 0)
+        eng.set_option("conv0_bwd", 0)
 
 
 def test_projection_linf_against_oracle(cuda_device):
