@@ -231,9 +231,9 @@ __global__ void fe_reset_kernel(FrontendState st) {
 
 // ---------------------------------------------------------------------------------------------------
 // Forward 1: waveform -> dB filterbank energies (B,F,128) + batch arg-max.
-__global__ void __launch_bounds__(FE_THREADS) fe_power_db_kernel(const float* __restrict__ x, int T, int F,
-                                                                   FrontendTables tb, FrontendState st,
-                                                                   float* __restrict__ dB) {
+__global__ void __launch_bounds__(FE_THREADS, 3) fe_power_db_kernel(const float* __restrict__ x, int T, int F,
+                                                                      FrontendTables tb, FrontendState st,
+                                                                      float* __restrict__ dB, int n_blocks, int n_clips) {
   extern __shared__ __align__(16) float smem[];
   float2* s_tw = reinterpret_cast<float2*>(smem);                    // 512 float2
   float* s_win = smem + 1024;                                        // 400
@@ -242,47 +242,51 @@ __global__ void __launch_bounds__(FE_THREADS) fe_power_db_kernel(const float* __
   for (int i = tid; i < 512; i += FE_THREADS) s_tw[i] = tb.tw[i];
   for (int i = tid; i < WIN; i += FE_THREADS) s_win[i] = tb.window[i];
   __syncthreads();
-
-  const int b = blockIdx.y;
-  const int ta = blockIdx.x * (2 * FE_WARPS) + 2 * warp;
-  if (ta >= F) return;
-  const bool has_b = (ta + 1) < F;
   float2* bufA = s_fft + warp * (FFT_A + FFT_B);
   float2* bufB = bufA + FFT_A;
   float* pa = reinterpret_cast<float*>(bufA);  // power vectors live in buffer A, which is scratch once Z sits in buffer B
   float* pb = pa + PSTRIDE;
-  const float* xb = x + (size_t)b * T;
-
-  load_frame_pair(xb, T, F, ta, s_win, bufA, lane);
-  warp_fft512(bufA, bufB, s_tw, lane);
-  for (int k = lane; k < NBIN; k += 32) {
-    float xar, xai, xbr, xbi;
-    unpack_bin(bufB, k, xar, xai, xbr, xbi);
-    pa[k] = xar * xar + xai * xai;
-    pb[k] = xbr * xbr + xbi * xbi;
-  }
-  __syncwarp();
 
   float best = -INFINITY;
   unsigned best_idx = 0xffffffffu;
-  const size_t rowa = ((size_t)b * F + ta) * NFILT;
-  float ea[4], eb[4];
-  filter_energy4(tb.fb, tb.klo, tb.kcnt, pa, pb, lane, ea, eb);
-#pragma unroll
-  for (int i = 0; i < NFILT / 32; ++i) {
-    const int m = lane + 32 * i;
-    const float da = to_db(ea[i]);
-    dB[rowa + m] = da;
-    if (da > best) {
-      best = da;
-      best_idx = (unsigned)(rowa + m);
+  // persistent over (clip, block of 16 frames): tables staged once per CTA, one atomicMax per warp per launch
+  for (int work = blockIdx.x; work < n_blocks * n_clips; work += gridDim.x) {
+    const int b = work / n_blocks;
+    const int ta = (work - b * n_blocks) * (2 * FE_WARPS) + 2 * warp;
+    if (ta >= F) continue;  // warp-uniform; the loop has no block-wide barrier
+    const bool has_b = (ta + 1) < F;
+    const float* xb = x + (size_t)b * T;
+
+    load_frame_pair(xb, T, F, ta, s_win, bufA, lane);
+    warp_fft512(bufA, bufB, s_tw, lane);
+    for (int k = lane; k < NBIN; k += 32) {
+      float xar, xai, xbr, xbi;
+      unpack_bin(bufB, k, xar, xai, xbr, xbi);
+      pa[k] = xar * xar + xai * xai;
+      pb[k] = xbr * xbr + xbi * xbi;
     }
-    if (has_b) {
-      const float db = to_db(eb[i]);
-      dB[rowa + NFILT + m] = db;
-      if (db > best) {
-        best = db;
-        best_idx = (unsigned)(rowa + NFILT + m);
+    __syncwarp();
+
+    const size_t rowa = ((size_t)b * F + ta) * NFILT;
+    float ea[4], eb[4];
+    filter_energy4(tb.fb, tb.klo, tb.kcnt, pa, pb, lane, ea, eb);
+    __syncwarp();  // the next item's frame load overwrites the power vectors (buffer A)
+#pragma unroll
+    for (int i = 0; i < NFILT / 32; ++i) {
+      const int m = lane + 32 * i;
+      const float da = to_db(ea[i]);
+      dB[rowa + m] = da;
+      if (da > best || (da == best && (unsigned)(rowa + m) < best_idx)) {
+        best = da;
+        best_idx = (unsigned)(rowa + m);
+      }
+      if (has_b) {
+        const float db = to_db(eb[i]);
+        dB[rowa + NFILT + m] = db;
+        if (db > best || (db == best && (unsigned)(rowa + NFILT + m) < best_idx)) {
+          best = db;
+          best_idx = (unsigned)(rowa + NFILT + m);
+        }
       }
     }
   }
@@ -294,7 +298,7 @@ __global__ void __launch_bounds__(FE_THREADS) fe_power_db_kernel(const float* __
     const unsigned long long other = __shfl_xor_sync(0xffffffffu, packed, o);
     packed = other > packed ? other : packed;
   }
-  if (lane == 0) atomicMax(st.gmax_packed, packed);
+  if (lane == 0 && best_idx != 0xffffffffu) atomicMax(st.gmax_packed, packed);
 }
 
 __device__ __forceinline__ void decode_gmax(unsigned long long packed, float& vmax, unsigned& idx) {
@@ -698,8 +702,9 @@ int frontend_forward(const FrontendTables& tb, const FrontendState& st, const fl
   ADVB_CHECK(T >= 512, "clip shorter than one FFT frame");
   fe_reset_kernel<<<1, 1, 0, stream>>>(st);
   ADVB_KERNEL_OK("fe_reset", stream);
-  dim3 g1(cdiv(F, 2 * FE_WARPS), B);
-  fe_power_db_kernel<<<g1, FE_THREADS, fe_fwd_smem(), stream>>>(x, T, F, tb, st, dB);
+  const int n_fb = cdiv(F, 2 * FE_WARPS);
+  const int g1 = n_fb * B < 148 * 3 ? n_fb * B : 148 * 3;  // persistent: 74 KB of shared memory -> 3 CTAs / SM
+  fe_power_db_kernel<<<g1, FE_THREADS, fe_fwd_smem(), stream>>>(x, T, F, tb, st, dB, n_fb, B);
   ADVB_KERNEL_OK("fe_power_db", stream);
   const int n_items = cdiv(B * F, FD_FR);
   const int g2 = n_items < 148 * 3 ? n_items : 148 * 3;  // persistent: 71 KB of shared memory -> 3 CTAs / SM

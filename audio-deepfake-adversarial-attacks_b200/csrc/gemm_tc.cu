@@ -747,10 +747,10 @@ int tune_epw() {
 }
 int tune_cluster() {  // cluster size along M for the weight multicast (1 = off)
   static const int v = [] {
-    // default 1: the 2-CTA weight multicast measured +1.4 % (146 vs 144 clips/s) - the kernel is not L2 -> SM bound - and is
-    // kept as an opt-in (ADVB_GEMM_CLUSTER=2 or 4)
-    const int c = tune_env("ADVB_GEMM_CLUSTER", 1);
-    return (c == 1 || c == 2 || c == 4) ? c : 1;
+    // measured on PGDL2-10, B = 16 with the direct epilogue: 145.8 / 155.9 / 147.4 clips/s for cluster sizes 1 / 2 / 4
+    // (with the older transposing epilogue the kernel was epilogue-bound and the multicast was worth only +1.4 %)
+    const int c = tune_env("ADVB_GEMM_CLUSTER", 2);
+    return (c == 1 || c == 2 || c == 4) ? c : 2;
   }();
   return v;
 }

@@ -148,7 +148,8 @@ def kernel_bytes(B, F, T):
         out[f"conv_fwd_b{i}"] = B * per_clip
         out[f"conv_bwd_b{i}"] = B * per_clip
         H, W = Ho, Wo
-    out["conv0_bwd_gemm"] = out.pop("conv_bwd_b0")  # the (F,80,5) col2im scratch is an implementation artefact
+    out["conv0_bwd_cells"] = out.pop("conv_bwd_b0")  # fp32 cell kernel (csrc/conv0_bwd.cu): stage gradient + codes in, d image out
+    out["conv0_bwd_gemm"] = out["conv0_bwd_cells"]   # tcgen05 variant (conv0_bwd=1): its (F,80,5) col2im scratch is an artefact
     # SpecRNet blocks (csrc/specrnet.cu): conv1 reads x writes h; conv2 reads h, x writes xb + 2-bit code; backward
     # kernels read the stage gradient / codes / h and write the gradient of their input
     H, W, ci = F, 80, 1
