@@ -76,13 +76,14 @@ struct TileGeom {
   int QW, QH, nQ, q0, q1, qy0, nrows, BW;
 };
 
-__device__ __forceinline__ TileGeom tile_geom(int H, int W, bool floor_quads, int pc) {
+// qpc = quads per CTA (32 on the LCNN cross-check path; the SpecRNet launcher picks whole quad rows, specrnet.cu)
+__device__ __forceinline__ TileGeom tile_geom(int H, int W, bool floor_quads, int pc, int qpc = 32) {
   TileGeom g;
   g.QW = floor_quads ? W / 2 : (W + 1) / 2;
   g.QH = floor_quads ? H / 2 : (H + 1) / 2;
   g.nQ = g.QH * g.QW;
-  g.q0 = blockIdx.x * 32;
-  g.q1 = min(g.q0 + 32, g.nQ) - 1;
+  g.q0 = blockIdx.x * qpc;
+  g.q1 = min(g.q0 + qpc, g.nQ) - 1;
   g.qy0 = g.q0 / g.QW;
   const int qy1 = g.q1 / g.QW;
   g.nrows = 2 * (qy1 - g.qy0 + 1) + 2 * pc;
@@ -91,9 +92,9 @@ __device__ __forceinline__ TileGeom tile_geom(int H, int W, bool floor_quads, in
 }
 
 
-// rows of the band a CTA of 32 quads may need (host side)
-inline int band_rows_max(int QH, int QW, int pc) {
-  int span = (32 + QW - 2) / QW + 1;
+// rows of the band a CTA of qpc quads may need (host side)
+inline int band_rows_max(int QH, int QW, int pc, int qpc = 32) {
+  int span = (qpc + QW - 2) / QW + 1;
   if (span > QH) span = QH;
   return 2 * span + 2 * pc;
 }

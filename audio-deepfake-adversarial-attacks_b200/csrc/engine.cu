@@ -493,7 +493,7 @@ int build_specrnet(advb_handle* h) {
     k.H = H, k.W = W, k.Hb = H / 2, k.Wb = W / 2, k.Hn = k.Hb / 2, k.Wn = k.Wb / 2;
     ADVB_CHECK(k.Hn > 0 && k.Wn > 0, "clip too short for the SpecRNet pooling stack");
     k.downsample = cin[i] != cout[i];
-    k.n_tiles = sr_conv2_tiles(H, W);
+    k.n_tiles = sr_conv2_tiles(H, W, k.C);
     k.xn_pad = i < 2 ? 1 : 0;
     const size_t C = k.C;
     ADVB_TRY(h->alloc(&k.w1f, 9 * (size_t)k.Ci * C));

@@ -21,6 +21,10 @@
 // Algorithmic HBM bytes per clip: every tensor above written once and read once (bench.py kernel_bytes).
 #include "specrnet.cuh"
 
+#include <stdlib.h>
+
+#include <algorithm>
+
 #include "conv_core.cuh"
 
 namespace advb {
@@ -59,6 +63,7 @@ struct SrArgs {
   const float* y;
   const float* gadd;
   const float* h;
+  int qpc;              // quads (2x2 output pixels) per CTA
 };
 
 // 4 consecutive channels (c..c+3) of the gradient at conv2's output pixel (yy, xx): un-pool of
@@ -95,12 +100,12 @@ __device__ __forceinline__ float4 expand_go(const SrArgs& a, int b, int yy, int 
 template <int MODE>
 __global__ void __launch_bounds__(256) sr_conv_kernel(SrArgs a, int band_floats) {
   extern __shared__ __align__(16) float smem[];
-  __shared__ float s_part[MODE == F2 ? 32 * 64 : 1];
-  const TileGeom g = tile_geom(a.H, a.W, MODE == F2, 1);
+  const TileGeom g = tile_geom(a.H, a.W, MODE == F2, 1, a.qpc);
   const int CK = a.CK;
   const int CKp = (CK & 3) == 0 ? CK + 4 : CK;
   float* band = smem;
   float* w_s = smem + band_floats;
+  float* s_part = w_s + CK * a.N;  // F2 only: qpc x N partial sums
   const int b = blockIdx.y, tid = threadIdx.x, nt = blockDim.x;
 
   // ---- stage the band: rows 2*qy0-1 ..., columns -1 .. 2*QW ----
@@ -231,11 +236,11 @@ __global__ void __launch_bounds__(256) sr_conv_kernel(SrArgs a, int band_floats)
     }
     // deterministic partial channel sums of this CTA's quads (avgpool of the attention)
 #pragma unroll
-    for (int j = 0; j < 8; ++j) s_part[ql * 64 + (j < 4 ? c0 : nh + c0 - 4) + j] = valid ? best[j] : 0.f;
+    for (int j = 0; j < 8; ++j) s_part[ql * N + (j < 4 ? c0 : nh + c0 - 4) + j] = valid ? best[j] : 0.f;
     __syncthreads();
     if (tid < N) {
       float s = 0.f;
-      for (int r = 0; r < 32; ++r) s += s_part[r * 64 + tid];
+      for (int r = 0; r < a.qpc; ++r) s += s_part[r * N + tid];
       a.psum[((size_t)b * gridDim.x + blockIdx.x) * N + tid] = s;
     }
   } else if (MODE == B2) {
@@ -658,19 +663,53 @@ inline int ew_blocks(int64_t n) {
   return (int)(b > 148 * 16 ? 148 * 16 : b);
 }
 
+// Quads per CTA: whole quad rows (so that a tile's halo band is its rows + 2, not up to 3x its rows as with 32 quads of a
+// 40-quad row), as many as 512 threads (qpc x N/8) and half an SM's shared memory allow; 32 when a single row does not fit.
+int sr_band_rows(int QH, int QW, int qpc) {  // rows of the halo band of a tile (row-aligned tiles need exactly theirs + 2)
+  if (qpc % QW == 0) return 2 * std::min(qpc / QW, QH) + 2;
+  return band_rows_max(QH, QW, 1, qpc);
+}
+int sr_qpc(int N, int CK, int QH, int QW) {
+  const int CKp = (CK % 4 == 0) ? CK + 4 : CK;
+  const int G = N / 8;
+  int best = 32;
+  // measured (B = 256, ms per PGD-40 call): row-aligned tiles of <= 256 threads pay where the band is deep and the thread
+  // tile narrow - block 0 conv2 forward 160 -> 118, backward 231 -> 136, block 2 conv1 backward 46 -> 37; the N = 64 layers
+  // (ADVB_SR_WIDE=1) and the 1-channel first conv got slower and keep 32 quads; 480-thread tiles (1 CTA per SM) lost to
+  // 240-thread ones everywhere
+  static const int wide = [] {
+    const char* e = getenv("ADVB_SR_WIDE");
+    return e != nullptr ? atoi(e) : 0;
+  }();
+  if ((N > 32 && !wide) || CK < 8) return best;
+  static const int max_threads = [] {
+    const char* e = getenv("ADVB_SR_THREADS");
+    const int v = e != nullptr ? atoi(e) : 256;
+    return v > 256 ? 256 : v;  // the kernel's __launch_bounds__
+  }();
+  for (int rows = 1; rows <= QH && rows * QW * G <= max_threads; ++rows) {
+    const int qpc = rows * QW;
+    const size_t smem = (size_t)(sr_band_rows(QH, QW, qpc) * (2 * QW + 2) * CKp + CK * N + qpc * N) * sizeof(float);
+    if (smem > 110 * 1024) break;
+    if (qpc >= 24) best = qpc;
+  }
+  return best;
+}
+
 template <int MODE>
 int launch_conv(SrArgs a, bool floor_quads, const char* tag, cudaStream_t stream) {
   const int QW = floor_quads ? a.W / 2 : (a.W + 1) / 2, QH = floor_quads ? a.H / 2 : (a.H + 1) / 2;
   ADVB_CHECK(QW > 0 && QH > 0, "empty SpecRNet conv output");
   const int CKp = (a.CK % 4 == 0) ? a.CK + 4 : a.CK;
-  int band = band_rows_max(QH, QW, 1) * (2 * QW + 2) * CKp;
+  a.qpc = sr_qpc(a.N, a.CK, QH, QW);
+  int band = sr_band_rows(QH, QW, a.qpc) * (2 * QW + 2) * CKp;
   band = (band + 3) & ~3;
-  const size_t smem = (size_t)(band + a.CK * a.N) * sizeof(float);
+  const size_t smem = (size_t)(band + a.CK * a.N + (MODE == F2 ? a.qpc * a.N : 0)) * sizeof(float);
   ADVB_CHECK(smem <= 227 * 1024, "SpecRNet conv tile does not fit shared memory");
   ADVB_CHECK(a.N % 8 == 0 && a.N <= 64, "SpecRNet conv: N must be a multiple of 8, <= 64");
   ADVB_CUDA_OK(cudaFuncSetAttribute(sr_conv_kernel<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  dim3 grid(cdiv(QH * QW, 32), a.B);
-  sr_conv_kernel<MODE><<<grid, 32 * (a.N / 8), smem, stream>>>(a, band);
+  dim3 grid(cdiv(QH * QW, a.qpc), a.B);
+  sr_conv_kernel<MODE><<<grid, a.qpc * (a.N / 8), smem, stream>>>(a, band);
   ADVB_KERNEL_OK(tag, stream);
   return 0;
 }
@@ -685,7 +724,7 @@ SrArgs base_args(const SrBlock& k, int B) {
 
 }  // namespace
 
-int sr_conv2_tiles(int H, int W) { return cdiv((H / 2) * (W / 2), 32); }
+int sr_conv2_tiles(int H, int W, int C) { return cdiv((H / 2) * (W / 2), sr_qpc(C, C, H / 2, W / 2)); }
 
 int sr_pack_first_bn(const float* w, const float* b, const float* rm, const float* rv, float* bn4, cudaStream_t stream) {
   sr_pack4_kernel<<<1, 1, 0, stream>>>(w, b, rm, rv, bn4);

@@ -48,7 +48,7 @@ struct SrGru {
   float* xin;                      // (B, L, 64): selu(bn(x)) fed to the GRU
 };
 
-int sr_conv2_tiles(int H, int W);  // CTAs per clip of the conv2 kernel = rows of SrBlock::psum
+int sr_conv2_tiles(int H, int W, int C);  // CTAs per clip of the conv2 kernel = rows of SrBlock::psum
 int sr_pack_first_bn(const float* w, const float* b, const float* rm, const float* rv, float* bn4, cudaStream_t stream);
 int sr_pack_block(SrBlock& k, cudaStream_t stream);
 int sr_pack_gru(SrGru& g, cudaStream_t stream);
