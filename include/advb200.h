@@ -87,8 +87,8 @@ ADVB_API int advb_rebind(advb_handle* h, int n_tensors, const advb_tensor_ref* t
  *   "conv_path"   0 = tcgen05 tensor-core convolutions / GEMMs (default), 1 = fp32 SIMT convolutions / GEMMs (cross-check)
  *   "tf32_passes" 3 = 3xTF32 error-compensated products, fp32-class accuracy (default), 1 = single-pass tf32
  *   "conv_sched"  0 = persistent warp-specialised convolution / GEMM kernels (default), 1 = one-tile-per-CTA kernels only
- *   "conv0_bwd"   LCNN first block backward: 0 = fp32 cell kernel (default), 1 = tcgen05 GEMM + col2im (cross-check)
- *                 (the first tcgen05 version; same arithmetic, kept as an in-process cross-check) */
+ *                 (the first tcgen05 version; same arithmetic, kept as an in-process cross-check)
+ *   "conv0_bwd"   LCNN first block backward: 0 = fp32 cell kernel (default), 1 = tcgen05 GEMM + col2im (cross-check) */
 ADVB_API int advb_set_option(advb_handle* h, const char* key, int value);
 
 /* Replaces  atk(images, labels)  = Attack.__call__ -> {FGSM,PGD,PGDL2,FAB,CW}.forward
