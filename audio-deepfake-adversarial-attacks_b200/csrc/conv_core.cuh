@@ -17,9 +17,12 @@ __device__ __forceinline__ void fma4(float (&acc)[8], int off, float a, const fl
 
 // acc[p][0..3] -> channels g4..g4+3, acc[p][4..7] -> channels nh+g4..nh+g4+3, p = 2x2 pixel of the quad.
 template <int KS>
+// ck_loop (optional): contraction channels actually visited, <= CK, when the staged layout is zero-padded beyond them
 __device__ __forceinline__ void conv_core(const float* band, int BW, int CK, int CKp, const float* __restrict__ wg,
-                                          float* w_s, int N, int rb, int cb, int g4, bool valid, float (&acc)[4][8]) {
+                                          float* w_s, int N, int rb, int cb, int g4, bool valid, float (&acc)[4][8],
+                                          int ck_loop = 0) {
   const int nh = N >> 1;
+  const int CKl = ck_loop > 0 ? ck_loop : CK;
   const int slab4 = (CK * N) >> 2;
 #pragma unroll 1
   for (int tap = 0; tap < KS * KS; ++tap) {
@@ -38,7 +41,7 @@ __device__ __forceinline__ void conv_core(const float* band, int BW, int CK, int
     const float* p11 = p10 + CKp;
     if ((CK & 3) == 0) {
 #pragma unroll 1
-      for (int ci = 0; ci < CK; ci += 4) {
+      for (int ci = 0; ci < CKl; ci += 4) {
         const float4 a0 = *reinterpret_cast<const float4*>(p00 + ci);
         const float4 a1 = *reinterpret_cast<const float4*>(p01 + ci);
         const float4 a2 = *reinterpret_cast<const float4*>(p10 + ci);
@@ -58,7 +61,7 @@ __device__ __forceinline__ void conv_core(const float* band, int BW, int CK, int
       }
     } else {
 #pragma unroll 1
-      for (int ci = 0; ci < CK; ++ci) {
+      for (int ci = 0; ci < CKl; ++ci) {
         const float av[4] = {p00[ci], p01[ci], p10[ci], p11[ci]};
         const float4 wl = *reinterpret_cast<const float4*>(w_s + ci * N + g4);
         const float4 wh = *reinterpret_cast<const float4*>(w_s + ci * N + nh + g4);

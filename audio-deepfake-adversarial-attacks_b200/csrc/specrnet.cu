@@ -64,6 +64,7 @@ struct SrArgs {
   const float* gadd;
   const float* h;
   int qpc;              // quads (2x2 output pixels) per CTA
+  int CKr;              // contraction channels that are not zero padding (multiple of 4 when CK is), <= CK
 };
 
 // 4 consecutive channels (c..c+3) of the gradient at conv2's output pixel (yy, xx): un-pool of
@@ -113,7 +114,7 @@ __global__ void __launch_bounds__(256) sr_conv_kernel(SrArgs a, int band_floats)
     const int Hp = a.H + 2, Wp = a.W + 2;
     const float* inb = a.in + (size_t)b * Hp * Wp * CK;
     if ((CK & 3) == 0) {
-      const int c4n = CK >> 2, total = g.nrows * g.BW * c4n;
+      const int c4n = a.CKr >> 2, total = g.nrows * g.BW * c4n;  // padded channels are never read
       for (int i = tid; i < total; i += nt) {
         const int c4 = i % c4n, col = (i / c4n) % g.BW, r = i / (c4n * g.BW);
         const int yp = 2 * g.qy0 + r, xp = col;  // (-1 + r) + pad 1
@@ -132,7 +133,7 @@ __global__ void __launch_bounds__(256) sr_conv_kernel(SrArgs a, int band_floats)
       }
     }
   } else {
-    const int c4n = CK >> 2, total = g.nrows * g.BW * c4n;
+    const int c4n = a.CKr >> 2, total = g.nrows * g.BW * c4n;  // padded channels are never read
     for (int i = tid; i < total; i += nt) {
       const int c4 = i % c4n, col = (i / c4n) % g.BW, r = i / (c4n * g.BW);
       const int y = 2 * g.qy0 - 1 + r, x = col - 1;
@@ -156,7 +157,7 @@ __global__ void __launch_bounds__(256) sr_conv_kernel(SrArgs a, int band_floats)
   for (int p = 0; p < 4; ++p)
 #pragma unroll
     for (int j = 0; j < 8; ++j) acc[p][j] = 0.f;
-  conv_core<3>(band, g.BW, CK, CKp, a.wpk, w_s, N, 2 * (qy - g.qy0), 2 * qx, 4 * cg, valid, acc);
+  conv_core<3>(band, g.BW, CK, CKp, a.wpk, w_s, N, 2 * (qy - g.qy0), 2 * qx, 4 * cg, valid, acc, a.CKr);
 
   const int nh = N >> 1, c0 = 4 * cg;
   if (MODE == F1) {
@@ -784,10 +785,11 @@ const SrTags& sr_tags(const char* tag) {
 int sr_block_forward(const SrBlock& k, const float* x, int B, const char* tag, cudaStream_t stream) {
   const SrTags& t = sr_tags(tag);
   SrArgs a = base_args(k, B);
-  a.CK = k.Ci, a.N = k.C;
+  // CKr: the padded channels (20 -> 24) carry zero weights; the contraction skips them (bit-identical up to the sign of zero)
+  a.CK = k.Ci, a.N = k.C, a.CKr = k.Ci % 4 == 0 ? std::min(k.Ci, (k.Cin + 3) / 4 * 4) : k.Ci;
   a.in = x, a.wpk = k.w1f, a.bias = k.b1p, a.out = k.h;
   ADVB_TRY(launch_conv<F1>(a, false, t.conv1, stream));
-  a.CK = k.C, a.in = k.h, a.wpk = k.w2f, a.bias = k.b2p, a.out = k.xb;
+  a.CK = k.C, a.CKr = std::min(k.C, (k.Cout + 3) / 4 * 4), a.in = k.h, a.wpk = k.w2f, a.bias = k.b2p, a.out = k.xb;
   a.x = x, a.Ci = k.Ci, a.wd = k.downsample ? k.wdf : nullptr, a.bd = k.bdp, a.code1w = k.code1, a.psum = k.psum;
   ADVB_TRY(launch_conv<F2>(a, true, t.conv2, stream));
   sr_attention_fwd_kernel<<<B, 64, 0, stream>>>(k.psum, k.n_tiles, k.att_w, k.att_b, k.y, k.C, k.Cout,
@@ -808,7 +810,7 @@ int sr_block_backward(const SrBlock& k, const float* x, float* g_x, int B, bool 
                                                     k.C, k.Cout, 1.0f / (float)(k.Hb * k.Wb));
   ADVB_KERNEL_OK("sr_attention_bwd", stream);
   SrArgs a = base_args(k, B);
-  a.CK = k.C, a.N = k.C, a.wpk = k.w2d, a.out = k.g_c1;
+  a.CK = k.C, a.CKr = std::min(k.C, (k.Cout + 3) / 4 * 4), a.N = k.C, a.wpk = k.w2d, a.out = k.g_c1;
   ADVB_TRY(launch_conv<B2>(a, false, t.conv2_bwd, stream));
   a.in = k.g_c1, a.x = x;
   if (first) {
@@ -817,7 +819,7 @@ int sr_block_backward(const SrBlock& k, const float* x, float* g_x, int B, bool 
     ADVB_KERNEL_OK(t.conv1_bwd, stream);
     return 0;
   }
-  a.CK = k.C, a.N = k.Ci, a.wpk = k.w1d, a.out = g_x, a.wd = k.downsample ? k.wdd : nullptr;
+  a.CK = k.C, a.CKr = std::min(k.C, (k.Cout + 3) / 4 * 4), a.N = k.Ci, a.wpk = k.w1d, a.out = g_x, a.wd = k.downsample ? k.wdd : nullptr;
   ADVB_TRY(launch_conv<B1>(a, false, t.conv1_bwd, stream));
   return 0;
 }
