@@ -70,6 +70,13 @@ struct LCfg {
   static constexpr size_t SMEM = (size_t)W_BYTES + BAND_BYTES + STAGE_BYTES + 1024;
   static constexpr int MAP = IM2COL ? (BWD ? 1 : 2) : 0;  // 0 FLAT, 1 OVL4, 2 BLK
   static constexpr int STEP = MAP == 1 ? 124 : 128;       // new pixels per tile (FLAT / OVL4)
+#ifndef ADVB_LIGHT_CTAS3
+#define ADVB_LIGHT_CTAS3 0
+#endif
+  // CTAs per SM the kernel is compiled for (register cap).  -DADVB_LIGHT_CTAS3=1 asks for 3 where shared memory and TMEM
+  // allow it (first block forward, 32 -> 64 1x1): measured slower, 13.5 vs 12.1 ms and 4.6 vs 4.2 ms per PGD-40 call (72
+  // registers per thread: spills, and the per-tile latency chain does not shorten), so the default stays 2
+  static constexpr int CTAS = SMEM > 113 * 1024 ? 1 : ((ADVB_LIGHT_CTAS3 && 3 * (SMEM + 1024) <= 227 * 1024 && 3 * TMEM_COLS <= 512) ? 3 : 2);
 };
 
 // pixel of tile-local row m: (y, x) on the conv grid; false when the row is padding
@@ -90,7 +97,7 @@ __device__ __forceinline__ bool tile_pixel(const LArgs& a, int tl, int m, int He
 }
 
 template <int KTOT, int NOUT, bool POOL, bool BWD, bool IM2COL>
-__global__ void __launch_bounds__(LT, (LCfg<KTOT, NOUT, POOL, BWD, IM2COL>::SMEM <= 113 * 1024) ? 2 : 1)
+__global__ void __launch_bounds__(LT, LCfg<KTOT, NOUT, POOL, BWD, IM2COL>::CTAS)
 conv_light_kernel(LArgs a) {
   using Cfg = LCfg<KTOT, NOUT, POOL, BWD, IM2COL>;
   constexpr int NKC = Cfg::NKC, CS = Cfg::CS, SS = Cfg::SS, MAP = Cfg::MAP;
@@ -487,7 +494,7 @@ int launch_light(LArgs a, const char* tag, cudaStream_t stream) {
   // gridDim.x and the surplus CTAs simply start later.
   int per_sm = (int)((227 * 1024) / (Cfg::SMEM + 1024));
   if (per_sm > 512 / Cfg::TMEM_COLS) per_sm = 512 / Cfg::TMEM_COLS;
-  if (per_sm > 2) per_sm = 2;
+  if (per_sm > Cfg::CTAS) per_sm = Cfg::CTAS;
   if (per_sm < 1) per_sm = 1;
   int n_sm = 148;
   int dev = 0;
