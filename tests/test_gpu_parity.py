@@ -48,6 +48,29 @@ def test_frontend_forward_backward(name, cuda_device):
         assert helpers.cosine(gx, gx_want) > 0.999
 
 
+@pytest.mark.parametrize("T", [6399, 6400, 6401, 12801, 19999])
+def test_frontend_clip_lengths_around_the_backward_tile(T, cuda_device):
+    """fe_bwd works on tiles of 40 hops = 6 400 samples, one warp per frame pair: lengths just below / at / above a tile
+    boundary (a last tile of ONE sample included) and odd lengths, forward and backward against the oracle."""
+    from advb200 import engine
+
+    case, x0, y0, holder, state, fwd = helpers.case_setup("lcnn_lfcc_t16000")
+    holder = helpers.load_holder_state(holder, state, cuda_device)
+    g = torch.Generator("cpu").manual_seed(T)
+    x = torch.rand(3, T, generator=g)
+    eng = engine.engine_for(holder, 3, T)
+    fb, dct, win, _ = ofe.tables_from_state(state)
+    xc = x.clone().requires_grad_(True)
+    want = ofe.cepstral_frontend(xc, fb, dct, win)
+    got = eng.frontend_fwd(x.to(cuda_device)).cpu()
+    assert got.shape == want.shape
+    assert (got - want).abs().max().item() < 1e-3
+    gc = torch.randn(want.shape, generator=g)
+    (gx_want,) = torch.autograd.grad((want * gc).sum(), xc)
+    gx = eng.frontend_bwd(x.to(cuda_device), gc.to(cuda_device)).cpu()
+    assert helpers.rel_err(gx, gx_want) < 1e-5
+
+
 def _oracle_taps(x, y, state, fwd, feat=None):
     """Oracle forward/backward with every stage tapped.  With ``feat`` (B,1,80,F) the embedding is evaluated at those
     features (a leaf) and the waveform gradient is the oracle frontend's VJP of the resulting feature gradient."""
