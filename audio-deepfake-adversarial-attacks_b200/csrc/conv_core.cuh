@@ -16,24 +16,38 @@ __device__ __forceinline__ void fma4(float (&acc)[8], int off, float a, const fl
 }
 
 // acc[p][0..3] -> channels g4..g4+3, acc[p][4..7] -> channels nh+g4..nh+g4+3, p = 2x2 pixel of the quad.
+// ck_loop (optional): contraction channels actually visited, <= CK, when the staged layout is zero-padded beyond them.
+// slab_all: w_s holds all KS*KS weight slabs (the caller sized it so): they are staged once, before the tap loop, instead of
+// one slab per tap between two block-wide barriers - for small layers the 9 exposed L2 round trips and 18 barriers per
+// tile cost about as much as the FMAs between them.
 template <int KS>
-// ck_loop (optional): contraction channels actually visited, <= CK, when the staged layout is zero-padded beyond them
 __device__ __forceinline__ void conv_core(const float* band, int BW, int CK, int CKp, const float* __restrict__ wg,
                                           float* w_s, int N, int rb, int cb, int g4, bool valid, float (&acc)[4][8],
-                                          int ck_loop = 0) {
+                                          int ck_loop = 0, bool slab_all = false) {
   const int nh = N >> 1;
   const int CKl = ck_loop > 0 ? ck_loop : CK;
   const int slab4 = (CK * N) >> 2;
+  if (slab_all) {
+    const float4* src = reinterpret_cast<const float4*>(wg);
+    float4* dst = reinterpret_cast<float4*>(w_s);
+    for (int i = threadIdx.x; i < KS * KS * slab4; i += blockDim.x) dst[i] = __ldg(src + i);
+    __syncthreads();  // also orders the caller's band stores before the first read
+  }
 #pragma unroll 1
   for (int tap = 0; tap < KS * KS; ++tap) {
     const int dy = tap / KS, dx = tap % KS;
-    __syncthreads();
-    {
-      const float4* src = reinterpret_cast<const float4*>(wg + (size_t)tap * CK * N);
-      float4* dst = reinterpret_cast<float4*>(w_s);
-      for (int i = threadIdx.x; i < slab4; i += blockDim.x) dst[i] = __ldg(src + i);
+    const float* w_t = w_s;
+    if (slab_all) {
+      w_t = w_s + (size_t)tap * CK * N;
+    } else {
+      __syncthreads();
+      {
+        const float4* src = reinterpret_cast<const float4*>(wg + (size_t)tap * CK * N);
+        float4* dst = reinterpret_cast<float4*>(w_s);
+        for (int i = threadIdx.x; i < slab4; i += blockDim.x) dst[i] = __ldg(src + i);
+      }
+      __syncthreads();
     }
-    __syncthreads();
     if (!valid) continue;
     const float* p00 = band + ((size_t)(rb + dy) * BW + cb + dx) * CKp;
     const float* p01 = p00 + CKp;
@@ -50,8 +64,8 @@ __device__ __forceinline__ void conv_core(const float* band, int BW, int CK, int
                                 {a3.x, a3.y, a3.z, a3.w}};
 #pragma unroll
         for (int u = 0; u < 4; ++u) {
-          const float4 wl = *reinterpret_cast<const float4*>(w_s + (ci + u) * N + g4);
-          const float4 wh = *reinterpret_cast<const float4*>(w_s + (ci + u) * N + nh + g4);
+          const float4 wl = *reinterpret_cast<const float4*>(w_t + (ci + u) * N + g4);
+          const float4 wh = *reinterpret_cast<const float4*>(w_t + (ci + u) * N + nh + g4);
 #pragma unroll
           for (int p = 0; p < 4; ++p) {
             fma4(acc[p], 0, av[p][u], wl);
@@ -63,8 +77,8 @@ __device__ __forceinline__ void conv_core(const float* band, int BW, int CK, int
 #pragma unroll 1
       for (int ci = 0; ci < CKl; ++ci) {
         const float av[4] = {p00[ci], p01[ci], p10[ci], p11[ci]};
-        const float4 wl = *reinterpret_cast<const float4*>(w_s + ci * N + g4);
-        const float4 wh = *reinterpret_cast<const float4*>(w_s + ci * N + nh + g4);
+        const float4 wl = *reinterpret_cast<const float4*>(w_t + ci * N + g4);
+        const float4 wh = *reinterpret_cast<const float4*>(w_t + ci * N + nh + g4);
 #pragma unroll
         for (int p = 0; p < 4; ++p) {
           fma4(acc[p], 0, av[p], wl);

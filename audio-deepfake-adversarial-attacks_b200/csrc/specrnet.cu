@@ -65,6 +65,7 @@ struct SrArgs {
   const float* h;
   int qpc;              // quads (2x2 output pixels) per CTA
   int CKr;              // contraction channels that are not zero padding (multiple of 4 when CK is), <= CK
+  int slab_all;         // 1: all 9 weight slabs are staged once per CTA (small layers), 0: one slab per tap
 };
 
 // 4 consecutive channels (c..c+3) of the gradient at conv2's output pixel (yy, xx): un-pool of
@@ -106,7 +107,7 @@ __global__ void __launch_bounds__(256) sr_conv_kernel(SrArgs a, int band_floats)
   const int CKp = (CK & 3) == 0 ? CK + 4 : CK;
   float* band = smem;
   float* w_s = smem + band_floats;
-  float* s_part = w_s + CK * a.N;  // F2 only: qpc x N partial sums
+  float* s_part = w_s + (a.slab_all ? 9 : 1) * CK * a.N;  // F2 only: qpc x N partial sums
   const int b = blockIdx.y, tid = threadIdx.x, nt = blockDim.x;
 
   // ---- stage the band: rows 2*qy0-1 ..., columns -1 .. 2*QW ----
@@ -157,7 +158,7 @@ __global__ void __launch_bounds__(256) sr_conv_kernel(SrArgs a, int band_floats)
   for (int p = 0; p < 4; ++p)
 #pragma unroll
     for (int j = 0; j < 8; ++j) acc[p][j] = 0.f;
-  conv_core<3>(band, g.BW, CK, CKp, a.wpk, w_s, N, 2 * (qy - g.qy0), 2 * qx, 4 * cg, valid, acc, a.CKr);
+  conv_core<3>(band, g.BW, CK, CKp, a.wpk, w_s, N, 2 * (qy - g.qy0), 2 * qx, 4 * cg, valid, acc, a.CKr, a.slab_all != 0);
 
   const int nh = N >> 1, c0 = 4 * cg;
   if (MODE == F1) {
@@ -670,8 +671,16 @@ int sr_band_rows(int QH, int QW, int qpc) {  // rows of the halo band of a tile 
   if (qpc % QW == 0) return 2 * std::min(qpc / QW, QH) + 2;
   return band_rows_max(QH, QW, 1, qpc);
 }
+bool sr_slab_all(int N, int CK) {
+  static const int on = [] {
+    const char* e = getenv("ADVB_SR_SLAB_ALL");
+    return e != nullptr ? atoi(e) : 1;
+  }();
+  return on != 0 && 9 * CK * N * (int)sizeof(float) <= 24 * 1024;
+}
 int sr_qpc(int N, int CK, int QH, int QW) {
   const int CKp = (CK % 4 == 0) ? CK + 4 : CK;
+  const int wfl = (sr_slab_all(N, CK) ? 9 : 1) * CK * N;
   const int G = N / 8;
   int best = 32;
   // measured (B = 256, ms per PGD-40 call): row-aligned tiles of <= 256 threads pay where the band is deep and the thread
@@ -690,7 +699,7 @@ int sr_qpc(int N, int CK, int QH, int QW) {
   }();
   for (int rows = 1; rows <= QH && rows * QW * G <= max_threads; ++rows) {
     const int qpc = rows * QW;
-    const size_t smem = (size_t)(sr_band_rows(QH, QW, qpc) * (2 * QW + 2) * CKp + CK * N + qpc * N) * sizeof(float);
+    const size_t smem = (size_t)(sr_band_rows(QH, QW, qpc) * (2 * QW + 2) * CKp + wfl + qpc * N) * sizeof(float);
     if (smem > 110 * 1024) break;
     if (qpc >= 24) best = qpc;
   }
@@ -703,9 +712,10 @@ int launch_conv(SrArgs a, bool floor_quads, const char* tag, cudaStream_t stream
   ADVB_CHECK(QW > 0 && QH > 0, "empty SpecRNet conv output");
   const int CKp = (a.CK % 4 == 0) ? a.CK + 4 : a.CK;
   a.qpc = sr_qpc(a.N, a.CK, QH, QW);
+  a.slab_all = sr_slab_all(a.N, a.CK) ? 1 : 0;
   int band = sr_band_rows(QH, QW, a.qpc) * (2 * QW + 2) * CKp;
   band = (band + 3) & ~3;
-  const size_t smem = (size_t)(band + a.CK * a.N + (MODE == F2 ? a.qpc * a.N : 0)) * sizeof(float);
+  const size_t smem = (size_t)(band + (a.slab_all ? 9 : 1) * a.CK * a.N + (MODE == F2 ? a.qpc * a.N : 0)) * sizeof(float);
   ADVB_CHECK(smem <= 227 * 1024, "SpecRNet conv tile does not fit shared memory");
   ADVB_CHECK(a.N % 8 == 0 && a.N <= 64, "SpecRNet conv: N must be a multiple of 8, <= 64");
   ADVB_CUDA_OK(cudaFuncSetAttribute(sr_conv_kernel<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
