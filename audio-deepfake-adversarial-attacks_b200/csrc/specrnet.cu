@@ -676,7 +676,13 @@ bool sr_slab_all(int N, int CK) {
     const char* e = getenv("ADVB_SR_SLAB_ALL");
     return e != nullptr ? atoi(e) : 1;
   }();
-  return on != 0 && 9 * CK * N * (int)sizeof(float) <= 24 * 1024;
+  // 24 KB = block 0's 24 x 24 layers (conv2 forward 107 -> 99 ms, backward 103 -> 94 ms per PGD-40 call at B = 256); with a
+  // 64 KB limit block 2's 64 x 24 backward also qualifies and got slower (36 -> 54 ms: it loses a CTA per SM)
+  static const int limit_kb = [] {
+    const char* e = getenv("ADVB_SR_SLAB_KB");
+    return e != nullptr ? atoi(e) : 24;
+  }();
+  return on != 0 && 9 * CK * N * (int)sizeof(float) <= limit_kb * 1024;
 }
 int sr_qpc(int N, int CK, int QH, int QW) {
   const int CKp = (CK % 4 == 0) ? CK + 4 : CK;
