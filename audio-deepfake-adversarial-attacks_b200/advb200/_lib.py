@@ -11,7 +11,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libadvb200.so")
 LIB_PATH = os.environ.get("ADVB_LIB", LIB_PATH)  # tuning experiments: an alternative build of the same library
 
-MODEL_LCNN, MODEL_SPECRNET, MODEL_RAWNET3 = 1, 2, 3
+MODEL_LCNN, MODEL_SPECRNET, MODEL_RAWNET3, MODEL_FRONTEND_ONLY = 1, 2, 3, 4
 FRONTEND_NONE, FRONTEND_LFCC, FRONTEND_MFCC = 0, 1, 2
 ATTACK_FGSM, ATTACK_PGD, ATTACK_PGDL2, ATTACK_FAB, ATTACK_CW = 1, 2, 3, 4, 5
 GRAD_CE, GRAD_LOGIT = 0, 1
@@ -32,7 +32,7 @@ class AttackDesc(C.Structure):
     _fields_ = [
         ("kind", C.c_int), ("eps", C.c_float), ("alpha", C.c_float), ("steps", C.c_int), ("eps_div", C.c_float),
         ("alpha_max", C.c_float), ("eta", C.c_float), ("beta", C.c_float), ("c", C.c_float), ("kappa", C.c_float),
-        ("lr", C.c_float), ("n_global_batch", C.c_int),
+        ("lr", C.c_float), ("n_global_batch", C.c_int), ("targeted", C.c_int), ("target_labels", C.c_void_p),
     ]
 
 
@@ -45,6 +45,7 @@ SIGNATURES = {
     "advb_workspace_bytes": (C.c_size_t, [C.c_void_p]),
     "advb_set_option": (C.c_int, [C.c_void_p, C.c_char_p, C.c_int]),
     "advb_rebind": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(TensorRef)]),
+    "advb_invalidate_weights": (C.c_int, [C.c_void_p]),
     "advb_attack": (C.c_int, [C.c_void_p, C.POINTER(AttackDesc), C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
                               C.c_int, C.c_int, C.c_void_p]),
     "advb_attack_minmax": (C.c_int, [C.c_void_p, C.POINTER(AttackDesc), C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,

@@ -33,16 +33,25 @@ def _require_cuda(t: torch.Tensor, what: str):
         raise RuntimeError(f"advb200 has no CPU path: {what} is on {t.device}; move the model and batch to a CUDA device")
 
 
+def _is_frontend(module: nn.Module) -> bool:
+    """A bare LFCC / MFCC transform (torchaudio's or the advb200 holder): ``LFCC_FN`` / ``MFCC_FN`` of src/frontends.py."""
+    keys = dict(module.named_buffers()).keys()
+    return "dct_mat" in keys and ("filter_mat" in keys or "MelSpectrogram.mel_scale.fb" in keys)
+
+
 class Engine:
     def __init__(self, module: nn.Module, max_batch: int, n_samples: int):
         self.lib = _lib.load()
+        self._prefix = ""
         kind = _MODEL_KINDS.get(type(module).__name__)
+        if kind is None and _is_frontend(module):
+            kind, self._prefix = _lib.MODEL_FRONTEND_ONLY, "frontend."
         if kind is None:
             raise NotImplementedError(f"advb200 engine does not support model class {type(module).__name__}")
         self.module_ref = weakref.ref(module)
         self.max_batch, self.n_samples = int(max_batch), int(n_samples)
         refs, self._ptrs = self._tensor_table(module)
-        first = next(module.parameters())
+        first = next(iter(self._state.values()))
         _require_cuda(first, "the model")
         self.device = first.device
         desc = _lib.ModelDesc(kind, _frontend_kind(self._state), self.device.index or 0, self.max_batch, self.n_samples,
@@ -52,9 +61,12 @@ class Engine:
             _lib.check(self.lib.advb_create(C.byref(handle), C.byref(desc)))
         self.handle = handle
         self._finalizer = weakref.finalize(self, self.lib.advb_destroy, handle)
+        # this host tracks weight versions itself (data_ptr + tensor._version stamps): unchanged weights skip the repack
+        _lib.check(self.lib.advb_set_option(handle, b"weight_cache", 1))
+        self._versions = None
 
     def _tensor_table(self, module):
-        state = {k: v for k, v in module.state_dict(keep_vars=True).items() if v.dtype == torch.float32}
+        state = {self._prefix + k: v for k, v in module.state_dict(keep_vars=True).items() if v.dtype == torch.float32}
         for k, v in state.items():
             _require_cuda(v, f"tensor '{k}'")
             if not v.is_contiguous():
@@ -67,14 +79,27 @@ class Engine:
         return refs, tuple(v.data_ptr() for v in state.values())
 
     def _sync_weights(self):
-        """Weights are read live; only if a storage was *replaced* (load_state_dict keeps storages) re-point."""
+        """Weights are read live.  A storage that was *replaced* is re-pointed (load_state_dict keeps storages); a tensor
+        whose autograd version counter moved (optimizer.step(), load_state_dict, any in-place op on the parameter) marks the
+        packed weight images stale.  In-place writes that bypass the version counter (``p.data.mul_()``) are invisible to
+        this check: call ``engine.invalidate()`` after them."""
         module = self.module_ref()
         if module is None:
             raise RuntimeError("model was garbage-collected")
-        ptrs = tuple(v.data_ptr() for v in module.state_dict(keep_vars=True).values() if v.dtype == torch.float32)
+        live = [v for v in module.state_dict(keep_vars=True).values() if v.dtype == torch.float32]
+        ptrs = tuple(v.data_ptr() for v in live)
         if ptrs != self._ptrs:
             refs, self._ptrs = self._tensor_table(module)
             _lib.check(self.lib.advb_rebind(self.handle, len(refs), refs))
+            self._versions = None
+        versions = tuple(v._version for v in live)
+        if versions != self._versions:
+            _lib.check(self.lib.advb_invalidate_weights(self.handle))
+            self._versions = versions
+
+    def invalidate(self):
+        """Force the next call to repack the weights (after writes the version stamps cannot see)."""
+        self._versions = None
 
     def _stream(self):
         return C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
@@ -87,18 +112,43 @@ class Engine:
             raise ValueError("batch does not fit this engine handle")
         return x.contiguous()
 
-    def attack(self, desc: "_lib.AttackDesc", x, y, start=None, minmax=False):
-        """``minmax=True``: ``x`` is the raw waveform batch; to_minmax / revert_minmax run inside the same native call."""
+    def attack(self, desc: "_lib.AttackDesc", x, y, start=None, minmax=False, target=None):
+        """``minmax=True``: ``x`` is the raw waveform batch; to_minmax / revert_minmax run inside the same native call.
+        ``target``: target labels of the targeted modes (attack.py:60-108); sets ``desc.targeted``."""
         x = self._check_x(x)
-        y = y.to(device=x.device, dtype=torch.int64).contiguous()
+        y = self._check_labels(y, x)
         self._sync_weights()
         out = torch.empty_like(x)
-        sp = C.c_void_p(start.contiguous().data_ptr()) if start is not None else None
+        sp = None
+        if start is not None:
+            if start.dtype != torch.float32 or start.shape != x.shape or start.device != x.device:
+                raise ValueError(f"random start must be a float32 tensor of shape {tuple(x.shape)} on {x.device}, got "
+                                 f"{start.dtype} {tuple(start.shape)} on {start.device}")
+            start = start.contiguous()  # kept alive in this frame until the call has been enqueued
+            sp = C.c_void_p(start.data_ptr())
+        desc.targeted, desc.target_labels = 0, None
+        if target is not None:
+            target = self._check_labels(target, x)  # kept alive in this frame until the call has been enqueued
+            desc.targeted, desc.target_labels = 1, target.data_ptr()
         fn = self.lib.advb_attack_minmax if minmax else self.lib.advb_attack
         with torch.cuda.device(self.device):
             _lib.check(fn(self.handle, C.byref(desc), x.data_ptr(), y.data_ptr(), sp, out.data_ptr(),
                                             x.shape[0], x.shape[1], self._stream()))
         return out
+
+    @staticmethod
+    def _check_labels(y, x):
+        """int64 labels in {0, 1} on the batch's device (the head uses (float) y and FAB / CW assume two classes)."""
+        if y is None or y.dim() != 1 or y.shape[0] != x.shape[0]:
+            raise ValueError(f"expected {x.shape[0]} labels of shape (B,)")
+        if y.dtype.is_floating_point or y.dtype == torch.bool:
+            raise ValueError(f"labels must be integer class indices, got {y.dtype}")
+        if not y.is_cuda:  # free on the host (src/trainer.py passes CPU labels)
+            if y.numel() and (int(y.min()) < 0 or int(y.max()) > 1):
+                raise ValueError("labels must be 0 (spoof) or 1 (bonafide)")
+        else:  # no host sync: device-side assertion
+            torch._assert_async(((y == 0) | (y == 1)).all())
+        return y.to(device=x.device, dtype=torch.int64).contiguous()
 
     def forward(self, x):
         x = self._check_x(x)
@@ -125,6 +175,7 @@ class Engine:
 
     def frontend_fwd(self, x):
         x = self._check_x(x)
+        self._sync_weights()
         F = 1 + x.shape[1] // 160
         out = torch.empty(x.shape[0], 80, F, device=x.device, dtype=torch.float32)
         with torch.cuda.device(self.device):
@@ -167,7 +218,8 @@ class Engine:
     def set_option(self, key: str, value: int):
         """``conv_path`` (0 tcgen05 / 1 fp32 SIMT), ``tf32_passes`` (3 = 3xTF32 / 1 = single pass), ``conv_sched``
         (0 persistent kernels / 1 one-tile-per-CTA kernels), ``conv0_bwd`` (first block backward: 0 fp32 cell kernel /
-        1 tcgen05 GEMM + col2im)."""
+        1 tcgen05 GEMM + col2im), ``graph`` (1 = replay the attack iteration as a CUDA graph), ``fuse_update`` (1 = FGSM /
+        PGD update rule in the frontend backward's epilogue)."""
         _lib.check(self.lib.advb_set_option(self.handle, key.encode(), int(value)))
 
     def profile_begin(self):
@@ -194,7 +246,9 @@ class Engine:
 
 def engine_for(model: nn.Module, batch: int, n_samples: int) -> Engine:
     module = unwrap(model)
-    first = next(module.parameters())
+    first = next(module.parameters(), None)
+    if first is None:  # a bare frontend transform has buffers only
+        first = next(module.buffers())
     _require_cuda(first, "the model")
     per_module = _ENGINES.setdefault(module, {})
     key = (first.device.index or 0, int(n_samples))
@@ -214,7 +268,14 @@ def model_forward(module: nn.Module, x: torch.Tensor) -> torch.Tensor:
 
 
 def frontend_forward(frontend: nn.Module, x: torch.Tensor) -> torch.Tensor:
-    raise NotImplementedError("call the frontend through a model handle: engine_for(model, B, T).frontend_fwd(x)")
+    """``LFCC_FN(x)`` / ``MFCC_FN(x)`` (src/frontends.py:13-32): coefficients (B, 80, 1 + T // 160), computed by the CUDA
+    frontend kernels on a frontend-only engine handle that borrows the transform's live buffers."""
+    _require_cuda(x, "the batch")
+    squeeze = x.dim() == 1
+    if squeeze:
+        x = x.unsqueeze(0)
+    out = engine_for(frontend, x.shape[0], x.shape[1]).frontend_fwd(x)
+    return out[0] if squeeze else out
 
 
 def projection_linf(t: torch.Tensor, w: torch.Tensor, b: torch.Tensor) -> torch.Tensor:

@@ -8,4 +8,5 @@ from .attack import Attack
 from .attacks import CW, FAB, FGSM, PGD, PGDL2
 
 __version__ = "3.2.7+advb200"
+__advb200__ = True  # marker: this module is the native replacement, not the vendored package
 __all__ = ["Attack", "FGSM", "PGD", "PGDL2", "FAB", "CW"]

@@ -33,9 +33,53 @@ class Attack(object):
         print("Attack mode is changed to 'default.'")
 
     def set_mode_targeted_by_function(self, target_map_function=None):
-        raise NotImplementedError("targeted modes are not used by the repo (SURVEY.md §8 f4) and not built natively")
+        """attack.py:60-77.  ``None`` uses the given labels as target labels."""
+        if "targeted" not in self._supported_mode:
+            raise ValueError("Targeted mode is not supported.")
+        self._attack_mode = "targeted"
+        self._targeted = True
+        self._target_map_function = target_map_function
+        print("Attack mode is changed to 'targeted.'")
 
-    set_mode_targeted_least_likely = set_mode_targeted_random = set_mode_targeted_by_function
+    def set_mode_targeted_least_likely(self, kth_min=1):
+        """attack.py:79-94."""
+        if "targeted" not in self._supported_mode:
+            raise ValueError("Targeted mode is not supported.")
+        self._attack_mode = "targeted(least-likely)"
+        self._targeted = True
+        assert kth_min > 0
+        self._kth_min = kth_min
+        self._target_map_function = self._get_least_likely_label
+        print("Attack mode is changed to 'targeted(least-likely).'")
+
+    def set_mode_targeted_random(self):
+        """attack.py:96-108."""
+        if "targeted" not in self._supported_mode:
+            raise ValueError("Targeted mode is not supported.")
+        self._attack_mode = "targeted(random)"
+        self._targeted = True
+        self._target_map_function = self._get_random_target_label
+        print("Attack mode is changed to 'targeted(random).'")
+
+    @torch.no_grad()
+    def _get_target_label(self, images, labels=None):
+        """attack.py:258-270 (the model.eval()/train() flips are no-ops here: the engine always runs the eval forward)."""
+        if not self._targeted:
+            raise ValueError("Please define target_map_function.")
+        if self._target_map_function is None:  # "None for using input labels as targeted labels"
+            return labels
+        return self._target_map_function(images, labels)
+
+    @torch.no_grad()
+    def _get_least_likely_label(self, images, labels=None):
+        """attack.py:273-287 on the model's own output.  The detectors emit ONE logit (B,1), so ``outputs.shape[-1]`` is 1
+        and the reference's ``list(range(1)).remove(label)`` raises for every label but 0: the
+        least-likely / random target pickers never worked on these models.  Same failure here, stated plainly."""
+        raise ValueError("targeted(least-likely) / targeted(random) pick targets over outputs.shape[-1] classes; the "
+                         "detectors emit a single logit (B,1), where the reference's picker fails too (attack.py:280). "
+                         "Use set_mode_targeted_by_function(lambda images, labels: 1 - labels).")
+
+    _get_random_target_label = _get_least_likely_label
 
     def set_return_type(self, type):
         if type == "float":

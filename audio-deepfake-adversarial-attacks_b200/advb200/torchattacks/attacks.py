@@ -17,11 +17,13 @@ class FGSM(Attack):
     def __init__(self, model, eps=0.007):
         super().__init__("FGSM", model)
         self.eps = eps
-        self._supported_mode = ["default"]
+        self._supported_mode = ["default", "targeted"]
 
     def forward(self, images, labels):
         images, labels = self._prepare(images, labels)
-        return self._engine(images).attack(_desc(_lib.ATTACK_FGSM, eps=self.eps), images, labels, minmax=self._fused_minmax)
+        target = self._get_target_label(images, labels) if self._targeted else None
+        return self._engine(images).attack(_desc(_lib.ATTACK_FGSM, eps=self.eps), images, labels, minmax=self._fused_minmax,
+                                           target=target)
 
 
 class PGD(Attack):
@@ -31,17 +33,18 @@ class PGD(Attack):
         self.alpha = alpha
         self.steps = steps
         self.random_start = random_start
-        self._supported_mode = ["default"]
+        self._supported_mode = ["default", "targeted"]
 
     def forward(self, images, labels, noise=None):
         images, labels = self._prepare(images, labels)
+        target = self._get_target_label(images, labels) if self._targeted else None
         if self.random_start and noise is None:
             # same draw, on the same device RNG stream, as pgd.py:56
             noise = torch.empty_like(images).uniform_(-self.eps, self.eps)
         if noise is not None:
             noise = noise.to(images.device)
         d = _desc(_lib.ATTACK_PGD, eps=self.eps, alpha=self.alpha, steps=self.steps)
-        return self._engine(images).attack(d, images, labels, noise, minmax=self._fused_minmax)
+        return self._engine(images).attack(d, images, labels, noise, minmax=self._fused_minmax, target=target)
 
 
 class PGDL2(Attack):
@@ -52,10 +55,11 @@ class PGDL2(Attack):
         self.steps = steps
         self.random_start = random_start
         self.eps_for_division = eps_for_division
-        self._supported_mode = ["default"]
+        self._supported_mode = ["default", "targeted"]
 
     def forward(self, images, labels, delta=None):
         images, labels = self._prepare(images, labels)
+        target = self._get_target_label(images, labels) if self._targeted else None
         if self.random_start and delta is None:
             # pgdl2.py:57-61: same RNG draws in the same order (normal_ then uniform_)
             delta = torch.empty_like(images).normal_()
@@ -65,7 +69,7 @@ class PGDL2(Attack):
         if delta is not None:
             delta = delta.to(images.device)
         d = _desc(_lib.ATTACK_PGDL2, eps=self.eps, alpha=self.alpha, steps=self.steps, eps_div=self.eps_for_division)
-        return self._engine(images).attack(d, images, labels, delta, minmax=self._fused_minmax)
+        return self._engine(images).attack(d, images, labels, delta, minmax=self._fused_minmax, target=target)
 
 
 class FAB(Attack):
@@ -79,8 +83,7 @@ class FAB(Attack):
         super().__init__("FAB", model)
         if norm != "Linf":
             raise NotImplementedError("advb200 FAB implements norm='Linf' (the AttackEnum presets); L2/L1 are SURVEY §8 f4")
-        if n_restarts != 1 or targeted:
-            raise NotImplementedError("advb200 FAB implements n_restarts=1, untargeted (the AttackEnum presets)")
+        # (the reference's patched copy ignores `targeted` too: fab.py:63 sets self.targeted = False unconditionally)
         self.norm = norm
         self.n_restarts = n_restarts
         self.eps = eps if eps is not None else {"Linf": 0.3, "L2": 1.0, "L1": 5.0}[norm]
@@ -104,8 +107,6 @@ class FAB(Attack):
         return (self._engine(x).forward(x)[:, 0] > 0).long()
 
     def attack_single_run(self, x, y=None, use_rand_start=False):
-        if use_rand_start:
-            raise NotImplementedError("random restarts are not built natively (n_restarts=1 in every preset)")
         y_pred = self._get_predicted_label(x)
         y = y_pred.clone() if y is None else y.clone().long().to(x.device)
         pred = y_pred == y
@@ -113,8 +114,15 @@ class FAB(Attack):
             return x
         idx = pred.nonzero().flatten()
         im2, la2 = x[idx].contiguous(), y[idx].contiguous()
+        start = None
+        if use_rand_start:
+            # fab.py:176-206 (Linf): res2 is still 1e10 at this point, so the radius is eps; same RNG draw (torch.rand on
+            # the CPU generator, then moved - exactly what fab.py:178 does), same op order
+            t = 2 * torch.rand(im2.shape).to(im2.device) - 1
+            radius = torch.full((im2.shape[0], 1), float(self.eps), device=im2.device)
+            start = (im2 + radius * t / t.abs().max(dim=1, keepdim=True)[0] * .5).clamp(0.0, 1.0)
         d = _desc(_lib.ATTACK_FAB, eps=self.eps, steps=self.steps, alpha_max=self.alpha_max, eta=self.eta, beta=self.beta)
-        adv = self._engine(x).attack(d, im2, la2)  # rows never found adversarial come back equal to im2
+        adv = self._engine(x).attack(d, im2, la2, start)  # rows never found adversarial come back equal to im2
         adv_c = x.clone()
         adv_c[idx] = adv
         return adv_c
@@ -125,16 +133,18 @@ class FAB(Attack):
         # fab.py:504-505: the reference reseeds the global RNGs on every call (kept: it affects later shuffles)
         torch.random.manual_seed(self.seed)
         torch.cuda.random.manual_seed(self.seed)
-        ind_to_fool = acc.nonzero().flatten()
-        if ind_to_fool.numel() != 0:
-            x_to_fool, y_to_fool = x[ind_to_fool].contiguous(), y[ind_to_fool].contiguous()
-            adv_curr = self.attack_single_run(x_to_fool, y_to_fool, use_rand_start=False)
-            eng = self._engine(x)
-            acc_curr = self._get_predicted_label(adv_curr) == y_to_fool
-            res, _ = eng.row_diff_norms(x_to_fool, adv_curr)
-            acc_curr = torch.max(acc_curr, res > self.eps)
-            ind_curr = (acc_curr == 0).nonzero().flatten()
-            adv[ind_to_fool[ind_curr]] = adv_curr[ind_curr].clone()
+        for counter in range(self.n_restarts):  # fab.py:507-526
+            ind_to_fool = acc.nonzero().flatten()
+            if ind_to_fool.numel() != 0:
+                x_to_fool, y_to_fool = x[ind_to_fool].contiguous(), y[ind_to_fool].contiguous()
+                adv_curr = self.attack_single_run(x_to_fool, y_to_fool, use_rand_start=(counter > 0))
+                eng = self._engine(x)
+                acc_curr = self._get_predicted_label(adv_curr) == y_to_fool
+                res, _ = eng.row_diff_norms(x_to_fool, adv_curr)
+                acc_curr = torch.max(acc_curr, res > self.eps)
+                ind_curr = (acc_curr == 0).nonzero().flatten()
+                acc[ind_to_fool[ind_curr]] = 0
+                adv[ind_to_fool[ind_curr]] = adv_curr[ind_curr].clone()
         return adv
 
 
@@ -147,9 +157,10 @@ class CW(Attack):
         self.kappa = kappa
         self.steps = steps
         self.lr = lr
-        self._supported_mode = ["default"]
+        self._supported_mode = ["default", "targeted"]
 
     def forward(self, images, labels):
         images, labels = self._prepare(images, labels)
+        target = self._get_target_label(images, labels) if self._targeted else None
         d = _desc(_lib.ATTACK_CW, c=self.c, kappa=self.kappa, steps=self.steps, lr=self.lr)
-        return self._engine(images).attack(d, images, labels)
+        return self._engine(images).attack(d, images, labels, target=target)

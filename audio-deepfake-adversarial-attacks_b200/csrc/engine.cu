@@ -4,6 +4,7 @@
 // API call re-reads the borrowed weight tensors (repack kernels at the head of the call), enqueues the whole
 // attack on the caller's stream and returns without synchronising.
 #include <cuda_runtime.h>
+#include <nvtx3/nvToolsExt.h>
 
 #include <string.h>
 
@@ -46,6 +47,11 @@ struct TensorRef {
   int64_t n;
 };
 
+struct NvtxRange {  // NVTX range around each API phase (nsys / ncu --nvtx): header-only nvtx3, a no-op without a tool attached
+  explicit NvtxRange(const char* name) { nvtxRangePushA(name); }
+  ~NvtxRange() { nvtxRangePop(); }
+};
+
 struct LcnnBlock {
   int idx, Cin, Cout, KS, bn_idx;
   bool pool;
@@ -77,6 +83,23 @@ struct advb_handle {
   int tf32_passes = 3;  // 3 = 3xTF32 (fp32-class accuracy), 1 = single-pass tf32
   int conv_sched = 0;   // 0 = persistent warp-specialised conv kernels, 1 = one-tile-per-CTA kernels only
   int conv0_bwd = 0;    // first block backward: 0 = fp32 cell kernel (conv0_bwd.cu), 1 = tcgen05 GEMM + col2im
+  int use_graph = 1;    // 1 = the PGD / PGDL2 iteration is captured once into a CUDA graph and replayed
+  int fuse_update = 1;  // 1 = FGSM / PGD update rule applied in the frontend backward's epilogue (no gradient in HBM)
+  int weight_cache = 0; // 1 = the caller promises advb_invalidate_weights() after every weight change: skip the repack otherwise
+  bool packed_valid = false;
+  int64_t bind_epoch = 0;  // bumped whenever the borrowed tensor table changes (graph cache key)
+
+  // cached CUDA graph of one attack iteration (all kernel arguments are engine-owned buffers, see run_attack)
+  struct GraphCache {
+    cudaGraphExec_t exec = nullptr;
+    cudaGraph_t graph = nullptr;
+    cudaEvent_t done = nullptr;  // recorded after the last replay: waited on before the exec is destroyed
+    int64_t launches = 0;        // kernel launches per replay
+    std::string key;
+  } gc;
+  cudaStream_t cap_stream = nullptr;
+  float *x_in = nullptr, *adv2 = nullptr;  // engine-owned copies: clean clips, second ping-pong iterate
+  int64_t* y_in = nullptr;
 
   // frontend
   float2* tw = nullptr;
@@ -108,7 +131,7 @@ struct advb_handle {
   float *grad = nullptr, *partial_g = nullptr, *partial_d = nullptr, *coef_tmp = nullptr;
   FabScratch fab{};  // allocated on the first FAB / CW call
   CwScratch cw{};
-  float *mm_x01 = nullptr, *mm_adv = nullptr, *mm_mn = nullptr, *mm_mx = nullptr;  // advb_attack_minmax scratch (first use)
+  float *mm_mn = nullptr, *mm_mx = nullptr;  // advb_attack_minmax: per-clip min / max (first use)
   float* host_cost = nullptr;  // pinned: CW's batch-wide early-stop scalar (cw.py:107-110)
 
   template <typename Tp>
@@ -150,6 +173,8 @@ const int kLcnnSpec[9][6] = {
 };
 
 int bind_tensors(advb_handle* h, int n, const advb_tensor_ref* refs) {
+  h->bind_epoch++;
+  h->packed_valid = false;
   for (int i = 0; i < n; ++i) {
     ADVB_CHECK(refs[i].name != nullptr && refs[i].ptr != nullptr, "null tensor reference");
     h->tensors[refs[i].name] = TensorRef{refs[i].ptr, refs[i].numel};
@@ -373,7 +398,7 @@ int lcnn_forward(advb_handle* h, const float* x, int B, cudaStream_t st) {
 
 // Gradient of (mode 0) the mean 2-class CE or (mode 1) the logit, w.r.t. the waveform of the last forward.
 int lcnn_backward(advb_handle* h, const float* x, const int64_t* y, int B, int mode, int n_global, float* gx,
-                  cudaStream_t st, const float* coef = nullptr) {
+                  cudaStream_t st, const float* coef = nullptr, const FusedUpdate* upd = nullptr) {
   ADVB_TRY(head_backward(h->logits, reinterpret_cast<const long long*>(y), h->t("m_output_act.weight"), h->dl2, B,
                          h->L, mode, n_global, st, coef));
   ADVB_TRY(blstm_backward(h->lp[1], h->gates2, h->dl2, h->cs2, nullptr, h->dl1, B, h->L, st));
@@ -409,7 +434,7 @@ int lcnn_backward(advb_handle* h, const float* x, const int64_t* y, int B, int m
   else
     ADVB_TRY(conv0_backward(k0.gout, k0.codes, h->t("m_transform.0.weight"), h->g_coef, B, k0.H, k0.W, k0.Ho, k0.Wo, st));
   ADVB_TRY(frontend_backward(h->ftb, h->fst, x, B, h->T, h->dB, h->g_coef, (long long)h->F * 80, 80, 1,
-                             h->mass_partial, h->g_dB, gx, st));
+                             h->mass_partial, h->g_dB, gx, st, upd));
   return 0;
 }
 
@@ -562,7 +587,7 @@ int specrnet_forward(advb_handle* h, const float* x, int B, cudaStream_t st) {
 }
 
 int specrnet_backward(advb_handle* h, const float* x, const int64_t* y, int B, int mode, int n_global, float* gx,
-                      cudaStream_t st, const float* coef) {
+                      cudaStream_t st, const float* coef, const FusedUpdate* upd = nullptr) {
   ADVB_TRY(sr_gru_backward(h->gru, h->sr[2].xn, h->logits, reinterpret_cast<const long long*>(y), mode, n_global, coef,
                            h->sr[2].g_xn, B, h->sr_L, st));
   const char* tags[3] = {"sr_b0", "sr_b2", "sr_b4"};
@@ -572,7 +597,7 @@ int specrnet_backward(advb_handle* h, const float* x, const int64_t* y, int B, i
     ADVB_TRY(sr_block_backward(h->sr[i], in, gin, B, i == 0, h->sr_bn4, tags[i], st));
   }
   ADVB_TRY(frontend_backward(h->ftb, h->fst, x, B, h->T, h->dB, h->g_coef, (long long)h->F * 80, 80, 1, h->mass_partial,
-                             h->g_dB, gx, st));
+                             h->g_dB, gx, st, upd));
   return 0;
 }
 
@@ -595,11 +620,18 @@ int prepare_rawnet3(advb_handle* h, cudaStream_t st) {
 }
 
 int model_prepare(advb_handle* h, cudaStream_t st) {
-  if (h->model_kind == ADVB_MODEL_RAWNET3) return prepare_rawnet3(h, st);
-  if (h->model_kind == ADVB_MODEL_LCNN) return prepare_lcnn(h, st);
-  if (h->model_kind == ADVB_MODEL_SPECRNET) return prepare_specrnet(h, st);
-  set_error("model kind not implemented");
-  return 1;
+  // Weights are live (adversarial training mutates them between calls): by default every API call repacks them.  A host
+  // that tracks weight versions (advb200/engine.py: data_ptr + tensor._version stamps) opts into "weight_cache" and
+  // calls advb_invalidate_weights() when a stamp changes; unchanged weights then skip the repack kernels.
+  if (h->weight_cache && h->packed_valid) return 0;
+  NvtxRange nvtx("advb.prepare");
+  int rc = 1;
+  if (h->model_kind == ADVB_MODEL_RAWNET3) rc = prepare_rawnet3(h, st);
+  else if (h->model_kind == ADVB_MODEL_LCNN) rc = prepare_lcnn(h, st);
+  else if (h->model_kind == ADVB_MODEL_SPECRNET) rc = prepare_specrnet(h, st);
+  else set_error("model kind not implemented");
+  h->packed_valid = rc == 0;
+  return rc;
 }
 int model_forward(advb_handle* h, const float* x, int B, cudaStream_t st) {
   if (h->model_kind == ADVB_MODEL_RAWNET3) return rn_forward(h->rn, x, h->logits, B, h->conv_path, h->tf32_passes, st);
@@ -609,18 +641,21 @@ int model_forward(advb_handle* h, const float* x, int B, cudaStream_t st) {
   return 1;
 }
 int model_backward(advb_handle* h, const float* x, const int64_t* y, int B, int mode, int n_global, float* gx,
-                   cudaStream_t st, const float* coef = nullptr) {
-  if (h->model_kind == ADVB_MODEL_RAWNET3)
+                   cudaStream_t st, const float* coef = nullptr, const FusedUpdate* upd = nullptr) {
+  if (h->model_kind == ADVB_MODEL_RAWNET3) {
+    ADVB_CHECK(upd == nullptr, "RawNet3 has no frontend backward to fuse the update into");
     return rn_backward(h->rn, x, h->logits, reinterpret_cast<const long long*>(y), B, mode, n_global, coef, gx, h->conv_path,
                        h->tf32_passes, st);
-  if (h->model_kind == ADVB_MODEL_LCNN) return lcnn_backward(h, x, y, B, mode, n_global, gx, st, coef);
-  if (h->model_kind == ADVB_MODEL_SPECRNET) return specrnet_backward(h, x, y, B, mode, n_global, gx, st, coef);
+  }
+  if (h->model_kind == ADVB_MODEL_LCNN) return lcnn_backward(h, x, y, B, mode, n_global, gx, st, coef, upd);
+  if (h->model_kind == ADVB_MODEL_SPECRNET) return specrnet_backward(h, x, y, B, mode, n_global, gx, st, coef, upd);
   set_error("model kind not implemented");
   return 1;
 }
 
-int check_call(advb_handle* h, int B, int T) {
+int check_call(advb_handle* h, int B, int T, bool needs_model = true) {
   ADVB_CHECK(h != nullptr, "null handle");
+  ADVB_CHECK(!needs_model || h->model_kind != ADVB_MODEL_FRONTEND_ONLY, "this handle holds a frontend only (no model to run)");
   ADVB_CHECK(B > 0 && B <= h->Bmax, "batch exceeds the handle's max_batch");
   ADVB_CHECK(T == h->T, "clip length differs from the handle's n_samples");
   return 0;
@@ -628,32 +663,94 @@ int check_call(advb_handle* h, int B, int T) {
 
 constexpr int ADVB_GRAD_SEEDED = 2;  // internal: d (sum_b coef[b] o_b) / d x
 
+// Lazily allocated scratch: every pointer is tested on its own, so a group whose allocation failed half-way (out of
+// memory) is completed - not skipped - by the next call.
+#define ADVB_ENSURE(ptr, count)                         \
+  do {                                                  \
+    if ((ptr) == nullptr) ADVB_TRY(h->alloc(&(ptr), (count))); \
+  } while (0)
+
 int ensure_fab_scratch(advb_handle* h) {
-  if (h->fab.x1 != nullptr) return 0;
   const size_t n = (size_t)h->Bmax * h->T;
-  ADVB_TRY(h->alloc(&h->fab.x1, n));
-  ADVB_TRY(h->alloc(&h->fab.d3, 2 * n));
-  ADVB_TRY(h->alloc(&h->fab.w, n));
-  ADVB_TRY(h->alloc(&h->fab.bh, h->Bmax));
-  ADVB_TRY(h->alloc(&h->fab.a0, 2 * (size_t)h->Bmax));
-  ADVB_TRY(h->alloc(&h->fab.res2, h->Bmax));
+  ADVB_ENSURE(h->fab.x1, n);
+  ADVB_ENSURE(h->fab.d3, 2 * n);
+  ADVB_ENSURE(h->fab.w, n);
+  ADVB_ENSURE(h->fab.bh, h->Bmax);
+  ADVB_ENSURE(h->fab.a0, 2 * (size_t)h->Bmax);
+  ADVB_ENSURE(h->fab.res2, h->Bmax);
   return 0;
 }
 
 int ensure_cw_scratch(advb_handle* h) {
-  if (h->cw.w != nullptr) return 0;
   const size_t n = (size_t)h->Bmax * h->T;
-  ADVB_TRY(h->alloc(&h->cw.w, n));
-  ADVB_TRY(h->alloc(&h->cw.m, n));
-  ADVB_TRY(h->alloc(&h->cw.v, n));
-  ADVB_TRY(h->alloc(&h->cw.adv, n));
-  ADVB_TRY(h->alloc(&h->cw.l2_partial, (size_t)h->Bmax * 8));
-  ADVB_TRY(h->alloc(&h->cw.cur_l2, h->Bmax));
-  ADVB_TRY(h->alloc(&h->cw.best_l2, h->Bmax));
-  ADVB_TRY(h->alloc(&h->cw.coef, h->Bmax));
-  ADVB_TRY(h->alloc(&h->cw.mask, h->Bmax));
-  ADVB_TRY(h->alloc(&h->cw.cost, 1));
-  ADVB_CUDA_OK(cudaMallocHost(reinterpret_cast<void**>(&h->host_cost), sizeof(float)));
+  ADVB_ENSURE(h->cw.w, n);
+  ADVB_ENSURE(h->cw.m, n);
+  ADVB_ENSURE(h->cw.v, n);
+  ADVB_ENSURE(h->cw.adv, n);
+  ADVB_ENSURE(h->cw.l2_partial, (size_t)h->Bmax * 8);
+  ADVB_ENSURE(h->cw.cur_l2, h->Bmax);
+  ADVB_ENSURE(h->cw.best_l2, h->Bmax);
+  ADVB_ENSURE(h->cw.coef, h->Bmax);
+  ADVB_ENSURE(h->cw.mask, h->Bmax);
+  ADVB_ENSURE(h->cw.cost, 1);
+  if (h->host_cost == nullptr) ADVB_CUDA_OK(cudaMallocHost(reinterpret_cast<void**>(&h->host_cost), sizeof(float)));
+  return 0;
+}
+
+int ensure_loop_buffers(advb_handle* h) {
+  const size_t n = (size_t)h->Bmax * h->T;
+  ADVB_ENSURE(h->x_in, n);
+  ADVB_ENSURE(h->adv2, n);
+  ADVB_ENSURE(h->y_in, h->Bmax);
+  if (h->cap_stream == nullptr) ADVB_CUDA_OK(cudaStreamCreateWithFlags(&h->cap_stream, cudaStreamNonBlocking));
+  return 0;
+}
+
+void drop_graph(advb_handle* h) {
+  auto& g = h->gc;
+  if (g.done != nullptr) {
+    cudaEventSynchronize(g.done);  // replays of the cached exec may still be in flight
+    cudaEventDestroy(g.done);
+  }
+  if (g.exec != nullptr) cudaGraphExecDestroy(g.exec);
+  if (g.graph != nullptr) cudaGraphDestroy(g.graph);
+  g = advb_handle::GraphCache{};
+}
+
+// Enqueue `body` `reps` times on `st`.  With graphs on, `body` is captured ONCE on the engine's capture stream (PyTorch's
+// current stream is usually the legacy default stream, which cannot be captured) and the instantiated graph is replayed;
+// the exec is cached under `key`, which must name everything the captured launches depend on besides the engine-owned
+// buffers they read and write.  Per-kernel profiling needs one event per launch, so it takes the direct path.
+template <typename Body>
+int replay(advb_handle* h, cudaStream_t st, int reps, const std::string& key, Body&& body) {
+  if (reps <= 0) return 0;
+  if (!h->use_graph || h->prof.on || reps < 2) {
+    for (int i = 0; i < reps; ++i) ADVB_TRY(body(st));
+    return 0;
+  }
+  auto& g = h->gc;
+  if (g.exec == nullptr || g.key != key) {
+    drop_graph(h);
+    const int64_t n0 = h->counter.n;
+    ADVB_CUDA_OK(cudaStreamBeginCapture(h->cap_stream, cudaStreamCaptureModeThreadLocal));
+    const int rc = body(h->cap_stream);
+    cudaGraph_t graph = nullptr;
+    const cudaError_t e = cudaStreamEndCapture(h->cap_stream, &graph);
+    g.launches = h->counter.n - n0;
+    h->counter.n = n0;  // nothing ran yet
+    if (rc != 0) {
+      if (graph != nullptr) cudaGraphDestroy(graph);
+      return rc;
+    }
+    ADVB_CUDA_OK(e);
+    g.graph = graph;
+    ADVB_CUDA_OK(cudaGraphInstantiate(&g.exec, graph, 0));
+    ADVB_CUDA_OK(cudaEventCreateWithFlags(&g.done, cudaEventDisableTiming));
+    g.key = key;
+  }
+  for (int i = 0; i < reps; ++i) ADVB_CUDA_OK(cudaGraphLaunch(g.exec, st));
+  ADVB_CUDA_OK(cudaEventRecord(g.done, st));
+  h->counter.n += g.launches * reps;
   return 0;
 }
 
@@ -697,7 +794,8 @@ int advb_create(advb_handle** out, const advb_model_desc* d) {
     return 1;
   };
   if (bind_tensors(h, d->n_tensors, d->tensors)) return fail();
-  if (h->model_kind != ADVB_MODEL_LCNN && h->model_kind != ADVB_MODEL_SPECRNET && h->model_kind != ADVB_MODEL_RAWNET3) {
+  if (h->model_kind != ADVB_MODEL_LCNN && h->model_kind != ADVB_MODEL_SPECRNET && h->model_kind != ADVB_MODEL_RAWNET3 &&
+      h->model_kind != ADVB_MODEL_FRONTEND_ONLY) {
     set_error("unknown model kind");
     return fail();
   }
@@ -728,7 +826,7 @@ int advb_create(advb_handle** out, const advb_model_desc* d) {
       h->alloc(&h->partial_d, B * ROW_CHUNKS))
     return fail();
   if (frontend_init_constants(h->tw, 0)) return fail();
-  if (h->model_kind == ADVB_MODEL_LCNN ? build_lcnn(h) : build_specrnet(h)) return fail();
+  if (h->model_kind == ADVB_MODEL_LCNN ? build_lcnn(h) : h->model_kind == ADVB_MODEL_SPECRNET ? build_specrnet(h) : 0) return fail();
   if (cudaDeviceSynchronize() != cudaSuccess) {
     set_error("device error during advb_create");
     return fail();
@@ -740,6 +838,8 @@ int advb_create(advb_handle** out, const advb_model_desc* d) {
 void advb_destroy(advb_handle* h) {
   if (h == nullptr) return;
   DeviceGuard guard(h->device);
+  drop_graph(h);
+  if (h->cap_stream != nullptr) cudaStreamDestroy(h->cap_stream);
   for (void* p : h->allocs) cudaFree(p);
   if (h->host_cost != nullptr) cudaFreeHost(h->host_cost);
   delete h;
@@ -751,6 +851,7 @@ int64_t advb_launch_count(const advb_handle* h) { return h ? h->counter.n : 0; }
 int advb_set_option(advb_handle* h, const char* key, int value) {
   ADVB_CHECK(h != nullptr && key != nullptr, "null argument");
   const std::string k(key);
+  h->packed_valid = false;  // conv_path / conv_sched choose which packed images are built
   if (k == "conv_path") {
     ADVB_CHECK(value == 0 || value == 1, "conv_path: 0 = tcgen05, 1 = fp32 SIMT");
     h->conv_path = value;
@@ -763,6 +864,15 @@ int advb_set_option(advb_handle* h, const char* key, int value) {
   } else if (k == "conv0_bwd") {
     ADVB_CHECK(value == 0 || value == 1, "conv0_bwd: 0 = fp32 cell kernel, 1 = tcgen05 GEMM + col2im");
     h->conv0_bwd = value;
+  } else if (k == "graph") {
+    ADVB_CHECK(value == 0 || value == 1, "graph: 1 = replay the attack iteration as a CUDA graph, 0 = enqueue every kernel");
+    h->use_graph = value;
+  } else if (k == "fuse_update") {
+    ADVB_CHECK(value == 0 || value == 1, "fuse_update: 1 = FGSM / PGD update in the frontend backward's epilogue, 0 = own kernel");
+    h->fuse_update = value;
+  } else if (k == "weight_cache") {
+    ADVB_CHECK(value == 0 || value == 1, "weight_cache: 1 = skip the weight repack until advb_invalidate_weights()");
+    h->weight_cache = value;
   } else {
     set_error("unknown option '" + k + "'");
     return 1;
@@ -808,84 +918,172 @@ int advb_grad(advb_handle* h, int what, const float* x, const int64_t* y, float*
 }  // extern "C"
 
 namespace {
-// The attack loops (caller holds a CallScope and has validated the arguments).
+
+std::string graph_key(const advb_handle* h, const advb_attack_desc* atk, int B, int n_global, int fused) {
+  auto bits = [](float f) {
+    uint32_t u;
+    memcpy(&u, &f, sizeof(u));
+    return std::to_string(u);
+  };
+  return std::to_string(atk->kind) + "|" + std::to_string(B) + "|" + bits(atk->eps) + "|" + bits(atk->alpha) + "|" +
+         bits(atk->eps_div) + "|" + std::to_string(n_global) + "|" + std::to_string(fused) + "|" +
+         std::to_string(h->conv_path) + "|" + std::to_string(h->tf32_passes) + "|" + std::to_string(h->conv_sched) + "|" +
+         std::to_string(h->conv0_bwd) + "|" + std::to_string(h->bind_epoch);
+}
+
+// The attack loops (caller holds a CallScope and has validated the arguments).  `minmax`: x / x_adv are raw waveforms and
+// to_minmax / revert_minmax (src/aa/utils.py:4-14) replace the copy-in / copy-out of the engine-owned loop buffers.
 int run_attack(advb_handle* h, const advb_attack_desc* atk, const float* x, const int64_t* y, const float* start, float* x_adv,
-               int B, int T, cudaStream_t st) {
+               int B, int T, cudaStream_t st, bool minmax) {
   const int n_global = atk->n_global_batch > 0 ? atk->n_global_batch : B;
   const int64_t n = (int64_t)B * T;
+  const size_t bytes = (size_t)n * sizeof(float);
+  const bool has_frontend = h->model_kind != ADVB_MODEL_RAWNET3;
+  const bool fused = h->fuse_update && has_frontend;
+  // targeted mode (fgsm.py:49-50, pgd.py:64-65, pgdl2.py:69-70): cost = -loss(outputs, target_labels), i.e. the same
+  // gradient negated: the ascent step becomes a descent step on the target labels' loss
+  const float dir = atk->targeted ? -1.0f : 1.0f;
+  if (atk->targeted && atk->kind != ADVB_ATTACK_CW) y = atk->target_labels;
   ADVB_TRY(model_prepare(h, st));
+  if (minmax || atk->kind == ADVB_ATTACK_PGD || atk->kind == ADVB_ATTACK_PGDL2) ADVB_TRY(ensure_loop_buffers(h));
+  if (minmax) {
+    ADVB_ENSURE(h->mm_mn, h->Bmax);
+    ADVB_ENSURE(h->mm_mx, h->Bmax);
+  }
+  // single-evaluation / host-driven attacks under minmax: scale into x_in, attack into adv2, revert into x_adv
+  const float* xc = x;
+  float* out = x_adv;
+  if (minmax && atk->kind != ADVB_ATTACK_PGD && atk->kind != ADVB_ATTACK_PGDL2) {
+    ADVB_TRY(minmax_scale(x, h->x_in, h->mm_mn, h->mm_mx, B, T, st));
+    xc = h->x_in;
+    out = h->adv2;
+  }
   switch (atk->kind) {
     case ADVB_ATTACK_FGSM: {
-      ADVB_TRY(model_forward(h, x, B, st));
-      ADVB_TRY(model_backward(h, x, y, B, ADVB_GRAD_CE, n_global, h->grad, st));
-      ADVB_TRY(fgsm_step(x, h->grad, x_adv, atk->eps, n, st));
-      return 0;
-    }
-    case ADVB_ATTACK_PGD: {
-      ADVB_CHECK(atk->steps >= 0, "bad step count");
-      ADVB_TRY(pgd_start(x, start, x_adv, n, st));
-      for (int it = 0; it < atk->steps; ++it) {
-        ADVB_TRY(model_forward(h, x_adv, B, st));
-        ADVB_TRY(model_backward(h, x_adv, y, B, ADVB_GRAD_CE, n_global, h->grad, st));
-        ADVB_TRY(pgd_step(x, h->grad, x_adv, atk->eps, atk->alpha, n, st));
+      NvtxRange nvtx("advb.fgsm");
+      ADVB_TRY(model_forward(h, xc, B, st));
+      if (fused) {
+        FusedUpdate u;
+        u.kind = 1, u.x_clean = xc, u.adv_out = out, u.eps = dir * atk->eps;
+        ADVB_TRY(model_backward(h, xc, y, B, ADVB_GRAD_CE, n_global, h->grad, st, nullptr, &u));
+      } else {
+        ADVB_TRY(model_backward(h, xc, y, B, ADVB_GRAD_CE, n_global, h->grad, st));
+        ADVB_TRY(fgsm_step(xc, h->grad, out, dir * atk->eps, n, st));
       }
-      return 0;
+      break;
     }
+    case ADVB_ATTACK_PGD:
     case ADVB_ATTACK_PGDL2: {
+      // pgd.py:59-76 / pgdl2.py:64-88.  The loop runs on engine-owned buffers only (clean clips x_in, labels y_in, iterates
+      // grad / adv2), so one captured iteration is valid for every later call with the same parameters.
       ADVB_CHECK(atk->steps >= 0, "bad step count");
-      ADVB_TRY(pgd_start(x, start, x_adv, n, st));
-      for (int it = 0; it < atk->steps; ++it) {
-        ADVB_TRY(model_forward(h, x_adv, B, st));
-        ADVB_TRY(model_backward(h, x_adv, y, B, ADVB_GRAD_CE, n_global, h->grad, st));
-        ADVB_TRY(pgdl2_step(x, h->grad, x_adv, atk->eps, atk->alpha, atk->eps_div, B, T, h->partial_g, h->partial_d,
-                            st));
+      NvtxRange nvtx(atk->kind == ADVB_ATTACK_PGD ? "advb.pgd" : "advb.pgdl2");
+      if (minmax) ADVB_TRY(minmax_scale(x, h->x_in, h->mm_mn, h->mm_mx, B, T, st));
+      else ADVB_CUDA_OK(cudaMemcpyAsync(h->x_in, x, bytes, cudaMemcpyDeviceToDevice, st));
+      ADVB_CUDA_OK(cudaMemcpyAsync(h->y_in, y, (size_t)B * sizeof(int64_t), cudaMemcpyDeviceToDevice, st));
+      const float* xin = h->x_in;
+      const int64_t* yin = h->y_in;
+      const float eps = atk->eps, alpha = dir * atk->alpha, eps_div = atk->eps_div;
+      const bool pgd_fused = fused && atk->kind == ADVB_ATTACK_PGD;
+      const std::string key = graph_key(h, atk, B, n_global, pgd_fused);
+      float* result = nullptr;
+      if (pgd_fused) {
+        // ping-pong iterates pp[0] = grad (no gradient is ever stored), pp[1] = adv2; the update rule runs in the
+        // epilogue of the frontend backward.  The graph holds two iterations pp[0] -> pp[1] -> pp[0].
+        float* pp[2] = {h->grad, h->adv2};
+        auto iter = [&](int from, cudaStream_t s) -> int {
+          FusedUpdate u;
+          u.kind = 2, u.x_clean = xin, u.adv_out = pp[from ^ 1], u.eps = eps, u.alpha = alpha;
+          ADVB_TRY(model_forward(h, pp[from], B, s));
+          ADVB_TRY(model_backward(h, pp[from], yin, B, ADVB_GRAD_CE, n_global, pp[from ^ 1], s, nullptr, &u));
+          return 0;
+        };
+        const int odd = atk->steps & 1;
+        ADVB_TRY(pgd_start(xin, start, pp[odd], n, st));
+        if (odd) ADVB_TRY(iter(1, st));
+        ADVB_TRY(replay(h, st, atk->steps / 2, key, [&](cudaStream_t s) -> int {
+          ADVB_TRY(iter(0, s));
+          ADVB_TRY(iter(1, s));
+          return 0;
+        }));
+        result = pp[0];
+      } else {
+        float* adv = h->adv2;
+        ADVB_TRY(pgd_start(xin, start, adv, n, st));
+        ADVB_TRY(replay(h, st, atk->steps, key, [&](cudaStream_t s) -> int {
+          ADVB_TRY(model_forward(h, adv, B, s));
+          ADVB_TRY(model_backward(h, adv, yin, B, ADVB_GRAD_CE, n_global, h->grad, s));
+          if (atk->kind == ADVB_ATTACK_PGD) ADVB_TRY(pgd_step(xin, h->grad, adv, eps, alpha, n, s));
+          else ADVB_TRY(pgdl2_step(xin, h->grad, adv, eps, alpha, eps_div, B, T, h->partial_g, h->partial_d, s));
+          return 0;
+        }));
+        result = adv;
       }
+      if (minmax) ADVB_TRY(minmax_revert(result, h->mm_mn, h->mm_mx, x_adv, B, T, st));
+      else ADVB_CUDA_OK(cudaMemcpyAsync(x_adv, result, bytes, cudaMemcpyDeviceToDevice, st));
       return 0;
     }
     case ADVB_ATTACK_FAB: {
-      // attack_single_run (fab.py:131-307) on a batch of correctly classified clips: L-inf, untargeted, no random
-      // start.  One backward per step (the class-0 gradient of z = [-o, o] is the exact negation of class 1's).
+      // attack_single_run (fab.py:131-307) on a batch of correctly classified clips: L-inf, untargeted.  `start` = the
+      // random restart point x1 of fab.py:176-206 (nullable: x1 = x).  One backward per step (the class-0 gradient of
+      // z = [-o, o] is the exact negation of class 1's).
       ADVB_CHECK(atk->steps >= 0, "bad step count");
+      ADVB_CHECK(!minmax || start == nullptr, "FAB random restarts are not available through the min-max entry point");
       ADVB_TRY(ensure_fab_scratch(h));
       const long long* yl = reinterpret_cast<const long long*>(y);
-      ADVB_TRY(fab_init(x, x_adv, h->fab, B, T, st));
+      NvtxRange nvtx("advb.fab");
+      ADVB_TRY(fab_init(xc, out, h->fab, B, T, st));
+      if (start != nullptr) ADVB_CUDA_OK(cudaMemcpyAsync(h->fab.x1, start, bytes, cudaMemcpyDeviceToDevice, st));
       for (int it = 0; it < atk->steps; ++it) {
         ADVB_TRY(model_forward(h, h->fab.x1, B, st));
         ADVB_TRY(model_backward(h, h->fab.x1, y, B, ADVB_GRAD_LOGIT, n_global, h->grad, st));
         ADVB_TRY(fab_hyperplane(h->grad, h->logits, yl, h->fab, B, T, st));
-        ADVB_TRY(fab_project(x, h->fab, B, T, st));
-        ADVB_TRY(fab_combine(x, h->fab, atk->eta, atk->alpha_max, B, T, st));
+        ADVB_TRY(fab_project(xc, h->fab, B, T, st));
+        ADVB_TRY(fab_combine(xc, h->fab, atk->eta, atk->alpha_max, B, T, st));
         ADVB_TRY(model_forward(h, h->fab.x1, B, st));
-        ADVB_TRY(fab_bookkeep(x, h->logits, yl, x_adv, h->fab, atk->beta, B, T, st));
+        ADVB_TRY(fab_bookkeep(xc, h->logits, yl, out, h->fab, atk->beta, B, T, st));
       }
-      return 0;
+      break;
     }
     case ADVB_ATTACK_CW: {
       ADVB_CHECK(atk->steps >= 0, "bad step count");
       ADVB_TRY(ensure_cw_scratch(h));
       const long long* yl = reinterpret_cast<const long long*>(y);
-      ADVB_TRY(cw_init(x, x_adv, h->cw, B, T, st));
+      const long long* yt = atk->targeted ? reinterpret_cast<const long long*>(atk->target_labels) : nullptr;
+      NvtxRange nvtx("advb.cw");
+      ADVB_TRY(cw_init(xc, out, h->cw, B, T, st));
       float prev_cost = 1e10f;
       const int every = atk->steps / 10 > 1 ? atk->steps / 10 : 1;
       for (int step = 0; step < atk->steps; ++step) {
-        ADVB_TRY(cw_forward_image(x, h->cw, B, T, st));
+        ADVB_TRY(cw_forward_image(xc, h->cw, B, T, st));
         ADVB_TRY(model_forward(h, h->cw.adv, B, st));
-        ADVB_TRY(cw_head(h->logits, yl, h->cw, atk->c, atk->kappa, B, st));
+        ADVB_TRY(cw_head(h->logits, yl, yt, h->cw, atk->c, atk->kappa, B, st));
         ADVB_TRY(model_backward(h, h->cw.adv, y, B, ADVB_GRAD_SEEDED, n_global, h->grad, st, h->cw.coef));
-        ADVB_TRY(cw_adam(x, h->grad, x_adv, h->cw, atk->lr, step + 1, B, T, st));
+        ADVB_TRY(cw_adam(xc, h->grad, out, h->cw, atk->lr, step + 1, B, T, st));
         if (step % every == 0) {  // batch-wide early stop: the one host sync the reference has too (cw.py:107-110)
           ADVB_CUDA_OK(cudaMemcpyAsync(h->host_cost, h->cw.cost, sizeof(float), cudaMemcpyDeviceToHost, st));
           ADVB_CUDA_OK(cudaStreamSynchronize(st));
-          if (*h->host_cost > prev_cost) return 0;
+          if (*h->host_cost > prev_cost) break;
           prev_cost = *h->host_cost;
         }
       }
-      return 0;
+      break;
     }
     default:
       set_error("attack kind not implemented in the native loop");
       return 1;
   }
+  if (minmax) ADVB_TRY(minmax_revert(out, h->mm_mn, h->mm_mx, x_adv, B, T, st));
+  return 0;
+}
+
+int check_attack_args(advb_handle* h, const advb_attack_desc* atk, const float* x, const int64_t* y, const float* x_adv, int B,
+                      int T) {
+  ADVB_TRY(check_call(h, B, T));
+  ADVB_CHECK(atk != nullptr && x != nullptr && y != nullptr && x_adv != nullptr, "null argument");
+  ADVB_CHECK(!atk->targeted || atk->target_labels != nullptr, "targeted mode needs target_labels");
+  ADVB_CHECK(!atk->targeted || atk->kind != ADVB_ATTACK_FAB, "FAB has no targeted mode in the reference's patched copy (fab.py:63)");
+  return 0;
 }
 }  // namespace
 
@@ -893,29 +1091,22 @@ extern "C" {
 
 int advb_attack(advb_handle* h, const advb_attack_desc* atk, const float* x, const int64_t* y, const float* start,
                 float* x_adv, int B, int T, void* cuda_stream) {
-  ADVB_TRY(check_call(h, B, T));
-  ADVB_CHECK(atk != nullptr && x != nullptr && y != nullptr && x_adv != nullptr, "null argument");
+  ADVB_TRY(check_attack_args(h, atk, x, y, x_adv, B, T));
   ADVB_CHECK(x != x_adv, "x_adv must not alias x");
   CallScope scope(h);
-  return run_attack(h, atk, x, y, start, x_adv, B, T, static_cast<cudaStream_t>(cuda_stream));
+  return run_attack(h, atk, x, y, start, x_adv, B, T, static_cast<cudaStream_t>(cuda_stream), false);
 }
 
 int advb_attack_minmax(advb_handle* h, const advb_attack_desc* atk, const float* x_raw, const int64_t* y, const float* start,
                        float* x_adv_raw, int B, int T, void* cuda_stream) {
-  ADVB_TRY(check_call(h, B, T));
-  ADVB_CHECK(atk != nullptr && x_raw != nullptr && y != nullptr && x_adv_raw != nullptr, "null argument");
+  ADVB_TRY(check_attack_args(h, atk, x_raw, y, x_adv_raw, B, T));
   CallScope scope(h);
-  cudaStream_t st = static_cast<cudaStream_t>(cuda_stream);
-  if (h->mm_x01 == nullptr) {
-    const size_t n = (size_t)h->Bmax * h->T;
-    ADVB_TRY(h->alloc(&h->mm_x01, n));
-    ADVB_TRY(h->alloc(&h->mm_adv, n));
-    ADVB_TRY(h->alloc(&h->mm_mn, h->Bmax));
-    ADVB_TRY(h->alloc(&h->mm_mx, h->Bmax));
-  }
-  ADVB_TRY(minmax_scale(x_raw, h->mm_x01, h->mm_mn, h->mm_mx, B, T, st));
-  ADVB_TRY(run_attack(h, atk, h->mm_x01, y, start, h->mm_adv, B, T, st));
-  ADVB_TRY(minmax_revert(h->mm_adv, h->mm_mn, h->mm_mx, x_adv_raw, B, T, st));
+  return run_attack(h, atk, x_raw, y, start, x_adv_raw, B, T, static_cast<cudaStream_t>(cuda_stream), true);
+}
+
+int advb_invalidate_weights(advb_handle* h) {
+  ADVB_CHECK(h != nullptr, "null handle");
+  h->packed_valid = false;
   return 0;
 }
 
@@ -942,7 +1133,7 @@ int advb_row_diff_norms(const float* a, const float* b, float* linf, float* l2, 
 }
 
 int advb_frontend_fwd(advb_handle* h, const float* x, float* coeff, int B, int T, void* cuda_stream) {
-  ADVB_TRY(check_call(h, B, T));
+  ADVB_TRY(check_call(h, B, T, false));
   ADVB_CHECK(h->frontend_kind != ADVB_FRONTEND_NONE, "this model takes the raw waveform: it has no spectral frontend");
   CallScope scope(h);
   cudaStream_t st = static_cast<cudaStream_t>(cuda_stream);
@@ -954,7 +1145,7 @@ int advb_frontend_fwd(advb_handle* h, const float* x, float* coeff, int B, int T
 
 int advb_frontend_bwd(advb_handle* h, const float* x, const float* g_coeff, float* g_x, int B, int T,
                       void* cuda_stream) {
-  ADVB_TRY(check_call(h, B, T));
+  ADVB_TRY(check_call(h, B, T, false));
   ADVB_CHECK(h->frontend_kind != ADVB_FRONTEND_NONE, "this model takes the raw waveform: it has no spectral frontend");
   CallScope scope(h);
   cudaStream_t st = static_cast<cudaStream_t>(cuda_stream);

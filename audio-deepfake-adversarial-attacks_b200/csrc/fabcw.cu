@@ -279,6 +279,7 @@ __global__ void __launch_bounds__(256) cw_image_kernel(const float* __restrict__
 }
 
 __global__ void __launch_bounds__(256) cw_head_kernel(const float* __restrict__ logits, const long long* __restrict__ y,
+                                                       const long long* __restrict__ y_target,
                                                        const float* __restrict__ partial, float* __restrict__ cur_l2,
                                                        float* __restrict__ best_l2, float* __restrict__ coef,
                                                        float* __restrict__ mask, float* __restrict__ cost, float c,
@@ -291,18 +292,22 @@ __global__ void __launch_bounds__(256) cw_head_kernel(const float* __restrict__ 
     cur_l2[b] = l2;
     const float o = logits[b];
     // z = [-o, o]; j = z[y]; i = max((1 - onehot) * z) = max(z[other], 0)      (cw.py:125-134)
-    const bool y1 = y[b] == 1;
+    // targeted (cw.py:82-83,131-132): the one-hot is built from the target labels and f = clamp(i - j, min=-kappa);
+    // the best-adversarial bookkeeping below always compares with the given labels (cw.py:95)
+    const bool tgt = y_target != nullptr;
+    const bool y1 = (tgt ? y_target[b] : y[b]) == 1;
     const float zj = y1 ? o : -o, zo = y1 ? -o : o;
     const float fi = fmaxf(zo, 0.f);
-    const float diff = zj - fi;
+    const float diff = tgt ? fi - zj : zj - fi;
     float f = diff, df = y1 ? 1.f : -1.f;                 // d zj / d o
     if (zo > 0.f) df += y1 ? 1.f : -1.f;                  // - d zo / d o when the other logit is the max
+    if (tgt) df = -df;
     if (diff < -kappa) {                                  // clamp(min=-kappa): value -kappa, zero gradient
       f = -kappa;
       df = 0.f;
     }
     coef[b] = c * df;
-    const bool correct = ((o > 0.f) ? 1 : 0) == (y1 ? 1 : 0);
+    const bool correct = ((o > 0.f) ? 1 : 0) == ((y[b] == 1) ? 1 : 0);
     const bool take = !correct && best_l2[b] > l2;        // cw.py:94-101
     mask[b] = take ? 1.f : 0.f;
     if (take) best_l2[b] = l2;
@@ -408,8 +413,9 @@ int cw_forward_image(const float* x, const CwScratch& s, int B, int T, cudaStrea
   ADVB_KERNEL_OK("cw_image", stream);
   return 0;
 }
-int cw_head(const float* logits, const long long* y, const CwScratch& s, float c, float kappa, int B, cudaStream_t stream) {
-  cw_head_kernel<<<1, 256, 0, stream>>>(logits, y, s.l2_partial, s.cur_l2, s.best_l2, s.coef, s.mask, s.cost, c, kappa, B);
+int cw_head(const float* logits, const long long* y, const long long* y_target, const CwScratch& s, float c, float kappa, int B,
+            cudaStream_t stream) {
+  cw_head_kernel<<<1, 256, 0, stream>>>(logits, y, y_target, s.l2_partial, s.cur_l2, s.best_l2, s.coef, s.mask, s.cost, c, kappa, B);
   ADVB_KERNEL_OK("cw_head", stream);
   return 0;
 }

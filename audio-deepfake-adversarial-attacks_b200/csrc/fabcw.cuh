@@ -43,7 +43,9 @@ int cw_init(const float* x, float* best_adv, const CwScratch& s, int B, int T, c
 // adv = 1/2 (tanh w + 1); cur_l2 = row sums of (adv - x)^2                          (cw.py:73-78,114-115)
 int cw_forward_image(const float* x, const CwScratch& s, int B, int T, cudaStream_t stream);
 // f, f', cost, best-L2 bookkeeping mask from the logits of adv                       (cw.py:80-101,125-134)
-int cw_head(const float* logits, const long long* y, const CwScratch& s, float c, float kappa, int B, cudaStream_t stream);
+// y_target: nullable target labels of the targeted mode (cw.py:82-83,131-132)
+int cw_head(const float* logits, const long long* y, const long long* y_target, const CwScratch& s, float c, float kappa, int B,
+            cudaStream_t stream);
 // g_w = (2 (adv - x) + g_model) * 1/2 (1 - tanh^2 w); Adam step on w; best_adv <- adv where mask   (cw.py:88-101)
 int cw_adam(const float* x, const float* g_model, float* best_adv, const CwScratch& s, float lr, int step, int B, int T,
             cudaStream_t stream);

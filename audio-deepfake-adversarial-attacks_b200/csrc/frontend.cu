@@ -517,7 +517,7 @@ __host__ __device__ __forceinline__ void tile_frames(int s0, int s1, int T, int 
 __global__ void __launch_bounds__(FB_THREADS, 1) fe_bwd_kernel(const float* __restrict__ x, int T, int F,
                                                                 FrontendTables tb, FrontendState st, float top_db,
                                                                 const float* __restrict__ gd, float* __restrict__ gx,
-                                                                int n_tiles, int n_clips) {
+                                                                int n_tiles, int n_clips, FusedUpdate upd) {
   extern __shared__ __align__(16) float smem[];
   float2* s_tw = reinterpret_cast<float2*>(smem);                  // 512 float2
   float* s_win = smem + 1024;                                      // 400
@@ -661,7 +661,21 @@ __global__ void __launch_bounds__(FB_THREADS, 1) fe_bwd_kernel(const float* __re
           acc += (fi & 1) ? -__fmul_rn(w, wv.y) : __fmul_rn(w, wv.x);
         }
       }
-      gx[(size_t)b * T + s] = acc;
+      const size_t o = (size_t)b * T + s;
+      if (upd.kind == 0) {
+        gx[o] = acc;
+      } else {
+        // same op-by-op fp32 rounding as update.cu (fgsm_step_kernel / pgd_step_kernel): bit-identical iterates
+        const float sg = acc > 0.f ? 1.f : (acc < 0.f ? -1.f : 0.f);
+        const float xi = __ldg(upd.x_clean + o);
+        if (upd.kind == 1) {
+          upd.adv_out[o] = fminf(fmaxf(__fadd_rn(xi, __fmul_rn(upd.eps, sg)), 0.f), 1.f);
+        } else {
+          const float a1 = __fadd_rn(__ldg(xb + s), __fmul_rn(upd.alpha, sg));
+          const float d = fminf(fmaxf(__fsub_rn(a1, xi), -upd.eps), upd.eps);
+          upd.adv_out[o] = fminf(fmaxf(__fadd_rn(xi, d), 0.f), 1.f);
+        }
+      }
     }
     __syncthreads();  // the FFT buffers are reused by the next tile
   }
@@ -716,7 +730,8 @@ int frontend_forward(const FrontendTables& tb, const FrontendState& st, const fl
 
 int frontend_backward(const FrontendTables& tb, const FrontendState& st, const float* x, int B, int T,
                       const float* dB, const float* gcoef, long long g_clip_stride, long long g_stride_f,
-                      long long g_stride_c, float* mass_partial, float* gd, float* gx, cudaStream_t stream) {
+                      long long g_stride_c, float* mass_partial, float* gd, float* gx, cudaStream_t stream,
+                      const FusedUpdate* upd) {
   const int F = frontend_frames(T);
   dim3 g1(cdiv(F, 2 * FE_WARPS), B);
   fe_floor_mass_kernel<<<g1, FE_THREADS, 0, stream>>>(dB, F, tb, st, 80.0f, gcoef, g_clip_stride, g_stride_f,
@@ -735,7 +750,13 @@ int frontend_backward(const FrontendTables& tb, const FrontendState& st, const f
     ADVB_CHECK(t_hi - t_lo + 1 <= NF_MAX, "frontend backward: a tile needs more frames than the kernel has warps for");
   }
   const int grid = n_tiles * B < 148 ? n_tiles * B : 148;  // one persistent CTA per SM (210 KB of shared memory each)
-  fe_bwd_kernel<<<grid, FB_THREADS, fe_bwd_smem(), stream>>>(x, T, F, tb, st, 80.0f, gd, gx, n_tiles, B);
+  FusedUpdate u{};
+  if (upd != nullptr) {
+    u = *upd;
+    ADVB_CHECK(u.kind == 0 || (u.x_clean != nullptr && u.adv_out != nullptr && u.adv_out != x),
+               "fused update needs the clean clips and an output buffer that does not alias the waveform");
+  }
+  fe_bwd_kernel<<<grid, FB_THREADS, fe_bwd_smem(), stream>>>(x, T, F, tb, st, 80.0f, gd, gx, n_tiles, B, u);
   ADVB_KERNEL_OK("fe_bwd", stream);
   return 0;
 }

@@ -22,6 +22,16 @@ struct FrontendState {
   float* mass_total;                // backward: summed gradient of clamped elements
 };
 
+// Optional epilogue of the backward: the attack's element-wise update rule (fgsm.py:59-60, pgd.py:74-76) applied to each
+// gradient sample while it is still in a register, so that the waveform gradient never reaches HBM.  `adv_out` must not
+// alias the waveform the backward reads (other tiles re-read its halo): the PGD loop ping-pongs two buffers.
+struct FusedUpdate {
+  int kind = 0;                 // 0 = none (store the gradient), 1 = FGSM sign step, 2 = PGD L-inf step
+  const float* x_clean = nullptr;  // (B,T) clean clips
+  float* adv_out = nullptr;        // (B,T) next iterate
+  float eps = 0.f, alpha = 0.f;
+};
+
 int frontend_frames(int T);
 int frontend_mass_blocks(int B, int T);
 int frontend_init_constants(float2* tw, cudaStream_t stream);
@@ -35,6 +45,7 @@ int frontend_forward(const FrontendTables& tb, const FrontendState& st, const fl
 // gradient of the dB tensor; gx (B,T)
 int frontend_backward(const FrontendTables& tb, const FrontendState& st, const float* x, int B, int T,
                       const float* dB, const float* gcoef, long long g_clip_stride, long long g_stride_f,
-                      long long g_stride_c, float* mass_partial, float* gd, float* gx, cudaStream_t stream);
+                      long long g_stride_c, float* mass_partial, float* gd, float* gx, cudaStream_t stream,
+                      const FusedUpdate* upd = nullptr);
 
 }  // namespace advb

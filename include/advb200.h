@@ -18,7 +18,7 @@
 extern "C" {
 #endif
 
-#define ADVB_VERSION 100
+#define ADVB_VERSION 200
 #if defined(__GNUC__)
 #define ADVB_API __attribute__((visibility("default")))
 #else
@@ -26,7 +26,9 @@ extern "C" {
 #endif
 
 /* model kinds: src/models/models.py:6-18 (get_model names) */
-enum { ADVB_MODEL_LCNN = 1, ADVB_MODEL_SPECRNET = 2, ADVB_MODEL_RAWNET3 = 3 };
+enum { ADVB_MODEL_LCNN = 1, ADVB_MODEL_SPECRNET = 2, ADVB_MODEL_RAWNET3 = 3,
+       ADVB_MODEL_FRONTEND_ONLY = 4 /* LFCC_FN(x) / MFCC_FN(x) on their own (src/frontends.py:13-50): only
+                                       advb_frontend_fwd / advb_frontend_bwd are valid on such a handle */ };
 /* frontend kinds: src/frontends.py:13-50 (0 = raw waveform, RawNet3) */
 enum { ADVB_FRONTEND_NONE = 0, ADVB_FRONTEND_LFCC = 1, ADVB_FRONTEND_MFCC = 2 };
 /* attack kinds: adversarial_attacks/torchattacks/attacks/{fgsm,pgd,pgdl2,fab,cw}.py */
@@ -72,6 +74,10 @@ typedef struct {
   float kappa;        /* CW */
   float lr;           /* CW */
   int n_global_batch; /* N of the CE mean when the batch is sharded over ranks (0 = use B) */
+  int targeted;       /* attack.py:60-108 targeted modes: cost = -loss(outputs, target_labels) (fgsm.py:49-50, pgd.py:64-65,
+                         pgdl2.py:69-70); CW: f = clamp(i - j, -kappa) on the target one-hot (cw.py:82-83,131-132) */
+  const int64_t* target_labels; /* [B] int64 device pointer, required when targeted != 0 (the host evaluates the
+                         target_map_function, attack.py:258-270) */
 } advb_attack_desc;
 
 ADVB_API int advb_version(void);
@@ -83,12 +89,21 @@ ADVB_API size_t advb_workspace_bytes(const advb_handle* h);
 /* Re-point the borrowed tensors (same names/sizes) without reallocating the workspace. */
 ADVB_API int advb_rebind(advb_handle* h, int n_tensors, const advb_tensor_ref* tensors);
 
+/* The engine repacks the borrowed weights at the head of every call because they are live.  A host that tracks weight
+ * versions itself sets option "weight_cache" = 1 and calls this after every change; unchanged weights then skip the repack. */
+ADVB_API int advb_invalidate_weights(advb_handle* h);
+
 /* Engine options (no reference counterpart; the reference's knobs are torch-global):
  *   "conv_path"   0 = tcgen05 tensor-core convolutions / GEMMs (default), 1 = fp32 SIMT convolutions / GEMMs (cross-check)
  *   "tf32_passes" 3 = 3xTF32 error-compensated products, fp32-class accuracy (default), 1 = single-pass tf32
  *   "conv_sched"  0 = persistent warp-specialised convolution / GEMM kernels (default), 1 = one-tile-per-CTA kernels only
  *                 (the first tcgen05 version; same arithmetic, kept as an in-process cross-check)
- *   "conv0_bwd"   LCNN first block backward: 0 = fp32 cell kernel (default), 1 = tcgen05 GEMM + col2im (cross-check) */
+ *   "conv0_bwd"   LCNN first block backward: 0 = fp32 cell kernel (default), 1 = tcgen05 GEMM + col2im (cross-check)
+ *   "graph"       1 = one PGD / PGDL2 iteration is captured into a CUDA graph and replayed `steps` times (default), 0 = every
+ *                 kernel enqueued by the host loop (same kernels, same results)
+ *   "fuse_update" 1 = the FGSM / PGD L-inf update rule runs in the epilogue of the frontend backward and the waveform gradient
+ *                 never reaches HBM (default; LFCC / MFCC models), 0 = separate update kernel (bit-identical iterates)
+ *   "weight_cache" see advb_invalidate_weights */
 ADVB_API int advb_set_option(advb_handle* h, const char* key, int value);
 
 /* Replaces  atk(images, labels)  = Attack.__call__ -> {FGSM,PGD,PGDL2,FAB,CW}.forward
@@ -96,7 +111,8 @@ ADVB_API int advb_set_option(advb_handle* h, const char* key, int value);
  * evaluate_models_on_adversarial_attacks.py:220 and src/trainer.py:426,470,492,511,539.
  *   x        [B,T] fp32 in [0,1], device;  y [B] int64 labels (1 = bonafide), device
  *   start    nullable [B,T]: the random start drawn by the host with torch:
- *            PGD: the U(-eps,eps) noise added at pgd.py:56;  PGDL2: the already scaled delta of pgdl2.py:57-61
+ *            PGD: the U(-eps,eps) noise added at pgd.py:56;  PGDL2: the already scaled delta of pgdl2.py:57-61;
+ *            FAB: the restart point x1 of fab.py:176-206 (random restarts, n_restarts > 1)
  *   FAB      runs attack_single_run (fab.py:131-307; L-inf, untargeted, n_restarts = 1) on the given clips, which
  *            the caller has already restricted to the correctly classified ones as FAB.perturb does (fab.py:506-513)
  *   CW       cw.py:46-112, including the batch-wide early stop (one host sync every steps/10 iterations)

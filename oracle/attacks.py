@@ -205,7 +205,9 @@ def fab(model_fn, x, y, eps=0.3, steps=100, alpha_max=0.1, eta=1.05, beta=0.9):
 # ------------------------------------------------------------------------------------------------------------
 # CW — cw.py:46-134.  SURVEY.md App. A.7.
 # ------------------------------------------------------------------------------------------------------------
-def cw(model_fn, x, y, c=1e-4, kappa=0.0, steps=1000, lr=0.01):
+def cw(model_fn, x, y, c=1e-4, kappa=0.0, steps=1000, lr=0.01, target=None):
+    """``target``: target labels of the targeted mode (cw.py:56-57,82-83,131-132); the best-adversarial bookkeeping keeps
+    comparing with ``y`` (cw.py:95)."""
     x = x.clone().detach()
     u = x * 2 - 1
     w = (0.5 * torch.log((1 + u) / (1 - u))).detach()  # cw.py:117-123 (+-inf where x is exactly 0 or 1)
@@ -214,7 +216,7 @@ def cw(model_fn, x, y, c=1e-4, kappa=0.0, steps=1000, lr=0.01):
     best_l2 = 1e10 * torch.ones(len(x))
     prev_cost = 1e10
     opt = torch.optim.Adam([w], lr=lr)
-    onehot = torch.eye(2)[y]
+    onehot = torch.eye(2)[y if target is None else target]
     for step in range(steps):
         adv = 0.5 * (torch.tanh(w) + 1)
         cur_l2 = ((adv.flatten(1) - x.flatten(1)) ** 2).sum(dim=1)
@@ -222,7 +224,7 @@ def cw(model_fn, x, y, c=1e-4, kappa=0.0, steps=1000, lr=0.01):
         z = torch.cat([-o, o], dim=1)
         i, _ = torch.max((1 - onehot) * z, dim=1)
         j = torch.masked_select(z, onehot.bool())
-        f_loss = torch.clamp(j - i, min=-kappa).sum()
+        f_loss = torch.clamp((j - i) if target is None else (i - j), min=-kappa).sum()
         cost = cur_l2.sum() + c * f_loss
         opt.zero_grad()
         cost.backward()

@@ -30,7 +30,7 @@ CASES = {
     # correctly classified and must be pushed across a real margin; the clip labelled 0 is already misclassified and
     # exercises FAB's "attack only the correctly classified clips" path (fab.py:506-513)
     "lcnn_lfcc_t16000_margin": dict(model="lcnn", frontend="lfcc", T=16000, B=4, cfg_id=14, silence=False,
-                                    margin=0.01, labels=(1, 1, 0, 1), attacks=("fab", "cw")),
+                                    margin=0.01, labels=(1, 1, 0, 1), attacks=("fab", "cw", "cw_strong")),
 }
 DEFAULT_ATTACKS = ("fgsm", "pgd", "pgdl2")
 
@@ -40,6 +40,9 @@ ATTACKS = {
     "pgdl2": dict(eps=0.1, alpha=0.2, steps=3),
     "fab": dict(eps=0.3, steps=8, eta=10.0, alpha_max=0.1, beta=0.9),   # AttackEnum.FAB preset, fewer steps
     "cw": dict(c=1e-4, kappa=0.0, steps=20, lr=0.01),
+    # CW with the classification term dominating the fp32 rounding noise of tanh(atanh(.)): elements are comparable, clips flip
+    # at steps 4-5 (best-adversarial mask path) and the batch-wide early stop fires at step 8 (cw.py:107-110)
+    "cw_strong": dict(c=1e4, kappa=0.0, steps=20, lr=5e-4),
 }
 
 

@@ -77,7 +77,7 @@ def main():
             if an == "fab":
                 atk = torchattacks.FAB(ref, norm="Linf", eps=ap["eps"], steps=ap["steps"], eta=ap["eta"],
                                        alpha_max=ap["alpha_max"], beta=ap["beta"], n_classes=2)
-            elif an == "cw":
+            elif an.startswith("cw"):
                 atk = torchattacks.CW(ref, c=ap["c"], kappa=ap["kappa"], steps=ap["steps"], lr=ap["lr"])
             elif an == "fgsm":
                 atk = torchattacks.FGSM(ref, eps=ap["eps"])

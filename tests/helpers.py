@@ -45,7 +45,7 @@ def oracle_attack(name, attack, x, y, state, fwd, case):
         return oatk.fgsm(model_fn, x, y, p["eps"])
     if attack == "fab":
         return oatk.fab(model_fn, x, y, p["eps"], p["steps"], p["alpha_max"], p["eta"], p["beta"])
-    if attack == "cw":
+    if attack.startswith("cw"):
         return oatk.cw(model_fn, x, y, p["c"], p["kappa"], p["steps"], p["lr"])
     if attack == "pgd":
         return oatk.pgd(model_fn, x, y, p["eps"], p["alpha"], p["steps"], noise=reference_start(case, "pgd", x, p["eps"]))
@@ -87,3 +87,16 @@ def grads_agree(g, ref, tight=2e-5):
     overall."""
     return (trimmed_rel_err(g, ref) < tight and cosine(g, ref) > 0.9995
             and (torch.sign(g) == torch.sign(ref)).float().mean().item() > 0.998)
+
+
+def oracle_targeted(kind, model_fn, x, y, target, case):
+    """Targeted variants of the oracle attacks: cost = -loss(outputs, target) is the same gradient negated, i.e. the ascent
+    step size changes sign (fgsm.py:49-50, pgd.py:64-65, pgdl2.py:69-70); CW builds f on the target one-hot (cw.py:131-132)."""
+    if kind == "fgsm":
+        return oatk.fgsm(model_fn, x, target, -0.005)
+    if kind == "pgd":
+        return oatk.pgd(model_fn, x, target, 0.001, -2 / 255, 3, noise=reference_start(case, "pgd", x, 0.001))
+    if kind == "pgdl2":
+        start = torch.clamp(x + reference_start(case, "pgdl2", x, 0.1), 0, 1)
+        return oatk.pgdl2(model_fn, x, target, 0.1, -0.2, 3, start=start)
+    return oatk.cw(model_fn, x, y, 1e4, 0.0, 5, 5e-4, target=target)

@@ -21,14 +21,15 @@ def test_library_exports_every_declared_symbol():
     assert declared == set(_lib.SIGNATURES), declared ^ set(_lib.SIGNATURES)
     for name in declared:
         assert isinstance(getattr(lib, name), ctypes._CFuncPtr)
-    assert lib.advb_version() == 100
+    assert lib.advb_version() == 200
 
 
 def test_struct_layout_matches_header():
     from advb200 import _lib
 
     assert ctypes.sizeof(_lib.TensorRef) == 24
-    assert ctypes.sizeof(_lib.AttackDesc) == 12 * 4
+    assert ctypes.sizeof(_lib.AttackDesc) == 12 * 4 + 4 + 4 + 8  # + targeted, padding, target_labels pointer
+    assert _lib.AttackDesc.target_labels.offset == 56 and _lib.AttackDesc.targeted.offset == 48
     assert ctypes.sizeof(_lib.ModelDesc) == 6 * 4 + 8
 
 
@@ -122,6 +123,34 @@ def test_attack_api_surface_and_no_cpu_fallback():
         holder(x)
     with pytest.raises(NotImplementedError):
         atk.set_training_mode(True, True)
+    # targeted modes (attack.py:60-108): by-function works; the least-likely / random pickers fail on a 1-logit model, as in
+    # the reference (attack.py:280: list(range(1)).remove(label))
+    atk.set_mode_targeted_by_function(lambda images, labels: 1 - labels)
+    assert atk.get_mode() == "targeted" and torch.equal(atk._get_target_label(x, y), 1 - y)
+    atk.set_mode_targeted_least_likely()
+    with pytest.raises(ValueError):
+        atk._get_target_label(x, y)
+    atk.set_mode_default()
+    with pytest.raises(ValueError, match="not supported"):
+        ta.FAB(holder, n_classes=2).set_mode_targeted_by_function()
+
+
+def test_reference_staging_manifest():
+    """oracle/_ref (when staged) holds byte-identical copies of the reference files: sha256 per file in MANIFEST.json."""
+    import hashlib
+    import json
+
+    from oracle import ref
+
+    if not os.path.isdir(ref.STAGED):
+        pytest.skip("oracle/_ref not staged (run python -m oracle.make_ref in the build container)")
+    man = json.load(open(os.path.join(ref.STAGED, "MANIFEST.json")))["files"]
+    assert "adversarial_attacks/torchattacks/attacks/pgd.py" in man and "src/models/lcnn.py" in man
+    for rel, sha in man.items():
+        path = os.path.join(ref.STAGED, rel)
+        assert hashlib.sha256(open(path, "rb").read()).hexdigest() == sha, rel
+        if os.path.exists(os.path.join("/root/reference", rel)):
+            assert open(path, "rb").read() == open(os.path.join("/root/reference", rel), "rb").read(), rel
 
 
 def test_install_swaps_reference_namespace():

@@ -56,7 +56,7 @@ def test_oracle_attacks_match_reference(name, attack):
 
 
 @pytest.mark.parametrize("name,attack", [("lcnn_lfcc_t16000_margin", "fab"), ("lcnn_lfcc_t16000_margin", "cw"),
-                                         ("rawnet3_t16000_margin", "fab")])
+                                         ("lcnn_lfcc_t16000_margin", "cw_strong"), ("rawnet3_t16000_margin", "fab")])
 def test_oracle_fab_cw_match_reference(name, attack):
     case, x, y, holder, state, fwd = helpers.case_setup(name)
     g = helpers.load_golden(name)
@@ -93,3 +93,72 @@ def test_oracle_projection_linf_solves_the_box_hyperplane_problem():
     d = oatk.projection_linf(t, w, b)
     assert ((t + d) >= -1e-6).all() and ((t + d) <= 1 + 1e-6).all()
     np.testing.assert_allclose((w * (t + d)).sum(1).numpy(), b.numpy(), rtol=1e-4, atol=1e-4)
+
+
+def test_oracle_matches_reference_at_config1():
+    """BASELINE.json configs[0] (FGSM eps=0.005, LCNN+LFCC, batch 8, 64 000 samples): the oracle port against the fixture the
+    unmodified reference produced (oracle/make_golden_cfg.py)."""
+    from oracle import lcnn as olcnn
+    from oracle.make_golden_cfg import BIAS_KEY, CFG_CASES, T
+
+    name = "cfg1_lcnn_fgsm_b8"
+    case, g = CFG_CASES[name], helpers.load_golden(name)
+    x, y = synth.clips(case["cfg_id"], case["B"], T)
+    _, state = cases.build_state(case["model"], case["frontend"])
+    state[BIAS_KEY[case["model"]]] = torch.from_numpy(g["bias"])
+    assert synth.state_digest(state) == str(g["digest"])
+    assert np.array_equal(y.numpy(), g["y"])
+    fn = lambda v: olcnn.forward(v, state)  # noqa: E731
+    with torch.no_grad():
+        np.testing.assert_allclose(fn(x).numpy(), g["logits_clean"], atol=3e-6)
+    xa = oatk.fgsm(fn, x, y, case["params"]["eps"])
+    np.testing.assert_allclose((xa - x).abs().amax(dim=1).numpy(), g["delta_linf"], atol=1e-5)
+    np.testing.assert_allclose((xa - x).norm(p=2, dim=1).numpy(), g["delta_l2"], rtol=1e-5)
+    sign = np.unpackbits(g["sign_bits"])[: x.numel()].reshape(x.shape).astype(bool)
+    assert ((xa > x).numpy() != sign).mean() < 2e-3
+    with torch.no_grad():
+        la = fn(xa)
+    np.testing.assert_allclose(la.numpy(), g["logits_adv"], atol=1e-4)
+    assert np.array_equal((torch.sigmoid(la.squeeze(1)) + .5).int().numpy(), g["pred_adv"])
+
+
+def test_oracle_targeted_modes_match_reference():
+    """attack.py:60-108 + fgsm.py:49-50 / pgd.py:64-65 / pgdl2.py:69-70 / cw.py:82-83,131-132: the oracle's targeted variants
+    (negated ascent on the target labels' loss) against the reference's own classes, run live on CPU."""
+    from oracle import ref
+
+    if not ref.available():
+        pytest.skip("reference not staged (oracle/_ref)")
+    ta = ref.torchattacks()
+    name = "lcnn_lfcc_t16000_margin"
+    case, x, y, holder, state, fwd = helpers.case_setup(name)
+    model = ref.model("lcnn", "lfcc", state)
+    fn = lambda v: fwd(v, state)  # noqa: E731
+    tmap = lambda images, labels: 1 - labels  # noqa: E731
+    for kind in ("fgsm", "pgd", "pgdl2", "cw"):
+        if kind == "fgsm":
+            atk = ta.FGSM(model, eps=0.005)
+        elif kind == "pgd":
+            atk = ta.PGD(model, eps=0.001, alpha=2 / 255, steps=3, random_start=True)
+        elif kind == "pgdl2":
+            atk = ta.PGDL2(model, eps=0.1, alpha=0.2, steps=3, random_start=True)
+        else:
+            atk = ta.CW(model, c=1e4, kappa=0.0, steps=5, lr=5e-4)
+        # model_training=False (torchattacks' default): with model_training=True the reference's _get_target_label
+        # (attack.py:262-268) calls model.eval(); ...; model.train(), which switches BatchNorm and Dropout(0.7) back to
+        # TRAINING mode for the attack forward - a stock-torchattacks quirk that makes targeted attacks on LCNN random
+        # (measured: 50 % of the FGSM signs differ run to run).  The native engine always runs the eval forward.
+        atk.set_training_mode(model_training=False)
+        atk.set_mode_targeted_by_function(tmap)
+        torch.manual_seed(2000 + case["cfg_id"])
+        model.eval()
+        want = atk(x, y)
+        # CW: tanh-space Adam takes sign-like +-lr steps, which amplify the 1e-6 gradient differences between two model
+        # implementations wherever the classification and distance terms nearly cancel (10 % of one clip's samples move by up
+        # to 3e-4 here) - so the targeted CW *logic* is pinned with the reference's own nn.Module as the model function
+        # (bit-exact), and the oracle's model is pinned by every other test in this file
+        got = helpers.oracle_targeted(kind, (lambda v: model(v)) if kind == "cw" else fn, x, y, 1 - y, case)
+        if kind in ("fgsm", "pgd"):
+            assert (got != want).float().mean().item() < 2e-3, kind
+        else:
+            assert (got - want).abs().max().item() < 1e-5, kind
