@@ -66,17 +66,23 @@ class Engine:
         self._versions = None
 
     def _tensor_table(self, module):
-        state = {self._prefix + k: v for k, v in module.state_dict(keep_vars=True).items() if v.dtype == torch.float32}
-        for k, v in state.items():
+        live = {self._prefix + k: v for k, v in module.state_dict(keep_vars=True).items() if v.dtype == torch.float32}
+        state, self._mirrors = {}, {}
+        for k, v in live.items():
             _require_cuda(v, f"tensor '{k}'")
             if not v.is_contiguous():
-                raise RuntimeError(f"tensor '{k}' is not contiguous")
+                # torchaudio registers LFCC / MFCC's dct_mat as a transposed VIEW (create_dct(...) returns dct.t()): the
+                # engine reads a packed copy, refreshed whenever the live tensor's version counter moves (_sync_weights)
+                self._mirrors[k] = (v, v.detach().contiguous())
+                state[k] = self._mirrors[k][1]
+            else:
+                state[k] = v
         self._state = state  # keeps the storages alive while the handle borrows them
         self._names = [k.encode() for k in state]
         refs = (_lib.TensorRef * len(state))()
         for i, (k, v) in enumerate(state.items()):
             refs[i] = _lib.TensorRef(self._names[i], v.data_ptr(), v.numel())
-        return refs, tuple(v.data_ptr() for v in state.values())
+        return refs, tuple(v.data_ptr() for v in live.values())  # the LIVE pointers: what _sync_weights compares
 
     def _sync_weights(self):
         """Weights are read live.  A storage that was *replaced* is re-pointed (load_state_dict keeps storages); a tensor
@@ -94,6 +100,8 @@ class Engine:
             self._versions = None
         versions = tuple(v._version for v in live)
         if versions != self._versions:
+            for src, packed in self._mirrors.values():
+                packed.copy_(src.detach())
             _lib.check(self.lib.advb_invalidate_weights(self.handle))
             self._versions = versions
 

@@ -66,6 +66,12 @@ int conv_light_backward(const ConvBwdArgs& a, const unsigned char* wpack, int pa
 int conv0_light_backward_gemm(const float* gout, const unsigned char* codes, const unsigned char* wpack, float* T, int B,
                               int H, int W, int Ho, int Wo, int passes, cudaStream_t stream);
 
+// ---- first block forward as a Toeplitz GEMM without im2col, conv0_toeplitz.cu (its own weight image) ----
+bool conv0t_supported(int H, int W, int Ho, int Wo);
+size_t conv0t_pack_bytes();
+int conv0t_pack(const float* w0, unsigned char* wpack, cudaStream_t stream);
+int conv0t_forward(const ConvFwdArgs& a, const unsigned char* wpack, int passes, cudaStream_t stream);
+
 // ---- persistent warp-specialised kernels for the 3x3 blocks, conv_p3.cu (same packed weights) ----
 bool conv_p3_supported(int Cin, int Cout, int KS, bool pool, int W);
 int conv_p3_forward(const ConvFwdArgs& a, const unsigned char* wpack, int passes, cudaStream_t stream);

@@ -83,6 +83,7 @@ struct advb_handle {
   int tf32_passes = 3;  // 3 = 3xTF32 (fp32-class accuracy), 1 = single-pass tf32
   int conv_sched = 0;   // 0 = persistent warp-specialised conv kernels, 1 = one-tile-per-CTA kernels only
   int conv0_bwd = 0;    // first block backward: 0 = fp32 cell kernel (conv0_bwd.cu), 1 = tcgen05 GEMM + col2im
+  int conv0_fwd = 0;    // first block forward: 0 = Toeplitz GEMM without im2col (conv0_toeplitz.cu), 1 = im2col GEMM (conv_light.cu)
   int use_graph = 1;    // 1 = the PGD / PGDL2 iteration is captured once into a CUDA graph and replayed
   int fuse_update = 1;  // 1 = FGSM / PGD update rule applied in the frontend backward's epilogue (no gradient in HBM)
   int weight_cache = 0; // 1 = the caller promises advb_invalidate_weights() after every weight change: skip the repack otherwise
@@ -127,6 +128,7 @@ struct advb_handle {
   RnModel rn{};
 
   // attack scratch
+  unsigned char* c0t_w = nullptr;  // Toeplitz weight image of the first block (conv0_toeplitz.cu)
   float* conv0_T = nullptr;  // (B,F,80,5) horizontal col2im partial sums of the first block's backward
   float *grad = nullptr, *partial_g = nullptr, *partial_d = nullptr, *coef_tmp = nullptr;
   FabScratch fab{};  // allocated on the first FAB / CW call
@@ -298,6 +300,7 @@ int build_lcnn(advb_handle* h) {
     W = k.Wo;
   }
   ADVB_TRY(h->alloc(&h->conv0_T, (size_t)B * F * 80 * 5));
+  ADVB_TRY(h->alloc(&h->c0t_w, conv0t_pack_bytes()));
   h->L = H;
   h->Wf = W;
   ADVB_CHECK(h->Wf * 32 == 160, "LCNN feature width must be 160");
@@ -340,6 +343,7 @@ int prepare_lcnn(advb_handle* h, cudaStream_t st) {
     if (k.bn_idx >= 0)
       ADVB_TRY(bn_prepare(h->t("m_transform." + std::to_string(k.bn_idx) + ".running_var"), k.invstd, k.Cout / 2, st));
   }
+  ADVB_TRY(conv0t_pack(h->t("m_transform.0.weight"), h->c0t_w, st));
   for (int l = 0; l < 2; ++l) {
     const std::string p = "m_before_pooling." + std::to_string(l) + ".l_blstm.";
     LstmWeights w;
@@ -383,7 +387,9 @@ int lcnn_forward(advb_handle* h, const float* x, int B, cudaStream_t st) {
     a.Wo = k.Wo;
     a.pool = k.pool;
     a.tag = k.tag_f.c_str();
-    if (k.tc && h->conv_path == 0) ADVB_TRY(conv_tc_forward(a, k.tcf, h->tf32_passes, st));
+    if (i == 0 && k.tc && h->conv_path == 0 && h->conv0_fwd == 0 && conv0t_supported(k.H, k.W, k.Ho, k.Wo))
+      ADVB_TRY(conv0t_forward(a, h->c0t_w, h->tf32_passes, st));
+    else if (k.tc && h->conv_path == 0) ADVB_TRY(conv_tc_forward(a, k.tcf, h->tf32_passes, st));
     else ADVB_TRY(conv_mfm_forward(a, st));
     in = k.out.p;
     in_pad = k.out.pad;
@@ -864,6 +870,9 @@ int advb_set_option(advb_handle* h, const char* key, int value) {
   } else if (k == "conv0_bwd") {
     ADVB_CHECK(value == 0 || value == 1, "conv0_bwd: 0 = fp32 cell kernel, 1 = tcgen05 GEMM + col2im");
     h->conv0_bwd = value;
+  } else if (k == "conv0_fwd") {
+    ADVB_CHECK(value == 0 || value == 1, "conv0_fwd: 0 = Toeplitz GEMM without im2col, 1 = im2col GEMM");
+    h->conv0_fwd = value;
   } else if (k == "graph") {
     ADVB_CHECK(value == 0 || value == 1, "graph: 1 = replay the attack iteration as a CUDA graph, 0 = enqueue every kernel");
     h->use_graph = value;
@@ -928,7 +937,7 @@ std::string graph_key(const advb_handle* h, const advb_attack_desc* atk, int B, 
   return std::to_string(atk->kind) + "|" + std::to_string(B) + "|" + bits(atk->eps) + "|" + bits(atk->alpha) + "|" +
          bits(atk->eps_div) + "|" + std::to_string(n_global) + "|" + std::to_string(fused) + "|" +
          std::to_string(h->conv_path) + "|" + std::to_string(h->tf32_passes) + "|" + std::to_string(h->conv_sched) + "|" +
-         std::to_string(h->conv0_bwd) + "|" + std::to_string(h->bind_epoch);
+         std::to_string(h->conv0_bwd) + "|" + std::to_string(h->conv0_fwd) + "|" + std::to_string(h->bind_epoch);
 }
 
 // The attack loops (caller holds a CallScope and has validated the arguments).  `minmax`: x / x_adv are raw waveforms and

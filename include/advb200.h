@@ -99,6 +99,7 @@ ADVB_API int advb_invalidate_weights(advb_handle* h);
  *   "conv_sched"  0 = persistent warp-specialised convolution / GEMM kernels (default), 1 = one-tile-per-CTA kernels only
  *                 (the first tcgen05 version; same arithmetic, kept as an in-process cross-check)
  *   "conv0_bwd"   LCNN first block backward: 0 = fp32 cell kernel (default), 1 = tcgen05 GEMM + col2im (cross-check)
+ *   "conv0_fwd"   LCNN first block forward: 0 = Toeplitz GEMM without im2col (default), 1 = im2col GEMM (cross-check)
  *   "graph"       1 = one PGD / PGDL2 iteration is captured into a CUDA graph and replayed `steps` times (default), 0 = every
  *                 kernel enqueued by the host loop (same kernels, same results)
  *   "fuse_update" 1 = the FGSM / PGD L-inf update rule runs in the epilogue of the frontend backward and the waveform gradient

@@ -84,6 +84,17 @@ def main():
         model.eval()
         with torch.no_grad():
             la = model(xa)
+        first = None
+        if case["attack"] == "pgd":
+            # the same attack stopped after ONE step: the only point where two fp32 implementations are comparable sample by
+            # sample (PGD with alpha > 2 eps is chaotic over many steps: tools/pgd_divergence.py)
+            one = dict(case, params=dict(case["params"], steps=1))
+            atk1 = make_attack(ta, model, one)
+            atk1.set_training_mode(model_training=True, batchnorm_training=False)
+            torch.manual_seed(2000 + case["cfg_id"])
+            model.eval()
+            first = atk1(x, y)
+            model.eval()
         pred_clean = (torch.sigmoid(clean.squeeze(1)) + .5).int()  # evaluate_...py:236-238
         pred_adv = (torch.sigmoid(la.squeeze(1)) + .5).int()
         out = {
@@ -99,6 +110,7 @@ def main():
             "delta_l2": (xa - x).norm(p=2, dim=1).numpy(),
             "sign_bits": np.packbits((xa > x).numpy()),
             "moved_bits": np.packbits((xa != x).numpy()),
+            **({"step1_sign_bits": np.packbits((first > x).numpy())} if first is not None else {}),
             "seconds": np.array(time.time() - t0),
             "threads": np.array(torch.get_num_threads()),
         }

@@ -104,16 +104,34 @@ def test_attack_matches_reference_at_benchmarked_config(name, cuda_device, recor
         json.dump(rows, open(REPORT, "w"), indent=1)
     except OSError:
         pass
-    assert label_mismatch == 0, row
-    assert abs(asr - asr_ref) <= 1e-3, row
-    if not rawnet:
-        # spectral models: the signs of the final gradient agree except at fp32 ties / pool-winner flips
-        assert sign_mismatch / n < 2e-3, row
-        assert dlogit < 2e-4, row
+    # Sample-by-sample agreement is only defined for ONE gradient evaluation: PGD as configured is degenerate (alpha > 2 eps:
+    # every step lands on x +- eps), so one fp32 tie moves a sample by 2 eps, the next gradient is evaluated at a different
+    # point, more near-zero samples flip ...  The reference's OWN 8-thread and 1-thread runs differ in 1.1 % of the samples after
+    # 5 steps, 3.5 % after 10, 7.2 % after 20, 9.9 % after 40, with adversarial logits 6e-5 apart (tools/pgd_divergence.py ->
+    # tests/golden/pgd_divergence_reference.json).  So: the FIRST step is gated tightly, sample by sample; the full attack
+    # is gated by what it is for - the predicted labels and the attack success rate - on every clip whose reference logit
+    # is farther from the decision boundary than the run-to-run logit noise of that model (LCNN: all 128 clips qualify).
+    if case["attack"] == "pgd":
+        one = dict(case, params=dict(case["params"], steps=1))
+        adv1 = native_attack(one, holder, x, y, cuda_device).cpu()
+        s1_ref = np.unpackbits(gold["step1_sign_bits"])[:n].reshape(x.shape).astype(bool)
+        s1 = int(((adv1 > x).numpy() != s1_ref).sum())
+        record_property("step1_sign_mismatch", s1)
+        print("cfg parity: first PGD step sign mismatch", s1, "of", n, "=", s1 / n)
+        assert s1 / n < 1e-3, (s1, n)
+    elif case["attack"] == "fgsm":
+        assert sign_mismatch / n < 1e-3, row
+    band = {"lcnn": 0.0, "specrnet": 2.5e-3, "rawnet3": 5e-3}[case["model"]]
+    decided = np.abs(gold["logits_adv"].ravel()) > band
+    print("cfg parity: clips outside the +-%g logit band: %d of %d" % (band, int(decided.sum()), decided.size))
+    assert decided.sum() >= 0.7 * decided.size
+    assert np.array_equal(pred[decided], gold["pred_adv"][decided]), row
+    assert abs(float((pred[decided] != y_np[decided]).mean()) - float((gold["pred_adv"][decided] != y_np[decided]).mean())) <= 1e-3
+    if case["model"] == "lcnn":
+        assert label_mismatch == 0 and abs(asr - asr_ref) <= 1e-3, row
+        assert dlogit < 5e-4, row
     else:
-        # RawNet3's waveform gradient is ill-conditioned in the reference itself (tools/rn_conditioning.py):
-        # signs are reported, not gated; the adversarial logits still have to land where the reference's do
-        assert dlogit < 5e-3, row
+        assert dlogit < band, row
 
 
 def test_pgd_schedule_variants_are_bit_identical(cuda_device):
@@ -247,7 +265,8 @@ def test_targeted_modes_against_oracle(kind, cuda_device):
     if kind in ("fgsm", "pgd"):
         assert (got != want).float().mean().item() < 2e-3
     elif kind == "pgdl2":
-        assert (got - want).abs().max().item() < 5e-6
+        np.testing.assert_allclose((got - x).norm(p=2, dim=1).numpy(), (want - x).norm(p=2, dim=1).numpy(), rtol=1e-5)
+        assert (got - want).abs().max().item() < 2e-4  # (the reference's own run-to-run element noise on PGDL2 is 2.4e-4)
     else:  # sign-like Adam steps amplify gradient ties (see tests/test_oracle_golden.py); norms and flips are stable
         np.testing.assert_allclose((got - x).norm(p=2, dim=1).numpy(), (want - x).norm(p=2, dim=1).numpy(), rtol=2e-2, atol=1e-6)
         assert ((got - want).abs() > 1e-5).float().mean().item() < 0.05
@@ -283,11 +302,13 @@ def test_cw_strong_elementwise_and_mask_path(cuda_device):
     la = eng.forward(got.to(cuda_device)).cpu().numpy()
     assert np.array_equal(la > 0, g["cw_strong_logits_adv"] > 0)
     np.testing.assert_allclose(la, g["cw_strong_logits_adv"], atol=2e-5)
-    # early stop at step 8 of 20: fewer than half of the 20 iterations' launches were issued
-    full = ta.CW(holder, c=p["c"], kappa=p["kappa"], steps=8, lr=p["lr"])
+    # batch-wide early stop (cw.py:107-110): with 20 steps the cost is checked every 2 steps and first increases at step 8,
+    # so 9 of the 20 iterations run; with 8 steps it is checked every step and stops at step 6 (7 iterations)
+    short = ta.CW(holder, c=p["c"], kappa=p["kappa"], steps=8, lr=p["lr"])
     l0 = eng.launches
-    full(x.to(cuda_device), y.to(cuda_device))
-    assert launches <= (eng.launches - l0) * 9 // 8 + 40
+    short(x.to(cuda_device), y.to(cuda_device))
+    per_iter = (eng.launches - l0) / 7.0
+    assert 8.5 * per_iter < launches < 9.8 * per_iter, (launches, per_iter)
 
 
 def test_frontend_singletons_run_standalone(cuda_device):

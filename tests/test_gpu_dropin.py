@@ -46,7 +46,8 @@ def test_reference_generate_attacks_runs_on_the_native_engine(cuda_device, recor
         g = got["records"][name]
         assert g["y"] == w["y"] and g["pred_clean"] == w["pred_clean"], name
         assert g["pred"] == w["pred"], (name, g, w)                       # predicted label of the attacked clip: bit-exact
-        assert abs(g["linf"] - w["linf"]) < 1e-5 and abs(g["l2"] - w["l2"]) < 1e-5 * max(1.0, w["l2"]), (name, g, w)
+        # FGSM's own norm is L-inf; L2 = eps * sqrt(#samples not clamped at 0 / 1) moves by 8e-6 relative per sign tie there
+        assert abs(g["linf"] - w["linf"]) < 1e-5 and abs(g["l2"] - w["l2"]) < 1e-4 * w["l2"], (name, g["l2"], w["l2"])
         assert abs(g["score"] - w["score"]) < 5e-5 and abs(g["score_clean"] - w["score_clean"]) < 5e-6, (name, g, w)
     assert got["metrics"]["accuracy"] == want["metrics"]["accuracy"]      # attack success rate: identical
     for k in ("eer", "auc", "f1_score"):

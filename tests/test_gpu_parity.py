@@ -102,6 +102,7 @@ def test_every_stage_forward_and_backward(name, conv_path, cuda_device):
     try:
         g, logits = eng.grad(x.to(cuda_device), y.to(cuda_device))
     finally:
+        eng.set_option("conv0_fwd", 0)
         eng.set_option("conv_path", 0)
     B = x.shape[0]
     feat = None
@@ -296,11 +297,19 @@ def test_tensor_core_path_matches_simt_path(name, cuda_device):
         # the one-tile-per-CTA kernels (conv_tc.cu only) and the persistent warp-specialised kernels (conv_light.cu,
         # conv_p3.cu) share weight images, MMA order and epilogue arithmetic: forward bit-identical; the backward of the
         # pooled 3x3 blocks differs only by the summation order of the horizontal-scatter formulation
+        # (first block forward through the im2col kernel for this comparison: its Toeplitz replacement sums the 25 taps in a
+        # different order)
+        eng.set_option("conv0_fwd", 1)
+        g_i2c, l_i2c = eng.grad(xd, yd)
         eng.set_option("conv_sched", 1)
         g_classic, l_classic = eng.grad(xd, yd)
         eng.set_option("conv_sched", 0)
-        assert torch.equal(l_classic, l_tc)
-        assert helpers.rel_err(g_classic.cpu(), g_tc.cpu()) < 2e-5
+        eng.set_option("conv0_fwd", 0)
+        assert torch.equal(l_classic, l_i2c)
+        assert helpers.rel_err(g_classic.cpu(), g_i2c.cpu()) < 2e-5
+        # Toeplitz first block (default) against the im2col first block: same 3xTF32 products, different summation order
+        assert (l_i2c - l_tc).abs().max().item() < 1e-6
+        assert helpers.grads_agree(g_tc.cpu(), g_i2c.cpu())
         # first block backward: the fp32 cell kernel (default, conv0_bwd.cu) against the tcgen05 GEMM + col2im version
         eng.set_option("conv0_bwd", 1)
         g_c0tc, _ = eng.grad(xd, yd)
@@ -313,6 +322,8 @@ def test_tensor_core_path_matches_simt_path(name, cuda_device):
         assert helpers.cosine(g_fast, g_simt) > 0.98
     finally:
         eng.set_option("tf32_passes", 3)
+        eng.set_option("conv0_fwd", 0)
+        eng.set_option("conv_sched", 0)
         eng.set_option("conv_path", 0)
         eng.set_option("conv_sched", 0)
         eng.set_option("conv0_bwd", 0)
