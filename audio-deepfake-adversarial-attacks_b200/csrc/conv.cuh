@@ -69,7 +69,7 @@ int conv0_light_backward_gemm(const float* gout, const unsigned char* codes, con
 // ---- first block forward as a Toeplitz GEMM without im2col, conv0_toeplitz.cu (its own weight image) ----
 bool conv0t_supported(int H, int W, int Ho, int Wo);
 size_t conv0t_pack_bytes();
-int conv0t_pack(const float* w0, unsigned char* wpack, cudaStream_t stream);
+int conv0t_pack(const float* w0, const float* bias, unsigned char* wpack, cudaStream_t stream);
 int conv0t_forward(const ConvFwdArgs& a, const unsigned char* wpack, int passes, cudaStream_t stream);
 
 // ---- persistent warp-specialised kernels for the 3x3 blocks, conv_p3.cu (same packed weights) ----

@@ -39,8 +39,10 @@ constexpr int SROWS = 20;                // 16 coefficients + 2 + 2 halo
 constexpr int PLANE = SROWS * SW * 4;    // bytes of one tf32 plane of a strip
 constexpr int STRIP = 2 * PLANE;         // hi plane, lo plane
 constexpr int WSLICE = 2 * 256 * 16;     // one (dc, part) weight image: [kc][n][16 B]
-constexpr int WBYTES = 5 * 2 * WSLICE;   // [dc][hi | lo]
-constexpr size_t C0T_SMEM = (size_t)WBYTES + 2 * STRIP + 1024;
+constexpr int WCONV = 5 * 2 * WSLICE;     // [dc][hi | lo]
+constexpr int WBYTES = WCONV + WSLICE;   // + the bias image (see pack_c0t_kernel)
+constexpr int ONES = 2304;               // >= 128 rows x 16 B + 16 B of 1.0f: the A operand that adds the bias inside the MMA
+constexpr size_t C0T_SMEM = (size_t)WBYTES + ONES + 2 * STRIP + 1024;
 static_assert(PLANE % 16 == 0 && (SW * 4) % 16 == 0, "descriptor start addresses and strides are in 16-byte units");
 static_assert(C0T_SMEM <= 227 * 1024, "conv0 Toeplitz kernel does not fit shared memory");
 
@@ -66,8 +68,25 @@ __device__ __forceinline__ uint64_t desc_interleave(uint32_t smem_addr, uint32_t
 }
 
 // Weight image of tap column dc, part (0 = tf32 hi, 1 = lo): B[n = fl * 64 + co][k = 4 kc + kk] = w[co][k - fl][dc].
-__global__ void pack_c0t_kernel(const float* __restrict__ w, float* __restrict__ out) {
+// Bias image (one more slice): B[n][0..2] = the three tf32 pieces of bias[co] (hi + mid + lo = bias to 2^-33), multiplied by an
+// all-ones A operand as the first MMA of every tile, so that the accumulator starts at the bias and the epilogue has no
+// per-channel add (64 shared-memory loads and 128 adds per thread and tile in the first version).
+__global__ void pack_c0t_kernel(const float* __restrict__ w, const float* __restrict__ bias, float* __restrict__ out) {
   const int e = blockIdx.x * blockDim.x + threadIdx.x;  // ((dc * 2 + kc) * 256 + n) * 4 + kk
+  if (e >= 5 * 2 * 256 * 4 && e < 5 * 2 * 256 * 4 + 2 * 256 * 4) {
+    const int i = e - 5 * 2 * 256 * 4, kk = i & 3, n = (i >> 2) & 255, kc = i >> 10;
+    float v = 0.f;
+    if (kc == 0 && kk < 3) {
+      float r = bias[n & 63], h = 0.f, l = 0.f;
+      for (int t = 0; t <= kk; ++t) {
+        split_tf32(r, h, l);
+        r = l;
+      }
+      v = h;
+    }
+    out[(size_t)(WCONV / 4) + i] = v;
+    return;
+  }
   if (e >= 5 * 2 * 256 * 4) return;
   const int kk = e & 3, n = (e >> 2) & 255, kc = (e >> 10) & 1, dc = e >> 11;
   const int fl = n >> 6, co = n & 63, df = 4 * kc + kk - fl;
@@ -93,10 +112,10 @@ __global__ void __launch_bounds__(TT, 1) conv0_toeplitz_kernel(C0TArgs a) {
   extern __shared__ unsigned char smem_raw[];
   unsigned char* base = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   unsigned char* w_s = base;              // WBYTES
-  unsigned char* strips = w_s + WBYTES;   // 2 x STRIP
+  float* ones = reinterpret_cast<float*>(w_s + WBYTES);
+  unsigned char* strips = w_s + WBYTES + ONES;   // 2 x STRIP
   __shared__ uint64_t bar_w, bar_strip[2], bar_mma[2], bar_free[2];
   __shared__ uint32_t tmem_base_s;
-  __shared__ float s_bias[64];
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   if (tid == 0) {
@@ -109,7 +128,8 @@ __global__ void __launch_bounds__(TT, 1) conv0_toeplitz_kernel(C0TArgs a) {
     fence_barrier_init();
   }
   if (warp == 0) tmem_alloc<512>(&tmem_base_s);
-  if (tid < 64) s_bias[tid] = __ldg(a.bias + tid);
+  for (int i = tid; i < ONES / 4; i += TT) ones[i] = 1.0f;
+  fence_proxy_async();
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -141,6 +161,9 @@ __global__ void __launch_bounds__(TT, 1) conv0_toeplitz_kernel(C0TArgs a) {
           tc_fence_after();
         }
         const uint32_t dcol = tmem + acc * 256;
+        if (leader)  // accumulator := 1 * bias  (all-ones A rows: any 16-byte unit of the region)
+          mma_tf32(dcol, desc_interleave(smem_u32(ones), a.swap_strides ? 128 : 16, a.swap_strides ? 16 : 128),
+                   desc_interleave(smem_u32(w_s + WCONV), b_lbo, b_sbo), IDESC, 0u);
 #pragma unroll
         for (int dc = 0; dc < 5; ++dc) {
           const uint32_t off = (uint32_t)(dc * SW + 32 * t) * 4u;
@@ -148,7 +171,7 @@ __global__ void __launch_bounds__(TT, 1) conv0_toeplitz_kernel(C0TArgs a) {
           const uint32_t wb = smem_u32(w_s + (size_t)dc * 2 * WSLICE);
           const uint64_t bh = desc_interleave(wb, b_lbo, b_sbo), bl = desc_interleave(wb + WSLICE, b_lbo, b_sbo);
           if (leader) {
-            mma_tf32(dcol, ah, bh, IDESC, dc > 0 ? 1u : 0u);
+            mma_tf32(dcol, ah, bh, IDESC, 1u);
             if (a.passes == 3) {
               mma_tf32(dcol, ah, bl, IDESC, 1u);
               mma_tf32(dcol, al, bh, IDESC, 1u);
@@ -202,9 +225,11 @@ __global__ void __launch_bounds__(TT, 1) conv0_toeplitz_kernel(C0TArgs a) {
   // ---- epilogue geometry of this thread ----
   const int wq = warp & 3, cf = warp >> 2;           // TMEM lane quadrant, frame cell of the unit (frames 2 cf, 2 cf + 1)
   const int r = wq * 32 + lane, ci = r >> 3, jj = r & 7;
-  const unsigned dx = (unsigned)(ci & 1);            // coefficient parity = pool column
-  const bool odd = dx != 0;
+  const bool odd = (ci & 1) != 0;                    // coefficient parity = pool column
   const int Hop = a.Ho + 2 * a.out_pad, Wop = a.Wo + 2 * a.out_pad;
+
+  // spread the low 4 bits of m to the low bit of the 4 bytes of a word (bit q -> bit 8 q): the shifted copies do not overlap
+  auto spread4 = [](unsigned m) { return ((m & 15u) * 0x00204081u) & 0x01010101u; };
 
   auto epilogue = [&](int b, int cb, int tile, int acc) {
     const int oy = 16 * tile + 2 * jj + cf, ox = 8 * cb + (ci >> 1);
@@ -217,48 +242,50 @@ __global__ void __launch_bounds__(TT, 1) conv0_toeplitz_kernel(C0TArgs a) {
       tmem_ld16_issue(taddr + 64 + c0, o0);        // odd frame
       tmem_ld16_issue(taddr + 96 + c0, o1);
       tmem_ld_wait();
+      // Winner bookkeeping as three 16-bit masks instead of 16 code registers: SE / SO = the second MFM half wins at the even /
+      // odd frame (strictly greater), TK = the odd frame wins the frame pair (strictly greater: first wins ties).
       float v[16];
-      unsigned code[16];
+      unsigned SE = 0u, SO = 0u, TK = 0u;
 #pragma unroll
       for (int j = 0; j < 16; ++j) {
-        const float b0 = s_bias[c0 + j], b1 = s_bias[32 + c0 + j];
-        const float el = __uint_as_float(e0[j]) + b0, eh = __uint_as_float(e1[j]) + b1;
-        const float ol = __uint_as_float(o0[j]) + b0, oh = __uint_as_float(o1[j]) + b1;
-        const bool se = eh > el, so = oh > ol;       // Max-Feature-Map: the second half wins only when strictly greater
-        const float ve = se ? eh : el, vo = so ? oh : ol;
-        const unsigned ce = ((se ? 1u : 0u) << 2) | dx, co = ((so ? 1u : 0u) << 2) | 2u | dx;
-        const bool take = vo > ve;                   // frame pair: first wins ties (pool position dy = 0)
-        v[j] = take ? vo : ve;
-        code[j] = take ? co : ce;
+        const float el = __uint_as_float(e0[j]), eh = __uint_as_float(e1[j]);
+        const float ol = __uint_as_float(o0[j]), oh = __uint_as_float(o1[j]);
+        const float ve = fmaxf(el, eh), vo = fmaxf(ol, oh);
+        SE |= (eh > el ? 1u : 0u) << j;
+        SO |= (oh > ol ? 1u : 0u) << j;
+        TK |= (vo > ve ? 1u : 0u) << j;
+        v[j] = fmaxf(ve, vo);
       }
-      // coefficient pair: lane ^ 8.  The even lane finalises channels c0..c0+7, the odd lane c0+8..c0+15.
-      unsigned cpack_send = 0u, cpack_mine = 0u;
-#pragma unroll
-      for (int q = 0; q < 8; ++q) {
-        cpack_send |= (odd ? code[q] : code[8 + q]) << (4 * q);
-        cpack_mine |= (odd ? code[8 + q] : code[q]) << (4 * q);
-      }
-      const unsigned cpack_recv = __shfl_xor_sync(0xffffffffu, cpack_send, 8);
+      const unsigned Hm = (TK & SO) | (~TK & SE);   // MFM half of the winner, per channel
+      // coefficient pair: lane ^ 8.  The even lane finalises channels c0..c0+7, the odd lane c0+8..c0+15 (shift `sh`).
+      const unsigned sh = odd ? 8u : 0u;
+      const unsigned Ho8 = (__shfl_xor_sync(0xffffffffu, Hm, 8) >> sh) & 0xffu;
+      const unsigned Do8 = (__shfl_xor_sync(0xffffffffu, TK, 8) >> sh) & 0xffu;
+      const unsigned Hm8 = (Hm >> sh) & 0xffu, Dm8 = (TK >> sh) & 0xffu;
+      // ATen's max-pool keeps the FIRST maximum in the order (0,0), (0,1), (1,0), (1,1): on equal values the partner wins iff
+      // its position is earlier.  Positions: mine = 2 dy_m + dx, partner = 2 dy_o + (dx ^ 1).
+      const unsigned earlier = odd ? ~(Do8 & ~Dm8) : (~Do8 & Dm8);
       float res[8];
-      unsigned rc[8];
+      unsigned GT = 0u, EQ = 0u;
 #pragma unroll
       for (int q = 0; q < 8; ++q) {
         const float send = odd ? v[q] : v[8 + q];
         const float mine = odd ? v[8 + q] : v[q];
         const float other = __shfl_xor_sync(0xffffffffu, send, 8);
-        const unsigned mc = (cpack_mine >> (4 * q)) & 15u, oc = (cpack_recv >> (4 * q)) & 15u;
-        // ATen's max-pool keeps the FIRST maximum in the order (0,0), (0,1), (1,0), (1,1): on ties the smaller position
-        const bool take = other > mine || (other == mine && (oc & 3u) < (mc & 3u));
-        res[q] = take ? other : mine;
-        rc[q] = take ? oc : mc;
+        GT |= (other > mine ? 1u : 0u) << q;
+        EQ |= (other == mine ? 1u : 0u) << q;
+        res[q] = fmaxf(mine, other);
       }
+      const unsigned T = (GT | (EQ & earlier)) & 0xffu;       // the partner's element is the pooled winner
+      const unsigned Hf = (T & Ho8) | (~T & Hm8), Df = (T & Do8) | (~T & Dm8), Xf = T ^ (odd ? 0xffu : 0u);
       if (oy < a.Ho) {
         const int cs = c0 + (odd ? 8 : 0);
         float* o = a.out + (((size_t)b * Hop + oy + a.out_pad) * Wop + ox + a.out_pad) * 32 + cs;
         *reinterpret_cast<float4*>(o) = make_float4(res[0], res[1], res[2], res[3]);
         *reinterpret_cast<float4*>(o + 4) = make_float4(res[4], res[5], res[6], res[7]);
-        const unsigned lo4 = rc[0] | (rc[1] << 8) | (rc[2] << 16) | (rc[3] << 24);
-        const unsigned hi4 = rc[4] | (rc[5] << 8) | (rc[6] << 16) | (rc[7] << 24);
+        // code byte = MFM half << 2 | frame parity << 1 | coefficient parity
+        const unsigned lo4 = (spread4(Hf) << 2) | (spread4(Df) << 1) | spread4(Xf);
+        const unsigned hi4 = (spread4(Hf >> 4) << 2) | (spread4(Df >> 4) << 1) | spread4(Xf >> 4);
         *reinterpret_cast<uint2*>(a.codes + (((size_t)b * a.Ho + oy) * a.Wo + ox) * 32 + cs) = make_uint2(lo4, hi4);
       }
     }
@@ -307,8 +334,8 @@ bool conv0t_supported(int H, int W, int Ho, int Wo) {
   return g_conv_sched == 0 && W == 80 && Wo == 40 && Ho == H / 2 && Ho >= 1;
 }
 
-int conv0t_pack(const float* w, unsigned char* wpack, cudaStream_t stream) {
-  pack_c0t_kernel<<<cdiv(5 * 2 * 256 * 4, 256), 256, 0, stream>>>(w, reinterpret_cast<float*>(wpack));
+int conv0t_pack(const float* w, const float* bias, unsigned char* wpack, cudaStream_t stream) {
+  pack_c0t_kernel<<<cdiv(5 * 2 * 256 * 4 + 2 * 256 * 4, 256), 256, 0, stream>>>(w, bias, reinterpret_cast<float*>(wpack));
   ADVB_KERNEL_OK("pack_c0t", stream);
   return 0;
 }

@@ -343,7 +343,7 @@ int prepare_lcnn(advb_handle* h, cudaStream_t st) {
     if (k.bn_idx >= 0)
       ADVB_TRY(bn_prepare(h->t("m_transform." + std::to_string(k.bn_idx) + ".running_var"), k.invstd, k.Cout / 2, st));
   }
-  ADVB_TRY(conv0t_pack(h->t("m_transform.0.weight"), h->c0t_w, st));
+  ADVB_TRY(conv0t_pack(h->t("m_transform.0.weight"), h->t("m_transform.0.bias"), h->c0t_w, st));
   for (int l = 0; l < 2; ++l) {
     const std::string p = "m_before_pooling." + std::to_string(l) + ".l_blstm.";
     LstmWeights w;

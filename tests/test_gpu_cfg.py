@@ -121,7 +121,9 @@ def test_attack_matches_reference_at_benchmarked_config(name, cuda_device, recor
         assert s1 / n < 1e-3, (s1, n)
     elif case["attack"] == "fgsm":
         assert sign_mismatch / n < 1e-3, row
-    band = {"lcnn": 0.0, "specrnet": 2.5e-3, "rawnet3": 5e-3}[case["model"]]
+    # (band, bound on the adversarial-logit difference): measured native-vs-reference differences are 1.7e-4 (LCNN), 1.1e-3
+    # (SpecRNet+MFCC, batch-coupled dB floor) and 1.9e-3 (RawNet3, ill-conditioned log|sinc| gradient)
+    band, dmax = {"lcnn": (0.0, 5e-4), "specrnet": (2.5e-3, 2.5e-3), "rawnet3": (2.2e-3, 3e-3)}[case["model"]]
     decided = np.abs(gold["logits_adv"].ravel()) > band
     print("cfg parity: clips outside the +-%g logit band: %d of %d" % (band, int(decided.sum()), decided.size))
     assert decided.sum() >= 0.7 * decided.size
@@ -129,9 +131,7 @@ def test_attack_matches_reference_at_benchmarked_config(name, cuda_device, recor
     assert abs(float((pred[decided] != y_np[decided]).mean()) - float((gold["pred_adv"][decided] != y_np[decided]).mean())) <= 1e-3
     if case["model"] == "lcnn":
         assert label_mismatch == 0 and abs(asr - asr_ref) <= 1e-3, row
-        assert dlogit < 5e-4, row
-    else:
-        assert dlogit < band, row
+    assert dlogit < dmax, row
 
 
 def test_pgd_schedule_variants_are_bit_identical(cuda_device):
