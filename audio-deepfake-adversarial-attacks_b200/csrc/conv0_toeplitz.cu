@@ -31,7 +31,7 @@ namespace {
 
 using namespace tc;
 
-constexpr int TW = 256;                  // worker threads: strip loader + epilogue
+constexpr int TW = 256;                  // worker threads: strip loader + epilogue (16 warps were slower: 96-register cap, 0.132 vs 0.117 ms)
 constexpr int TT = TW + 32;              // + one MMA-issue warp
 constexpr int NT_MAX = 7;                // frame tiles (32 frames) per work item
 constexpr int SW = 32 * NT_MAX + 4;      // strip width in frames: 2 + 2 halo (the K = 8 window of the last unit ends at +3)

@@ -107,7 +107,10 @@ struct advb_handle {
   float *dB = nullptr, *g_dB = nullptr, *mass_partial = nullptr, *g_coef = nullptr;
   int *klo = nullptr, *kcnt = nullptr, *mlo = nullptr, *mcnt = nullptr;
   float* dctT = nullptr;
+  float2* spec = nullptr;  // packed spectra of the last forward (option "fe_spec"): the backward reads them instead of recomputing
+  int fe_spec = 1;
   FrontendState fst{};
+  FrontendHost fe_host{};
   FrontendTables ftb{};
 
   // LCNN
@@ -304,6 +307,7 @@ int build_lcnn(advb_handle* h) {
   h->L = H;
   h->Wf = W;
   ADVB_CHECK(h->Wf * 32 == 160, "LCNN feature width must be 160");
+  ADVB_CHECK(h->blk[8].out.pad == 0, "the last block's output feeds the BLSTM without a border");
   const size_t bl = (size_t)B * h->L;
   ADVB_TRY(h->alloc(&h->feats, bl * 160));
   ADVB_TRY(h->alloc(&h->l1, bl * 160));
@@ -354,7 +358,7 @@ int prepare_lcnn(advb_handle* h, cudaStream_t st) {
       w.b_ih[d] = h->t(p + "bias_ih" + sfx);
       w.b_hh[d] = h->t(p + "bias_hh" + sfx);
     }
-    ADVB_TRY(lstm_pack(w, h->lp[l], st));
+    ADVB_TRY(lstm_pack(w, h->lp[l], st, l == 0 ? h->Wf : 0));  // layer 0 reads the last block's NHWC output as it is
   }
   return 0;
 }
@@ -362,7 +366,7 @@ int prepare_lcnn(advb_handle* h, cudaStream_t st) {
 int lcnn_forward(advb_handle* h, const float* x, int B, cudaStream_t st) {
   const Act& a0 = h->act0;
   ADVB_TRY(frontend_forward(h->ftb, h->fst, x, B, h->T, h->dB, a0.p, (long long)a0.per_clip(), (long long)a0.Wp(), 1,
-                            (long long)a0.pad * a0.Wp() + a0.pad, st));
+                            (long long)a0.pad * a0.Wp() + a0.pad, st, h->fe_spec ? h->spec : nullptr, &h->fe_host));
   const float* in = a0.p;
   int in_pad = a0.pad;
   for (int i = 0; i < 9; ++i) {
@@ -394,22 +398,25 @@ int lcnn_forward(advb_handle* h, const float* x, int B, cudaStream_t st) {
     in = k.out.p;
     in_pad = k.out.pad;
   }
-  ADVB_TRY(feats_gather(h->blk[8].out.p, h->feats, B, h->L, h->Wf, 32, st));
-  ADVB_TRY(blstm_forward(h->lp[0], h->feats, h->gates1, h->l1, h->cs1, B, h->L, st));
+  // The (B, L, Wf, 32) output of the last block IS the BLSTM's input: the permutation of lcnn.py:196-199 lives in the packed
+  // input-projection weights of layer 0 and in the head's index map (no gather kernel)
+  const float* feats = h->blk[8].out.p;
+  ADVB_TRY(blstm_forward(h->lp[0], feats, h->gates1, h->l1, h->cs1, B, h->L, st));
   ADVB_TRY(blstm_forward(h->lp[1], h->l1, h->gates2, h->l2, h->cs2, B, h->L, st));
-  ADVB_TRY(head_forward(h->l2, h->feats, h->t("m_output_act.weight"), h->t("m_output_act.bias"), h->logits, B, h->L,
-                        st));
+  ADVB_TRY(head_forward(h->l2, feats, h->t("m_output_act.weight"), h->t("m_output_act.bias"), h->logits, B, h->L, st,
+                        h->Wf));
   return 0;
 }
 
 // Gradient of (mode 0) the mean 2-class CE or (mode 1) the logit, w.r.t. the waveform of the last forward.
 int lcnn_backward(advb_handle* h, const float* x, const int64_t* y, int B, int mode, int n_global, float* gx,
                   cudaStream_t st, const float* coef = nullptr, const FusedUpdate* upd = nullptr) {
+  // dfeats = the head's residual contribution, already in the block's NHWC order; the input gradient of layer 0 then lands
+  // in the last block's gradient buffer directly (no scatter kernel)
   ADVB_TRY(head_backward(h->logits, reinterpret_cast<const long long*>(y), h->t("m_output_act.weight"), h->dl2, B,
-                         h->L, mode, n_global, st, coef));
+                         h->L, mode, n_global, st, coef, h->dfeats, h->Wf));
   ADVB_TRY(blstm_backward(h->lp[1], h->gates2, h->dl2, h->cs2, nullptr, h->dl1, B, h->L, st));
-  ADVB_TRY(blstm_backward(h->lp[0], h->gates1, h->dl1, h->cs1, h->dl2, h->dfeats, B, h->L, st));
-  ADVB_TRY(feats_scatter(h->dfeats, h->blk[8].gout, B, h->L, h->Wf, 32, st));
+  ADVB_TRY(blstm_backward(h->lp[0], h->gates1, h->dl1, h->cs1, h->dfeats, h->blk[8].gout, B, h->L, st));
   for (int i = 8; i >= 1; --i) {
     LcnnBlock& k = h->blk[i];
     ConvBwdArgs a{};
@@ -440,7 +447,7 @@ int lcnn_backward(advb_handle* h, const float* x, const int64_t* y, int B, int m
   else
     ADVB_TRY(conv0_backward(k0.gout, k0.codes, h->t("m_transform.0.weight"), h->g_coef, B, k0.H, k0.W, k0.Ho, k0.Wo, st));
   ADVB_TRY(frontend_backward(h->ftb, h->fst, x, B, h->T, h->dB, h->g_coef, (long long)h->F * 80, 80, 1,
-                             h->mass_partial, h->g_dB, gx, st, upd));
+                             h->mass_partial, h->g_dB, gx, st, upd, h->fe_spec ? h->spec : nullptr, &h->fe_host));
   return 0;
 }
 
@@ -580,7 +587,8 @@ int prepare_specrnet(advb_handle* h, cudaStream_t st) {
 
 int specrnet_forward(advb_handle* h, const float* x, int B, cudaStream_t st) {
   const int F = h->F;
-  ADVB_TRY(frontend_forward(h->ftb, h->fst, x, B, h->T, h->dB, h->sr_img, (long long)(F + 2) * 82, 82, 1, 82 + 1, st));
+  ADVB_TRY(frontend_forward(h->ftb, h->fst, x, B, h->T, h->dB, h->sr_img, (long long)(F + 2) * 82, 82, 1, 82 + 1, st,
+                            h->fe_spec ? h->spec : nullptr, &h->fe_host));
   ADVB_TRY(sr_input_forward(h->sr_img, h->sr_bn4, B, F, 80, st));
   const float* in = h->sr_img;
   const char* tags[3] = {"sr_b0", "sr_b2", "sr_b4"};
@@ -603,7 +611,7 @@ int specrnet_backward(advb_handle* h, const float* x, const int64_t* y, int B, i
     ADVB_TRY(sr_block_backward(h->sr[i], in, gin, B, i == 0, h->sr_bn4, tags[i], st));
   }
   ADVB_TRY(frontend_backward(h->ftb, h->fst, x, B, h->T, h->dB, h->g_coef, (long long)h->F * 80, 80, 1, h->mass_partial,
-                             h->g_dB, gx, st, upd));
+                             h->g_dB, gx, st, upd, h->fe_spec ? h->spec : nullptr, &h->fe_host));
   return 0;
 }
 
@@ -824,9 +832,9 @@ int advb_create(advb_handle** out, const advb_model_desc* d) {
   if (check_frontend_tensors(h)) return fail();
   if (h->alloc(&h->tw, 512) || h->alloc(&h->dctT, 128 * 80) || h->alloc(&h->klo, 128) || h->alloc(&h->kcnt, 128) ||
       h->alloc(&h->mlo, 257) || h->alloc(&h->mcnt, 257) || h->alloc(&h->fst.gmax_packed, 1) ||
-      h->alloc(&h->fst.n_clamped, 1) || h->alloc(&h->fst.mass_total, 1) ||
+      h->alloc(&h->fst.n_clamped, 1) || h->alloc(&h->fst.mass_total, 1) || h->alloc(&h->fst.done, 2) ||
       h->alloc(&h->dB, B * h->F * 128) || h->alloc(&h->g_dB, B * h->F * 128) || h->alloc(&h->g_coef, B * h->F * 80) ||
-      h->alloc(&h->coef_tmp, B * h->F * 80) ||
+      h->alloc(&h->coef_tmp, B * h->F * 80) || h->alloc(reinterpret_cast<float**>(&h->spec), frontend_spec_floats(h->Bmax, h->T)) ||
       h->alloc(&h->mass_partial, (size_t)frontend_mass_blocks(h->Bmax, h->T)) || h->alloc(&h->logits, B) ||
       h->alloc(&h->grad, B * h->T) || h->alloc(&h->partial_g, B * ROW_CHUNKS) ||
       h->alloc(&h->partial_d, B * ROW_CHUNKS))
@@ -873,6 +881,9 @@ int advb_set_option(advb_handle* h, const char* key, int value) {
   } else if (k == "conv0_fwd") {
     ADVB_CHECK(value == 0 || value == 1, "conv0_fwd: 0 = Toeplitz GEMM without im2col, 1 = im2col GEMM");
     h->conv0_fwd = value;
+  } else if (k == "fe_spec") {
+    ADVB_CHECK(value == 0 || value == 1, "fe_spec: 1 = the frontend backward reads the forward's stored spectra, 0 = recomputes the STFT");
+    h->fe_spec = value;
   } else if (k == "graph") {
     ADVB_CHECK(value == 0 || value == 1, "graph: 1 = replay the attack iteration as a CUDA graph, 0 = enqueue every kernel");
     h->use_graph = value;
@@ -937,7 +948,8 @@ std::string graph_key(const advb_handle* h, const advb_attack_desc* atk, int B, 
   return std::to_string(atk->kind) + "|" + std::to_string(B) + "|" + bits(atk->eps) + "|" + bits(atk->alpha) + "|" +
          bits(atk->eps_div) + "|" + std::to_string(n_global) + "|" + std::to_string(fused) + "|" +
          std::to_string(h->conv_path) + "|" + std::to_string(h->tf32_passes) + "|" + std::to_string(h->conv_sched) + "|" +
-         std::to_string(h->conv0_bwd) + "|" + std::to_string(h->conv0_fwd) + "|" + std::to_string(h->bind_epoch);
+         std::to_string(h->conv0_bwd) + "|" + std::to_string(h->conv0_fwd) + "|" + std::to_string(h->fe_spec) + "|" +
+         std::to_string(h->bind_epoch);
 }
 
 // The attack loops (caller holds a CallScope and has validated the arguments).  `minmax`: x / x_adv are raw waveforms and
@@ -990,6 +1002,7 @@ int run_attack(advb_handle* h, const advb_attack_desc* atk, const float* x, cons
       if (minmax) ADVB_TRY(minmax_scale(x, h->x_in, h->mm_mn, h->mm_mx, B, T, st));
       else ADVB_CUDA_OK(cudaMemcpyAsync(h->x_in, x, bytes, cudaMemcpyDeviceToDevice, st));
       ADVB_CUDA_OK(cudaMemcpyAsync(h->y_in, y, (size_t)B * sizeof(int64_t), cudaMemcpyDeviceToDevice, st));
+      if (has_frontend) ADVB_TRY(frontend_clean(h->fst, &h->fe_host, st));  // the captured body assumes (and leaves) a clean state
       const float* xin = h->x_in;
       const int64_t* yin = h->y_in;
       const float eps = atk->eps, alpha = dir * atk->alpha, eps_div = atk->eps_div;
@@ -1148,7 +1161,7 @@ int advb_frontend_fwd(advb_handle* h, const float* x, float* coeff, int B, int T
   cudaStream_t st = static_cast<cudaStream_t>(cuda_stream);
   refresh_frontend_tables(h);
   ADVB_TRY(frontend_prepare(h->ftb, st));
-  ADVB_TRY(frontend_forward(h->ftb, h->fst, x, B, T, h->dB, coeff, (long long)80 * h->F, 1, h->F, 0, st));
+  ADVB_TRY(frontend_forward(h->ftb, h->fst, x, B, T, h->dB, coeff, (long long)80 * h->F, 1, h->F, 0, st, nullptr, &h->fe_host));
   return 0;
 }
 
@@ -1161,9 +1174,9 @@ int advb_frontend_bwd(advb_handle* h, const float* x, const float* g_coeff, floa
   refresh_frontend_tables(h);
   ADVB_TRY(frontend_prepare(h->ftb, st));
   // forward first: backward needs the batch arg-max / floor state of this input
-  ADVB_TRY(frontend_forward(h->ftb, h->fst, x, B, T, h->dB, h->coef_tmp, (long long)80 * h->F, 1, h->F, 0, st));
+  ADVB_TRY(frontend_forward(h->ftb, h->fst, x, B, T, h->dB, h->coef_tmp, (long long)80 * h->F, 1, h->F, 0, st, nullptr, &h->fe_host));
   ADVB_TRY(frontend_backward(h->ftb, h->fst, x, B, T, h->dB, g_coeff, (long long)80 * h->F, 1, h->F, h->mass_partial,
-                             h->g_dB, g_x, st));
+                             h->g_dB, g_x, st, nullptr, nullptr, &h->fe_host));
   return 0;
 }
 
@@ -1266,7 +1279,10 @@ int64_t advb_debug_stage(advb_handle* h, const char* stage, float* dst, int64_t 
     d[2] = k.Wo;
     d[3] = k.Cout / 2;
   } else if (s == "feats" || s == "lstm1" || s == "lstm2" || s == "dfeats") {
-    src = s == "feats" ? h->feats : s == "lstm1" ? h->l1 : s == "lstm2" ? h->l2 : h->dfeats;
+    // features / their gradient in the reference's (c * Wf + w) order: gathered on demand from the NHWC block buffers
+    if (s == "feats" && feats_gather(h->blk[8].out.p, h->feats, h->Bmax, h->L, h->Wf, 32, st)) return -1;
+    if (s == "dfeats" && feats_gather(h->blk[8].gout, h->feats, h->Bmax, h->L, h->Wf, 32, st)) return -1;
+    src = (s == "feats" || s == "dfeats") ? h->feats : s == "lstm1" ? h->l1 : h->l2;
     d[1] = h->L;
     d[2] = 1;
     d[3] = 160;

@@ -13,9 +13,9 @@
 //   fe_power_db   : one warp = two frames packed in one 512-point complex FFT held in shared memory;
 //                   power -> sparse triangular filterbank -> 10 log10 -> dB store + batch arg-max (64-bit atomicMax)
 //   fe_floor_dct  : floor at (batch max - 80), DCT by shared-memory matrix, strided store, clamped-element count
-//   fe_floor_mass : (only when the floor is active) sum of the gradient mass of clamped elements, which autograd
-//                   routes to the batch arg-max element; two-stage fixed-order reduction (deterministic)
-//   fe_dct_t      : d dB = d coefficients x dct^T for every frame (register-tiled fp32 SIMT product, (B,F,128) out)
+//   fe_dct_t      : d dB = d coefficients x dct^T for every frame (register-tiled fp32 SIMT product, (B,F,128) out); when
+//                   the floor is active also the summed gradient of the clamped elements, which autograd routes to the batch
+//                   arg-max element (per-block sums, added in block order by the last block to finish: deterministic)
 //   fe_bwd        : per tile of 40 hops, one warp per frame pair: recompute FFT/power/energies, dB+floor backward,
 //                   filterbank^T, one-sided inverse DFT as a packed complex FFT, window, overlap-add and reflect-pad
 //                   fold in shared memory in a fixed order (deterministic, no atomics), gradient store
@@ -227,13 +227,16 @@ __global__ void fe_reset_kernel(FrontendState st) {
   *st.gmax_packed = 0ull;
   *st.n_clamped = 0;
   *st.mass_total = 0.f;
+  st.done[0] = 0u;
+  st.done[1] = 0u;
 }
 
 // ---------------------------------------------------------------------------------------------------
 // Forward 1: waveform -> dB filterbank energies (B,F,128) + batch arg-max.
 __global__ void __launch_bounds__(FE_THREADS, 3) fe_power_db_kernel(const float* __restrict__ x, int T, int F,
                                                                       FrontendTables tb, FrontendState st,
-                                                                      float* __restrict__ dB, int n_blocks, int n_clips) {
+                                                                      float* __restrict__ dB, float2* __restrict__ spec,
+                                                                      int n_blocks, int n_clips) {
   extern __shared__ __align__(16) float smem[];
   float2* s_tw = reinterpret_cast<float2*>(smem);                    // 512 float2
   float* s_win = smem + 1024;                                        // 400
@@ -259,6 +262,14 @@ __global__ void __launch_bounds__(FE_THREADS, 3) fe_power_db_kernel(const float*
 
     load_frame_pair(xb, T, F, ta, s_win, bufA, lane);
     warp_fft512(bufA, bufB, s_tw, lane);
+    if (spec != nullptr) {
+      // keep the packed spectrum of the frame pair (ta, ta + 1) for the backward: 4 KB per pair, coalesced float2 rows.  The
+      // backward used to recompute load + FFT per pair; every frontend kernel is latency-bound at 3 % of the DRAM bandwidth,
+      // so 105 MB of extra traffic per pass (B = 128) is cheaper than the second FFT.
+      float2* dst = spec + ((size_t)b * ((F + 1) >> 1) + (ta >> 1)) * NFFT;
+#pragma unroll
+      for (int i = 0; i < NFFT / 32; ++i) dst[lane + 32 * i] = bufB[lane + 32 * i];
+    }
     for (int k = lane; k < NBIN; k += 32) {
       float xar, xai, xbr, xbi;
       unpack_bin(bufB, k, xar, xai, xbr, xbi);
@@ -380,81 +391,30 @@ __global__ void __launch_bounds__(256, 3) fe_floor_dct_kernel(const float* __res
 }
 
 // ---------------------------------------------------------------------------------------------------
-// Backward pre-pass: gradient mass of clamped dB elements (routed to the arg-max element by autograd).
-__global__ void __launch_bounds__(FE_THREADS) fe_floor_mass_kernel(const float* __restrict__ dB, int F,
-                                                                     FrontendTables tb, FrontendState st,
-                                                                     float top_db, const float* __restrict__ gcoef,
-                                                                     long long g_clip_stride, long long g_stride_f,
-                                                                     long long g_stride_c, float* partial) {
-  __shared__ float s_gc[FE_WARPS][2][NCOEF];
-  __shared__ float s_part[FE_WARPS];
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int bid = blockIdx.y * gridDim.x + blockIdx.x;
-  if (*st.n_clamped == 0) {
-    if (tid == 0) partial[bid] = 0.f;
-    return;
-  }
-  float vmax;
-  unsigned amax_idx;
-  decode_gmax(*st.gmax_packed, vmax, amax_idx);
-  const float floor_v = vmax - top_db;
-  const int b = blockIdx.y;
-  const int ta = blockIdx.x * (2 * FE_WARPS) + 2 * warp;
-  float mass = 0.f;
-  for (int fr = 0; fr < 2; ++fr) {
-    const int t = ta + fr;
-    if (t < F)
-      for (int c = lane; c < NCOEF; c += 32)
-        s_gc[warp][fr][c] = gcoef[(size_t)b * g_clip_stride + (long long)t * g_stride_f + (long long)c * g_stride_c];
-  }
-  __syncwarp();
-  for (int fr = 0; fr < 2; ++fr) {
-    const int t = ta + fr;
-    if (t >= F) continue;
-    for (int m = lane; m < NFILT; m += 32) {
-      const float d = dB[((size_t)b * F + t) * NFILT + m];
-      if (d < floor_v) {
-        float g = 0.f;
-        for (int c = 0; c < NCOEF; ++c) g += __ldg(tb.dct + m * NCOEF + c) * s_gc[warp][fr][c];
-        mass += g;
-      }
-    }
-  }
-  mass = warp_sum(mass);
-  if (lane == 0) s_part[warp] = mass;
-  __syncthreads();
-  if (tid == 0) {
-    float s = 0.f;
-    for (int w = 0; w < FE_WARPS; ++w) s += s_part[w];
-    partial[bid] = s;
-  }
-}
-
-__global__ void __launch_bounds__(1024) fe_mass_reduce_kernel(const float* __restrict__ partial, int n,
-                                                               FrontendState st) {
-  __shared__ float s[1024];
-  float acc = 0.f;
-  for (int i = threadIdx.x; i < n; i += 1024) acc += partial[i];
-  s[threadIdx.x] = acc;
-  __syncthreads();
-  for (int o = 512; o > 0; o >>= 1) {
-    if (threadIdx.x < o) s[threadIdx.x] += s[threadIdx.x + o];
-    __syncthreads();
-  }
-  if (threadIdx.x == 0) *st.mass_total = s[0];
-}
-
-// ---------------------------------------------------------------------------------------------------
 // Backward pre-pass: d dB (before the floor) = d coefficients x dct^T, one (B F, 80) x (80, 128) fp32 SIMT product.
 // Thread = 8 frames x 4 filters (32 accumulators): per 4 coefficients 4 conflict-free LDS.128 of dct^T and 8 broadcast
 // LDS.128 of the gradients feed 128 FMAs.  Persistent: dct^T (40 KB) is staged once per CTA.
+// It also produces what the two mass kernels used to: the summed gradient of the dB elements the top_db floor clamped (the
+// product row IS their gradient), per block in a fixed order, reduced by the last block to finish in block order.
 __global__ void __launch_bounds__(256, 3) fe_dct_t_kernel(const float* __restrict__ gcoef, long long g_clip_stride,
                                                         long long g_stride_f, long long g_stride_c, int F,
-                                                        FrontendTables tb, float* __restrict__ gd, int n_rows) {
+                                                        FrontendTables tb, float* __restrict__ gd, int n_rows,
+                                                        const float* __restrict__ dB, FrontendState st, float top_db,
+                                                        float* __restrict__ partial) {
   extern __shared__ __align__(16) float smem[];
   float* s_w = smem;                  // 80 x 128: s_w[c][m] = dct[m][c]
   float* s_g = s_w + NCOEF * NFILT;   // DT_FR x DT_GLD
+  __shared__ float s_mass[8];
+  __shared__ unsigned s_last;
   const int tid = threadIdx.x, mq = tid & 31, fg = tid >> 5;
+  const bool floor_active = *st.n_clamped != 0;
+  float floor_v = 0.f, mass = 0.f;
+  if (floor_active) {
+    float vmax;
+    unsigned amax_idx;
+    decode_gmax(*st.gmax_packed, vmax, amax_idx);
+    floor_v = vmax - top_db;
+  }
   for (int i = tid; i < NFILT * NCOEF / 4; i += 256)
     reinterpret_cast<float4*>(s_w)[i] = __ldg(reinterpret_cast<const float4*>(tb.dctT) + i);
   // rows = (clip, frame) pairs, flat
@@ -493,9 +453,37 @@ __global__ void __launch_bounds__(256, 3) fe_dct_t_kernel(const float* __restric
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
       const int r = r0 + fg * 8 + j;
-      if (r < n_rows)
+      if (r < n_rows) {
         *reinterpret_cast<float4*>(gd + (size_t)r * NFILT + 4 * mq) =
             make_float4(acc[j][0], acc[j][1], acc[j][2], acc[j][3]);
+        if (floor_active) {
+          const float4 d = __ldg(reinterpret_cast<const float4*>(dB + (size_t)r * NFILT) + mq);
+          mass += (d.x < floor_v ? acc[j][0] : 0.f) + (d.y < floor_v ? acc[j][1] : 0.f) +
+                  (d.z < floor_v ? acc[j][2] : 0.f) + (d.w < floor_v ? acc[j][3] : 0.f);
+        }
+      }
+    }
+  }
+  // block sum (fixed order), then the last block to arrive adds the per-block sums in block order: deterministic
+  mass = warp_sum(mass);
+  if (mq == 0) s_mass[fg] = mass;
+  __syncthreads();
+  if (tid == 0) {
+    float s = 0.f;
+    for (int w = 0; w < 8; ++w) s += s_mass[w];
+    partial[blockIdx.x] = s;
+    __threadfence();
+    s_last = atomicAdd(&st.done[0], 1u) == gridDim.x - 1 ? 1u : 0u;
+  }
+  __syncthreads();
+  if (s_last != 0u && tid < 32) {
+    __threadfence();
+    float s = 0.f;
+    for (int i = tid; i < (int)gridDim.x; i += 32) s += __ldcg(partial + i);
+    s = warp_sum(s);
+    if (tid == 0) {
+      *st.mass_total = floor_active ? s : 0.f;
+      st.done[0] = 0u;
     }
   }
 }
@@ -517,7 +505,8 @@ __host__ __device__ __forceinline__ void tile_frames(int s0, int s1, int T, int 
 __global__ void __launch_bounds__(FB_THREADS, 1) fe_bwd_kernel(const float* __restrict__ x, int T, int F,
                                                                 FrontendTables tb, FrontendState st, float top_db,
                                                                 const float* __restrict__ gd, float* __restrict__ gx,
-                                                                int n_tiles, int n_clips, FusedUpdate upd) {
+                                                                const float2* __restrict__ spec, int n_tiles, int n_clips,
+                                                                FusedUpdate upd) {
   extern __shared__ __align__(16) float smem[];
   float2* s_tw = reinterpret_cast<float2*>(smem);                  // 512 float2
   float* s_win = smem + 1024;                                      // 400
@@ -546,6 +535,7 @@ __global__ void __launch_bounds__(FB_THREADS, 1) fe_bwd_kernel(const float* __re
     const int s1 = min(T, s0 + TILE_S);
     int t_lo, t_hi;
     tile_frames(s0, s1, T, F, t_lo, t_hi);
+    if (spec != nullptr) t_lo &= ~1;  // pairs aligned with the forward's (even, even + 1) pairs, whose packed spectra are stored
     const int nf = t_hi - t_lo + 1;  // host guarantees nf <= NF_MAX: warp w owns frames t_lo + 2 w, t_lo + 2 w + 1
     const float* xb = x + (size_t)b * T;
 
@@ -560,9 +550,16 @@ __global__ void __launch_bounds__(FB_THREADS, 1) fe_bwd_kernel(const float* __re
         gda[i] = __ldg(gd + rowa + lane + 32 * i);
         gdb[i] = has_b ? __ldg(gd + rowa + NFILT + lane + 32 * i) : 0.f;
       }
-      // 2. recompute the packed FFT of both frames: Z in bufB
-      load_frame_pair(xb, T, has_b ? F : ta + 1, ta, s_win, bufA, lane);
-      warp_fft512(bufA, bufB, s_tw, lane);
+      // 2. packed FFT of both frames, Z in bufB: read back from the forward's store, or recomputed
+      if (spec != nullptr) {
+        const float2* src = spec + ((size_t)b * ((F + 1) >> 1) + (ta >> 1)) * NFFT;
+#pragma unroll
+        for (int i = 0; i < NFFT / 32; ++i) bufB[lane + 32 * i] = __ldg(src + lane + 32 * i);
+        __syncwarp();
+      } else {
+        load_frame_pair(xb, T, has_b ? F : ta + 1, ta, s_win, bufA, lane);
+        warp_fft512(bufA, bufB, s_tw, lane);
+      }
       // 3. power
       for (int k = lane; k < NBIN; k += 32) {
         float xar, xai, xbr, xbi;
@@ -679,6 +676,17 @@ __global__ void __launch_bounds__(FB_THREADS, 1) fe_bwd_kernel(const float* __re
     }
     __syncthreads();  // the FFT buffers are reused by the next tile
   }
+  // Every block read the batch arg-max / floor state at its start; the last one to finish resets it for the next forward
+  // (the separate reset kernel of every iteration is gone; a forward that follows a forward still launches it).
+  if (tid == 0) {
+    __threadfence();
+    if (atomicAdd(&st.done[1], 1u) == gridDim.x - 1) {
+      *st.gmax_packed = 0ull;
+      *st.n_clamped = 0;
+      *st.mass_total = 0.f;
+      st.done[1] = 0u;
+    }
+  }
 }
 
 size_t fe_fwd_smem() { return (size_t)(1024 + 400 + FE_WARPS * 2 * (FFT_A + FFT_B)) * sizeof(float); }  // 74 KB: 3 CTAs / SM
@@ -689,7 +697,8 @@ size_t fe_bwd_smem() { return (size_t)(1024 + 400 + FB_WARPS * 2 * (FFT_A + FFT_
 }  // namespace
 
 int frontend_frames(int T) { return 1 + T / HOP; }
-int frontend_mass_blocks(int B, int T) { return B * cdiv(frontend_frames(T), 2 * FE_WARPS); }
+size_t frontend_spec_floats(int B, int T) { return (size_t)B * ((frontend_frames(T) + 1) / 2) * NFFT * 2; }
+int frontend_mass_blocks(int B, int T) { return std::max(B * cdiv(frontend_frames(T), 2 * FE_WARPS), 148 * 3 + 8); }
 
 int frontend_init_constants(float2* tw, cudaStream_t stream) {
   fe_twiddle_kernel<<<2, 256, 0, stream>>>(tw);
@@ -711,14 +720,17 @@ int frontend_prepare(const FrontendTables& tb, cudaStream_t stream) {
 
 int frontend_forward(const FrontendTables& tb, const FrontendState& st, const float* x, int B, int T, float* dB,
                      float* out, long long clip_stride, long long stride_f, long long stride_c, long long offset,
-                     cudaStream_t stream) {
+                     cudaStream_t stream, float2* spec, FrontendHost* host) {
   const int F = frontend_frames(T);
   ADVB_CHECK(T >= 512, "clip shorter than one FFT frame");
-  fe_reset_kernel<<<1, 1, 0, stream>>>(st);
-  ADVB_KERNEL_OK("fe_reset", stream);
+  if (host == nullptr || host->dirty) {
+    fe_reset_kernel<<<1, 1, 0, stream>>>(st);
+    ADVB_KERNEL_OK("fe_reset", stream);
+  }
+  if (host != nullptr) host->dirty = true;
   const int n_fb = cdiv(F, 2 * FE_WARPS);
   const int g1 = n_fb * B < 148 * 3 ? n_fb * B : 148 * 3;  // persistent: 74 KB of shared memory -> 3 CTAs / SM
-  fe_power_db_kernel<<<g1, FE_THREADS, fe_fwd_smem(), stream>>>(x, T, F, tb, st, dB, n_fb, B);
+  fe_power_db_kernel<<<g1, FE_THREADS, fe_fwd_smem(), stream>>>(x, T, F, tb, st, dB, spec, n_fb, B);
   ADVB_KERNEL_OK("fe_power_db", stream);
   const int n_items = cdiv(B * F, FD_FR);
   const int g2 = n_items < 148 * 3 ? n_items : 148 * 3;  // persistent: 71 KB of shared memory -> 3 CTAs / SM
@@ -731,22 +743,18 @@ int frontend_forward(const FrontendTables& tb, const FrontendState& st, const fl
 int frontend_backward(const FrontendTables& tb, const FrontendState& st, const float* x, int B, int T,
                       const float* dB, const float* gcoef, long long g_clip_stride, long long g_stride_f,
                       long long g_stride_c, float* mass_partial, float* gd, float* gx, cudaStream_t stream,
-                      const FusedUpdate* upd) {
+                      const FusedUpdate* upd, const float2* spec, FrontendHost* host) {
   const int F = frontend_frames(T);
-  dim3 g1(cdiv(F, 2 * FE_WARPS), B);
-  fe_floor_mass_kernel<<<g1, FE_THREADS, 0, stream>>>(dB, F, tb, st, 80.0f, gcoef, g_clip_stride, g_stride_f,
-                                                     g_stride_c, mass_partial);
-  ADVB_KERNEL_OK("fe_floor_mass", stream);
-  fe_mass_reduce_kernel<<<1, 1024, 0, stream>>>(mass_partial, (int)(g1.x * g1.y), st);
-  ADVB_KERNEL_OK("fe_mass_reduce", stream);
   const int n_items = cdiv(B * F, DT_FR);
   const int g2 = n_items < 148 * 3 ? n_items : 148 * 3;  // persistent: 61 KB of shared memory -> 3 CTAs / SM
-  fe_dct_t_kernel<<<g2, 256, fe_dct_t_smem(), stream>>>(gcoef, g_clip_stride, g_stride_f, g_stride_c, F, tb, gd, B * F);
+  fe_dct_t_kernel<<<g2, 256, fe_dct_t_smem(), stream>>>(gcoef, g_clip_stride, g_stride_f, g_stride_c, F, tb, gd, B * F, dB, st,
+                                                       80.0f, mass_partial);
   ADVB_KERNEL_OK("fe_dct_t", stream);
   const int n_tiles = cdiv(T, TILE_S);
   for (int tile = 0; tile < n_tiles; ++tile) {
     int t_lo, t_hi;
     tile_frames(tile * TILE_S, std::min(T, (tile + 1) * TILE_S), T, F, t_lo, t_hi);
+    if (spec != nullptr) t_lo &= ~1;
     ADVB_CHECK(t_hi - t_lo + 1 <= NF_MAX, "frontend backward: a tile needs more frames than the kernel has warps for");
   }
   const int grid = n_tiles * B < 148 ? n_tiles * B : 148;  // one persistent CTA per SM (210 KB of shared memory each)
@@ -756,8 +764,17 @@ int frontend_backward(const FrontendTables& tb, const FrontendState& st, const f
     ADVB_CHECK(u.kind == 0 || (u.x_clean != nullptr && u.adv_out != nullptr && u.adv_out != x),
                "fused update needs the clean clips and an output buffer that does not alias the waveform");
   }
-  fe_bwd_kernel<<<grid, FB_THREADS, fe_bwd_smem(), stream>>>(x, T, F, tb, st, 80.0f, gd, gx, n_tiles, B, u);
+  fe_bwd_kernel<<<grid, FB_THREADS, fe_bwd_smem(), stream>>>(x, T, F, tb, st, 80.0f, gd, gx, spec, n_tiles, B, u);
   ADVB_KERNEL_OK("fe_bwd", stream);
+  if (host != nullptr) host->dirty = false;  // the kernel's last block has reset the state
+  return 0;
+}
+
+int frontend_clean(const FrontendState& st, FrontendHost* host, cudaStream_t stream) {
+  if (host != nullptr && !host->dirty) return 0;
+  fe_reset_kernel<<<1, 1, 0, stream>>>(st);
+  ADVB_KERNEL_OK("fe_reset", stream);
+  if (host != nullptr) host->dirty = false;
   return 0;
 }
 

@@ -20,6 +20,7 @@ struct FrontendState {
   unsigned long long* gmax_packed;  // batch arg-max of the dB tensor: (ordered float key << 32) | ~index
   int* n_clamped;                   // > 0 iff the top_db floor clamped anything in the last forward
   float* mass_total;                // backward: summed gradient of clamped elements
+  unsigned* done;                   // [2] "last block" counters: fe_dct_t (mass reduction), fe_bwd (state reset)
 };
 
 // Optional epilogue of the backward: the attack's element-wise update rule (fgsm.py:59-60, pgd.py:74-76) applied to each
@@ -34,18 +35,28 @@ struct FusedUpdate {
 
 int frontend_frames(int T);
 int frontend_mass_blocks(int B, int T);
+// Host-side bookkeeping of the device state: the backward's last block resets it, so only a forward that follows another
+// forward needs the reset kernel.
+struct FrontendHost {
+  bool dirty = false;  // a forward has accumulated into the state and no backward has reset it yet
+};
 int frontend_init_constants(float2* tw, cudaStream_t stream);
 int frontend_prepare(const FrontendTables& tb, cudaStream_t stream);
 
 // out[b*clip_stride + offset + f*stride_f + c*stride_c] = coefficient c of frame f
 int frontend_forward(const FrontendTables& tb, const FrontendState& st, const float* x, int B, int T, float* dB,
                      float* out, long long clip_stride, long long stride_f, long long stride_c, long long offset,
-                     cudaStream_t stream);
+                     cudaStream_t stream, float2* spec = nullptr, FrontendHost* host = nullptr);
 // gcoef read through the same kind of strides (no offset: pass the shifted pointer); gd: (B,F,128) scratch for the
 // gradient of the dB tensor; gx (B,T)
 int frontend_backward(const FrontendTables& tb, const FrontendState& st, const float* x, int B, int T,
                       const float* dB, const float* gcoef, long long g_clip_stride, long long g_stride_f,
                       long long g_stride_c, float* mass_partial, float* gd, float* gx, cudaStream_t stream,
-                      const FusedUpdate* upd = nullptr);
+                      const FusedUpdate* upd = nullptr, const float2* spec = nullptr, FrontendHost* host = nullptr);
+// reset the state now if a forward left it dirty (before a captured loop whose body assumes a clean state)
+int frontend_clean(const FrontendState& st, FrontendHost* host, cudaStream_t stream);
+// floats of the optional packed-spectrum buffer (B clips): `spec` of frontend_forward (written) / frontend_backward (read
+// instead of recomputing the STFT); both calls must then see the same waveform
+size_t frontend_spec_floats(int B, int T);
 
 }  // namespace advb

@@ -94,13 +94,18 @@ __global__ void __launch_bounds__(256) gemm_kernel(const float* __restrict__ A, 
 
 // Pack one BLSTM layer: wihT [160][640] (col = dir*320 + gate row), bias [640] = b_ih + b_hh,
 // whhT [2][80][320], wih_cat [640][160], whh [2][320][80] (straight copies of the live tensors).
-__global__ void lstm_pack_kernel(LstmWeights w, LstmPacked p, int I) {
+// perm_wf > 0: the layer's input arrives in the convolution's NHWC order (index w * C + c, C = I / perm_wf) instead of the
+// reference's (c * Wf + w) of lcnn.py:196-199: the input-projection weights are permuted here, once per call, so that
+// the block output feeds the GEMM as it is and the input gradient lands in the block's gradient buffer directly (the
+// feats_gather / feats_scatter kernels of every iteration are gone).
+__global__ void lstm_pack_kernel(LstmWeights w, LstmPacked p, int I, int perm_wf) {
   const int tid = blockIdx.x * blockDim.x + threadIdx.x, nt = gridDim.x * blockDim.x;
   for (int i = tid; i < 2 * G4 * I; i += nt) {
     const int k = i % I, j = (i / I) % G4, d = i / (I * G4);
     const float v = (d == 0 ? w.w_ih[0] : w.w_ih[1])[(size_t)j * I + k];
-    p.wihT[(size_t)k * (2 * G4) + d * G4 + j] = v;
-    p.wih_cat[(size_t)(d * G4 + j) * I + k] = v;
+    const int kp = perm_wf > 0 ? (k % perm_wf) * (I / perm_wf) + k / perm_wf : k;
+    p.wihT[(size_t)kp * (2 * G4) + d * G4 + j] = v;
+    p.wih_cat[(size_t)(d * G4 + j) * I + kp] = v;
   }
   for (int i = tid; i < 2 * G4 * HID; i += nt) {
     const int k = i % HID, j = (i / HID) % G4, d = i / (HID * G4);
@@ -314,15 +319,17 @@ __global__ void feats_scatter_kernel(const float* __restrict__ gfeats, float* __
 }
 
 // logits[b] = w . mean_t(l2 + feats) + bias   (lcnn.py:205)
+// feats is read at index `kp`: k itself, or its position in the NHWC block output (perm_wf > 0, see lstm_pack_kernel)
 __global__ void __launch_bounds__(160) head_fwd_kernel(const float* __restrict__ l2, const float* __restrict__ feats,
                                                         const float* __restrict__ w, const float* __restrict__ bias,
-                                                        float* __restrict__ logits, int L) {
+                                                        float* __restrict__ logits, int L, int perm_wf) {
   __shared__ float s_red[5];
   const int b = blockIdx.x, k = threadIdx.x;
+  const int kp = perm_wf > 0 ? (k % perm_wf) * (160 / perm_wf) + k / perm_wf : k;
   float s = 0.f;
   for (int t = 0; t < L; ++t) {
-    const size_t o = ((size_t)b * L + t) * 160 + k;
-    s += l2[o] + feats[o];
+    const size_t o = ((size_t)b * L + t) * 160;
+    s += l2[o + k] + feats[o + kp];
   }
   float v = (s / (float)L) * w[k];
   v = warp_sum(v);
@@ -334,8 +341,10 @@ __global__ void __launch_bounds__(160) head_fwd_kernel(const float* __restrict__
 // d loss / d logit, then d/d(l2) = d/d(feats residual) = g_o * w / L for every time step.
 __global__ void __launch_bounds__(160) head_bwd_kernel(const float* __restrict__ logits, const long long* __restrict__ y,
                                                         const float* __restrict__ w, float* __restrict__ dl2, int L,
-                                                        int mode, float inv_n, const float* __restrict__ coef) {
+                                                        int mode, float inv_n, const float* __restrict__ coef,
+                                                        float* __restrict__ dfeat_add, int perm_wf) {
   const int b = blockIdx.x, k = threadIdx.x;
+  const int kp = perm_wf > 0 ? (k % perm_wf) * (160 / perm_wf) + k / perm_wf : k;
   float go = 1.0f;
   if (mode == 2) go = coef[b];
   if (mode == 0) {
@@ -345,6 +354,8 @@ __global__ void __launch_bounds__(160) head_bwd_kernel(const float* __restrict__
   }
   const float v = go * w[k] / (float)L;
   for (int t = 0; t < L; ++t) dl2[((size_t)b * L + t) * 160 + k] = v;
+  if (dfeat_add != nullptr)  // the same vector for the residual branch, in the feature buffer's own order
+    for (int t = 0; t < L; ++t) dfeat_add[((size_t)b * L + t) * 160 + kp] = v;
 }
 
 }  // namespace
@@ -374,8 +385,8 @@ int gemm(const float* A, const float* Bm, const float* bias, const float* Cadd, 
   return 0;
 }
 
-int lstm_pack(const LstmWeights& w, const LstmPacked& p, cudaStream_t stream) {
-  lstm_pack_kernel<<<64, 256, 0, stream>>>(w, p, 160);
+int lstm_pack(const LstmWeights& w, const LstmPacked& p, cudaStream_t stream, int perm_wf) {
+  lstm_pack_kernel<<<64, 256, 0, stream>>>(w, p, 160, perm_wf);
   ADVB_KERNEL_OK("lstm_pack", stream);
   return 0;
 }
@@ -412,14 +423,14 @@ int feats_scatter(const float* gfeats, float* gact, int B, int L, int Wf, int C,
 }
 
 int head_forward(const float* l2, const float* feats, const float* w, const float* bias, float* logits, int B, int L,
-                 cudaStream_t stream) {
-  head_fwd_kernel<<<B, 160, 0, stream>>>(l2, feats, w, bias, logits, L);
+                 cudaStream_t stream, int perm_wf) {
+  head_fwd_kernel<<<B, 160, 0, stream>>>(l2, feats, w, bias, logits, L, perm_wf);
   ADVB_KERNEL_OK("head_fwd", stream);
   return 0;
 }
 int head_backward(const float* logits, const long long* y, const float* w, float* dl2, int B, int L, int mode,
-                  int n_global, cudaStream_t stream, const float* coef) {
-  head_bwd_kernel<<<B, 160, 0, stream>>>(logits, y, w, dl2, L, mode, 1.0f / (float)n_global, coef);
+                  int n_global, cudaStream_t stream, const float* coef, float* dfeat_add, int perm_wf) {
+  head_bwd_kernel<<<B, 160, 0, stream>>>(logits, y, w, dl2, L, mode, 1.0f / (float)n_global, coef, dfeat_add, perm_wf);
   ADVB_KERNEL_OK("head_bwd", stream);
   return 0;
 }

@@ -21,7 +21,8 @@ struct LstmPacked {
 int rnn_init();
 int gemm(const float* A, const float* Bm, const float* bias, const float* Cadd, float* C, int M, int N, int K,
          cudaStream_t stream, const char* tag = "gemm");
-int lstm_pack(const LstmWeights& w, const LstmPacked& p, cudaStream_t stream);
+// perm_wf > 0: the layer input is the NHWC block output (index w * C + c) instead of the reference's c * Wf + w order
+int lstm_pack(const LstmWeights& w, const LstmPacked& p, cudaStream_t stream, int perm_wf = 0);
 // x (B,L,160) -> hout (B,L,160); gates (B,L,640) and cs (B,L,2,80) are saved for backward
 int blstm_forward(const LstmPacked& p, const float* x, float* gates, float* hout, float* cs, int B, int L,
                   cudaStream_t stream);
@@ -31,9 +32,10 @@ int blstm_backward(const LstmPacked& p, float* gates, const float* dout, const f
 int feats_gather(const float* act, float* feats, int B, int L, int Wf, int C, cudaStream_t stream);
 int feats_scatter(const float* gfeats, float* gact, int B, int L, int Wf, int C, cudaStream_t stream);
 int head_forward(const float* l2, const float* feats, const float* w, const float* bias, float* logits, int B, int L,
-                 cudaStream_t stream);
+                 cudaStream_t stream, int perm_wf = 0);
 // mode 0: d mean-CE / d logit = 2 (sigmoid(2 o) - y) / n_global ; mode 1: 1 ; mode 2: coef[b] (caller-supplied seed)
+// dfeat_add (nullable): the same gradient for the residual feature branch, written in the feature buffer's order (perm_wf)
 int head_backward(const float* logits, const long long* y, const float* w, float* dl2, int B, int L, int mode,
-                  int n_global, cudaStream_t stream, const float* coef = nullptr);
+                  int n_global, cudaStream_t stream, const float* coef = nullptr, float* dfeat_add = nullptr, int perm_wf = 0);
 
 }  // namespace advb
