@@ -53,6 +53,7 @@ struct P3Args {
   float* gin;
   int passes;
   FastDiv dTiles, dWp, dW, dWo;
+  long long* prof;  // optional (ADVB_P3_PROF=1): per-phase cycle counts of CTA 0 (worker thread 0, MMA warp leader)
 };
 
 // HS ("horizontal scatter", backward only): the MMA computes Z[q][dx][ci] = sum_dy sum_co g[q + (dy-1) Wp][co] Wt[dy][dx][co][ci]
@@ -159,22 +160,34 @@ __global__ void __launch_bounds__(P3Cfg<KTOT, NOUT, POOL, BWD, HS>::PT, 1) conv_
     // ================= MMA warp =================
     const bool leader = elect_one();
     int u_glob = 0, s_glob = 0, it = 0;
+    const bool mprof = a.prof != nullptr && blockIdx.x == 0 && leader;
+    long long mc[3] = {0, 0, 0}, m_last = clock64();
+#define P3MPROF(k)                    \
+  if (mprof) {                        \
+    const long long now_ = clock64(); \
+    mc[k] += now_ - m_last;           \
+    m_last = now_;                    \
+  }
     for (int tile = blockIdx.x; tile < a.n_tiles; tile += gridDim.x, ++it) {
       int b, y0, rows, nM;
       tile_geom(tile, b, y0, rows, nM);
       const uint32_t dbase = tmem + (uint32_t)(it & 1) * NM3 * Cfg::NSTRIDE;
 #pragma unroll 1
       for (int kc = 0; kc < NKC; ++kc, ++u_glob) {
+        P3MPROF(2)
         mbar_wait(&bar_band_full, (uint32_t)(u_glob & 1));
         tc_fence_after();
+        P3MPROF(0)
         const uint32_t a_hi_addr = smem_u32(band + (DB ? (size_t)(u_glob & 1) * Cfg::BUF_BYTES : 0));
         const uint32_t a_lo_addr = a_hi_addr + BR * 128;
         const int kvalid = (KTOT - 32 * kc) >= 32 ? 32 : (KTOT - 32 * kc);
 #pragma unroll 1
         for (int tap = 0; tap < NTAP; ++tap, ++s_glob) {
           const int slot = s_glob % NST;
+          P3MPROF(2)
           mbar_wait(&bar_wfull[slot], (uint32_t)((s_glob / NST) & 1));
           tc_fence_after();
+          P3MPROF(1)
           const uint32_t w_hi = smem_u32(wring + (size_t)slot * Cfg::SLICE_BYTES), w_lo = w_hi + NMMA * 128;
           const int dy = HS ? tap : tap / 3, dx = HS ? 1 : tap - dy * 3;  // HS: vertical taps only, centre column
           const uint32_t row_off = (uint32_t)(dy * Wp + dx) * 128u;
@@ -203,6 +216,12 @@ __global__ void __launch_bounds__(P3Cfg<KTOT, NOUT, POOL, BWD, HS>::PT, 1) conv_
         __syncwarp();
       }
     }
+    P3MPROF(2)
+    if (mprof) {
+      a.prof[8] = mc[0];
+      a.prof[9] = mc[1];
+      a.prof[10] = mc[2];
+    }
   } else {
     // ================= worker warps =================
     const int c4 = tid & 7, r0 = tid >> 3;  // channel group; first band row (rows r0 + (PW / 8) u)
@@ -211,6 +230,37 @@ __global__ void __launch_bounds__(P3Cfg<KTOT, NOUT, POOL, BWD, HS>::PT, 1) conv_
     uchar4 rc[NI_MAX];
     unsigned rok = 0;  // bit u: item u is a real element (loads stay RAW in registers until convert)
     unsigned char rwant[NI_MAX];
+    // Backward: the pixel a band row holds does not depend on the tile beyond its first image row y0 - band row r >= 1 is padded
+    // pixel (y0 + (r - 1) / Wp, (r - 1) % Wp) - so each item's column, pooled-column offset and row offset are computed ONCE per
+    // kernel (the per-unit index math - a division, 64-bit address arithmetic and five range checks per item - was 46 % of the
+    // worker time of the block-2 backward: ADVB_P3_PROF phase counters, profiles/r02_p3_phases.md).
+    int geo[BWD ? NI_MAX : 1];  // dy + 2 (bits 0-4) | x valid (bit 5) | x parity (bit 6) | pooled-column element offset (bits 8..)
+    if (BWD) {
+      constexpr int Ch = KTOT / 2;
+#pragma unroll
+      for (int u = 0; u < NI_MAX; ++u) {
+        const int r = r0 + RSTEP * u;
+        const int rr = r > 0 ? r - 1 : 0;
+        const int dyp = fdiv(rr, a.dWp), xp = rr - dyp * Wp;
+        const int x = xp - 1;
+        const int px = POOL ? (x >> 1) : x;
+        const bool xok = r > 0 && x >= 0 && x < a.W && px < a.Wo;
+        geo[u] = ((dyp + 1) & 31) | (xok ? 32 : 0) | ((x & 1) << 6) | ((xok ? px * Ch : 0) << 8);
+      }
+    }
+
+    // BatchNorm(eval) scale of this thread's channel group, per chunk (was a dependent global load at the head of every convert)
+    float4 sc_kc[BWD ? NKC : 1];
+    if (BWD) {
+      constexpr int Ch = KTOT / 2;
+#pragma unroll
+      for (int k = 0; k < NKC; ++k) {
+        const int ch = 32 * k + 4 * c4;
+        sc_kc[k] = make_float4(1.f, 1.f, 1.f, 1.f);
+        if (a.bn_invstd != nullptr && ch < KTOT) sc_kc[k] = __ldg(reinterpret_cast<const float4*>(a.bn_invstd + (ch >= Ch ? ch - Ch : ch)));
+      }
+    }
+    const uint32_t off0 = sw128_chunk(r0, c4);  // band row r0 + 32 u keeps r0's swizzle phase: its chunk sits u * 4096 bytes further
 
     auto issue_loads = [&](int tile, int kc) {
       int b, y0, rows, nM;
@@ -224,21 +274,20 @@ __global__ void __launch_bounds__(P3Cfg<KTOT, NOUT, POOL, BWD, HS>::PT, 1) conv_
         constexpr int Ch = KTOT / 2;
         const int half = ch >= Ch ? 1 : 0;
         const int c = ch - half * Ch;
+        const float* gbase = a.gout + (size_t)b * a.Ho * a.Wo * Ch + c;
+        const unsigned char* cbase = a.codes_in + (size_t)b * a.Ho * a.Wo * Ch + c;
+        const int row_elems = a.Wo * Ch;
 #pragma unroll
         for (int u = 0; u < NI_MAX; ++u) {
           const int r = r0 + RSTEP * u;
-          const int q = q_lo + r;
-          bool ok = ch_ok && r < band_used && q >= 0 && q < npix;
-          const int qq = ok ? q : 0;
-          const int yp = fdiv(qq, a.dWp), xp = qq - yp * Wp;
-          const int y = yp - 1, x = xp - 1;
-          ok = ok && y >= 0 && y < a.H && x >= 0 && x < a.W;
-          const int py = POOL ? (y >> 1) : y, px = POOL ? (x >> 1) : x;
-          ok = ok && py < a.Ho && px < a.Wo;
-          const size_t o = ok ? (((size_t)b * a.Ho + py) * a.Wo + px) * Ch + c : 0;
-          rv[u] = __ldg(reinterpret_cast<const float4*>(a.gout + o));
-          rc[u] = __ldg(reinterpret_cast<const uchar4*>(a.codes_in + o));
-          rwant[u] = (unsigned char)(ok ? ((POOL ? (((y & 1) << 1) | (x & 1)) : 0) | (half << 2)) : 0xff);
+          const int g = geo[u];
+          const int y = y0 + (g & 31) - 2;
+          const int py = POOL ? (y >> 1) : y;
+          const bool ok = ch_ok && (g & 32) != 0 && r < band_used && y >= 0 && y < a.H && py < a.Ho;
+          const int o = ok ? py * row_elems + (g >> 8) : 0;
+          rv[u] = __ldg(reinterpret_cast<const float4*>(gbase + o));
+          rc[u] = __ldg(reinterpret_cast<const uchar4*>(cbase + o));
+          rwant[u] = (unsigned char)(ok ? ((POOL ? (((y & 1) << 1) | ((g >> 6) & 1)) : 0) | (half << 2)) : 0xff);
         }
       } else {
         const float* inb = a.in + (size_t)b * npix * KTOT + ch;
@@ -260,10 +309,10 @@ __global__ void __launch_bounds__(P3Cfg<KTOT, NOUT, POOL, BWD, HS>::PT, 1) conv_
       unsigned char* a_lo = a_hi + BR * 128;
       const int band_used = nM * 128 + 2 * (Wp + 1);
       float4 sc = make_float4(1.f, 1.f, 1.f, 1.f);
-      if (BWD && a.bn_invstd != nullptr) {
-        constexpr int Ch = KTOT / 2;
-        const int ch = 32 * kc + 4 * c4;
-        if (ch < KTOT) sc = __ldg(reinterpret_cast<const float4*>(a.bn_invstd + (ch >= Ch ? ch - Ch : ch)));
+      if (BWD) {
+#pragma unroll
+        for (int k = 0; k < NKC; ++k)
+          if (k == kc) sc = sc_kc[k];
       }
 #pragma unroll
       for (int u = 0; u < NI_MAX; ++u) {
@@ -284,7 +333,7 @@ __global__ void __launch_bounds__(P3Cfg<KTOT, NOUT, POOL, BWD, HS>::PT, 1) conv_
           split_tf32(v.y, hi.y, lo.y);
           split_tf32(v.z, hi.z, lo.z);
           split_tf32(v.w, hi.w, lo.w);
-          const uint32_t off = sw128_chunk(r, c4);
+          const uint32_t off = off0 + (uint32_t)u * (RSTEP * 128);
           *reinterpret_cast<float4*>(a_hi + off) = hi;
           *reinterpret_cast<float4*>(a_lo + off) = lo;
         }
@@ -408,6 +457,14 @@ __global__ void __launch_bounds__(P3Cfg<KTOT, NOUT, POOL, BWD, HS>::PT, 1) conv_
 
     // ---- persistent loop over units (tile, chunk) ----
     int tile = blockIdx.x, kc = 0, u_glob = 0, it = 0, prev_tile = -1;
+    const bool prof = a.prof != nullptr && blockIdx.x == 0 && tid == 0;
+    long long pc[6] = {0, 0, 0, 0, 0, 0}, t_last = clock64();
+#define P3PROF(k)                     \
+  if (prof) {                         \
+    const long long now_ = clock64(); \
+    pc[k] += now_ - t_last;           \
+    t_last = now_;                    \
+  }
     if (tile < a.n_tiles) issue_loads(tile, 0);
     // unit u commits bar_unit_done[DB ? u & 1 : 0]; its k-th completion there has parity k & 1
     auto wait_unit = [&](int u) {
@@ -417,12 +474,16 @@ __global__ void __launch_bounds__(P3Cfg<KTOT, NOUT, POOL, BWD, HS>::PT, 1) conv_
     };
     while (tile < a.n_tiles) {
       // the band buffer this unit overwrites must have been read completely: unit u-1 (single buffer) / u-2 (double)
+      P3PROF(5)
       if (u_glob >= (DB ? 2 : 1)) wait_unit(u_glob - (DB ? 2 : 1));
+      P3PROF(0)
       convert_store(tile, kc, DB ? (u_glob & 1) : 0);
+      P3PROF(1)
       fence_proxy_async();
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&bar_band_full);
+      P3PROF(2)
       // next unit
       int ntile = tile, nkc = kc + 1;
       if (nkc == NKC) {
@@ -430,9 +491,12 @@ __global__ void __launch_bounds__(P3Cfg<KTOT, NOUT, POOL, BWD, HS>::PT, 1) conv_
         ntile = tile + gridDim.x;
       }
       if (ntile < a.n_tiles) issue_loads(ntile, nkc);
+      P3PROF(3)
       if (kc == 0 && it > 0) {  // overlaps the MMAs of this tile
         if (DB) wait_unit(u_glob - 1);  // last chunk of the previous tile (already awaited when single-buffered)
+        P3PROF(0)
         epilogue(prev_tile, (it - 1) & 1);
+        P3PROF(4)
       }
       if (nkc == 0) {
         prev_tile = tile;
@@ -445,6 +509,10 @@ __global__ void __launch_bounds__(P3Cfg<KTOT, NOUT, POOL, BWD, HS>::PT, 1) conv_
     if (it > 0) {
       wait_unit(u_glob - 1);
       epilogue(prev_tile, (it - 1) & 1);
+    }
+    if (prof) {
+      for (int k = 0; k < 6; ++k) a.prof[k] = pc[k];
+      a.prof[6] = it;
     }
   }
   tc_fence_before();
@@ -489,8 +557,21 @@ int launch_p3(P3Args a, const char* tag, cudaStream_t stream) {
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev);
   const int grid = a.n_tiles < n_sm ? a.n_tiles : n_sm;
+  static long long* prof_buf = nullptr;
+  static const bool want_prof = getenv("ADVB_P3_PROF") != nullptr;
+  if (want_prof && prof_buf == nullptr) cudaMalloc(reinterpret_cast<void**>(&prof_buf), 16 * sizeof(long long));
+  a.prof = want_prof ? prof_buf : nullptr;
   kern<<<grid, Cfg::PT, Cfg::SMEM, stream>>>(a);
   ADVB_KERNEL_OK(tag, stream);
+  if (want_prof) {  // diagnostic only: synchronises
+    long long hp[16];
+    cudaStreamSynchronize(stream);
+    cudaMemcpy(hp, prof_buf, sizeof(hp), cudaMemcpyDeviceToHost);
+    const long long n = hp[6] > 0 ? hp[6] : 1;
+    fprintf(stderr, "[p3 %s] NST %d DB %d tiles/cta %lld | worker cycles/tile: wait_unit %lld convert %lld fence+arrive %lld issue_loads %lld "
+                    "epilogue %lld other %lld | mma warp: wait_band %lld wait_w %lld issue %lld\n",
+            tag, Cfg::NST, (int)Cfg::DB, hp[6], hp[0] / n, hp[1] / n, hp[2] / n, hp[3] / n, hp[4] / n, hp[5] / n, hp[8] / n, hp[9] / n, hp[10] / n);
+  }
   return 0;
 }
 
