@@ -182,11 +182,7 @@ __global__ void __launch_bounds__(TT, 1) conv0_toeplitz_kernel(C0TArgs a) {
         __syncwarp();
       }
     }
-    tc_fence_before();
-    __syncthreads();
-    return;
-  }
-
+  } else {
   // ================= worker warps =================
   const int Hp = a.H + 4, Wp = a.W + 4;
   float4 rv[5];  // the next strip's 20 coefficients of this thread's frame, kept raw until convert_store
@@ -321,6 +317,9 @@ __global__ void __launch_bounds__(TT, 1) conv0_toeplitz_kernel(C0TArgs a) {
       if (lane == 0) mbar_arrive(&bar_free[acc]);
     }
   }
+  }  // worker warps
+  // one barrier instruction for every warp of the CTA (compute-sanitizer synccheck flags role branches that end in their own
+  // __syncthreads as divergent barriers)
   tc_fence_before();
   __syncthreads();
   if (warp == 0) tmem_dealloc<512>(tmem);

@@ -168,10 +168,7 @@ conv_light_kernel(LArgs a) {
       if (leader) mma_commit(&bar_mma[buf]);
       __syncwarp();
     }
-    tc_fence_before();
-    __syncthreads();  // matches the workers' final barrier
-    return;
-  }
+  } else {
   // ================= worker warps =================
 
   // ---- per-thread item geometry: 4 band rows (m = tid/8 + 32 u), one 16-byte channel group c4 of every chunk ----
@@ -456,6 +453,9 @@ conv_light_kernel(LArgs a) {
     tc_fence_after();
     epilogue(prev_tile, buf);
   }
+  }  // worker warps
+  // one barrier instruction for every warp of the CTA (compute-sanitizer synccheck reports role branches that each end in
+  // their own __syncthreads as divergent barriers)
   tc_fence_before();
   __syncthreads();
   if (warp == 0) tmem_dealloc<Cfg::TMEM_COLS>(tmem);

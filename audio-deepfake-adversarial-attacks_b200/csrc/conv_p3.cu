@@ -105,7 +105,10 @@ __global__ void __launch_bounds__(P3Cfg<KTOT, NOUT, POOL, BWD, HS>::PT, 1) conv_
   unsigned char* wring = band + Cfg::BAND_BYTES;     // BUF_BYTES is a multiple of 1024: stays 1024-byte aligned
   float* stage = reinterpret_cast<float*>(wring + (size_t)NST * Cfg::SLICE_BYTES);
   unsigned long long* flags = reinterpret_cast<unsigned long long*>(stage + (size_t)NM3 * 128 * SS);
-  __shared__ uint64_t bar_wfull[NST], bar_wempty[NST], bar_band_full, bar_unit_done[2];
+  // bar_band_full[b]: one per band buffer.  With a single barrier and two buffers the workers could complete the phase of unit
+  // u + 1 before the MMA warp had looked at the phase of unit u (parity waits cannot tell two completed phases from none:
+  // compute-sanitizer synccheck, "missing wait"); per buffer, unit u + 2 is staged only after the MMAs of unit u completed.
+  __shared__ uint64_t bar_wfull[NST], bar_wempty[NST], bar_band_full[2], bar_unit_done[2];
   __shared__ uint32_t tmem_base_s;
   __shared__ float s_bias[BWD ? 1 : NOUT];
 
@@ -119,7 +122,8 @@ __global__ void __launch_bounds__(P3Cfg<KTOT, NOUT, POOL, BWD, HS>::PT, 1) conv_
       mbar_init(&bar_wfull[s], 1);
       mbar_init(&bar_wempty[s], 1);
     }
-    mbar_init(&bar_band_full, PW / 32);
+    mbar_init(&bar_band_full[0], PW / 32);
+    mbar_init(&bar_band_full[1], PW / 32);
     mbar_init(&bar_unit_done[0], 1);
     mbar_init(&bar_unit_done[1], 1);
     fence_barrier_init();
@@ -175,7 +179,7 @@ __global__ void __launch_bounds__(P3Cfg<KTOT, NOUT, POOL, BWD, HS>::PT, 1) conv_
 #pragma unroll 1
       for (int kc = 0; kc < NKC; ++kc, ++u_glob) {
         P3MPROF(2)
-        mbar_wait(&bar_band_full, (uint32_t)(u_glob & 1));
+        mbar_wait(&bar_band_full[DB ? (u_glob & 1) : 0], (uint32_t)(DB ? ((u_glob >> 1) & 1) : (u_glob & 1)));
         tc_fence_after();
         P3MPROF(0)
         const uint32_t a_hi_addr = smem_u32(band + (DB ? (size_t)(u_glob & 1) * Cfg::BUF_BYTES : 0));
@@ -482,7 +486,7 @@ __global__ void __launch_bounds__(P3Cfg<KTOT, NOUT, POOL, BWD, HS>::PT, 1) conv_
       fence_proxy_async();
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(&bar_band_full);
+      if (lane == 0) mbar_arrive(&bar_band_full[DB ? (u_glob & 1) : 0]);
       P3PROF(2)
       // next unit
       int ntile = tile, nkc = kc + 1;

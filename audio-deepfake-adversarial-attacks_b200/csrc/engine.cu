@@ -120,6 +120,9 @@ struct advb_handle {
   float *feats = nullptr, *l1 = nullptr, *l2 = nullptr, *gates1 = nullptr, *gates2 = nullptr, *cs1 = nullptr,
         *cs2 = nullptr, *dl2 = nullptr, *dl1 = nullptr, *dfeats = nullptr, *logits = nullptr;
   LstmPacked lp[2]{};
+  unsigned char* lp_tc[2][2] = {{nullptr, nullptr}, {nullptr, nullptr}};  // tcgen05 images of the BLSTM input projections
+  int lstm_tc = 0;  // 1 = BLSTM input projections on the tcgen05 GEMM (3xTF32; measured 21 / 40 us vs 30 / 37 us: the persistent
+                    // GEMM's fixed costs eat the gain at 0.66 GFLOP), 0 = fp32 SIMT GEMM (default)
 
   // SpecRNet
   SrBlock sr[3]{};
@@ -325,6 +328,8 @@ int build_lcnn(advb_handle* h) {
     ADVB_TRY(h->alloc(&h->lp[l].whhT, 2 * 80 * 320));
     ADVB_TRY(h->alloc(&h->lp[l].wih_cat, 640 * 160));
     ADVB_TRY(h->alloc(&h->lp[l].whh, 2 * 320 * 80));
+    ADVB_TRY(h->alloc(&h->lp_tc[l][0], lstm_tc_fwd_bytes()));
+    ADVB_TRY(h->alloc(&h->lp_tc[l][1], lstm_tc_bwd_bytes()));
   }
   ADVB_TRY(rnn_init());
   return 0;
@@ -358,6 +363,8 @@ int prepare_lcnn(advb_handle* h, cudaStream_t st) {
       w.b_ih[d] = h->t(p + "bias_ih" + sfx);
       w.b_hh[d] = h->t(p + "bias_hh" + sfx);
     }
+    h->lp[l].tc_fwd = (h->lstm_tc && h->conv_path == 0) ? h->lp_tc[l][0] : nullptr;
+    h->lp[l].tc_bwd = (h->lstm_tc && h->conv_path == 0) ? h->lp_tc[l][1] : nullptr;
     ADVB_TRY(lstm_pack(w, h->lp[l], st, l == 0 ? h->Wf : 0));  // layer 0 reads the last block's NHWC output as it is
   }
   return 0;
@@ -881,6 +888,9 @@ int advb_set_option(advb_handle* h, const char* key, int value) {
   } else if (k == "conv0_fwd") {
     ADVB_CHECK(value == 0 || value == 1, "conv0_fwd: 0 = Toeplitz GEMM without im2col, 1 = im2col GEMM");
     h->conv0_fwd = value;
+  } else if (k == "lstm_tc") {
+    ADVB_CHECK(value == 0 || value == 1, "lstm_tc: 1 = BLSTM input projections on the tcgen05 GEMM, 0 = fp32 SIMT GEMM");
+    h->lstm_tc = value;
   } else if (k == "fe_spec") {
     ADVB_CHECK(value == 0 || value == 1, "fe_spec: 1 = the frontend backward reads the forward's stored spectra, 0 = recomputes the STFT");
     h->fe_spec = value;
@@ -948,7 +958,7 @@ std::string graph_key(const advb_handle* h, const advb_attack_desc* atk, int B, 
   return std::to_string(atk->kind) + "|" + std::to_string(B) + "|" + bits(atk->eps) + "|" + bits(atk->alpha) + "|" +
          bits(atk->eps_div) + "|" + std::to_string(n_global) + "|" + std::to_string(fused) + "|" +
          std::to_string(h->conv_path) + "|" + std::to_string(h->tf32_passes) + "|" + std::to_string(h->conv_sched) + "|" +
-         std::to_string(h->conv0_bwd) + "|" + std::to_string(h->conv0_fwd) + "|" + std::to_string(h->fe_spec) + "|" +
+         std::to_string(h->conv0_bwd) + "|" + std::to_string(h->conv0_fwd) + "|" + std::to_string(h->fe_spec) + "|" + std::to_string(h->lstm_tc) + "|" +
          std::to_string(h->bind_epoch);
 }
 

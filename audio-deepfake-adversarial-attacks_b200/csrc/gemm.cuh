@@ -32,6 +32,7 @@ struct GemmArgs {
   GemmW w;                                // SIMT path reads the live weights through this view
   const unsigned char* wpack = nullptr;   // tcgen05 path: image produced by gemm_pack() from the same view
   int N = 0;                              // multiple of 128
+  int n_store = 0;                        // > 0: only columns n < n_store (a multiple of 16) are stored (N padded up from n_store)
   // ---- row space: r = clip * Tp + pad + t, t in [0, Tv) is a valid row; other rows are never stored ----
   int Tp = 1, pad = 0, Tv = 1;
   // ---- epilogue, in this order (every per-column vector is indexed by n in [0, N); every matrix pointer already points

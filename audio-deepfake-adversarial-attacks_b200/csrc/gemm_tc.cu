@@ -133,6 +133,7 @@ __device__ __forceinline__ void epi_apply(const GemmArgs& a, int r, int clip, in
 // thread reads / writes 64 contiguous bytes of its own row (4 x 16 B; the warp touches 32 rows per instruction, L2 merges
 // the sectors), per-column vectors are warp-uniform broadcast loads, and the ReLU / gate masks move as one 16-byte word.
 __device__ __forceinline__ void epi_direct16(const GemmArgs& a, int r, int clip, int n0, const uint32_t (&v)[16]) {
+  if (a.n_store > 0 && n0 >= a.n_store) return;  // padding columns of a GEMM whose true N is not a multiple of 128
   float4 addv[4];
   uint4 gm = make_uint4(0, 0, 0, 0), gm2 = make_uint4(0, 0, 0, 0);
   const float* addp = a.add != nullptr ? a.add + (size_t)r * a.ld_add + n0

@@ -11,6 +11,8 @@
 // second small GEMM.  PyTorch gate order i,f,g,o; zero initial state.
 #include "rnn.cuh"
 
+#include "gemm.cuh"
+
 namespace advb {
 
 namespace {
@@ -385,15 +387,44 @@ int gemm(const float* A, const float* Bm, const float* bias, const float* Cadd, 
   return 0;
 }
 
+size_t lstm_tc_fwd_bytes() { return gemm_pack_bytes(2 * G4, 160, 1); }
+size_t lstm_tc_bwd_bytes() { return gemm_pack_bytes(256, 2 * G4, 1); }
+
 int lstm_pack(const LstmWeights& w, const LstmPacked& p, cudaStream_t stream, int perm_wf) {
   lstm_pack_kernel<<<64, 256, 0, stream>>>(w, p, 160, perm_wf);
   ADVB_KERNEL_OK("lstm_pack", stream);
+  if (p.tc_fwd != nullptr) {  // the two input projections as tcgen05 3xTF32 GEMMs: views of the (already permuted) wih_cat [640][160]
+    GemmW f;
+    f.w = p.wih_cat, f.s_n = 160, f.s_k = 1, f.n_valid = 2 * G4, f.k_valid = 160;
+    ADVB_TRY(gemm_pack(f, 2 * G4, 160, 1, p.tc_fwd, stream));
+    GemmW b;
+    b.w = p.wih_cat, b.s_n = 1, b.s_k = 160, b.n_valid = 160, b.k_valid = 2 * G4;
+    ADVB_TRY(gemm_pack(b, 256, 2 * G4, 1, p.tc_bwd, stream));
+  }
   return 0;
+}
+
+// The input projections are 0.66 GFLOP GEMMs (3 200 x 640 x 160): 30 / 37 us each on the fp32 SIMT kernel, i.e. 135 us of every
+// PGD iteration; on the persistent tcgen05 GEMM of gemm_tc.cu (3xTF32, fp32-class) they are one wave of 125 / 50 tiles.
+static int lstm_proj_tc(const float* A, int K, const unsigned char* wpack, int N, int n_store, const float* bias, const float* add,
+                        float* out, int M, int passes, cudaStream_t stream, const char* tag) {
+  GemmArgs a;
+  a.A = A, a.lda = K, a.M = M, a.K = K, a.ntap = 1;
+  a.wpack = wpack, a.N = N, a.n_store = n_store;
+  a.Tp = 1, a.pad = 0, a.Tv = 1;
+  a.bias = bias;
+  a.add = add, a.ld_add = n_store > 0 ? n_store : N;
+  a.out = out, a.ldc = n_store > 0 ? n_store : N;
+  a.tag = tag;
+  return gemm_run(a, 0, passes, stream);
 }
 
 int blstm_forward(const LstmPacked& p, const float* x, float* gates, float* hout, float* cs, int B, int L,
                   cudaStream_t stream) {
-  ADVB_TRY(gemm(x, p.wihT, p.bias, nullptr, gates, B * L, 2 * G4, 160, stream, "lstm_inproj_fwd"));
+  if (p.tc_fwd != nullptr)
+    ADVB_TRY(lstm_proj_tc(x, 160, p.tc_fwd, 2 * G4, 0, p.bias, nullptr, gates, B * L, 3, stream, "lstm_inproj_fwd"));
+  else
+    ADVB_TRY(gemm(x, p.wihT, p.bias, nullptr, gates, B * L, 2 * G4, 160, stream, "lstm_inproj_fwd"));
   dim3 grid(cdiv(B, CL), 2);
   lstm_rec_fwd_kernel<<<grid, G4, lstm_rec_fwd_smem(), stream>>>(gates, p.whhT, hout, cs, B, L);
   ADVB_KERNEL_OK("lstm_rec_fwd", stream);
@@ -405,7 +436,10 @@ int blstm_backward(const LstmPacked& p, float* gates, const float* dout, const f
   dim3 grid(cdiv(B, CL), 2);
   lstm_rec_bwd_kernel<<<grid, G4, lstm_rec_bwd_smem(), stream>>>(gates, p.whh, dout, cs, B, L);
   ADVB_KERNEL_OK("lstm_rec_bwd", stream);
-  ADVB_TRY(gemm(gates, p.wih_cat, nullptr, dx_add, dx, B * L, 160, 2 * G4, stream, "lstm_inproj_bwd"));
+  if (p.tc_bwd != nullptr)
+    ADVB_TRY(lstm_proj_tc(gates, 2 * G4, p.tc_bwd, 256, 160, nullptr, dx_add, dx, B * L, 3, stream, "lstm_inproj_bwd"));
+  else
+    ADVB_TRY(gemm(gates, p.wih_cat, nullptr, dx_add, dx, B * L, 160, 2 * G4, stream, "lstm_inproj_bwd"));
   return 0;
 }
 

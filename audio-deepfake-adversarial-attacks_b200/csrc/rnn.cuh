@@ -16,7 +16,12 @@ struct LstmPacked {
   float* whhT;     // [2][80][320]
   float* wih_cat;  // [640][160]
   float* whh;      // [2][320][80]
+  // tcgen05 images of wih_cat for the two input projections (gemm.cuh; null = fp32 SIMT gemm_kernel):
+  unsigned char* tc_fwd;  // gates[r][n] = sum_k x[r][k] wih_cat[n][k]:        N = 640, K = 160
+  unsigned char* tc_bwd;  // dx[r][k]    = sum_n dgates[r][n] wih_cat[n][k]:   N = 160 (padded to 256), K = 640
 };
+size_t lstm_tc_fwd_bytes();
+size_t lstm_tc_bwd_bytes();
 
 int rnn_init();
 int gemm(const float* A, const float* Bm, const float* bias, const float* Cadd, float* C, int M, int N, int K,

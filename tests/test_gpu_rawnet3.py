@@ -9,6 +9,8 @@ The tests pin every segment tightly where that is meaningful - the forward stage
 evaluated AT THE ENGINE'S OWN sinc outputs / fed with the engine's own intermediate gradients - and gate the end-to-end
 quantities with the tolerances the conditioning allows.
 """
+import os
+
 import numpy as np
 import pytest
 import torch
@@ -121,8 +123,21 @@ def test_logits_and_gradient_against_reference_golden(name, conv_path, cuda_devi
     taps["sinc"].retain_grad()
     torch.nn.CrossEntropyLoss()(torch.cat([-o, o], dim=1), y).backward()
     gs = _valid(_stage(eng, "rn_gsinc", B), 2)
-    assert helpers.cosine(gs, taps["sinc"].grad.transpose(1, 2)) > 0.999
-    assert helpers.trimmed_rel_err(gs, taps["sinc"].grad.transpose(1, 2)) < 2e-2
+    gs_ref = taps["sinc"].grad.transpose(1, 2)
+    assert helpers.cosine(gs, gs_ref) > 0.999
+    assert helpers.trimmed_rel_err(gs, gs_ref) < 2e-2
+    # ... and tightly where the filter output is well above the rounding noise of a 251-tap fp32 dot product (~1e-5 absolute:
+    # at |s| >= 0.05, 96 % of the outputs, the 1 / (|s| + 1e-6) factor is known to 2e-4 relative).  What is left there are
+    # the isolated patches behind a ReLU / max-pool winner that two correct fp32 forwards decide differently (measured:
+    # untrimmed 1.8e-2 on the tcgen05 AND on the fp32 FMA path alike); the trimmed error drops them.
+    s_abs = taps["sinc"].detach().transpose(1, 2).abs()
+    well = s_abs >= 0.05
+    assert well.float().mean().item() > 0.95
+    t01, t1, t10 = (helpers.trimmed_rel_err(gs[well], gs_ref[well], drop=d) for d in (0.001, 0.01, 0.10))
+    print(f"rn_gsinc on |s| >= 0.05 [{name}, conv_path {conv_path}]: trimmed relative error {t01:.2e} (0.1 %), {t1:.2e} (1 %), "
+          f"{t10:.2e} (10 %)")
+    assert t10 < 2e-3  # (the unmasked comparison above: 2e-2)
+    assert (torch.sign(gs[well]) == torch.sign(gs_ref[well])).float().mean().item() > 0.995
     # The waveform gradient itself is dominated by the few filter outputs nearest to a zero crossing (|s| ~ 1e-6..1e-5,
     # below the 1e-5 rounding noise of the 251-tap dot product), and InstanceNorm's backward spreads them over every
     # sample: against the reference only its scale is comparable (measured cosine: 0.98 at T = 16 000, 0.1-0.25 at
@@ -132,6 +147,21 @@ def test_logits_and_gradient_against_reference_golden(name, conv_path, cuda_devi
     assert torch.isfinite(g).all()
     ratio = (g.cpu().abs().median() / ref.abs().median()).item()
     assert 0.5 < ratio < 2.0
+    # The yardstick for the waveform gradient is the FLOAT64 run of the reference model (tools/rn_conditioning.py ->
+    # tests/golden/rawnet3_fp64_grad_*.npz).  The reference's own float32 gradient agrees with it in 99.0 % / 98.6 % of the
+    # signs and with cosine 0.906 / -0.085 (T = 16 000 / 64 000; 8 threads and 1 thread alike) - a handful of 1 / (|s| + 1e-6)
+    # terms carry most of the norm.  The engine is held to the same standard: at least as close to float64 as the reference's
+    # float32 runs are (signs decide FGSM / PGD; the norm-dominating terms decide nothing an L-inf attack uses).
+    f64 = np.load(os.path.join(cases.GOLDEN_DIR, name.replace("rawnet3_", "rawnet3_fp64_grad_") + ".npz"))
+    g64 = torch.from_numpy(f64["g64"])
+    sign_ref = min(float(f64["ref32_t8_sign"]), float(f64["ref32_t1_sign"]))
+    sign_eng = (torch.sign(g.cpu().double()) == torch.sign(g64)).double().mean().item()
+    cos_eng, cos_ref = helpers.cosine(g.cpu(), g64), min(float(f64["ref32_t8_cos"]), float(f64["ref32_t1_cos"]))
+    print(f"rawnet3 waveform gradient vs float64 [{name}, conv_path {conv_path}]: signs engine {sign_eng:.4f} / reference fp32 "
+          f"{sign_ref:.4f}; cosine engine {cos_eng:.4f} / reference fp32 {cos_ref:.4f}")
+    assert sign_eng > sign_ref - 0.01
+    if cos_ref > 0.5:  # (T = 64 000: the reference's own cosine with float64 is -0.09 - nothing to hold the engine to)
+        assert cos_eng > cos_ref - 0.1
     # logit-gradient mode (FAB, fab.py:90-105): the CE gradient is its per-clip multiple
     from advb200 import _lib
 

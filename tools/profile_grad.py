@@ -22,6 +22,8 @@ def main():
     ap.add_argument("--calls", type=int, default=2)
     ap.add_argument("--conv-path", type=int, default=0)
     ap.add_argument("--model", default="lcnn", choices=["lcnn", "specrnet", "rawnet3"])
+    ap.add_argument("--samples", type=int, default=bench.T_SAMPLES)
+    ap.add_argument("--attack", action="store_true", help="run a 2-step PGD call (graph replay + fused update) instead of advb_grad")
     args = ap.parse_args()
     from advb200 import engine
 
@@ -31,9 +33,18 @@ def main():
     holder.load_state_dict(state)
     holder = holder.to(dev)
     x, y = bench.synthetic_batch(args.batch, 1002)
-    x, y = x.to(dev), y.to(dev)
-    eng = engine.engine_for(holder, args.batch, bench.T_SAMPLES)
+    x, y = x[:, :args.samples].contiguous().to(dev), y.to(dev)
+    eng = engine.engine_for(holder, args.batch, args.samples)
     eng.set_option("conv_path", args.conv_path)
+    if args.attack:
+        from advb200 import torchattacks as ta
+
+        atk = ta.PGD(holder, eps=0.001, alpha=2 / 255, steps=4) if args.model != "rawnet3" else ta.PGDL2(holder, eps=0.1, alpha=0.2, steps=2)
+        for _ in range(args.calls):
+            adv = atk(x, y)
+        torch.cuda.synchronize()
+        print("attack linf", (adv - x).abs().max().item())
+        return
     for _ in range(args.calls):
         g, logits = eng.grad(x, y)
     torch.cuda.synchronize()

@@ -1,0 +1,19 @@
+#!/bin/bash
+# compute-sanitizer on one gradient evaluation / one short attack call per model: memcheck, racecheck
+# (shared-memory hazards of the hand-rolled mbarrier / TMEM pipelines), synccheck.  Small shapes: the tools slow kernels 10-100x.
+out=gpurun_out/${1:-r02_sanitizer}; mkdir -p $out
+CS=/usr/local/cuda/bin/compute-sanitizer
+run() {  # tool, tag, args...
+  local tool=$1 tag=$2; shift 2
+  timeout 900 $CS --tool $tool --print-limit 5 python tools/profile_grad.py "$@" > $out/${tool}_${tag}.log 2>&1
+  echo "$tool $tag rc=$? : $(grep -E 'ERROR SUMMARY|RACECHECK SUMMARY|hazard|grad norm|attack linf' $out/${tool}_${tag}.log | tr '\n' ' ' | cut -c1-300)"
+}
+run memcheck lcnn --model lcnn --batch 2 --samples 16000 --calls 1
+run memcheck lcnn_attack --model lcnn --batch 2 --samples 16000 --calls 2 --attack
+run racecheck lcnn --model lcnn --batch 2 --samples 16000 --calls 1
+run synccheck lcnn --model lcnn --batch 2 --samples 16000 --calls 1
+run memcheck specrnet --model specrnet --batch 2 --samples 16000 --calls 1
+run racecheck specrnet --model specrnet --batch 2 --samples 16000 --calls 1
+run memcheck rawnet3 --model rawnet3 --batch 1 --samples 16000 --calls 1
+run racecheck rawnet3 --model rawnet3 --batch 1 --samples 16000 --calls 1
+run synccheck rawnet3 --model rawnet3 --batch 1 --samples 16000 --calls 1
