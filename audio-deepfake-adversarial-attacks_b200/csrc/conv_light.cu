@@ -114,6 +114,7 @@ conv_light_kernel(LArgs a) {
   __shared__ uint64_t bar_w, bar_mma[2], bar_full;
   __shared__ uint32_t tmem_base_s;
   __shared__ float s_bias[BWD ? 1 : NOUT];
+  __shared__ float s_bnm[BWD ? 1 : NOUT / 2], s_bni[BWD ? 1 : NOUT / 2];  // BatchNorm(eval) mean / inverse std (0 / 1 without BN)
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int Heff = (!BWD && POOL) ? 2 * a.Ho : a.H;
@@ -126,8 +127,13 @@ conv_light_kernel(LArgs a) {
     fence_barrier_init();
   }
   if (warp == 0) tmem_alloc<Cfg::TMEM_COLS>(&tmem_base_s);
-  if (!BWD)
+  if (!BWD) {
     for (int i = tid; i < NOUT; i += LT) s_bias[i] = __ldg(a.bias + i);
+    for (int i = tid; i < NOUT / 2; i += LT) {
+      s_bnm[i] = a.bn_mean != nullptr ? __ldg(a.bn_mean + i) : 0.f;
+      s_bni[i] = a.bn_mean != nullptr ? __ldg(a.bn_invstd + i) : 1.f;
+    }
+  }
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -278,6 +284,63 @@ conv_light_kernel(LArgs a) {
   // ---- epilogue of one tile: TMEM accumulator `buf` -> staging -> global ----
   auto epilogue = [&](int tile, int buf) {
     const int b = fdiv(tile, a.dTiles), tl = tile - b * a.tiles_per_clip;
+    if (MAP == 0) {
+      // ---- 1x1 blocks (FLAT map), round 2: straight from the tcgen05.ld registers to global memory.  Thread = TMEM lane =
+      // pixel holds every channel of its pixel, so the Max-Feature-Map pair (c, c + C/2), BatchNorm and the code bytes need
+      // no staging tile, no second pass and no barrier; a pixel's channels are one contiguous row of the NHWC output, and a
+      // warp's 32 pixels are consecutive rows.  (The staged version: TMEM -> shared -> barrier -> coalesced copy with its own
+      // index math, ~2x the instructions; these layers moved 35 % of the HBM peak.)
+      const int wq = warp & 3, hsel = warp >> 2;
+      const int r = wq * 32 + lane;
+      const int px = 128 * tl + r;
+      const bool valid = px < a.H * a.W;
+      const uint32_t taddr = tmem + ((uint32_t)(wq * 32) << 16) + buf * Cfg::NSTRIDE;
+      if (BWD) {
+        float* dst = a.gin + ((size_t)b * a.H * a.W + (valid ? px : 0)) * NOUT;
+#pragma unroll 1
+        for (int c0 = hsel * 16; c0 < NOUT; c0 += 32) {
+          uint32_t v[16];
+          tmem_ld16_issue(taddr + c0, v);
+          tmem_ld_wait();
+          if (valid) {
+#pragma unroll
+            for (int j = 0; j < 16; j += 4)
+              *reinterpret_cast<float4*>(dst + c0 + j) = make_float4(__uint_as_float(v[j]), __uint_as_float(v[j + 1]),
+                                                                     __uint_as_float(v[j + 2]), __uint_as_float(v[j + 3]));
+          }
+        }
+      } else {
+        const int p = valid ? px : 0;
+        const int y = fdiv(p, a.dW), x = p - y * a.W;
+        const int Hop = a.Ho + 2 * a.out_pad, Wop = a.Wo + 2 * a.out_pad;
+        float* dst = a.out + (((size_t)b * Hop + y + a.out_pad) * Wop + x + a.out_pad) * CS;
+        unsigned char* cdst = a.codes + ((size_t)b * a.H * a.W + p) * CS;
+#pragma unroll 1
+        for (int c0 = hsel * 16; c0 < CS; c0 += 32) {
+          uint32_t lo[16], hi[16];
+          tmem_ld16_issue(taddr + c0, lo);
+          tmem_ld16_issue(taddr + CS + c0, hi);
+          tmem_ld_wait();
+          float o[16];
+          unsigned cw[4] = {0u, 0u, 0u, 0u};
+#pragma unroll
+          for (int j = 0; j < 16; ++j) {
+            const float l = __uint_as_float(lo[j]) + s_bias[c0 + j];
+            const float h = __uint_as_float(hi[j]) + s_bias[CS + c0 + j];
+            const bool sel = h > l;
+            o[j] = ((sel ? h : l) - s_bnm[c0 + j]) * s_bni[c0 + j];
+            cw[j >> 2] |= (sel ? 4u : 0u) << (8 * (j & 3));  // code byte: MFM half << 2 (no pool position)
+          }
+          if (valid) {
+#pragma unroll
+            for (int j = 0; j < 16; j += 4) *reinterpret_cast<float4*>(dst + c0 + j) = make_float4(o[j], o[j + 1], o[j + 2], o[j + 3]);
+            *reinterpret_cast<uint4*>(cdst + c0) = make_uint4(cw[0], cw[1], cw[2], cw[3]);
+          }
+        }
+      }
+      tc_fence_before();
+      return;
+    }
     asm volatile("bar.sync 1, %0;" ::"n"(LW) : "memory");  // every worker has finished reading the previous staging tile
     {
       // TMEM -> registers -> staging.  Warps w and w+4 share TMEM lane quadrant w%4 and split the columns.
