@@ -76,6 +76,8 @@ int conv0t_forward(const ConvFwdArgs& a, const unsigned char* wpack, int passes,
 bool conv_p3_supported(int Cin, int Cout, int KS, bool pool, int W);
 int conv_p3_forward(const ConvFwdArgs& a, const unsigned char* wpack, int passes, cudaStream_t stream);
 int conv_p3_backward(const ConvBwdArgs& a, const unsigned char* wpack, int passes, cudaStream_t stream);
+// mixed mode (passes = 2, forward only): tf32 main term + both cross terms as ONE bf16 MMA; its own weight image (same bytes)
+int conv_p3_pack_mix(const float* w, unsigned char* wf, int Cout, int Cin, cudaStream_t stream);
 // "horizontal scatter" backward (N = 3 C_in): needs its own weight image in the layer's backward pack buffer
 bool conv_p3_bwd_hs(int Cin, int Cout, int KS, bool pool, int W);
 int conv_p3_pack_hs(const float* w, unsigned char* wd, int Cout, int Cin, cudaStream_t stream);

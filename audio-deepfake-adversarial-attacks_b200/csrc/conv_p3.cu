@@ -209,6 +209,8 @@ __global__ void __launch_bounds__(P3Cfg<KTOT, NOUT, POOL, BWD, HS>::PT, 1) conv_
                 if (a.passes == 3) {
                   mma_tf32(dcol, ah + moff, bl, IDESC, 1u);
                   mma_tf32(dcol, al + moff, bh, IDESC, 1u);
+                } else if (a.passes == 2) {  // both cross terms as one bf16 MMA over the interleaved second planes
+                  mma_bf16(dcol, al + moff, bl, idesc_bf16(128, Cfg::NMMA), 1u);
                 }
               }
             }
@@ -228,6 +230,14 @@ __global__ void __launch_bounds__(P3Cfg<KTOT, NOUT, POOL, BWD, HS>::PT, 1) conv_
     }
   } else {
     // ================= worker warps =================
+    const bool prof = a.prof != nullptr && blockIdx.x == 0 && tid == 0;
+    long long pc[10] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0}, t_last = clock64();
+#define P3PROF(k)                     \
+  if (prof) {                         \
+    const long long now_ = clock64(); \
+    pc[k] += now_ - t_last;           \
+    t_last = now_;                    \
+  }
     const int c4 = tid & 7, r0 = tid >> 3;  // channel group; first band row (rows r0 + (PW / 8) u)
     constexpr int RSTEP = PW / 8;
     float4 rv[NI_MAX];
@@ -339,7 +349,16 @@ __global__ void __launch_bounds__(P3Cfg<KTOT, NOUT, POOL, BWD, HS>::PT, 1) conv_
           split_tf32(v.w, hi.w, lo.w);
           const uint32_t off = off0 + (uint32_t)u * (RSTEP * 128);
           *reinterpret_cast<float4*>(a_hi + off) = hi;
-          *reinterpret_cast<float4*>(a_lo + off) = lo;
+          if (!BWD && a.passes == 2) {
+            // mixed mode: the second plane holds, per 16-byte chunk, bf16(a) x 4 then bf16(a - tf32(a)) x 4: ONE bf16 MMA
+            // (K = 16) against [bf16(w_lo) x 4 | bf16(w) x 4] adds both cross terms a_hi w_lo + a_lo w_hi
+            uint4 xw;
+            xw.x = pack_bf16x2(v.x, v.y), xw.y = pack_bf16x2(v.z, v.w);
+            xw.z = pack_bf16x2(lo.x, lo.y), xw.w = pack_bf16x2(lo.z, lo.w);
+            *reinterpret_cast<uint4*>(a_lo + off) = xw;
+          } else {
+            *reinterpret_cast<float4*>(a_lo + off) = lo;
+          }
         }
       }
     };
@@ -347,7 +366,9 @@ __global__ void __launch_bounds__(P3Cfg<KTOT, NOUT, POOL, BWD, HS>::PT, 1) conv_
     auto epilogue = [&](int tile, int buf) {
       int b, y0, rows, nM;
       tile_geom(tile, b, y0, rows, nM);
+      P3PROF(4)
       asm volatile("bar.sync 1, %0;" ::"n"(PW) : "memory");  // previous staging tile fully consumed
+      P3PROF(6)
       {
         const int wq = warp & 3, wg = warp >> 2;
         for (int m = wg; m < nM; m += 2) {
@@ -390,8 +411,10 @@ __global__ void __launch_bounds__(P3Cfg<KTOT, NOUT, POOL, BWD, HS>::PT, 1) conv_
           }
         }
       }
+      P3PROF(7)
       tc_fence_before();
       asm volatile("bar.sync 1, %0;" ::"n"(PW) : "memory");
+      P3PROF(8)
       constexpr int C4 = CS / 4;
       if (BWD) {
         constexpr int O4 = NOUT / 4;  // float4 groups of the C_in output channels
@@ -461,14 +484,6 @@ __global__ void __launch_bounds__(P3Cfg<KTOT, NOUT, POOL, BWD, HS>::PT, 1) conv_
 
     // ---- persistent loop over units (tile, chunk) ----
     int tile = blockIdx.x, kc = 0, u_glob = 0, it = 0, prev_tile = -1;
-    const bool prof = a.prof != nullptr && blockIdx.x == 0 && tid == 0;
-    long long pc[6] = {0, 0, 0, 0, 0, 0}, t_last = clock64();
-#define P3PROF(k)                     \
-  if (prof) {                         \
-    const long long now_ = clock64(); \
-    pc[k] += now_ - t_last;           \
-    t_last = now_;                    \
-  }
     if (tile < a.n_tiles) issue_loads(tile, 0);
     // unit u commits bar_unit_done[DB ? u & 1 : 0]; its k-th completion there has parity k & 1
     auto wait_unit = [&](int u) {
@@ -517,6 +532,7 @@ __global__ void __launch_bounds__(P3Cfg<KTOT, NOUT, POOL, BWD, HS>::PT, 1) conv_
     if (prof) {
       for (int k = 0; k < 6; ++k) a.prof[k] = pc[k];
       a.prof[6] = it;
+      a.prof[12] = pc[6], a.prof[13] = pc[7], a.prof[14] = pc[8];
     }
   }
   tc_fence_before();
@@ -575,6 +591,8 @@ int launch_p3(P3Args a, const char* tag, cudaStream_t stream) {
     fprintf(stderr, "[p3 %s] NST %d DB %d tiles/cta %lld | worker cycles/tile: wait_unit %lld convert %lld fence+arrive %lld issue_loads %lld "
                     "epilogue %lld other %lld | mma warp: wait_band %lld wait_w %lld issue %lld\n",
             tag, Cfg::NST, (int)Cfg::DB, hp[6], hp[0] / n, hp[1] / n, hp[2] / n, hp[3] / n, hp[4] / n, hp[5] / n, hp[8] / n, hp[9] / n, hp[10] / n);
+    fprintf(stderr, "      epilogue split: entry barrier %lld, TMEM->stage %lld, barrier %lld, pool/gather+store (rest of 'epilogue') \n", hp[12] / n,
+            hp[13] / n, hp[14] / n);
   }
   return 0;
 }
@@ -599,6 +617,31 @@ __global__ void pack_hs_kernel(const float* __restrict__ w, unsigned char* __res
   }
 }
 
+// Mixed-mode forward slices in consumption order [chunk kc][tap]: tf32-hi image (K-major SWIZZLE_128B [Cout rows][32 k]) then
+// the CROSS image: row n, 16-byte chunk c = [bf16(w_lo[4c..4c+3]) | bf16(w[4c..4c+3])], same swizzle.
+__global__ void pack_mix_kernel(const float* __restrict__ w, unsigned char* __restrict__ dst, int Cout, int Cin) {
+  const int NKC = (Cin + 31) / 32;
+  const int total = NKC * 9 * Cout * 8;  // one thread per (slice, row, chunk of 4 channels)
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+    const int c = i & 7, n = (i >> 3) % Cout, sl = i / (8 * Cout);
+    const int tap = sl % 9, kc = sl / 9;
+    float v[4], hi[4], lo[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int ci = 32 * kc + 4 * c + j;
+      v[j] = ci < Cin ? w[((size_t)n * Cin + ci) * 9 + tap] : 0.f;
+      tc::split_tf32(v[j], hi[j], lo[j]);
+    }
+    const size_t slice = (size_t)sl * 2 * Cout * 128;
+    const uint32_t off = (uint32_t)(n * 128 + ((c ^ (n & 7)) << 4));
+    *reinterpret_cast<float4*>(dst + slice + off) = make_float4(hi[0], hi[1], hi[2], hi[3]);
+    uint4 x;
+    x.x = tc::pack_bf16x2(lo[0], lo[1]), x.y = tc::pack_bf16x2(lo[2], lo[3]);
+    x.z = tc::pack_bf16x2(v[0], v[1]), x.w = tc::pack_bf16x2(v[2], v[3]);
+    *reinterpret_cast<uint4*>(dst + slice + (size_t)Cout * 128 + off) = x;
+  }
+}
+
 int tune_hs() {
   static const int v = [] {
     const char* e = getenv("ADVB_P3_HS");
@@ -617,6 +660,13 @@ int conv_p3_pack_hs(const float* w, unsigned char* wd, int Cout, int Cin, cudaSt
   const int n = ((Cout + 31) / 32) * 3 * 3 * Cin * 32;
   pack_hs_kernel<<<cdiv(n, 256), 256, 0, stream>>>(w, wd, Cout, Cin);
   ADVB_KERNEL_OK("pack_tc_bwd_hs", stream);
+  return 0;
+}
+
+int conv_p3_pack_mix(const float* w, unsigned char* wf, int Cout, int Cin, cudaStream_t stream) {
+  const int total = ((Cin + 31) / 32) * 9 * Cout * 8;
+  pack_mix_kernel<<<cdiv(total, 256), 256, 0, stream>>>(w, wf, Cout, Cin);
+  ADVB_KERNEL_OK("pack_mix", stream);
   return 0;
 }
 

@@ -60,6 +60,7 @@ struct LcnnBlock {
   float* wd = nullptr;  // packed backward weights
   unsigned char* tcf = nullptr;  // tensor-core weight slices (forward / backward)
   unsigned char* tcd = nullptr;
+  unsigned char* tcf_mix = nullptr;  // forward slices of the mixed mode (tf32_passes = 2): tf32 hi + bf16 cross image
   bool tc = false;
   float* invstd = nullptr;
   Act out{};             // block output (zero-bordered for the next conv)
@@ -99,6 +100,8 @@ struct advb_handle {
     std::string key;
   } gc;
   cudaStream_t cap_stream = nullptr;
+  cudaEvent_t last_done = nullptr;     // recorded at the end of every call: a call on another stream waits for it (CallScope)
+  cudaStream_t last_stream = nullptr;
   float *x_in = nullptr, *adv2 = nullptr;  // engine-owned copies: clean clips, second ping-pong iterate
   int64_t* y_in = nullptr;
 
@@ -301,6 +304,7 @@ int build_lcnn(advb_handle* h) {
     if (k.tc) {
       ADVB_TRY(h->alloc(&k.tcf, conv_tc_pack_bytes(k.Cout, k.Cin, k.KS, false)));
       ADVB_TRY(h->alloc(&k.tcd, conv_tc_pack_bytes(k.Cout, k.Cin, k.KS, true)));
+      if (k.KS == 3) ADVB_TRY(h->alloc(&k.tcf_mix, conv_tc_pack_bytes(k.Cout, k.Cin, k.KS, false)));
     }
     H = k.Ho;
     W = k.Wo;
@@ -346,6 +350,7 @@ int prepare_lcnn(advb_handle* h, cudaStream_t st) {
       ADVB_TRY(conv_tc_pack(h->t(p + ".weight"), k.tcf, k.tcd, k.Cout, k.Cin, k.KS, st));
       if (conv_p3_bwd_hs(k.Cin, k.Cout, k.KS, k.pool, k.W))  // same bytes, horizontal-scatter layout
         ADVB_TRY(conv_p3_pack_hs(h->t(p + ".weight"), k.tcd, k.Cout, k.Cin, st));
+      if (h->tf32_passes == 2 && k.tcf_mix != nullptr) ADVB_TRY(conv_p3_pack_mix(h->t(p + ".weight"), k.tcf_mix, k.Cout, k.Cin, st));
     }
     if (!(k.tc && h->conv_path == 0))
       ADVB_TRY(conv_pack_weights(h->t(p + ".weight"), k.wf, k.wd, k.Cout, k.Cin, k.KS, st));
@@ -398,9 +403,14 @@ int lcnn_forward(advb_handle* h, const float* x, int B, cudaStream_t st) {
     a.Wo = k.Wo;
     a.pool = k.pool;
     a.tag = k.tag_f.c_str();
+    // tf32_passes = 2 (mixed mode) exists for the forward 3x3 kernels only; everything else keeps 3xTF32
+    const int passes = h->tf32_passes == 2 ? 3 : h->tf32_passes;
     if (i == 0 && k.tc && h->conv_path == 0 && h->conv0_fwd == 0 && conv0t_supported(k.H, k.W, k.Ho, k.Wo))
-      ADVB_TRY(conv0t_forward(a, h->c0t_w, h->tf32_passes, st));
-    else if (k.tc && h->conv_path == 0) ADVB_TRY(conv_tc_forward(a, k.tcf, h->tf32_passes, st));
+      ADVB_TRY(conv0t_forward(a, h->c0t_w, passes, st));
+    else if (k.tc && h->conv_path == 0 && h->tf32_passes == 2 && k.tcf_mix != nullptr &&
+             conv_p3_supported(k.Cin, k.Cout, k.KS, k.pool, k.W))
+      ADVB_TRY(conv_p3_forward(a, k.tcf_mix, 2, st));
+    else if (k.tc && h->conv_path == 0) ADVB_TRY(conv_tc_forward(a, k.tcf, passes, st));
     else ADVB_TRY(conv_mfm_forward(a, st));
     in = k.out.p;
     in_pad = k.out.pad;
@@ -442,7 +452,7 @@ int lcnn_backward(advb_handle* h, const float* x, const int64_t* y, int B, int m
     a.Wo = k.Wo;
     a.pool = k.pool;
     a.tag = k.tag_b.c_str();
-    if (k.tc && h->conv_path == 0) ADVB_TRY(conv_tc_backward(a, k.tcd, h->tf32_passes, st));
+    if (k.tc && h->conv_path == 0) ADVB_TRY(conv_tc_backward(a, k.tcd, h->tf32_passes == 2 ? 3 : h->tf32_passes, st));
     else ADVB_TRY(conv_mfm_backward(a, st));
   }
   const LcnnBlock& k0 = h->blk[0];
@@ -450,7 +460,7 @@ int lcnn_backward(advb_handle* h, const float* x, const int64_t* y, int B, int m
     ADVB_TRY(conv0_cells_backward(k0.gout, k0.codes, h->t("m_transform.0.weight"), h->g_coef, B, k0.H, k0.W, k0.Ho, k0.Wo, st));
   else if (k0.tc && h->conv_path == 0)
     ADVB_TRY(conv0_tc_backward(k0.gout, k0.codes, k0.tcd, h->conv0_T, h->g_coef, B, k0.H, k0.W, k0.Ho, k0.Wo,
-                               h->tf32_passes, st));
+                               h->tf32_passes == 2 ? 3 : h->tf32_passes, st));
   else
     ADVB_TRY(conv0_backward(k0.gout, k0.codes, h->t("m_transform.0.weight"), h->g_coef, B, k0.H, k0.W, k0.Ho, k0.Wo, st));
   ADVB_TRY(frontend_backward(h->ftb, h->fst, x, B, h->T, h->dB, h->g_coef, (long long)h->F * 80, 80, 1,
@@ -655,7 +665,7 @@ int model_prepare(advb_handle* h, cudaStream_t st) {
   return rc;
 }
 int model_forward(advb_handle* h, const float* x, int B, cudaStream_t st) {
-  if (h->model_kind == ADVB_MODEL_RAWNET3) return rn_forward(h->rn, x, h->logits, B, h->conv_path, h->tf32_passes, st);
+  if (h->model_kind == ADVB_MODEL_RAWNET3) return rn_forward(h->rn, x, h->logits, B, h->conv_path, h->tf32_passes == 2 ? 3 : h->tf32_passes, st);
   if (h->model_kind == ADVB_MODEL_LCNN) return lcnn_forward(h, x, B, st);
   if (h->model_kind == ADVB_MODEL_SPECRNET) return specrnet_forward(h, x, B, st);
   set_error("model kind not implemented");
@@ -666,7 +676,7 @@ int model_backward(advb_handle* h, const float* x, const int64_t* y, int B, int 
   if (h->model_kind == ADVB_MODEL_RAWNET3) {
     ADVB_CHECK(upd == nullptr, "RawNet3 has no frontend backward to fuse the update into");
     return rn_backward(h->rn, x, h->logits, reinterpret_cast<const long long*>(y), B, mode, n_global, coef, gx, h->conv_path,
-                       h->tf32_passes, st);
+                       h->tf32_passes == 2 ? 3 : h->tf32_passes, st);
   }
   if (h->model_kind == ADVB_MODEL_LCNN) return lcnn_backward(h, x, y, B, mode, n_global, gx, st, coef, upd);
   if (h->model_kind == ADVB_MODEL_SPECRNET) return specrnet_backward(h, x, y, B, mode, n_global, gx, st, coef, upd);
@@ -775,14 +785,29 @@ int replay(advb_handle* h, cudaStream_t st, int reps, const std::string& key, Bo
   return 0;
 }
 
+// One call per handle in flight: every activation / scratch buffer belongs to the handle, so a call enqueued on another
+// stream than the previous one first waits for that call's completion event (calls on one stream are ordered anyway).
 struct CallScope {
   DeviceGuard guard;
-  explicit CallScope(advb_handle* h) : guard(h->device) {
+  advb_handle* h;
+  cudaStream_t st = nullptr;
+  bool ordered = false;
+  explicit CallScope(advb_handle* handle) : guard(handle->device), h(handle) {
     g_counter = &h->counter;
     g_prof = &h->prof;
     g_conv_sched = h->conv_sched;
   }
+  void order(cudaStream_t stream) {
+    st = stream;
+    ordered = true;
+    if (h->last_done != nullptr && h->last_stream != stream) cudaStreamWaitEvent(stream, h->last_done, 0);
+  }
   ~CallScope() {
+    if (ordered) {
+      if (h->last_done == nullptr) cudaEventCreateWithFlags(&h->last_done, cudaEventDisableTiming);
+      if (h->last_done != nullptr) cudaEventRecord(h->last_done, st);
+      h->last_stream = st;
+    }
     g_counter = nullptr;
     g_prof = nullptr;
   }
@@ -861,6 +886,7 @@ void advb_destroy(advb_handle* h) {
   DeviceGuard guard(h->device);
   drop_graph(h);
   if (h->cap_stream != nullptr) cudaStreamDestroy(h->cap_stream);
+  if (h->last_done != nullptr) cudaEventDestroy(h->last_done);
   for (void* p : h->allocs) cudaFree(p);
   if (h->host_cost != nullptr) cudaFreeHost(h->host_cost);
   delete h;
@@ -877,7 +903,8 @@ int advb_set_option(advb_handle* h, const char* key, int value) {
     ADVB_CHECK(value == 0 || value == 1, "conv_path: 0 = tcgen05, 1 = fp32 SIMT");
     h->conv_path = value;
   } else if (k == "tf32_passes") {
-    ADVB_CHECK(value == 1 || value == 3, "tf32_passes: 3 = 3xTF32, 1 = single pass");
+    ADVB_CHECK(value == 1 || value == 2 || value == 3,
+               "tf32_passes: 3 = 3xTF32, 2 = tf32 main term + bf16 cross terms in the forward 3x3 blocks (experiment), 1 = single pass");
     h->tf32_passes = value;
   } else if (k == "conv_sched") {
     ADVB_CHECK(value == 0 || value == 1, "conv_sched: 0 = persistent kernels, 1 = one-tile-per-CTA kernels");
@@ -924,6 +951,7 @@ int advb_forward(advb_handle* h, const float* x, float* logits, int B, int T, vo
   ADVB_TRY(check_call(h, B, T));
   CallScope scope(h);
   cudaStream_t st = static_cast<cudaStream_t>(cuda_stream);
+  scope.order(st);
   ADVB_TRY(model_prepare(h, st));
   ADVB_TRY(model_forward(h, x, B, st));
   ADVB_CUDA_OK(cudaMemcpyAsync(logits, h->logits, (size_t)B * sizeof(float), cudaMemcpyDeviceToDevice, st));
@@ -937,6 +965,7 @@ int advb_grad(advb_handle* h, int what, const float* x, const int64_t* y, float*
   ADVB_CHECK(what == ADVB_GRAD_LOGIT || y != nullptr, "labels required");
   CallScope scope(h);
   cudaStream_t st = static_cast<cudaStream_t>(cuda_stream);
+  scope.order(st);
   ADVB_TRY(model_prepare(h, st));
   ADVB_TRY(model_forward(h, x, B, st));
   ADVB_TRY(model_backward(h, x, y, B, what, n_global_batch > 0 ? n_global_batch : B, grad, st));
@@ -1126,6 +1155,7 @@ int advb_attack(advb_handle* h, const advb_attack_desc* atk, const float* x, con
   ADVB_TRY(check_attack_args(h, atk, x, y, x_adv, B, T));
   ADVB_CHECK(x != x_adv, "x_adv must not alias x");
   CallScope scope(h);
+  scope.order(static_cast<cudaStream_t>(cuda_stream));
   return run_attack(h, atk, x, y, start, x_adv, B, T, static_cast<cudaStream_t>(cuda_stream), false);
 }
 
@@ -1133,6 +1163,7 @@ int advb_attack_minmax(advb_handle* h, const advb_attack_desc* atk, const float*
                        float* x_adv_raw, int B, int T, void* cuda_stream) {
   ADVB_TRY(check_attack_args(h, atk, x_raw, y, x_adv_raw, B, T));
   CallScope scope(h);
+  scope.order(static_cast<cudaStream_t>(cuda_stream));
   return run_attack(h, atk, x_raw, y, start, x_adv_raw, B, T, static_cast<cudaStream_t>(cuda_stream), true);
 }
 
@@ -1169,6 +1200,7 @@ int advb_frontend_fwd(advb_handle* h, const float* x, float* coeff, int B, int T
   ADVB_CHECK(h->frontend_kind != ADVB_FRONTEND_NONE, "this model takes the raw waveform: it has no spectral frontend");
   CallScope scope(h);
   cudaStream_t st = static_cast<cudaStream_t>(cuda_stream);
+  scope.order(st);
   refresh_frontend_tables(h);
   ADVB_TRY(frontend_prepare(h->ftb, st));
   ADVB_TRY(frontend_forward(h->ftb, h->fst, x, B, T, h->dB, coeff, (long long)80 * h->F, 1, h->F, 0, st, nullptr, &h->fe_host));
@@ -1181,6 +1213,7 @@ int advb_frontend_bwd(advb_handle* h, const float* x, const float* g_coeff, floa
   ADVB_CHECK(h->frontend_kind != ADVB_FRONTEND_NONE, "this model takes the raw waveform: it has no spectral frontend");
   CallScope scope(h);
   cudaStream_t st = static_cast<cudaStream_t>(cuda_stream);
+  scope.order(st);
   refresh_frontend_tables(h);
   ADVB_TRY(frontend_prepare(h->ftb, st));
   // forward first: backward needs the batch arg-max / floor state of this input
@@ -1250,6 +1283,7 @@ int64_t advb_debug_stage(advb_handle* h, const char* stage, float* dst, int64_t 
   }
   CallScope scope(h);
   cudaStream_t st = static_cast<cudaStream_t>(cuda_stream);
+  scope.order(st);
   const std::string s(stage);
   const float* src = nullptr;
   int64_t d[5] = {h->Bmax, 1, 1, 1, 0};

@@ -19,7 +19,10 @@ namespace {
 
 constexpr int HID = 80;
 constexpr int G4 = 4 * HID;  // 320
-constexpr int CL = 2;        // clips per recurrence CTA
+#ifndef ADVB_LSTM_CL
+#define ADVB_LSTM_CL 2
+#endif
+constexpr int CL = ADVB_LSTM_CL;  // clips per recurrence CTA
 
 // C[M,N] = A[M,K] * Bm[K,N] (+ bias[N]) (+ Cadd[M,N]); row-major, K and N multiples of 4, 16-byte aligned rows.
 // BM x BN tile, 16-deep k-steps, 256 threads with a (BM/16) x (BN/16) register tile; 128-bit global and shared loads.

@@ -347,3 +347,34 @@ def test_fab_random_restarts(cuda_device):
     moved2 = (two != xd).any(dim=1)
     assert (moved2 | ~moved1).all(), "a restart may add adversarial clips, never drop one"
     assert torch.equal(two[moved1], one[moved1]), "clips already fooled keep their first adversarial example (fab.py:523-524)"
+
+
+def test_calls_on_different_streams_are_ordered(cuda_device):
+    """A handle's activations and scratch belong to the handle: a call enqueued on another CUDA stream must wait for the
+    previous call (completion event in the C ABI), so interleaving streams gives the serial results."""
+    from advb200 import engine
+    from advb200 import torchattacks as ta
+
+    case, x, y, holder, state, fwd = helpers.case_setup("lcnn_lfcc_t16000")
+    holder = helpers.load_holder_state(holder, state, cuda_device)
+    eng = engine.engine_for(holder, x.shape[0], x.shape[1])
+    xd, yd = x.to(cuda_device), y.to(cuda_device)
+    noise = helpers.reference_start(case, "pgd", x, 0.001).to(cuda_device)
+    atk = ta.PGD(holder, eps=0.001, alpha=2 / 255, steps=6)
+    want_adv = atk.forward(xd, yd, noise=noise)
+    want_logits = eng.forward(want_adv)
+    torch.cuda.synchronize()
+    s1, s2 = torch.cuda.Stream(), torch.cuda.Stream()
+    for _ in range(3):
+        with torch.cuda.stream(s1):
+            adv = atk.forward(xd, yd, noise=noise)
+        ready = torch.cuda.Event()
+        ready.record(s1)
+        with torch.cuda.stream(s2):
+            s2.wait_event(ready)           # the caller's own dependency on `adv` ...
+            logits = eng.forward(adv)      # ... and the engine's: its buffers are still in use by s1's call until it completes
+            g, _ = eng.grad(xd, yd)
+        with torch.cuda.stream(s1):
+            adv2 = atk.forward(xd, yd, noise=noise)  # back on s1 while s2's calls may still run
+        torch.cuda.synchronize()
+        assert torch.equal(adv, want_adv) and torch.equal(adv2, want_adv) and torch.equal(logits, want_logits)
