@@ -97,6 +97,7 @@ __global__ void __launch_bounds__(P3Cfg<KTOT, NOUT, POOL, BWD, HS>::PT, 1) conv_
   constexpr int NKC = Cfg::NKC, NSLICE = Cfg::NSLICE, NST = Cfg::NST, CS = Cfg::CS, SS = Cfg::SS;
   constexpr int NM3 = Cfg::NM3, NI_MAX = Cfg::NI_MAX, BR = Cfg::BR, NTAP = Cfg::NTAP, NMMA = Cfg::NMMA;
   constexpr bool DB = Cfg::DB;
+  constexpr int KSU = BWD ? 1 : 4;
   constexpr uint32_t IDESC = idesc_tf32(128, Cfg::NMMA);
 
   extern __shared__ unsigned char smem_raw[];
@@ -110,7 +111,7 @@ __global__ void __launch_bounds__(P3Cfg<KTOT, NOUT, POOL, BWD, HS>::PT, 1) conv_
   // compute-sanitizer synccheck, "missing wait"); per buffer, unit u + 2 is staged only after the MMAs of unit u completed.
   __shared__ uint64_t bar_wfull[NST], bar_wempty[NST], bar_band_full[2], bar_unit_done[2];
   __shared__ uint32_t tmem_base_s;
-  __shared__ float s_bias[BWD ? 1 : NOUT];
+  __shared__ __align__(16) float s_bias[BWD ? 4 : NOUT];
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int Wp = a.W + 2, Hp = a.H + 2;
@@ -195,8 +196,12 @@ __global__ void __launch_bounds__(P3Cfg<KTOT, NOUT, POOL, BWD, HS>::PT, 1) conv_
           const uint32_t w_hi = smem_u32(wring + (size_t)slot * Cfg::SLICE_BYTES), w_lo = w_hi + NMMA * 128;
           const int dy = HS ? tap : tap / 3, dx = HS ? 1 : tap - dy * 3;  // HS: vertical taps only, centre column
           const uint32_t row_off = (uint32_t)(dy * Wp + dx) * 128u;
-#pragma unroll 1
-          for (int ks = 0; ks < kvalid / 8; ++ks) {
+          // Forward: k-steps unrolled - the descriptor arithmetic of a step is a chain of uniform-datapath instructions (~140 cycles
+          // when the steps run one after the other: tools/tc_probe.cu section 5).  Backward: NOT unrolled - denser MMA issue slowed the
+          // worker warps' fill by more than it saved (block 2: 388 -> 445 us, profiles/r02_p3_phases.md).
+#pragma unroll KSU
+          for (int ks = 0; ks < 4; ++ks) {
+            if (ks >= kvalid / 8) break;
             const uint64_t bh = desc_sw128(w_hi + ks * 32), bl = desc_sw128(w_lo + ks * 32);
             const uint64_t ah = desc_sw128(a_hi_addr + row_off + ks * 32), al = desc_sw128(a_lo_addr + row_off + ks * 32);
             const uint32_t acc0 = (kc > 0 || tap > 0 || ks > 0) ? 1u : 0u;
@@ -387,27 +392,39 @@ __global__ void __launch_bounds__(P3Cfg<KTOT, NOUT, POOL, BWD, HS>::PT, 1) conv_
                     __uint_as_float(v[j]), __uint_as_float(v[j + 1]), __uint_as_float(v[j + 2]), __uint_as_float(v[j + 3]));
             }
           } else {
-            unsigned long long fl = 0ull;
-#pragma unroll 1
+            // c0 unrolled: flag bits become immediates, the bias comes by LDS.128 and the row goes out by st.shared (the generic
+            // stores emitted before cost an address-space check each): 92 instructions per 16 channels instead of 210; this phase
+            // was 4.4-6 k cycles per tile (ADVB_P3_PROF "TMEM->stage"), issue-bound, not TMEM-latency-bound
+            uint32_t fl0 = 0u, fl1 = 0u;
+            const uint32_t srow_s = smem_u32(srow);
+#pragma unroll
             for (int c0 = 0; c0 < CS; c0 += 16) {
               uint32_t lo[16], hi[16];
               tmem_ld16_issue(taddr + c0, lo);
               tmem_ld16_issue(taddr + CS + c0, hi);
               tmem_ld_wait();
-              float m4[16];
 #pragma unroll
-              for (int j = 0; j < 16; ++j) {
-                const float l = __uint_as_float(lo[j]) + s_bias[c0 + j];
-                const float h = __uint_as_float(hi[j]) + s_bias[CS + c0 + j];
-                const bool sel = h > l;
-                m4[j] = sel ? h : l;
-                fl |= (unsigned long long)(sel ? 1u : 0u) << (c0 + j);
+              for (int j = 0; j < 16; j += 4) {
+                const float4 bl = *reinterpret_cast<const float4*>(s_bias + c0 + j);
+                const float4 bh = *reinterpret_cast<const float4*>(s_bias + CS + c0 + j);
+                const float bla[4] = {bl.x, bl.y, bl.z, bl.w}, bha[4] = {bh.x, bh.y, bh.z, bh.w};
+                float m4[4];
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                  const float l = __uint_as_float(lo[j + k]) + bla[k];
+                  const float h = __uint_as_float(hi[j + k]) + bha[k];
+                  const bool sel = h > l;
+                  m4[k] = sel ? h : l;
+                  const int bit = c0 + j + k;
+                  if (bit < 32) fl0 |= sel ? (1u << bit) : 0u;
+                  else fl1 |= sel ? (1u << (bit - 32)) : 0u;
+                }
+                asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(srow_s + (uint32_t)(c0 + j) * 4u), "f"(m4[0]), "f"(m4[1]),
+                             "f"(m4[2]), "f"(m4[3])
+                             : "memory");
               }
-#pragma unroll
-              for (int j = 0; j < 16; j += 4)
-                *reinterpret_cast<float4*>(srow + c0 + j) = make_float4(m4[j], m4[j + 1], m4[j + 2], m4[j + 3]);
             }
-            flags[r] = fl;
+            flags[r] = ((unsigned long long)fl1 << 32) | fl0;
           }
         }
       }

@@ -71,7 +71,8 @@ for p in (3, 2, 1):
                          "max_abs_dlogit_adv": float(np.abs(la.numpy() - fx["logits_adv"].ravel()).max()),
                          "clips_per_s": 3 * B / (ev0.elapsed_time(ev1) * 1e-3),
                          "kernel_us": {k: round(1e3 * prof[k]["total_ms"] / prof[k]["count"], 1)
-                                       for k in ("conv_fwd_b2", "conv_fwd_b4", "conv_fwd_b6", "conv_fwd_b8")}}
+                                       for k in ("conv_fwd_b2", "conv_fwd_b4", "conv_fwd_b6", "conv_fwd_b8",
+                                                 "conv_bwd_b2", "conv_bwd_b4", "conv_bwd_b6", "conv_bwd_b8")}}
 job.eng.set_option("tf32_passes", 3)
 print("MIXCHECK " + json.dumps(out))
 for k, v in out.items():

@@ -23,6 +23,7 @@ def main():
     ap.add_argument("--conv-path", type=int, default=0)
     ap.add_argument("--model", default="lcnn", choices=["lcnn", "specrnet", "rawnet3"])
     ap.add_argument("--samples", type=int, default=bench.T_SAMPLES)
+    ap.add_argument("--opt", action="append", default=[], help="engine option name=value (repeatable)")
     ap.add_argument("--attack", action="store_true", help="run a 2-step PGD call (graph replay + fused update) instead of advb_grad")
     args = ap.parse_args()
     from advb200 import engine
@@ -36,6 +37,9 @@ def main():
     x, y = x[:, :args.samples].contiguous().to(dev), y.to(dev)
     eng = engine.engine_for(holder, args.batch, args.samples)
     eng.set_option("conv_path", args.conv_path)
+    for kv in args.opt:
+        k, v = kv.split("=")
+        eng.set_option(k, int(v))
     if args.attack:
         from advb200 import torchattacks as ta
 
