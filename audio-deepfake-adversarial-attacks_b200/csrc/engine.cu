@@ -815,6 +815,14 @@ struct CallScope {
 
 }  // namespace
 
+namespace advb {
+namespace {
+__global__ void u8_to_f32_kernel(const unsigned char* __restrict__ src, float* __restrict__ dst, int64_t n) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) dst[i] = (float)src[i];
+}
+}  // namespace
+}  // namespace advb
+
 extern "C" {
 
 int advb_version(void) { return ADVB_VERSION; }
@@ -1286,6 +1294,7 @@ int64_t advb_debug_stage(advb_handle* h, const char* stage, float* dst, int64_t 
   scope.order(st);
   const std::string s(stage);
   const float* src = nullptr;
+  const unsigned char* src_u8 = nullptr;  // winner codes: converted to float on the way out
   int64_t d[5] = {h->Bmax, 1, 1, 1, 0};
   auto from_act = [&](const Act& a) {
     src = a.p;
@@ -1322,6 +1331,13 @@ int64_t advb_debug_stage(advb_handle* h, const char* stage, float* dst, int64_t 
     d[1] = k.Ho;
     d[2] = k.Wo;
     d[3] = k.Cout / 2;
+  } else if (!is_sr && s.rfind("codes", 0) == 0 && s.size() == 6 && s[5] >= '0' && s[5] <= '8') {
+    // per output element of block N: (Max-Feature-Map half of the winning pixel) << 2 | (2x2 pool position dy << 1 | dx)
+    const LcnnBlock& k = h->blk[s[5] - '0'];
+    src_u8 = k.codes;
+    d[1] = k.Ho;
+    d[2] = k.Wo;
+    d[3] = k.Cout / 2;
   } else if (s == "feats" || s == "lstm1" || s == "lstm2" || s == "dfeats") {
     // features / their gradient in the reference's (c * Wf + w) order: gathered on demand from the NHWC block buffers
     if (s == "feats" && feats_gather(h->blk[8].out.p, h->feats, h->Bmax, h->L, h->Wf, 32, st)) return -1;
@@ -1351,6 +1367,14 @@ int64_t advb_debug_stage(advb_handle* h, const char* stage, float* dst, int64_t 
   if (capacity < n) {
     set_error("debug buffer too small");
     return -1;
+  }
+  if (src_u8 != nullptr) {
+    advb::u8_to_f32_kernel<<<1024, 256, 0, st>>>(src_u8, dst, n);
+    if (cudaGetLastError() != cudaSuccess) {
+      set_error("debug copy failed");
+      return -1;
+    }
+    return n;
   }
   if (cudaMemcpyAsync(dst, src, (size_t)n * sizeof(float), cudaMemcpyDeviceToDevice, st) != cudaSuccess) {
     set_error("debug copy failed");

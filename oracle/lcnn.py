@@ -64,9 +64,18 @@ def embedding(feat, state, taps=None):
     for idx, pool, bn in BLOCKS:
         w = state[f"m_transform.{idx}.weight"]
         x = F.conv2d(x, w, state[f"m_transform.{idx}.bias"], padding=w.shape[-1] // 2)
+        if taps is not None:  # winner bookkeeping in the engine's encoding: (MFM half of the winning pixel) << 2 | (dy << 1 | dx)
+            Bc, Cc, Hc, Wc = x.shape
+            half = x.view(Bc, 2, Cc // 2, Hc, Wc).max(1)[1]
         x = mfm(x)
         if pool:
+            if taps is not None:
+                _, flat = F.max_pool2d(x, 2, 2, return_indices=True)
+                wy, wx = flat // x.shape[3], flat % x.shape[3]
+                taps[f"codes{idx}"] = (half.flatten(2).gather(2, flat.flatten(2)).view_as(flat) << 2) | ((wy & 1) << 1) | (wx & 1)
             x = F.max_pool2d(x, 2, 2)
+        elif taps is not None:
+            taps[f"codes{idx}"] = half << 2
         if bn is not None:
             rm = state[f"m_transform.{bn}.running_mean"].view(1, -1, 1, 1)
             rv = state[f"m_transform.{bn}.running_var"].view(1, -1, 1, 1)

@@ -85,7 +85,8 @@ def _oracle_taps(x, y, state, fwd, feat=None):
         taps["frontend"] = leaf
         o = olcnn.embedding(leaf, state, taps)
     for v in taps.values():
-        v.retain_grad()
+        if v.requires_grad:  # the integer winner codes are not differentiable
+            v.retain_grad()
     torch.nn.functional.cross_entropy(torch.cat([-o, o], dim=1), y).backward()
     if feat is None:
         return o.detach(), taps, xc.grad
@@ -95,7 +96,7 @@ def _oracle_taps(x, y, state, fwd, feat=None):
 
 
 @pytest.mark.parametrize("conv_path", [0, 1], ids=["tcgen05", "simt"])
-@pytest.mark.parametrize("name", LCNN_CASES[:2])
+@pytest.mark.parametrize("name", LCNN_CASES[:3])
 def test_every_stage_forward_and_backward(name, conv_path, cuda_device):
     case, x, y, holder, state, fwd, eng = _setup(name, cuda_device)
     eng.set_option("conv_path", conv_path)
@@ -124,6 +125,19 @@ def test_every_stage_forward_and_backward(name, conv_path, cuda_device):
     for nm in ("feats", "lstm1", "lstm2"):
         t, _ = eng.debug_stage(nm)
         assert helpers.rel_err(t[:B, :, 0, :].cpu(), taps[nm].detach()) < 2e-5, nm
+    if conv_path == 0 and not case["silence"]:
+        # COUNT of Max-Feature-Map / max-pool winners the engine decides differently from the oracle: the
+        # gradient gates above are flip-robust, this bounds how many flips they absorb.  A winner decided by a margin below the
+        # fp32 noise of the conv sums (~1e-6 relative) may legitimately differ; measured 0-3 per block of up to 128 000 elements.
+        flips = {}
+        for i, (idx, _, _) in enumerate(BLOCKS):
+            t, _ = eng.debug_stage(f"codes{i}")
+            got = t[:B].permute(0, 3, 1, 2).cpu().long()
+            want = taps[f"codes{idx}"]
+            assert got.shape == want.shape, (i, got.shape, want.shape)
+            flips[f"block{i}"] = (int((got != want).sum()), want.numel())
+        print("winner flips vs oracle", name, flips)
+        assert all(n <= max(4, 1e-4 * tot) for n, tot in flips.values()), flips
     t, _ = eng.debug_stage("gcoef")  # (B,F,80,1): d loss / d cepstral image
     gc = t[:B].permute(0, 3, 2, 1).cpu()
     if not case["silence"]:
