@@ -14,6 +14,7 @@ LIB_PATH = os.environ.get("ADVB_LIB", LIB_PATH)  # tuning experiments: an altern
 MODEL_LCNN, MODEL_SPECRNET, MODEL_RAWNET3, MODEL_FRONTEND_ONLY = 1, 2, 3, 4
 FRONTEND_NONE, FRONTEND_LFCC, FRONTEND_MFCC = 0, 1, 2
 ATTACK_FGSM, ATTACK_PGD, ATTACK_PGDL2, ATTACK_FAB, ATTACK_CW = 1, 2, 3, 4, 5
+NORM_LINF, NORM_L2 = 0, 1
 GRAD_CE, GRAD_LOGIT = 0, 1
 
 
@@ -32,7 +33,7 @@ class AttackDesc(C.Structure):
     _fields_ = [
         ("kind", C.c_int), ("eps", C.c_float), ("alpha", C.c_float), ("steps", C.c_int), ("eps_div", C.c_float),
         ("alpha_max", C.c_float), ("eta", C.c_float), ("beta", C.c_float), ("c", C.c_float), ("kappa", C.c_float),
-        ("lr", C.c_float), ("n_global_batch", C.c_int), ("targeted", C.c_int), ("target_labels", C.c_void_p),
+        ("lr", C.c_float), ("n_global_batch", C.c_int), ("targeted", C.c_int), ("norm", C.c_int), ("target_labels", C.c_void_p),
     ]
 
 
@@ -58,6 +59,7 @@ SIGNATURES = {
     "advb_minmax": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p]),
     "advb_revert_minmax": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p]),
     "advb_projection_linf": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p]),
+    "advb_projection_l2": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p]),
     "advb_row_diff_norms": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p]),
     "advb_debug_stage": (C.c_int64, [C.c_void_p, C.c_char_p, C.c_void_p, C.c_int64, C.POINTER(C.c_int64), C.c_void_p]),
     "advb_launch_count": (C.c_int64, [C.c_void_p]),

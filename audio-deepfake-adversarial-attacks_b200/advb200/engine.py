@@ -298,6 +298,18 @@ def projection_linf(t: torch.Tensor, w: torch.Tensor, b: torch.Tensor) -> torch.
     return d
 
 
+def projection_l2(t: torch.Tensor, w: torch.Tensor, b: torch.Tensor) -> torch.Tensor:
+    """fab.py:617-665 on the GPU (rows independent)."""
+    _require_cuda(t, "the points")
+    lib = _lib.load()
+    t, w, b = t.contiguous(), w.contiguous(), b.contiguous()
+    d = torch.empty_like(t)
+    with torch.cuda.device(t.device):
+        _lib.check(lib.advb_projection_l2(t.data_ptr(), w.data_ptr(), b.data_ptr(), d.data_ptr(), t.shape[0], t.shape[1],
+                                          C.c_void_p(torch.cuda.current_stream(t.device).cuda_stream)))
+    return d
+
+
 def to_minmax(x: torch.Tensor):
     """src/aa/utils.py:4-9 on the GPU: returns (x01, mn (B,1), mx (B,1))."""
     _require_cuda(x, "the batch")

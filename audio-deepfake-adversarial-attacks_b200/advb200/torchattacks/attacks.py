@@ -73,16 +73,20 @@ class PGDL2(Attack):
 
 
 class FAB(Attack):
-    """fab.py:11-78, :495-526 (perturb), :131-307 (attack_single_run).  The native loop covers what the repo's
-    ``AttackEnum`` reaches: ``norm='Linf'``, untargeted, ``n_restarts=1`` (no random start).  The index selection of
-    the reference (attack only the clips that are still correctly classified) stays here as tensor plumbing; every
-    forward, gradient, projection and norm runs in libadvb200."""
+    """fab.py:11-78, :495-526 (perturb), :131-307 (attack_single_run): ``norm='Linf'`` (what the repo's ``AttackEnum``
+    reaches) and ``norm='L2'``, untargeted, any ``n_restarts``.  ``norm='L1'`` cannot run in the reference either
+    (``FAB.perturb`` never assigns ``res`` for it, fab.py:515-521: NameError) and raises here.  The index selection of the
+    reference (attack only the clips that are still correctly classified) stays here as tensor plumbing; every forward,
+    gradient, projection and norm runs in libadvb200."""
 
     def __init__(self, model, norm="Linf", eps=None, steps=100, n_restarts=1, alpha_max=0.1, eta=1.05, beta=0.9,
                  verbose=False, seed=0, targeted=False, n_classes=10):
         super().__init__("FAB", model)
-        if norm != "Linf":
-            raise NotImplementedError("advb200 FAB implements norm='Linf' (the AttackEnum presets); L2/L1 are SURVEY §8 f4")
+        if norm == "L1":
+            raise NotImplementedError("FAB norm='L1' does not run in the reference (fab.py:515-521 leaves `res` undefined); "
+                                      "advb200 provides 'Linf' and 'L2'")
+        if norm not in ("Linf", "L2"):
+            raise ValueError("norm not supported")  # fab.py:224
         # (the reference's patched copy ignores `targeted` too: fab.py:63 sets self.targeted = False unconditionally)
         self.norm = norm
         self.n_restarts = n_restarts
@@ -116,12 +120,18 @@ class FAB(Attack):
         im2, la2 = x[idx].contiguous(), y[idx].contiguous()
         start = None
         if use_rand_start:
-            # fab.py:176-206 (Linf): res2 is still 1e10 at this point, so the radius is eps; same RNG draw (torch.rand on
-            # the CPU generator, then moved - exactly what fab.py:178 does), same op order
-            t = 2 * torch.rand(im2.shape).to(im2.device) - 1
+            # fab.py:176-194: res2 is still 1e10 at this point, so the radius is eps; same RNG draw (torch.rand / torch.randn on
+            # the CPU generator, then moved - exactly what fab.py:178,185 do), same op order
             radius = torch.full((im2.shape[0], 1), float(self.eps), device=im2.device)
-            start = (im2 + radius * t / t.abs().max(dim=1, keepdim=True)[0] * .5).clamp(0.0, 1.0)
-        d = _desc(_lib.ATTACK_FAB, eps=self.eps, steps=self.steps, alpha_max=self.alpha_max, eta=self.eta, beta=self.beta)
+            if self.norm == "Linf":
+                t = 2 * torch.rand(im2.shape).to(im2.device) - 1
+                start = im2 + radius * t / t.abs().max(dim=1, keepdim=True)[0] * .5
+            else:
+                t = torch.randn(im2.shape).to(im2.device)
+                start = im2 + radius * t / (t ** 2).sum(dim=-1, keepdim=True).sqrt() * .5
+            start = start.clamp(0.0, 1.0)
+        d = _desc(_lib.ATTACK_FAB, eps=self.eps, steps=self.steps, alpha_max=self.alpha_max, eta=self.eta, beta=self.beta,
+                  norm=_lib.NORM_L2 if self.norm == "L2" else _lib.NORM_LINF)
         adv = self._engine(x).attack(d, im2, la2, start)  # rows never found adversarial come back equal to im2
         adv_c = x.clone()
         adv_c[idx] = adv
@@ -140,7 +150,8 @@ class FAB(Attack):
                 adv_curr = self.attack_single_run(x_to_fool, y_to_fool, use_rand_start=(counter > 0))
                 eng = self._engine(x)
                 acc_curr = self._get_predicted_label(adv_curr) == y_to_fool
-                res, _ = eng.row_diff_norms(x_to_fool, adv_curr)
+                linf, l2 = eng.row_diff_norms(x_to_fool, adv_curr)
+                res = l2 if self.norm == "L2" else linf  # fab.py:515-519
                 acc_curr = torch.max(acc_curr, res > self.eps)
                 ind_curr = (acc_curr == 0).nonzero().flatten()
                 acc[ind_to_fool[ind_curr]] = 0

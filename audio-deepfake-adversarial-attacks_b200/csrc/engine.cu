@@ -1093,10 +1093,12 @@ int run_attack(advb_handle* h, const advb_attack_desc* atk, const float* x, cons
       return 0;
     }
     case ADVB_ATTACK_FAB: {
-      // attack_single_run (fab.py:131-307) on a batch of correctly classified clips: L-inf, untargeted.  `start` = the
+      // attack_single_run (fab.py:131-307) on a batch of correctly classified clips: L-inf or L2 (atk->norm), untargeted.  `start` = the
       // random restart point x1 of fab.py:176-206 (nullable: x1 = x).  One backward per step (the class-0 gradient of
       // z = [-o, o] is the exact negation of class 1's).
       ADVB_CHECK(atk->steps >= 0, "bad step count");
+      ADVB_CHECK(atk->norm == ADVB_NORM_LINF || atk->norm == ADVB_NORM_L2, "FAB norm must be ADVB_NORM_LINF or ADVB_NORM_L2");
+      const int norm_l2 = atk->norm == ADVB_NORM_L2 ? 1 : 0;
       ADVB_CHECK(!minmax || start == nullptr, "FAB random restarts are not available through the min-max entry point");
       ADVB_TRY(ensure_fab_scratch(h));
       const long long* yl = reinterpret_cast<const long long*>(y);
@@ -1107,10 +1109,10 @@ int run_attack(advb_handle* h, const advb_attack_desc* atk, const float* x, cons
         ADVB_TRY(model_forward(h, h->fab.x1, B, st));
         ADVB_TRY(model_backward(h, h->fab.x1, y, B, ADVB_GRAD_LOGIT, n_global, h->grad, st));
         ADVB_TRY(fab_hyperplane(h->grad, h->logits, yl, h->fab, B, T, st));
-        ADVB_TRY(fab_project(xc, h->fab, B, T, st));
+        ADVB_TRY(fab_project(xc, h->fab, B, T, norm_l2, st));
         ADVB_TRY(fab_combine(xc, h->fab, atk->eta, atk->alpha_max, B, T, st));
         ADVB_TRY(model_forward(h, h->fab.x1, B, st));
-        ADVB_TRY(fab_bookkeep(xc, h->logits, yl, out, h->fab, atk->beta, B, T, st));
+        ADVB_TRY(fab_bookkeep(xc, h->logits, yl, out, h->fab, atk->beta, B, T, norm_l2, st));
       }
       break;
     }
@@ -1181,7 +1183,17 @@ int advb_invalidate_weights(advb_handle* h) {
   return 0;
 }
 
+static int projection_rows(const float* t, const float* w, const float* b, float* d, int R, int T, int norm_l2, void* cuda_stream);
+
 int advb_projection_linf(const float* t, const float* w, const float* b, float* d, int R, int T, void* cuda_stream) {
+  return projection_rows(t, w, b, d, R, T, 0, cuda_stream);
+}
+
+int advb_projection_l2(const float* t, const float* w, const float* b, float* d, int R, int T, void* cuda_stream) {
+  return projection_rows(t, w, b, d, R, T, 1, cuda_stream);
+}
+
+static int projection_rows(const float* t, const float* w, const float* b, float* d, int R, int T, int norm_l2, void* cuda_stream) {
   ADVB_CHECK(t && w && b && d && R > 0 && T > 0, "bad argument");
   cudaStream_t st = static_cast<cudaStream_t>(cuda_stream);
   // rows are independent: run them as the "x1" half of a FAB step whose second half is empty
@@ -1193,7 +1205,7 @@ int advb_projection_linf(const float* t, const float* w, const float* b, float* 
   s.bh = const_cast<float*>(b);
   s.d3 = d;
   s.a0 = a0;
-  const int rc = fab_project_rows(s, R, T, st);
+  const int rc = fab_project_rows(s, R, T, norm_l2, st);
   cudaFreeAsync(a0, st);
   return rc;
 }

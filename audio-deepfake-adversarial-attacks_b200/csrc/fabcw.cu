@@ -1,4 +1,4 @@
-// FAB (Fast Adaptive Boundary, L-inf, untargeted, 2 classes) and CW (Carlini-Wagner L2) update kernels (sm_100a).
+// FAB (Fast Adaptive Boundary, L-inf / L2, untargeted, 2 classes) and CW (Carlini-Wagner L2) update kernels (sm_100a).
 //
 // Replaces the tensor arithmetic of adversarial_attacks/torchattacks/attacks/fab.py:131-307 (attack_single_run),
 // :562-614 (projection_linf) and cw.py:46-134.  The model forward / input-gradient backward between these kernels is
@@ -203,6 +203,136 @@ __global__ void __launch_bounds__(RT) fab_project_kernel(const float* __restrict
   if (tid == 0) a0[r] = amax;
 }
 
+// projection_l2 (fab.py:617-665) without a sort.  After the sign flip (c = <w,t> - b >= 0) the projection is
+//   d_i = -min(alpha, r_i) w_i,   r_i = max(t_i / w_i, (t_i - 1) / w_i)   (the alpha at which coordinate i reaches its box face),
+// with alpha the root of the monotone piecewise-linear  H(alpha) = sum_i w_i^2 min(alpha, r_i) = c.  The reference sorts r,
+// builds s[k] = -H(rs[k]) by cumulative sums and bisects over the sorted INDEX; its three branches are
+//   c4: c < w5 r_min            -> alpha = c / w5 (no coordinate saturates)                 (:644,659-661)
+//   c3: c > H(inf)              -> every coordinate at its face (the hyperplane is out of the box's reach)  (:645)
+//   c2: otherwise               -> alpha = (s[lb] + c) / ws[lb] + rs[lb] on the linear piece that contains the root (:662-666)
+// Here, as in the L-inf kernel above: one CTA per row, an 8-ary search over the float bit patterns of [r_min, r_max] for the
+// piece, then the same closed-form root.  Coordinates with |w| < 1e-8 never move (:627,667).
+__device__ __forceinline__ float fab_l2_r(float wi, float ti) {
+  if (fabsf(wi) < 1e-8f) return 1e12f;                                             // :627
+  float r = fmaxf(__fdiv_rn(ti, wi), __fdiv_rn(ti - 1.f, wi));                      // :626
+  r = fminf(fmaxf(r, -1e12f), 1e12f);
+  return r == -1e12f ? 1e12f : r;                                                  // :628
+}
+
+__global__ void __launch_bounds__(RT) fab_project_l2_kernel(const float* __restrict__ x1, const float* __restrict__ x0,
+                                                             const float* __restrict__ wmat, const float* __restrict__ bh,
+                                                             float* __restrict__ d3, float* __restrict__ a0, int B, int T) {
+  __shared__ float s_red[33];
+  const int r = blockIdx.x, rb = r < B ? r : r - B;
+  const float* t = (r < B ? x1 : x0) + (size_t)rb * T;
+  const float* w = wmat + (size_t)rb * T;
+  float* d = d3 + (size_t)r * T;
+  const int tid = threadIdx.x;
+
+  float wt = 0.f, w5 = 0.f;
+  for (int i = tid; i < T; i += RT) {
+    const float wi = w[i];
+    wt = fmaf(wi, t[i], wt);
+    w5 = fmaf(wi, wi, w5);
+  }
+  wt = block_reduce<OpSum>(wt, s_red);
+  w5 = block_reduce<OpSum>(w5, s_red);
+  const float c_in = wt - bh[rb];
+  const float sgn = c_in >= 0.f ? 1.f : -1.f;   // :622
+  const float c = sgn * c_in;                    // :624  (>= 0)
+
+  // H(inf) over the movable coordinates, range of r over them
+  float Hall = 0.f, rmin = INFINITY, rmax = -INFINITY;
+  for (int i = tid; i < T; i += RT) {
+    const float wi = sgn * w[i];
+    const float ri = fab_l2_r(wi, t[i]);
+    if (ri < 1e12f) {
+      Hall = fmaf(wi * wi, ri, Hall);
+      rmin = fminf(rmin, ri);
+      rmax = fmaxf(rmax, ri);
+    }
+  }
+  Hall = block_reduce<OpSum>(Hall, s_red);
+  rmin = block_reduce<OpMin>(rmin, s_red);
+  rmax = block_reduce<OpMax>(rmax, s_red);
+  const bool any_movable = rmin <= rmax;
+  const bool c4 = any_movable ? (c - w5 * rmin < 0.f) : true;   // s[:,0] + c < 0 with s[:,0] = -w5 rs[0]
+  const bool c3 = !c4 && (c - Hall > 0.f);                       // <d,w> + c > 0 with every coordinate at its face
+  float alpha = 0.f;
+  int mode = 0;  // 0: all faces (c3), 1: uniform alpha (c4), 2: saturating alpha (c2)
+  if (c4) {
+    mode = 1;
+    alpha = w5 > 0.f ? c / w5 : 0.f;
+  } else if (!c3) {
+    mode = 2;
+    // invariant: H(lo) <= c < ... cond(tau) := H(tau) - c >= 0 is false at lo and true at hi
+    unsigned lo = __float_as_uint(fmaxf(rmin, 0.f)), hi = __float_as_uint(fmaxf(rmax, 0.f));
+    while (hi - lo > 1u) {
+      const unsigned width = hi - lo;
+      float th[NTH], acc[NTH];
+#pragma unroll
+      for (int k = 0; k < NTH; ++k) {
+        th[k] = __uint_as_float(lo + (unsigned)(((unsigned long long)width * (k + 1)) >> 3));
+        acc[k] = 0.f;
+      }
+      for (int i = tid; i < T; i += RT) {
+        const float wi = sgn * w[i];
+        const float ri = fab_l2_r(wi, t[i]), w2 = wi * wi;
+        if (ri < 1e12f) {
+#pragma unroll
+          for (int k = 0; k < NTH; ++k) acc[k] = fmaf(w2, fminf(ri, th[k]), acc[k]);
+        }
+      }
+      unsigned new_lo = lo, new_hi = hi;
+      bool found = false;
+#pragma unroll
+      for (int k = 0; k < NTH; ++k) {
+        const float Hk = block_reduce<OpSum>(acc[k], s_red);
+        const unsigned bits = __float_as_uint(th[k]);
+        if (!found) {
+          if (Hk - c >= 0.f && bits > lo) {
+            new_hi = bits;
+            found = true;
+          } else {
+            new_lo = bits;
+          }
+        }
+      }
+      lo = new_lo;
+      hi = new_hi;
+    }
+    // root on the linear piece {r >= hi still free}: sum_{r < hi} w^2 r + alpha sum_{r >= hi} w^2 = c
+    const float hf = __uint_as_float(hi);
+    float below = 0.f, Wh = 0.f;
+    for (int i = tid; i < T; i += RT) {
+      const float wi = sgn * w[i];
+      const float ri = fab_l2_r(wi, t[i]), w2 = wi * wi;
+      if (ri >= hf) Wh += w2;  // includes the immovable coordinates, as the reference's ws does (their w^2 < 1e-16)
+      else below = fmaf(w2, ri, below);
+    }
+    below = block_reduce<OpSum>(below, s_red);
+    Wh = block_reduce<OpSum>(Wh, s_red);
+    alpha = Wh > 0.f ? (c - below) / Wh : 0.f;               // :663-664
+  }
+
+  float ss = 0.f;
+  for (int i = tid; i < T; i += RT) {
+    const float wi = sgn * w[i];
+    const float ri = fab_l2_r(wi, t[i]);
+    float di = 0.f;
+    if (fabsf(wi) > 1e-8f) {
+      const float face = -__fmul_rn(ri, wi);                   // :637
+      if (mode == 0) di = face;
+      else if (mode == 1) di = -__fmul_rn(alpha, wi);          // :661
+      else di = alpha > ri ? face : -__fmul_rn(alpha, wi);     // :665-666
+    }
+    d[i] = di;
+    ss = fmaf(di, di, ss);
+  }
+  ss = block_reduce<OpSum>(ss, s_red);
+  if (tid == 0) a0[r] = sqrtf(ss);
+}
+
 __global__ void fab_combine_kernel(const float* __restrict__ x0, float* __restrict__ x1, const float* __restrict__ d3,
                                    const float* __restrict__ a0, float eta, float alpha_max, int B, int T) {
   const int r = blockIdx.y;
@@ -220,17 +350,26 @@ __global__ void fab_combine_kernel(const float* __restrict__ x0, float* __restri
 __global__ void __launch_bounds__(RT) fab_bookkeep_kernel(const float* __restrict__ x0, const float* __restrict__ logits,
                                                            const long long* __restrict__ y, float* __restrict__ adv,
                                                            float* __restrict__ x1, float* __restrict__ res2, float beta,
-                                                           int T) {
+                                                           int T, int norm_l2) {
   __shared__ float s_red[33];
   const int r = blockIdx.x;
   const long long pred = logits[r] > 0.f ? 1 : 0;  // argmax of [-o, o]; a tie goes to class 0 (torch.max)
   if (pred == y[r]) return;                        // not adversarial: nothing changes (fab.py:269-271)
   float tmax = 0.f;
-  for (int i = threadIdx.x; i < T; i += RT) {
-    const size_t o = (size_t)r * T + i;
-    tmax = fmaxf(tmax, fabsf(__fsub_rn(x1[o], x0[o])));
+  if (norm_l2) {                                   // :277-279
+    for (int i = threadIdx.x; i < T; i += RT) {
+      const size_t o = (size_t)r * T + i;
+      const float df = __fsub_rn(x1[o], x0[o]);
+      tmax = fmaf(df, df, tmax);
+    }
+    tmax = sqrtf(block_reduce<OpSum>(tmax, s_red));
+  } else {                                         // :274-276
+    for (int i = threadIdx.x; i < T; i += RT) {
+      const size_t o = (size_t)r * T + i;
+      tmax = fmaxf(tmax, fabsf(__fsub_rn(x1[o], x0[o])));
+    }
+    tmax = block_reduce<OpMax>(tmax, s_red);
   }
-  tmax = block_reduce<OpMax>(tmax, s_red);
   const bool better = tmax < res2[r];
   for (int i = threadIdx.x; i < T; i += RT) {
     const size_t o = (size_t)r * T + i;
@@ -379,14 +518,17 @@ int fab_hyperplane(const float* g, const float* logits, const long long* y, cons
   ADVB_KERNEL_OK("fab_hyperplane", stream);
   return 0;
 }
-int fab_project(const float* x0, const FabScratch& s, int B, int T, cudaStream_t stream) {
-  fab_project_kernel<<<2 * B, RT, 0, stream>>>(s.x1, x0, s.w, s.bh, s.d3, s.a0, B, T);
-  ADVB_KERNEL_OK("fab_project", stream);
+int fab_project(const float* x0, const FabScratch& s, int B, int T, int norm_l2, cudaStream_t stream) {
+  if (norm_l2) fab_project_l2_kernel<<<2 * B, RT, 0, stream>>>(s.x1, x0, s.w, s.bh, s.d3, s.a0, B, T);
+  else fab_project_kernel<<<2 * B, RT, 0, stream>>>(s.x1, x0, s.w, s.bh, s.d3, s.a0, B, T);
+  ADVB_KERNEL_OK(norm_l2 ? "fab_project_l2" : "fab_project", stream);
   return 0;
 }
-int fab_project_rows(const FabScratch& s, int R, int T, cudaStream_t stream) {
-  fab_project_kernel<<<R, RT, 0, stream>>>(s.x1, s.x1, s.w, s.bh, s.d3, s.a0, R, T);  // r < B = R for every row
-  ADVB_KERNEL_OK("fab_project", stream);
+int fab_project_rows(const FabScratch& s, int R, int T, int norm_l2, cudaStream_t stream) {
+  // r < B = R for every row
+  if (norm_l2) fab_project_l2_kernel<<<R, RT, 0, stream>>>(s.x1, s.x1, s.w, s.bh, s.d3, s.a0, R, T);
+  else fab_project_kernel<<<R, RT, 0, stream>>>(s.x1, s.x1, s.w, s.bh, s.d3, s.a0, R, T);
+  ADVB_KERNEL_OK(norm_l2 ? "fab_project_l2" : "fab_project", stream);
   return 0;
 }
 int fab_combine(const float* x0, const FabScratch& s, float eta, float alpha_max, int B, int T, cudaStream_t stream) {
@@ -396,8 +538,8 @@ int fab_combine(const float* x0, const FabScratch& s, float eta, float alpha_max
   return 0;
 }
 int fab_bookkeep(const float* x0, const float* logits, const long long* y, float* adv, const FabScratch& s, float beta,
-                 int B, int T, cudaStream_t stream) {
-  fab_bookkeep_kernel<<<B, RT, 0, stream>>>(x0, logits, y, adv, s.x1, s.res2, beta, T);
+                 int B, int T, int norm_l2, cudaStream_t stream) {
+  fab_bookkeep_kernel<<<B, RT, 0, stream>>>(x0, logits, y, adv, s.x1, s.res2, beta, T, norm_l2);
   ADVB_KERNEL_OK("fab_bookkeep", stream);
   return 0;
 }

@@ -1,4 +1,4 @@
-// FAB (L-inf, untargeted, 2 classes) and CW kernels — see fabcw.cu.
+// FAB (L-inf / L2, untargeted, 2 classes) and CW kernels — see fabcw.cu.
 #pragma once
 #include "common.cuh"
 
@@ -9,8 +9,8 @@ struct FabScratch {
   float* d3;      // (2B,T) projections of x1 (rows 0..B-1) and of the original clip (rows B..2B-1)
   float* w;       // (B,T) hyperplane normal  dg = +-2 d o / d x1
   float* bh;      // (B)   hyperplane offset b
-  float* a0;      // (2B)  L-inf norm of each projection row
-  float* res2;    // (B)   best L-inf distance of an adversarial iterate so far (1e10 = none)
+  float* a0;      // (2B)  L-inf (L2) norm of each projection row
+  float* res2;    // (B)   best L-inf (L2) distance of an adversarial iterate so far (1e10 = none)
 };
 
 // x1 <- x, adv <- x, res2 <- 1e10                                                   (fab.py:165-170)
@@ -19,14 +19,15 @@ int fab_init(const float* x, float* adv, const FabScratch& s, int B, int T, cuda
 int fab_hyperplane(const float* g, const float* logits, const long long* y, const FabScratch& s, int B, int T,
                    cudaStream_t stream);
 // d3 = projection_linf(cat(x1, x0), cat(w, w), cat(b, b)); a0 = row L-inf norms      (fab.py:232-235,562-614)
-int fab_project(const float* x0, const FabScratch& s, int B, int T, cudaStream_t stream);
-// R independent rows: t = s.x1, w = s.w, b = s.bh -> d = s.d3, a0 = s.a0 (test entry advb_projection_linf)
-int fab_project_rows(const FabScratch& s, int R, int T, cudaStream_t stream);
+// norm_l2: projection_l2 and row L2 norms instead                                  (fab.py:236-240,251-253,617-665)
+int fab_project(const float* x0, const FabScratch& s, int B, int T, int norm_l2, cudaStream_t stream);
+// R independent rows: t = s.x1, w = s.w, b = s.bh -> d = s.d3, a0 = s.a0 (test entries advb_projection_linf / _l2)
+int fab_project_rows(const FabScratch& s, int R, int T, int norm_l2, cudaStream_t stream);
 // alpha = clamp(a1 / (a1 + a2), 0, alpha_max); x1 = clamp((x1 + eta d1)(1 - alpha) + (x0 + eta d2) alpha, 0, 1)   (fab.py:249-267)
 int fab_combine(const float* x0, const FabScratch& s, float eta, float alpha_max, int B, int T, cudaStream_t stream);
 // rows whose new prediction differs from the label: keep the closest one in adv/res2, step back by beta (fab.py:269-290)
 int fab_bookkeep(const float* x0, const float* logits, const long long* y, float* adv, const FabScratch& s, float beta,
-                 int B, int T, cudaStream_t stream);
+                 int B, int T, int norm_l2, cudaStream_t stream);
 
 struct CwScratch {
   float *w, *m, *v;   // (B,T) tanh-space variable and Adam moments

@@ -18,7 +18,7 @@
 extern "C" {
 #endif
 
-#define ADVB_VERSION 200
+#define ADVB_VERSION 201
 #if defined(__GNUC__)
 #define ADVB_API __attribute__((visibility("default")))
 #else
@@ -33,6 +33,7 @@ enum { ADVB_MODEL_LCNN = 1, ADVB_MODEL_SPECRNET = 2, ADVB_MODEL_RAWNET3 = 3,
 enum { ADVB_FRONTEND_NONE = 0, ADVB_FRONTEND_LFCC = 1, ADVB_FRONTEND_MFCC = 2 };
 /* attack kinds: adversarial_attacks/torchattacks/attacks/{fgsm,pgd,pgdl2,fab,cw}.py */
 enum { ADVB_ATTACK_FGSM = 1, ADVB_ATTACK_PGD = 2, ADVB_ATTACK_PGDL2 = 3, ADVB_ATTACK_FAB = 4, ADVB_ATTACK_CW = 5 };
+enum { ADVB_NORM_LINF = 0, ADVB_NORM_L2 = 1 }; /* advb_attack_desc.norm (FAB) */
 /* what advb_grad differentiates */
 enum { ADVB_GRAD_CE = 0 /* mean 2-class cross-entropy, fgsm.py:43-57 */, ADVB_GRAD_LOGIT = 1 /* d o_i / d x_i, fab.py:90-105 */ };
 
@@ -76,6 +77,9 @@ typedef struct {
   int n_global_batch; /* N of the CE mean when the batch is sharded over ranks (0 = use B) */
   int targeted;       /* attack.py:60-108 targeted modes: cost = -loss(outputs, target_labels) (fgsm.py:49-50, pgd.py:64-65,
                          pgdl2.py:69-70); CW: f = clamp(i - j, -kappa) on the target one-hot (cw.py:82-83,131-132) */
+  int norm;           /* FAB: ADVB_NORM_LINF (0, the AttackEnum presets) or ADVB_NORM_L2 (fab.py:55,184-194,216-219,236-240,
+                         251-253,277-279).  L1 cannot run in the reference (FAB.perturb never defines `res` for it, fab.py:515-521)
+                         and is not provided.  Occupies what used to be padding: the layout of every other field is unchanged */
   const int64_t* target_labels; /* [B] int64 device pointer, required when targeted != 0 (the host evaluates the
                          target_map_function, attack.py:258-270) */
 } advb_attack_desc;
@@ -155,6 +159,8 @@ ADVB_API int advb_revert_minmax(const float* x01, const float* mn, const float* 
 /* Replaces projection_linf(points_to_project, w_hyperplane, b_hyperplane) (fab.py:562-614): for each of R rows the
  * minimal-L-inf move d with <w, t + d> = b, t + d in [0,1]^T.  t, w, d: [R,T]; b: [R].  Test / f4 entry point. */
 ADVB_API int advb_projection_linf(const float* t, const float* w, const float* b, float* d, int R, int T, void* cuda_stream);
+/* Same contract for fab.py:617-665 (projection_l2): the minimum-L2 step onto the hyperplane inside the box. */
+ADVB_API int advb_projection_l2(const float* t, const float* w, const float* b, float* d, int R, int T, void* cuda_stream);
 
 /* Per-clip perturbation norms  ||a_i - b_i||_inf  and  ||a_i - b_i||_2  (either output nullable): the row reductions of
  * FAB.perturb (fab.py:515-521) and of the L-inf / L2 parity gates. */

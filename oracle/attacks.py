@@ -137,8 +137,63 @@ def projection_linf(t, w, b):
     return d * (w != 0).float()
 
 
-def fab_single_run(model_fn, x, y, steps=100, alpha_max=0.1, eta=1.05, beta=0.9, trace=None):
-    """fab.py:131-307 with norm='Linf', use_rand_start=False."""
+def projection_l2(t, w, b):
+    """fab.py:617-665, statement by statement (rows independent)."""
+    import math
+
+    import torch.nn.functional as F
+
+    w = w.clone()
+    c = (w * t).sum(1) - b
+    ind2 = 2 * (c >= 0) - 1
+    w.mul_(ind2.unsqueeze(1))
+    c = c * ind2
+    r = torch.max(t / w, (t - 1) / w).clamp(min=-1e12, max=1e12)
+    r.masked_fill_(w.abs() < 1e-8, 1e12)
+    r[r == -1e12] *= -1
+    rs, indr = torch.sort(r, dim=1)
+    rs2 = F.pad(rs[:, 1:], (0, 1))
+    rs.masked_fill_(rs == 1e12, 0)
+    rs2.masked_fill_(rs2 == 1e12, 0)
+    w3s = (w ** 2).gather(1, indr)
+    w5 = w3s.sum(dim=1, keepdim=True)
+    ws = w5 - torch.cumsum(w3s, dim=1)
+    d = -(r * w)
+    d.mul_((w.abs() > 1e-8).float())
+    s = torch.cat((-w5 * rs[:, 0:1], torch.cumsum((-rs2 + rs) * ws, dim=1) - w5 * rs[:, 0:1]), 1)
+    c4 = s[:, 0] + c < 0
+    c3 = (d * w).sum(dim=1) + c > 0
+    c2 = ~(c4 | c3)
+    lb = torch.zeros(int(c2.sum()))
+    ub = torch.full_like(lb, w.shape[1] - 1)
+    nitermax = math.ceil(math.log2(w.shape[1]))
+    s_, c_ = s[c2], c[c2]
+    for _ in range(nitermax):
+        counter4 = torch.floor((lb + ub) / 2)
+        counter2 = counter4.long().unsqueeze(1)
+        c3b = s_.gather(1, counter2).squeeze(1) + c_ > 0
+        lb = torch.where(c3b, counter4, lb)
+        ub = torch.where(c3b, ub, counter4)
+    lb = lb.long()
+    if c4.any():
+        alpha = c[c4] / w5[c4].squeeze(-1)
+        d[c4] = -alpha.unsqueeze(-1) * w[c4]
+    if c2.any():
+        alpha = (s[c2, lb] + c[c2]) / ws[c2, lb] + rs[c2, lb]
+        alpha[ws[c2, lb] == 0] = 0
+        c5 = (alpha.unsqueeze(-1) > r[c2]).float()
+        d[c2] = d[c2] * c5 - alpha.unsqueeze(-1) * w[c2] * (1 - c5)
+    return d * (w.abs() > 1e-8).float()
+
+
+def _row_norm(v, norm):
+    """The per-row norm FAB uses for its distances (fab.py:248-256,273-281)."""
+    v = v.reshape(v.shape[0], -1)
+    return v.abs().max(dim=1)[0] if norm == "Linf" else (v ** 2).sum(dim=-1).sqrt()
+
+
+def fab_single_run(model_fn, x, y, steps=100, alpha_max=0.1, eta=1.05, beta=0.9, trace=None, norm="Linf", start=None):
+    """fab.py:131-307 with norm='Linf' / 'L2'; ``start`` = the random restart point of :176-194 (None: no random start)."""
     x = x.detach().clone()
     pred = predicted_label(model_fn, x) == y
     if pred.sum() == 0:
@@ -150,6 +205,9 @@ def fab_single_run(model_fn, x, y, steps=100, alpha_max=0.1, eta=1.05, beta=0.9,
     adv, adv_c = im2.clone(), x.clone()
     res2 = 1e10 * torch.ones(bs)
     x1, x0 = im2.clone(), im2.clone().reshape(bs, -1)
+    if start is not None:
+        x1 = start[pred].clone()
+    proj = projection_linf if norm == "Linf" else projection_l2
     for _ in range(steps):
         o, g = logit_and_grad(model_fn, x1)
         z = torch.cat([-o, o], dim=1)
@@ -157,14 +215,17 @@ def fab_single_run(model_fn, x, y, steps=100, alpha_max=0.1, eta=1.05, beta=0.9,
         df = z - z[u1, la2].unsqueeze(1)
         dg = g2 - g2[u1, la2].unsqueeze(1)
         df[u1, la2] = 1e10
-        dist1 = df.abs() / (1e-12 + dg.abs().view(bs, 2, -1).sum(dim=-1))
+        if norm == "Linf":
+            dist1 = df.abs() / (1e-12 + dg.abs().view(bs, 2, -1).sum(dim=-1))
+        else:
+            dist1 = df.abs() / (1e-12 + (dg ** 2).view(bs, 2, -1).sum(dim=-1).sqrt())
         ind = dist1.min(dim=1)[1]
         dg2 = dg[u1, ind]
         b = -df[u1, ind] + (dg2 * x1).view(bs, -1).sum(dim=-1)
         w = dg2.reshape(bs, -1)
-        d3 = projection_linf(torch.cat((x1.reshape(bs, -1), x0), 0), torch.cat((w, w), 0), torch.cat((b, b), 0))
+        d3 = proj(torch.cat((x1.reshape(bs, -1), x0), 0), torch.cat((w, w), 0), torch.cat((b, b), 0))
         d1, d2 = d3[:bs].reshape(x1.shape), d3[-bs:].reshape(x1.shape)
-        a0 = d3.abs().max(dim=1, keepdim=True)[0]
+        a0 = _row_norm(d3, norm).unsqueeze(1)
         a0 = torch.max(a0, 1e-8 * torch.ones_like(a0))
         a1, a2 = a0[:bs], a0[-bs:]
         alpha = torch.min(torch.max(a1 / (a1 + a2), torch.zeros_like(a1)), alpha_max * torch.ones_like(a1))
@@ -174,7 +235,7 @@ def fab_single_run(model_fn, x, y, steps=100, alpha_max=0.1, eta=1.05, beta=0.9,
             trace.append(dict(o=o.clone(), linf_d3=a0.clone(), x1=x1.clone(), is_adv=is_adv.clone()))
         if is_adv.sum() > 0:
             ia = is_adv.nonzero().flatten()
-            t = (x1[ia] - im2[ia]).reshape(ia.shape[0], -1).abs().max(dim=1)[0]
+            t = _row_norm(x1[ia] - im2[ia], norm)
             better = (t < res2[ia]).float().unsqueeze(1)
             adv[ia] = x1[ia] * better + adv[ia] * (1 - better)
             res2[ia] = t * (t < res2[ia]).float() + res2[ia] * (t >= res2[ia]).float()
@@ -184,8 +245,8 @@ def fab_single_run(model_fn, x, y, steps=100, alpha_max=0.1, eta=1.05, beta=0.9,
     return adv_c
 
 
-def fab(model_fn, x, y, eps=0.3, steps=100, alpha_max=0.1, eta=1.05, beta=0.9):
-    """fab.py:495-526 (n_restarts=1, untargeted, Linf).  The reference reseeds torch's global RNG here (:504-505);
+def fab(model_fn, x, y, eps=0.3, steps=100, alpha_max=0.1, eta=1.05, beta=0.9, norm="Linf"):
+    """fab.py:495-526 (n_restarts=1, untargeted, Linf / L2).  The reference reseeds torch's global RNG here (:504-505);
     with one restart no random number is consumed."""
     adv = x.clone()
     acc = predicted_label(model_fn, x) == y
@@ -193,9 +254,9 @@ def fab(model_fn, x, y, eps=0.3, steps=100, alpha_max=0.1, eta=1.05, beta=0.9):
     if idx.numel() == 0:
         return adv
     xf, yf = x[idx].clone(), y[idx].clone()
-    cur = fab_single_run(model_fn, xf, yf, steps, alpha_max, eta, beta)
+    cur = fab_single_run(model_fn, xf, yf, steps, alpha_max, eta, beta, norm=norm)
     still = predicted_label(model_fn, cur) == yf
-    res = (xf - cur).abs().view(xf.shape[0], -1).max(1)[0]
+    res = _row_norm(xf - cur, norm)
     still = torch.max(still, res > eps)
     ok = (still == 0).nonzero().flatten()
     adv[idx[ok]] = cur[ok].clone()

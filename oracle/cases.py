@@ -31,6 +31,9 @@ CASES = {
     # exercises FAB's "attack only the correctly classified clips" path (fab.py:506-513)
     "lcnn_lfcc_t16000_margin": dict(model="lcnn", frontend="lfcc", T=16000, B=4, cfg_id=14, silence=False,
                                     margin=0.01, labels=(1, 1, 0, 1), attacks=("fab", "cw", "cw_strong")),
+    # same clips, weights and labels (same cfg_id): FAB with norm='L2' (fab.py:184-194,216-219,236-240,617-665)
+    "lcnn_lfcc_t16000_margin_l2": dict(model="lcnn", frontend="lfcc", T=16000, B=4, cfg_id=14, silence=False,
+                                       margin=0.01, labels=(1, 1, 0, 1), attacks=("fab_l2",)),
 }
 DEFAULT_ATTACKS = ("fgsm", "pgd", "pgdl2")
 
@@ -39,6 +42,7 @@ ATTACKS = {
     "pgd": dict(eps=0.001, alpha=2 / 255, steps=3),
     "pgdl2": dict(eps=0.1, alpha=0.2, steps=3),
     "fab": dict(eps=0.3, steps=8, eta=10.0, alpha_max=0.1, beta=0.9),   # AttackEnum.FAB preset, fewer steps
+    "fab_l2": dict(eps=2.0, steps=8, eta=1.05, alpha_max=0.1, beta=0.9, norm="L2"),
     "cw": dict(c=1e-4, kappa=0.0, steps=20, lr=0.01),
     # CW with the classification term dominating the fp32 rounding noise of tanh(atanh(.)): elements are comparable, clips flip
     # at steps 4-5 (best-adversarial mask path) and the batch-wide early stop fires at step 8 (cw.py:107-110)

@@ -74,8 +74,8 @@ def main():
 
         for an in case.get("attacks", cases.DEFAULT_ATTACKS):
             ap = cases.ATTACKS[an]
-            if an == "fab":
-                atk = torchattacks.FAB(ref, norm="Linf", eps=ap["eps"], steps=ap["steps"], eta=ap["eta"],
+            if an.startswith("fab"):
+                atk = torchattacks.FAB(ref, norm=ap.get("norm", "Linf"), eps=ap["eps"], steps=ap["steps"], eta=ap["eta"],
                                        alpha_max=ap["alpha_max"], beta=ap["beta"], n_classes=2)
             elif an.startswith("cw"):
                 atk = torchattacks.CW(ref, c=ap["c"], kappa=ap["kappa"], steps=ap["steps"], lr=ap["lr"])

@@ -43,8 +43,8 @@ def oracle_attack(name, attack, x, y, state, fwd, case):
     model_fn = lambda v: fwd(v, state)  # noqa: E731
     if attack == "fgsm":
         return oatk.fgsm(model_fn, x, y, p["eps"])
-    if attack == "fab":
-        return oatk.fab(model_fn, x, y, p["eps"], p["steps"], p["alpha_max"], p["eta"], p["beta"])
+    if attack.startswith("fab"):
+        return oatk.fab(model_fn, x, y, p["eps"], p["steps"], p["alpha_max"], p["eta"], p["beta"], norm=p.get("norm", "Linf"))
     if attack.startswith("cw"):
         return oatk.cw(model_fn, x, y, p["c"], p["kappa"], p["steps"], p["lr"])
     if attack == "pgd":

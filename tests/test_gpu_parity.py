@@ -370,6 +370,78 @@ def test_projection_linf_against_oracle(cuda_device):
     np.testing.assert_allclose((w * (t + got)).sum(1)[hit].numpy(), b[hit].numpy(), rtol=1e-3, atol=2e-5)
 
 
+def test_projection_l2_against_oracle(cuda_device):
+    """fab.py:617-665: the sort-free CUDA projection against the sort-based restatement, all three branches (no coordinate
+    saturates / some saturate / the hyperplane is out of the box's reach), immovable coordinates, ragged row length."""
+    from advb200 import engine
+
+    g = torch.Generator("cpu").manual_seed(12)
+    R, T = 12, 16001
+    t = torch.rand(R, T, generator=g)
+    w = torch.randn(R, T, generator=g) * 1e-3
+    w[3, ::7] = 0.0                          # |w| < 1e-8: never move
+    w[5, ::5] = 5e-9
+    z = torch.rand(R, T, generator=g)
+    b = (w * z).sum(1)                       # hyperplane through a box point: saturating alpha (c2)
+    t[:2] = 0.3 + 0.4 * t[:2]                # away from the faces, so that a well-conditioned offset stays in branch c4
+    b[0] = (w[0] * t[0]).sum() + 1e-2        # close to the plane: uniform alpha, no coordinate saturates (c4)
+    b[1] = (w[1] * t[1]).sum() - 2e-2
+    b[2] = (w[2].abs()).sum() * 5            # does not meet the box: every coordinate at its face (c3)
+    t[4, :100] = 0.0                         # already at a face
+    t[4, 100:200] = 1.0
+    want = oatk.projection_l2(t, w, b)
+    got = engine.projection_l2(t.to(cuda_device), w.to(cuda_device), b.to(cuda_device)).cpu()
+    # the attack only uses d through x + eta d and ||d||_2: compare at those scales
+    scale = want.abs().amax(dim=1).clamp_min(1e-12)
+    assert ((got - want).abs().amax(dim=1) / scale).max().item() < 2e-4
+    np.testing.assert_allclose(got.norm(dim=1).numpy(), want.norm(dim=1).numpy(), rtol=2e-4)
+    hit = [i for i in range(R) if i != 2]
+    np.testing.assert_allclose((w * (t + got)).sum(1)[hit].numpy(), b[hit].numpy(), rtol=1e-3, atol=2e-5)
+    assert (got[3, ::7] == 0).all() and (got[5, ::5] == 0).all()
+    assert ((t + got) >= -1e-6).all() and ((t + got) <= 1 + 1e-6).all()
+
+
+def test_fab_l2_against_oracle_and_golden(cuda_device):
+    """torchattacks.FAB(norm='L2') (fab.py:184-194,216-219,236-240,251-253,277-279,617-665) against the
+    fixture the unmodified reference produced; norm='L1' cannot run upstream either and must say so."""
+    from advb200 import torchattacks as ta
+
+    name, attack = "lcnn_lfcc_t16000_margin_l2", "fab_l2"
+    case, x, y, holder, state, fwd, eng = _setup(name, cuda_device)
+    g = helpers.load_golden(name)
+    p = cases.ATTACKS[attack]
+    xd, yd = x.to(cuda_device), y.to(cuda_device)
+    atk = ta.FAB(holder, norm="L2", eps=p["eps"], steps=p["steps"], eta=p["eta"], alpha_max=p["alpha_max"], beta=p["beta"],
+                 n_classes=2)
+    atk.set_training_mode(True, False)
+    got = atk(xd, yd).cpu()
+    assert torch.equal(xd.cpu(), x) and got.min().item() >= 0.0 and got.max().item() <= 1.0
+    d = got - x
+    ref = torch.from_numpy(g["fab_l2_adv"])
+    # FAB-L2's own norm is L2
+    np.testing.assert_allclose(d.norm(p=2, dim=1).numpy(), g["fab_l2_delta_l2"], rtol=1e-4, atol=1e-6)
+    np.testing.assert_allclose(d.abs().amax(dim=1).numpy(), g["fab_l2_delta_linf"], rtol=1e-3, atol=1e-6)
+    assert torch.equal(got[2], x[2]), "a clip that is misclassified from the start must come back untouched"
+    # the L2 step is proportional to the gradient itself: elements agree to the gradient's own parity
+    assert helpers.rel_err(d, ref - x) < 5e-3  # oracle vs reference: 1e-3 (tests/test_oracle_golden.py)
+    la = eng.forward(got.to(cuda_device)).cpu().numpy()
+    # the returned iterates sit ON the decision boundary (reference logits -2e-7 ... -4e-6): their sign is below the fp32 noise
+    # of any two forwards; what is comparable is that they are as close to it
+    np.testing.assert_allclose(la[[0, 1, 3]], g["fab_l2_logits_adv"][[0, 1, 3]], atol=2e-5)
+    assert la[2] > 0
+    lr = eng.forward(ref.to(cuda_device)).cpu().numpy()
+    np.testing.assert_allclose(lr, g["fab_l2_logits_adv"], atol=3e-6)
+    # restarts (fab.py:184-194): the L2 random start stays inside the eps / 2 ball and the result never loses an adversarial clip
+    two = ta.FAB(holder, norm="L2", eps=p["eps"], steps=p["steps"], eta=p["eta"], alpha_max=p["alpha_max"], beta=p["beta"],
+                 n_classes=2, n_restarts=2)
+    two.set_training_mode(True, False)
+    got2 = two(xd, yd).cpu()
+    assert ((got2 != x).any(dim=1) | ~(got != x).any(dim=1)).all()
+    assert (got2 - x).norm(p=2, dim=1).max().item() <= p["eps"] + 1e-5
+    with pytest.raises(NotImplementedError):
+        ta.FAB(holder, norm="L1")
+
+
 @pytest.mark.parametrize("attack", ["fab", "cw"])
 def test_fab_cw_against_oracle_and_golden(attack, cuda_device):
     from advb200 import torchattacks as ta

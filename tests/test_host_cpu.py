@@ -21,15 +21,15 @@ def test_library_exports_every_declared_symbol():
     assert declared == set(_lib.SIGNATURES), declared ^ set(_lib.SIGNATURES)
     for name in declared:
         assert isinstance(getattr(lib, name), ctypes._CFuncPtr)
-    assert lib.advb_version() == 200
+    assert lib.advb_version() == 201
 
 
 def test_struct_layout_matches_header():
     from advb200 import _lib
 
     assert ctypes.sizeof(_lib.TensorRef) == 24
-    assert ctypes.sizeof(_lib.AttackDesc) == 12 * 4 + 4 + 4 + 8  # + targeted, padding, target_labels pointer
-    assert _lib.AttackDesc.target_labels.offset == 56 and _lib.AttackDesc.targeted.offset == 48
+    assert ctypes.sizeof(_lib.AttackDesc) == 12 * 4 + 4 + 4 + 8  # + targeted, norm (the former padding), target_labels pointer
+    assert _lib.AttackDesc.target_labels.offset == 56 and _lib.AttackDesc.targeted.offset == 48 and _lib.AttackDesc.norm.offset == 52
     assert ctypes.sizeof(_lib.ModelDesc) == 6 * 4 + 8
 
 
