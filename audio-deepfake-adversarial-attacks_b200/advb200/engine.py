@@ -310,6 +310,25 @@ def projection_l2(t: torch.Tensor, w: torch.Tensor, b: torch.Tensor) -> torch.Te
     return d
 
 
+def mel_spec_forward(audio: torch.Tensor, fb: torch.Tensor) -> torch.Tensor:
+    """src/frontends.py:53-79 on the GPU: (B, 2, n_mels, F) = [abs, angle] of the mel-scaled complex STFT.  Forward only."""
+    _require_cuda(audio, "the waveform")
+    if audio.requires_grad:
+        raise NotImplementedError("the mel_spec frontend is forward-only in advb200 (no model of the reference consumes it)")
+    squeeze = audio.dim() == 1
+    x = (audio.unsqueeze(0) if squeeze else audio).contiguous().float()
+    fbc = fb.to(x.device).contiguous().float()
+    if fbc.dim() != 2 or fbc.shape[0] != 257:
+        raise ValueError("mel filterbank must be (257, n_mels)")
+    lib = _lib.load()
+    B, T = x.shape
+    out = torch.empty(B, 2, fbc.shape[1], 1 + T // 160, device=x.device, dtype=torch.float32)
+    with torch.cuda.device(x.device):
+        _lib.check(lib.advb_mel_spec_fwd(x.data_ptr(), fbc.data_ptr(), fbc.shape[1], out.data_ptr(), B, T,
+                                         C.c_void_p(torch.cuda.current_stream(x.device).cuda_stream)))
+    return out[0] if squeeze else out
+
+
 def to_minmax(x: torch.Tensor):
     """src/aa/utils.py:4-9 on the GPU: returns (x01, mn (B,1), mx (B,1))."""
     _require_cuda(x, "the batch")

@@ -1,7 +1,8 @@
 """Frontend buffer holders (LFCC / MFCC) for the B200 engine.
 
-Mirrors the plugin surface of the reference's ``src/frontends.py:13-50``: module-level singletons
-``LFCC_FN`` / ``MFCC_FN`` and ``get_frontend(names)``.  The holders carry exactly the buffers the
+Mirrors the plugin surface of the reference's ``src/frontends.py:13-79``: module-level singletons
+``LFCC_FN`` / ``MFCC_FN`` / ``MEL_SCALE_FN``, ``get_frontend(names)`` and the `mel_spec` functions
+``prepare_mel_scale_vector`` / ``prepare_stft_features`` (forward only).  The holders carry exactly the buffers the
 reference's torchaudio transforms register, under the same state_dict keys:
 
     LFCC : ``filter_mat`` (257,128), ``dct_mat`` (128,80), ``Spectrogram.window`` (400,)
@@ -49,11 +50,11 @@ def linear_fbanks() -> torch.Tensor:
     return _triangular_filterbank(all_freqs, f_pts)
 
 
-def mel_fbanks() -> torch.Tensor:
+def mel_fbanks(n_mels: int = N_FILTER) -> torch.Tensor:
     all_freqs = torch.linspace(0, SAMPLING_RATE // 2, N_FREQS)
     m_min = 2595.0 * math.log10(1.0 + 0.0 / 700.0)
     m_max = 2595.0 * math.log10(1.0 + (float(SAMPLING_RATE // 2) / 700.0))
-    m_pts = torch.linspace(m_min, m_max, N_FILTER + 2)
+    m_pts = torch.linspace(m_min, m_max, n_mels + 2)
     f_pts = 700.0 * (10.0 ** (m_pts / 2595.0) - 1.0)
     return _triangular_filterbank(all_freqs, f_pts)
 
@@ -125,9 +126,39 @@ class MFCC(_Frontend):
         return self.MelSpectrogram.mel_scale.fb, self.dct_mat, self.MelSpectrogram.spectrogram.window
 
 
+class MelScale(nn.Module):
+    """Buffer holder of ``torchaudio.transforms.MelScale(n_mels=80, n_stft=257, sample_rate=16000)`` (src/frontends.py:34-38):
+    state_dict key ``fb`` (257,80).  Calling it on a (..., 257, F) tensor is the linear map ``fb^T @ x`` of the reference;
+    the `mel_spec` path itself runs in ``csrc/frontend.cu`` (fe_melspec_kernel)."""
+
+    def __init__(self, n_mels: int = N_COEFF):
+        super().__init__()
+        self.register_buffer("fb", mel_fbanks(n_mels))
+
+
 # module-level singletons shared by every model in the process, like the reference (SURVEY.md F6)
 MFCC_FN = MFCC()
 LFCC_FN = LFCC()
+MEL_SCALE_FN = MelScale()
+
+
+def prepare_stft_features(audio: torch.Tensor, win_length: int = WIN_LENGTH, hop_length: int = HOP_LENGTH):
+    """src/frontends.py:61-79: (|mel(STFT)|, angle(mel(STFT))), each (B, 80, F)."""
+    if win_length != WIN_LENGTH or hop_length != HOP_LENGTH:
+        raise NotImplementedError("advb200 implements the reference's own framing (win_length=400, hop_length=160)")
+    from . import engine
+
+    out = engine.mel_spec_forward(audio, MEL_SCALE_FN.fb)
+    return out[..., 0, :, :], out[..., 1, :, :]
+
+
+def prepare_mel_scale_vector(audio: torch.Tensor, win_length: int = WIN_LENGTH, hop_length: int = HOP_LENGTH) -> torch.Tensor:
+    """src/frontends.py:53-58: torch.stack([abs, angle], dim=1) -> (B, 2, 80, F)."""
+    if win_length != WIN_LENGTH or hop_length != HOP_LENGTH:
+        raise NotImplementedError("advb200 implements the reference's own framing (win_length=400, hop_length=160)")
+    from . import engine
+
+    return engine.mel_spec_forward(audio, MEL_SCALE_FN.fb)
 
 
 def get_frontend(frontends: List[str]):
@@ -135,6 +166,8 @@ def get_frontend(frontends: List[str]):
         return MFCC_FN
     elif "lfcc" in frontends:
         return LFCC_FN
+    elif "mel_spec" in frontends:
+        return prepare_mel_scale_vector
     raise ValueError(f"{frontends} frontend is not supported!")
 
 

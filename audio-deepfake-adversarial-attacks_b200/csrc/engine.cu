@@ -1210,6 +1210,11 @@ static int projection_rows(const float* t, const float* w, const float* b, float
   return rc;
 }
 
+int advb_mel_spec_fwd(const float* x, const float* fb, int n_mels, float* out, int B, int T, void* cuda_stream) {
+  ADVB_CHECK(x && fb && out && B > 0 && T > 0, "bad argument");
+  return frontend_mel_spec(x, fb, n_mels, out, B, T, static_cast<cudaStream_t>(cuda_stream));
+}
+
 int advb_row_diff_norms(const float* a, const float* b, float* linf, float* l2, int B, int T, void* cuda_stream) {
   ADVB_CHECK(a && b && (linf || l2) && B > 0 && T > 0, "bad argument");
   return row_diff_norms(a, b, linf, l2, B, T, static_cast<cudaStream_t>(cuda_stream));

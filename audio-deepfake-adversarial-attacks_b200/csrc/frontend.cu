@@ -136,7 +136,7 @@ __device__ __forceinline__ void load_frame_pair(const float* __restrict__ xb, in
   for (int n = lane; n < NFFT; n += 32) {
     float a = 0.f, b = 0.f;
     if (n >= WOFF && n < WOFF + WIN) {
-      const float w = s_win[n - WOFF];
+      const float w = s_win != nullptr ? s_win[n - WOFF] : 1.0f;  // no table: torch.stft's default rectangular window
       const int ja = HOP * ta + n - NFFT / 2;
       a = w * __ldg(xb + reflect_index(ja, T));
       if (has_b) b = w * __ldg(xb + reflect_index(ja + HOP, T));
@@ -310,6 +310,70 @@ __global__ void __launch_bounds__(FE_THREADS, 3) fe_power_db_kernel(const float*
     packed = other > packed ? other : packed;
   }
   if (lane == 0 && best_idx != 0xffffffffu) atomicMax(st.gmax_packed, packed);
+}
+
+// ---------------------------------------------------------------------------------------------------
+// `mel_spec` frontend (src/frontends.py:53-79, prepare_mel_scale_vector): torch.stft(n_fft 512, hop 160, win_length 400, no
+// window = ones(400) centred in the 512-sample frame, reflect-padded, one-sided), MelScale applied to the REAL and to the
+// IMAGINARY part separately (a linear map: fb^T re, fb^T im), then |.| and angle of the resulting complex number.
+// out (B, 2, n_mels, F): channel 0 = abs, channel 1 = angle.  Same two-frames-per-warp FFT as the cepstral frontends; the
+// filter sums read the packed spectrum directly (each bin feeds at most two triangular filters).
+constexpr int MS_MAX_MELS = 128;
+__global__ void __launch_bounds__(FE_THREADS, 3) fe_melspec_kernel(const float* __restrict__ x, int T, int F,
+                                                                     const float* __restrict__ fb, int n_mels,
+                                                                     float* __restrict__ out, int n_blocks, int n_clips) {
+  extern __shared__ __align__(16) float smem[];
+  float2* s_tw = reinterpret_cast<float2*>(smem);                    // 512 float2
+  int* s_klo = reinterpret_cast<int*>(smem + 1024);                  // MS_MAX_MELS
+  int* s_kcnt = s_klo + MS_MAX_MELS;
+  float2* s_fft = reinterpret_cast<float2*>(s_kcnt + MS_MAX_MELS);   // FE_WARPS * (FFT_A + FFT_B) float2
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  for (int k = tid; k < 512; k += FE_THREADS) {
+    float sn, cs;
+    sincospif(2.0f * (float)k / 512.0f, &sn, &cs);
+    s_tw[k] = make_float2(cs, -sn);
+  }
+  for (int m = tid; m < n_mels; m += FE_THREADS) {  // extent of each (triangular) filter in the live table
+    int lo = NBIN, hi = -1;
+    for (int k = 0; k < NBIN; ++k)
+      if (fb[(size_t)k * n_mels + m] != 0.f) {
+        if (k < lo) lo = k;
+        hi = k;
+      }
+    s_klo[m] = hi < 0 ? 0 : lo;
+    s_kcnt[m] = hi < 0 ? 0 : hi - lo + 1;
+  }
+  __syncthreads();
+  float2* bufA = s_fft + warp * (FFT_A + FFT_B);
+  float2* bufB = bufA + FFT_A;
+  for (int work = blockIdx.x; work < n_blocks * n_clips; work += gridDim.x) {
+    const int b = work / n_blocks;
+    const int ta = (work - b * n_blocks) * (2 * FE_WARPS) + 2 * warp;
+    if (ta >= F) continue;  // warp-uniform
+    const bool has_b = (ta + 1) < F;
+    load_frame_pair(x + (size_t)b * T, T, F, ta, nullptr, bufA, lane);
+    warp_fft512(bufA, bufB, s_tw, lane);
+    for (int m = lane; m < n_mels; m += 32) {
+      float ar = 0.f, ai = 0.f, br = 0.f, bi = 0.f;
+      const int k0 = s_klo[m], n = s_kcnt[m];
+      for (int i = 0; i < n; ++i) {
+        const float w = __ldg(fb + (size_t)(k0 + i) * n_mels + m);
+        float xar, xai, xbr, xbi;
+        unpack_bin(bufB, k0 + i, xar, xai, xbr, xbi);
+        ar = fmaf(xar, w, ar), ai = fmaf(xai, w, ai);
+        br = fmaf(xbr, w, br), bi = fmaf(xbi, w, bi);
+      }
+      float* o_abs = out + (((size_t)b * 2 + 0) * n_mels + m) * F + ta;
+      float* o_ang = out + (((size_t)b * 2 + 1) * n_mels + m) * F + ta;
+      o_abs[0] = hypotf(ar, ai);
+      o_ang[0] = atan2f(ai, ar);
+      if (has_b) {
+        o_abs[1] = hypotf(br, bi);
+        o_ang[1] = atan2f(bi, br);
+      }
+    }
+    __syncwarp();  // the next item's frame load overwrites buffer A / the spectrum in buffer B is re-used
+  }
 }
 
 __device__ __forceinline__ void decode_gmax(unsigned long long packed, float& vmax, unsigned& idx) {
@@ -737,6 +801,19 @@ int frontend_forward(const FrontendTables& tb, const FrontendState& st, const fl
   fe_floor_dct_kernel<<<g2, 256, fe_dct_smem(), stream>>>(dB, F, tb, st, 80.0f, out, clip_stride, stride_f, stride_c,
                                                          offset, B * F);
   ADVB_KERNEL_OK("fe_floor_dct", stream);
+  return 0;
+}
+
+int frontend_mel_spec(const float* x, const float* fb, int n_mels, float* out, int B, int T, cudaStream_t stream) {
+  ADVB_CHECK(T >= 512, "clip shorter than one FFT frame");
+  ADVB_CHECK(n_mels >= 1 && n_mels <= MS_MAX_MELS, "mel_spec: 1..128 mel filters");
+  const int F = frontend_frames(T);
+  const int n_fb = cdiv(F, 2 * FE_WARPS);
+  const size_t smem = (size_t)(1024 + 2 * MS_MAX_MELS) * sizeof(float) + (size_t)FE_WARPS * (FFT_A + FFT_B) * sizeof(float2);
+  ADVB_CUDA_OK(cudaFuncSetAttribute(fe_melspec_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));  // per device
+  const int grid = n_fb * B < 148 * 3 ? n_fb * B : 148 * 3;
+  fe_melspec_kernel<<<grid, FE_THREADS, smem, stream>>>(x, T, F, fb, n_mels, out, n_fb, B);
+  ADVB_KERNEL_OK("fe_melspec", stream);
   return 0;
 }
 

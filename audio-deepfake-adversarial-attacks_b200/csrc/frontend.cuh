@@ -53,6 +53,9 @@ int frontend_backward(const FrontendTables& tb, const FrontendState& st, const f
                       const float* dB, const float* gcoef, long long g_clip_stride, long long g_stride_f,
                       long long g_stride_c, float* mass_partial, float* gd, float* gx, cudaStream_t stream,
                       const FusedUpdate* upd = nullptr, const float2* spec = nullptr, FrontendHost* host = nullptr);
+// src/frontends.py:53-79 (`mel_spec`): out (B, 2, n_mels, F) = |.| and angle of (fb^T Re STFT, fb^T Im STFT); fb (257, n_mels) live
+// buffer (MEL_SCALE_FN.fb).  Stateless; forward only (no model of the reference consumes this 2-channel frontend).
+int frontend_mel_spec(const float* x, const float* fb, int n_mels, float* out, int B, int T, cudaStream_t stream);
 // reset the state now if a forward left it dirty (before a captured loop whose body assumes a clean state)
 int frontend_clean(const FrontendState& st, FrontendHost* host, cudaStream_t stream);
 // floats of the optional packed-spectrum buffer (B clips): `spec` of frontend_forward (written) / frontend_backward (read

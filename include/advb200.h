@@ -151,6 +151,12 @@ ADVB_API int advb_frontend_fwd(advb_handle* h, const float* x, float* coeff, int
 ADVB_API int advb_frontend_bwd(advb_handle* h, const float* x, const float* g_coeff, float* g_x, int B, int T,
                       void* cuda_stream);
 
+/* Replaces prepare_mel_scale_vector(audio) (src/frontends.py:53-79, the `mel_spec` frontend of get_frontend, :48-49):
+ * torch.stft(n_fft=512, hop=160, win_length=400, window=None) -> MEL_SCALE_FN on the real and on the imaginary part ->
+ * stack([abs, angle], dim=1).  x [B,T]; fb [257,n_mels] = MEL_SCALE_FN.fb (live buffer, n_mels <= 128); out [B,2,n_mels,F],
+ * F = 1 + T / 160.  Forward only: nothing in the reference differentiates through it (no model takes its 2 channels). */
+ADVB_API int advb_mel_spec_fwd(const float* x, const float* fb, int n_mels, float* out, int B, int T, void* cuda_stream);
+
 /* Replaces to_minmax / revert_minmax (src/aa/utils.py:4-14).  mn, mx: [B]. */
 ADVB_API int advb_minmax(const float* x, float* x01, float* mn, float* mx, int B, int T, void* cuda_stream);
 ADVB_API int advb_revert_minmax(const float* x01, const float* mn, const float* mx, float* x, int B, int T,

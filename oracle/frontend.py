@@ -50,3 +50,14 @@ def tables_from_state(state: dict):
         return state["frontend.filter_mat"], state["frontend.dct_mat"], state["frontend.Spectrogram.window"], "lfcc"
     return (state["frontend.MelSpectrogram.mel_scale.fb"], state["frontend.dct_mat"],
             state["frontend.MelSpectrogram.spectrogram.window"], "mfcc")
+
+
+def mel_spec(x: torch.Tensor, fb: torch.Tensor) -> torch.Tensor:
+    """src/frontends.py:53-79 (prepare_mel_scale_vector / prepare_stft_features): torch.stft without a window (:65-71), the mel
+    filterbank applied to the real and to the imaginary part separately (:74-75; MelScale.forward is ``fb^T @ x``), abs and angle of
+    the complex result (:77-79), stacked on dim 1 (:58).  x (B,T), fb (257,n_mels) -> (B,2,n_mels,F)."""
+    st = torch.stft(x, n_fft=N_FFT, return_complex=True, hop_length=HOP, win_length=WIN)
+    mr = torch.matmul(st.real.transpose(-1, -2), fb).transpose(-1, -2)
+    mi = torch.matmul(st.imag.transpose(-1, -2), fb).transpose(-1, -2)
+    c = torch.complex(mr, mi)
+    return torch.stack([c.abs(), c.angle()], dim=1)

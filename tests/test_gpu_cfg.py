@@ -378,3 +378,34 @@ def test_calls_on_different_streams_are_ordered(cuda_device):
             adv2 = atk.forward(xd, yd, noise=noise)  # back on s1 while s2's calls may still run
         torch.cuda.synchronize()
         assert torch.equal(adv, want_adv) and torch.equal(adv2, want_adv) and torch.equal(logits, want_logits)
+
+
+def test_mel_spec_frontend_matches_reference(cuda_device):
+    """get_frontend(["mel_spec"]) = prepare_mel_scale_vector (src/frontends.py:53-79) on the GPU (fe_melspec_kernel)
+    against the fixture the unmodified reference produced and against the oracle; odd frame count and a 1-D clip included."""
+    from advb200 import frontends
+    from oracle import frontend as ofe
+    from oracle import synth
+
+    g = helpers.load_golden("mel_spec")
+    fn = frontends.get_frontend(["mel_spec"])
+    for tag, cfg_id, B, T in (("t16000", 31, 2, 16000), ("t16150", 32, 1, 16150)):
+        x, _ = synth.clips(cfg_id, B, T)
+        got = fn(x.to(cuda_device)).cpu()
+        want = torch.from_numpy(g[f"{tag}_out"])
+        assert got.shape == want.shape
+        zg, zw = torch.polar(got[:, 0], got[:, 1]), torch.polar(want[:, 0], want[:, 1])
+        scale = zw.abs().max().item()
+        assert (zg - zw).abs().max().item() < 2e-5 * scale, tag            # the complex mel spectrum, element-wise
+        np.testing.assert_allclose(got[:, 0].numpy(), want[:, 0].numpy(), atol=2e-5 * scale)   # channel 0: abs
+        big = want[:, 0] > 1e-2 * scale                                      # channel 1: angle, where it is well conditioned
+        dphi = torch.remainder(got[:, 1] - want[:, 1] + np.pi, 2 * np.pi) - np.pi
+        assert dphi[big].abs().max().item() < 2e-3
+        zo = ofe.mel_spec(x, torch.from_numpy(g["fb"]))
+        assert (zg - torch.polar(zo[:, 0], zo[:, 1])).abs().max().item() < 2e-5 * scale
+    mag, ang = frontends.prepare_stft_features(x.to(cuda_device))
+    assert torch.equal(mag.cpu(), got[:, 0]) and torch.equal(ang.cpu(), got[:, 1])
+    one = fn(x[0].to(cuda_device))
+    assert one.shape == (2, 80, 101) and torch.equal(one.cpu(), got[0])
+    with pytest.raises(NotImplementedError):
+        fn(x.to(cuda_device).requires_grad_(True))

@@ -119,6 +119,24 @@ def test_oracle_projection_l2_solves_the_box_hyperplane_problem():
     assert (d.norm(dim=1) <= d_inf.norm(dim=1) * (1 + 1e-5)).all()
 
 
+def test_oracle_mel_spec_matches_reference():
+    """src/frontends.py:53-79: the oracle's `mel_spec` against what the unmodified prepare_mel_scale_vector produced
+    (oracle/make_golden_melspec.py), and the table advb200's MEL_SCALE_FN holds against the reference's MelScale buffer."""
+    from advb200 import frontends
+    from oracle import frontend as ofe
+
+    g = helpers.load_golden("mel_spec")
+    fb = torch.from_numpy(g["fb"])
+    assert torch.equal(frontends.MEL_SCALE_FN.fb, fb) and frontends.get_frontend(["mel_spec"]) is frontends.prepare_mel_scale_vector
+    for tag, cfg_id, B, T in (("t16000", 31, 2, 16000), ("t16150", 32, 1, 16150)):
+        x, _ = synth.clips(cfg_id, B, T)
+        assert abs(x.double().sum().item() - float(g[f"{tag}_x_sum"])) < 1e-9
+        got, want = ofe.mel_spec(x, fb), torch.from_numpy(g[f"{tag}_out"])
+        assert got.shape == want.shape == (B, 2, 80, 101)
+        zg, zw = torch.polar(got[:, 0], got[:, 1]), torch.polar(want[:, 0], want[:, 1])
+        assert (zg - zw).abs().max().item() < 1e-5 * zw.abs().max().item()
+
+
 def test_oracle_matches_reference_at_config1():
     """BASELINE.json configs[0] (FGSM eps=0.005, LCNN+LFCC, batch 8, 64 000 samples): the oracle port against the fixture the
     unmodified reference produced (oracle/make_golden_cfg.py)."""
