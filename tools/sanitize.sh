@@ -17,3 +17,11 @@ run racecheck specrnet --model specrnet --batch 2 --samples 16000 --calls 1
 run memcheck rawnet3 --model rawnet3 --batch 1 --samples 16000 --calls 1
 run racecheck rawnet3 --model rawnet3 --batch 1 --samples 16000 --calls 1
 run synccheck rawnet3 --model rawnet3 --batch 1 --samples 16000 --calls 1
+# the attack entry points the gradient runs above do not reach (FAB L-inf / L2 + restart, CW, PGDL2, targeted FGSM, projections, mel_spec)
+runx() {
+  local tool=$1
+  timeout 1200 $CS --tool $tool --print-limit 5 python tools/sanitize_extras.py > $out/${tool}_extras.log 2>&1
+  echo "$tool extras rc=$? : $(grep -E 'ERROR SUMMARY|RACECHECK SUMMARY|hazard|extras ok' $out/${tool}_extras.log | tr '\n' ' ' | cut -c1-400)"
+}
+runx memcheck
+runx racecheck
