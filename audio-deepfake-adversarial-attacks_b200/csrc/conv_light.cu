@@ -66,9 +66,21 @@ struct LCfg {
   static constexpr int BAND_BYTES = NKC * 2 * 128 * 128; // per chunk: hi rows then lo rows (128 rows x 128 B)
   static constexpr int CS = BWD ? NOUT : NOUT / 2;       // channels per staged pixel
   static constexpr int SS = CS + 4;
-  static constexpr int STAGE_BYTES = 128 * SS * 4 + 128 * 8;
-  static constexpr size_t SMEM = (size_t)W_BYTES + BAND_BYTES + STAGE_BYTES + 1024;
   static constexpr int MAP = IM2COL ? (BWD ? 1 : 2) : 0;  // 0 FLAT, 1 OVL4, 2 BLK
+  // FLAT (1x1) FORWARD kernels, round 2: a tile's operand rows are ONE contiguous span of the NHWC tensor (128 pixels x KTOT
+  // floats), so they arrive by 1-D TMA bulk copies into a raw ring RAW_SLOTS tiles deep instead of through the workers' registers
+  // one tile ahead (ncu: long_scoreboard was the top stall).  Block 1 forward: 100 -> 90 us, bit-identical.  The same ring in the
+  // backward kernel (gradient rows + code bytes) costs it its second CTA per SM and measured no gain (107 us either way), so the
+  // backward keeps the register prefetch.
+  static constexpr bool RAW = MAP == 0 && !BWD;
+  static constexpr int RAW_MAIN = 128 * KTOT * 4;   // activation rows of one tile
+  static constexpr int RAW_SLOT = RAW_MAIN;
+  static constexpr int STAGE_BYTES = RAW ? 0 : 128 * SS * 4 + 128 * 8;
+  static constexpr int FIXED_BYTES = W_BYTES + BAND_BYTES + STAGE_BYTES + 1024;
+  // as many slots as keep the CTAs-per-SM count the kernel had without the ring (2 where it was 2), at most 4, at least 2
+  static constexpr int RAW_BUDGET = (FIXED_BYTES + 2 * RAW_SLOT + 1024 <= 113 * 1024 ? 113 * 1024 : 226 * 1024) - 1024 - FIXED_BYTES;
+  static constexpr int RAW_SLOTS = !RAW ? 0 : (RAW_BUDGET / RAW_SLOT >= 4 ? 4 : (RAW_BUDGET / RAW_SLOT >= 3 ? 3 : 2));
+  static constexpr size_t SMEM = (size_t)FIXED_BYTES + (size_t)RAW_SLOTS * RAW_SLOT;
   static constexpr int STEP = MAP == 1 ? 124 : 128;       // new pixels per tile (FLAT / OVL4)
 #ifndef ADVB_LIGHT_CTAS3
 #define ADVB_LIGHT_CTAS3 0
@@ -110,8 +122,11 @@ conv_light_kernel(LArgs a) {
   unsigned char* w_s = base;                       // [NKC][hi NOUT x 128 B | lo NOUT x 128 B]
   unsigned char* band = w_s + Cfg::W_BYTES;        // [NKC][hi 128 x 128 B | lo 128 x 128 B]   (W_BYTES is a multiple of 1024)
   float* stage = reinterpret_cast<float*>(band + Cfg::BAND_BYTES);
-  unsigned long long* flags = reinterpret_cast<unsigned long long*>(stage + 128 * SS);
-  __shared__ uint64_t bar_w, bar_mma[2], bar_full;
+  unsigned long long* flags = reinterpret_cast<unsigned long long*>(stage + 128 * SS);  // (unused when RAW: no staging tile)
+  unsigned char* raw = band + Cfg::BAND_BYTES + Cfg::STAGE_BYTES;  // RAW: [RAW_SLOTS][RAW_SLOT] ring of unconverted tiles
+  constexpr bool RAW = Cfg::RAW;
+  constexpr int RSL = Cfg::RAW_SLOTS > 0 ? Cfg::RAW_SLOTS : 1;
+  __shared__ uint64_t bar_w, bar_mma[2], bar_full, bar_raw[RSL];
   __shared__ uint32_t tmem_base_s;
   __shared__ float s_bias[BWD ? 1 : NOUT];
   __shared__ float s_bnm[BWD ? 1 : NOUT / 2], s_bni[BWD ? 1 : NOUT / 2];  // BatchNorm(eval) mean / inverse std (0 / 1 without BN)
@@ -124,6 +139,7 @@ conv_light_kernel(LArgs a) {
     mbar_init(&bar_mma[0], 1);
     mbar_init(&bar_mma[1], 1);
     mbar_init(&bar_full, LW / 32);
+    for (int i = 0; i < RSL; ++i) mbar_init(&bar_raw[i], 1);
     fence_barrier_init();
   }
   if (warp == 0) tmem_alloc<Cfg::TMEM_COLS>(&tmem_base_s);
@@ -145,13 +161,31 @@ conv_light_kernel(LArgs a) {
 
   if (warp == LW / 32) {
     // ================= MMA-issue warp =================
-    mbar_wait(&bar_w, 0u);
     const bool leader = elect_one();
+    // RAW: this warp is also the producer of the raw ring.  Slot it % RSL holds tile `it`; it is refilled with tile it + RSL as soon
+    // as every worker warp has converted tile `it` out of it (= bar_full of tile `it`, which this warp waits for anyway).
+    auto raw_load = [&](int tile, int slot) {
+      const int b = fdiv(tile, a.dTiles), tl = tile - b * a.tiles_per_clip;
+      const int npx = min(128, a.H * a.W - 128 * tl);
+      unsigned char* dst = raw + (size_t)slot * Cfg::RAW_SLOT;
+      const size_t px0 = (size_t)b * a.H * a.W + (size_t)128 * tl;
+      mbar_expect_tx(&bar_raw[slot], (uint32_t)(npx * KTOT * 4));
+      bulk_g2s(dst, a.in + px0 * KTOT, (uint32_t)(npx * KTOT * 4), &bar_raw[slot]);
+    };
+    if (RAW && leader) {
+      int t = blockIdx.x;
+      for (int i = 0; i < RSL && t < a.n_tiles; ++i, t += gridDim.x) raw_load(t, i);
+    }
+    mbar_wait(&bar_w, 0u);
     int it = 0;
     for (int tile = blockIdx.x; tile < a.n_tiles; tile += gridDim.x, ++it) {
       const int buf = it & 1;
       mbar_wait(&bar_full, (uint32_t)(it & 1));  // band of tile `it` is staged (and accumulator `buf` has been drained)
       tc_fence_after();
+      if (RAW && leader) {
+        const long long nt = (long long)tile + (long long)RSL * gridDim.x;
+        if (nt < a.n_tiles) raw_load((int)nt, it % RSL);
+      }
       const uint32_t dcol = tmem + buf * Cfg::NSTRIDE;
 #pragma unroll
       for (int kc = 0; kc < NKC; ++kc) {
@@ -247,6 +281,27 @@ conv_light_kernel(LArgs a) {
     const uint32_t off = sw128_chunk(m, c4);
     *reinterpret_cast<float4*>(hb + off) = hi;
     *reinterpret_cast<float4*>(hb + 128 * 128 + off) = lo;
+  };
+
+  // RAW: tile `it` out of its ring slot (rows >= npx of a clip's last tile are zero)
+  auto convert_store_raw = [&](int tile, int it) {
+    const int slot = it % RSL;
+    mbar_wait(&bar_raw[slot], (uint32_t)((it / RSL) & 1));
+    const int b = fdiv(tile, a.dTiles), tl = tile - b * a.tiles_per_clip;
+    const int npx = min(128, a.H * a.W - 128 * tl);
+    const unsigned char* src = raw + (size_t)slot * Cfg::RAW_SLOT;
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int m = m0 + 32 * u;
+      const bool ok = m < npx;
+#pragma unroll
+      for (int kc = 0; kc < NKC; ++kc) {
+        const int ch = 32 * kc + 4 * c4;
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (ok && ch < KTOT) v = *reinterpret_cast<const float4*>(src + ((size_t)m * KTOT + ch) * 4);
+        store_item(kc, m, v);
+      }
+    }
   };
 
   auto convert_store = [&]() {
@@ -475,7 +530,7 @@ conv_light_kernel(LArgs a) {
 
   // ---- persistent loop (workers) ----
   int tile = blockIdx.x;
-  if (tile < a.n_tiles) issue_loads(tile);
+  if (!RAW && tile < a.n_tiles) issue_loads(tile);
   int it = 0, prev_tile = -1;
   long long pc[4] = {0, 0, 0, 0};
   const bool prof = a.prof != nullptr && blockIdx.x == 0 && tid == 0;
@@ -493,14 +548,15 @@ conv_light_kernel(LArgs a) {
       tc_fence_after();
     }
     LPROF(0)
-    convert_store();
+    if (RAW) convert_store_raw(tile, it);
+    else convert_store();
     fence_proxy_async();
     tc_fence_before();
     __syncwarp();
     if (lane == 0) mbar_arrive(&bar_full);  // 8 worker warps -> the MMA warp may issue tile `it`
     LPROF(1)
     const int next = tile + gridDim.x;
-    if (next < a.n_tiles) issue_loads(next);
+    if (!RAW && next < a.n_tiles) issue_loads(next);
     LPROF(2)
     if (it > 0) epilogue(prev_tile, buf ^ 1);  // overlaps the MMAs of tile `it`
     LPROF(3)
