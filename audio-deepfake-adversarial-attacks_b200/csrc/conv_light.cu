@@ -67,19 +67,20 @@ struct LCfg {
   static constexpr int CS = BWD ? NOUT : NOUT / 2;       // channels per staged pixel
   static constexpr int SS = CS + 4;
   static constexpr int MAP = IM2COL ? (BWD ? 1 : 2) : 0;  // 0 FLAT, 1 OVL4, 2 BLK
-  // FLAT (1x1) FORWARD kernels, round 2: a tile's operand rows are ONE contiguous span of the NHWC tensor (128 pixels x KTOT
-  // floats), so they arrive by 1-D TMA bulk copies into a raw ring RAW_SLOTS tiles deep instead of through the workers' registers
-  // one tile ahead (ncu: long_scoreboard was the top stall).  Block 1 forward: 100 -> 90 us, bit-identical.  The same ring in the
-  // backward kernel (gradient rows + code bytes) costs it its second CTA per SM and measured no gain (107 us either way), so the
-  // backward keeps the register prefetch.
-  static constexpr bool RAW = MAP == 0 && !BWD;
-  static constexpr int RAW_MAIN = 128 * KTOT * 4;   // activation rows of one tile
-  static constexpr int RAW_SLOT = RAW_MAIN;
+  // FLAT (1x1) kernels, round 2: a tile's operand rows are ONE contiguous span of the NHWC tensor (forward: 128 pixels x KTOT
+  // floats; backward: 128 x 32 gradient floats + 128 x 32 code bytes), so they arrive by 1-D TMA bulk copies into a raw ring
+  // instead of through the workers' registers one tile ahead (ncu: long_scoreboard was the top stall; the backward's workers
+  // spent 1.8 k of 5.7 k cycles per tile just ISSUING their prefetch loads).  Forward: 3-4 slots (block 1: 100 -> 90 us).
+  // Backward: the ring must not cost the second CTA per SM (4 slots at one CTA per SM measured no gain), so ONE slot, refilled
+  // as soon as the tile in it has been converted - the same look-ahead as the register prefetch without its issue cost.
+  static constexpr bool RAW = MAP == 0;
+  static constexpr int RAW_MAIN = BWD ? 128 * 32 * 4 : 128 * KTOT * 4;   // gradient / activation rows of one tile
+  static constexpr int RAW_SLOT = RAW_MAIN + (BWD ? 128 * 32 : 0);       // + the code bytes (backward)
   static constexpr int STAGE_BYTES = RAW ? 0 : 128 * SS * 4 + 128 * 8;
   static constexpr int FIXED_BYTES = W_BYTES + BAND_BYTES + STAGE_BYTES + 1024;
   // as many slots as keep the CTAs-per-SM count the kernel had without the ring (2 where it was 2), at most 4, at least 2
   static constexpr int RAW_BUDGET = (FIXED_BYTES + 2 * RAW_SLOT + 1024 <= 113 * 1024 ? 113 * 1024 : 226 * 1024) - 1024 - FIXED_BYTES;
-  static constexpr int RAW_SLOTS = !RAW ? 0 : (RAW_BUDGET / RAW_SLOT >= 4 ? 4 : (RAW_BUDGET / RAW_SLOT >= 3 ? 3 : 2));
+  static constexpr int RAW_SLOTS = !RAW ? 0 : BWD ? 1 : (RAW_BUDGET / RAW_SLOT >= 4 ? 4 : (RAW_BUDGET / RAW_SLOT >= 3 ? 3 : 2));
   static constexpr size_t SMEM = (size_t)FIXED_BYTES + (size_t)RAW_SLOTS * RAW_SLOT;
   static constexpr int STEP = MAP == 1 ? 124 : 128;       // new pixels per tile (FLAT / OVL4)
 #ifndef ADVB_LIGHT_CTAS3
@@ -115,6 +116,7 @@ conv_light_kernel(LArgs a) {
   constexpr int NKC = Cfg::NKC, CS = Cfg::CS, SS = Cfg::SS, MAP = Cfg::MAP;
   constexpr uint32_t IDESC = idesc_tf32(128, NOUT);
   static_assert(!BWD || KTOT == 64, "light backward kernels assume Cout = 64 (one 32-channel chunk per MFM half)");
+  static_assert(!(Cfg::RAW && BWD && POOL), "the raw-ring backward assumes an un-pooled 1x1 block (gradient and codes on the conv grid)");
   static_assert(!(IM2COL && !BWD) || KTOT == 32, "first-block forward: 25 taps padded to one 32-wide chunk");
 
   extern __shared__ unsigned char smem_raw[];
@@ -169,8 +171,14 @@ conv_light_kernel(LArgs a) {
       const int npx = min(128, a.H * a.W - 128 * tl);
       unsigned char* dst = raw + (size_t)slot * Cfg::RAW_SLOT;
       const size_t px0 = (size_t)b * a.H * a.W + (size_t)128 * tl;
-      mbar_expect_tx(&bar_raw[slot], (uint32_t)(npx * KTOT * 4));
-      bulk_g2s(dst, a.in + px0 * KTOT, (uint32_t)(npx * KTOT * 4), &bar_raw[slot]);
+      if (BWD) {
+        mbar_expect_tx(&bar_raw[slot], (uint32_t)(npx * 32 * 5));
+        bulk_g2s(dst, a.gout + px0 * 32, (uint32_t)(npx * 32 * 4), &bar_raw[slot]);
+        bulk_g2s(dst + Cfg::RAW_MAIN, a.codes_in + px0 * 32, (uint32_t)(npx * 32), &bar_raw[slot]);
+      } else {
+        mbar_expect_tx(&bar_raw[slot], (uint32_t)(npx * KTOT * 4));
+        bulk_g2s(dst, a.in + px0 * KTOT, (uint32_t)(npx * KTOT * 4), &bar_raw[slot]);
+      }
     };
     if (RAW && leader) {
       int t = blockIdx.x;
@@ -294,12 +302,32 @@ conv_light_kernel(LArgs a) {
     for (int u = 0; u < 4; ++u) {
       const int m = m0 + 32 * u;
       const bool ok = m < npx;
+      if (BWD) {
+        float4 g = make_float4(0.f, 0.f, 0.f, 0.f);
+        uchar4 cd = make_uchar4(0xff, 0xff, 0xff, 0xff);
+        if (ok) {
+          g = *reinterpret_cast<const float4*>(src + ((size_t)m * 32 + 4 * c4) * 4);
+          cd = *reinterpret_cast<const uchar4*>(src + Cfg::RAW_MAIN + (size_t)m * 32 + 4 * c4);
+          g = make_float4(g.x * sc.x, g.y * sc.y, g.z * sc.z, g.w * sc.w);
+        }
 #pragma unroll
-      for (int kc = 0; kc < NKC; ++kc) {
-        const int ch = 32 * kc + 4 * c4;
-        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (ok && ch < KTOT) v = *reinterpret_cast<const float4*>(src + ((size_t)m * KTOT + ch) * 4);
-        store_item(kc, m, v);
+        for (int kc = 0; kc < NKC; ++kc) {  // chunk kc = MFM half kc of the same 32 channels (1x1 blocks do not pool: position 0)
+          const unsigned want = (unsigned)(kc << 2);
+          float4 v;
+          v.x = cd.x == want ? g.x : 0.f;
+          v.y = cd.y == want ? g.y : 0.f;
+          v.z = cd.z == want ? g.z : 0.f;
+          v.w = cd.w == want ? g.w : 0.f;
+          store_item(kc, m, v);
+        }
+      } else {
+#pragma unroll
+        for (int kc = 0; kc < NKC; ++kc) {
+          const int ch = 32 * kc + 4 * c4;
+          float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (ok && ch < KTOT) v = *reinterpret_cast<const float4*>(src + ((size_t)m * KTOT + ch) * 4);
+          store_item(kc, m, v);
+        }
       }
     }
   };
