@@ -130,8 +130,8 @@ conv_light_kernel(LArgs a) {
   constexpr int RSL = Cfg::RAW_SLOTS > 0 ? Cfg::RAW_SLOTS : 1;
   __shared__ uint64_t bar_w, bar_mma[2], bar_full, bar_raw[RSL];
   __shared__ uint32_t tmem_base_s;
-  __shared__ float s_bias[BWD ? 1 : NOUT];
-  __shared__ float s_bnm[BWD ? 1 : NOUT / 2], s_bni[BWD ? 1 : NOUT / 2];  // BatchNorm(eval) mean / inverse std (0 / 1 without BN)
+  __shared__ __align__(16) float s_bias[BWD ? 4 : NOUT];
+  __shared__ __align__(16) float s_bnm[BWD ? 4 : NOUT / 2], s_bni[BWD ? 4 : NOUT / 2];  // BatchNorm(eval) mean / inverse std (0 / 1 without BN)
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int Heff = (!BWD && POOL) ? 2 * a.Ho : a.H;
@@ -407,12 +407,22 @@ conv_light_kernel(LArgs a) {
           float o[16];
           unsigned cw[4] = {0u, 0u, 0u, 0u};
 #pragma unroll
-          for (int j = 0; j < 16; ++j) {
-            const float l = __uint_as_float(lo[j]) + s_bias[c0 + j];
-            const float h = __uint_as_float(hi[j]) + s_bias[CS + c0 + j];
-            const bool sel = h > l;
-            o[j] = ((sel ? h : l) - s_bnm[c0 + j]) * s_bni[c0 + j];
-            cw[j >> 2] |= (sel ? 4u : 0u) << (8 * (j & 3));  // code byte: MFM half << 2 (no pool position)
+          for (int j4 = 0; j4 < 16; j4 += 4) {  // per-channel vectors as LDS.128 (they were 64 scalar LDS per 16 channels)
+            const float4 bl4 = *reinterpret_cast<const float4*>(s_bias + c0 + j4);
+            const float4 bh4 = *reinterpret_cast<const float4*>(s_bias + CS + c0 + j4);
+            const float4 mn4 = *reinterpret_cast<const float4*>(s_bnm + c0 + j4);
+            const float4 is4 = *reinterpret_cast<const float4*>(s_bni + c0 + j4);
+            const float bl[4] = {bl4.x, bl4.y, bl4.z, bl4.w}, bh[4] = {bh4.x, bh4.y, bh4.z, bh4.w};
+            const float mn[4] = {mn4.x, mn4.y, mn4.z, mn4.w}, is[4] = {is4.x, is4.y, is4.z, is4.w};
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+              const int j = j4 + k;
+              const float l = __uint_as_float(lo[j]) + bl[k];
+              const float h = __uint_as_float(hi[j]) + bh[k];
+              const bool sel = h > l;
+              o[j] = ((sel ? h : l) - mn[k]) * is[k];
+              cw[j >> 2] |= sel ? (4u << (8 * k)) : 0u;  // code byte: MFM half << 2 (no pool position)
+            }
           }
           if (valid) {
 #pragma unroll
