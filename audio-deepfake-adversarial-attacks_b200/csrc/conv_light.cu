@@ -74,13 +74,15 @@ struct LCfg {
   // Backward: the ring must not cost the second CTA per SM (4 slots at one CTA per SM measured no gain), so ONE slot, refilled
   // as soon as the tile in it has been converted - the same look-ahead as the register prefetch without its issue cost.
   static constexpr bool RAW = MAP == 0;
-  static constexpr int RAW_MAIN = BWD ? 128 * 32 * 4 : 128 * KTOT * 4;   // gradient / activation rows of one tile
-  static constexpr int RAW_SLOT = RAW_MAIN + (BWD ? 128 * 32 : 0);       // + the code bytes (backward)
+  static constexpr int CH = KTOT / 2;                                     // backward: channels of the stage gradient (C_out / 2)
+  static constexpr int RAW_MAIN = BWD ? 128 * CH * 4 : 128 * KTOT * 4;   // gradient / activation rows of one tile
+  static constexpr int RAW_SLOT = RAW_MAIN + (BWD ? 128 * CH : 0);       // + the code bytes (backward)
   static constexpr int STAGE_BYTES = RAW ? 0 : 128 * SS * 4 + 128 * 8;
   static constexpr int FIXED_BYTES = W_BYTES + BAND_BYTES + STAGE_BYTES + 1024;
   // as many slots as keep the CTAs-per-SM count the kernel had without the ring (2 where it was 2), at most 4, at least 2
   static constexpr int RAW_BUDGET = (FIXED_BYTES + 2 * RAW_SLOT + 1024 <= 113 * 1024 ? 113 * 1024 : 226 * 1024) - 1024 - FIXED_BYTES;
-  static constexpr int RAW_SLOTS = !RAW ? 0 : BWD ? 1 : (RAW_BUDGET / RAW_SLOT >= 4 ? 4 : (RAW_BUDGET / RAW_SLOT >= 3 ? 3 : 2));
+  static constexpr bool BWD_ONE = BWD && FIXED_BYTES + RAW_SLOT + 1024 <= 113 * 1024;  // one slot keeps two CTAs per SM
+  static constexpr int RAW_SLOTS = !RAW ? 0 : BWD_ONE ? 1 : (RAW_BUDGET / RAW_SLOT >= 4 ? 4 : (RAW_BUDGET / RAW_SLOT >= 3 ? 3 : 2));
   static constexpr size_t SMEM = (size_t)FIXED_BYTES + (size_t)RAW_SLOTS * RAW_SLOT;
   static constexpr int STEP = MAP == 1 ? 124 : 128;       // new pixels per tile (FLAT / OVL4)
 #ifndef ADVB_LIGHT_CTAS3
@@ -115,7 +117,7 @@ conv_light_kernel(LArgs a) {
   using Cfg = LCfg<KTOT, NOUT, POOL, BWD, IM2COL>;
   constexpr int NKC = Cfg::NKC, CS = Cfg::CS, SS = Cfg::SS, MAP = Cfg::MAP;
   constexpr uint32_t IDESC = idesc_tf32(128, NOUT);
-  static_assert(!BWD || KTOT == 64, "light backward kernels assume Cout = 64 (one 32-channel chunk per MFM half)");
+  static_assert(!BWD || KTOT == 64 || Cfg::RAW, "the register-prefetch backward assumes Cout = 64 (one 32-channel chunk per MFM half)");
   static_assert(!(Cfg::RAW && BWD && POOL), "the raw-ring backward assumes an un-pooled 1x1 block (gradient and codes on the conv grid)");
   static_assert(!(IM2COL && !BWD) || KTOT == 32, "first-block forward: 25 taps padded to one 32-wide chunk");
 
@@ -172,9 +174,9 @@ conv_light_kernel(LArgs a) {
       unsigned char* dst = raw + (size_t)slot * Cfg::RAW_SLOT;
       const size_t px0 = (size_t)b * a.H * a.W + (size_t)128 * tl;
       if (BWD) {
-        mbar_expect_tx(&bar_raw[slot], (uint32_t)(npx * 32 * 5));
-        bulk_g2s(dst, a.gout + px0 * 32, (uint32_t)(npx * 32 * 4), &bar_raw[slot]);
-        bulk_g2s(dst + Cfg::RAW_MAIN, a.codes_in + px0 * 32, (uint32_t)(npx * 32), &bar_raw[slot]);
+        mbar_expect_tx(&bar_raw[slot], (uint32_t)(npx * Cfg::CH * 5));
+        bulk_g2s(dst, a.gout + px0 * Cfg::CH, (uint32_t)(npx * Cfg::CH * 4), &bar_raw[slot]);
+        bulk_g2s(dst + Cfg::RAW_MAIN, a.codes_in + px0 * Cfg::CH, (uint32_t)(npx * Cfg::CH), &bar_raw[slot]);
       } else {
         mbar_expect_tx(&bar_raw[slot], (uint32_t)(npx * KTOT * 4));
         bulk_g2s(dst, a.in + px0 * KTOT, (uint32_t)(npx * KTOT * 4), &bar_raw[slot]);
@@ -235,6 +237,15 @@ conv_light_kernel(LArgs a) {
   }
   float4 sc = make_float4(1.f, 1.f, 1.f, 1.f);
   if (BWD && a.bn_invstd != nullptr) sc = __ldg(reinterpret_cast<const float4*>(a.bn_invstd + 4 * c4));
+  float4 scr[(BWD && Cfg::RAW) ? NKC : 1];  // RAW backward: BatchNorm(eval) scale of this thread's 4 channels in every chunk
+  if (BWD && Cfg::RAW) {
+#pragma unroll
+    for (int kc = 0; kc < NKC; ++kc) {
+      const int k0 = 32 * kc + 4 * c4, c = k0 >= Cfg::CH ? k0 - Cfg::CH : k0;
+      scr[kc] = make_float4(1.f, 1.f, 1.f, 1.f);
+      if (a.bn_invstd != nullptr && k0 < KTOT) scr[kc] = __ldg(reinterpret_cast<const float4*>(a.bn_invstd + c));
+    }
+  }
 
   // registers holding the next tile's raw loads
   float4 rv[4][BWD ? 1 : NKC];
@@ -303,21 +314,29 @@ conv_light_kernel(LArgs a) {
       const int m = m0 + 32 * u;
       const bool ok = m < npx;
       if (BWD) {
-        float4 g = make_float4(0.f, 0.f, 0.f, 0.f);
-        uchar4 cd = make_uchar4(0xff, 0xff, 0xff, 0xff);
-        if (ok) {
-          g = *reinterpret_cast<const float4*>(src + ((size_t)m * 32 + 4 * c4) * 4);
-          cd = *reinterpret_cast<const uchar4*>(src + Cfg::RAW_MAIN + (size_t)m * 32 + 4 * c4);
-          g = make_float4(g.x * sc.x, g.y * sc.y, g.z * sc.z, g.w * sc.w);
+        // K index k = 32 kc + 4 c4 of the expanded gradient = (MFM half k / CH, stage channel k % CH); a 1x1 block does not pool,
+        // so the stored code of a channel is just its winning half << 2
+        constexpr int CH = Cfg::CH;
+        float4 g0 = make_float4(0.f, 0.f, 0.f, 0.f);
+        uchar4 cd0 = make_uchar4(0xff, 0xff, 0xff, 0xff);
+        if (CH == 32 && ok) {  // both chunks are the two halves of the SAME 32 channels: one load serves them
+          g0 = *reinterpret_cast<const float4*>(src + ((size_t)m * CH + 4 * c4) * 4);
+          cd0 = *reinterpret_cast<const uchar4*>(src + Cfg::RAW_MAIN + (size_t)m * CH + 4 * c4);
         }
 #pragma unroll
-        for (int kc = 0; kc < NKC; ++kc) {  // chunk kc = MFM half kc of the same 32 channels (1x1 blocks do not pool: position 0)
-          const unsigned want = (unsigned)(kc << 2);
-          float4 v;
-          v.x = cd.x == want ? g.x : 0.f;
-          v.y = cd.y == want ? g.y : 0.f;
-          v.z = cd.z == want ? g.z : 0.f;
-          v.w = cd.w == want ? g.w : 0.f;
+        for (int kc = 0; kc < NKC; ++kc) {
+          const int k0 = 32 * kc + 4 * c4;
+          const int half = k0 >= CH ? 1 : 0, c = k0 - half * CH;
+          float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (ok && k0 < KTOT) {
+            const float4 g = CH == 32 ? g0 : *reinterpret_cast<const float4*>(src + ((size_t)m * CH + c) * 4);
+            const uchar4 cd = CH == 32 ? cd0 : *reinterpret_cast<const uchar4*>(src + Cfg::RAW_MAIN + (size_t)m * CH + c);
+            const unsigned want = (unsigned)(half << 2);
+            v.x = cd.x == want ? g.x * scr[kc].x : 0.f;
+            v.y = cd.y == want ? g.y * scr[kc].y : 0.f;
+            v.z = cd.z == want ? g.z * scr[kc].z : 0.f;
+            v.w = cd.w == want ? g.w * scr[kc].w : 0.f;
+          }
           store_item(kc, m, v);
         }
       } else {
@@ -682,7 +701,7 @@ bool conv_light_supported(int Cin, int Cout, int KS, bool pool, bool bwd) {
   if (KS == 5) return Cin == 1 && Cout == 64 && pool;
   if (KS != 1 || pool) return false;
   if (!bwd) return (Cin == 32 && Cout == 64) || (Cin == 48 && Cout == 96) || (Cin == 64 && Cout == 128);
-  return Cout == 64 && Cin == 32;
+  return (Cout == 64 && Cin == 32) || (Cout == 96 && Cin == 48);
 }
 
 int conv_light_forward(const ConvFwdArgs& f, const unsigned char* wpack, int passes, cudaStream_t stream) {
@@ -708,6 +727,7 @@ int conv_light_backward(const ConvBwdArgs& g, const unsigned char* wpack, int pa
   a.gout = g.gout, a.codes_in = g.codes, a.gin = g.gin, a.bn_invstd = g.bn_invstd;
   a.passes = passes;
   if (g.KS == 1 && g.Cout == 64 && g.Cin == 32 && !g.pool) return launch_light<64, 32, false, true, false>(a, g.tag, stream);
+  if (g.KS == 1 && g.Cout == 96 && g.Cin == 48 && !g.pool) return launch_light<96, 48, false, true, false>(a, g.tag, stream);
   set_error("conv shape has no light instantiation (backward)");
   return 1;
 }
