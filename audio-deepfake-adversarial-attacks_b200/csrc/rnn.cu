@@ -97,6 +97,96 @@ __global__ void __launch_bounds__(256) gemm_kernel(const float* __restrict__ A, 
   }
 }
 
+// General register-tiled variant (round 2): BM x BN tile, (BM / TM) x (BN / TN) threads with a TM x TN register tile each.  Every
+// output is still ONE sequential fmaf chain over k = 0 .. K-1, so the results are bit-identical to gemm_kernel's whatever the tile
+// shape; what changes is the LDS : FMA ratio (gemm_kernel's 4 x 4 tile issues two LDS.128 per 16 FMAs, its 4 x 2 tile for the narrow
+// N = 160 backward projection one LDS.128 + one LDS.64 per 8).
+template <int BM, int BN, int TM, int TN>
+__global__ void __launch_bounds__((BM / TM) * (BN / TN)) gemm_rt_kernel(const float* __restrict__ A, const float* __restrict__ Bm,
+                                                                         const float* __restrict__ bias,
+                                                                         const float* __restrict__ Cadd, float* __restrict__ C,
+                                                                         int M, int N, int K) {
+  constexpr int NX = BN / TN, NY = BM / TM, NT = NX * NY;
+  constexpr int A4 = BM * 4, B4 = 4 * BN;  // float4 loads per k-step of the A / B tile
+  constexpr int PA = (A4 + NT - 1) / NT, PB = (B4 + NT - 1) / NT;
+  static_assert(TM % 4 == 0 && (TN == 4 || TN == 2) && BN % 4 == 0, "register tile shapes");
+  __shared__ __align__(16) float As[16][BM + 4];  // k-major
+  __shared__ __align__(16) float Bs[16][BN + 4];
+  const int tid = threadIdx.x, tx = tid % NX, ty = tid / NX;
+  const int m0 = blockIdx.y * BM, n0 = blockIdx.x * BN;
+  float acc[TM][TN] = {};
+  float4 pa[PA], pb[PB];
+  auto load_tiles = [&](int k0) {
+#pragma unroll
+    for (int q = 0; q < PA; ++q) {
+      const int i = tid + q * NT, row = i >> 2, kq = (i & 3) * 4;
+      pa[q] = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (i < A4 && m0 + row < M && k0 + kq < K) pa[q] = __ldg(reinterpret_cast<const float4*>(A + (size_t)(m0 + row) * K + k0 + kq));
+    }
+#pragma unroll
+    for (int q = 0; q < PB; ++q) {
+      const int i = tid + q * NT, row = i / (BN / 4), c4 = (i % (BN / 4)) * 4;
+      pb[q] = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (i < B4 && k0 + row < K && n0 + c4 < N) pb[q] = __ldg(reinterpret_cast<const float4*>(Bm + (size_t)(k0 + row) * N + n0 + c4));
+    }
+  };
+  load_tiles(0);
+  for (int k0 = 0; k0 < K; k0 += 16) {
+#pragma unroll
+    for (int q = 0; q < PA; ++q) {
+      const int i = tid + q * NT, row = i >> 2, kq = (i & 3) * 4;
+      if (i < A4) {
+        As[kq + 0][row] = pa[q].x;
+        As[kq + 1][row] = pa[q].y;
+        As[kq + 2][row] = pa[q].z;
+        As[kq + 3][row] = pa[q].w;
+      }
+    }
+#pragma unroll
+    for (int q = 0; q < PB; ++q) {
+      const int i = tid + q * NT, row = i / (BN / 4), c4 = (i % (BN / 4)) * 4;
+      if (i < B4) *reinterpret_cast<float4*>(&Bs[row][c4]) = pb[q];
+    }
+    if (k0 + 16 < K) load_tiles(k0 + 16);
+    __syncthreads();
+#pragma unroll
+    for (int kk = 0; kk < 16; ++kk) {
+      float a[TM], bv[TN];
+#pragma unroll
+      for (int i = 0; i < TM; i += 4) {
+        const float4 av = *reinterpret_cast<const float4*>(&As[kk][ty * TM + i]);
+        a[i] = av.x, a[i + 1] = av.y, a[i + 2] = av.z, a[i + 3] = av.w;
+      }
+      if (TN == 4) {
+        const float4 b4 = *reinterpret_cast<const float4*>(&Bs[kk][tx * 4]);
+        bv[0] = b4.x, bv[1] = b4.y, bv[TN - 2] = b4.z, bv[TN - 1] = b4.w;
+      } else {
+        const float2 b2 = *reinterpret_cast<const float2*>(&Bs[kk][tx * 2]);
+        bv[0] = b2.x, bv[1] = b2.y;
+      }
+#pragma unroll
+      for (int i = 0; i < TM; ++i)
+#pragma unroll
+        for (int j = 0; j < TN; ++j) acc[i][j] = fmaf(a[i], bv[j], acc[i][j]);
+    }
+    __syncthreads();
+  }
+#pragma unroll
+  for (int i = 0; i < TM; ++i) {
+    const int m = m0 + ty * TM + i;
+    if (m >= M) continue;
+#pragma unroll
+    for (int j = 0; j < TN; ++j) {
+      const int n = n0 + tx * TN + j;
+      if (n >= N) continue;
+      float v = acc[i][j];
+      if (bias != nullptr) v += bias[n];
+      if (Cadd != nullptr) v += Cadd[(size_t)m * N + n];
+      C[(size_t)m * N + n] = v;
+    }
+  }
+}
+
 // Pack one BLSTM layer: wihT [160][640] (col = dir*320 + gate row), bias [640] = b_ih + b_hh,
 // whhT [2][80][320], wih_cat [640][160], whh [2][320][80] (straight copies of the live tensors).
 // perm_wf > 0: the layer's input arrives in the convolution's NHWC order (index w * C + c, C = I / perm_wf) instead of the
@@ -379,7 +469,26 @@ int rnn_init() {
 int gemm(const float* A, const float* Bm, const float* bias, const float* Cadd, float* C, int M, int N, int K,
          cudaStream_t stream, const char* tag) {
   ADVB_CHECK(K % 4 == 0 && N % 4 == 0, "gemm: K and N must be multiples of 4");
-  if (cdiv(N, 64) * cdiv(M, 64) < 2 * 148) {
+  static const int cfg = [] {  // ADVB_GEMM_RT=0: the first 4 x 4 / 4 x 2 register-tile kernel (bit-identical results, A/B only)
+    const char* e = getenv("ADVB_GEMM_RT");
+    return e != nullptr ? atoi(e) : 1;
+  }();
+  const bool narrow = cdiv(N, 64) * cdiv(M, 64) < 2 * 148;
+  // measured on the BLSTM projections (B = 128: 3 200 x 640 x 160 forward, 3 200 x 160 x 640 backward): 30.5 -> 26.7 us and
+  // 36.9 -> 33.3 us; (128 x 32, 8 x 2) for the narrow one: 35.9 us
+  if (cfg == 1 && !narrow) {  // 128 x 64 tile, 8 x 4 per thread
+    dim3 grid(cdiv(N, 64), cdiv(M, 128));
+    gemm_rt_kernel<128, 64, 8, 4><<<grid, 256, 0, stream>>>(A, Bm, bias, Cadd, C, M, N, K);
+    ADVB_KERNEL_OK(tag, stream);
+    return 0;
+  }
+  if (cfg == 1 && narrow) {  // 64 x 32 tile, 4 x 4 per thread (128 threads)
+    dim3 grid(cdiv(N, 32), cdiv(M, 64));
+    gemm_rt_kernel<64, 32, 4, 4><<<grid, 128, 0, stream>>>(A, Bm, bias, Cadd, C, M, N, K);
+    ADVB_KERNEL_OK(tag, stream);
+    return 0;
+  }
+  if (narrow) {
     dim3 grid(cdiv(N, 32), cdiv(M, 64));
     gemm_kernel<64, 32><<<grid, 256, 0, stream>>>(A, Bm, bias, Cadd, C, M, N, K);
   } else {
