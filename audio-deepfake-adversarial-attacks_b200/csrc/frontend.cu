@@ -20,6 +20,7 @@
 //                   filterbank^T, one-sided inverse DFT as a packed complex FFT, window, overlap-add and reflect-pad
 //                   fold in shared memory in a fixed order (deterministic, no atomics), gradient store
 #include "frontend.cuh"
+#include "tc_common.cuh"
 
 #include <math.h>
 
@@ -146,6 +147,21 @@ __device__ __forceinline__ void load_frame_pair(const float* __restrict__ xb, in
   __syncwarp();
 }
 
+// Same frame pair out of `raw` = the 560 consecutive samples x[160 ta - 200 ..] (interior pairs: no reflection), already in
+// shared memory (TMA prefetch of fe_power_db_kernel).
+__device__ __forceinline__ void load_frame_pair_raw(const float* raw, const float* s_win, float2* buf, int lane) {
+  for (int n = lane; n < NFFT; n += 32) {
+    float a = 0.f, b = 0.f;
+    if (n >= WOFF && n < WOFF + WIN) {
+      const float w = s_win[n - WOFF];
+      a = w * raw[n - WOFF];
+      b = w * raw[n - WOFF + HOP];
+    }
+    buf[n] = make_float2(a, b);
+  }
+  __syncwarp();
+}
+
 // From the packed spectrum Z: one-sided spectra of both frames at bin k.
 __device__ __forceinline__ void unpack_bin(const float2* z, int k, float& xar, float& xai, float& xbr, float& xbi) {
   const float2 p = z[k], q = z[(NFFT - k) & (NFFT - 1)];
@@ -249,6 +265,23 @@ __global__ void __launch_bounds__(FE_THREADS, 3) fe_power_db_kernel(const float*
   float2* bufB = bufA + FFT_A;
   float* pa = reinterpret_cast<float*>(bufA);  // power vectors live in buffer A, which is scratch once Z sits in buffer B
   float* pb = pa + PSTRIDE;
+  // Sample prefetch (round 2): an interior frame pair is 560 CONSECUTIVE, 16-byte aligned samples (160 ta - 200 is a multiple of
+  // 4), and buffer B is free from the moment the power vectors are built until the next item's FFT writes it - so the warp's
+  // elected lane posts ONE 2 240-byte TMA bulk copy of the NEXT item's samples into B there, and the filterbank / dB / arg-max
+  // phase of this item hides its latency (the per-lane scalar __ldg's of the frame load were the kernel's top stall:
+  // long_scoreboard 5.9 warps per issue).  The first / last pair of a clip (reflection) keep the direct loads.
+  __shared__ uint64_t bar_pf[FE_WARPS];
+  if (lane == 0) tc::mbar_init(&bar_pf[warp], 1);
+  tc::fence_barrier_init();
+  __syncwarp();
+  bool pf_valid = false;
+  unsigned pf_count = 0;
+  const bool x_al16 = (reinterpret_cast<uintptr_t>(x) & 15) == 0;
+  // interior pair whose first sample is 16-byte aligned in global memory (clip starts are not when T is not a multiple of 4)
+  auto pair_interior = [&](int b_, int ta_) {
+    const int s0 = HOP * ta_ - (NFFT / 2 - WOFF);
+    return x_al16 && (ta_ + 1) < F && s0 >= 0 && s0 + HOP + WIN <= T && ((((long long)b_ * T + s0) & 3) == 0);
+  };
 
   float best = -INFINITY;
   unsigned best_idx = 0xffffffffu;
@@ -256,11 +289,19 @@ __global__ void __launch_bounds__(FE_THREADS, 3) fe_power_db_kernel(const float*
   for (int work = blockIdx.x; work < n_blocks * n_clips; work += gridDim.x) {
     const int b = work / n_blocks;
     const int ta = (work - b * n_blocks) * (2 * FE_WARPS) + 2 * warp;
-    if (ta >= F) continue;  // warp-uniform; the loop has no block-wide barrier
+    if (ta >= F) {  // warp-uniform; the loop has no block-wide barrier
+      pf_valid = false;
+      continue;
+    }
     const bool has_b = (ta + 1) < F;
     const float* xb = x + (size_t)b * T;
 
-    load_frame_pair(xb, T, F, ta, s_win, bufA, lane);
+    if (pf_valid) {
+      tc::mbar_wait(&bar_pf[warp], (pf_count - 1u) & 1u);
+      load_frame_pair_raw(reinterpret_cast<const float*>(bufB), s_win, bufA, lane);
+    } else {
+      load_frame_pair(xb, T, F, ta, s_win, bufA, lane);
+    }
     warp_fft512(bufA, bufB, s_tw, lane);
     if (spec != nullptr) {
       // keep the packed spectrum of the frame pair (ta, ta + 1) for the backward: 4 KB per pair, coalesced float2 rows.  The
@@ -277,6 +318,23 @@ __global__ void __launch_bounds__(FE_THREADS, 3) fe_power_db_kernel(const float*
       pb[k] = xbr * xbr + xbi * xbi;
     }
     __syncwarp();
+    {  // buffer B is free: prefetch the next item's samples into it
+      const int nwork = work + gridDim.x;
+      pf_valid = false;
+      if (nwork < n_blocks * n_clips) {
+        const int nb = nwork / n_blocks;
+        const int nta = (nwork - nb * n_blocks) * (2 * FE_WARPS) + 2 * warp;
+        if (nta < F && pair_interior(nb, nta)) {
+          pf_valid = true;
+          ++pf_count;
+          if (lane == 0) {
+            tc::fence_proxy_async();
+            tc::mbar_expect_tx(&bar_pf[warp], (uint32_t)((HOP + WIN) * sizeof(float)));
+            tc::bulk_g2s(bufB, x + (size_t)nb * T + HOP * nta - (NFFT / 2 - WOFF), (uint32_t)((HOP + WIN) * sizeof(float)), &bar_pf[warp]);
+          }
+        }
+      }
+    }
 
     const size_t rowa = ((size_t)b * F + ta) * NFILT;
     float ea[4], eb[4];
