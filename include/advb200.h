@@ -99,7 +99,9 @@ ADVB_API int advb_invalidate_weights(advb_handle* h);
 
 /* Engine options (no reference counterpart; the reference's knobs are torch-global):
  *   "conv_path"   0 = tcgen05 tensor-core convolutions / GEMMs (default), 1 = fp32 SIMT convolutions / GEMMs (cross-check)
- *   "tf32_passes" 3 = 3xTF32 error-compensated products, fp32-class accuracy (default), 1 = single-pass tf32
+ *   "tf32_passes" 3 = 3xTF32 error-compensated products, fp32-class accuracy (default); 2 = LCNN forward 3x3 blocks with the tf32
+ *                 main term + ONE bf16 MMA for both cross terms, 3xTF32 everywhere else (opt-in experiment: same logits and
+ *                 gradients to the reference's tolerance, but the strict element-wise CW gate fails under it); 1 = single-pass tf32
  *   "conv_sched"  0 = persistent warp-specialised convolution / GEMM kernels (default), 1 = one-tile-per-CTA kernels only
  *                 (the first tcgen05 version; same arithmetic, kept as an in-process cross-check)
  *   "conv0_bwd"   LCNN first block backward: 0 = fp32 cell kernel (default), 1 = tcgen05 GEMM + col2im (cross-check)
@@ -108,6 +110,8 @@ ADVB_API int advb_invalidate_weights(advb_handle* h);
  *                 kernel enqueued by the host loop (same kernels, same results)
  *   "fuse_update" 1 = the FGSM / PGD L-inf update rule runs in the epilogue of the frontend backward and the waveform gradient
  *                 never reaches HBM (default; LFCC / MFCC models), 0 = separate update kernel (bit-identical iterates)
+ *   "fe_spec"     1 = the frontend backward reads the packed spectra the forward stored (default), 0 = recomputes the STFT
+ *   "lstm_tc"     1 = BLSTM input projections on the tcgen05 3xTF32 GEMM, 0 = fp32 SIMT GEMM (default)
  *   "weight_cache" see advb_invalidate_weights */
 ADVB_API int advb_set_option(advb_handle* h, const char* key, int value);
 
