@@ -76,6 +76,12 @@ int conv0t_forward(const ConvFwdArgs& a, const unsigned char* wpack, int passes,
 bool conv_p3_supported(int Cin, int Cout, int KS, bool pool, int W);
 int conv_p3_forward(const ConvFwdArgs& a, const unsigned char* wpack, int passes, cudaStream_t stream);
 int conv_p3_backward(const ConvBwdArgs& a, const unsigned char* wpack, int passes, cudaStream_t stream);
+// Plain 3x3 convolution (pad 1, stride 1, 64 -> 64 channels, W <= 40) on the same persistent tcgen05 kernel: in (B, H+2, W+2, 64) with a
+// zero border, wpack = a forward image of conv_tc_pack; out (B, H+2p, W+2p, 64) = (acc + bias) [* (mul_h > 0 ? 1 : slope) * mul_scale[c]]
+// with mul_h in the layout of `in`.  Fed with the backward image of conv_tc_pack it is the transposed convolution.
+int conv_p3_plain_forward(const float* in, float* out, int out_pad, const unsigned char* wpack, const float* bias,
+                          const float* mul_h, const float* mul_scale, float mul_slope, int B, int H, int W, int C, int passes,
+                          const char* tag, cudaStream_t stream);
 // mixed mode (passes = 2, forward only): tf32 main term + both cross terms as ONE bf16 MMA; its own weight image (same bytes)
 int conv_p3_pack_mix(const float* w, unsigned char* wf, int Cout, int Cin, cudaStream_t stream);
 // "horizontal scatter" backward (N = 3 C_in): needs its own weight image in the layer's backward pack buffer

@@ -52,6 +52,9 @@ struct P3Args {
   const unsigned char* codes_in;
   float* gin;
   int passes;
+  const float* mul_h;      // PLAIN: optional (B, H+2, W+2, NOUT) bordered tensor whose sign gates the output (LeakyReLU')
+  const float* mul_scale;  // PLAIN: per-channel factor applied together with mul_h
+  float mul_slope;
   FastDiv dTiles, dWp, dW, dWo;
   long long* prof;  // optional (ADVB_P3_PROF=1): per-phase cycle counts of CTA 0 (worker thread 0, MMA warp leader)
 };
@@ -61,9 +64,13 @@ struct P3Args {
 // gin[q][ci] = sum_dx Z[q + dx - 1][dx][ci].  The plain backward has N = C_in = 32 / 48, and tcgen05.mma costs ~64 cycles
 // per M=128, K=8 instruction however small N is (measured: block 2 backward ran at exactly that issue floor whatever the
 // schedule), so 3x fewer, 3x wider MMAs cut its tensor time 3x.
-template <int KTOT, int NOUT, bool POOL, bool BWD, bool HS>
+// PLAIN (forward only): an ordinary 3x3 convolution - every output channel kept (no Max-Feature-Map pairing, no pooling, no code
+// bytes), out = (acc + bias) [* (mul_h > 0 ? 1 : mul_slope) * mul_scale[c]].  SpecRNet's 64 -> 64 convolutions and, fed with the
+// flipped / transposed weight image, their transposes (specrnet.cu).
+template <int KTOT, int NOUT, bool POOL, bool BWD, bool HS, bool PLAIN = false>
 struct P3Cfg {
   static_assert(!HS || BWD, "horizontal scatter is a backward formulation");
+  static_assert(!PLAIN || (!BWD && !POOL), "the plain variant is a forward convolution without pooling");
   static constexpr int PW = 256;
   static constexpr int PT = PW + 64;
   static constexpr int NM3 = BWD ? 1 : 2;
@@ -76,7 +83,7 @@ struct P3Cfg {
   static constexpr int NSTRIDE = p3_pow2(NMMA);
   static constexpr int TMEM_COLS = p3_pow2(2 * NM3 * NSTRIDE);
   static constexpr int SLICE_BYTES = 2 * NMMA * 128;
-  static constexpr int CS = BWD ? NMMA : NOUT / 2;  // staged floats per pixel
+  static constexpr int CS = (BWD || PLAIN) ? NMMA : NOUT / 2;  // staged floats per pixel
   static constexpr int SS = CS + 4;
   static constexpr int STAGE_BYTES = NM3 * 128 * SS * 4 + NM3 * 128 * 8;
   static constexpr int BUF_BYTES = 2 * BR * 128;                    // hi rows then lo rows
@@ -90,9 +97,9 @@ struct P3Cfg {
   static_assert(ROOM / SLICE_BYTES >= 2, "weight ring does not fit");
 };
 
-template <int KTOT, int NOUT, bool POOL, bool BWD, bool HS>
-__global__ void __launch_bounds__(P3Cfg<KTOT, NOUT, POOL, BWD, HS>::PT, 1) conv_p3_kernel(P3Args a) {
-  using Cfg = P3Cfg<KTOT, NOUT, POOL, BWD, HS>;
+template <int KTOT, int NOUT, bool POOL, bool BWD, bool HS, bool PLAIN = false>
+__global__ void __launch_bounds__(P3Cfg<KTOT, NOUT, POOL, BWD, HS, PLAIN>::PT, 1) conv_p3_kernel(P3Args a) {
+  using Cfg = P3Cfg<KTOT, NOUT, POOL, BWD, HS, PLAIN>;
   constexpr int PW = Cfg::PW, PT = Cfg::PT;
   constexpr int NKC = Cfg::NKC, NSLICE = Cfg::NSLICE, NST = Cfg::NST, CS = Cfg::CS, SS = Cfg::SS;
   constexpr int NM3 = Cfg::NM3, NI_MAX = Cfg::NI_MAX, BR = Cfg::BR, NTAP = Cfg::NTAP, NMMA = Cfg::NMMA;
@@ -131,7 +138,7 @@ __global__ void __launch_bounds__(P3Cfg<KTOT, NOUT, POOL, BWD, HS>::PT, 1) conv_
   }
   if (warp == 0) tmem_alloc<Cfg::TMEM_COLS>(&tmem_base_s);
   if (!BWD)
-    for (int i = tid; i < NOUT; i += PT) s_bias[i] = __ldg(a.bias + i);
+    for (int i = tid; i < NOUT; i += PT) s_bias[i] = a.bias != nullptr ? __ldg(a.bias + i) : 0.f;
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -391,6 +398,22 @@ __global__ void __launch_bounds__(P3Cfg<KTOT, NOUT, POOL, BWD, HS>::PT, 1) conv_
                 *reinterpret_cast<float4*>(srow + c0 + j) = make_float4(
                     __uint_as_float(v[j]), __uint_as_float(v[j + 1]), __uint_as_float(v[j + 2]), __uint_as_float(v[j + 3]));
             }
+          } else if (PLAIN) {
+            const uint32_t srow_s = smem_u32(srow);
+#pragma unroll
+            for (int c0 = 0; c0 < NOUT; c0 += 16) {
+              uint32_t v[16];
+              tmem_ld16_issue(taddr + c0, v);
+              tmem_ld_wait();
+#pragma unroll
+              for (int j = 0; j < 16; j += 4) {
+                const float4 b4 = *reinterpret_cast<const float4*>(s_bias + c0 + j);
+                asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(srow_s + (uint32_t)(c0 + j) * 4u),
+                             "f"(__uint_as_float(v[j]) + b4.x), "f"(__uint_as_float(v[j + 1]) + b4.y),
+                             "f"(__uint_as_float(v[j + 2]) + b4.z), "f"(__uint_as_float(v[j + 3]) + b4.w)
+                             : "memory");
+              }
+            }
           } else {
             // c0 unrolled: flag bits become immediates, the bias comes by LDS.128 and the row goes out by st.shared (the generic
             // stores emitted before cost an address-space check each): 92 instructions per 16 channels instead of 210; this phase
@@ -449,6 +472,23 @@ __global__ void __launch_bounds__(P3Cfg<KTOT, NOUT, POOL, BWD, HS>::PT, 1) conv_
             v = *reinterpret_cast<const float4*>(sp);
           }
           *reinterpret_cast<float4*>(a.gin + (((size_t)b * a.H + y0 + yl) * a.W + x) * NOUT + 4 * c4i) = v;
+        }
+      } else if (PLAIN) {
+        const int Hop = a.Ho + 2 * a.out_pad, Wop = a.Wo + 2 * a.out_pad;
+        const int items = rows * a.Wo * C4;
+        for (int i = tid; i < items; i += PW) {
+          const int ic = i / C4, c4i = i - C4 * ic, yl = fdiv(ic, a.dWo), x = ic - yl * a.Wo;
+          const int c = 4 * c4i, oy = y0 + yl;
+          float4 v = *reinterpret_cast<const float4*>(stage + (size_t)(yl * Wp + x + 1) * SS + c);
+          if (a.mul_h != nullptr) {  // * LeakyReLU'(h) * per-channel scale: the transposed convolution's chain-rule factor
+            const float4 hv = __ldg(reinterpret_cast<const float4*>(a.mul_h + (((size_t)b * Hp + oy + 1) * Wp + x + 1) * NOUT + c));
+            const float4 sv = __ldg(reinterpret_cast<const float4*>(a.mul_scale + c));
+            v.x *= (hv.x > 0.f ? 1.0f : a.mul_slope) * sv.x;
+            v.y *= (hv.y > 0.f ? 1.0f : a.mul_slope) * sv.y;
+            v.z *= (hv.z > 0.f ? 1.0f : a.mul_slope) * sv.z;
+            v.w *= (hv.w > 0.f ? 1.0f : a.mul_slope) * sv.w;
+          }
+          *reinterpret_cast<float4*>(a.out + (((size_t)b * Hop + oy + a.out_pad) * Wop + x + a.out_pad) * NOUT + c) = v;
         }
       } else {
         const int Hop = a.Ho + 2 * a.out_pad, Wop = a.Wo + 2 * a.out_pad;
@@ -565,9 +605,9 @@ int tune_p3() {
   return v;
 }
 
-template <int KTOT, int NOUT, bool POOL, bool BWD, bool HS = false>
+template <int KTOT, int NOUT, bool POOL, bool BWD, bool HS = false, bool PLAIN = false>
 int launch_p3(P3Args a, const char* tag, cudaStream_t stream) {
-  using Cfg = P3Cfg<KTOT, NOUT, POOL, BWD, HS>;
+  using Cfg = P3Cfg<KTOT, NOUT, POOL, BWD, HS, PLAIN>;
   const int Wp = a.W + 2;
   const int Heff = (!BWD && POOL) ? 2 * a.Ho : a.H;
   const bool even = !BWD && POOL;
@@ -588,7 +628,7 @@ int launch_p3(P3Args a, const char* tag, cudaStream_t stream) {
   a.dW = make_fastdiv(a.W);
   a.dWo = make_fastdiv(a.Wo);
   ADVB_CHECK(cdiv(R * Wp, 128) * 128 + 2 * (Wp + 1) <= Cfg::BR, "persistent 3x3 conv: band exceeds its buffer");
-  auto kern = conv_p3_kernel<KTOT, NOUT, POOL, BWD, HS>;
+  auto kern = conv_p3_kernel<KTOT, NOUT, POOL, BWD, HS, PLAIN>;
   ADVB_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::SMEM));
   int n_sm = 148, dev = 0;
   cudaGetDevice(&dev);
@@ -707,6 +747,19 @@ int conv_p3_forward(const ConvFwdArgs& f, const unsigned char* wpack, int passes
   if (f.Cin == 64 && f.Cout == 64 && !f.pool) return launch_p3<64, 64, false, false>(a, f.tag, stream);
   set_error("conv shape has no persistent 3x3 instantiation");
   return 1;
+}
+
+int conv_p3_plain_forward(const float* in, float* out, int out_pad, const unsigned char* wpack, const float* bias,
+                          const float* mul_h, const float* mul_scale, float mul_slope, int B, int H, int W, int C, int passes,
+                          const char* tag, cudaStream_t stream) {
+  ADVB_CHECK(C == 64 && W <= 40, "plain persistent 3x3 conv: 64 -> 64 channels, width <= 40");
+  P3Args a{};
+  a.B = B, a.H = H, a.W = W, a.Ho = H, a.Wo = W;
+  a.wpack = wpack;
+  a.in = in, a.out = out, a.out_pad = out_pad, a.bias = bias;
+  a.mul_h = mul_h, a.mul_scale = mul_scale, a.mul_slope = mul_slope;
+  a.passes = passes;
+  return launch_p3<64, 64, false, false, false, true>(a, tag, stream);
 }
 
 int conv_p3_backward(const ConvBwdArgs& g, const unsigned char* wpack, int passes, cudaStream_t stream) {

@@ -124,6 +124,7 @@ struct advb_handle {
         *cs2 = nullptr, *dl2 = nullptr, *dl1 = nullptr, *dfeats = nullptr, *logits = nullptr;
   LstmPacked lp[2]{};
   unsigned char* lp_tc[2][2] = {{nullptr, nullptr}, {nullptr, nullptr}};  // tcgen05 images of the BLSTM input projections
+  int sr_tc = 1;    // SpecRNet: 1 = the 64 -> 64 convolutions (conv2 of blocks 2 and 4) on the tcgen05 kernel (round 2), 0 = fp32 SIMT
   int lstm_tc = 0;  // 1 = BLSTM input projections on the tcgen05 GEMM (3xTF32; measured 21 / 40 us vs 30 / 37 us: the persistent
                     // GEMM's fixed costs eat the gain at 0.66 GFLOP), 0 = fp32 SIMT GEMM (default)
 
@@ -572,6 +573,13 @@ int build_specrnet(advb_handle* h) {
     ADVB_TRY(h->alloc(&k.g_xn, B * k.Hn * k.Wn * C));
     ADVB_TRY(h->alloc(&k.gadd, B * C));
     ADVB_TRY(h->alloc(&k.g_c1, B * H * W * C));
+    if (k.Cout == 64 && k.C == 64 && W <= 40) {  // conv2 (64 -> 64) on the persistent tcgen05 kernel (conv_path = 0)
+      ADVB_TRY(h->alloc(&k.w2t, 9 * C * C));
+      ADVB_TRY(h->alloc(&k.tcf2, conv_tc_pack_bytes(64, 64, 3, false)));
+      ADVB_TRY(h->alloc(&k.tcd2, conv_tc_pack_bytes(64, 64, 3, true)));
+      ADVB_TRY(h->alloc(&k.c2, B * H * W * C));
+      ADVB_TRY(h->alloc(&k.go, B * (H + 2) * (W + 2) * C));
+    }
     H = k.Hn, W = k.Wn;
   }
   ADVB_CHECK(W == 1, "SpecRNet expects the coefficient axis to pool down to 1");
@@ -597,7 +605,10 @@ int prepare_specrnet(advb_handle* h, cudaStream_t st) {
   bind_specrnet(h);
   ADVB_TRY(sr_pack_first_bn(h->t("first_bn.weight"), h->t("first_bn.bias"), h->t("first_bn.running_mean"),
                             h->t("first_bn.running_var"), h->sr_bn4, st));
-  for (int i = 0; i < 3; ++i) ADVB_TRY(sr_pack_block(h->sr[i], st));
+  for (int i = 0; i < 3; ++i) {
+    h->sr[i].tc2 = h->sr[i].tcf2 != nullptr && h->conv_path == 0 && h->sr_tc != 0;
+    ADVB_TRY(sr_pack_block(h->sr[i], st));
+  }
   ADVB_TRY(sr_pack_gru(h->gru, st));
   return 0;
 }
@@ -923,6 +934,9 @@ int advb_set_option(advb_handle* h, const char* key, int value) {
   } else if (k == "conv0_fwd") {
     ADVB_CHECK(value == 0 || value == 1, "conv0_fwd: 0 = Toeplitz GEMM without im2col, 1 = im2col GEMM");
     h->conv0_fwd = value;
+  } else if (k == "sr_tc") {
+    ADVB_CHECK(value == 0 || value == 1, "sr_tc: 1 = SpecRNet 64 -> 64 convolutions on tcgen05 (3xTF32), 0 = fp32 SIMT");
+    h->sr_tc = value;
   } else if (k == "lstm_tc") {
     ADVB_CHECK(value == 0 || value == 1, "lstm_tc: 1 = BLSTM input projections on the tcgen05 GEMM, 0 = fp32 SIMT GEMM");
     h->lstm_tc = value;
@@ -995,7 +1009,7 @@ std::string graph_key(const advb_handle* h, const advb_attack_desc* atk, int B, 
   return std::to_string(atk->kind) + "|" + std::to_string(B) + "|" + bits(atk->eps) + "|" + bits(atk->alpha) + "|" +
          bits(atk->eps_div) + "|" + std::to_string(n_global) + "|" + std::to_string(fused) + "|" +
          std::to_string(h->conv_path) + "|" + std::to_string(h->tf32_passes) + "|" + std::to_string(h->conv_sched) + "|" +
-         std::to_string(h->conv0_bwd) + "|" + std::to_string(h->conv0_fwd) + "|" + std::to_string(h->fe_spec) + "|" + std::to_string(h->lstm_tc) + "|" +
+         std::to_string(h->conv0_bwd) + "|" + std::to_string(h->conv0_fwd) + "|" + std::to_string(h->fe_spec) + "|" + std::to_string(h->lstm_tc) + "|" + std::to_string(h->sr_tc) + "|" +
          std::to_string(h->bind_epoch);
 }
 

@@ -25,6 +25,7 @@
 
 #include <algorithm>
 
+#include "conv.cuh"
 #include "conv_core.cuh"
 
 namespace advb {
@@ -66,6 +67,7 @@ struct SrArgs {
   int qpc;              // quads (2x2 output pixels) per CTA
   int CKr;              // contraction channels that are not zero padding (multiple of 4 when CK is), <= CK
   int slab_all;         // 1: all 9 weight slabs are staged once per CTA (small layers), 0: one slab per tap
+  const float* c2;      // F2 only: conv2(h) (B, H, W, N) computed by the tensor-core kernel - the contraction here is skipped
 };
 
 // 4 consecutive channels (c..c+3) of the gradient at conv2's output pixel (yy, xx): un-pool of
@@ -110,8 +112,11 @@ __global__ void __launch_bounds__(256) sr_conv_kernel(SrArgs a, int band_floats)
   float* s_part = w_s + (a.slab_all ? 9 : 1) * CK * a.N;  // F2 only: qpc x N partial sums
   const int b = blockIdx.y, tid = threadIdx.x, nt = blockDim.x;
 
+  const bool from_c2 = MODE == F2 && a.c2 != nullptr;
   // ---- stage the band: rows 2*qy0-1 ..., columns -1 .. 2*QW ----
-  if (MODE == F1 || MODE == F2) {
+  if (from_c2) {
+    // nothing to stage: the accumulators come from the tensor-core convolution
+  } else if (MODE == F1 || MODE == F2) {
     const int Hp = a.H + 2, Wp = a.W + 2;
     const float* inb = a.in + (size_t)b * Hp * Wp * CK;
     if ((CK & 3) == 0) {
@@ -158,7 +163,22 @@ __global__ void __launch_bounds__(256) sr_conv_kernel(SrArgs a, int band_floats)
   for (int p = 0; p < 4; ++p)
 #pragma unroll
     for (int j = 0; j < 8; ++j) acc[p][j] = 0.f;
-  conv_core<3>(band, g.BW, CK, CKp, a.wpk, w_s, N, 2 * (qy - g.qy0), 2 * qx, 4 * cg, valid, acc, a.CKr, a.slab_all != 0);
+  if (from_c2) {
+    if (valid) {
+      const int nh2 = N >> 1;
+#pragma unroll
+      for (int p = 0; p < 4; ++p) {
+        const int y = 2 * qy + (p >> 1), x = 2 * qx + (p & 1);
+        const float* src = a.c2 + (((size_t)b * a.H + y) * a.W + x) * N;
+        const float4 lo = __ldg(reinterpret_cast<const float4*>(src + 4 * cg));
+        const float4 hi = __ldg(reinterpret_cast<const float4*>(src + nh2 + 4 * cg));
+        acc[p][0] = lo.x, acc[p][1] = lo.y, acc[p][2] = lo.z, acc[p][3] = lo.w;
+        acc[p][4] = hi.x, acc[p][5] = hi.y, acc[p][6] = hi.z, acc[p][7] = hi.w;
+      }
+    }
+  } else {
+    conv_core<3>(band, g.BW, CK, CKp, a.wpk, w_s, N, 2 * (qy - g.qy0), 2 * qx, 4 * cg, valid, acc, a.CKr, a.slab_all != 0);
+  }
 
   const int nh = N >> 1, c0 = 4 * cg;
   if (MODE == F1) {
@@ -445,6 +465,30 @@ __global__ void __launch_bounds__(256) sr_attention_bwd_kernel(const float* __re
     if (tid < Cout)
       for (int cc = 0; cc < Cout; ++cc) s = fmaf(__ldg(att_w + cc * Cout + tid), s_gz[cc], s);
     gadd[(size_t)b * C + tid] = s * inv_hw;
+  }
+}
+
+// The expanded gradient at conv2's output, materialised with a zero border for the tensor-core transposed convolution.
+__global__ void sr_expand_go_kernel(SrArgs a, float* __restrict__ go, int64_t n4) {
+  const int C4 = a.C >> 2, Hp = a.H + 2, Wp = a.W + 2;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n4; i += (int64_t)gridDim.x * blockDim.x) {
+    const int c4 = (int)(i % C4);
+    int64_t r = i / C4;
+    const int xp = (int)(r % Wp);
+    r /= Wp;
+    const int yp = (int)(r % Hp), b = (int)(r / Hp);
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (yp >= 1 && yp <= a.H && xp >= 1 && xp <= a.W) v = expand_go(a, b, yp - 1, xp - 1, 4 * c4);
+    reinterpret_cast<float4*>(go)[i] = v;
+  }
+}
+
+// wt[co][ci][a][b] = w[co][ci][b][a]: the engine's image is the transpose of the reference's (frames x coeffs)
+__global__ void sr_tap_transpose_kernel(const float* __restrict__ w, float* __restrict__ wt, int n) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) {
+    const int t = i % 9, a_ = t / 3, b_ = t % 3;
+    wt[i] = w[i - t + b_ * 3 + a_];
   }
 }
 
@@ -768,6 +812,11 @@ int sr_pack_block(SrBlock& k, cudaStream_t stream) {
       ADVB_KERNEL_OK("sr_pack", stream);
     }
   }
+  if (k.tcf2 != nullptr) {
+    sr_tap_transpose_kernel<<<cdiv(k.Cout * k.Cout * 9, 256), 256, 0, stream>>>(k.w2, k.w2t, k.Cout * k.Cout * 9);
+    ADVB_KERNEL_OK("sr_pack", stream);
+    ADVB_TRY(conv_tc_pack(k.w2t, k.tcf2, k.tcd2, k.Cout, k.Cout, 3, stream));
+  }
   sr_pack_vec_kernel<<<1, 64, 0, stream>>>(k.b1, k.b2, k.downsample ? k.bds : nullptr, k.bn_w, k.bn_b, k.bn_rm, k.bn_rv,
                                           k.b1p, k.b2p, k.bdp, k.bn_scale, k.bn_shift, k.Cout, k.C);
   ADVB_KERNEL_OK("sr_pack", stream);
@@ -789,12 +838,12 @@ int sr_input_forward(float* img, const float* bn4, int B, int H, int W, cudaStre
 
 // profiler labels must outlive the call (prof_mark keeps the pointer): string literals per block
 struct SrTags {
-  const char *conv1, *conv2, *conv2_bwd, *conv1_bwd;
+  const char *conv1, *conv2, *conv2_bwd, *conv1_bwd, *conv2_tc, *expand_go;
 };
 const SrTags& sr_tags(const char* tag) {
-  static const SrTags t0{"sr_b0_conv1", "sr_b0_conv2", "sr_b0_conv2_bwd", "sr_b0_conv1_bwd"};
-  static const SrTags t2{"sr_b2_conv1", "sr_b2_conv2", "sr_b2_conv2_bwd", "sr_b2_conv1_bwd"};
-  static const SrTags t4{"sr_b4_conv1", "sr_b4_conv2", "sr_b4_conv2_bwd", "sr_b4_conv1_bwd"};
+  static const SrTags t0{"sr_b0_conv1", "sr_b0_conv2", "sr_b0_conv2_bwd", "sr_b0_conv1_bwd", "sr_b0_conv2_tc", "sr_b0_expand_go"};
+  static const SrTags t2{"sr_b2_conv1", "sr_b2_conv2", "sr_b2_conv2_bwd", "sr_b2_conv1_bwd", "sr_b2_conv2_tc", "sr_b2_expand_go"};
+  static const SrTags t4{"sr_b4_conv1", "sr_b4_conv2", "sr_b4_conv2_bwd", "sr_b4_conv1_bwd", "sr_b4_conv2_tc", "sr_b4_expand_go"};
   return tag[4] == '0' ? t0 : (tag[4] == '2' ? t2 : t4);
 }
 
@@ -807,6 +856,10 @@ int sr_block_forward(const SrBlock& k, const float* x, int B, const char* tag, c
   ADVB_TRY(launch_conv<F1>(a, false, t.conv1, stream));
   a.CK = k.C, a.CKr = std::min(k.C, (k.Cout + 3) / 4 * 4), a.in = k.h, a.wpk = k.w2f, a.bias = k.b2p, a.out = k.xb;
   a.x = x, a.Ci = k.Ci, a.wd = k.downsample ? k.wdf : nullptr, a.bd = k.bdp, a.code1w = k.code1, a.psum = k.psum;
+  if (k.tc2) {  // conv2(h) on the tensor cores; the fused kernel below keeps bias + identity + max-pool + arg-max + channel sums
+    ADVB_TRY(conv_p3_plain_forward(k.h, k.c2, 0, k.tcf2, nullptr, nullptr, nullptr, 0.f, B, k.H, k.W, k.C, 3, t.conv2_tc, stream));
+    a.c2 = k.c2;
+  }
   ADVB_TRY(launch_conv<F2>(a, true, t.conv2, stream));
   sr_attention_fwd_kernel<<<B, 64, 0, stream>>>(k.psum, k.n_tiles, k.att_w, k.att_b, k.y, k.C, k.Cout,
                                                1.0f / (float)(k.Hb * k.Wb));
@@ -827,7 +880,14 @@ int sr_block_backward(const SrBlock& k, const float* x, float* g_x, int B, bool 
   ADVB_KERNEL_OK("sr_attention_bwd", stream);
   SrArgs a = base_args(k, B);
   a.CK = k.C, a.CKr = std::min(k.C, (k.Cout + 3) / 4 * 4), a.N = k.C, a.wpk = k.w2d, a.out = k.g_c1;
-  ADVB_TRY(launch_conv<B2>(a, false, t.conv2_bwd, stream));
+  if (k.tc2) {  // g_o materialised once (zero border), conv2^T on the tensor cores with the LeakyReLU' * bn2-scale factor in its epilogue
+    const int64_t n4 = (int64_t)B * (k.H + 2) * (k.W + 2) * (k.C / 4);
+    sr_expand_go_kernel<<<ew_blocks(n4), 256, 0, stream>>>(a, k.go, n4);
+    ADVB_KERNEL_OK(t.expand_go, stream);
+    ADVB_TRY(conv_p3_plain_forward(k.go, k.g_c1, 0, k.tcd2, nullptr, k.h, k.bn_scale, 0.3f, B, k.H, k.W, k.C, 3, t.conv2_bwd, stream));
+  } else {
+    ADVB_TRY(launch_conv<B2>(a, false, t.conv2_bwd, stream));
+  }
   a.in = k.g_c1, a.x = x;
   if (first) {
     dim3 grid(cdiv(k.H * k.W, 256), B);

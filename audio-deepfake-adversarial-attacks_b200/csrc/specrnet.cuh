@@ -34,6 +34,14 @@ struct SrBlock {
   float* g_xn;            // (B, Hn, Wn, C)
   float* gadd;            // (B, C) broadcast term of the attention backward
   float* g_c1;            // (B, H, W, C) gradient at conv1's output (pre-BN)
+  // conv2 on the tensor cores (round 2; blocks with 64 -> 64 channels and W <= 40, engine option conv_path = 0): the persistent
+  // tcgen05 kernel of conv_p3.cu computes the plain convolution / its transpose, the fused SIMT kernel keeps only its epilogue
+  bool tc2 = false;
+  float* w2t = nullptr;            // conv2 weights with the 3x3 taps transposed (the engine's image is the reference's transposed)
+  unsigned char* tcf2 = nullptr;   // conv_tc_pack images of w2t: forward ...
+  unsigned char* tcd2 = nullptr;   // ... and flipped / channel-transposed (the transposed convolution as a forward one)
+  float* c2 = nullptr;             // (B, H, W, C) conv2(h) without bias
+  float* go = nullptr;             // (B, H+2, W+2, C) gradient at conv2's output, zero border
 };
 
 struct SrGru {

@@ -112,6 +112,8 @@ ADVB_API int advb_invalidate_weights(advb_handle* h);
  *                 never reaches HBM (default; LFCC / MFCC models), 0 = separate update kernel (bit-identical iterates)
  *   "fe_spec"     1 = the frontend backward reads the packed spectra the forward stored (default), 0 = recomputes the STFT
  *   "lstm_tc"     1 = BLSTM input projections on the tcgen05 3xTF32 GEMM, 0 = fp32 SIMT GEMM (default)
+ *   "sr_tc"       SpecRNet: 1 = the 64 -> 64 convolutions (conv2 of blocks 2 and 4) and their transposes on the persistent tcgen05
+ *                 kernel, 3xTF32 (default), 0 = fp32 SIMT like the rest of SpecRNet
  *   "weight_cache" see advb_invalidate_weights */
 ADVB_API int advb_set_option(advb_handle* h, const char* key, int value);
 

@@ -343,6 +343,23 @@ def test_tensor_core_path_matches_simt_path(name, cuda_device):
         eng.set_option("conv0_bwd", 0)
 
 
+def test_specrnet_tensor_core_conv2_matches_simt(cuda_device):
+    """Option sr_tc: conv2 of SpecRNet's 64-channel blocks on the persistent tcgen05 kernel (3xTF32; conv_p3's PLAIN variant, and the
+    same kernel fed with the flipped / channel-transposed image as the transposed convolution) against the fp32 SIMT kernels."""
+    name = SPEC_CASES[0]
+    case, x, y, holder, state, fwd, eng = _setup(name, cuda_device)
+    xd, yd = x.to(cuda_device), y.to(cuda_device)
+    try:
+        g1, l1 = eng.grad(xd, yd)
+        eng.set_option("sr_tc", 0)
+        g0, l0 = eng.grad(xd, yd)
+    finally:
+        eng.set_option("sr_tc", 1)
+    assert (l1 - l0).abs().max().item() < 2e-6
+    assert helpers.grads_agree(g1.cpu(), g0.cpu())
+    assert not torch.equal(g1, g0), "the two paths are different kernels: identical bits would mean the option is not wired"
+
+
 def test_projection_linf_against_oracle(cuda_device):
     """fab.py:562-614: the sort-free CUDA projection against the sort-based restatement, all three branches
     (unreachable hyperplane -> box corner, uniform level, saturating level), ragged row length."""
