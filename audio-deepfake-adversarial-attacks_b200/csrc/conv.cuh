@@ -52,6 +52,9 @@ bool conv_tc_supported(int Cin, int Cout, int KS, bool pool);
 size_t conv_tc_pack_bytes(int Cout, int Cin, int KS, bool bwd);
 // wf / wd: packed forward / backward weight slices (wd may be null)
 int conv_tc_pack(const float* w, unsigned char* wf, unsigned char* wd, int Cout, int Cin, int KS, cudaStream_t stream);
+// same images with N padded to `npad` rows (zero rows): (Cout, Cin) = (24, 24) -> MMA N = 32
+int conv_tc_pack_padded(const float* w, unsigned char* wf, unsigned char* wd, int Cout, int Cin, int KS, int npad, cudaStream_t stream);
+size_t conv_tc_pack_bytes_padded(int Cout, int Cin, int KS, bool bwd, int npad);
 // passes: 3 = 3xTF32 (fp32-class accuracy, default), 1 = single-pass tf32
 int conv_tc_forward(const ConvFwdArgs& a, const unsigned char* wpack, int passes, cudaStream_t stream);
 int conv_tc_backward(const ConvBwdArgs& a, const unsigned char* wpack, int passes, cudaStream_t stream);
@@ -76,7 +79,8 @@ int conv0t_forward(const ConvFwdArgs& a, const unsigned char* wpack, int passes,
 bool conv_p3_supported(int Cin, int Cout, int KS, bool pool, int W);
 int conv_p3_forward(const ConvFwdArgs& a, const unsigned char* wpack, int passes, cudaStream_t stream);
 int conv_p3_backward(const ConvBwdArgs& a, const unsigned char* wpack, int passes, cudaStream_t stream);
-// Plain 3x3 convolution (pad 1, stride 1, 64 -> 64 channels, W <= 40) on the same persistent tcgen05 kernel: in (B, H+2, W+2, 64) with a
+// Plain 3x3 convolution (pad 1, stride 1; C = 64 channels at W <= 40, or C = 24 at W <= 80 with N padded to 32 inside) on the same
+// persistent tcgen05 kernel: in (B, H+2, W+2, 64) with a
 // zero border, wpack = a forward image of conv_tc_pack; out (B, H+2p, W+2p, 64) = (acc + bias) [* (mul_h > 0 ? 1 : slope) * mul_scale[c]]
 // with mul_h in the layout of `in`.  Fed with the backward image of conv_tc_pack it is the transposed convolution.
 int conv_p3_plain_forward(const float* in, float* out, int out_pad, const unsigned char* wpack, const float* bias,

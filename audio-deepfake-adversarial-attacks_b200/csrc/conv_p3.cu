@@ -55,6 +55,7 @@ struct P3Args {
   const float* mul_h;      // PLAIN: optional (B, H+2, W+2, NOUT) bordered tensor whose sign gates the output (LeakyReLU')
   const float* mul_scale;  // PLAIN: per-channel factor applied together with mul_h
   float mul_slope;
+  int out_ch;              // PLAIN: channels stored per pixel (= the channel stride of out and mul_h); 0 = NOUT
   FastDiv dTiles, dWp, dW, dWo;
   long long* prof;  // optional (ADVB_P3_PROF=1): per-phase cycle counts of CTA 0 (worker thread 0, MMA warp leader)
 };
@@ -67,16 +68,18 @@ struct P3Args {
 // PLAIN (forward only): an ordinary 3x3 convolution - every output channel kept (no Max-Feature-Map pairing, no pooling, no code
 // bytes), out = (acc + bias) [* (mul_h > 0 ? 1 : mul_slope) * mul_scale[c]].  SpecRNet's 64 -> 64 convolutions and, fed with the
 // flipped / transposed weight image, their transposes (specrnet.cu).
-template <int KTOT, int NOUT, bool POOL, bool BWD, bool HS, bool PLAIN = false>
+// WMAX: widest image row the band is sized for (40: every LCNN block; 80: SpecRNet's first block, with 12 worker warps so that the
+// larger band still is <= 10 prefetch items per thread).
+template <int KTOT, int NOUT, bool POOL, bool BWD, bool HS, bool PLAIN = false, int WMAX = 40>
 struct P3Cfg {
   static_assert(!HS || BWD, "horizontal scatter is a backward formulation");
   static_assert(!PLAIN || (!BWD && !POOL), "the plain variant is a forward convolution without pooling");
-  static constexpr int PW = 256;
+  static constexpr int PW = WMAX > 40 ? 384 : 256;
   static constexpr int PT = PW + 64;
   static constexpr int NM3 = BWD ? 1 : 2;
   static constexpr int NTAP = HS ? 3 : 9;
   static constexpr int NMMA = HS ? 3 * NOUT : NOUT;  // MMA N = accumulator columns per M-tile
-  static constexpr int BR = (NM3 * 128 + 2 * (42 + 1) + 7) & ~7;  // band rows per buffer (widest layer: W = 40)
+  static constexpr int BR = (NM3 * 128 + 2 * (WMAX + 2 + 1) + 7) & ~7;  // band rows per buffer (widest row: W = WMAX)
   static constexpr int NI_MAX = (BR * 8 + PW - 1) / PW;            // prefetch items per worker thread
   static constexpr int NKC = (KTOT + 31) / 32;
   static constexpr int NSLICE = NKC * NTAP;
@@ -97,9 +100,9 @@ struct P3Cfg {
   static_assert(ROOM / SLICE_BYTES >= 2, "weight ring does not fit");
 };
 
-template <int KTOT, int NOUT, bool POOL, bool BWD, bool HS, bool PLAIN = false>
-__global__ void __launch_bounds__(P3Cfg<KTOT, NOUT, POOL, BWD, HS, PLAIN>::PT, 1) conv_p3_kernel(P3Args a) {
-  using Cfg = P3Cfg<KTOT, NOUT, POOL, BWD, HS, PLAIN>;
+template <int KTOT, int NOUT, bool POOL, bool BWD, bool HS, bool PLAIN = false, int WMAX = 40>
+__global__ void __launch_bounds__(P3Cfg<KTOT, NOUT, POOL, BWD, HS, PLAIN, WMAX>::PT, 1) conv_p3_kernel(P3Args a) {
+  using Cfg = P3Cfg<KTOT, NOUT, POOL, BWD, HS, PLAIN, WMAX>;
   constexpr int PW = Cfg::PW, PT = Cfg::PT;
   constexpr int NKC = Cfg::NKC, NSLICE = Cfg::NSLICE, NST = Cfg::NST, CS = Cfg::CS, SS = Cfg::SS;
   constexpr int NM3 = Cfg::NM3, NI_MAX = Cfg::NI_MAX, BR = Cfg::BR, NTAP = Cfg::NTAP, NMMA = Cfg::NMMA;
@@ -479,16 +482,18 @@ __global__ void __launch_bounds__(P3Cfg<KTOT, NOUT, POOL, BWD, HS, PLAIN>::PT, 1
         for (int i = tid; i < items; i += PW) {
           const int ic = i / C4, c4i = i - C4 * ic, yl = fdiv(ic, a.dWo), x = ic - yl * a.Wo;
           const int c = 4 * c4i, oy = y0 + yl;
+          const int och = a.out_ch > 0 ? a.out_ch : NOUT;  // NOUT may be padded beyond the stored channels (24 -> 32)
+          if (c >= och) continue;
           float4 v = *reinterpret_cast<const float4*>(stage + (size_t)(yl * Wp + x + 1) * SS + c);
           if (a.mul_h != nullptr) {  // * LeakyReLU'(h) * per-channel scale: the transposed convolution's chain-rule factor
-            const float4 hv = __ldg(reinterpret_cast<const float4*>(a.mul_h + (((size_t)b * Hp + oy + 1) * Wp + x + 1) * NOUT + c));
+            const float4 hv = __ldg(reinterpret_cast<const float4*>(a.mul_h + (((size_t)b * Hp + oy + 1) * Wp + x + 1) * och + c));
             const float4 sv = __ldg(reinterpret_cast<const float4*>(a.mul_scale + c));
-            v.x *= (hv.x > 0.f ? 1.0f : a.mul_slope) * sv.x;
-            v.y *= (hv.y > 0.f ? 1.0f : a.mul_slope) * sv.y;
-            v.z *= (hv.z > 0.f ? 1.0f : a.mul_slope) * sv.z;
-            v.w *= (hv.w > 0.f ? 1.0f : a.mul_slope) * sv.w;
+            v.x = v.x * (hv.x > 0.f ? 1.0f : a.mul_slope) * sv.x;
+            v.y = v.y * (hv.y > 0.f ? 1.0f : a.mul_slope) * sv.y;
+            v.z = v.z * (hv.z > 0.f ? 1.0f : a.mul_slope) * sv.z;
+            v.w = v.w * (hv.w > 0.f ? 1.0f : a.mul_slope) * sv.w;
           }
-          *reinterpret_cast<float4*>(a.out + (((size_t)b * Hop + oy + a.out_pad) * Wop + x + a.out_pad) * NOUT + c) = v;
+          *reinterpret_cast<float4*>(a.out + (((size_t)b * Hop + oy + a.out_pad) * Wop + x + a.out_pad) * och + c) = v;
         }
       } else {
         const int Hop = a.Ho + 2 * a.out_pad, Wop = a.Wo + 2 * a.out_pad;
@@ -605,16 +610,16 @@ int tune_p3() {
   return v;
 }
 
-template <int KTOT, int NOUT, bool POOL, bool BWD, bool HS = false, bool PLAIN = false>
+template <int KTOT, int NOUT, bool POOL, bool BWD, bool HS = false, bool PLAIN = false, int WMAX = 40>
 int launch_p3(P3Args a, const char* tag, cudaStream_t stream) {
-  using Cfg = P3Cfg<KTOT, NOUT, POOL, BWD, HS, PLAIN>;
+  using Cfg = P3Cfg<KTOT, NOUT, POOL, BWD, HS, PLAIN, WMAX>;
   const int Wp = a.W + 2;
   const int Heff = (!BWD && POOL) ? 2 * a.Ho : a.H;
   const bool even = !BWD && POOL;
   constexpr int NM3 = Cfg::NM3;
   int Rmax = (NM3 * 128) / Wp;
   if (even) Rmax &= ~1;
-  ADVB_CHECK(Rmax >= (even ? 2 : 1) && Wp <= 42, "persistent 3x3 conv: image too wide for the tile");
+  ADVB_CHECK(Rmax >= (even ? 2 : 1) && Wp <= WMAX + 2, "persistent 3x3 conv: image too wide for the tile");
   int tiles = cdiv(Heff, Rmax);
   int R = cdiv(Heff, tiles);
   if (even && (R & 1)) ++R;
@@ -628,7 +633,7 @@ int launch_p3(P3Args a, const char* tag, cudaStream_t stream) {
   a.dW = make_fastdiv(a.W);
   a.dWo = make_fastdiv(a.Wo);
   ADVB_CHECK(cdiv(R * Wp, 128) * 128 + 2 * (Wp + 1) <= Cfg::BR, "persistent 3x3 conv: band exceeds its buffer");
-  auto kern = conv_p3_kernel<KTOT, NOUT, POOL, BWD, HS, PLAIN>;
+  auto kern = conv_p3_kernel<KTOT, NOUT, POOL, BWD, HS, PLAIN, WMAX>;
   ADVB_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::SMEM));
   int n_sm = 148, dev = 0;
   cudaGetDevice(&dev);
@@ -752,13 +757,15 @@ int conv_p3_forward(const ConvFwdArgs& f, const unsigned char* wpack, int passes
 int conv_p3_plain_forward(const float* in, float* out, int out_pad, const unsigned char* wpack, const float* bias,
                           const float* mul_h, const float* mul_scale, float mul_slope, int B, int H, int W, int C, int passes,
                           const char* tag, cudaStream_t stream) {
-  ADVB_CHECK(C == 64 && W <= 40, "plain persistent 3x3 conv: 64 -> 64 channels, width <= 40");
+  ADVB_CHECK((C == 64 && W <= 40) || (C == 24 && W <= 80), "plain persistent 3x3 conv: 64 channels at width <= 40 or 24 at width <= 80");
   P3Args a{};
   a.B = B, a.H = H, a.W = W, a.Ho = H, a.Wo = W;
   a.wpack = wpack;
   a.in = in, a.out = out, a.out_pad = out_pad, a.bias = bias;
   a.mul_h = mul_h, a.mul_scale = mul_scale, a.mul_slope = mul_slope;
   a.passes = passes;
+  a.out_ch = C;
+  if (C == 24) return launch_p3<24, 32, false, false, false, true, 80>(a, tag, stream);  // K = 24 (3 k-steps), N = 24 padded to 32
   return launch_p3<64, 64, false, false, false, true>(a, tag, stream);
 }
 

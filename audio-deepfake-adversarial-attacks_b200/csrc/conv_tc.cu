@@ -573,6 +573,22 @@ int conv_tc_pack(const float* w, unsigned char* wf, unsigned char* wd, int Cout,
   return 0;
 }
 
+size_t conv_tc_pack_bytes_padded(int Cout, int Cin, int KS, bool bwd, int npad) {
+  const int KTOT = bwd ? Cout : Cin;
+  return (size_t)((KTOT + 31) / 32) * KS * KS * 2 * npad * 128;
+}
+
+int conv_tc_pack_padded(const float* w, unsigned char* wf, unsigned char* wd, int Cout, int Cin, int KS, int npad, cudaStream_t stream) {
+  ADVB_CHECK(npad >= Cout && npad >= Cin && npad % 16 == 0, "padded pack: npad must cover both channel counts");
+  const int nf = ((Cin + 31) / 32) * KS * KS * npad * 32;
+  pack_tc_kernel<<<cdiv(nf, 256), 256, 0, stream>>>(w, wf, Cout, Cin, KS, 0, npad);
+  ADVB_KERNEL_OK("pack_tc_fwd", stream);
+  const int nb = ((Cout + 31) / 32) * KS * KS * npad * 32;
+  pack_tc_kernel<<<cdiv(nb, 256), 256, 0, stream>>>(w, wd, Cout, Cin, KS, 1, npad);
+  ADVB_KERNEL_OK("pack_tc_bwd", stream);
+  return 0;
+}
+
 bool conv_tc_supported(int Cin, int Cout, int KS, bool pool) {
   if (KS == 5 && pool) return Cin == 1 && Cout == 64;  // forward only (im2col); its backward is conv0_backward
   if (KS == 1 && !pool) return (Cin == 32 && Cout == 64) || (Cin == 48 && Cout == 96) || (Cin == 64 && Cout == 128);

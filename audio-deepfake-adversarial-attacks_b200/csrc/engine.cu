@@ -573,10 +573,11 @@ int build_specrnet(advb_handle* h) {
     ADVB_TRY(h->alloc(&k.g_xn, B * k.Hn * k.Wn * C));
     ADVB_TRY(h->alloc(&k.gadd, B * C));
     ADVB_TRY(h->alloc(&k.g_c1, B * H * W * C));
-    if (k.Cout == 64 && k.C == 64 && W <= 40) {  // conv2 (64 -> 64) on the persistent tcgen05 kernel (conv_path = 0)
+    if ((k.C == 64 && W <= 40) || (k.C == 24 && W <= 80)) {  // conv2 on the persistent tcgen05 kernel (conv_path = 0)
       ADVB_TRY(h->alloc(&k.w2t, 9 * C * C));
-      ADVB_TRY(h->alloc(&k.tcf2, conv_tc_pack_bytes(64, 64, 3, false)));
-      ADVB_TRY(h->alloc(&k.tcd2, conv_tc_pack_bytes(64, 64, 3, true)));
+      const int npad = k.C == 64 ? 64 : 32;
+      ADVB_TRY(h->alloc(&k.tcf2, conv_tc_pack_bytes_padded(k.Cout, k.Cout, 3, false, npad)));
+      ADVB_TRY(h->alloc(&k.tcd2, conv_tc_pack_bytes_padded(k.Cout, k.Cout, 3, true, npad)));
       ADVB_TRY(h->alloc(&k.c2, B * H * W * C));
       ADVB_TRY(h->alloc(&k.go, B * (H + 2) * (W + 2) * C));
     }

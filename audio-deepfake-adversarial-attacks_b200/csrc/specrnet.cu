@@ -815,7 +815,8 @@ int sr_pack_block(SrBlock& k, cudaStream_t stream) {
   if (k.tcf2 != nullptr) {
     sr_tap_transpose_kernel<<<cdiv(k.Cout * k.Cout * 9, 256), 256, 0, stream>>>(k.w2, k.w2t, k.Cout * k.Cout * 9);
     ADVB_KERNEL_OK("sr_pack", stream);
-    ADVB_TRY(conv_tc_pack(k.w2t, k.tcf2, k.tcd2, k.Cout, k.Cout, 3, stream));
+    if (k.C == 64) ADVB_TRY(conv_tc_pack(k.w2t, k.tcf2, k.tcd2, k.Cout, k.Cout, 3, stream));
+    else ADVB_TRY(conv_tc_pack_padded(k.w2t, k.tcf2, k.tcd2, k.Cout, k.Cout, 3, 32, stream));  // 20 x 20 -> K = 24, N = 32 (zero rows / columns)
   }
   sr_pack_vec_kernel<<<1, 64, 0, stream>>>(k.b1, k.b2, k.downsample ? k.bds : nullptr, k.bn_w, k.bn_b, k.bn_rm, k.bn_rv,
                                           k.b1p, k.b2p, k.bdp, k.bn_scale, k.bn_shift, k.Cout, k.C);

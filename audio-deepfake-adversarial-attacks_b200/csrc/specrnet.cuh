@@ -34,7 +34,7 @@ struct SrBlock {
   float* g_xn;            // (B, Hn, Wn, C)
   float* gadd;            // (B, C) broadcast term of the attention backward
   float* g_c1;            // (B, H, W, C) gradient at conv1's output (pre-BN)
-  // conv2 on the tensor cores (round 2; blocks with 64 -> 64 channels and W <= 40, engine option conv_path = 0): the persistent
+  // conv2 on the tensor cores (round 2; 64 -> 64 channels at W <= 40 and 20 -> 20 (padded 24) at W <= 80, engine option conv_path = 0): the persistent
   // tcgen05 kernel of conv_p3.cu computes the plain convolution / its transpose, the fused SIMT kernel keeps only its epilogue
   bool tc2 = false;
   float* w2t = nullptr;            // conv2 weights with the 3x3 taps transposed (the engine's image is the reference's transposed)
