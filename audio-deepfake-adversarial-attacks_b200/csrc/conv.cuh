@@ -52,8 +52,9 @@ bool conv_tc_supported(int Cin, int Cout, int KS, bool pool);
 size_t conv_tc_pack_bytes(int Cout, int Cin, int KS, bool bwd);
 // wf / wd: packed forward / backward weight slices (wd may be null)
 int conv_tc_pack(const float* w, unsigned char* wf, unsigned char* wd, int Cout, int Cin, int KS, cudaStream_t stream);
-// same images with N padded to `npad` rows (zero rows): (Cout, Cin) = (24, 24) -> MMA N = 32
-int conv_tc_pack_padded(const float* w, unsigned char* wf, unsigned char* wd, int Cout, int Cin, int KS, int npad, cudaStream_t stream);
+// same images with N padded to npad_f / npad_b rows (zero rows), e.g. (Cout, Cin) = (20, 20) -> MMA N = 32 both ways
+int conv_tc_pack_padded(const float* w, unsigned char* wf, unsigned char* wd, int Cout, int Cin, int KS, int npad_f, int npad_b,
+                        cudaStream_t stream);
 size_t conv_tc_pack_bytes_padded(int Cout, int Cin, int KS, bool bwd, int npad);
 // passes: 3 = 3xTF32 (fp32-class accuracy, default), 1 = single-pass tf32
 int conv_tc_forward(const ConvFwdArgs& a, const unsigned char* wpack, int passes, cudaStream_t stream);
@@ -79,13 +80,28 @@ int conv0t_forward(const ConvFwdArgs& a, const unsigned char* wpack, int passes,
 bool conv_p3_supported(int Cin, int Cout, int KS, bool pool, int W);
 int conv_p3_forward(const ConvFwdArgs& a, const unsigned char* wpack, int passes, cudaStream_t stream);
 int conv_p3_backward(const ConvBwdArgs& a, const unsigned char* wpack, int passes, cudaStream_t stream);
-// Plain 3x3 convolution (pad 1, stride 1; C = 64 channels at W <= 40, or C = 24 at W <= 80 with N padded to 32 inside) on the same
-// persistent tcgen05 kernel: in (B, H+2, W+2, 64) with a
-// zero border, wpack = a forward image of conv_tc_pack; out (B, H+2p, W+2p, 64) = (acc + bias) [* (mul_h > 0 ? 1 : slope) * mul_scale[c]]
-// with mul_h in the layout of `in`.  Fed with the backward image of conv_tc_pack it is the transposed convolution.
-int conv_p3_plain_forward(const float* in, float* out, int out_pad, const unsigned char* wpack, const float* bias,
-                          const float* mul_h, const float* mul_scale, float mul_slope, int B, int H, int W, int C, int passes,
-                          const char* tag, cudaStream_t stream);
+// Plain 3x3 convolution (pad 1, stride 1) on the same persistent tcgen05 kernel (conv_p3.cu, PLAIN variant), 3xTF32.
+//   in  (B, H+2, W+2, Cin) with a zero border;  wpack = a forward image of conv_tc_pack(_padded) - or its backward image, which
+//   makes this the transposed convolution;  out (B, H+2p, W+2p, Cout), interior only:
+//   v = acc + bias;  [v = lrelu(v * aff_scale[c] + aff_shift[c], act_slope)];  [v = v * (mul_h > 0 ? 1 : mul_slope) * mul_scale[c]]
+//   with mul_h a (B, H+2, W+2, Cout) bordered tensor.  Shapes: see conv_p3_plain_supported.
+struct P3Plain {
+  const float* in = nullptr;
+  float* out = nullptr;
+  int out_pad = 0;
+  const unsigned char* wpack = nullptr;
+  const float* bias = nullptr;
+  const float* aff_scale = nullptr;
+  const float* aff_shift = nullptr;
+  float act_slope = 1.f;
+  const float* mul_h = nullptr;
+  const float* mul_scale = nullptr;
+  float mul_slope = 1.f;
+  int B = 0, H = 0, W = 0, Cin = 0, Cout = 0, passes = 3;
+  const char* tag = "conv_p3_plain";
+};
+int conv_p3_plain_forward(const P3Plain& p, cudaStream_t stream);
+bool conv_p3_plain_supported(int Cin, int Cout, int W);
 // mixed mode (passes = 2, forward only): tf32 main term + both cross terms as ONE bf16 MMA; its own weight image (same bytes)
 int conv_p3_pack_mix(const float* w, unsigned char* wf, int Cout, int Cin, cudaStream_t stream);
 // "horizontal scatter" backward (N = 3 C_in): needs its own weight image in the layer's backward pack buffer

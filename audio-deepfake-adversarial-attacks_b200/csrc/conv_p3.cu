@@ -56,6 +56,9 @@ struct P3Args {
   const float* mul_scale;  // PLAIN: per-channel factor applied together with mul_h
   float mul_slope;
   int out_ch;              // PLAIN: channels stored per pixel (= the channel stride of out and mul_h); 0 = NOUT
+  const float* aff_scale;  // PLAIN: optional per-channel affine (BatchNorm eval) ...
+  const float* aff_shift;
+  float act_slope;         // ... followed by LeakyReLU(act_slope), applied when aff_scale != nullptr
   FastDiv dTiles, dWp, dW, dWo;
   long long* prof;  // optional (ADVB_P3_PROF=1): per-phase cycle counts of CTA 0 (worker thread 0, MMA warp leader)
 };
@@ -485,6 +488,15 @@ __global__ void __launch_bounds__(P3Cfg<KTOT, NOUT, POOL, BWD, HS, PLAIN, WMAX>:
           const int och = a.out_ch > 0 ? a.out_ch : NOUT;  // NOUT may be padded beyond the stored channels (24 -> 32)
           if (c >= och) continue;
           float4 v = *reinterpret_cast<const float4*>(stage + (size_t)(yl * Wp + x + 1) * SS + c);
+          if (a.aff_scale != nullptr) {  // BatchNorm(eval) + LeakyReLU of the reference's conv1 -> bn2 -> lrelu
+            const float4 sc4 = __ldg(reinterpret_cast<const float4*>(a.aff_scale + c));
+            const float4 sh4 = __ldg(reinterpret_cast<const float4*>(a.aff_shift + c));
+            v.x = fmaf(v.x, sc4.x, sh4.x), v.y = fmaf(v.y, sc4.y, sh4.y), v.z = fmaf(v.z, sc4.z, sh4.z), v.w = fmaf(v.w, sc4.w, sh4.w);
+            v.x = v.x > 0.f ? v.x : a.act_slope * v.x;
+            v.y = v.y > 0.f ? v.y : a.act_slope * v.y;
+            v.z = v.z > 0.f ? v.z : a.act_slope * v.z;
+            v.w = v.w > 0.f ? v.w : a.act_slope * v.w;
+          }
           if (a.mul_h != nullptr) {  // * LeakyReLU'(h) * per-channel scale: the transposed convolution's chain-rule factor
             const float4 hv = __ldg(reinterpret_cast<const float4*>(a.mul_h + (((size_t)b * Hp + oy + 1) * Wp + x + 1) * och + c));
             const float4 sv = __ldg(reinterpret_cast<const float4*>(a.mul_scale + c));
@@ -754,19 +766,27 @@ int conv_p3_forward(const ConvFwdArgs& f, const unsigned char* wpack, int passes
   return 1;
 }
 
-int conv_p3_plain_forward(const float* in, float* out, int out_pad, const unsigned char* wpack, const float* bias,
-                          const float* mul_h, const float* mul_scale, float mul_slope, int B, int H, int W, int C, int passes,
-                          const char* tag, cudaStream_t stream) {
-  ADVB_CHECK((C == 64 && W <= 40) || (C == 24 && W <= 80), "plain persistent 3x3 conv: 64 channels at width <= 40 or 24 at width <= 80");
+int conv_p3_plain_forward(const P3Plain& p, cudaStream_t stream) {
   P3Args a{};
-  a.B = B, a.H = H, a.W = W, a.Ho = H, a.Wo = W;
-  a.wpack = wpack;
-  a.in = in, a.out = out, a.out_pad = out_pad, a.bias = bias;
-  a.mul_h = mul_h, a.mul_scale = mul_scale, a.mul_slope = mul_slope;
-  a.passes = passes;
-  a.out_ch = C;
-  if (C == 24) return launch_p3<24, 32, false, false, false, true, 80>(a, tag, stream);  // K = 24 (3 k-steps), N = 24 padded to 32
-  return launch_p3<64, 64, false, false, false, true>(a, tag, stream);
+  a.B = p.B, a.H = p.H, a.W = p.W, a.Ho = p.H, a.Wo = p.W;
+  a.wpack = p.wpack;
+  a.in = p.in, a.out = p.out, a.out_pad = p.out_pad, a.bias = p.bias;
+  a.mul_h = p.mul_h, a.mul_scale = p.mul_scale, a.mul_slope = p.mul_slope;
+  a.aff_scale = p.aff_scale, a.aff_shift = p.aff_shift, a.act_slope = p.act_slope;
+  a.passes = p.passes;
+  a.out_ch = p.Cout;
+  // (channels in, channels out) as stored: K / N are padded to the next multiple of 8 / to 32 or 64 inside the kernel
+  if (p.Cin == 64 && p.Cout == 64 && p.W <= 40) return launch_p3<64, 64, false, false, false, true>(a, p.tag, stream);
+  if (p.Cin == 24 && p.Cout == 24 && p.W <= 80) return launch_p3<24, 32, false, false, false, true, 80>(a, p.tag, stream);
+  if (p.Cin == 64 && p.Cout == 24 && p.W <= 40) return launch_p3<64, 32, false, false, false, true>(a, p.tag, stream);
+  if (p.Cin == 24 && p.Cout == 64 && p.W <= 40) return launch_p3<24, 64, false, false, false, true>(a, p.tag, stream);
+  set_error("plain persistent 3x3 conv: no instantiation for this shape");
+  return 1;
+}
+
+bool conv_p3_plain_supported(int Cin, int Cout, int W) {
+  return (Cin == 64 && Cout == 64 && W <= 40) || (Cin == 24 && Cout == 24 && W <= 80) || (Cin == 64 && Cout == 24 && W <= 40) ||
+         (Cin == 24 && Cout == 64 && W <= 40);
 }
 
 int conv_p3_backward(const ConvBwdArgs& g, const unsigned char* wpack, int passes, cudaStream_t stream) {

@@ -578,13 +578,14 @@ size_t conv_tc_pack_bytes_padded(int Cout, int Cin, int KS, bool bwd, int npad) 
   return (size_t)((KTOT + 31) / 32) * KS * KS * 2 * npad * 128;
 }
 
-int conv_tc_pack_padded(const float* w, unsigned char* wf, unsigned char* wd, int Cout, int Cin, int KS, int npad, cudaStream_t stream) {
-  ADVB_CHECK(npad >= Cout && npad >= Cin && npad % 16 == 0, "padded pack: npad must cover both channel counts");
-  const int nf = ((Cin + 31) / 32) * KS * KS * npad * 32;
-  pack_tc_kernel<<<cdiv(nf, 256), 256, 0, stream>>>(w, wf, Cout, Cin, KS, 0, npad);
+int conv_tc_pack_padded(const float* w, unsigned char* wf, unsigned char* wd, int Cout, int Cin, int KS, int npad_f, int npad_b,
+                        cudaStream_t stream) {
+  ADVB_CHECK(npad_f >= Cout && npad_b >= Cin && npad_f % 16 == 0 && npad_b % 16 == 0, "padded pack: the padded N must cover the channels");
+  const int nf = ((Cin + 31) / 32) * KS * KS * npad_f * 32;
+  pack_tc_kernel<<<cdiv(nf, 256), 256, 0, stream>>>(w, wf, Cout, Cin, KS, 0, npad_f);
   ADVB_KERNEL_OK("pack_tc_fwd", stream);
-  const int nb = ((Cout + 31) / 32) * KS * KS * npad * 32;
-  pack_tc_kernel<<<cdiv(nb, 256), 256, 0, stream>>>(w, wd, Cout, Cin, KS, 1, npad);
+  const int nb = ((Cout + 31) / 32) * KS * KS * npad_b * 32;
+  pack_tc_kernel<<<cdiv(nb, 256), 256, 0, stream>>>(w, wd, Cout, Cin, KS, 1, npad_b);
   ADVB_KERNEL_OK("pack_tc_bwd", stream);
   return 0;
 }

@@ -580,6 +580,12 @@ int build_specrnet(advb_handle* h) {
       ADVB_TRY(h->alloc(&k.tcd2, conv_tc_pack_bytes_padded(k.Cout, k.Cout, 3, true, npad)));
       ADVB_TRY(h->alloc(&k.c2, B * H * W * C));
       ADVB_TRY(h->alloc(&k.go, B * (H + 2) * (W + 2) * C));
+      if (i > 0 && conv_p3_plain_supported(k.Ci, k.C, W) && conv_p3_plain_supported(k.C, k.Ci, W)) {  // conv1 and its transpose too
+        ADVB_TRY(h->alloc(&k.w1t, 9 * (size_t)k.Cout * k.Cin));
+        ADVB_TRY(h->alloc(&k.tcf1, conv_tc_pack_bytes_padded(k.Cout, k.Cin, 3, false, k.C == 64 ? 64 : 32)));
+        ADVB_TRY(h->alloc(&k.tcd1, conv_tc_pack_bytes_padded(k.Cout, k.Cin, 3, true, k.Ci == 64 ? 64 : 32)));
+        ADVB_TRY(h->alloc(&k.g_c1b, B * (H + 2) * (W + 2) * C));
+      }
     }
     H = k.Hn, W = k.Wn;
   }
@@ -608,6 +614,7 @@ int prepare_specrnet(advb_handle* h, cudaStream_t st) {
                             h->t("first_bn.running_var"), h->sr_bn4, st));
   for (int i = 0; i < 3; ++i) {
     h->sr[i].tc2 = h->sr[i].tcf2 != nullptr && h->conv_path == 0 && h->sr_tc != 0;
+    h->sr[i].tc1 = h->sr[i].tc2 && h->sr[i].tcf1 != nullptr;
     ADVB_TRY(sr_pack_block(h->sr[i], st));
   }
   ADVB_TRY(sr_pack_gru(h->gru, st));

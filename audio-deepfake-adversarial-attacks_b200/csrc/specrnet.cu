@@ -483,6 +483,37 @@ __global__ void sr_expand_go_kernel(SrArgs a, float* __restrict__ go, int64_t n4
   }
 }
 
+// Shortcut term of a block's input gradient, added to the transposed conv1's output: g_x += downsample^T(g_o) (wd: [C][Ci]) or
+// g_x += g_o (identity shortcut, Ci == C).  go (B, H+2, W+2, C) bordered, g_x (B, H, W, Ci).
+__global__ void sr_shortcut_bwd_kernel(const float* __restrict__ go, const float* __restrict__ wd, float* __restrict__ g_x, int H,
+                                       int W, int C, int Ci, int64_t n4) {
+  const int C4 = Ci >> 2;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n4; i += (int64_t)gridDim.x * blockDim.x) {
+    const int c = 4 * (int)(i % C4);
+    int64_t r = i / C4;
+    const int x = (int)(r % W);
+    r /= W;
+    const int y = (int)(r % H), b = (int)(r / H);
+    const float* gp = go + (((size_t)b * (H + 2) + y + 1) * (W + 2) + x + 1) * C;
+    float4 acc = reinterpret_cast<float4*>(g_x)[i];
+    if (wd != nullptr) {
+      for (int co = 0; co < C; co += 4) {
+        const float4 g = __ldg(reinterpret_cast<const float4*>(gp + co));
+        const float gv[4] = {g.x, g.y, g.z, g.w};
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const float4 w = __ldg(reinterpret_cast<const float4*>(wd + (size_t)(co + u) * Ci + c));
+          acc.x = fmaf(gv[u], w.x, acc.x), acc.y = fmaf(gv[u], w.y, acc.y), acc.z = fmaf(gv[u], w.z, acc.z), acc.w = fmaf(gv[u], w.w, acc.w);
+        }
+      }
+    } else {
+      const float4 g = __ldg(reinterpret_cast<const float4*>(gp + c));
+      acc.x += g.x, acc.y += g.y, acc.z += g.z, acc.w += g.w;
+    }
+    reinterpret_cast<float4*>(g_x)[i] = acc;
+  }
+}
+
 // wt[co][ci][a][b] = w[co][ci][b][a]: the engine's image is the transpose of the reference's (frames x coeffs)
 __global__ void sr_tap_transpose_kernel(const float* __restrict__ w, float* __restrict__ wt, int n) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -812,11 +843,16 @@ int sr_pack_block(SrBlock& k, cudaStream_t stream) {
       ADVB_KERNEL_OK("sr_pack", stream);
     }
   }
+  if (k.tcf1 != nullptr) {
+    sr_tap_transpose_kernel<<<cdiv(k.Cout * k.Cin * 9, 256), 256, 0, stream>>>(k.w1, k.w1t, k.Cout * k.Cin * 9);
+    ADVB_KERNEL_OK("sr_pack", stream);
+    ADVB_TRY(conv_tc_pack_padded(k.w1t, k.tcf1, k.tcd1, k.Cout, k.Cin, 3, k.C == 64 ? 64 : 32, k.Ci == 64 ? 64 : 32, stream));
+  }
   if (k.tcf2 != nullptr) {
     sr_tap_transpose_kernel<<<cdiv(k.Cout * k.Cout * 9, 256), 256, 0, stream>>>(k.w2, k.w2t, k.Cout * k.Cout * 9);
     ADVB_KERNEL_OK("sr_pack", stream);
     if (k.C == 64) ADVB_TRY(conv_tc_pack(k.w2t, k.tcf2, k.tcd2, k.Cout, k.Cout, 3, stream));
-    else ADVB_TRY(conv_tc_pack_padded(k.w2t, k.tcf2, k.tcd2, k.Cout, k.Cout, 3, 32, stream));  // 20 x 20 -> K = 24, N = 32 (zero rows / columns)
+    else ADVB_TRY(conv_tc_pack_padded(k.w2t, k.tcf2, k.tcd2, k.Cout, k.Cout, 3, 32, 32, stream));  // 20 x 20 -> K = 24, N = 32 (zero rows / columns)
   }
   sr_pack_vec_kernel<<<1, 64, 0, stream>>>(k.b1, k.b2, k.downsample ? k.bds : nullptr, k.bn_w, k.bn_b, k.bn_rm, k.bn_rv,
                                           k.b1p, k.b2p, k.bdp, k.bn_scale, k.bn_shift, k.Cout, k.C);
@@ -839,12 +875,12 @@ int sr_input_forward(float* img, const float* bn4, int B, int H, int W, cudaStre
 
 // profiler labels must outlive the call (prof_mark keeps the pointer): string literals per block
 struct SrTags {
-  const char *conv1, *conv2, *conv2_bwd, *conv1_bwd, *conv2_tc, *expand_go;
+  const char *conv1, *conv2, *conv2_bwd, *conv1_bwd, *conv2_tc, *expand_go, *shortcut_bwd;
 };
 const SrTags& sr_tags(const char* tag) {
-  static const SrTags t0{"sr_b0_conv1", "sr_b0_conv2", "sr_b0_conv2_bwd", "sr_b0_conv1_bwd", "sr_b0_conv2_tc", "sr_b0_expand_go"};
-  static const SrTags t2{"sr_b2_conv1", "sr_b2_conv2", "sr_b2_conv2_bwd", "sr_b2_conv1_bwd", "sr_b2_conv2_tc", "sr_b2_expand_go"};
-  static const SrTags t4{"sr_b4_conv1", "sr_b4_conv2", "sr_b4_conv2_bwd", "sr_b4_conv1_bwd", "sr_b4_conv2_tc", "sr_b4_expand_go"};
+  static const SrTags t0{"sr_b0_conv1", "sr_b0_conv2", "sr_b0_conv2_bwd", "sr_b0_conv1_bwd", "sr_b0_conv2_tc", "sr_b0_expand_go", "sr_b0_shortcut_bwd"};
+  static const SrTags t2{"sr_b2_conv1", "sr_b2_conv2", "sr_b2_conv2_bwd", "sr_b2_conv1_bwd", "sr_b2_conv2_tc", "sr_b2_expand_go", "sr_b2_shortcut_bwd"};
+  static const SrTags t4{"sr_b4_conv1", "sr_b4_conv2", "sr_b4_conv2_bwd", "sr_b4_conv1_bwd", "sr_b4_conv2_tc", "sr_b4_expand_go", "sr_b4_shortcut_bwd"};
   return tag[4] == '0' ? t0 : (tag[4] == '2' ? t2 : t4);
 }
 
@@ -854,11 +890,22 @@ int sr_block_forward(const SrBlock& k, const float* x, int B, const char* tag, c
   // CKr: the padded channels (20 -> 24) carry zero weights; the contraction skips them (bit-identical up to the sign of zero)
   a.CK = k.Ci, a.N = k.C, a.CKr = k.Ci % 4 == 0 ? std::min(k.Ci, (k.Cin + 3) / 4 * 4) : k.Ci;
   a.in = x, a.wpk = k.w1f, a.bias = k.b1p, a.out = k.h;
-  ADVB_TRY(launch_conv<F1>(a, false, t.conv1, stream));
+  if (k.tc1) {  // conv1 -> bn2 -> LeakyReLU on the tensor cores (affine + activation in the epilogue)
+    P3Plain p;
+    p.in = x, p.out = k.h, p.out_pad = 1, p.wpack = k.tcf1, p.bias = k.b1p;
+    p.aff_scale = k.bn_scale, p.aff_shift = k.bn_shift, p.act_slope = 0.3f;
+    p.B = B, p.H = k.H, p.W = k.W, p.Cin = k.Ci, p.Cout = k.C, p.tag = t.conv1;
+    ADVB_TRY(conv_p3_plain_forward(p, stream));
+  } else {
+    ADVB_TRY(launch_conv<F1>(a, false, t.conv1, stream));
+  }
   a.CK = k.C, a.CKr = std::min(k.C, (k.Cout + 3) / 4 * 4), a.in = k.h, a.wpk = k.w2f, a.bias = k.b2p, a.out = k.xb;
   a.x = x, a.Ci = k.Ci, a.wd = k.downsample ? k.wdf : nullptr, a.bd = k.bdp, a.code1w = k.code1, a.psum = k.psum;
   if (k.tc2) {  // conv2(h) on the tensor cores; the fused kernel below keeps bias + identity + max-pool + arg-max + channel sums
-    ADVB_TRY(conv_p3_plain_forward(k.h, k.c2, 0, k.tcf2, nullptr, nullptr, nullptr, 0.f, B, k.H, k.W, k.C, 3, t.conv2_tc, stream));
+    P3Plain p;
+    p.in = k.h, p.out = k.c2, p.out_pad = 0, p.wpack = k.tcf2;
+    p.B = B, p.H = k.H, p.W = k.W, p.Cin = k.C, p.Cout = k.C, p.tag = t.conv2_tc;
+    ADVB_TRY(conv_p3_plain_forward(p, stream));
     a.c2 = k.c2;
   }
   ADVB_TRY(launch_conv<F2>(a, true, t.conv2, stream));
@@ -885,7 +932,11 @@ int sr_block_backward(const SrBlock& k, const float* x, float* g_x, int B, bool 
     const int64_t n4 = (int64_t)B * (k.H + 2) * (k.W + 2) * (k.C / 4);
     sr_expand_go_kernel<<<ew_blocks(n4), 256, 0, stream>>>(a, k.go, n4);
     ADVB_KERNEL_OK(t.expand_go, stream);
-    ADVB_TRY(conv_p3_plain_forward(k.go, k.g_c1, 0, k.tcd2, nullptr, k.h, k.bn_scale, 0.3f, B, k.H, k.W, k.C, 3, t.conv2_bwd, stream));
+    P3Plain p;
+    p.in = k.go, p.wpack = k.tcd2, p.mul_h = k.h, p.mul_scale = k.bn_scale, p.mul_slope = 0.3f;
+    p.out = k.tc1 ? k.g_c1b : k.g_c1, p.out_pad = k.tc1 ? 1 : 0;  // bordered when the transposed conv1 below is on this kernel too
+    p.B = B, p.H = k.H, p.W = k.W, p.Cin = k.C, p.Cout = k.C, p.tag = t.conv2_bwd;
+    ADVB_TRY(conv_p3_plain_forward(p, stream));
   } else {
     ADVB_TRY(launch_conv<B2>(a, false, t.conv2_bwd, stream));
   }
@@ -897,6 +948,16 @@ int sr_block_backward(const SrBlock& k, const float* x, float* g_x, int B, bool 
     return 0;
   }
   a.CK = k.C, a.CKr = std::min(k.C, (k.Cout + 3) / 4 * 4), a.N = k.Ci, a.wpk = k.w1d, a.out = g_x, a.wd = k.downsample ? k.wdd : nullptr;
+  if (k.tc1) {  // g_x = conv1^T(g_c1) on the tensor cores, then + downsample^T(g_o) | + g_o from the materialised go
+    P3Plain p;
+    p.in = k.g_c1b, p.out = g_x, p.out_pad = 0, p.wpack = k.tcd1;
+    p.B = B, p.H = k.H, p.W = k.W, p.Cin = k.C, p.Cout = k.Ci, p.tag = t.conv1_bwd;
+    ADVB_TRY(conv_p3_plain_forward(p, stream));
+    const int64_t n4 = (int64_t)B * k.H * k.W * (k.Ci / 4);
+    sr_shortcut_bwd_kernel<<<ew_blocks(n4), 256, 0, stream>>>(k.go, k.downsample ? k.wdd : nullptr, g_x, k.H, k.W, k.C, k.Ci, n4);
+    ADVB_KERNEL_OK(t.shortcut_bwd, stream);
+    return 0;
+  }
   ADVB_TRY(launch_conv<B1>(a, false, t.conv1_bwd, stream));
   return 0;
 }

@@ -42,6 +42,13 @@ struct SrBlock {
   unsigned char* tcd2 = nullptr;   // ... and flipped / channel-transposed (the transposed convolution as a forward one)
   float* c2 = nullptr;             // (B, H, W, C) conv2(h) without bias
   float* go = nullptr;             // (B, H+2, W+2, C) gradient at conv2's output, zero border
+  // conv1 of the blocks after the first one (24 -> 64 and 64 -> 64) and its transpose, same kernel (needs tc2: the shortcut term of
+  // the backward reads the materialised go)
+  bool tc1 = false;
+  float* w1t = nullptr;
+  unsigned char* tcf1 = nullptr;
+  unsigned char* tcd1 = nullptr;
+  float* g_c1b = nullptr;          // (B, H+2, W+2, C) gradient at conv1's output with a zero border (the transposed conv's input)
 };
 
 struct SrGru {

@@ -121,9 +121,12 @@ def test_attack_matches_reference_at_benchmarked_config(name, cuda_device, recor
         assert s1 / n < 1e-3, (s1, n)
     elif case["attack"] == "fgsm":
         assert sign_mismatch / n < 1e-3, row
-    # (band, bound on the adversarial-logit difference): measured native-vs-reference differences are 1.7e-4 (LCNN), 1.1e-3
-    # (SpecRNet+MFCC, batch-coupled dB floor) and 1.9e-3 (RawNet3, ill-conditioned log|sinc| gradient)
-    band, dmax = {"lcnn": (0.0, 5e-4), "specrnet": (2.5e-3, 2.5e-3), "rawnet3": (2.2e-3, 3e-3)}[case["model"]]
+    # (band, bound on the adversarial-logit difference): measured native-vs-reference differences are 1.7e-4 (LCNN), 1.1e-3 - 3.1e-3
+    # (SpecRNet+MFCC, batch-coupled dB floor; fp32 SIMT convolutions / 3xTF32 tensor-core convolutions) and 1.9e-3 (RawNet3,
+    # ill-conditioned log|sinc| gradient).  SpecRNet's band is set from the reference's OWN noise: its 8-thread and
+    # 1-thread PGD-40 runs end 2.9e-3 apart in the adversarial logit on 8 clips (15.7 % of the samples differ; 9e-8 after one step:
+    # tools/pgd_divergence.py specrnet -> tests/golden/pgd_divergence_reference_specrnet.json): band = that, bound = twice that.
+    band, dmax = {"lcnn": (0.0, 5e-4), "specrnet": (3e-3, 6e-3), "rawnet3": (2.2e-3, 3e-3)}[case["model"]]
     decided = np.abs(gold["logits_adv"].ravel()) > band
     print("cfg parity: clips outside the +-%g logit band: %d of %d" % (band, int(decided.sum()), decided.size))
     assert decided.sum() >= 0.7 * decided.size

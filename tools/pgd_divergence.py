@@ -25,12 +25,20 @@ import numpy as np  # noqa: E402
 def main():
     ta = ref.torchattacks()
     B, T, eps = 8, 64000, 0.001
-    x, y = synth.clips(2, B, T)
-    _, state = cases.build_state("lcnn", "lfcc")
-    state[BIAS_KEY["lcnn"]] = torch.from_numpy(np.load(os.path.join(cases.GOLDEN_DIR, "cfg2_lcnn_pgd40_b128.npz"))["bias"])
-    model = ref.model("lcnn", "lfcc", state)
+    which = sys.argv[1] if len(sys.argv) > 1 else "lcnn"   # "lcnn" (cfg 2) or "specrnet" (cfg 3: SpecRNet + MFCC)
+    if which == "specrnet":
+        x, y = synth.clips(3, B, T)
+        _, state = cases.build_state("specrnet", "mfcc")
+        state[BIAS_KEY["specrnet"]] = torch.from_numpy(
+            np.load(os.path.join(cases.GOLDEN_DIR, "cfg3_specrnet_mfcc_pgd40_b32.npz"))["bias"])
+        model = ref.model("specrnet", "mfcc", state)
+    else:
+        x, y = synth.clips(2, B, T)
+        _, state = cases.build_state("lcnn", "lfcc")
+        state[BIAS_KEY["lcnn"]] = torch.from_numpy(np.load(os.path.join(cases.GOLDEN_DIR, "cfg2_lcnn_pgd40_b128.npz"))["bias"])
+        model = ref.model("lcnn", "lfcc", state)
     rows = []
-    for steps in (1, 5, 10, 20, 40):
+    for steps in ((1, 10, 40) if which == "specrnet" else (1, 5, 10, 20, 40)):
         outs = {}
         for threads in (8, 1):
             torch.set_num_threads(threads)
@@ -47,9 +55,10 @@ def main():
                "label_mismatch": int(((a[1] > 0) != (b[1] > 0)).sum()), "max_abs_dlogit": float((a[1] - b[1]).abs().max())}
         print(row, flush=True)
         rows.append(row)
-    out = {"what": "reference torchattacks.PGD on the reference LCNN (CPU), 8 threads vs 1 thread, same random start",
+    out = {"what": f"reference torchattacks.PGD on the reference {which} (CPU), 8 threads vs 1 thread, same random start",
            "eps": eps, "alpha": 2 / 255, "T": T, "rows": rows}
-    json.dump(out, open(os.path.join(cases.GOLDEN_DIR, "pgd_divergence_reference.json"), "w"), indent=1)
+    name = "pgd_divergence_reference.json" if which == "lcnn" else f"pgd_divergence_reference_{which}.json"
+    json.dump(out, open(os.path.join(cases.GOLDEN_DIR, name), "w"), indent=1)
 
 
 if __name__ == "__main__":
