@@ -366,6 +366,66 @@ __global__ void __launch_bounds__(256) sr_first_bwd_kernel(SrArgs a, const float
   g_feat[((size_t)b * a.H + y) * a.W + x] = acc * selu_grad_from_out(x0) * sc;
 }
 
+// Same operator, tiled (round 2; used when the expanded gradient `go` is materialised).  The kernel above reads every 24-channel
+// gradient pixel nine times (once per tap) through L1: 7 GB per launch at B = 256, which is what its 0.76 ms was.  Here a CTA
+// owns SR_FB_ROWS image rows: phase 1 reads each pixel of the rows + halo ONCE and forms its nine per-tap dot products
+// P[t] = sum_c g[c] w[t][c] in shared memory; phase 2 gathers out = sum_t P_t[neighbour t] (the col2im of conv0_bwd.cu) and adds the
+// 1x1 shortcut term from `go`.
+constexpr int SR_FB_ROWS = 8;
+__global__ void __launch_bounds__(256) sr_first_bwd_tiled_kernel(SrArgs a, const float* __restrict__ w1, const float* __restrict__ wds,
+                                                                  int Cout, const float* __restrict__ bn4, const float* __restrict__ go,
+                                                                  float* __restrict__ g_feat) {
+  extern __shared__ __align__(16) float sm[];
+  const int C = a.C, Wp = a.W + 2;
+  float* s_w = sm;                 // [9][C] flipped taps
+  float* s_d = s_w + 9 * C;        // [C]
+  float* s_p = s_d + C;            // [(SR_FB_ROWS + 2) * Wp][9]
+  for (int i = threadIdx.x; i < 9 * C; i += blockDim.x) {
+    const int co = i % C, tap = i / C;
+    const int r = tap / 3, c = tap % 3;
+    s_w[i] = co < Cout ? w1[co * 9 + (2 - c) * 3 + (2 - r)] : 0.f;
+  }
+  for (int i = threadIdx.x; i < C; i += blockDim.x) s_d[i] = i < Cout ? wds[i] : 0.f;
+  __syncthreads();
+  const int b = blockIdx.y, y0 = blockIdx.x * SR_FB_ROWS;
+  const int nslots = (SR_FB_ROWS + 2) * Wp;
+  for (int sl = threadIdx.x; sl < nslots; sl += blockDim.x) {
+    const int yy = y0 - 1 + sl / Wp, xx = sl % Wp - 1;
+    float p[9];
+#pragma unroll
+    for (int t = 0; t < 9; ++t) p[t] = 0.f;
+    if (yy >= 0 && yy < a.H && xx >= 0 && xx < a.W) {
+      const float* gp = a.in + (((size_t)b * a.H + yy) * a.W + xx) * C;
+      for (int c = 0; c < C; c += 4) {
+        const float4 gv = __ldg(reinterpret_cast<const float4*>(gp + c));
+#pragma unroll
+        for (int t = 0; t < 9; ++t) {
+          const float* wp = s_w + t * C + c;
+          p[t] = fmaf(gv.w, wp[3], fmaf(gv.z, wp[2], fmaf(gv.y, wp[1], fmaf(gv.x, wp[0], p[t]))));
+        }
+      }
+    }
+#pragma unroll
+    for (int t = 0; t < 9; ++t) s_p[sl * 9 + t] = p[t];
+  }
+  __syncthreads();
+  const float sc = __ldg(bn4 + 0) / sqrtf(__ldg(bn4 + 3) + 1e-5f);
+  for (int i = threadIdx.x; i < SR_FB_ROWS * a.W; i += blockDim.x) {
+    const int yl = i / a.W, x = i % a.W, y = y0 + yl;
+    if (y >= a.H) continue;
+    float acc = 0.f;
+#pragma unroll
+    for (int t = 0; t < 9; ++t) acc += s_p[((yl + t / 3) * Wp + x + t % 3) * 9 + t];
+    const float* gop = go + (((size_t)b * (a.H + 2) + y + 1) * Wp + x + 1) * C;
+    for (int c = 0; c < C; c += 4) {
+      const float4 g = __ldg(reinterpret_cast<const float4*>(gop + c));
+      acc = fmaf(g.w, s_d[c + 3], fmaf(g.z, s_d[c + 2], fmaf(g.y, s_d[c + 1], fmaf(g.x, s_d[c], acc))));
+    }
+    const float x0 = __ldg(a.x + ((size_t)b * (a.H + 2) + y + 1) * Wp + x + 1);
+    g_feat[((size_t)b * a.H + y) * a.W + x] = acc * selu_grad_from_out(x0) * sc;
+  }
+}
+
 __global__ void sr_input_kernel(float* __restrict__ img, const float* __restrict__ bn4, int H, int W, int64_t n) {
   const float sc = bn4[0] / sqrtf(bn4[3] + 1e-5f), sh = bn4[1] - bn4[2] * sc;
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
@@ -941,6 +1001,13 @@ int sr_block_backward(const SrBlock& k, const float* x, float* g_x, int B, bool 
     ADVB_TRY(launch_conv<B2>(a, false, t.conv2_bwd, stream));
   }
   a.in = k.g_c1, a.x = x;
+  if (first && k.tc2) {
+    dim3 grid(cdiv(k.H, SR_FB_ROWS), B);
+    const size_t smem = (size_t)(10 * k.C + (SR_FB_ROWS + 2) * (k.W + 2) * 9) * sizeof(float);
+    sr_first_bwd_tiled_kernel<<<grid, 256, smem, stream>>>(a, k.w1, k.wds, k.Cout, bn4, k.go, g_x);
+    ADVB_KERNEL_OK(t.conv1_bwd, stream);
+    return 0;
+  }
   if (first) {
     dim3 grid(cdiv(k.H * k.W, 256), B);
     sr_first_bwd_kernel<<<grid, 256, 0, stream>>>(a, k.w1, k.wds, k.Cout, bn4, g_x);
