@@ -109,7 +109,8 @@ __global__ void __launch_bounds__(256) sr_conv_kernel(SrArgs a, int band_floats)
   const int CKp = (CK & 3) == 0 ? CK + 4 : CK;
   float* band = smem;
   float* w_s = smem + band_floats;
-  float* s_part = w_s + (a.slab_all ? 9 : 1) * CK * a.N;  // F2 only: qpc x N partial sums
+  // F2 only: qpc x N partial sums (alone in shared memory when the contraction comes from the tensor-core kernel)
+  float* s_part = (MODE == F2 && a.c2 != nullptr) ? smem : w_s + (a.slab_all ? 9 : 1) * CK * a.N;
   const int b = blockIdx.y, tid = threadIdx.x, nt = blockDim.x;
 
   const bool from_c2 = MODE == F2 && a.c2 != nullptr;
@@ -366,6 +367,41 @@ __global__ void __launch_bounds__(256) sr_first_bwd_kernel(SrArgs a, const float
   g_feat[((size_t)b * a.H + y) * a.W + x] = acc * selu_grad_from_out(x0) * sc;
 }
 
+// First block, conv1 (1 -> C channels) + bn2 + LeakyReLU as its own kernel (round 2): thread = (pixel, 4 output channels), nine
+// scalar loads of the 1-channel image (L1) and 36 FMAs; the generic F1 path staged bands and weight slabs for a contraction of
+// length 9 and ran at a quarter of the HBM rate of its 812 MB output.
+__global__ void __launch_bounds__(256) sr_first_conv1_kernel(const float* __restrict__ img /*(B, H+2, W+2)*/,
+                                                              const float* __restrict__ wpk /*[tap][1][N]*/,
+                                                              const float* __restrict__ bias, const float* __restrict__ scale,
+                                                              const float* __restrict__ shift, float* __restrict__ h, int H, int W,
+                                                              int N, int64_t n4) {
+  const int C4 = N >> 2, Wp = W + 2;
+  // (32-bit index arithmetic: the 64-bit divisions of the first version were most of its instructions)
+  const unsigned total = (unsigned)n4, step = gridDim.x * blockDim.x;
+  for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += step) {
+    const int c = 4 * (int)(i % (unsigned)C4);
+    unsigned r = i / (unsigned)C4;
+    const int x = (int)(r % (unsigned)W);
+    r /= (unsigned)W;
+    const int y = (int)(r % (unsigned)H), b = (int)(r / (unsigned)H);
+    const float* ip = img + ((size_t)b * (H + 2) + y) * Wp + x;  // top-left of the 3x3 window in the bordered image
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+    for (int t = 0; t < 9; ++t) {
+      const float v = __ldg(ip + (t / 3) * Wp + t % 3);
+      const float4 w = __ldg(reinterpret_cast<const float4*>(wpk + (size_t)t * N + c));
+      acc.x = fmaf(v, w.x, acc.x), acc.y = fmaf(v, w.y, acc.y), acc.z = fmaf(v, w.z, acc.z), acc.w = fmaf(v, w.w, acc.w);
+    }
+    const float4 bi = __ldg(reinterpret_cast<const float4*>(bias + c)), sc = __ldg(reinterpret_cast<const float4*>(scale + c));
+    const float4 sh = __ldg(reinterpret_cast<const float4*>(shift + c));
+    float o[4] = {fmaf(acc.x + bi.x, sc.x, sh.x), fmaf(acc.y + bi.y, sc.y, sh.y), fmaf(acc.z + bi.z, sc.z, sh.z),
+                  fmaf(acc.w + bi.w, sc.w, sh.w)};
+#pragma unroll
+    for (int j = 0; j < 4; ++j) o[j] = o[j] > 0.f ? o[j] : 0.3f * o[j];
+    *reinterpret_cast<float4*>(h + (((size_t)b * (H + 2) + y + 1) * Wp + x + 1) * N + c) = make_float4(o[0], o[1], o[2], o[3]);
+  }
+}
+
 // Same operator, tiled (round 2; used when the expanded gradient `go` is materialised).  The kernel above reads every 24-channel
 // gradient pixel nine times (once per tap) through L1: 7 GB per launch at B = 256, which is what its 0.76 ms was.  Here a CTA
 // owns SR_FB_ROWS image rows: phase 1 reads each pixel of the rows + halo ONCE and forms its nine per-tap dot products
@@ -531,12 +567,13 @@ __global__ void __launch_bounds__(256) sr_attention_bwd_kernel(const float* __re
 // The expanded gradient at conv2's output, materialised with a zero border for the tensor-core transposed convolution.
 __global__ void sr_expand_go_kernel(SrArgs a, float* __restrict__ go, int64_t n4) {
   const int C4 = a.C >> 2, Hp = a.H + 2, Wp = a.W + 2;
-  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n4; i += (int64_t)gridDim.x * blockDim.x) {
-    const int c4 = (int)(i % C4);
-    int64_t r = i / C4;
-    const int xp = (int)(r % Wp);
-    r /= Wp;
-    const int yp = (int)(r % Hp), b = (int)(r / Hp);
+  const unsigned total = (unsigned)n4, step = gridDim.x * blockDim.x;  // 32-bit index arithmetic (n4 < 2^31, checked on the host)
+  for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += step) {
+    const int c4 = (int)(i % (unsigned)C4);
+    unsigned r = i / (unsigned)C4;
+    const int xp = (int)(r % (unsigned)Wp);
+    r /= (unsigned)Wp;
+    const int yp = (int)(r % (unsigned)Hp), b = (int)(r / (unsigned)Hp);
     float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
     if (yp >= 1 && yp <= a.H && xp >= 1 && xp <= a.W) v = expand_go(a, b, yp - 1, xp - 1, 4 * c4);
     reinterpret_cast<float4*>(go)[i] = v;
@@ -548,12 +585,13 @@ __global__ void sr_expand_go_kernel(SrArgs a, float* __restrict__ go, int64_t n4
 __global__ void sr_shortcut_bwd_kernel(const float* __restrict__ go, const float* __restrict__ wd, float* __restrict__ g_x, int H,
                                        int W, int C, int Ci, int64_t n4) {
   const int C4 = Ci >> 2;
-  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n4; i += (int64_t)gridDim.x * blockDim.x) {
-    const int c = 4 * (int)(i % C4);
-    int64_t r = i / C4;
-    const int x = (int)(r % W);
-    r /= W;
-    const int y = (int)(r % H), b = (int)(r / H);
+  const unsigned total = (unsigned)n4, step = gridDim.x * blockDim.x;
+  for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += step) {
+    const int c = 4 * (int)(i % (unsigned)C4);
+    unsigned r = i / (unsigned)C4;
+    const int x = (int)(r % (unsigned)W);
+    r /= (unsigned)W;
+    const int y = (int)(r % (unsigned)H), b = (int)(r / (unsigned)H);
     const float* gp = go + (((size_t)b * (H + 2) + y + 1) * (W + 2) + x + 1) * C;
     float4 acc = reinterpret_cast<float4*>(g_x)[i];
     if (wd != nullptr) {
@@ -856,7 +894,8 @@ int launch_conv(SrArgs a, bool floor_quads, const char* tag, cudaStream_t stream
   a.slab_all = sr_slab_all(a.N, a.CK) ? 1 : 0;
   int band = sr_band_rows(QH, QW, a.qpc) * (2 * QW + 2) * CKp;
   band = (band + 3) & ~3;
-  const size_t smem = (size_t)(band + (a.slab_all ? 9 : 1) * a.CK * a.N + (MODE == F2 ? a.qpc * a.N : 0)) * sizeof(float);
+  size_t smem = (size_t)(band + (a.slab_all ? 9 : 1) * a.CK * a.N + (MODE == F2 ? a.qpc * a.N : 0)) * sizeof(float);
+  if (MODE == F2 && a.c2 != nullptr) smem = (size_t)a.qpc * a.N * sizeof(float);  // no band, no weights: only the partial sums
   ADVB_CHECK(smem <= 227 * 1024, "SpecRNet conv tile does not fit shared memory");
   ADVB_CHECK(a.N % 8 == 0 && a.N <= 64, "SpecRNet conv: N must be a multiple of 8, <= 64");
   ADVB_CUDA_OK(cudaFuncSetAttribute(sr_conv_kernel<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -950,7 +989,11 @@ int sr_block_forward(const SrBlock& k, const float* x, int B, const char* tag, c
   // CKr: the padded channels (20 -> 24) carry zero weights; the contraction skips them (bit-identical up to the sign of zero)
   a.CK = k.Ci, a.N = k.C, a.CKr = k.Ci % 4 == 0 ? std::min(k.Ci, (k.Cin + 3) / 4 * 4) : k.Ci;
   a.in = x, a.wpk = k.w1f, a.bias = k.b1p, a.out = k.h;
-  if (k.tc1) {  // conv1 -> bn2 -> LeakyReLU on the tensor cores (affine + activation in the epilogue)
+  if (k.Ci == 1 && k.tc2) {  // first block: 1-channel input, a 9-term contraction
+    const int64_t n4 = (int64_t)B * k.H * k.W * (k.C / 4);
+    sr_first_conv1_kernel<<<ew_blocks(n4), 256, 0, stream>>>(x, k.w1f, k.b1p, k.bn_scale, k.bn_shift, k.h, k.H, k.W, k.C, n4);
+    ADVB_KERNEL_OK(t.conv1, stream);
+  } else if (k.tc1) {  // conv1 -> bn2 -> LeakyReLU on the tensor cores (affine + activation in the epilogue)
     P3Plain p;
     p.in = x, p.out = k.h, p.out_pad = 1, p.wpack = k.tcf1, p.bias = k.b1p;
     p.aff_scale = k.bn_scale, p.aff_shift = k.bn_shift, p.act_slope = 0.3f;
@@ -990,6 +1033,7 @@ int sr_block_backward(const SrBlock& k, const float* x, float* g_x, int B, bool 
   a.CK = k.C, a.CKr = std::min(k.C, (k.Cout + 3) / 4 * 4), a.N = k.C, a.wpk = k.w2d, a.out = k.g_c1;
   if (k.tc2) {  // g_o materialised once (zero border), conv2^T on the tensor cores with the LeakyReLU' * bn2-scale factor in its epilogue
     const int64_t n4 = (int64_t)B * (k.H + 2) * (k.W + 2) * (k.C / 4);
+    ADVB_CHECK(n4 < (1LL << 31), "SpecRNet: batch too large for the 32-bit element index of the expanded gradient");
     sr_expand_go_kernel<<<ew_blocks(n4), 256, 0, stream>>>(a, k.go, n4);
     ADVB_KERNEL_OK(t.expand_go, stream);
     P3Plain p;
