@@ -227,7 +227,8 @@ class Engine:
         """``conv_path`` (0 tcgen05 / 1 fp32 SIMT), ``tf32_passes`` (3 = 3xTF32 / 1 = single pass), ``conv_sched``
         (0 persistent kernels / 1 one-tile-per-CTA kernels), ``conv0_bwd`` (first block backward: 0 fp32 cell kernel /
         1 tcgen05 GEMM + col2im), ``graph`` (1 = replay the attack iteration as a CUDA graph), ``fuse_update`` (1 = FGSM /
-        PGD update rule in the frontend backward's epilogue)."""
+        PGD update rule in the frontend backward's epilogue), ``sr_tc`` (SpecRNet 3x3 convolutions: 1 tcgen05 / 0 fp32 SIMT),
+        ``fe_spec``, ``lstm_tc``, ``conv0_fwd``, ``weight_cache``: see ``include/advb200.h``."""
         _lib.check(self.lib.advb_set_option(self.handle, key.encode(), int(value)))
 
     def profile_begin(self):
