@@ -374,31 +374,39 @@ __global__ void __launch_bounds__(256) sr_first_conv1_kernel(const float* __rest
                                                               const float* __restrict__ wpk /*[tap][1][N]*/,
                                                               const float* __restrict__ bias, const float* __restrict__ scale,
                                                               const float* __restrict__ shift, float* __restrict__ h, int H, int W,
-                                                              int N, int64_t n4) {
-  const int C4 = N >> 2, Wp = W + 2;
-  // (32-bit index arithmetic: the 64-bit divisions of the first version were most of its instructions)
-  const unsigned total = (unsigned)n4, step = gridDim.x * blockDim.x;
+                                                              int N, int64_t n_px) {
+  // thread = pixel: the nine image samples and the index arithmetic are shared by all N channels (one thread per 4 channels was
+  // instruction-bound: 68 % issue slots at 22 % of the DRAM rate); weights, bias and the BatchNorm affine sit in shared memory
+  __shared__ __align__(16) float s_w[9 * 64], s_b[64], s_sc[64], s_sh[64];
+  for (int i = threadIdx.x; i < 9 * N; i += blockDim.x) s_w[i] = wpk[i];
+  for (int i = threadIdx.x; i < N; i += blockDim.x) s_b[i] = bias[i], s_sc[i] = scale[i], s_sh[i] = shift[i];
+  __syncthreads();
+  const int Wp = W + 2;
+  const unsigned total = (unsigned)n_px, step = gridDim.x * blockDim.x;
   for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += step) {
-    const int c = 4 * (int)(i % (unsigned)C4);
-    unsigned r = i / (unsigned)C4;
-    const int x = (int)(r % (unsigned)W);
-    r /= (unsigned)W;
+    const int x = (int)(i % (unsigned)W);
+    const unsigned r = i / (unsigned)W;
     const int y = (int)(r % (unsigned)H), b = (int)(r / (unsigned)H);
     const float* ip = img + ((size_t)b * (H + 2) + y) * Wp + x;  // top-left of the 3x3 window in the bordered image
-    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    float v[9];
 #pragma unroll
-    for (int t = 0; t < 9; ++t) {
-      const float v = __ldg(ip + (t / 3) * Wp + t % 3);
-      const float4 w = __ldg(reinterpret_cast<const float4*>(wpk + (size_t)t * N + c));
-      acc.x = fmaf(v, w.x, acc.x), acc.y = fmaf(v, w.y, acc.y), acc.z = fmaf(v, w.z, acc.z), acc.w = fmaf(v, w.w, acc.w);
+    for (int t = 0; t < 9; ++t) v[t] = __ldg(ip + (t / 3) * Wp + t % 3);
+    float* hp = h + (((size_t)b * (H + 2) + y + 1) * Wp + x + 1) * N;
+    for (int c = 0; c < N; c += 4) {
+      float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+      for (int t = 0; t < 9; ++t) {
+        const float4 w = *reinterpret_cast<const float4*>(s_w + t * N + c);
+        acc.x = fmaf(v[t], w.x, acc.x), acc.y = fmaf(v[t], w.y, acc.y), acc.z = fmaf(v[t], w.z, acc.z), acc.w = fmaf(v[t], w.w, acc.w);
+      }
+      const float4 bi = *reinterpret_cast<const float4*>(s_b + c), sc = *reinterpret_cast<const float4*>(s_sc + c);
+      const float4 sh = *reinterpret_cast<const float4*>(s_sh + c);
+      float o[4] = {fmaf(acc.x + bi.x, sc.x, sh.x), fmaf(acc.y + bi.y, sc.y, sh.y), fmaf(acc.z + bi.z, sc.z, sh.z),
+                    fmaf(acc.w + bi.w, sc.w, sh.w)};
+#pragma unroll
+      for (int j = 0; j < 4; ++j) o[j] = o[j] > 0.f ? o[j] : 0.3f * o[j];
+      *reinterpret_cast<float4*>(hp + c) = make_float4(o[0], o[1], o[2], o[3]);
     }
-    const float4 bi = __ldg(reinterpret_cast<const float4*>(bias + c)), sc = __ldg(reinterpret_cast<const float4*>(scale + c));
-    const float4 sh = __ldg(reinterpret_cast<const float4*>(shift + c));
-    float o[4] = {fmaf(acc.x + bi.x, sc.x, sh.x), fmaf(acc.y + bi.y, sc.y, sh.y), fmaf(acc.z + bi.z, sc.z, sh.z),
-                  fmaf(acc.w + bi.w, sc.w, sh.w)};
-#pragma unroll
-    for (int j = 0; j < 4; ++j) o[j] = o[j] > 0.f ? o[j] : 0.3f * o[j];
-    *reinterpret_cast<float4*>(h + (((size_t)b * (H + 2) + y + 1) * Wp + x + 1) * N + c) = make_float4(o[0], o[1], o[2], o[3]);
   }
 }
 
@@ -990,8 +998,9 @@ int sr_block_forward(const SrBlock& k, const float* x, int B, const char* tag, c
   a.CK = k.Ci, a.N = k.C, a.CKr = k.Ci % 4 == 0 ? std::min(k.Ci, (k.Cin + 3) / 4 * 4) : k.Ci;
   a.in = x, a.wpk = k.w1f, a.bias = k.b1p, a.out = k.h;
   if (k.Ci == 1 && k.tc2) {  // first block: 1-channel input, a 9-term contraction
-    const int64_t n4 = (int64_t)B * k.H * k.W * (k.C / 4);
-    sr_first_conv1_kernel<<<ew_blocks(n4), 256, 0, stream>>>(x, k.w1f, k.b1p, k.bn_scale, k.bn_shift, k.h, k.H, k.W, k.C, n4);
+    const int64_t n_px = (int64_t)B * k.H * k.W;
+    ADVB_CHECK(k.C <= 64 && n_px < (1LL << 31), "SpecRNet first conv1: at most 64 channels, 2^31 pixels");
+    sr_first_conv1_kernel<<<ew_blocks(n_px), 256, 0, stream>>>(x, k.w1f, k.b1p, k.bn_scale, k.bn_shift, k.h, k.H, k.W, k.C, n_px);
     ADVB_KERNEL_OK(t.conv1, stream);
   } else if (k.tc1) {  // conv1 -> bn2 -> LeakyReLU on the tensor cores (affine + activation in the epilogue)
     P3Plain p;
