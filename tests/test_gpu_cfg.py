@@ -137,6 +137,30 @@ def test_attack_matches_reference_at_benchmarked_config(name, cuda_device, recor
     assert dlogit < dmax, row
 
 
+def test_clips_are_independent_at_the_headline_size(cuda_device):
+    """Size-independent property at BASELINE.json configs[1] (B = 128, T = 64 000): clips shard with no data-path coupling
+    (SURVEY.md §8e), so the attack of the whole batch is, bit for bit, the attacks of its two halves - whatever the persistent
+    kernels' tile schedules (148 CTAs over 128 or 64 clips) and the CUDA-graph replay do.  (LFCC on these clips never reaches the
+    batch-wide dB floor, the one coupling the reference itself has: F5.)  PGD-6 and the gradient of one evaluation."""
+    from advb200 import torchattacks as ta
+
+    name = "cfg2_lcnn_pgd40_b128"
+    case, gold, x, y, holder, eng = cfg_setup(name, cuda_device)
+    p = case["params"]
+    xd, yd = x.to(cuda_device), y.to(cuda_device)
+    noise = helpers.reference_start(case, "pgd", x, p["eps"]).to(cuda_device)
+    atk = ta.PGD(holder, eps=p["eps"], alpha=p["alpha"], steps=6, random_start=True)
+    atk.set_training_mode(model_training=True, batchnorm_training=False)
+    whole = atk.forward(xd, yd, noise=noise)
+    halves = torch.cat([atk.forward(xd[:64], yd[:64], noise=noise[:64]), atk.forward(xd[64:], yd[64:], noise=noise[64:])])
+    assert torch.equal(whole, halves)
+    # the CE mean is over the batch the call sees: compare per-clip gradients at the same normalisation
+    g_all, l_all = eng.grad(xd, yd)
+    g_a, l_a = eng.grad(xd[:64], yd[:64])
+    assert torch.equal(l_all[:64], l_a)
+    assert (g_all[:64] * 2.0 - g_a).abs().max().item() <= 1e-12  # 1 / 128 vs 1 / 64: a power of two, exact
+
+
 def test_pgd_schedule_variants_are_bit_identical(cuda_device):
     """CUDA-graph replay vs host loop, update fused into the frontend backward vs its own kernel, even and odd step counts
     (the fused loop ping-pongs two iterate buffers): every variant must return the same bits."""
