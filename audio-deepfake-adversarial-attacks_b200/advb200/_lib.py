@@ -66,7 +66,11 @@ SIGNATURES = {
     "advb_launch_count": (C.c_int64, [C.c_void_p]),
     "advb_profile_begin": (C.c_int, [C.c_void_p, C.c_void_p]),
     "advb_profile_end": (C.c_int64, [C.c_void_p, C.c_char_p, C.c_int64]),
+    "advb_xrank_export": (C.c_int, [C.c_void_p, C.c_char_p, C.POINTER(C.c_void_p)]),
+    "advb_xrank_connect": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_char_p, C.POINTER(C.c_void_p)]),
+    "advb_xrank_status": (C.c_int, [C.c_void_p, C.POINTER(C.c_int)]),
 }
+XRANK_HANDLE_BYTES = 64
 
 _lib = None
 

@@ -231,6 +231,52 @@ class Engine:
         ``fe_spec``, ``lstm_tc``, ``conv0_fwd``, ``weight_cache``: see ``include/advb200.h``."""
         _lib.check(self.lib.advb_set_option(self.handle, key.encode(), int(value)))
 
+    # ---- strict multi-GPU mode (include/advb200.h, advb_xrank_*; SURVEY.md §8(e) ii) ---------------------------------
+    def xrank_export(self):
+        """(64-byte CUDA IPC handle, device pointer) of this handle's mailbox; clears the mailbox (protocol step 1)."""
+        buf = C.create_string_buffer(_lib.XRANK_HANDLE_BYTES)
+        ptr = C.c_void_p()
+        with torch.cuda.device(self.device):
+            _lib.check(self.lib.advb_xrank_export(self.handle, buf, C.byref(ptr)))
+        return buf.raw, ptr.value
+
+    def xrank_connect(self, rank: int, world: int, ipc_handles=None, local_ptrs=None):
+        """Map the peers' mailboxes (protocol step 3).  ``ipc_handles``: the ranks' 64-byte handles in rank order (peers in
+        other processes); ``local_ptrs``: device pointers of handles living in this process (``None`` entries fall back to
+        the IPC handle).  ``world <= 1`` returns to per-shard floors."""
+        blob = b"".join(ipc_handles) if ipc_handles is not None else None
+        if blob is not None and len(blob) != world * _lib.XRANK_HANDLE_BYTES:
+            raise ValueError("one 64-byte IPC handle per rank, in rank order")
+        ptrs = None
+        if local_ptrs is not None:
+            ptrs = (C.c_void_p * world)(*[C.c_void_p(p) if p else C.c_void_p() for p in local_ptrs])
+        with torch.cuda.device(self.device):
+            _lib.check(self.lib.advb_xrank_connect(self.handle, int(rank), int(world), blob, ptrs))
+        self.strict_world = int(world) if world > 1 else 1
+
+    def enable_strict(self, group=None):
+        """One process per GPU: from now on the dB floor of every frontend pass spans the clips of ALL ranks of ``group``, so
+        the sharded run reproduces the single-device batch.  Collective: every rank of the group must call it, and must then
+        make the same sequence of forward / gradient / FGSM / PGD / PGDL2 calls."""
+        import torch.distributed as dist
+
+        world, rank = dist.get_world_size(group), dist.get_rank(group)
+        if world == 1:
+            return self.xrank_connect(0, 1)
+        handle, _ = self.xrank_export()
+        handles = [None] * world
+        dist.all_gather_object(handles, handle, group=group)  # also the barrier between "cleared" and "first exchange"
+        self.xrank_connect(rank, world, ipc_handles=handles)
+        dist.barrier(group=group)  # nobody starts exchanging before every rank has mapped its peers
+
+    def strict_timed_out(self) -> bool:
+        """True when an exchange gave up waiting for a peer (the ranks' call sequences diverged, or a peer died); the results
+        since then used per-shard floors.  Synchronises the device."""
+        torch.cuda.synchronize(self.device)
+        flag = C.c_int(0)
+        _lib.check(self.lib.advb_xrank_status(self.handle, C.byref(flag)))
+        return bool(flag.value)
+
     def profile_begin(self):
         _lib.check(self.lib.advb_profile_begin(self.handle, self._stream()))
 

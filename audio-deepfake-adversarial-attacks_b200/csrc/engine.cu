@@ -114,6 +114,10 @@ struct advb_handle {
   int fe_spec = 1;
   FrontendState fst{};
   FrontendHost fe_host{};
+  // strict multi-GPU mode (advb_xrank_*): own mailbox + peers' mailboxes mapped with CUDA IPC
+  unsigned long long* xr_mailbox = nullptr;
+  std::vector<void*> xr_ipc_opened;
+  int xr_gen = 0;  // graph cache key: the captured exchange nodes hold the peers' pointers
   FrontendTables ftb{};
 
   // LCNN
@@ -912,6 +916,7 @@ void advb_destroy(advb_handle* h) {
   if (h == nullptr) return;
   DeviceGuard guard(h->device);
   drop_graph(h);
+  for (void* p : h->xr_ipc_opened) cudaIpcCloseMemHandle(p);
   if (h->cap_stream != nullptr) cudaStreamDestroy(h->cap_stream);
   if (h->last_done != nullptr) cudaEventDestroy(h->last_done);
   for (void* p : h->allocs) cudaFree(p);
@@ -967,6 +972,88 @@ int advb_set_option(advb_handle* h, const char* key, int value) {
   return 0;
 }
 
+// ---- strict multi-GPU mode: the batch-wide dB floor spans every rank's clips (frontend.cuh, FrontendXRank) -------------
+int advb_xrank_export(advb_handle* h, unsigned char* ipc_handle, void** local_ptr) {
+  ADVB_CHECK(h != nullptr, "null handle");
+  ADVB_CHECK(h->frontend_kind != ADVB_FRONTEND_NONE, "strict mode couples the dB floor of a spectral frontend; this model has none");
+  static_assert(sizeof(cudaIpcMemHandle_t) == ADVB_XRANK_HANDLE_BYTES, "cudaIpcMemHandle_t is 64 bytes");
+  DeviceGuard guard(h->device);
+  CallScope scope(h);
+  ADVB_CUDA_OK(cudaDeviceSynchronize());
+  if (h->xr_mailbox == nullptr) {
+    ADVB_TRY(h->alloc(&h->xr_mailbox, 2 * XR_MAX_RANKS));
+    ADVB_TRY(h->alloc(&h->fst.xr.epoch, 1));
+    ADVB_TRY(h->alloc(&h->fst.xr.timed_out, 1));
+  }
+  // every rank clears its mailbox and exchange counter BEFORE the handles are exchanged (the exchange is the barrier), so no
+  // peer can have written into it yet
+  ADVB_CUDA_OK(cudaMemset(h->xr_mailbox, 0, 2 * XR_MAX_RANKS * sizeof(unsigned long long)));
+  ADVB_CUDA_OK(cudaMemset(h->fst.xr.epoch, 0, sizeof(unsigned)));
+  ADVB_CUDA_OK(cudaMemset(h->fst.xr.timed_out, 0, sizeof(int)));
+  ADVB_CUDA_OK(cudaDeviceSynchronize());
+  if (ipc_handle != nullptr) {
+    cudaIpcMemHandle_t ipc;
+    ADVB_CUDA_OK(cudaIpcGetMemHandle(&ipc, h->xr_mailbox));
+    memcpy(ipc_handle, &ipc, sizeof(ipc));
+  }
+  if (local_ptr != nullptr) *local_ptr = h->xr_mailbox;
+  return 0;
+}
+
+int advb_xrank_connect(advb_handle* h, int rank, int world, const unsigned char* ipc_handles, void* const* local_ptrs) {
+  ADVB_CHECK(h != nullptr, "null handle");
+  DeviceGuard guard(h->device);
+  CallScope scope(h);
+  ADVB_CUDA_OK(cudaDeviceSynchronize());
+  drop_graph(h);
+  h->xr_gen++;
+  for (void* p : h->xr_ipc_opened) cudaIpcCloseMemHandle(p);
+  h->xr_ipc_opened.clear();
+  h->fst.xr.world = 1;
+  h->fst.xr.rank = 0;
+  if (world <= 1) return 0;  // back to per-shard floors
+  ADVB_CHECK(world <= XR_MAX_RANKS && rank >= 0 && rank < world, "strict mode: 2..8 ranks, 0 <= rank < world");
+  ADVB_CHECK(h->xr_mailbox != nullptr, "advb_xrank_export first");
+  ADVB_CHECK(ipc_handles != nullptr || local_ptrs != nullptr, "peer mailboxes: IPC handles (other processes) or device pointers (this process)");
+  for (int r = 0; r < world; ++r) {
+    void* p = nullptr;
+    if (r == rank) {
+      p = h->xr_mailbox;
+    } else if (local_ptrs != nullptr && local_ptrs[r] != nullptr) {
+      p = local_ptrs[r];
+      cudaPointerAttributes attr{};
+      ADVB_CUDA_OK(cudaPointerGetAttributes(&attr, p));
+      if (attr.device != h->device) {
+        int can = 0;
+        ADVB_CUDA_OK(cudaDeviceCanAccessPeer(&can, h->device, attr.device));
+        ADVB_CHECK(can != 0, "strict mode needs peer access between the ranks' devices");
+        cudaError_t e = cudaDeviceEnablePeerAccess(attr.device, 0);
+        if (e == cudaErrorPeerAccessAlreadyEnabled) cudaGetLastError();
+        else ADVB_CUDA_OK(e);
+      }
+    } else {
+      ADVB_CHECK(ipc_handles != nullptr, "no mailbox given for a peer rank");
+      cudaIpcMemHandle_t ipc;
+      memcpy(&ipc, ipc_handles + (size_t)r * ADVB_XRANK_HANDLE_BYTES, sizeof(ipc));
+      ADVB_CUDA_OK(cudaIpcOpenMemHandle(&p, ipc, cudaIpcMemLazyEnablePeerAccess));
+      h->xr_ipc_opened.push_back(p);
+    }
+    h->fst.xr.mailbox[r] = static_cast<unsigned long long*>(p);
+  }
+  h->fst.xr.world = world;
+  h->fst.xr.rank = rank;
+  return 0;
+}
+
+int advb_xrank_status(advb_handle* h, int* timed_out) {
+  ADVB_CHECK(h != nullptr && timed_out != nullptr, "null argument");
+  *timed_out = 0;
+  if (h->fst.xr.timed_out == nullptr) return 0;
+  DeviceGuard guard(h->device);
+  ADVB_CUDA_OK(cudaMemcpy(timed_out, h->fst.xr.timed_out, sizeof(int), cudaMemcpyDeviceToHost));
+  return 0;
+}
+
 int advb_rebind(advb_handle* h, int n_tensors, const advb_tensor_ref* tensors) {
   ADVB_CHECK(h != nullptr, "null handle");
   ADVB_TRY(bind_tensors(h, n_tensors, tensors));
@@ -1018,7 +1105,7 @@ std::string graph_key(const advb_handle* h, const advb_attack_desc* atk, int B, 
          bits(atk->eps_div) + "|" + std::to_string(n_global) + "|" + std::to_string(fused) + "|" +
          std::to_string(h->conv_path) + "|" + std::to_string(h->tf32_passes) + "|" + std::to_string(h->conv_sched) + "|" +
          std::to_string(h->conv0_bwd) + "|" + std::to_string(h->conv0_fwd) + "|" + std::to_string(h->fe_spec) + "|" + std::to_string(h->lstm_tc) + "|" + std::to_string(h->sr_tc) + "|" +
-         std::to_string(h->bind_epoch);
+         std::to_string(h->bind_epoch) + "|" + std::to_string(h->xr_gen);
 }
 
 // The attack loops (caller holds a CallScope and has validated the arguments).  `minmax`: x / x_adv are raw waveforms and
@@ -1176,6 +1263,9 @@ int check_attack_args(advb_handle* h, const advb_attack_desc* atk, const float* 
   ADVB_CHECK(atk != nullptr && x != nullptr && y != nullptr && x_adv != nullptr, "null argument");
   ADVB_CHECK(!atk->targeted || atk->target_labels != nullptr, "targeted mode needs target_labels");
   ADVB_CHECK(!atk->targeted || atk->kind != ADVB_ATTACK_FAB, "FAB has no targeted mode in the reference's patched copy (fab.py:63)");
+  ADVB_CHECK(h->fst.xr.world <= 1 || (atk->kind != ADVB_ATTACK_FAB && atk->kind != ADVB_ATTACK_CW),
+             "strict multi-GPU mode needs the same call sequence on every rank: FAB (per-rank clip selection) and CW (per-rank early "
+             "stop) are not supported under it");
   return 0;
 }
 }  // namespace

@@ -200,6 +200,67 @@ __device__ __forceinline__ void filter_energy4(const float* __restrict__ fb, con
 
 __device__ __forceinline__ float to_db(float e) { return 10.0f * log10f(fmaxf(e, 1e-10f)); }
 
+// Strict multi-GPU mode: all ranks agree on the batch-wide dB maximum (kind 0, between fe_power_db and fe_floor_dct) or on
+// the summed gradient of the clamped elements (kind 1, between fe_dct_t and fe_bwd).  Lane r talks to rank r.
+//   kind 0: the rank holding the largest key keeps its packed arg-max (ties: lowest rank = earliest clips, as the packed
+//           ~index order decides inside one device); every other rank takes the key with an index no element matches, so the
+//           clamped mass is applied exactly once, by the owner.
+//   kind 1: partial sums are added in rank order on every rank (same bits everywhere).
+constexpr unsigned long long XR_TIMEOUT_NS = 5ull * 1000 * 1000 * 1000;  // then sticky: later exchanges do not wait again
+__device__ __forceinline__ unsigned long long xr_globaltimer() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+  return t;
+}
+__global__ void __launch_bounds__(32) fe_xrank_kernel(FrontendState st, int kind) {
+  const FrontendXRank& xr = st.xr;
+  const int lane = threadIdx.x;
+  const unsigned e = *xr.epoch + 1u;
+  __syncwarp();
+  const unsigned mine = kind == 0 ? (unsigned)(*st.gmax_packed >> 32) : __float_as_uint(*st.mass_total);
+  const int par = (int)(e & 1u);
+  unsigned got = 0u;
+  bool ok = true;
+  const bool dead = *(volatile int*)xr.timed_out != 0;
+  if (lane < xr.world) {
+    // a rank can run at most one exchange ahead of a peer that is still reading, hence the two parities
+    unsigned long long* dst = xr.mailbox[lane] + par * XR_MAX_RANKS + xr.rank;
+    const unsigned long long word = ((unsigned long long)mine << 32) | e;
+    asm volatile("st.relaxed.sys.global.u64 [%0], %1;" ::"l"(dst), "l"(word) : "memory");
+    const unsigned long long* src = xr.mailbox[xr.rank] + par * XR_MAX_RANKS + lane;
+    const unsigned long long t0 = xr_globaltimer();
+    unsigned long long w;
+    for (;;) {
+      asm volatile("ld.relaxed.sys.global.u64 %0, [%1];" : "=l"(w) : "l"(src) : "memory");
+      if ((unsigned)w == e) break;
+      if (dead || xr_globaltimer() - t0 > XR_TIMEOUT_NS) {
+        ok = false;
+        break;
+      }
+      __nanosleep(200);
+    }
+    got = (unsigned)(w >> 32);
+  }
+  if (__any_sync(0xffffffffu, !ok) && lane == 0) *xr.timed_out = 1;
+  if (kind == 0) {
+    // the packed key (float_to_key ^ 0x80000000) orders like the float under an unsigned compare; 0 = nothing seen
+    unsigned best = lane < xr.world ? got : 0u;
+    int owner = lane < xr.world ? lane : XR_MAX_RANKS;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      const unsigned b2 = __shfl_xor_sync(0xffffffffu, best, o);
+      const int o2 = __shfl_xor_sync(0xffffffffu, owner, o);
+      if (b2 > best || (b2 == best && o2 < owner)) best = b2, owner = o2;
+    }
+    if (lane == 0 && owner != xr.rank) *st.gmax_packed = (unsigned long long)best << 32;  // ~index = 0: no element matches
+  } else {
+    float s = 0.f;
+    for (int r = 0; r < xr.world; ++r) s += __uint_as_float(__shfl_sync(0xffffffffu, got, r));
+    if (lane == 0) *st.mass_total = s;
+  }
+  if (lane == 0) *xr.epoch = e;
+}
+
 // ---------------------------------------------------------------------------------------------------
 __global__ void fe_tables_kernel(const float* __restrict__ fb, int* klo, int* kcnt, int* mlo, int* mcnt) {
   const int i = threadIdx.x;
@@ -854,6 +915,10 @@ int frontend_forward(const FrontendTables& tb, const FrontendState& st, const fl
   const int g1 = n_fb * B < 148 * 3 ? n_fb * B : 148 * 3;  // persistent: 74 KB of shared memory -> 3 CTAs / SM
   fe_power_db_kernel<<<g1, FE_THREADS, fe_fwd_smem(), stream>>>(x, T, F, tb, st, dB, spec, n_fb, B);
   ADVB_KERNEL_OK("fe_power_db", stream);
+  if (st.xr.world > 1) {
+    fe_xrank_kernel<<<1, 32, 0, stream>>>(st, 0);
+    ADVB_KERNEL_OK("fe_xrank_max", stream);
+  }
   const int n_items = cdiv(B * F, FD_FR);
   const int g2 = n_items < 148 * 3 ? n_items : 148 * 3;  // persistent: 71 KB of shared memory -> 3 CTAs / SM
   fe_floor_dct_kernel<<<g2, 256, fe_dct_smem(), stream>>>(dB, F, tb, st, 80.0f, out, clip_stride, stride_f, stride_c,
@@ -885,6 +950,10 @@ int frontend_backward(const FrontendTables& tb, const FrontendState& st, const f
   fe_dct_t_kernel<<<g2, 256, fe_dct_t_smem(), stream>>>(gcoef, g_clip_stride, g_stride_f, g_stride_c, F, tb, gd, B * F, dB, st,
                                                        80.0f, mass_partial);
   ADVB_KERNEL_OK("fe_dct_t", stream);
+  if (st.xr.world > 1) {
+    fe_xrank_kernel<<<1, 32, 0, stream>>>(st, 1);
+    ADVB_KERNEL_OK("fe_xrank_sum", stream);
+  }
   const int n_tiles = cdiv(T, TILE_S);
   for (int tile = 0; tile < n_tiles; ++tile) {
     int t_lo, t_hi;

@@ -16,11 +16,26 @@ struct FrontendTables {
   int* mcnt;            // 257
 };
 
+// Strict multi-GPU mode (SURVEY.md §8(e) ii): the top_db floor of amplitude_to_DB is relative to the maximum of the WHOLE
+// batch (F5), so a clip-sharded run reproduces the single-device result only if the ranks agree on that maximum (forward) and
+// on the summed gradient of the clamped elements, which autograd routes to the arg-max element (backward).  Both are one float
+// per rank: each rank stores (value << 32 | exchange number) straight into every peer's mailbox over NVLink (peer memory mapped
+// with CUDA IPC; one 8-byte store is atomic) and polls its own mailbox until every rank's word carries the current exchange
+// number.  No NCCL call, no host round trip: the exchange is a 32-thread kernel node of the replayed CUDA graph.
+constexpr int XR_MAX_RANKS = 8;
+struct FrontendXRank {
+  int world = 1, rank = 0;                               // world == 1: exchange disabled
+  unsigned long long* mailbox[XR_MAX_RANKS] = {};        // mailbox[r]: rank r's [2 parities][XR_MAX_RANKS] words (mailbox[rank] is local)
+  unsigned* epoch = nullptr;                             // local: exchanges done so far (all ranks make the same sequence of calls)
+  int* timed_out = nullptr;                              // local: set when a peer did not arrive within XR_TIMEOUT_NS
+};
+
 struct FrontendState {
   unsigned long long* gmax_packed;  // batch arg-max of the dB tensor: (ordered float key << 32) | ~index
   int* n_clamped;                   // > 0 iff the top_db floor clamped anything in the last forward
   float* mass_total;                // backward: summed gradient of clamped elements
   unsigned* done;                   // [2] "last block" counters: fe_dct_t (mass reduction), fe_bwd (state reset)
+  FrontendXRank xr;                 // strict multi-GPU mode; world == 1 otherwise
 };
 
 // Optional epilogue of the backward: the attack's element-wise update rule (fgsm.py:59-60, pgd.py:74-76) applied to each

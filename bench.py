@@ -438,6 +438,9 @@ def run_native(args):
     wl = WORKLOADS[args.workload]
     job = Job(args.workload, args.batch, dev, rank)
     B, eng, atk, x_dev, y_dev = job.B, job.eng, job.atk, job.x, job.y
+    if args.strict and world > 1:
+        eng.enable_strict()
+        args.no_other_workloads = True
 
     sampler = ClockSampler(local) if rank == 0 else None
     ms, ms_e2e, launches, adv = timed(job, args.steps, args.warmup)
@@ -570,6 +573,9 @@ def run_native(args):
                                   "clean logits straddle 0 (the value the reference-generated fixture used, when there is one)",
                        "loop": "one PGD iteration pair captured as a CUDA graph and replayed; update rule fused into the frontend "
                                "backward's epilogue",
+                       "db_floor": ("strict: one batch-wide floor across the ranks (two one-float peer-memory exchanges per iteration, "
+                                    "kernel nodes of the replayed graph)" if args.strict and world > 1 else
+                                    "per shard (what the reference's nn.DataParallel computes)"),
                        **({"engine_options": list(ENGINE_OPTS)} if ENGINE_OPTS else {})},
             "e2e": {"value": n_clips / (ms_e2e * 1e-3), "unit": "clips/s", "h2d_bytes_per_step": B * T_SAMPLES * 4 + B * 8,
                     "d2h_bytes_per_step": B * T_SAMPLES * 4},
@@ -625,6 +631,9 @@ def main():
                     help="lcnn = BASELINE.json configs[1] (the headline), specrnet = configs[2], rawnet3 / rawnet3_fab = configs[3] "
                          "(PGDL2 / FAB), lcnn_advtrain = configs[4] (attack call of adversarial training)")
     ap.add_argument("--engine-opt", action="append", default=[], help="engine option name=value for experiments (recorded in config)")
+    ap.add_argument("--strict", action="store_true",
+                    help="N > 1: the batch-wide dB floor spans the clips of every rank (advb_xrank_*: one-float peer-memory exchanges "
+                         "inside the replayed graph) instead of one floor per shard; recorded in config")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-other-workloads", action="store_true",
                     help="skip the short secondary measurements (configs[0], [2], [3], [4]) appended as `other_workloads`")

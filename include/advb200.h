@@ -18,7 +18,7 @@
 extern "C" {
 #endif
 
-#define ADVB_VERSION 201
+#define ADVB_VERSION 202
 #if defined(__GNUC__)
 #define ADVB_API __attribute__((visibility("default")))
 #else
@@ -116,6 +116,25 @@ ADVB_API int advb_invalidate_weights(advb_handle* h);
  *                 kernel, 3xTF32 (default), 0 = fp32 SIMT like the rest of SpecRNet
  *   "weight_cache" see advb_invalidate_weights */
 ADVB_API int advb_set_option(advb_handle* h, const char* key, int value);
+
+/* Strict multi-GPU mode (SURVEY.md §8(e) ii; no reference counterpart: the reference's nn.DataParallel computes one dB floor per
+ * replica, evaluate_models_on_adversarial_attacks.py:163-167, which is also this engine's default).  amplitude_to_DB's top_db floor
+ * is relative to the maximum of the whole batch, so a clip-sharded LFCC / MFCC run equals the single-device run only if the ranks
+ * share that maximum (forward) and the summed gradient of the clamped elements (backward).  Under strict mode every frontend
+ * forward / backward exchanges one float per rank through peer memory (8-byte stores into the peers' mailboxes over NVLink, polled
+ * by a 32-thread kernel; no NCCL call, no host sync, part of the replayed CUDA graph).  Protocol, identical on every rank:
+ *   1. advb_xrank_export   clears this rank's mailbox and returns its CUDA IPC handle (64 bytes) and device pointer
+ *   2. the host exchanges the handles (torch.distributed.all_gather_object; this exchange is the barrier the protocol needs)
+ *   3. advb_xrank_connect  maps the peers' mailboxes: ipc_handles = world x 64 bytes in rank order (other processes), and / or
+ *      local_ptrs[r] = the device pointer of a handle living in THIS process (tests; peer access is enabled when the devices
+ *      differ).  world <= 1 disconnects.
+ * From then on every rank must make the same sequence of forward / gradient / FGSM / PGD / PGDL2 calls (any batch size >= 1 per
+ * rank; pass n_global_batch); FAB and CW return an error.  A peer that does not arrive within 5 s makes the exchange give up
+ * (results of that call are then per-shard floors) and sets the flag advb_xrank_status reads (call it after a stream sync). */
+#define ADVB_XRANK_HANDLE_BYTES 64
+ADVB_API int advb_xrank_export(advb_handle* h, unsigned char* ipc_handle, void** local_ptr);
+ADVB_API int advb_xrank_connect(advb_handle* h, int rank, int world, const unsigned char* ipc_handles, void* const* local_ptrs);
+ADVB_API int advb_xrank_status(advb_handle* h, int* timed_out);
 
 /* Replaces  atk(images, labels)  = Attack.__call__ -> {FGSM,PGD,PGDL2,FAB,CW}.forward
  * (attack.py:308-331; fgsm.py:33-62; pgd.py:40-78; pgdl2.py:40-90; fab.py:70-78; cw.py:46-112), called from
