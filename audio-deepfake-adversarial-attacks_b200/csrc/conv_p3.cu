@@ -78,15 +78,28 @@ struct P3Cfg {
   static_assert(!HS || BWD, "horizontal scatter is a backward formulation");
   static_assert(!PLAIN || (!BWD && !POOL), "the plain variant is a forward convolution without pooling");
   static constexpr int PW = WMAX > 40 ? 384 : 256;
-  static constexpr int PT = PW + 64;
   static constexpr int NM3 = BWD ? 1 : 2;
+  // MMA-issuing warps.  One thread issues an MMA every ~140-150 cycles whatever N is (descriptor arithmetic on the uniform datapath:
+  // tools/tc_probe.cu section 5; ADVB_P3_PROF: 8.0 k cycles of issue per 2-M-tile unit of SpecRNet's first block with three OR two
+  // MMAs per k-step), which at N <= 64 is longer than the MMAs take.  PLAIN: one issuing warp per M-tile - both wait on the same
+  // full barriers and each commits to the empty / done barriers (arrival count NMW).
+  static constexpr int NMW = PLAIN ? NM3 : 1;
+  static constexpr int PT = PW + 32 * (1 + NMW);
   static constexpr int NTAP = HS ? 3 : 9;
   static constexpr int NMMA = HS ? 3 * NOUT : NOUT;  // MMA N = accumulator columns per M-tile
   static constexpr int BR = (NM3 * 128 + 2 * (WMAX + 2 + 1) + 7) & ~7;  // band rows per buffer (widest row: W = WMAX)
   static constexpr int NI_MAX = (BR * 8 + PW - 1) / PW;            // prefetch items per worker thread
   static constexpr int NKC = (KTOT + 31) / 32;
   static constexpr int NSLICE = NKC * NTAP;
-  static constexpr int NSTRIDE = p3_pow2(NMMA);
+  // WIDE (PLAIN only, 3xTF32): the weight slice holds its hi rows then its lo rows, NMMA x 128 B each, so ONE B descriptor with
+  // N = 2 NMMA covers [W_hi | W_lo]: A_hi x [W_hi | W_lo] is one MMA into 2 NMMA accumulator columns and A_lo x W_hi a second one
+  // into the first NMMA; the epilogue adds the two halves.  tcgen05.mma costs ~(128 + N) / 4 cycles per K = 8 step however small N
+  // is (profiles/r01_tc_probe.log), so two MMAs (N = 64 + 32: 48 + 46.5 cycles) replace three (3 x 46.5) at SpecRNet's N = 32, and
+  // 64 + 48 replace 3 x 48 at N = 64.  LCNN's forward blocks 2 / 4 (N = 96 / 128) cannot do this: two double-buffered M-tiles of
+  // 2 N accumulator columns exceed the 512 TMEM columns.
+  static constexpr bool WIDE = PLAIN;
+  static constexpr int NACC = WIDE ? 2 * NMMA : NMMA;  // accumulator columns per M-tile
+  static constexpr int NSTRIDE = p3_pow2(NACC);
   static constexpr int TMEM_COLS = p3_pow2(2 * NM3 * NSTRIDE);
   static constexpr int SLICE_BYTES = 2 * NMMA * 128;
   static constexpr int CS = (BWD || PLAIN) ? NMMA : NOUT / 2;  // staged floats per pixel
@@ -112,6 +125,7 @@ __global__ void __launch_bounds__(P3Cfg<KTOT, NOUT, POOL, BWD, HS, PLAIN, WMAX>:
   constexpr bool DB = Cfg::DB;
   constexpr int KSU = BWD ? 1 : 4;
   constexpr uint32_t IDESC = idesc_tf32(128, Cfg::NMMA);
+  constexpr uint32_t IDESC_WIDE = idesc_tf32(128, Cfg::NACC);
 
   extern __shared__ unsigned char smem_raw[];
   unsigned char* base = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -134,12 +148,12 @@ __global__ void __launch_bounds__(P3Cfg<KTOT, NOUT, POOL, BWD, HS, PLAIN, WMAX>:
   if (tid == 0) {
     for (int s = 0; s < NST; ++s) {
       mbar_init(&bar_wfull[s], 1);
-      mbar_init(&bar_wempty[s], 1);
+      mbar_init(&bar_wempty[s], Cfg::NMW);
     }
     mbar_init(&bar_band_full[0], PW / 32);
     mbar_init(&bar_band_full[1], PW / 32);
-    mbar_init(&bar_unit_done[0], 1);
-    mbar_init(&bar_unit_done[1], 1);
+    mbar_init(&bar_unit_done[0], Cfg::NMW);
+    mbar_init(&bar_unit_done[1], Cfg::NMW);
     fence_barrier_init();
   }
   if (warp == 0) tmem_alloc<Cfg::TMEM_COLS>(&tmem_base_s);
@@ -159,7 +173,7 @@ __global__ void __launch_bounds__(P3Cfg<KTOT, NOUT, POOL, BWD, HS, PLAIN, WMAX>:
     nM = (rows * Wp + 127) >> 7;
   };
 
-  if (warp == PW / 32 + 1) {
+  if (warp == PW / 32 + Cfg::NMW) {
     // ================= weight warp: TMA ring =================
     int s_glob = 0;
     for (int tile = blockIdx.x; tile < a.n_tiles; tile += gridDim.x) {
@@ -174,11 +188,12 @@ __global__ void __launch_bounds__(P3Cfg<KTOT, NOUT, POOL, BWD, HS, PLAIN, WMAX>:
         __syncwarp();
       }
     }
-  } else if (warp == PW / 32) {
-    // ================= MMA warp =================
+  } else if (warp >= PW / 32) {
+    // ================= MMA warp(s) =================
     const bool leader = elect_one();
+    const int mw = warp - PW / 32;  // this warp issues M-tiles mw, mw + NMW, ...
     int u_glob = 0, s_glob = 0, it = 0;
-    const bool mprof = a.prof != nullptr && blockIdx.x == 0 && leader;
+    const bool mprof = a.prof != nullptr && blockIdx.x == 0 && leader && mw == 0;
     long long mc[3] = {0, 0, 0}, m_last = clock64();
 #define P3MPROF(k)                    \
   if (mprof) {                        \
@@ -219,10 +234,16 @@ __global__ void __launch_bounds__(P3Cfg<KTOT, NOUT, POOL, BWD, HS, PLAIN, WMAX>:
             const uint64_t ah = desc_sw128(a_hi_addr + row_off + ks * 32), al = desc_sw128(a_lo_addr + row_off + ks * 32);
             const uint32_t acc0 = (kc > 0 || tap > 0 || ks > 0) ? 1u : 0u;
 #pragma unroll
-            for (int m = 0; m < NM3; ++m) {
+            for (int m0 = 0; m0 < NM3; m0 += Cfg::NMW) {
+              const int m = m0 + mw;
               if (m < nM && leader) {
                 const uint32_t dcol = dbase + m * Cfg::NSTRIDE;
                 const uint64_t moff = (uint64_t)(m * ((128 * 128) >> 4));
+                if (Cfg::WIDE && a.passes == 3) {
+                  mma_tf32(dcol, ah + moff, bh, IDESC_WIDE, acc0);  // columns [0, N): a_hi w_hi, [N, 2N): a_hi w_lo
+                  mma_tf32(dcol, al + moff, bh, IDESC, 1u);         // columns [0, N) += a_lo w_hi
+                  continue;
+                }
                 mma_tf32(dcol, ah + moff, bh, IDESC, acc0);
                 if (a.passes == 3) {
                   mma_tf32(dcol, ah + moff, bl, IDESC, 1u);
@@ -410,7 +431,15 @@ __global__ void __launch_bounds__(P3Cfg<KTOT, NOUT, POOL, BWD, HS, PLAIN, WMAX>:
             for (int c0 = 0; c0 < NOUT; c0 += 16) {
               uint32_t v[16];
               tmem_ld16_issue(taddr + c0, v);
-              tmem_ld_wait();
+              if (Cfg::WIDE && a.passes == 3) {  // second accumulator half: the a_hi w_lo cross term
+                uint32_t v2[16];
+                tmem_ld16_issue(taddr + NMMA + c0, v2);
+                tmem_ld_wait();
+#pragma unroll
+                for (int j = 0; j < 16; ++j) v[j] = __float_as_uint(__uint_as_float(v[j]) + __uint_as_float(v2[j]));
+              } else {
+                tmem_ld_wait();
+              }
 #pragma unroll
               for (int j = 0; j < 16; j += 4) {
                 const float4 b4 = *reinterpret_cast<const float4*>(s_bias + c0 + j);
@@ -482,30 +511,50 @@ __global__ void __launch_bounds__(P3Cfg<KTOT, NOUT, POOL, BWD, HS, PLAIN, WMAX>:
       } else if (PLAIN) {
         const int Hop = a.Ho + 2 * a.out_pad, Wop = a.Wo + 2 * a.out_pad;
         const int items = rows * a.Wo * C4;
-        for (int i = tid; i < items; i += PW) {
-          const int ic = i / C4, c4i = i - C4 * ic, yl = fdiv(ic, a.dWo), x = ic - yl * a.Wo;
-          const int c = 4 * c4i, oy = y0 + yl;
-          const int och = a.out_ch > 0 ? a.out_ch : NOUT;  // NOUT may be padded beyond the stored channels (24 -> 32)
-          if (c >= och) continue;
-          float4 v = *reinterpret_cast<const float4*>(stage + (size_t)(yl * Wp + x + 1) * SS + c);
-          if (a.aff_scale != nullptr) {  // BatchNorm(eval) + LeakyReLU of the reference's conv1 -> bn2 -> lrelu
-            const float4 sc4 = __ldg(reinterpret_cast<const float4*>(a.aff_scale + c));
-            const float4 sh4 = __ldg(reinterpret_cast<const float4*>(a.aff_shift + c));
-            v.x = fmaf(v.x, sc4.x, sh4.x), v.y = fmaf(v.y, sc4.y, sh4.y), v.z = fmaf(v.z, sc4.z, sh4.z), v.w = fmaf(v.w, sc4.w, sh4.w);
-            v.x = v.x > 0.f ? v.x : a.act_slope * v.x;
-            v.y = v.y > 0.f ? v.y : a.act_slope * v.y;
-            v.z = v.z > 0.f ? v.z : a.act_slope * v.z;
-            v.w = v.w > 0.f ? v.w : a.act_slope * v.w;
+        const int och = a.out_ch > 0 ? a.out_ch : NOUT;  // NOUT may be padded beyond the stored channels (24 -> 32)
+        float* out_tile = a.out + (((size_t)b * Hop + y0 + a.out_pad) * Wop + a.out_pad) * och;
+        const bool has_mul = a.mul_h != nullptr;
+        const float* mul_tile = has_mul ? a.mul_h + (((size_t)b * Hp + y0 + 1) * Wp + 1) * och : nullptr;
+        // EU items per thread and pass, the gating tensor's loads of all of them issued before the first is used: one item at a time,
+        // each (dependent, DRAM-latency) load of mul_h stood alone and this loop was 5.4 k of the transposed convolution's 10.9 k
+        // cycles per tile in SpecRNet's first block (ADVB_P3_PROF)
+        constexpr int EU = 3;
+        for (int i0 = tid; i0 < items; i0 += EU * PW) {
+          float4 hv[EU];
+          int sidx[EU], oidx[EU], cc[EU];
+#pragma unroll
+          for (int u = 0; u < EU; ++u) {
+            const int i = i0 + u * PW;
+            const int ic = i / C4, c = 4 * (i - C4 * ic), yl = fdiv(ic, a.dWo), x = ic - yl * a.Wo;
+            cc[u] = (i < items && c < och) ? c : -1;
+            sidx[u] = (yl * Wp + x + 1) * SS + c;
+            oidx[u] = (yl * Wop + x) * och + c;
+            hv[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (has_mul && cc[u] >= 0) hv[u] = __ldg(reinterpret_cast<const float4*>(mul_tile + (yl * Wp + x) * och + c));
           }
-          if (a.mul_h != nullptr) {  // * LeakyReLU'(h) * per-channel scale: the transposed convolution's chain-rule factor
-            const float4 hv = __ldg(reinterpret_cast<const float4*>(a.mul_h + (((size_t)b * Hp + oy + 1) * Wp + x + 1) * och + c));
-            const float4 sv = __ldg(reinterpret_cast<const float4*>(a.mul_scale + c));
-            v.x = v.x * (hv.x > 0.f ? 1.0f : a.mul_slope) * sv.x;
-            v.y = v.y * (hv.y > 0.f ? 1.0f : a.mul_slope) * sv.y;
-            v.z = v.z * (hv.z > 0.f ? 1.0f : a.mul_slope) * sv.z;
-            v.w = v.w * (hv.w > 0.f ? 1.0f : a.mul_slope) * sv.w;
+#pragma unroll
+          for (int u = 0; u < EU; ++u) {
+            const int c = cc[u];
+            if (c < 0) continue;
+            float4 v = *reinterpret_cast<const float4*>(stage + sidx[u]);
+            if (a.aff_scale != nullptr) {  // BatchNorm(eval) + LeakyReLU of the reference's conv1 -> bn2 -> lrelu
+              const float4 sc4 = __ldg(reinterpret_cast<const float4*>(a.aff_scale + c));
+              const float4 sh4 = __ldg(reinterpret_cast<const float4*>(a.aff_shift + c));
+              v.x = fmaf(v.x, sc4.x, sh4.x), v.y = fmaf(v.y, sc4.y, sh4.y), v.z = fmaf(v.z, sc4.z, sh4.z), v.w = fmaf(v.w, sc4.w, sh4.w);
+              v.x = v.x > 0.f ? v.x : a.act_slope * v.x;
+              v.y = v.y > 0.f ? v.y : a.act_slope * v.y;
+              v.z = v.z > 0.f ? v.z : a.act_slope * v.z;
+              v.w = v.w > 0.f ? v.w : a.act_slope * v.w;
+            }
+            if (has_mul) {  // * LeakyReLU'(h) * per-channel scale: the transposed convolution's chain-rule factor
+              const float4 sv = __ldg(reinterpret_cast<const float4*>(a.mul_scale + c));
+              v.x = v.x * (hv[u].x > 0.f ? 1.0f : a.mul_slope) * sv.x;
+              v.y = v.y * (hv[u].y > 0.f ? 1.0f : a.mul_slope) * sv.y;
+              v.z = v.z * (hv[u].z > 0.f ? 1.0f : a.mul_slope) * sv.z;
+              v.w = v.w * (hv[u].w > 0.f ? 1.0f : a.mul_slope) * sv.w;
+            }
+            *reinterpret_cast<float4*>(out_tile + oidx[u]) = v;
           }
-          *reinterpret_cast<float4*>(a.out + (((size_t)b * Hop + oy + a.out_pad) * Wop + x + a.out_pad) * och + c) = v;
         }
       } else {
         const int Hop = a.Ho + 2 * a.out_pad, Wop = a.Wo + 2 * a.out_pad;

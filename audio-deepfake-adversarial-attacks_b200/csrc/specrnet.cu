@@ -701,6 +701,29 @@ __global__ void sr_gru_pack_kernel(SrGru g) {
 
 __device__ __forceinline__ float sigmoid_f(float v) { return 1.0f / (1.0f + expf(-v)); }
 
+// acc += sum_k w[k * stride] * v[k] (v in shared memory), one sequential fmaf chain in k like the plain loop (same bits), but with
+// the NEXT 16 weights already in flight while 16 are consumed: the plain loop kept 2-4 loads ahead of their use and the kernels sat
+// on the L2 latency of these weight reads (two layers x two directions exceed L1).
+template <int N>
+__device__ __forceinline__ float dot_prefetched(const float* __restrict__ w, int stride, const float* v, float acc) {
+  static_assert(N % 16 == 0, "chunks of 16");
+  float cur[16], nxt[16];
+#pragma unroll
+  for (int u = 0; u < 16; ++u) cur[u] = __ldg(w + (size_t)u * stride);
+#pragma unroll 1
+  for (int k0 = 0; k0 < N; k0 += 16) {
+    if (k0 + 16 < N) {
+#pragma unroll
+      for (int u = 0; u < 16; ++u) nxt[u] = __ldg(w + (size_t)(k0 + 16 + u) * stride);
+    }
+#pragma unroll
+    for (int u = 0; u < 16; ++u) acc = fmaf(cur[u], v[k0 + u], acc);
+#pragma unroll
+    for (int u = 0; u < 16; ++u) cur[u] = nxt[u];
+  }
+  return acc;
+}
+
 // One CTA per clip, 384 threads = 2 directions x 192 gate rows.
 __global__ void __launch_bounds__(384) sr_gru_fwd_kernel(SrGru g, const float* __restrict__ xn, float* __restrict__ logits,
                                                           int L) {
@@ -727,8 +750,8 @@ __global__ void __launch_bounds__(384) sr_gru_fwd_kernel(SrGru g, const float* _
     for (int s = 0; s < L; ++s) {
       const int t = d == 0 ? s : L - 1 - s;
       float gi = bi, gh = bh;
-      for (int k = 0; k < K; ++k) gi = fmaf(__ldg(wih + k * G3 + j), s_in[t][k], gi);
-      for (int k = 0; k < GH; ++k) gh = fmaf(__ldg(whh + k * G3 + j), s_h[d][k], gh);
+      gi = l == 0 ? dot_prefetched<64>(wih + j, G3, s_in[t], gi) : dot_prefetched<128>(wih + j, G3, s_in[t], gi);
+      gh = dot_prefetched<GH>(whh + j, G3, s_h[d], gh);
       s_gi[d][j] = gi;
       s_gh[d][j] = gh;
       __syncthreads();
@@ -814,14 +837,9 @@ __global__ void __launch_bounds__(256) sr_gru_bwd_kernel(SrGru g, const float* _
         s_dh[d][i] = dh * z;  // direct path; the W_hh^T term is added below
       }
       __syncthreads();
-      if (i < K) {
-        float acc = 0.f;
-        for (int j = 0; j < G3; ++j) acc = fmaf(__ldg(wih + j * K + i), s_ggi[d][j], acc);
-        s_gin[d][t][i] = acc;
-      }
+      if (i < K) s_gin[d][t][i] = dot_prefetched<G3>(wih + i, K, s_ggi[d], 0.f);
       float accH = 0.f;
-      if (i < GH)
-        for (int j = 0; j < G3; ++j) accH = fmaf(__ldg(whh + j * GH + i), s_ggh[d][j], accH);
+      if (i < GH) accH = dot_prefetched<G3>(whh + i, GH, s_ggh[d], 0.f);
       __syncthreads();
       if (i < GH) s_dh[d][i] += accH;
       __syncthreads();
