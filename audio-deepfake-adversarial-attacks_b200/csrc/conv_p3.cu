@@ -31,6 +31,9 @@ using namespace tc;
 //   backward : 1 M-tile and TWO band buffers, so the convert of unit u+1 overlaps the MMAs of unit u (3-4 chunks per
 //              tile and N = 32/48 operand-read-bound MMAs made the single-buffer version convert-then-multiply serial).
 
+#ifndef P3_NMW_ALL_FWD
+#define P3_NMW_ALL_FWD 1  // 1: every forward variant issues its two M-tiles from two warps (0: PLAIN only)
+#endif
 __host__ __device__ constexpr int p3_pow2(int v) {
   int p = 32;
   while (p < v) p <<= 1;
@@ -83,7 +86,7 @@ struct P3Cfg {
   // tools/tc_probe.cu section 5; ADVB_P3_PROF: 8.0 k cycles of issue per 2-M-tile unit of SpecRNet's first block with three OR two
   // MMAs per k-step), which at N <= 64 is longer than the MMAs take.  PLAIN: one issuing warp per M-tile - both wait on the same
   // full barriers and each commits to the empty / done barriers (arrival count NMW).
-  static constexpr int NMW = PLAIN ? NM3 : 1;
+  static constexpr int NMW = P3_NMW_ALL_FWD ? NM3 : (PLAIN ? NM3 : 1);
   static constexpr int PT = PW + 32 * (1 + NMW);
   static constexpr int NTAP = HS ? 3 : 9;
   static constexpr int NMMA = HS ? 3 * NOUT : NOUT;  // MMA N = accumulator columns per M-tile
@@ -518,7 +521,7 @@ __global__ void __launch_bounds__(P3Cfg<KTOT, NOUT, POOL, BWD, HS, PLAIN, WMAX>:
         // EU items per thread and pass, the gating tensor's loads of all of them issued before the first is used: one item at a time,
         // each (dependent, DRAM-latency) load of mul_h stood alone and this loop was 5.4 k of the transposed convolution's 10.9 k
         // cycles per tile in SpecRNet's first block (ADVB_P3_PROF)
-        constexpr int EU = 3;
+        constexpr int EU = PW > 256 ? 3 : 5;
         for (int i0 = tid; i0 < items; i0 += EU * PW) {
           float4 hv[EU];
           int sidx[EU], oidx[EU], cc[EU];

@@ -27,6 +27,7 @@
 
 #include "conv.cuh"
 #include "conv_core.cuh"
+#include "tc_common.cuh"
 
 namespace advb {
 
@@ -367,6 +368,7 @@ __global__ void __launch_bounds__(256) sr_first_bwd_kernel(SrArgs a, const float
   g_feat[((size_t)b * a.H + y) * a.W + x] = acc * selu_grad_from_out(x0) * sc;
 }
 
+constexpr int SR_C1_NMAX = 32;  // channels (padded) the first conv1 kernel stages per pixel
 // First block, conv1 (1 -> C channels) + bn2 + LeakyReLU as its own kernel (round 2): thread = (pixel, 4 output channels), nine
 // scalar loads of the 1-channel image (L1) and 36 FMAs; the generic F1 path staged bands and weight slabs for a contraction of
 // length 9 and ran at a quarter of the HBM rate of its 812 MB output.
@@ -374,39 +376,59 @@ __global__ void __launch_bounds__(256) sr_first_conv1_kernel(const float* __rest
                                                               const float* __restrict__ wpk /*[tap][1][N]*/,
                                                               const float* __restrict__ bias, const float* __restrict__ scale,
                                                               const float* __restrict__ shift, float* __restrict__ h, int H, int W,
-                                                              int N, int64_t n_px) {
+                                                              int N, int64_t n_px, tc::FastDiv dW, tc::FastDiv dH, tc::FastDiv dQ) {
   // thread = pixel: the nine image samples and the index arithmetic are shared by all N channels (one thread per 4 channels was
-  // instruction-bound: 68 % issue slots at 22 % of the DRAM rate); weights, bias and the BatchNorm affine sit in shared memory
-  __shared__ __align__(16) float s_w[9 * 64], s_b[64], s_sc[64], s_sh[64];
+  // instruction-bound: 68 % issue slots at 22 % of the DRAM rate); weights, bias and the BatchNorm affine sit in shared memory.
+  // The N outputs of a pixel are 4 N contiguous bytes, so a warp's float4 stores went out 96 bytes apart (24 cache lines per
+  // instruction); they are staged per warp (row stride N + 4 floats: conflict-free) and written pixel-major, 512 contiguous bytes
+  // per store instruction.
+  __shared__ __align__(16) float s_w[9 * SR_C1_NMAX], s_b[SR_C1_NMAX], s_sc[SR_C1_NMAX], s_sh[SR_C1_NMAX];
+  __shared__ __align__(16) float s_o[8][32 * (SR_C1_NMAX + 4)];
+  __shared__ unsigned s_off[8][32];
   for (int i = threadIdx.x; i < 9 * N; i += blockDim.x) s_w[i] = wpk[i];
   for (int i = threadIdx.x; i < N; i += blockDim.x) s_b[i] = bias[i], s_sc[i] = scale[i], s_sh[i] = shift[i];
   __syncthreads();
-  const int Wp = W + 2;
+  const int Wp = W + 2, RS = N + 4, Q = N >> 2;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  float* so = s_o[warp];
+  unsigned* soff = s_off[warp];
   const unsigned total = (unsigned)n_px, step = gridDim.x * blockDim.x;
-  for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += step) {
-    const int x = (int)(i % (unsigned)W);
-    const unsigned r = i / (unsigned)W;
-    const int y = (int)(r % (unsigned)H), b = (int)(r / (unsigned)H);
-    const float* ip = img + ((size_t)b * (H + 2) + y) * Wp + x;  // top-left of the 3x3 window in the bordered image
-    float v[9];
+  for (unsigned base = (blockIdx.x * 8 + warp) * 32; base < total; base += step) {
+    const unsigned i = base + lane;
+    unsigned off = 0xffffffffu;
+    if (i < total) {
+      const int r = tc::fdiv((int)i, dW), x = (int)i - r * W;
+      const int b = tc::fdiv(r, dH), y = r - b * H;
+      const float* ip = img + ((size_t)b * (H + 2) + y) * Wp + x;  // top-left of the 3x3 window in the bordered image
+      float v[9];
 #pragma unroll
-    for (int t = 0; t < 9; ++t) v[t] = __ldg(ip + (t / 3) * Wp + t % 3);
-    float* hp = h + (((size_t)b * (H + 2) + y + 1) * Wp + x + 1) * N;
-    for (int c = 0; c < N; c += 4) {
-      float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+      for (int t = 0; t < 9; ++t) v[t] = __ldg(ip + (t / 3) * Wp + t % 3);
+      off = (unsigned)((((size_t)b * (H + 2) + y + 1) * Wp + x + 1) * N);  // < 2^32: checked on the host
+      float* sp = so + lane * RS;
+      for (int c = 0; c < N; c += 4) {
+        float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
-      for (int t = 0; t < 9; ++t) {
-        const float4 w = *reinterpret_cast<const float4*>(s_w + t * N + c);
-        acc.x = fmaf(v[t], w.x, acc.x), acc.y = fmaf(v[t], w.y, acc.y), acc.z = fmaf(v[t], w.z, acc.z), acc.w = fmaf(v[t], w.w, acc.w);
+        for (int t = 0; t < 9; ++t) {
+          const float4 w = *reinterpret_cast<const float4*>(s_w + t * N + c);
+          acc.x = fmaf(v[t], w.x, acc.x), acc.y = fmaf(v[t], w.y, acc.y), acc.z = fmaf(v[t], w.z, acc.z), acc.w = fmaf(v[t], w.w, acc.w);
+        }
+        const float4 bi = *reinterpret_cast<const float4*>(s_b + c), sc = *reinterpret_cast<const float4*>(s_sc + c);
+        const float4 sh = *reinterpret_cast<const float4*>(s_sh + c);
+        float o[4] = {fmaf(acc.x + bi.x, sc.x, sh.x), fmaf(acc.y + bi.y, sc.y, sh.y), fmaf(acc.z + bi.z, sc.z, sh.z),
+                      fmaf(acc.w + bi.w, sc.w, sh.w)};
+#pragma unroll
+        for (int j = 0; j < 4; ++j) o[j] = o[j] > 0.f ? o[j] : 0.3f * o[j];
+        *reinterpret_cast<float4*>(sp + c) = make_float4(o[0], o[1], o[2], o[3]);
       }
-      const float4 bi = *reinterpret_cast<const float4*>(s_b + c), sc = *reinterpret_cast<const float4*>(s_sc + c);
-      const float4 sh = *reinterpret_cast<const float4*>(s_sh + c);
-      float o[4] = {fmaf(acc.x + bi.x, sc.x, sh.x), fmaf(acc.y + bi.y, sc.y, sh.y), fmaf(acc.z + bi.z, sc.z, sh.z),
-                    fmaf(acc.w + bi.w, sc.w, sh.w)};
-#pragma unroll
-      for (int j = 0; j < 4; ++j) o[j] = o[j] > 0.f ? o[j] : 0.3f * o[j];
-      *reinterpret_cast<float4*>(hp + c) = make_float4(o[0], o[1], o[2], o[3]);
     }
+    soff[lane] = off;
+    __syncwarp();
+    for (int f = lane; f < 32 * Q; f += 32) {
+      const int p = tc::fdiv(f, dQ), q = f - p * Q;
+      const unsigned po = soff[p];
+      if (po != 0xffffffffu) *reinterpret_cast<float4*>(h + po + 4 * q) = *reinterpret_cast<const float4*>(so + p * RS + 4 * q);
+    }
+    __syncwarp();
   }
 }
 
@@ -572,16 +594,19 @@ __global__ void __launch_bounds__(256) sr_attention_bwd_kernel(const float* __re
   }
 }
 
+// __umulhi(n, ceil(2^32 / d)) == n / d for every n with n * (d - 1) < 2^32
+inline bool fastdiv_exact(int64_t n_max, int d) { return d <= 1 || n_max * (int64_t)(d - 1) < (1LL << 32); }
+
 // The expanded gradient at conv2's output, materialised with a zero border for the tensor-core transposed convolution.
-__global__ void sr_expand_go_kernel(SrArgs a, float* __restrict__ go, int64_t n4) {
+__global__ void sr_expand_go_kernel(SrArgs a, float* __restrict__ go, int64_t n4, tc::FastDiv dC4, tc::FastDiv dWp, tc::FastDiv dHp) {
   const int C4 = a.C >> 2, Hp = a.H + 2, Wp = a.W + 2;
   const unsigned total = (unsigned)n4, step = gridDim.x * blockDim.x;  // 32-bit index arithmetic (n4 < 2^31, checked on the host)
   for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += step) {
-    const int c4 = (int)(i % (unsigned)C4);
-    unsigned r = i / (unsigned)C4;
-    const int xp = (int)(r % (unsigned)Wp);
-    r /= (unsigned)Wp;
-    const int yp = (int)(r % (unsigned)Hp), b = (int)(r / (unsigned)Hp);
+    // multiply-high divisions (exact for these ranges, checked on the host): the five runtime / and % were a third of the kernel's
+    // instructions at 67 % issue-slot use
+    const int r1 = tc::fdiv((int)i, dC4), c4 = (int)i - r1 * C4;
+    const int r2 = tc::fdiv(r1, dWp), xp = r1 - r2 * Wp;
+    const int b = tc::fdiv(r2, dHp), yp = r2 - b * Hp;
     float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
     if (yp >= 1 && yp <= a.H && xp >= 1 && xp <= a.W) v = expand_go(a, b, yp - 1, xp - 1, 4 * c4);
     reinterpret_cast<float4*>(go)[i] = v;
@@ -1018,7 +1043,10 @@ int sr_block_forward(const SrBlock& k, const float* x, int B, const char* tag, c
   if (k.Ci == 1 && k.tc2) {  // first block: 1-channel input, a 9-term contraction
     const int64_t n_px = (int64_t)B * k.H * k.W;
     ADVB_CHECK(k.C <= 64 && n_px < (1LL << 31), "SpecRNet first conv1: at most 64 channels, 2^31 pixels");
-    sr_first_conv1_kernel<<<ew_blocks(n_px), 256, 0, stream>>>(x, k.w1f, k.b1p, k.bn_scale, k.bn_shift, k.h, k.H, k.W, k.C, n_px);
+    ADVB_CHECK(k.C <= SR_C1_NMAX && k.C % 4 == 0 && (int64_t)B * (k.H + 2) * (k.W + 2) * k.C < (1LL << 32) && fastdiv_exact(n_px, k.W),
+               "SpecRNet first conv1: channel count / index range");
+    sr_first_conv1_kernel<<<ew_blocks(n_px), 256, 0, stream>>>(x, k.w1f, k.b1p, k.bn_scale, k.bn_shift, k.h, k.H, k.W, k.C, n_px,
+                                                               tc::make_fastdiv(k.W), tc::make_fastdiv(k.H), tc::make_fastdiv(k.C / 4));
     ADVB_KERNEL_OK(t.conv1, stream);
   } else if (k.tc1) {  // conv1 -> bn2 -> LeakyReLU on the tensor cores (affine + activation in the epilogue)
     P3Plain p;
@@ -1061,7 +1089,9 @@ int sr_block_backward(const SrBlock& k, const float* x, float* g_x, int B, bool 
   if (k.tc2) {  // g_o materialised once (zero border), conv2^T on the tensor cores with the LeakyReLU' * bn2-scale factor in its epilogue
     const int64_t n4 = (int64_t)B * (k.H + 2) * (k.W + 2) * (k.C / 4);
     ADVB_CHECK(n4 < (1LL << 31), "SpecRNet: batch too large for the 32-bit element index of the expanded gradient");
-    sr_expand_go_kernel<<<ew_blocks(n4), 256, 0, stream>>>(a, k.go, n4);
+    ADVB_CHECK(fastdiv_exact(n4, k.C / 4) && fastdiv_exact(n4 / (k.C / 4), k.W + 2), "SpecRNet: index range of the multiply-high division");
+    sr_expand_go_kernel<<<ew_blocks(n4), 256, 0, stream>>>(a, k.go, n4, tc::make_fastdiv(k.C / 4), tc::make_fastdiv(k.W + 2),
+                                                           tc::make_fastdiv(k.H + 2));
     ADVB_KERNEL_OK(t.expand_go, stream);
     P3Plain p;
     p.in = k.go, p.wpack = k.tcd2, p.mul_h = k.h, p.mul_scale = k.bn_scale, p.mul_slope = 0.3f;
