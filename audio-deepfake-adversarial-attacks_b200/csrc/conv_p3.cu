@@ -113,7 +113,10 @@ struct P3Cfg {
   static constexpr bool DB = BWD && (227 * 1024 - 1024 - 2 * BUF_BYTES - STAGE_BYTES >= 2 * SLICE_BYTES);
   static constexpr int BAND_BYTES = (DB ? 2 : 1) * BUF_BYTES;
   static constexpr int ROOM = 227 * 1024 - 1024 - BAND_BYTES - STAGE_BYTES;
-  static constexpr int NST = ROOM / SLICE_BYTES >= 4 ? 4 : (ROOM / SLICE_BYTES >= 3 ? 3 : 2);
+  // RESIDENT: every weight slice fits beside the band and the staging tile (SpecRNet's first block: 9 x 8 KB) - loaded once per CTA
+  // instead of once per tile; the MMA warps waited ~1 k of 8.3 k cycles per tile for the ring's refills (ADVB_P3_PROF "wait_w")
+  static constexpr bool RESIDENT = ROOM / SLICE_BYTES >= NSLICE;
+  static constexpr int NST = RESIDENT ? NSLICE : (ROOM / SLICE_BYTES >= 4 ? 4 : (ROOM / SLICE_BYTES >= 3 ? 3 : 2));
   static constexpr size_t SMEM = (size_t)NST * SLICE_BYTES + BAND_BYTES + STAGE_BYTES + 1024;
   static_assert(TMEM_COLS <= 512, "two accumulator sets must fit the 512 TMEM columns");
   static_assert(ROOM / SLICE_BYTES >= 2, "weight ring does not fit");
@@ -179,7 +182,15 @@ __global__ void __launch_bounds__(P3Cfg<KTOT, NOUT, POOL, BWD, HS, PLAIN, WMAX>:
   if (warp == PW / 32 + Cfg::NMW) {
     // ================= weight warp: TMA ring =================
     int s_glob = 0;
-    for (int tile = blockIdx.x; tile < a.n_tiles; tile += gridDim.x) {
+    if (Cfg::RESIDENT) {
+      if (blockIdx.x < a.n_tiles && lane == 0)
+        for (int sl = 0; sl < NSLICE; ++sl) {
+          mbar_expect_tx(&bar_wfull[sl], Cfg::SLICE_BYTES);
+          bulk_g2s(wring + (size_t)sl * Cfg::SLICE_BYTES, a.wpack + (size_t)sl * Cfg::SLICE_BYTES, Cfg::SLICE_BYTES, &bar_wfull[sl]);
+        }
+      __syncwarp();
+    }
+    for (int tile = blockIdx.x; !Cfg::RESIDENT && tile < a.n_tiles; tile += gridDim.x) {
       for (int sl = 0; sl < NSLICE; ++sl, ++s_glob) {
         const int slot = s_glob % NST, use = s_glob / NST;
         if (use > 0) mbar_wait(&bar_wempty[slot], (uint32_t)((use - 1) & 1));
@@ -219,9 +230,9 @@ __global__ void __launch_bounds__(P3Cfg<KTOT, NOUT, POOL, BWD, HS, PLAIN, WMAX>:
         const int kvalid = (KTOT - 32 * kc) >= 32 ? 32 : (KTOT - 32 * kc);
 #pragma unroll 1
         for (int tap = 0; tap < NTAP; ++tap, ++s_glob) {
-          const int slot = s_glob % NST;
+          const int slot = Cfg::RESIDENT ? kc * NTAP + tap : s_glob % NST;
           P3MPROF(2)
-          mbar_wait(&bar_wfull[slot], (uint32_t)((s_glob / NST) & 1));
+          mbar_wait(&bar_wfull[slot], Cfg::RESIDENT ? 0u : (uint32_t)((s_glob / NST) & 1));  // resident: phase 0 completes once
           tc_fence_after();
           P3MPROF(1)
           const uint32_t w_hi = smem_u32(wring + (size_t)slot * Cfg::SLICE_BYTES), w_lo = w_hi + NMMA * 128;
@@ -257,7 +268,7 @@ __global__ void __launch_bounds__(P3Cfg<KTOT, NOUT, POOL, BWD, HS, PLAIN, WMAX>:
               }
             }
           }
-          if (leader) mma_commit(&bar_wempty[slot]);  // slot free once these MMAs have read it
+          if (leader && !Cfg::RESIDENT) mma_commit(&bar_wempty[slot]);  // slot free once these MMAs have read it
           __syncwarp();
         }
         if (leader) mma_commit(&bar_unit_done[DB ? (u_glob & 1) : 0]);  // band buffer free; last chunk: accumulator complete
