@@ -420,6 +420,14 @@ __global__ void __launch_bounds__(P3Cfg<KTOT, NOUT, POOL, BWD, HS, PLAIN, WMAX>:
       int b, y0, rows, nM;
       tile_geom(tile, b, y0, rows, nM);
       P3PROF(4)
+      if (PLAIN && a.mul_h != nullptr) {
+        // the gating tensor's lines of this tile into L2 / L1 now: the TMEM -> stage phase below (~2 k cycles) hides their DRAM
+        // latency, which the store loop otherwise pays once per pass
+        const int och = a.out_ch > 0 ? a.out_ch : NOUT;
+        const float* mul_tile = a.mul_h + (((size_t)b * Hp + y0 + 1) * Wp + 1) * och;
+        const int lines = (rows * Wp * och + 31) >> 5;  // 128-byte lines of the rows' contiguous span (borders included)
+        for (int i = tid; i < lines; i += PW) asm volatile("prefetch.global.L2 [%0];" ::"l"(mul_tile + (size_t)i * 32));
+      }
       asm volatile("bar.sync 1, %0;" ::"n"(PW) : "memory");  // previous staging tile fully consumed
       P3PROF(6)
       {
