@@ -2,7 +2,7 @@
 the maximum of the WHOLE batch (F5), so a clip-sharded run equals the single-device run only when the ranks share that maximum
 and the summed gradient of the clamped elements.  The exchange is a 32-thread kernel storing into the peers' mailboxes.
 
-* in process: two engine handles ("ranks") on one device, on two streams, connected by device pointers;
+* in process: two / four engine handles ("ranks") on one device, one stream each, connected by device pointers;
 * two processes under torchrun (CUDA IPC mapping; one GPU each when the box has two, else both on cuda:0): tools/strict_equiv.py.
 
 Model: SpecRNet + MFCC (floor always active: mel filter 0 is identically zero); the second half of the batch is 6 dB quieter.
@@ -36,36 +36,37 @@ def _check(line):
     assert p["grad_rel_err"] > 100 * s["grad_rel_err"], line
 
 
-def test_strict_floor_two_handles_in_process(cuda_device, record_property):
+@pytest.mark.parametrize("world", [2, 4])
+def test_strict_floor_handles_in_process(world, cuda_device, record_property):
+    """`world` engine handles ("ranks") on one device, one stream each, coupled through their mailboxes' device pointers."""
     sys.path.insert(0, os.path.join(ROOT, "tools"))
     import strict_equiv as se
     from advb200 import engine
 
-    case, x, y, holder, state = se.batch()
-    n, half = x.shape[0], x.shape[0] // 2
-    holders = [helpers.load_holder_state(copy.deepcopy(holder), state, cuda_device) for _ in range(3)]
+    case, x, y, holder, state = se.batch(world)
+    n, half = x.shape[0], x.shape[0] // world
+    holders = [helpers.load_holder_state(copy.deepcopy(holder), state, cuda_device) for _ in range(world + 1)]
     torch.manual_seed(77)
     noise = torch.empty_like(x).uniform_(-0.001, 0.001).to(cuda_device)
     xd, yd = x.to(cuda_device), y.to(cuda_device)
     full = se.run_all(engine.engine_for(holders[0], n, x.shape[1]), holders[0], xd, yd, noise, n)
     engs = [engine.engine_for(h, half, x.shape[1]) for h in holders[1:]]
-    spans = [(0, half), (half, n)]
+    spans = [(r * half, (r + 1) * half) for r in range(world)]
     # per-shard floors first: this also makes every lazy allocation and graph capture happen before the handles are coupled
     plain = [se.run_all(e, h, xd[lo:hi], yd[lo:hi], noise[lo:hi], n) for e, h, (lo, hi) in zip(engs, holders[1:], spans)]
     ptrs = [e.xrank_export()[1] for e in engs]
     for r, e in enumerate(engs):
-        e.xrank_connect(r, 2, local_ptrs=ptrs)
+        e.xrank_connect(r, world, local_ptrs=ptrs)
     # the two "ranks" run on two streams: every call only enqueues, the exchange kernels of one handle wait for the other's
     streams = [torch.cuda.Stream(cuda_device) for _ in engs]
     for s in streams:
         s.wait_stream(torch.cuda.current_stream(cuda_device))
-    strict = [None, None]
     from advb200 import torchattacks as ta
 
     atks = [ta.PGD(h, eps=0.001, alpha=2 / 255, steps=se.STEPS, random_start=True) for h in holders[1:]]
     for a in atks:
         a.set_training_mode(model_training=True, batchnorm_training=False)
-    res = [dict(), dict()]
+    res = [dict() for _ in engs]
     for stage in ("grad", "pgd", "fwd"):  # same call sequence on both handles, interleaved like two ranks in lock step
         for r, (e, (lo, hi)) in enumerate(zip(engs, spans)):
             with torch.cuda.stream(streams[r]):
@@ -89,7 +90,7 @@ def test_strict_floor_two_handles_in_process(cuda_device, record_property):
     print("strict in-process:", json.dumps(line))
     _check(line)
     # FAB / CW cannot keep the ranks' call sequences equal: refused under strict mode
-    engs[0].xrank_connect(0, 2, local_ptrs=ptrs)
+    engs[0].xrank_connect(0, world, local_ptrs=ptrs)
     with pytest.raises(RuntimeError, match="strict"):
         ta.CW(holders[1], c=1e-4, kappa=0, steps=2, lr=0.01)(xd[:half], yd[:half])
     engs[0].xrank_connect(0, 1)

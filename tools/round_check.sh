@@ -19,6 +19,9 @@ if [ "${NCU_FULL:-0}" = 1 ]; then  # one --set full capture of the second gradie
   ncu --set full --clock-control none --import-source on \
       -k regex:"fe_bwd_kernel|fe_dct_t_kernel|fe_floor_dct_kernel|fe_power_db_kernel|conv0_bwd_cells_kernel|conv_p3_kernel|conv0_toeplitz_kernel|conv_light_kernel" -s 21 -c 21 \
       -f -o $out/full python tools/profile_grad.py --calls 2 > $out/ncu_full.log 2>&1
+  # SpecRNet's tensor-core convolutions (first forward + backward of one gradient evaluation)
+  ncu --set full --clock-control none --import-source on -k regex:"conv_p3_kernel|sr_first_conv1|sr_expand_go|sr_first_bwd" -c 14 \
+      -f -o $out/full_specrnet python tools/profile_grad.py --model specrnet --batch 256 --calls 1 > $out/ncu_full_specrnet.log 2>&1
 fi
 grep -E "passed|failed" $out/pytest_gpu.log | tail -2; tail -1 $out/smoke.log
 for f in lcnn reference specrnet rawnet3 rawnet3_fab lcnn_advtrain; do tail -1 $out/bench_$f.log | cut -c1-200; done

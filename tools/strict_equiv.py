@@ -29,12 +29,13 @@ CASE = "specrnet_mfcc_t16000"
 STEPS = 4
 
 
-def batch():
-    """The golden case's clips, then the same clips 6 dB quieter (different batch maxima in the two halves)."""
+def batch(groups=2):
+    """The golden case's clips, then the same clips 6 dB quieter, 12 dB quieter, ... (one group per rank: every shard has its own
+    batch maximum)."""
     import helpers
 
     case, x, y, holder, state, _ = helpers.case_setup(CASE)
-    return case, torch.cat([x, 0.5 * x]), torch.cat([y, y]), holder, state
+    return case, torch.cat([x * 0.5 ** g for g in range(groups)]), torch.cat([y] * groups), holder, state
 
 
 def run_all(eng, holder, xs, ys, noise, n_global):
@@ -73,7 +74,7 @@ def main():
     import helpers
     from advb200 import engine, shard
 
-    case, x, y, holder, state = batch()
+    case, x, y, holder, state = batch(max(2, world))
     n = x.shape[0]
     holder = helpers.load_holder_state(holder, state, dev)
     eng = engine.engine_for(holder, n, x.shape[1])
