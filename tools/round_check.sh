@@ -19,9 +19,12 @@ if [ "${NCU_FULL:-0}" = 1 ]; then  # one --set full capture of the second gradie
   ncu --set full --clock-control none --import-source on \
       -k regex:"fe_bwd_kernel|fe_dct_t_kernel|fe_floor_dct_kernel|fe_power_db_kernel|conv0_bwd_cells_kernel|conv_p3_kernel|conv0_toeplitz_kernel|conv_light_kernel" -s 21 -c 21 \
       -f -o $out/full python tools/profile_grad.py --calls 2 > $out/ncu_full.log 2>&1
+  # gpurun brings back at most 64 MiB: export the raw page here and drop the report (two reports do not fit)
+  ncu -i $out/full.ncu-rep --page raw --csv > $out/full_raw.csv 2>/dev/null; rm -f $out/full.ncu-rep
   # SpecRNet's tensor-core convolutions (first forward + backward of one gradient evaluation)
   ncu --set full --clock-control none --import-source on -k regex:"conv_p3_kernel|sr_first_conv1|sr_expand_go|sr_first_bwd" -c 14 \
       -f -o $out/full_specrnet python tools/profile_grad.py --model specrnet --batch 256 --calls 1 > $out/ncu_full_specrnet.log 2>&1
+  ncu -i $out/full_specrnet.ncu-rep --page raw --csv > $out/full_specrnet_raw.csv 2>/dev/null; rm -f $out/full_specrnet.ncu-rep
 fi
 grep -E "passed|failed" $out/pytest_gpu.log | tail -2; tail -1 $out/smoke.log
 for f in lcnn reference specrnet rawnet3 rawnet3_fab lcnn_advtrain; do tail -1 $out/bench_$f.log | cut -c1-200; done
