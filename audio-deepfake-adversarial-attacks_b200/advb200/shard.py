@@ -44,6 +44,27 @@ def gather_rows(t: torch.Tensor, n_total: int, group=None) -> torch.Tensor:
     return torch.cat([p[:n] for p, n in zip(parts, sizes)], dim=0)
 
 
+def gather_evaluation(logits: torch.Tensor, labels: torch.Tensor, n_total: int, group=None) -> dict:
+    """End of a sharded evaluation (evaluate_models_on_adversarial_attacks.py:236-298): every rank contributes the logits of its
+    (attacked) clips and their labels; ONE all_gather of (score, label) rows (NCCL on GPUs), then the reference's host arithmetic on
+    the gathered rows - labels ``(sigmoid(o) + .5).int()`` (:238), accuracy in percent (:262-265), EER of ``calculate_eer(1 - y,
+    sigmoid(o))`` (:282-288, src/metrics.py:9-14).  Every rank returns the same dict, equal to the unsharded evaluation."""
+    import numpy as np
+    from scipy.interpolate import interp1d
+    from scipy.optimize import brentq
+    from sklearn.metrics import roc_curve
+
+    rows = torch.stack([torch.sigmoid(logits.flatten().float()), labels.flatten().to(logits.device).float()], dim=1)
+    rows = gather_rows(rows, n_total, group).cpu()
+    score, y = rows[:, 0].numpy(), rows[:, 1].numpy().astype(np.int64)
+    pred = (rows[:, 0] + 0.5).int().numpy()
+    out = {"clips": int(y.shape[0]), "accuracy": float((pred == y).mean() * 100.0), "eer": None}
+    if 0 < y.sum() < y.shape[0]:  # roc_curve needs both classes
+        fpr, tpr, _ = roc_curve(1 - y, -score)
+        out["eer"] = float(brentq(lambda v: 1.0 - v - interp1d(fpr, tpr)(v), 0.0, 1.0))
+    return out
+
+
 def max_over_ranks(value: float, device=None, group=None) -> float:
     """Slowest rank's value (multi-GPU timings are reported as the max over ranks)."""
     if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:

@@ -451,6 +451,11 @@ def run_native(args):
     logits_adv = eng.forward(adv).flatten()
     pred = torch.stack([(logits_clean > 0).long(), (logits_adv > 0).long(), y_dev], dim=1)
     pred = shard.gather_rows(pred, world * B).cpu()  # NCCL all_gather: the only collective of the job
+    # ... and the reference's end-of-evaluation numbers on the gathered (score, label) rows (evaluate...py:236-298): accuracy, EER
+    try:
+        evals = {"clean": shard.gather_evaluation(logits_clean, y_dev, world * B), "adv": shard.gather_evaluation(logits_adv, y_dev, world * B)}
+    except Exception as e:  # reporting only: never fail the measurement over it
+        evals = {"error": repr(e)}
     linf = (adv - x_dev).abs().max().item()
 
     # ---- the other BASELINE.json configurations, measured by the same driver run (short: 1 warm-up + 2 timed calls) ------
@@ -589,7 +594,7 @@ def run_native(args):
             "attack": {"linf": linf, "clean_acc": float((pred[:, 0] == pred[:, 2]).float().mean()),
                        "adv_acc": float((pred[:, 1] == pred[:, 2]).float().mean()),
                        "flipped": int((pred[:, 0] != pred[:, 1]).sum()), "clips": int(pred.shape[0]),
-                       "parity_vs_reference": parity},
+                       "parity_vs_reference": parity, "evaluation": evals},
             "other_workloads": others,
         }
         if wl["model"] == "rawnet3":

@@ -43,6 +43,20 @@ def _worker(rank, world, port, n_clips, out_dir):
         # accuracy from the gathered scores is identical on every rank and equals the unsharded value
         acc = ((got[:, 0] > 0).long() == got_y).float().mean().item()
         assert acc == ((logits[:, 0] > 0).long() == labels).float().mean().item()
+        # (score, label) gather + the reference's accuracy / EER arithmetic: same result on every rank as the unsharded evaluation
+        ev = shard.gather_evaluation(mine, shard.shard(labels, rank, world), n_clips)
+        ref_path = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "oracle", "_ref", "src", "metrics.py")
+        if os.path.exists(ref_path):  # the reference's own calculate_eer (src/metrics.py:9-14), staged by oracle/make_ref.py
+            import importlib.util
+
+            spec = importlib.util.spec_from_file_location("ref_metrics", ref_path)
+            ref_metrics = importlib.util.module_from_spec(spec)
+            spec.loader.exec_module(ref_metrics)
+            y_np, score_np = labels.numpy(), torch.sigmoid(logits[:, 0]).numpy()
+            _, eer_ref, _, _ = ref_metrics.calculate_eer(y=1 - y_np, y_score=score_np)
+            assert abs(ev["eer"] - eer_ref) < 1e-12
+        assert ev["clips"] == n_clips
+        assert abs(ev["accuracy"] - ((torch.sigmoid(logits[:, 0]) + 0.5).int() == labels).float().mean().item() * 100) < 1e-4
         slowest = shard.max_over_ranks(10.0 + rank)
         assert slowest == 10.0 + world - 1
         with open(os.path.join(out_dir, f"ok{rank}"), "w") as f:
