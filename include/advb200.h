@@ -130,7 +130,8 @@ ADVB_API int advb_set_option(advb_handle* h, const char* key, int value);
  *      differ).  world <= 1 disconnects.
  * From then on every rank must make the same sequence of forward / gradient / FGSM / PGD / PGDL2 calls (any batch size >= 1 per
  * rank; pass n_global_batch); FAB and CW return an error.  A peer that does not arrive within 5 s makes the exchange give up
- * (results of that call are then per-shard floors) and sets the flag advb_xrank_status reads (call it after a stream sync). */
+ * (results of that call are then per-shard floors) and sets the flag advb_xrank_status reads (call it after a stream sync).
+ * Disconnect (advb_xrank_connect with world <= 1) on every rank before any rank destroys its handle: peers store into its mailbox. */
 #define ADVB_XRANK_HANDLE_BYTES 64
 ADVB_API int advb_xrank_export(advb_handle* h, unsigned char* ipc_handle, void** local_ptr);
 ADVB_API int advb_xrank_connect(advb_handle* h, int rank, int world, const unsigned char* ipc_handles, void* const* local_ptrs);
