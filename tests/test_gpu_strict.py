@@ -96,10 +96,18 @@ def test_strict_floor_handles_in_process(world, cuda_device, record_property):
     engs[0].xrank_connect(0, 1)
 
 
+def _free_port():
+    import socket
+
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        return s.getsockname()[1]
+
+
 def test_strict_floor_two_processes(cuda_device, tmp_path, record_property):
     out = tmp_path / "strict_equiv.json"
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
-           "--master-port", "29517", os.path.join(ROOT, "tools", "strict_equiv.py"), "--out", str(out)]
+           "--master-port", str(_free_port()), os.path.join(ROOT, "tools", "strict_equiv.py"), "--out", str(out)]
     r = subprocess.run(cmd, capture_output=True, text=True, timeout=600, cwd=ROOT)
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-4000:]
     line = json.loads(out.read_text())
