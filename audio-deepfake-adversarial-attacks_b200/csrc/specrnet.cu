@@ -466,8 +466,10 @@ __global__ void __launch_bounds__(256) sr_first_bwd_tiled_kernel(SrArgs a, const
         const float4 gv = __ldg(reinterpret_cast<const float4*>(gp + c));
 #pragma unroll
         for (int t = 0; t < 9; ++t) {
-          const float* wp = s_w + t * C + c;
-          p[t] = fmaf(gv.w, wp[3], fmaf(gv.z, wp[2], fmaf(gv.y, wp[1], fmaf(gv.x, wp[0], p[t]))));
+          // one LDS.128 per tap (C is a multiple of 4 and s_w is 16-byte aligned; with a runtime C the compiler cannot know and
+          // emitted four scalar loads per tap: 216 LDS for 216 FFMA per slot)
+          const float4 w4 = *reinterpret_cast<const float4*>(s_w + t * C + c);
+          p[t] = fmaf(gv.w, w4.w, fmaf(gv.z, w4.z, fmaf(gv.y, w4.y, fmaf(gv.x, w4.x, p[t]))));
         }
       }
     }
@@ -485,7 +487,8 @@ __global__ void __launch_bounds__(256) sr_first_bwd_tiled_kernel(SrArgs a, const
     const float* gop = go + (((size_t)b * (a.H + 2) + y + 1) * Wp + x + 1) * C;
     for (int c = 0; c < C; c += 4) {
       const float4 g = __ldg(reinterpret_cast<const float4*>(gop + c));
-      acc = fmaf(g.w, s_d[c + 3], fmaf(g.z, s_d[c + 2], fmaf(g.y, s_d[c + 1], fmaf(g.x, s_d[c], acc))));
+      const float4 d4 = *reinterpret_cast<const float4*>(s_d + c);
+      acc = fmaf(g.w, d4.w, fmaf(g.z, d4.z, fmaf(g.y, d4.y, fmaf(g.x, d4.x, acc))));
     }
     const float x0 = __ldg(a.x + ((size_t)b * (a.H + 2) + y + 1) * Wp + x + 1);
     g_feat[((size_t)b * a.H + y) * a.W + x] = acc * selu_grad_from_out(x0) * sc;
@@ -615,18 +618,48 @@ __global__ void __launch_bounds__(256) sr_attention_bwd_kernel(const float* __re
 inline bool fastdiv_exact(int64_t n_max, int d) { return d <= 1 || n_max * (int64_t)(d - 1) < (1LL << 32); }
 
 // The expanded gradient at conv2's output, materialised with a zero border for the tensor-core transposed convolution.
-__global__ void sr_expand_go_kernel(SrArgs a, float* __restrict__ go, int64_t n4, tc::FastDiv dC4, tc::FastDiv dWp, tc::FastDiv dHp) {
-  const int C4 = a.C >> 2, Hp = a.H + 2, Wp = a.W + 2;
-  const unsigned total = (unsigned)n4, step = gridDim.x * blockDim.x;  // 32-bit index arithmetic (n4 < 2^31, checked on the host)
+// Thread = (clip, 2x2 pool cell, 4 channels): the four pixels of a cell share the code bytes, the attention term and the pooled
+// gradient (expand_go loads them per pixel), so one set of loads feeds four stores; the border is never written - the buffer is
+// zeroed when it is allocated and nothing else touches it.  Same expressions as expand_go: same bits.
+__global__ void sr_expand_go_kernel(SrArgs a, float* __restrict__ go, int64_t n_items, tc::FastDiv dC4, tc::FastDiv dQW, tc::FastDiv dQH) {
+  const int C4 = a.C >> 2, Hp = a.H + 2, Wp = a.W + 2, QH = (a.H + 1) >> 1, QW = (a.W + 1) >> 1;
+  const unsigned total = (unsigned)n_items, step = gridDim.x * blockDim.x;  // 32-bit index arithmetic (checked on the host)
   for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += step) {
-    // multiply-high divisions (exact for these ranges, checked on the host): the five runtime / and % were a third of the kernel's
-    // instructions at 67 % issue-slot use
-    const int r1 = tc::fdiv((int)i, dC4), c4 = (int)i - r1 * C4;
-    const int r2 = tc::fdiv(r1, dWp), xp = r1 - r2 * Wp;
-    const int b = tc::fdiv(r2, dHp), yp = r2 - b * Hp;
-    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (yp >= 1 && yp <= a.H && xp >= 1 && xp <= a.W) v = expand_go(a, b, yp - 1, xp - 1, 4 * c4);
-    reinterpret_cast<float4*>(go)[i] = v;
+    const int r1 = tc::fdiv((int)i, dC4), c = 4 * ((int)i - r1 * C4);
+    const int r2 = tc::fdiv(r1, dQW), cx = r1 - r2 * QW;
+    const int b = tc::fdiv(r2, dQH), cy = r2 - b * QH;
+    const bool live = cy < a.Hb && cx < a.Wb;
+    uchar4 c1 = make_uchar4(255, 255, 255, 255);
+    float4 g = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (live) {
+      const size_t o1 = (((size_t)b * a.Hb + cy) * a.Wb + cx) * a.C + c;
+      c1 = __ldg(reinterpret_cast<const uchar4*>(a.code1 + o1));
+      g = __ldg(reinterpret_cast<const float4*>(a.gadd + (size_t)b * a.C + c));
+      const int ny = cy >> 1, nx = cx >> 1;
+      if (ny < a.Hn && nx < a.Wn) {
+        const size_t o2 = (((size_t)b * a.Hn + ny) * a.Wn + nx) * a.C + c;
+        const uchar4 c2 = __ldg(reinterpret_cast<const uchar4*>(a.code2 + o2));
+        const float4 gn = __ldg(reinterpret_cast<const float4*>(a.g_xn + o2));
+        const float4 yv = __ldg(reinterpret_cast<const float4*>(a.y + (size_t)b * a.C + c));
+        const unsigned pos2 = (unsigned)(((cy & 1) << 1) | (cx & 1));
+        if (c2.x == pos2) g.x += gn.x * yv.x;
+        if (c2.y == pos2) g.y += gn.y * yv.y;
+        if (c2.z == pos2) g.z += gn.z * yv.z;
+        if (c2.w == pos2) g.w += gn.w * yv.w;
+      }
+    }
+#pragma unroll
+    for (int p = 0; p < 4; ++p) {
+      const int y = 2 * cy + (p >> 1), x = 2 * cx + (p & 1);
+      if (y >= a.H || x >= a.W) continue;
+      const unsigned pos1 = (unsigned)p;
+      float4 v;
+      v.x = c1.x == pos1 ? g.x : 0.f;
+      v.y = c1.y == pos1 ? g.y : 0.f;
+      v.z = c1.z == pos1 ? g.z : 0.f;
+      v.w = c1.w == pos1 ? g.w : 0.f;
+      *reinterpret_cast<float4*>(go + (((size_t)b * Hp + y + 1) * Wp + x + 1) * a.C + c) = v;
+    }
   }
 }
 
@@ -1104,11 +1137,13 @@ int sr_block_backward(const SrBlock& k, const float* x, float* g_x, int B, bool 
   SrArgs a = base_args(k, B);
   a.CK = k.C, a.CKr = std::min(k.C, (k.Cout + 3) / 4 * 4), a.N = k.C, a.wpk = k.w2d, a.out = k.g_c1;
   if (k.tc2) {  // g_o materialised once (zero border), conv2^T on the tensor cores with the LeakyReLU' * bn2-scale factor in its epilogue
-    const int64_t n4 = (int64_t)B * (k.H + 2) * (k.W + 2) * (k.C / 4);
-    ADVB_CHECK(n4 < (1LL << 31), "SpecRNet: batch too large for the 32-bit element index of the expanded gradient");
-    ADVB_CHECK(fastdiv_exact(n4, k.C / 4) && fastdiv_exact(n4 / (k.C / 4), k.W + 2), "SpecRNet: index range of the multiply-high division");
-    sr_expand_go_kernel<<<ew_blocks(n4), 256, 0, stream>>>(a, k.go, n4, tc::make_fastdiv(k.C / 4), tc::make_fastdiv(k.W + 2),
-                                                           tc::make_fastdiv(k.H + 2));
+    const int QH = (k.H + 1) / 2, QW = (k.W + 1) / 2;
+    const int64_t n4 = (int64_t)B * QH * QW * (k.C / 4);  // one thread per (2x2 pool cell, 4 channels)
+    ADVB_CHECK((int64_t)B * (k.H + 2) * (k.W + 2) * k.C < (1LL << 32) && n4 < (1LL << 31),
+               "SpecRNet: batch too large for the 32-bit element index of the expanded gradient");
+    ADVB_CHECK(fastdiv_exact(n4, k.C / 4) && fastdiv_exact(n4 / (k.C / 4), QW), "SpecRNet: index range of the multiply-high division");
+    sr_expand_go_kernel<<<ew_blocks(n4), 256, 0, stream>>>(a, k.go, n4, tc::make_fastdiv(k.C / 4), tc::make_fastdiv(QW),
+                                                           tc::make_fastdiv(QH));
     ADVB_KERNEL_OK(t.expand_go, stream);
     P3Plain p;
     p.in = k.go, p.wpack = k.tcd2, p.mul_h = k.h, p.mul_scale = k.bn_scale, p.mul_slope = 0.3f;
@@ -1120,6 +1155,7 @@ int sr_block_backward(const SrBlock& k, const float* x, float* g_x, int B, bool 
   }
   a.in = k.g_c1, a.x = x;
   if (first && k.tc2) {
+    ADVB_CHECK(k.C % 4 == 0, "SpecRNet first block: channel count padded to a multiple of 4");
     dim3 grid(cdiv(k.H, SR_FB_ROWS), B);
     const size_t smem = (size_t)(10 * k.C + (SR_FB_ROWS + 2) * (k.W + 2) * 9) * sizeof(float);
     sr_first_bwd_tiled_kernel<<<grid, 256, smem, stream>>>(a, k.w1, k.wds, k.Cout, bn4, k.go, g_x);
